@@ -1,0 +1,325 @@
+/*
+ * rtb.h — C ABI of librtb200.so, the B200 (sm_100a) implementation of RTBase's
+ * per-pixel path-tracing loop.
+ *
+ * The reference (NoSameRain/RayTracingRenderer, directory RTBase/) has no FFI: its seam is
+ * the C++ class surface used by RTBase/Main.cpp:67-71,114,124,135
+ *     Scene* loadScene(std::string)                       RTBase/SceneLoader.h:237
+ *     RayTracer::init / clear / render / getSPP / saveHDR RTBase/Renderer.h:45-67, 876-898
+ * Everything below `RayTracer::render()` (Renderer.h:876-885) runs on the device behind the
+ * functions declared here.  Plain pointers and sizes only; no C++ or torch types; no
+ * exceptions cross; every function returns an rtb_status (0 = OK, <0 = error) unless noted
+ * and the message of the last error is available from rtb_last_error().
+ *
+ * A context owns ONE device (one process per GPU is the deployment model; the film
+ * reduction across GPUs is done by the caller with NCCL on rtb_film_device_ptr()).
+ * A context is not thread-safe.
+ */
+#ifndef RTB_H_
+#define RTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_ABI_VERSION 1
+
+typedef struct rtb_ctx rtb_ctx;
+
+typedef enum rtb_status {
+	RTB_OK = 0,
+	RTB_ERR_ARG = -1,   /* null pointer, bad enum, size mismatch                     */
+	RTB_ERR_CUDA = -2,  /* a CUDA runtime call or kernel failed                        */
+	RTB_ERR_STATE = -3, /* call order: e.g. render before upload_scene                */
+	RTB_ERR_OOM = -4,   /* host or device allocation failed                           */
+	RTB_ERR_NODEV = -5  /* no CUDA device / device index out of range                 */
+} rtb_status;
+
+/* ------------------------------------------------------------------------------------
+ * Scene description (POD mirror of RTBase/Scene.h:72-81 `Scene`).  All arrays are copied
+ * by rtb_upload_scene; the caller keeps ownership.  float = IEEE binary32, little endian.
+ * ---------------------------------------------------------------------------------- */
+
+/* Camera (RTBase/Scene.h:10-54).  Matrices row-major like RTBase/Core.h:205-212.       */
+typedef struct rtb_camera {
+	float inv_proj[16];     /* Camera::inverseProjectionMatrix                       */
+	float cam_to_world[16]; /* Camera::camera                                        */
+	float origin[3];        /* Camera::origin                                        */
+	float width, height;    /* Camera::width/height (floats, as in the reference)    */
+	float pad_[3];
+} rtb_camera; /* 160 B */
+
+/* One node of the reference BVH (RTBase/Geometry.h:294-313 `BVHNode`), flattened in
+ * pre-order (left subtree directly follows its parent).  The device needs the reference's
+ * own tree for EXACT traversal and its leaves (<= MAXNODE_TRIANGLES = 2 triangles,
+ * Geometry.h:240,337) as the primitives of the accelerated tree.
+ *   interior: a = index of l (>= 0), b = index of r
+ *   leaf    : a = ~startIndex (< 0), b = endIndex - startIndex                         */
+typedef struct rtb_ref_node {
+	float bmin[3];
+	int32_t a;
+	float bmax[3];
+	int32_t b;
+} rtb_ref_node; /* 32 B */
+
+/* Intersection record of one triangle (RTBase/Geometry.h:62-83 `Triangle`): exactly the
+ * fields Triangle::rayIntersect (Geometry.h:89-105) reads.  n, d, area are the values
+ * Triangle::init computed; inv_area = 1.0f / Dot(e1.cross(e2), n) (Geometry.h:98), hoisted.
+ * e1 = v2 - v1 and e2 = v0 - v2 are re-derived on the device (single rounding, same bits). */
+typedef struct rtb_tri_isect {
+	float v0[3], d;
+	float v1[3], inv_area;
+	float v2[3];
+	uint32_t material;
+	float n[3], area;
+} rtb_tri_isect; /* 64 B */
+
+/* Shading attributes (Geometry.h:106-112, 127-130): vertex normals / uvs and the sign used
+ * by Triangle::gNormal(): gsign = Dot(vertices[0].normal, n) > 0 ? +1 : -1.              */
+typedef struct rtb_tri_shade {
+	float n0[3], u0;
+	float n1[3], u1;
+	float n2[3], u2;
+	float tv0, tv1, tv2, gsign;
+} rtb_tri_shade; /* 64 B */
+
+/* BSDF classes of RTBase/Materials.h:118-511. */
+typedef enum rtb_bsdf_type {
+	RTB_BSDF_DIFFUSE = 0,    /* DiffuseBSDF    Materials.h:118 */
+	RTB_BSDF_MIRROR = 1,     /* MirrorBSDF     Materials.h:158 */
+	RTB_BSDF_CONDUCTOR = 2,  /* ConductorBSDF  Materials.h:203 */
+	RTB_BSDF_GLASS = 3,      /* GlassBSDF      Materials.h:252 */
+	RTB_BSDF_DIELECTRIC = 4, /* DielectricBSDF Materials.h:320 */
+	RTB_BSDF_ORENNAYAR = 5,  /* OrenNayarBSDF  Materials.h:369 */
+	RTB_BSDF_PLASTIC = 6     /* PlasticBSDF    Materials.h:414 */
+} rtb_bsdf_type;
+
+#define RTB_MAT_SPECULAR 1u  /* isPureSpecular()                                      */
+#define RTB_MAT_TWO_SIDED 2u /* isTwoSided() (LayeredBSDF forces true, :503-506)      */
+#define RTB_MAT_LIGHT 4u     /* isLight(): emission.Lum() > 0 (:103-106)              */
+#define RTB_MAT_LAYERED 8u   /* wrapped in LayeredBSDF (:467); `type` is the base's   */
+
+typedef struct rtb_material {
+	uint32_t type;  /* rtb_bsdf_type of the (base) BSDF                              */
+	uint32_t flags; /* RTB_MAT_*                                                     */
+	int32_t tex;    /* index into textures: the BSDF's `albedo`                      */
+	float int_ior, ext_ior;
+	float emission[3];
+	float alpha;    /* 1.62142f*sqrtf(roughness) (Conductor/Dielectric/Plastic) or sigma (OrenNayar) */
+	float eta[3], k[3]; /* ConductorBSDF                                             */
+	float thickness;    /* LayeredBSDF                                               */
+} rtb_material; /* 64 B */
+
+/* Texture (RTBase/Imaging.h:19-31): `offset` counts TEXELS into the shared texel pool,
+ * 3 floats per texel (Colour r,g,b), row-major.                                          */
+typedef struct rtb_texture {
+	uint32_t offset;
+	int32_t width, height;
+	int32_t pad_;
+} rtb_texture; /* 16 B */
+
+typedef enum rtb_light_type {
+	RTB_LIGHT_AREA = 0,       /* AreaLight        RTBase/Lights.h:30  */
+	RTB_LIGHT_BACKGROUND = 1, /* BackgroundColour RTBase/Lights.h:84  */
+	RTB_LIGHT_ENVMAP = 2      /* EnvironmentMap   RTBase/Lights.h:135 */
+} rtb_light_type;
+
+/* Entry of Scene::lights (RTBase/Scene.h:77), in the reference's order: the background
+ * first when totalIntegratedPower() > 0 (Scene.h:156-159), then one AreaLight per
+ * emissive triangle in ascending triangle index (Scene.h:96-105).                       */
+typedef struct rtb_light {
+	uint32_t type;
+	uint32_t triangle; /* area: index into triangles                                */
+	float emission[3]; /* area: AreaLight::emission; background: colour             */
+	float area;        /* area: Triangle::area                                      */
+	int32_t tex;       /* envmap: texture index                                     */
+	int32_t pad_;
+} rtb_light; /* 32 B */
+
+typedef struct rtb_scene_desc {
+	rtb_camera camera;
+	const rtb_ref_node* ref_nodes;
+	uint32_t n_ref_nodes;
+	uint32_t n_tris;
+	const rtb_tri_isect* tri_isect; /* [n_tris], index = position in Scene::triangles after build() */
+	const rtb_tri_shade* tri_shade; /* [n_tris]                                              */
+	const rtb_material* materials;
+	uint32_t n_materials;
+	uint32_t n_textures;
+	const rtb_texture* textures;
+	const float* texels; /* [n_texels*3]                                              */
+	uint64_t n_texels;
+	const rtb_light* lights;
+	uint32_t n_lights;
+	/* Scene::background (always present; it is also lights[0] when it has power). */
+	uint32_t background_type; /* RTB_LIGHT_BACKGROUND or RTB_LIGHT_ENVMAP          */
+	float background_colour[3];
+	int32_t background_tex;
+} rtb_scene_desc;
+
+/* ------------------------------------------------------------------------------------
+ * Parameters (the reference's compile-time constants and commented-out switches made
+ * run-time; defaults reproduce the reference as committed).
+ * ---------------------------------------------------------------------------------- */
+typedef enum rtb_integrator {
+	RTB_INT_PATH = 0,    /* RayTracer::pathTrace   Renderer.h:328-392 (the default)   */
+	RTB_INT_DIRECT = 1,  /* RayTracer::direct      Renderer.h:393-407                */
+	RTB_INT_ALBEDO = 2,  /* RayTracer::albedo      Renderer.h:558-571                */
+	RTB_INT_NORMALS = 3  /* RayTracer::viewNormals Renderer.h:572-581                */
+} rtb_integrator;
+
+typedef enum rtb_sampling {
+	RTB_SAMPLING_STRICT = 0,    /* sampling decisions exactly as the reference: uniform
+	                               light pick, uniform-sphere env, no MIS (Renderer.h:423-473) */
+	RTB_SAMPLING_IMPORTANCE = 1 /* same estimator expectation, lower variance: env-map
+	                               luminance CDF for the NEE direction      */
+} rtb_sampling;
+
+typedef enum rtb_traversal {
+	RTB_TRAV_EXACT = 0, /* the reference's own tree, exhaustive DFS (Geometry.h:399-427) */
+	RTB_TRAV_FAST = 1   /* accelerated tree over the reference's leaves, ordered + culled;
+	                       must return identical hits (tests assert it)                */
+} rtb_traversal;
+
+typedef enum rtb_filter {
+	RTB_FILTER_BOX = 0,     /* BoxFilter size 0 (Imaging.h:139-154, Renderer.h:50)     */
+	RTB_FILTER_GAUSSIAN = 1 /* GaussianFilter(radius, alpha) (Imaging.h:155-187)       */
+} rtb_filter;
+
+typedef enum rtb_partition {
+	RTB_PART_NONE = 0,
+	RTB_PART_SPP = 1, /* this rank renders sample indices s with s % world == rank      */
+	RTB_PART_TILE = 2 /* this rank renders 32x32 tiles t with t % world == rank          */
+} rtb_partition;
+
+typedef struct rtb_params {
+	int32_t max_depth;  /* MAX_DEPTH, Renderer.h:20 (4)                              */
+	float epsilon;      /* EPSILON, Geometry.h:60 (1e-4f)                            */
+	float rr_cap;       /* 0.9f, Renderer.h:353                                      */
+	int32_t integrator; /* rtb_integrator                                            */
+	int32_t sampling;   /* rtb_sampling                                              */
+	int32_t traversal;  /* rtb_traversal                                             */
+	int32_t filter;     /* rtb_filter                                                */
+	float filter_radius, filter_alpha; /* Gaussian (2.0, 0.1 at Renderer.h:51)        */
+	uint32_t seed;      /* key of the counter-based RNG                              */
+	int32_t partition;  /* rtb_partition                                             */
+	int32_t part_rank, part_world;
+	float cull_rel;     /* FAST traversal: relative slack of the t-cull (1e-5)       */
+	int32_t reserved_[2];
+} rtb_params; /* 64 B */
+
+/* Ray / hit records of the batched parity entry points. */
+typedef struct rtb_ray {
+	float o[3];
+	float tmax; /* any-hit: maxT of BVHNode::traverseVisible; closest-hit: ignored   */
+	float d[3];
+	float pad_;
+} rtb_ray; /* 32 B */
+
+/* == IntersectionData, RTBase/Geometry.h:231-238.  Miss: t = FLT_MAX, id = 0xFFFFFFFF. */
+typedef struct rtb_hit {
+	uint32_t id;
+	float t, alpha, beta, gamma;
+} rtb_hit; /* 20 B */
+
+/* == the float members of ShadingData, RTBase/Materials.h:15-35 (Vec3 w dropped). */
+typedef struct rtb_shading {
+	float x[3], wo[3], s_normal[3], g_normal[3];
+	float tu, tv;
+	float frame_u[3], frame_v[3], frame_w[3];
+	float t;
+	int32_t material; /* index of `bsdf` in Scene::materials; -1 on miss             */
+} rtb_shading; /* 100 B */
+
+typedef struct rtb_stats {
+	uint64_t samples;       /* pixel samples completed since the last clear        */
+	uint64_t closest_rays;  /* Scene::traverse calls                               */
+	uint64_t shadow_rays;   /* Scene::visible calls                                */
+	uint64_t kernel_launches; /* kernels of this library launched since create     */
+	double render_ms;       /* device time of the render kernels since last clear  */
+	uint64_t box_tests, tri_tests; /* only when built with RTB_COUNT_TESTS          */
+} rtb_stats;
+
+/* ------------------------------------------------------------------------------------
+ * Life cycle
+ * ---------------------------------------------------------------------------------- */
+int rtb_abi_version(void);
+/* Creates a context on CUDA device `device`.  Fails with RTB_ERR_NODEV when there is no
+ * such device: there is NO CPU fallback.                                                */
+int rtb_create(int device, rtb_ctx** out);
+void rtb_destroy(rtb_ctx* ctx);
+/* Message of the last failing call on ctx (ctx may be NULL: creation errors).  Never NULL. */
+const char* rtb_last_error(const rtb_ctx* ctx);
+/* All work of ctx is issued on `cuda_stream` (a cudaStream_t; NULL = the legacy default
+ * stream) so that the caller's events/graphs order against it.                          */
+int rtb_set_stream(rtb_ctx* ctx, void* cuda_stream);
+int rtb_synchronize(rtb_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------
+ * Scene + parameters
+ * ---------------------------------------------------------------------------------- */
+void rtb_default_params(rtb_params* p);
+int rtb_set_params(rtb_ctx* ctx, const rtb_params* p);
+int rtb_get_params(const rtb_ctx* ctx, rtb_params* p);
+/* Copies the scene to the device, builds the accelerated tree over the reference leaves
+ * and (re)allocates a cleared film of camera.width x camera.height.  Replaces
+ * RayTracer::init (Renderer.h:45-63).                                                    */
+int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* scene);
+/* Camera::updateView / RTCamera::updateCamera (Scene.h:33-41): new camera, same scene.   */
+int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam);
+
+/* ------------------------------------------------------------------------------------
+ * The hot path
+ * ---------------------------------------------------------------------------------- */
+/* RayTracer::clear (Renderer.h:64-67): zero the film sums and SPP.                       */
+int rtb_clear(rtb_ctx* ctx);
+/* spp_count calls of RayTracer::render() (Renderer.h:876-885) in one go: accumulates the
+ * samples with global indices [spp_begin, spp_begin + spp_count) of every pixel this rank
+ * owns (see rtb_params.partition) into the device sum-film.  Asynchronous.  Resumable:
+ * the RNG is keyed by (seed, pixel, sample index), not by call order.                    */
+int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count);
+/* Film::film (Imaging.h:204): waits for the device and copies the running SUM (not the
+ * mean; Film::save divides by SPP, Imaging.h:262-271) as width*height*3 floats (r,g,b per
+ * pixel, row-major) to host memory; *spp receives Film::SPP.  Either may be NULL.         */
+int rtb_read_film(rtb_ctx* ctx, float* rgb_sum, uint32_t* spp);
+/* Device address of the sum film (width*height*3 floats) for the caller's NCCL reduce.   */
+int rtb_film_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_floats);
+/* Film::tonemap for every pixel (Imaging.h:233-242; what presentFilmToCanvas draws,
+ * Renderer.h:69-80): width*height*3 bytes r,g,b.                                          */
+int rtb_tonemap(rtb_ctx* ctx, uint8_t* rgb8, float exposure);
+int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out);
+int rtb_film_size(const rtb_ctx* ctx, uint32_t* width, uint32_t* height);
+
+/* ------------------------------------------------------------------------------------
+ * Parity entry points (batched restatements of single reference calls; host buffers)
+ * ---------------------------------------------------------------------------------- */
+/* Camera::generateRay(x+0.5, y+0.5) + Scene::traverse for every pixel (Renderer.h:806-808,
+ * Scene.h:43-54,107-130).  ids/t/rays row-major; any pointer may be NULL.  `traversal`
+ * is an rtb_traversal.                                                                   */
+int rtb_primary_hits(rtb_ctx* ctx, int traversal, uint32_t* ids, float* t, rtb_ray* rays);
+/* Scene::traverse (any_hit = 0) or BVHNode::traverseVisible with maxT = ray.tmax
+ * (any_hit = 1; hit.id = 1 if occluded, 0 if visible).                                  */
+int rtb_trace(rtb_ctx* ctx, int traversal, int any_hit, const rtb_ray* rays, uint64_t n, rtb_hit* hits);
+/* Scene::visible(p1, p2) (Scene.h:161-169): p1p2 = n*6 floats; out[i] = 1 if visible.    */
+int rtb_visible(rtb_ctx* ctx, int traversal, const float* p1p2, uint64_t n, uint8_t* out);
+/* Scene::calculateShadingData (Scene.h:174-203).                                         */
+int rtb_shading_data(rtb_ctx* ctx, const rtb_ray* rays, const rtb_hit* hits, uint64_t n, rtb_shading* out);
+/* BSDF::evaluate / PDF at wi and BSDF::sample with the uniforms u[3] (u[0],u[1] = the two
+ * cosine-hemisphere draws in reference order r1,r2; u[2] = the glass reflect/refract draw).
+ * Any output may be NULL.  eval: n*3, pdf: n, s_wi: n*3, s_f: n*3, s_pdf: n.             */
+int rtb_eval_bsdf(rtb_ctx* ctx, const rtb_shading* sd, const float* wi, const float* u, uint64_t n,
+                  float* eval, float* pdf, float* s_wi, float* s_f, float* s_pdf);
+/* Light::sample with uniforms u[2] (r1, r2) for light `light[i]` -> p_or_wi (n*3),
+ * emitted (n*3), pdf (n); Light::evaluate(wi) -> eval (n*3).  STRICT sampling only.       */
+int rtb_eval_light(rtb_ctx* ctx, const int32_t* light, const float* wi, const float* u, uint64_t n,
+                   float* p_or_wi, float* emitted, float* pdf, float* eval);
+/* The uniforms the render kernel draws: out[i] = u(pixel, sample, dim i), dims [0, n).    */
+int rtb_rng_draws(rtb_ctx* ctx, uint32_t pixel, uint32_t sample, uint32_t n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H_ */
