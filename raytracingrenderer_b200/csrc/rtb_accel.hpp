@@ -1,0 +1,370 @@
+// rtb_accel.hpp — host-side builders run by rtb_upload_scene:
+//   * skip links for the stack-free EXACT traversal of the reference's tree,
+//   * the FAST tree: a binned-SAH binary BVH whose primitives are the reference's LEAVES
+//     (<= 2 triangles each, RTBase/Geometry.h:240,337) with their exact AABBs, so that the
+//     box test that admits a leaf is the reference's own leaf test,
+//   * the environment-map sampling tables.
+#pragma once
+#include "../../include/rtb.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace rtb_accel
+{
+
+struct F4
+{
+	float x, y, z, w;
+};
+inline float bitsToFloat(uint32_t u)
+{
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
+}
+
+// xnodes[2i] = bmin, bits(skip); xnodes[2i+1] = bmax, bits(leaf).  Also checks that the
+// array really is a pre-order tree (left child = i + 1) and collects the leaves.
+struct RefLeaf
+{
+	float bmin[3], bmax[3];
+	uint32_t start, count;
+};
+
+inline bool buildExact(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris, std::vector<F4>& xnodes,
+                       std::vector<RefLeaf>& leaves, const char** err)
+{
+	xnodes.resize((size_t)n * 2);
+	leaves.clear();
+	if (n == 0) return true;
+	std::vector<uint32_t> skip(n, 0);
+	// iterative post-order: skip[i] = first index after i's subtree
+	struct Item
+	{
+		uint32_t node, end;
+	};
+	std::vector<Item> stack;
+	stack.push_back({0u, n});
+	while (!stack.empty())
+	{
+		Item it = stack.back();
+		stack.pop_back();
+		const rtb_ref_node& nd = nodes[it.node];
+		skip[it.node] = it.end;
+		if (nd.a < 0) continue;
+		if ((uint32_t)nd.a != it.node + 1 || (uint32_t)nd.b <= it.node + 1 || (uint32_t)nd.b >= it.end)
+		{
+			*err = "ref_nodes is not a pre-order tree";
+			return false;
+		}
+		stack.push_back({(uint32_t)nd.a, (uint32_t)nd.b});
+		stack.push_back({(uint32_t)nd.b, it.end});
+	}
+	for (uint32_t i = 0; i < n; i++)
+	{
+		const rtb_ref_node& nd = nodes[i];
+		uint32_t leaf = 0xFFFFFFFFu;
+		if (nd.a < 0)
+		{
+			uint32_t start = (uint32_t)(~nd.a), count = (uint32_t)nd.b;
+			if (count > 3u || start >= (1u << 30) || (uint64_t)start + count > nTris)
+			{
+				*err = "ref leaf out of range (count > 3 or start + count > n_tris)";
+				return false;
+			}
+			leaf = (start << 2) | count;
+			RefLeaf L;
+			memcpy(L.bmin, nd.bmin, 12);
+			memcpy(L.bmax, nd.bmax, 12);
+			L.start = start, L.count = count;
+			if (count) leaves.push_back(L);
+		}
+		xnodes[(size_t)i * 2] = {nd.bmin[0], nd.bmin[1], nd.bmin[2], bitsToFloat(skip[i])};
+		xnodes[(size_t)i * 2 + 1] = {nd.bmax[0], nd.bmax[1], nd.bmax[2], bitsToFloat(leaf)};
+	}
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// FAST tree
+// ---------------------------------------------------------------------------------------
+struct Box
+{
+	float mn[3], mx[3];
+	void reset()
+	{
+		mn[0] = mn[1] = mn[2] = FLT_MAX;
+		mx[0] = mx[1] = mx[2] = -FLT_MAX;
+	}
+	void grow(const float* a, const float* b)
+	{
+		for (int k = 0; k < 3; k++)
+		{
+			if (a[k] < mn[k]) mn[k] = a[k];
+			if (b[k] > mx[k]) mx[k] = b[k];
+		}
+	}
+	void grow(const Box& o) { grow(o.mn, o.mx); }
+	float area() const
+	{
+		float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+		if (dx < 0 || dy < 0 || dz < 0) return 0.0f;
+		return 2.0f * (dx * dy + dy * dz + dz * dx);
+	}
+};
+
+struct FastTree
+{
+	std::vector<F4> nodes; // 4 x F4 per node (layout in rtb_dev_scene.cuh)
+	int32_t root = 0;      // child reference of the root
+	uint32_t maxDepth = 0;
+};
+
+class FastBuilder
+{
+public:
+	FastBuilder(const std::vector<RefLeaf>& leaves) : L(leaves) {}
+
+	void build(FastTree& out)
+	{
+		out.nodes.clear();
+		out.maxDepth = 0;
+		uint32_t n = (uint32_t)L.size();
+		if (n == 0)
+		{
+			out.root = ~0; // empty leaf (start 0, count 0)
+			return;
+		}
+		idx.resize(n);
+		cen.resize((size_t)n * 3);
+		for (uint32_t i = 0; i < n; i++)
+		{
+			idx[i] = i;
+			for (int k = 0; k < 3; k++) cen[(size_t)i * 3 + k] = 0.5f * (L[i].bmin[k] + L[i].bmax[k]);
+		}
+		if (n == 1)
+		{
+			out.root = leafRef(0);
+			return;
+		}
+		out.nodes.reserve((size_t)(n - 1) * 4);
+		tree = &out;
+		Box b;
+		out.root = recurse(0, n, 0, b);
+	}
+
+private:
+	static const int BINS = 32;
+	static const uint32_t MAX_SAH_DEPTH = 40; // deeper than this: median splits (bounded stack on device)
+	const std::vector<RefLeaf>& L;
+	std::vector<uint32_t> idx;
+	std::vector<float> cen;
+	FastTree* tree = nullptr;
+
+	int32_t leafRef(uint32_t prim) const { return ~(int32_t)((L[prim].start << 2) | L[prim].count); }
+
+	// returns the child reference and the exact box of the subtree (= union of leaf boxes)
+	int32_t recurse(uint32_t lo, uint32_t hi, uint32_t depth, Box& box)
+	{
+		if (depth > tree->maxDepth) tree->maxDepth = depth;
+		uint32_t n = hi - lo;
+		box.reset();
+		if (n == 1)
+		{
+			box.grow(L[idx[lo]].bmin, L[idx[lo]].bmax);
+			return leafRef(idx[lo]);
+		}
+		uint32_t mid = split(lo, hi, depth);
+		size_t self = tree->nodes.size() / 4;
+		tree->nodes.resize(tree->nodes.size() + 4);
+		Box b0, b1;
+		int32_t c0 = recurse(lo, mid, depth + 1, b0);
+		int32_t c1 = recurse(mid, hi, depth + 1, b1);
+		F4* nd = &tree->nodes[self * 4];
+		nd[0] = {b0.mn[0], b0.mx[0], b0.mn[1], b0.mx[1]};
+		nd[1] = {b1.mn[0], b1.mx[0], b1.mn[1], b1.mx[1]};
+		nd[2] = {b0.mn[2], b0.mx[2], b1.mn[2], b1.mx[2]};
+		nd[3] = {bitsToFloat((uint32_t)c0), bitsToFloat((uint32_t)c1), 0.0f, 0.0f};
+		box.grow(b0);
+		box.grow(b1);
+		return (int32_t)self;
+	}
+
+	uint32_t split(uint32_t lo, uint32_t hi, uint32_t depth)
+	{
+		uint32_t n = hi - lo;
+		if (n == 2) return lo + 1;
+		// centroid bounds
+		float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+		for (uint32_t i = lo; i < hi; i++)
+		{
+			const float* c = &cen[(size_t)idx[i] * 3];
+			for (int k = 0; k < 3; k++)
+			{
+				if (c[k] < cmn[k]) cmn[k] = c[k];
+				if (c[k] > cmx[k]) cmx[k] = c[k];
+			}
+		}
+		int bestAxis = -1, bestBin = -1;
+		float bestCost = FLT_MAX;
+		if (depth < MAX_SAH_DEPTH)
+		{
+			for (int ax = 0; ax < 3; ax++)
+			{
+				float ext = cmx[ax] - cmn[ax];
+				if (!(ext > 0.0f)) continue;
+				float scale = (float)BINS / ext;
+				Box bb[BINS];
+				uint32_t cnt[BINS];
+				for (int b = 0; b < BINS; b++)
+				{
+					bb[b].reset();
+					cnt[b] = 0;
+				}
+				for (uint32_t i = lo; i < hi; i++)
+				{
+					uint32_t p = idx[i];
+					int b = (int)((cen[(size_t)p * 3 + ax] - cmn[ax]) * scale);
+					if (b >= BINS) b = BINS - 1;
+					if (b < 0) b = 0;
+					bb[b].grow(L[p].bmin, L[p].bmax);
+					cnt[b] += L[p].count; // cost weight: triangles in the leaf
+				}
+				float rightArea[BINS];
+				uint32_t rightCnt[BINS];
+				Box acc;
+				acc.reset();
+				uint32_t c = 0;
+				for (int b = BINS - 1; b > 0; b--)
+				{
+					acc.grow(bb[b]);
+					c += cnt[b];
+					rightArea[b] = acc.area();
+					rightCnt[b] = c;
+				}
+				acc.reset();
+				c = 0;
+				for (int b = 0; b < BINS - 1; b++)
+				{
+					acc.grow(bb[b]);
+					c += cnt[b];
+					if (c == 0 || rightCnt[b + 1] == 0) continue;
+					float cost = acc.area() * (float)c + rightArea[b + 1] * (float)rightCnt[b + 1];
+					if (cost < bestCost)
+					{
+						bestCost = cost;
+						bestAxis = ax;
+						bestBin = b;
+					}
+				}
+			}
+		}
+		if (bestAxis >= 0)
+		{
+			float ext = cmx[bestAxis] - cmn[bestAxis];
+			float scale = (float)BINS / ext;
+			float base = cmn[bestAxis];
+			int ax = bestAxis, bin = bestBin;
+			uint32_t* first = &idx[lo];
+			uint32_t* last = &idx[hi];
+			uint32_t* m = std::partition(first, last, [&](uint32_t p) {
+				int b = (int)((cen[(size_t)p * 3 + ax] - base) * scale);
+				if (b >= BINS) b = BINS - 1;
+				if (b < 0) b = 0;
+				return b <= bin;
+			});
+			uint32_t mid = (uint32_t)(m - &idx[0]);
+			if (mid > lo && mid < hi) return mid;
+		}
+		// fallback: median split along the widest centroid axis (or by index if all equal)
+		int ax = 0;
+		float e0 = cmx[0] - cmn[0], e1 = cmx[1] - cmn[1], e2 = cmx[2] - cmn[2];
+		if (e1 > e0 && e1 >= e2) ax = 1;
+		else if (e2 > e0 && e2 > e1) ax = 2;
+		uint32_t mid = lo + n / 2;
+		std::nth_element(&idx[lo], &idx[mid], &idx[0] + hi, [&](uint32_t a, uint32_t b) {
+			float ca = cen[(size_t)a * 3 + ax], cb = cen[(size_t)b * 3 + ax];
+			return ca < cb || (ca == cb && a < b);
+		});
+		return mid;
+	}
+};
+
+// ---------------------------------------------------------------------------------------
+// Environment-map sampling tables (RTB_SAMPLING_IMPORTANCE).  EnvironmentMap::evaluate
+// (RTBase/Lights.h:158-165) maps a direction to u = phi/2pi, v = theta/pi and
+// Texture::sample (Imaging.h:72-94) blends texels floor(u W), floor(u W)+1 (no half-texel
+// shift), so the radiance inside cell (x, y) = [x/W,(x+1)/W) x [y/H,(y+1)/H) depends on
+// texels (x..x+1, y..y+1).  Cell weight = max luminance of those four texels x sin(theta)
+// at the cell centre, plus a floor so that the pdf is positive wherever radiance can be:
+// the estimator's expectation is unchanged for ANY such positive density.
+// ---------------------------------------------------------------------------------------
+inline void buildEnvTables(const float* texels, int W, int H, std::vector<float>& marginal, std::vector<float>& cond)
+{
+	std::vector<double> w((size_t)W * H);
+	double sum = 0.0;
+	auto lumAt = [&](int x, int y) {
+		const float* p = texels + ((size_t)(y % H) * W + (size_t)(x % W)) * 3;
+		return 0.2126 * p[0] + 0.7152 * p[1] + 0.0722 * p[2];
+	};
+	for (int y = 0; y < H; y++)
+	{
+		double st = sin(((double)y + 0.5) / (double)H * 3.14159265358979323846);
+		for (int x = 0; x < W; x++)
+		{
+			double l = std::max(std::max(lumAt(x, y), lumAt(x + 1, y)), std::max(lumAt(x, y + 1), lumAt(x + 1, y + 1)));
+			if (!(l > 0.0)) l = 0.0;
+			w[(size_t)y * W + x] = l * st;
+			sum += l * st;
+		}
+	}
+	double mean = sum / ((double)W * H);
+	double floorW = (mean > 0.0) ? 0.05 * mean : 1.0;
+	marginal.assign((size_t)H + 1, 0.0f);
+	cond.assign((size_t)H * (W + 1), 0.0f);
+	std::vector<double> rowSum(H);
+	double total = 0.0;
+	for (int y = 0; y < H; y++)
+	{
+		double st = sin(((double)y + 0.5) / (double)H * 3.14159265358979323846);
+		double rs = 0.0;
+		for (int x = 0; x < W; x++)
+		{
+			w[(size_t)y * W + x] += floorW * st;
+			rs += w[(size_t)y * W + x];
+		}
+		rowSum[y] = rs;
+		total += rs;
+	}
+	double acc = 0.0;
+	for (int y = 0; y < H; y++)
+	{
+		marginal[y] = (float)(acc / total);
+		acc += rowSum[y];
+		double ca = 0.0;
+		float* cd = &cond[(size_t)y * (W + 1)];
+		for (int x = 0; x < W; x++)
+		{
+			cd[x] = (float)(ca / rowSum[y]);
+			ca += w[(size_t)y * W + x];
+		}
+		cd[W] = 1.0f;
+	}
+	marginal[H] = 1.0f;
+	// make the float CDFs non-decreasing (rounding)
+	for (int y = 1; y <= H; y++)
+		if (marginal[y] < marginal[y - 1]) marginal[y] = marginal[y - 1];
+	for (int y = 0; y < H; y++)
+	{
+		float* cd = &cond[(size_t)y * (W + 1)];
+		for (int x = 1; x <= W; x++)
+			if (cd[x] < cd[x - 1]) cd[x] = cd[x - 1];
+	}
+}
+
+} // namespace rtb_accel

@@ -1,0 +1,710 @@
+// rtb_api.cu — implementation of the C ABI declared in include/rtb.h: context, scene upload,
+// launch wrappers.  Device code: rtb_kernels.cuh.  Build: see raytracingrenderer_b200/build.py
+// (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo).
+#include "rtb_accel.hpp"
+#include "rtb_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace
+{
+thread_local std::string g_createError;
+
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t bytes = 0;
+};
+
+struct EventPair
+{
+	cudaEvent_t a, b;
+};
+} // namespace
+
+struct rtb_ctx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string error;
+	rtb_params params;
+	bool haveScene = false;
+	DevScene S;
+	std::vector<void*> sceneAllocs;
+	float* film = nullptr;
+	float* filmFiltered = nullptr;
+	uint8_t* tone = nullptr;
+	unsigned long long* counters = nullptr; // 8 x u64
+	uint32_t width = 0, height = 0;
+	uint32_t spp = 0;
+	uint64_t launches = 0;
+	double renderMs = 0.0;
+	std::vector<EventPair> pending;
+	std::vector<cudaEvent_t> eventPool;
+	uint32_t fastDepth = 0;
+};
+
+namespace
+{
+int fail(rtb_ctx* ctx, int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (ctx) ctx->error = buf;
+	else g_createError = buf;
+	return code;
+}
+
+#define CK(call)                                                                                        \
+	do                                                                                                  \
+	{                                                                                                   \
+		cudaError_t e_ = (call);                                                                        \
+		if (e_ != cudaSuccess)                                                                          \
+			return fail(ctx, e_ == cudaErrorMemoryAllocation ? RTB_ERR_OOM : RTB_ERR_CUDA, "%s: %s", #call, \
+			            cudaGetErrorString(e_));                                                        \
+	} while (0)
+
+int bind(rtb_ctx* ctx)
+{
+	CK(cudaSetDevice(ctx->device));
+	return RTB_OK;
+}
+
+void freeScene(rtb_ctx* ctx)
+{
+	for (void* p : ctx->sceneAllocs) cudaFree(p);
+	ctx->sceneAllocs.clear();
+	if (ctx->film) cudaFree(ctx->film);
+	if (ctx->filmFiltered) cudaFree(ctx->filmFiltered);
+	if (ctx->tone) cudaFree(ctx->tone);
+	ctx->film = ctx->filmFiltered = nullptr;
+	ctx->tone = nullptr;
+	ctx->haveScene = false;
+}
+
+template <class T>
+int uploadArray(rtb_ctx* ctx, const T* host, size_t n, const T** dev)
+{
+	*dev = nullptr;
+	if (n == 0) return RTB_OK;
+	void* p = nullptr;
+	CK(cudaMalloc(&p, n * sizeof(T)));
+	ctx->sceneAllocs.push_back(p);
+	CK(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	*dev = (const T*)p;
+	return RTB_OK;
+}
+
+// scratch device buffer for the batched entry points
+struct Scratch
+{
+	std::vector<void*> ptrs;
+	~Scratch()
+	{
+		for (void* p : ptrs) cudaFree(p);
+	}
+	template <class T>
+	cudaError_t in(const T* host, size_t n, T** dev, cudaStream_t s)
+	{
+		*dev = nullptr;
+		if (!host || n == 0) return cudaSuccess;
+		void* p = nullptr;
+		cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+		if (e != cudaSuccess) return e;
+		ptrs.push_back(p);
+		*dev = (T*)p;
+		return cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, s);
+	}
+	template <class T>
+	cudaError_t out(const T* hostWanted, size_t n, T** dev)
+	{
+		*dev = nullptr;
+		if (!hostWanted || n == 0) return cudaSuccess;
+		void* p = nullptr;
+		cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+		if (e != cudaSuccess) return e;
+		ptrs.push_back(p);
+		*dev = (T*)p;
+		return cudaSuccess;
+	}
+};
+
+cudaEvent_t getEvent(rtb_ctx* ctx)
+{
+	if (!ctx->eventPool.empty())
+	{
+		cudaEvent_t e = ctx->eventPool.back();
+		ctx->eventPool.pop_back();
+		return e;
+	}
+	cudaEvent_t e = nullptr;
+	cudaEventCreate(&e);
+	return e;
+}
+
+void resolveTimings(rtb_ctx* ctx)
+{
+	for (EventPair& p : ctx->pending)
+	{
+		float ms = 0.0f;
+		if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+			ctx->renderMs += ms;
+		ctx->eventPool.push_back(p.a);
+		ctx->eventPool.push_back(p.b);
+	}
+	ctx->pending.clear();
+}
+
+int checkTrav(rtb_ctx* ctx, int traversal)
+{
+	if (traversal != RTB_TRAV_EXACT && traversal != RTB_TRAV_FAST) return fail(ctx, RTB_ERR_ARG, "bad traversal %d", traversal);
+	return RTB_OK;
+}
+} // namespace
+
+template <int TRAV>
+static void launchRender(rtb_ctx* ctx, const RenderArgs& A, dim3 grid, dim3 block)
+{
+	switch (ctx->params.integrator)
+	{
+	case RTB_INT_DIRECT: k_render<TRAV, RTB_INT_DIRECT><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
+	case RTB_INT_ALBEDO: k_render<TRAV, RTB_INT_ALBEDO><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
+	case RTB_INT_NORMALS: k_render<TRAV, RTB_INT_NORMALS><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
+	default: k_render<TRAV, RTB_INT_PATH><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
+	}
+}
+
+static int filteredFilm(rtb_ctx* ctx, const float** src)
+{
+	*src = ctx->film;
+	if (ctx->params.filter != RTB_FILTER_GAUSSIAN) return RTB_OK;
+	size_t npx = (size_t)ctx->width * ctx->height;
+	if (!ctx->filmFiltered) CK(cudaMalloc((void**)&ctx->filmFiltered, npx * 3 * sizeof(float)));
+	int size = (int)ceilf(ctx->params.filter_radius);
+	if (size < 0) size = 0;
+	if (size > 2) size = 2; // filterWeights[25], RTBase/Imaging.h:212
+	k_gaussian<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(ctx->film, ctx->filmFiltered, (int)ctx->width, (int)ctx->height,
+	                                                                      size, ctx->params.filter_radius, ctx->params.filter_alpha);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	*src = ctx->filmFiltered;
+	return RTB_OK;
+}
+
+extern "C" {
+
+int rtb_abi_version(void) { return RTB_ABI_VERSION; }
+
+void rtb_default_params(rtb_params* p)
+{
+	if (!p) return;
+	memset(p, 0, sizeof(*p));
+	p->max_depth = 4;     // MAX_DEPTH, RTBase/Renderer.h:20
+	p->epsilon = 1e-4f;   // EPSILON, RTBase/Geometry.h:60
+	p->rr_cap = 0.9f;     // RTBase/Renderer.h:353
+	p->integrator = RTB_INT_PATH;
+	p->sampling = RTB_SAMPLING_STRICT;
+	p->traversal = RTB_TRAV_FAST;
+	p->filter = RTB_FILTER_BOX; // RTBase/Renderer.h:50
+	p->filter_radius = 2.0f;    // RTBase/Renderer.h:51
+	p->filter_alpha = 0.1f;
+	p->seed = 1;                // MTRandom(seed = 1), RTBase/Sampling.h:18
+	p->partition = RTB_PART_NONE;
+	p->part_rank = 0;
+	p->part_world = 1;
+	p->cull_rel = 1e-5f;
+}
+
+int rtb_create(int device, rtb_ctx** out)
+{
+	rtb_ctx* ctx = nullptr;
+	if (!out) return fail(nullptr, RTB_ERR_ARG, "rtb_create: out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return fail(nullptr, RTB_ERR_NODEV, "no CUDA device (%s); librtb200 has no CPU fallback",
+		            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+	if (device < 0 || device >= n) return fail(nullptr, RTB_ERR_NODEV, "device %d out of range [0,%d)", device, n);
+	ctx = new (std::nothrow) rtb_ctx();
+	if (!ctx) return fail(nullptr, RTB_ERR_OOM, "out of host memory");
+	ctx->device = device;
+	rtb_default_params(&ctx->params);
+	memset(&ctx->S, 0, sizeof(ctx->S));
+	if (cudaSetDevice(device) != cudaSuccess || cudaMalloc((void**)&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)) != cudaSuccess)
+	{
+		int rc = fail(nullptr, RTB_ERR_CUDA, "context creation on device %d failed: %s", device,
+		              cudaGetErrorString(cudaGetLastError()));
+		delete ctx;
+		return rc;
+	}
+	*out = ctx;
+	return RTB_OK;
+}
+
+void rtb_destroy(rtb_ctx* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	resolveTimings(ctx);
+	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+	freeScene(ctx);
+	if (ctx->counters) cudaFree(ctx->counters);
+	delete ctx;
+}
+
+const char* rtb_last_error(const rtb_ctx* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+int rtb_set_stream(rtb_ctx* ctx, void* cuda_stream)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	ctx->stream = (cudaStream_t)cuda_stream;
+	return RTB_OK;
+}
+
+int rtb_synchronize(rtb_ctx* ctx)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (int rc = bind(ctx)) return rc;
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_set_params(rtb_ctx* ctx, const rtb_params* p)
+{
+	if (!ctx || !p) return fail(ctx, RTB_ERR_ARG, "rtb_set_params: NULL argument");
+	if (p->integrator < RTB_INT_PATH || p->integrator > RTB_INT_NORMALS) return fail(ctx, RTB_ERR_ARG, "bad integrator %d", p->integrator);
+	if (p->sampling != RTB_SAMPLING_STRICT && p->sampling != RTB_SAMPLING_IMPORTANCE) return fail(ctx, RTB_ERR_ARG, "bad sampling %d", p->sampling);
+	if (int rc = checkTrav(ctx, p->traversal)) return rc;
+	if (p->filter != RTB_FILTER_BOX && p->filter != RTB_FILTER_GAUSSIAN) return fail(ctx, RTB_ERR_ARG, "bad filter %d", p->filter);
+	if (p->partition < RTB_PART_NONE || p->partition > RTB_PART_TILE) return fail(ctx, RTB_ERR_ARG, "bad partition %d", p->partition);
+	if (p->partition != RTB_PART_NONE && (p->part_world < 1 || p->part_rank < 0 || p->part_rank >= p->part_world))
+		return fail(ctx, RTB_ERR_ARG, "bad partition rank %d of %d", p->part_rank, p->part_world);
+	if (p->max_depth < 0 || !(p->epsilon >= 0.0f)) return fail(ctx, RTB_ERR_ARG, "bad max_depth/epsilon");
+	ctx->params = *p;
+	return RTB_OK;
+}
+
+int rtb_get_params(const rtb_ctx* ctx, rtb_params* p)
+{
+	if (!ctx || !p) return RTB_ERR_ARG;
+	*p = ctx->params;
+	return RTB_OK;
+}
+
+int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
+{
+	if (!ctx || !sc) return fail(ctx, RTB_ERR_ARG, "rtb_upload_scene: NULL argument");
+	if (int rc = bind(ctx)) return rc;
+	if (sc->n_tris && (!sc->tri_isect || !sc->tri_shade)) return fail(ctx, RTB_ERR_ARG, "triangle arrays missing");
+	if (sc->n_ref_nodes && !sc->ref_nodes) return fail(ctx, RTB_ERR_ARG, "ref_nodes missing");
+	if (sc->n_tris && !sc->n_ref_nodes) return fail(ctx, RTB_ERR_ARG, "triangles without a BVH");
+	if (sc->n_tris && (!sc->materials || !sc->n_materials)) return fail(ctx, RTB_ERR_ARG, "materials missing");
+	if (!(sc->camera.width >= 1.0f) || !(sc->camera.height >= 1.0f) || sc->camera.width > 65536.0f || sc->camera.height > 65536.0f)
+		return fail(ctx, RTB_ERR_ARG, "bad film size %g x %g", sc->camera.width, sc->camera.height);
+	for (uint32_t i = 0; i < sc->n_tris; i++)
+		if (sc->tri_isect[i].material >= sc->n_materials) return fail(ctx, RTB_ERR_ARG, "triangle %u: material %u out of range", i, sc->tri_isect[i].material);
+	for (uint32_t i = 0; i < sc->n_materials; i++)
+	{
+		const rtb_material& m = sc->materials[i];
+		if (m.type > RTB_BSDF_PLASTIC) return fail(ctx, RTB_ERR_ARG, "material %u: unknown bsdf type %u", i, m.type);
+		if (m.tex < 0 || (uint32_t)m.tex >= sc->n_textures) return fail(ctx, RTB_ERR_ARG, "material %u: texture %d out of range", i, m.tex);
+	}
+	for (uint32_t i = 0; i < sc->n_textures; i++)
+	{
+		const rtb_texture& t = sc->textures[i];
+		if (t.width < 1 || t.height < 1 || (uint64_t)t.offset + (uint64_t)t.width * (uint64_t)t.height > sc->n_texels)
+			return fail(ctx, RTB_ERR_ARG, "texture %u out of the texel pool", i);
+	}
+	for (uint32_t i = 0; i < sc->n_lights; i++)
+	{
+		const rtb_light& l = sc->lights[i];
+		if (l.type > RTB_LIGHT_ENVMAP) return fail(ctx, RTB_ERR_ARG, "light %u: unknown type", i);
+		if (l.type == RTB_LIGHT_AREA && l.triangle >= sc->n_tris) return fail(ctx, RTB_ERR_ARG, "light %u: triangle out of range", i);
+		if (l.type == RTB_LIGHT_ENVMAP && (l.tex < 0 || (uint32_t)l.tex >= sc->n_textures)) return fail(ctx, RTB_ERR_ARG, "light %u: env texture out of range", i);
+	}
+	if (sc->background_type == RTB_LIGHT_ENVMAP && (sc->background_tex < 0 || (uint32_t)sc->background_tex >= sc->n_textures))
+		return fail(ctx, RTB_ERR_ARG, "background env texture out of range");
+
+	// host-side acceleration data
+	std::vector<rtb_accel::F4> xnodes;
+	std::vector<rtb_accel::RefLeaf> leaves;
+	const char* err = nullptr;
+	if (!rtb_accel::buildExact(sc->ref_nodes, sc->n_ref_nodes, sc->n_tris, xnodes, leaves, &err)) return fail(ctx, RTB_ERR_ARG, "%s", err);
+	rtb_accel::FastTree fast;
+	{
+		rtb_accel::FastBuilder fb(leaves);
+		fb.build(fast);
+	}
+	if (fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u)", fast.maxDepth);
+
+	CK(cudaStreamSynchronize(ctx->stream));
+	freeScene(ctx);
+	DevScene& S = ctx->S;
+	memset(&S, 0, sizeof(S));
+	S.cam = sc->camera;
+	int rc;
+	const rtb_accel::F4* dx = nullptr;
+	const rtb_accel::F4* df = nullptr;
+	if ((rc = uploadArray(ctx, xnodes.data(), xnodes.size(), &dx))) return rc;
+	if ((rc = uploadArray(ctx, fast.nodes.data(), fast.nodes.size(), &df))) return rc;
+	S.xnodes = (const float4*)dx;
+	S.fnodes = (const float4*)df;
+	S.n_xnodes = sc->n_ref_nodes;
+	S.n_fnodes = (uint32_t)(fast.nodes.size() / 4);
+	S.fast_root = fast.root;
+	ctx->fastDepth = fast.maxDepth;
+	const rtb_tri_isect* dti = nullptr;
+	const rtb_tri_shade* dts = nullptr;
+	if ((rc = uploadArray(ctx, sc->tri_isect, sc->n_tris, &dti))) return rc;
+	if ((rc = uploadArray(ctx, sc->tri_shade, sc->n_tris, &dts))) return rc;
+	S.tri = (const float4*)dti;
+	S.tsh = (const float4*)dts;
+	S.n_tris = sc->n_tris;
+	if ((rc = uploadArray(ctx, sc->materials, sc->n_materials, &S.mats))) return rc;
+	if ((rc = uploadArray(ctx, sc->textures, sc->n_textures, &S.texs))) return rc;
+	if ((rc = uploadArray(ctx, sc->texels, (size_t)sc->n_texels * 3, &S.texels))) return rc;
+	if ((rc = uploadArray(ctx, sc->lights, sc->n_lights, &S.lights))) return rc;
+	S.n_mats = sc->n_materials, S.n_texs = sc->n_textures, S.n_lights = sc->n_lights;
+	S.bg_type = sc->background_type;
+	memcpy(S.bg_colour, sc->background_colour, sizeof(S.bg_colour));
+	S.bg_tex = sc->background_tex;
+	// env sampling tables when the environment map is a light
+	std::vector<float> marginal, cond;
+	for (uint32_t i = 0; i < sc->n_lights; i++)
+	{
+		if (sc->lights[i].type == RTB_LIGHT_ENVMAP)
+		{
+			const rtb_texture& t = sc->textures[sc->lights[i].tex];
+			rtb_accel::buildEnvTables(sc->texels + (size_t)t.offset * 3, t.width, t.height, marginal, cond);
+			S.env_w = t.width, S.env_h = t.height;
+			if ((rc = uploadArray(ctx, marginal.data(), marginal.size(), &S.env_marginal))) return rc;
+			if ((rc = uploadArray(ctx, cond.data(), cond.size(), &S.env_cond))) return rc;
+			break;
+		}
+	}
+	ctx->width = (uint32_t)sc->camera.width;
+	ctx->height = (uint32_t)sc->camera.height;
+	size_t npx = (size_t)ctx->width * ctx->height;
+	CK(cudaMalloc((void**)&ctx->film, npx * 3 * sizeof(float)));
+	CK(cudaMemsetAsync(ctx->film, 0, npx * 3 * sizeof(float), ctx->stream));
+	CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	ctx->spp = 0;
+	ctx->renderMs = 0.0;
+	// the host vectors above die at return: finish the async copies first
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->haveScene = true;
+	return RTB_OK;
+}
+
+int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam)
+{
+	if (!ctx || !cam) return fail(ctx, RTB_ERR_ARG, "rtb_update_camera: NULL argument");
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if ((uint32_t)cam->width != ctx->width || (uint32_t)cam->height != ctx->height)
+		return fail(ctx, RTB_ERR_ARG, "camera film size differs from the uploaded scene's");
+	ctx->S.cam = *cam;
+	return RTB_OK;
+}
+
+int rtb_clear(rtb_ctx* ctx)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = bind(ctx)) return rc;
+	CK(cudaMemsetAsync(ctx->film, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(float), ctx->stream));
+	CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	resolveTimings(ctx);
+	ctx->spp = 0;
+	ctx->renderMs = 0.0;
+	return RTB_OK;
+}
+
+int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render before rtb_upload_scene");
+	if (spp_count == 0) return RTB_OK;
+	if ((uint64_t)spp_begin + spp_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "sample index overflow");
+	if (int rc = bind(ctx)) return rc;
+	RenderArgs A;
+	A.film = ctx->film;
+	A.counters = ctx->counters;
+	A.spp_begin = spp_begin, A.spp_count = spp_count;
+	A.width = ctx->width, A.height = ctx->height;
+	A.P = ctx->params;
+	uint32_t warps = ((ctx->width + 7) / 8) * ((ctx->height + 3) / 4);
+	dim3 block(64), grid((warps + 1) / 2);
+	EventPair ev = {getEvent(ctx), getEvent(ctx)};
+	cudaEventRecord(ev.a, ctx->stream);
+	if (ctx->params.traversal == RTB_TRAV_EXACT) launchRender<RTB_TRAV_EXACT>(ctx, A, grid, block);
+	else launchRender<RTB_TRAV_FAST>(ctx, A, grid, block);
+	cudaEventRecord(ev.b, ctx->stream);
+	ctx->pending.push_back(ev);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	ctx->spp += spp_count;
+	return RTB_OK;
+}
+
+int rtb_read_film(rtb_ctx* ctx, float* rgb_sum, uint32_t* spp)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = bind(ctx)) return rc;
+	if (rgb_sum)
+	{
+		const float* src = nullptr;
+		if (int rc = filteredFilm(ctx, &src)) return rc;
+		CK(cudaMemcpyAsync(rgb_sum, src, (size_t)ctx->width * ctx->height * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (spp) *spp = ctx->spp;
+	return RTB_OK;
+}
+
+int rtb_film_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_floats)
+{
+	if (!ctx || !dptr) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	*dptr = ctx->film;
+	if (n_floats) *n_floats = (uint64_t)ctx->width * ctx->height * 3;
+	return RTB_OK;
+}
+
+int rtb_film_size(const rtb_ctx* ctx, uint32_t* width, uint32_t* height)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (width) *width = ctx->width;
+	if (height) *height = ctx->height;
+	return RTB_OK;
+}
+
+int rtb_tonemap(rtb_ctx* ctx, uint8_t* rgb8, float exposure)
+{
+	if (!ctx || !rgb8) return fail(ctx, RTB_ERR_ARG, "rtb_tonemap: NULL argument");
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = bind(ctx)) return rc;
+	size_t n = (size_t)ctx->width * ctx->height * 3;
+	if (!ctx->tone) CK(cudaMalloc((void**)&ctx->tone, n));
+	const float* src = nullptr;
+	if (int rc = filteredFilm(ctx, &src)) return rc;
+	k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->width * ctx->height, (float)ctx->spp, exposure, ctx->tone);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(rgb8, ctx->tone, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out)
+{
+	if (!ctx || !out) return RTB_ERR_ARG;
+	if (int rc = bind(ctx)) return rc;
+	unsigned long long c[8];
+	CK(cudaMemcpyAsync(c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	resolveTimings(ctx);
+	memset(out, 0, sizeof(*out));
+	out->samples = c[0], out->closest_rays = c[1], out->shadow_rays = c[2];
+	out->box_tests = c[3], out->tri_tests = c[4];
+	out->kernel_launches = ctx->launches;
+	out->render_ms = ctx->renderMs;
+	return RTB_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// parity entry points
+// --------------------------------------------------------------------------------------
+int rtb_primary_hits(rtb_ctx* ctx, int traversal, uint32_t* ids, float* t, rtb_ray* rays)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = checkTrav(ctx, traversal)) return rc;
+	if (int rc = bind(ctx)) return rc;
+	size_t n = (size_t)ctx->width * ctx->height;
+	Scratch sc;
+	uint32_t* dIds;
+	float* dT;
+	rtb_ray* dR;
+	CK(sc.out(ids, n, &dIds));
+	CK(sc.out(t, n, &dT));
+	CK(sc.out(rays, n, &dR));
+	unsigned grid = (unsigned)((n + 127) / 128);
+	if (traversal == RTB_TRAV_EXACT)
+		k_primary<RTB_TRAV_EXACT><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, ctx->width, ctx->height, dIds, dT, dR, ctx->counters);
+	else
+		k_primary<RTB_TRAV_FAST><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, ctx->width, ctx->height, dIds, dT, dR, ctx->counters);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	if (ids) CK(cudaMemcpyAsync(ids, dIds, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (t) CK(cudaMemcpyAsync(t, dT, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (rays) CK(cudaMemcpyAsync(rays, dR, n * sizeof(rtb_ray), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_trace(rtb_ctx* ctx, int traversal, int any_hit, const rtb_ray* rays, uint64_t n, rtb_hit* hits)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = checkTrav(ctx, traversal)) return rc;
+	if (n == 0) return RTB_OK;
+	if (!rays || !hits) return fail(ctx, RTB_ERR_ARG, "rtb_trace: NULL buffer");
+	if (int rc = bind(ctx)) return rc;
+	Scratch sc;
+	rtb_ray* dR;
+	rtb_hit* dH;
+	CK(sc.in(rays, n, &dR, ctx->stream));
+	CK(sc.out(hits, n, &dH));
+	unsigned grid = (unsigned)((n + 127) / 128);
+	if (traversal == RTB_TRAV_EXACT)
+		k_trace<RTB_TRAV_EXACT><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, any_hit, dR, n, dH, ctx->counters);
+	else
+		k_trace<RTB_TRAV_FAST><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, any_hit, dR, n, dH, ctx->counters);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(hits, dH, n * sizeof(rtb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_visible(rtb_ctx* ctx, int traversal, const float* p1p2, uint64_t n, uint8_t* out)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = checkTrav(ctx, traversal)) return rc;
+	if (n == 0) return RTB_OK;
+	if (!p1p2 || !out) return fail(ctx, RTB_ERR_ARG, "rtb_visible: NULL buffer");
+	if (int rc = bind(ctx)) return rc;
+	Scratch sc;
+	float* dP;
+	uint8_t* dO;
+	CK(sc.in(p1p2, n * 6, &dP, ctx->stream));
+	CK(sc.out(out, n, &dO));
+	unsigned grid = (unsigned)((n + 127) / 128);
+	if (traversal == RTB_TRAV_EXACT)
+		k_visible<RTB_TRAV_EXACT><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, dP, n, dO, ctx->counters);
+	else
+		k_visible<RTB_TRAV_FAST><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, dP, n, dO, ctx->counters);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out, dO, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_shading_data(rtb_ctx* ctx, const rtb_ray* rays, const rtb_hit* hits, uint64_t n, rtb_shading* out)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (n == 0) return RTB_OK;
+	if (!rays || !hits || !out) return fail(ctx, RTB_ERR_ARG, "rtb_shading_data: NULL buffer");
+	if (int rc = bind(ctx)) return rc;
+	Scratch sc;
+	rtb_ray* dR;
+	rtb_hit* dH;
+	rtb_shading* dO;
+	CK(sc.in(rays, n, &dR, ctx->stream));
+	CK(sc.in(hits, n, &dH, ctx->stream));
+	CK(sc.out(out, n, &dO));
+	k_shading<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->S, dR, dH, n, dO);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out, dO, n * sizeof(rtb_shading), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_eval_bsdf(rtb_ctx* ctx, const rtb_shading* sd, const float* wi, const float* u, uint64_t n, float* eval,
+                  float* pdf, float* s_wi, float* s_f, float* s_pdf)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (n == 0) return RTB_OK;
+	if (!sd || !wi || !u) return fail(ctx, RTB_ERR_ARG, "rtb_eval_bsdf: NULL input");
+	for (uint64_t i = 0; i < n; i++)
+		if (sd[i].material < 0 || (uint32_t)sd[i].material >= ctx->S.n_mats) return fail(ctx, RTB_ERR_ARG, "rtb_eval_bsdf: record %llu has no material", (unsigned long long)i);
+	if (int rc = bind(ctx)) return rc;
+	Scratch sc;
+	rtb_shading* dS;
+	float *dWi, *dU, *dE, *dP, *dSw, *dSf, *dSp;
+	CK(sc.in(sd, n, &dS, ctx->stream));
+	CK(sc.in(wi, n * 3, &dWi, ctx->stream));
+	CK(sc.in(u, n * 3, &dU, ctx->stream));
+	CK(sc.out(eval, n * 3, &dE));
+	CK(sc.out(pdf, n, &dP));
+	CK(sc.out(s_wi, n * 3, &dSw));
+	CK(sc.out(s_f, n * 3, &dSf));
+	CK(sc.out(s_pdf, n, &dSp));
+	k_eval_bsdf<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->S, dS, dWi, dU, n, dE, dP, dSw, dSf, dSp);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	if (eval) CK(cudaMemcpyAsync(eval, dE, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	if (pdf) CK(cudaMemcpyAsync(pdf, dP, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (s_wi) CK(cudaMemcpyAsync(s_wi, dSw, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	if (s_f) CK(cudaMemcpyAsync(s_f, dSf, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	if (s_pdf) CK(cudaMemcpyAsync(s_pdf, dSp, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_eval_light(rtb_ctx* ctx, const int32_t* light, const float* wi, const float* u, uint64_t n, float* p_or_wi,
+                   float* emitted, float* pdf, float* eval)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (n == 0) return RTB_OK;
+	if (!light || !wi || !u) return fail(ctx, RTB_ERR_ARG, "rtb_eval_light: NULL input");
+	for (uint64_t i = 0; i < n; i++)
+		if (light[i] < 0 || (uint32_t)light[i] >= ctx->S.n_lights) return fail(ctx, RTB_ERR_ARG, "rtb_eval_light: light index %d out of range", light[i]);
+	if (int rc = bind(ctx)) return rc;
+	Scratch sc;
+	int32_t* dL;
+	float *dWi, *dU, *dP, *dE, *dPd, *dEv;
+	CK(sc.in(light, n, &dL, ctx->stream));
+	CK(sc.in(wi, n * 3, &dWi, ctx->stream));
+	CK(sc.in(u, n * 2, &dU, ctx->stream));
+	CK(sc.out(p_or_wi, n * 3, &dP));
+	CK(sc.out(emitted, n * 3, &dE));
+	CK(sc.out(pdf, n, &dPd));
+	CK(sc.out(eval, n * 3, &dEv));
+	k_eval_light<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->S, dL, dWi, dU, n, dP, dE, dPd, dEv);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	if (p_or_wi) CK(cudaMemcpyAsync(p_or_wi, dP, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	if (emitted) CK(cudaMemcpyAsync(emitted, dE, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	if (pdf) CK(cudaMemcpyAsync(pdf, dPd, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (eval) CK(cudaMemcpyAsync(eval, dEv, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_rng_draws(rtb_ctx* ctx, uint32_t pixel, uint32_t sample, uint32_t n, float* out)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (n == 0) return RTB_OK;
+	if (!out) return fail(ctx, RTB_ERR_ARG, "rtb_rng_draws: NULL buffer");
+	if (int rc = bind(ctx)) return rc;
+	Scratch sc;
+	float* d;
+	CK(sc.out(out, n, &d));
+	uint32_t blocks = (n + 3) / 4;
+	k_rng<<<(blocks + 127) / 128, 128, 0, ctx->stream>>>(ctx->params.seed, pixel, sample, n, d);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out, d, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,695 @@
+// rtb_dev_scene.cuh — device-side scene view, ray/box/triangle tests, traversal, shading
+// data, textures, BSDFs, lights and the counter-based RNG.  Each function cites the
+// reference code it restates; arithmetic order follows rtb_dev_math.cuh.
+#pragma once
+#include "../../include/rtb.h"
+#include "rtb_dev_math.cuh"
+
+#define RTB_INTERIOR 0xFFFFFFFFu
+#define RTB_MISS_ID 0xFFFFFFFFu
+#define RTB_PI_F 3.14159274101257324f   /* (float)M_PI */
+#define RTB_PI_D 3.14159265358979323846 /* M_PI */
+
+// Device view of an uploaded scene; passed to kernels by value (__grid_constant__).
+struct DevScene
+{
+	rtb_camera cam;
+	// EXACT tree: the reference's nodes in pre-order, 2 x float4 per node:
+	//   [2i]   = bmin.xyz, bits(skip)   skip = index of the first node after i's subtree
+	//   [2i+1] = bmax.xyz, bits(leaf)   leaf = RTB_INTERIOR, or (start << 2) | count
+	const float4* xnodes;
+	// FAST tree: binary tree over the reference's leaves, 4 x float4 per node:
+	//   [4i]   = c0.min.x c0.max.x c0.min.y c0.max.y
+	//   [4i+1] = c1.min.x c1.max.x c1.min.y c1.max.y
+	//   [4i+2] = c0.min.z c0.max.z c1.min.z c1.max.z
+	//   [4i+3] = bits(child0) bits(child1) - -     child >= 0: node index; < 0: ~((start<<2)|count)
+	const float4* fnodes;
+	const float4* tri;  // 4 x float4 per triangle = rtb_tri_isect
+	const float4* tsh;  // 4 x float4 per triangle = rtb_tri_shade
+	const rtb_material* mats;
+	const rtb_texture* texs;
+	const float* texels;
+	const rtb_light* lights;
+	// env-map importance tables (RTB_SAMPLING_IMPORTANCE): see rtb_api.cu buildEnvTables
+	const float* env_marginal; // [H+1] cdf over rows
+	const float* env_cond;     // [H*(W+1)] cdf over columns of each row
+	const float* env_pdf;      // [H*W] solid-angle pdf of the texel's centre direction
+	uint32_t n_xnodes, n_fnodes, n_tris, n_lights, n_mats, n_texs;
+	int32_t fast_root; // child reference of the FAST root (may itself be a leaf)
+	uint32_t bg_type;
+	float bg_colour[3];
+	int32_t bg_tex;
+	int32_t env_w, env_h;
+};
+
+struct HitD
+{
+	uint32_t id;
+	float t, alpha, beta;
+};
+
+RTB_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------------------
+// AABB::rayAABB (RTBase/Geometry.h:173-184).  Returns the reference's accept decision;
+// tEntry is t_entry_f (used only by the FAST traversal's ordering and culling).
+// ---------------------------------------------------------------------------------------
+RTB_DEV bool slabTest(float minx, float miny, float minz, float maxx, float maxy, float maxz, const RayD& r,
+                      float& tEntry)
+{
+	float ax = (minx - r.o.x) * r.inv.x, ay = (miny - r.o.y) * r.inv.y, az = (minz - r.o.z) * r.inv.z;
+	float bx = (maxx - r.o.x) * r.inv.x, by = (maxy - r.o.y) * r.inv.y, bz = (maxz - r.o.z) * r.inv.z;
+	float ex = selMin(ax, bx), ey = selMin(ay, by), ez = selMin(az, bz);
+	float xx = selMax(ax, bx), xy = selMax(ay, by), xz = selMax(az, bz);
+	float te = stdMax(stdMax(ex, ey), ez);
+	float tx = stdMin(stdMin(xx, xy), xz);
+	tEntry = te;
+	return !(tx < te || tx < 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------
+// Triangle::rayIntersect (RTBase/Geometry.h:89-105).
+// ---------------------------------------------------------------------------------------
+RTB_DEV bool triTest(const float4* __restrict__ tri, uint32_t id, const RayD& r, float& t, float& u, float& v)
+{
+	const float4* q = tri + (size_t)id * 4;
+	float4 q3 = ldg4(q + 3);
+	V3 n = mk(q3);
+	float denom = dot(n, r.d);
+	if (denom == 0.0f) return false;
+	float4 q0 = ldg4(q);
+	t = (q0.w - dot(n, r.o)) / denom;
+	if (t < 0.0f) return false;
+	float4 q1 = ldg4(q + 1);
+	float4 q2 = ldg4(q + 2);
+	V3 v0 = mk(q0), v1 = mk(q1), v2 = mk(q2);
+	V3 p = r.o + (r.d * t);
+	V3 e1 = v2 - v1;
+	V3 e2 = v0 - v2;
+	float invArea = q1.w;
+	u = dot(cross(e1, p - v1), n) * invArea;
+	if (u < 0.0f || u > 1.0f) return false;
+	v = dot(cross(e2, p - v2), n) * invArea;
+	if (v < 0.0f || (u + v) > 1.0f) return false;
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// EXACT traversal: BVHNode::traverse (RTBase/Geometry.h:399-427) on the reference's own
+// tree, every node whose box passes, left before right, no culling; stack-free through the
+// pre-order skip links.  Leaf acceptance `t < best && t > EPSILON` (:412).
+// ---------------------------------------------------------------------------------------
+RTB_DEV void closestExact(const DevScene& S, const RayD& r, float eps, HitD& h, uint32_t& nBox, uint32_t& nTri)
+{
+	h.id = RTB_MISS_ID;
+	h.t = FLT_MAX;
+	h.alpha = h.beta = 0.0f;
+	uint32_t i = 0;
+	while (i < S.n_xnodes)
+	{
+		float4 A = ldg4(S.xnodes + 2 * (size_t)i);
+		float4 B = ldg4(S.xnodes + 2 * (size_t)i + 1);
+		float te;
+		nBox++;
+		if (!slabTest(A.x, A.y, A.z, B.x, B.y, B.z, r, te))
+		{
+			i = __float_as_uint(A.w);
+			continue;
+		}
+		uint32_t leaf = __float_as_uint(B.w);
+		if (leaf == RTB_INTERIOR)
+		{
+			i = i + 1;
+			continue;
+		}
+		uint32_t start = leaf >> 2, count = leaf & 3u;
+		for (uint32_t k = 0; k < count; k++)
+		{
+			float t, u, v;
+			nTri++;
+			if (triTest(S.tri, start + k, r, t, u, v))
+			{
+				if (t < h.t && t > eps)
+				{
+					h.t = t, h.id = start + k, h.alpha = u, h.beta = v;
+				}
+			}
+		}
+		i = __float_as_uint(A.w);
+	}
+}
+
+// BVHNode::traverseVisible (RTBase/Geometry.h:435-462): true = nothing in (eps, maxT).
+RTB_DEV bool visibleExact(const DevScene& S, const RayD& r, float eps, float maxT, uint32_t& nBox, uint32_t& nTri)
+{
+	uint32_t i = 0;
+	while (i < S.n_xnodes)
+	{
+		float4 A = ldg4(S.xnodes + 2 * (size_t)i);
+		float4 B = ldg4(S.xnodes + 2 * (size_t)i + 1);
+		float te;
+		nBox++;
+		if (!slabTest(A.x, A.y, A.z, B.x, B.y, B.z, r, te))
+		{
+			i = __float_as_uint(A.w);
+			continue;
+		}
+		uint32_t leaf = __float_as_uint(B.w);
+		if (leaf == RTB_INTERIOR)
+		{
+			i = i + 1;
+			continue;
+		}
+		uint32_t start = leaf >> 2, count = leaf & 3u;
+		for (uint32_t k = 0; k < count; k++)
+		{
+			float t, u, v;
+			nTri++;
+			if (triTest(S.tri, start + k, r, t, u, v))
+			{
+				if (t >= maxT || t <= eps) continue;
+				return false;
+			}
+		}
+		i = __float_as_uint(A.w);
+	}
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// FAST traversal: a different tree over the SAME leaves.  Legal because the
+// reference's result is the lexicographic (t, ID) minimum over the triangles of every leaf
+// whose exact box passes; a leaf box passing implies all its ancestors pass (box nesting +
+// monotone rounding) unless a ray-direction component is 0/denormal (0*inf = NaN can
+// reject an ancestor only) — such rays take the EXACT path.  Every box here, interior or
+// leaf, is tested with the reference's exact slab arithmetic, children are visited
+// near-first and popped nodes are dropped when t_entry - |t_entry|*rel > t_best.
+// ---------------------------------------------------------------------------------------
+#define RTB_STACK 64
+
+RTB_DEV bool rayIsDegenerate(const RayD& r)
+{
+	// an infinite reciprocal: direction component +-0 or so small that 1/d overflows
+	return isinf(r.inv.x) || isinf(r.inv.y) || isinf(r.inv.z);
+}
+
+RTB_DEV void leafClosest(const DevScene& S, int32_t ref, const RayD& r, float eps, HitD& h, uint32_t& nTri)
+{
+	uint32_t leaf = (uint32_t)(~ref);
+	uint32_t start = leaf >> 2, count = leaf & 3u;
+	for (uint32_t k = 0; k < count; k++)
+	{
+		float t, u, v;
+		nTri++;
+		if (triTest(S.tri, start + k, r, t, u, v))
+		{
+			uint32_t id = start + k;
+			if (t > eps && (t < h.t || (t == h.t && id < h.id)))
+			{
+				h.t = t, h.id = id, h.alpha = u, h.beta = v;
+			}
+		}
+	}
+}
+
+RTB_DEV void closestFast(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox,
+                         uint32_t& nTri)
+{
+	if (rayIsDegenerate(r))
+	{
+		closestExact(S, r, eps, h, nBox, nTri);
+		return;
+	}
+	h.id = RTB_MISS_ID;
+	h.t = FLT_MAX;
+	h.alpha = h.beta = 0.0f;
+	if (S.n_xnodes == 0) return;
+	int32_t stackNode[RTB_STACK];
+	float stackT[RTB_STACK];
+	int sp = 0;
+	int32_t cur = S.fast_root;
+	if (cur < 0)
+	{
+		// single-leaf scene: the root box is the leaf box
+		float4 A = ldg4(S.xnodes), B = ldg4(S.xnodes + 1);
+		float te;
+		nBox++;
+		if (slabTest(A.x, A.y, A.z, B.x, B.y, B.z, r, te)) leafClosest(S, cur, r, eps, h, nTri);
+		return;
+	}
+	for (;;)
+	{
+		// cur is an interior node: test both children
+		const float4* nd = S.fnodes + (size_t)cur * 4;
+		float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
+		float t0, t1;
+		nBox += 2;
+		bool h0 = slabTest(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, r, t0);
+		bool h1 = slabTest(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, r, t1);
+		int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
+		// cull against the current best
+		h0 = h0 && !((t0 - fabsf(t0) * cullRel) > h.t);
+		h1 = h1 && !((t1 - fabsf(t1) * cullRel) > h.t);
+		// leaves are intersected immediately (their box test is the exact leaf test)
+		if (h0 && c0 < 0)
+		{
+			leafClosest(S, c0, r, eps, h, nTri);
+			h0 = false;
+		}
+		if (h1 && c1 < 0)
+		{
+			leafClosest(S, c1, r, eps, h, nTri);
+			h1 = false;
+		}
+		if (h0 && h1)
+		{
+			// near child first, far child on the stack
+			bool swap = t1 < t0;
+			int32_t nearC = swap ? c1 : c0, farC = swap ? c0 : c1;
+			float farT = swap ? t0 : t1;
+			if (sp < RTB_STACK)
+			{
+				stackNode[sp] = farC;
+				stackT[sp] = farT;
+				sp++;
+			}
+			cur = nearC;
+			continue;
+		}
+		if (h0)
+		{
+			cur = c0;
+			continue;
+		}
+		if (h1)
+		{
+			cur = c1;
+			continue;
+		}
+		// pop
+		bool found = false;
+		while (sp > 0)
+		{
+			sp--;
+			float te = stackT[sp];
+			if ((te - fabsf(te) * cullRel) > h.t) continue;
+			cur = stackNode[sp];
+			found = true;
+			break;
+		}
+		if (!found) break;
+	}
+}
+
+RTB_DEV bool leafOccludes(const DevScene& S, int32_t ref, const RayD& r, float eps, float maxT, uint32_t& nTri)
+{
+	uint32_t leaf = (uint32_t)(~ref);
+	uint32_t start = leaf >> 2, count = leaf & 3u;
+	for (uint32_t k = 0; k < count; k++)
+	{
+		float t, u, v;
+		nTri++;
+		if (triTest(S.tri, start + k, r, t, u, v))
+		{
+			if (t >= maxT || t <= eps) continue;
+			return true;
+		}
+	}
+	return false;
+}
+
+RTB_DEV bool visibleFast(const DevScene& S, const RayD& r, float eps, float maxT, float cullRel, uint32_t& nBox,
+                         uint32_t& nTri)
+{
+	if (rayIsDegenerate(r)) return visibleExact(S, r, eps, maxT, nBox, nTri);
+	if (S.n_xnodes == 0) return true;
+	int32_t stackNode[RTB_STACK];
+	int sp = 0;
+	int32_t cur = S.fast_root;
+	if (cur < 0)
+	{
+		float4 A = ldg4(S.xnodes), B = ldg4(S.xnodes + 1);
+		float te;
+		nBox++;
+		if (slabTest(A.x, A.y, A.z, B.x, B.y, B.z, r, te)) return !leafOccludes(S, cur, r, eps, maxT, nTri);
+		return true;
+	}
+	for (;;)
+	{
+		const float4* nd = S.fnodes + (size_t)cur * 4;
+		float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
+		float t0, t1;
+		nBox += 2;
+		bool h0 = slabTest(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, r, t0);
+		bool h1 = slabTest(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, r, t1);
+		int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
+		// a box entered at or beyond maxT cannot hold an occluder (t < maxT needed)
+		h0 = h0 && !((t0 - fabsf(t0) * cullRel) >= maxT);
+		h1 = h1 && !((t1 - fabsf(t1) * cullRel) >= maxT);
+		if (h0 && c0 < 0)
+		{
+			if (leafOccludes(S, c0, r, eps, maxT, nTri)) return false;
+			h0 = false;
+		}
+		if (h1 && c1 < 0)
+		{
+			if (leafOccludes(S, c1, r, eps, maxT, nTri)) return false;
+			h1 = false;
+		}
+		if (h0 && h1)
+		{
+			if (sp < RTB_STACK) stackNode[sp++] = c1;
+			cur = c0;
+			continue;
+		}
+		if (h0)
+		{
+			cur = c0;
+			continue;
+		}
+		if (h1)
+		{
+			cur = c1;
+			continue;
+		}
+		if (sp == 0) break;
+		cur = stackNode[--sp];
+	}
+	return true;
+}
+
+template <int TRAV>
+RTB_DEV void closestHit(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox,
+                        uint32_t& nTri)
+{
+	if (TRAV == RTB_TRAV_EXACT) closestExact(S, r, eps, h, nBox, nTri);
+	else closestFast(S, r, eps, cullRel, h, nBox, nTri);
+}
+
+template <int TRAV>
+RTB_DEV bool anyVisible(const DevScene& S, const RayD& r, float eps, float maxT, float cullRel, uint32_t& nBox,
+                        uint32_t& nTri)
+{
+	if (TRAV == RTB_TRAV_EXACT) return visibleExact(S, r, eps, maxT, nBox, nTri);
+	return visibleFast(S, r, eps, maxT, cullRel, nBox, nTri);
+}
+
+// Scene::visible (RTBase/Scene.h:161-169)
+template <int TRAV>
+RTB_DEV bool sceneVisible(const DevScene& S, V3 p1, V3 p2, float eps, float cullRel, uint32_t& nBox, uint32_t& nTri)
+{
+	V3 dir = p2 - p1;
+	float maxT = sqrtf(lengthSq(dir)) - (2.0f * eps);
+	dir = normalize(dir);
+	RayD r = mkRay(p1 + (dir * eps), dir);
+	return anyVisible<TRAV>(S, r, eps, maxT, cullRel, nBox, nTri);
+}
+
+// ---------------------------------------------------------------------------------------
+// Camera::generateRay (RTBase/Scene.h:43-54) with Matrix::mulPoint / mulVec
+// (RTBase/Core.h:295-309).  Must be bit-exact: it feeds the hit-ID gate.
+// ---------------------------------------------------------------------------------------
+RTB_DEV RayD generateRay(const rtb_camera& c, float x, float y)
+{
+	float xprime = x / c.width;
+	float yprime = 1.0f - (y / c.height);
+	xprime = (xprime * 2.0f) - 1.0f;
+	yprime = (yprime * 2.0f) - 1.0f;
+	const float* m = c.inv_proj;
+	V3 d = mk(((xprime * m[0] + yprime * m[1]) + 1.0f * m[2]) + m[3],
+	          ((xprime * m[4] + yprime * m[5]) + 1.0f * m[6]) + m[7],
+	          ((xprime * m[8] + yprime * m[9]) + 1.0f * m[10]) + m[11]);
+	const float* k = c.cam_to_world;
+	V3 w = mk((d.x * k[0] + d.y * k[1]) + d.z * k[2], (d.x * k[4] + d.y * k[5]) + d.z * k[6],
+	          (d.x * k[8] + d.y * k[9]) + d.z * k[10]);
+	w = normalize(w);
+	return mkRay(mk(c.origin), w);
+}
+
+// ---------------------------------------------------------------------------------------
+// ShadingData (RTBase/Materials.h:15-35) + Scene::calculateShadingData (Scene.h:174-203),
+// Triangle::interpolateAttributes / gNormal (Geometry.h:106-112,127-130),
+// Frame::fromVector (Core.h:513-527).
+// ---------------------------------------------------------------------------------------
+struct ShadeD
+{
+	V3 x, wo, sN, gN;
+	float tu, tv;
+	V3 fu, fv, fw;
+	float t;
+	int32_t mat;
+};
+
+RTB_DEV void frameFromVector(V3 n, V3& u, V3& v, V3& w)
+{
+	w = normalize(n);
+	if (fabsf(w.x) > fabsf(w.y))
+	{
+		float l = 1.0f / sqrtf(w.x * w.x + w.z * w.z);
+		u = mk(w.z * l, 0.0f, -w.x * l);
+	}
+	else
+	{
+		float l = 1.0f / sqrtf(w.y * w.y + w.z * w.z);
+		u = mk(0.0f, w.z * l, -w.y * l);
+	}
+	v = cross(w, u);
+}
+RTB_DEV V3 toLocal(const ShadeD& s, V3 a) { return mk(dot(a, s.fu), dot(a, s.fv), dot(a, s.fw)); }
+RTB_DEV V3 toWorld(const ShadeD& s, V3 a) { return ((s.fu * a.x) + (s.fv * a.y)) + (s.fw * a.z); }
+
+RTB_DEV void calcShading(const DevScene& S, uint32_t id, float t, float alpha, float beta, float gamma,
+                         const RayD& r, ShadeD& sd)
+{
+	const float4* qi = S.tri + (size_t)id * 4;
+	const float4* qs = S.tsh + (size_t)id * 4;
+	float4 i2 = ldg4(qi + 2), i3 = ldg4(qi + 3);
+	float4 s0 = ldg4(qs), s1 = ldg4(qs + 1), s2 = ldg4(qs + 2), s3 = ldg4(qs + 3);
+	sd.x = r.o + (r.d * t);
+	sd.gN = mk(i3) * s3.w;
+	V3 nrm = ((mk(s0) * alpha) + (mk(s1) * beta)) + (mk(s2) * gamma);
+	sd.sN = normalize(nrm);
+	sd.tu = (s0.w * alpha + s1.w * beta) + s2.w * gamma;
+	sd.tv = (s3.x * alpha + s3.y * beta) + s3.z * gamma;
+	sd.mat = (int32_t)__float_as_uint(i2.w);
+	sd.wo = -r.d;
+	uint32_t flags = S.mats[sd.mat].flags;
+	if (flags & RTB_MAT_TWO_SIDED)
+	{
+		if (dot(sd.wo, sd.sN) < 0.0f) sd.sN = -sd.sN;
+		if (dot(sd.wo, sd.gN) < 0.0f) sd.gN = -sd.gN;
+	}
+	frameFromVector(sd.sN, sd.fu, sd.fv, sd.fw);
+	sd.t = t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Texture::sample (RTBase/Imaging.h:72-94): software bilinear with wrap, float texels.
+// ---------------------------------------------------------------------------------------
+RTB_DEV V3 texel(const float* __restrict__ texels, uint32_t base, int idx)
+{
+	const float* p = texels + ((size_t)base + (size_t)idx) * 3;
+	return mk(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+RTB_DEV V3 sampleTexture(const DevScene& S, int tex, float tu, float tv)
+{
+	rtb_texture T = S.texs[tex];
+	float u = stdMax(0.0f, fabsf(tu)) * (float)T.width;
+	float v = stdMax(0.0f, fabsf(tv)) * (float)T.height;
+	int x = (int)floorf(u);
+	int y = (int)floorf(v);
+	float fu = u - (float)x;
+	float fv = v - (float)y;
+	float w0 = (1.0f - fu) * (1.0f - fv);
+	float w1 = fu * (1.0f - fv);
+	float w2 = (1.0f - fu) * fv;
+	float w3 = fu * fv;
+	x = x % T.width;
+	y = y % T.height;
+	int x1 = (x + 1) % T.width, y1 = (y + 1) % T.height;
+	V3 a = texel(S.texels, T.offset, y * T.width + x);
+	V3 b = texel(S.texels, T.offset, y * T.width + x1);
+	V3 c = texel(S.texels, T.offset, y1 * T.width + x);
+	V3 d = texel(S.texels, T.offset, y1 * T.width + x1);
+	return (((a * w0) + (b * w1)) + (c * w2)) + (d * w3);
+}
+
+// ---------------------------------------------------------------------------------------
+// SamplingDistributions (RTBase/Sampling.h:29-70) + sphericalToWorld (Core.h:547-550).
+// `2.0f * M_PI * r2` is a double product in the reference; a float product differs by
+// <= 1 ulp of phi, far inside the 1e-5 evaluation tolerance.
+// ---------------------------------------------------------------------------------------
+RTB_DEV V3 sphericalToWorld(float theta, float phi)
+{
+	float st, ct, sp, cp;
+	sincosf(theta, &st, &ct);
+	sincosf(phi, &sp, &cp);
+	return mk(cp * st, sp * st, ct);
+}
+RTB_DEV V3 cosineSampleHemisphere(float r1, float r2)
+{
+	float theta = acosf(sqrtf(r1));
+	float phi = (float)(2.0 * RTB_PI_D * (double)r2);
+	return sphericalToWorld(theta, phi);
+}
+RTB_DEV V3 uniformSampleSphere(float r1, float r2)
+{
+	float theta = acosf(1.0f - 2.0f * r1);
+	float phi = (float)(2.0 * RTB_PI_D * (double)r2);
+	return sphericalToWorld(theta, phi);
+}
+
+// ---------------------------------------------------------------------------------------
+// BSDFs in PARITY mode = what RTBase/Materials.h actually computes:
+//   Diffuse :118, OrenNayar :369, Plastic :414, Conductor :203, Dielectric :320 -> Lambert
+//   Mirror :158, Glass :252 (+ ShadingHelper::fresnelDielectric :55-77); Layered -> base.
+// ---------------------------------------------------------------------------------------
+RTB_DEV V3 bsdfAlbedo(const DevScene& S, const rtb_material& m, const ShadeD& sd)
+{
+	return sampleTexture(S, m.tex, sd.tu, sd.tv);
+}
+
+RTB_DEV V3 bsdfEvaluate(const DevScene& S, const rtb_material& m, const ShadeD& sd, V3 wi)
+{
+	(void)wi;
+	if (m.type == RTB_BSDF_GLASS) return mk(0.0f, 0.0f, 0.0f);     // Materials.h:295-299
+	if (m.type == RTB_BSDF_MIRROR) return bsdfAlbedo(S, m, sd);     // Materials.h:178-183 (sic)
+	return bsdfAlbedo(S, m, sd) / RTB_PI_F;                         // albedo / M_PI
+}
+
+RTB_DEV float bsdfPdf(const rtb_material& m, const ShadeD& sd, V3 wi)
+{
+	if (m.type == RTB_BSDF_GLASS || m.type == RTB_BSDF_MIRROR) return 0.0f;
+	V3 l = toLocal(sd, wi);
+	return (l.z >= 0.0f) ? (float)((double)l.z / RTB_PI_D) : 0.0f; // cosineHemispherePDF, Sampling.h:44-48
+}
+
+// ShadingHelper::fresnelDielectric (Materials.h:55-77), including its non-standard Fpe
+// denominator.  iorInt/iorExt are the CALL's arguments (etaI, etaT at Materials.h:274).
+RTB_DEV float fresnelDielectric(float cosTheta, float iorInt, float iorExt, V3& wt, V3 wol)
+{
+	float ior = iorInt / iorExt;
+	float sinTheta_i = sqrtf(1.0f - (cosTheta * cosTheta));
+	float sinTheta_t = ior * sinTheta_i;
+	float ior2sin2 = (ior * ior) * (1.0f - (cosTheta * cosTheta));
+	if (ior2sin2 > 1.0f) return 1.0f;
+	float cosTheta_t = sqrtf(1.0f - (sinTheta_t * sinTheta_t));
+	wt = mk(-ior * wol.x, -ior * wol.y, -cosTheta_t);
+	float Fpa = (cosTheta - ior * cosTheta_t) / (cosTheta + ior * cosTheta_t);
+	float Fpe = (ior * cosTheta - cosTheta_t) / (ior * cosTheta + ior * cosTheta_t);
+	float average = ((Fpa * Fpa) + (Fpe * Fpe)) * 0.5f;
+	return stdMax(0.0f, stdMin(1.0f, average)); // clamp(), Materials.h:8-11
+}
+
+// BSDF::sample.  r1, r2: the cosine-hemisphere uniforms; r3: glass reflect/refract draw.
+// `usedR3` tells the caller whether the reference would have consumed that draw.
+RTB_DEV V3 bsdfSample(const DevScene& S, const rtb_material& m, const ShadeD& sd, float r1, float r2, float r3,
+                      V3& f, float& pdf)
+{
+	if (m.type == RTB_BSDF_MIRROR) // Materials.h:167-177
+	{
+		V3 wol = toLocal(sd, sd.wo);
+		V3 wi = mk(-wol.x, -wol.y, wol.z);
+		pdf = 1.0f;
+		f = bsdfAlbedo(S, m, sd);
+		return toWorld(sd, wi);
+	}
+	if (m.type == RTB_BSDF_GLASS) // Materials.h:265-294
+	{
+		V3 wol = toLocal(sd, sd.wo);
+		float cosTheta_i = fabsf(wol.z);
+		bool enter = wol.z > 0.0f;
+		float etaI = enter ? m.ext_ior : m.int_ior;
+		float etaT = enter ? m.int_ior : m.ext_ior;
+		V3 wt = mk(0.0f, 0.0f, 0.0f); // Vec3() default (w = 1 is unused)
+		float R = fresnelDielectric(cosTheta_i, etaI, etaT, wt, wol);
+		if (!enter) wt.z = -wt.z;
+		bool reflect = (R == 1.0f) || (r3 < R);
+		V3 a = bsdfAlbedo(S, m, sd);
+		V3 wi;
+		if (reflect)
+		{
+			wi = mk(-wol.x, -wol.y, wol.z);
+			pdf = R;
+			f = a * R;
+		}
+		else
+		{
+			wi = wt;
+			pdf = 1.0f - R;
+			f = a * (1.0f - R);
+		}
+		return toWorld(sd, wi);
+	}
+	// Lambert-like stubs.  DiffuseBSDF clamps the pdf (Materials.h:130), the others use
+	// pdf = wi.z / M_PI un-clamped (:222, :339, :384, :437).
+	V3 wl = cosineSampleHemisphere(r1, r2);
+	float p = (float)((double)wl.z / RTB_PI_D);
+	if (m.type == RTB_BSDF_DIFFUSE && !(wl.z >= 0.0f)) p = 0.0f;
+	pdf = p;
+	f = bsdfAlbedo(S, m, sd) / RTB_PI_F;
+	return toWorld(sd, wl);
+}
+
+// ---------------------------------------------------------------------------------------
+// Lights (RTBase/Lights.h).  EnvironmentMap::evaluate :158-165; BackgroundColour :84-133;
+// AreaLight :30-82 with Triangle::sample (Geometry.h:114-126).
+// ---------------------------------------------------------------------------------------
+RTB_DEV V3 envLookup(const DevScene& S, int tex, V3 wi)
+{
+	float u = atan2f(wi.z, wi.x);
+	u = (u < 0.0f) ? (float)((double)u + (2.0 * RTB_PI_D)) : u;
+	u = (float)((double)u / (2.0 * RTB_PI_D));
+	float v = (float)((double)acosf(wi.y) / RTB_PI_D);
+	return sampleTexture(S, tex, u, v);
+}
+// Scene::background->evaluate(dir)
+RTB_DEV V3 backgroundEval(const DevScene& S, V3 wi)
+{
+	if (S.bg_type == RTB_LIGHT_ENVMAP) return envLookup(S, S.bg_tex, wi);
+	return mk(S.bg_colour);
+}
+RTB_DEV V3 trianglePoint(const DevScene& S, uint32_t id, float r1, float r2)
+{
+	const float4* q = S.tri + (size_t)id * 4;
+	V3 v0 = mk(ldg4(q)), v1 = mk(ldg4(q + 1)), v2 = mk(ldg4(q + 2));
+	float sr = sqrtf(r1);
+	float alpha = 1.0f - sr;
+	float beta = r2 * sr;
+	float gamma = 1.0f - (alpha + beta);
+	return ((v0 * alpha) + (v1 * beta)) + (v2 * gamma);
+}
+RTB_DEV V3 triangleGNormal(const DevScene& S, uint32_t id)
+{
+	float4 n = ldg4(S.tri + (size_t)id * 4 + 3);
+	float gs = ldg4(S.tsh + (size_t)id * 4 + 3).w;
+	return mk(n) * gs;
+}
+
+// ---------------------------------------------------------------------------------------
+// Counter-based RNG (replaces MTRandom, RTBase/Sampling.h:13-26): Philox-4x32-10
+// (Salmon et al. 2011).  counter = (pixel, sample, block, 0), key = (seed, "RTB2").
+// One block = 4 uniforms; a path vertex at depth k uses blocks 2k and 2k+1:
+//   block 2k   : [0] light pick  [1],[2] light sample  [3] Russian roulette
+//   block 2k+1 : [0],[1] BSDF (r1, r2)  [2] glass reflect/refract  [3] unused
+// Uniforms lie strictly inside (0,1): ((x >> 9) + 0.5) * 2^-23.
+// ---------------------------------------------------------------------------------------
+RTB_DEV uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+	for (int i = 0; i < 10; i++)
+	{
+		uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+		uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+		c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	return c;
+}
+RTB_DEV float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-7f; }
+RTB_DEV float4 rngBlock(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t block)
+{
+	uint4 r = philox4x32_10(make_uint4(pixel, sample, block, 0u), seed, 0x52544232u);
+	return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}

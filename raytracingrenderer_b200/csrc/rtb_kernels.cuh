@@ -1,0 +1,530 @@
+// rtb_kernels.cuh — the kernels of librtb200.so (sm_100a).  Launch wrappers live in
+// rtb_api.cu.  Hot path: k_render (RayTracer::render -> renderTile -> pathTrace /
+// computeDirect -> Scene::traverse / visible -> Film::splat, RTBase/Renderer.h:328-473,
+// 795-885).  The rest are the batched parity entry points of include/rtb.h.
+#pragma once
+#include "rtb_dev_scene.cuh"
+
+struct RenderArgs
+{
+	float* film;                   // width*height*3 running sums (Film::film)
+	unsigned long long* counters;  // [0] samples [1] closest rays [2] shadow rays [3] box tests [4] tri tests
+	uint32_t spp_begin, spp_count;
+	uint32_t width, height;
+	rtb_params P;
+};
+
+struct Tally
+{
+	uint32_t samples, closest, shadow, box, tri;
+};
+
+RTB_DEV void flushTally(const Tally& c, unsigned long long* counters)
+{
+	uint32_t v[5] = {c.samples, c.closest, c.shadow, c.box, c.tri};
+#pragma unroll
+	for (int k = 0; k < 5; k++)
+	{
+		uint32_t x = v[k];
+		for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+		if ((threadIdx.x & 31) == 0 && x) atomicAdd(&counters[k], (unsigned long long)x);
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// RayTracer::computeDirect (RTBase/Renderer.h:423-473) with Scene::sampleLight
+// (Scene.h:131-140).  u = (light pick, r1, r2).
+// ---------------------------------------------------------------------------------------
+template <int TRAV>
+RTB_DEV V3 computeDirect(const DevScene& S, const rtb_params& P, const ShadeD& sd, const rtb_material& m, float uPick,
+                         float r1, float r2, Tally& tl)
+{
+	V3 zero = mk(0.0f, 0.0f, 0.0f);
+	if (m.flags & RTB_MAT_SPECULAR) return zero;
+	if (S.n_lights == 0) return zero; // the reference would divide by zero here (Scene.h:137)
+	float nl = (float)S.n_lights;
+	float pmf = 1.0f / nl;
+	int li = (int)(nl * uPick);
+	if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+	rtb_light L = S.lights[li];
+	if (L.type == RTB_LIGHT_AREA)
+	{
+		V3 p = trianglePoint(S, L.triangle, r1, r2);
+		float pdf = 1.0f / L.area;
+		V3 wi = p - sd.x;
+		float l = lengthSq(wi);
+		wi = normalize(wi);
+		V3 nL = triangleGNormal(S, L.triangle);
+		float G = (selMax(dot(wi, sd.sN), 0.0f) * selMax(-dot(wi, nL), 0.0f)) / l;
+		if (G > 0.0f)
+		{
+			tl.shadow++;
+			if (sceneVisible<TRAV>(S, sd.x, p, P.epsilon, P.cull_rel, tl.box, tl.tri))
+			{
+				return ((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G) / (pmf * pdf);
+			}
+		}
+		return zero;
+	}
+	// BackgroundColour / EnvironmentMap: a direction (Lights.h:89-95, 143-149)
+	V3 wi;
+	V3 emitted;
+	float pdf;
+	if (L.type == RTB_LIGHT_ENVMAP && P.sampling == RTB_SAMPLING_IMPORTANCE && S.env_marginal != nullptr)
+	{
+		// Expectation-preserving replacement of the uniform-sphere draw:
+		// pick a texel by luminance*sin(theta), then a uniform point inside it.
+		int W = S.env_w, H = S.env_h;
+		// row: largest r with marginal[r] <= r1
+		int lo = 0, hi = H;
+		while (hi - lo > 1)
+		{
+			int mid = (lo + hi) >> 1;
+			if (__ldg(S.env_marginal + mid) <= r1) lo = mid;
+			else hi = mid;
+		}
+		int row = lo;
+		float m0 = __ldg(S.env_marginal + row), m1 = __ldg(S.env_marginal + row + 1);
+		float fr = (m1 > m0) ? (r1 - m0) / (m1 - m0) : 0.5f;
+		const float* cd = S.env_cond + (size_t)row * (W + 1);
+		lo = 0, hi = W;
+		while (hi - lo > 1)
+		{
+			int mid = (lo + hi) >> 1;
+			if (__ldg(cd + mid) <= r2) lo = mid;
+			else hi = mid;
+		}
+		int col = lo;
+		float c0 = __ldg(cd + col), c1 = __ldg(cd + col + 1);
+		float fc = (c1 > c0) ? (r2 - c0) / (c1 - c0) : 0.5f;
+		float v = ((float)row + fr) / (float)H; // = theta / pi
+		float u = ((float)col + fc) / (float)W; // = phi / 2pi
+		float theta = v * RTB_PI_F, phi = u * (2.0f * RTB_PI_F);
+		float st, ct, sp, cp;
+		sincosf(theta, &st, &ct);
+		sincosf(phi, &sp, &cp);
+		wi = mk(cp * st, ct, sp * st); // inverse of EnvironmentMap::evaluate's (u,v) mapping
+		float pmfTexel = (m1 - m0) * (c1 - c0);
+		// texel solid angle ~ (2pi/W)(pi/H) sin(theta)
+		pdf = pmfTexel * ((float)W * (float)H) / (2.0f * RTB_PI_F * RTB_PI_F * fmaxf(st, 1e-8f));
+		emitted = envLookup(S, L.tex, wi);
+		if (!(pdf > 0.0f)) return zero;
+	}
+	else
+	{
+		wi = uniformSampleSphere(r1, r2);
+		pdf = (float)(1.0 / (4.0 * RTB_PI_D));
+		emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
+	}
+	float G = selMax(dot(wi, sd.sN), 0.0f);
+	if (G > 0.0f)
+	{
+		tl.shadow++;
+		if (sceneVisible<TRAV>(S, sd.x, sd.x + (wi * 10000.0f), P.epsilon, P.cull_rel, tl.box, tl.tri))
+		{
+			return ((bsdfEvaluate(S, m, sd, wi) * emitted) * G) / (pmf * pdf);
+		}
+	}
+	return zero;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_render: one thread per pixel (a warp = an 8x4 pixel tile); each thread runs its pixel's
+// samples back to back, so a lane whose path ends early immediately regenerates the next
+// sample instead of idling ("path regeneration").  The pixel's colour is summed in
+// registers and added to the film once: Film::splat with BoxFilter, size() == 0
+// (RTBase/Imaging.h:139-154, 209-232) without atomics.
+//
+// INTEGRATOR: rtb_integrator.  pathTrace's recursion (Renderer.h:328-392) is unrolled into
+// the loop below; SURVEY A.6 lists the estimator's quirks that are reproduced on purpose:
+// the miss term is NOT weighted by the throughput, emitters count only after a specular
+// bounce (or at depth 0), Russian roulette from depth 0 with p = min(Lum(T), 0.9).
+// ---------------------------------------------------------------------------------------
+template <int TRAV, int INTEGRATOR>
+__global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A)
+{
+	const rtb_params& P = A.P;
+	uint32_t lane = threadIdx.x & 31u;
+	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t tilesX = (A.width + 7u) >> 3, tilesY = (A.height + 3u) >> 2;
+	Tally tl = {0, 0, 0, 0, 0};
+	if (warp < tilesX * tilesY)
+	{
+		uint32_t px = (warp % tilesX) * 8u + (lane & 7u);
+		uint32_t py = (warp / tilesX) * 4u + (lane >> 3);
+		bool valid = px < A.width && py < A.height;
+		uint32_t sBegin = A.spp_begin, sEnd = A.spp_begin + A.spp_count, sStep = 1;
+		if (P.partition == RTB_PART_TILE && P.part_world > 1)
+		{
+			// TILE_SIZE = 32 (Renderer.h:18), tiles dealt round-robin in row-major order
+			uint32_t t32x = (A.width + 31u) >> 5;
+			uint32_t tile = (py >> 5) * t32x + (px >> 5);
+			valid = valid && ((int)(tile % (uint32_t)P.part_world) == P.part_rank);
+		}
+		else if (P.partition == RTB_PART_SPP && P.part_world > 1)
+		{
+			uint32_t w = (uint32_t)P.part_world, r = (uint32_t)P.part_rank;
+			sBegin += (r + w - (sBegin % w)) % w;
+			sStep = w;
+		}
+		if (valid)
+		{
+			uint32_t pixel = py * A.width + px;
+			RayD primary = generateRay(S.cam, (float)px + 0.5f, (float)py + 0.5f);
+			V3 acc = mk(0.0f, 0.0f, 0.0f);
+			uint32_t s = sBegin, curS = 0;
+			bool alive = false;
+			RayD ray = primary;
+			V3 T = mk(1.0f, 1.0f, 1.0f), Lo = mk(0.0f, 0.0f, 0.0f);
+			int depth = 0;
+			bool canHitLight = true;
+			for (;;)
+			{
+				if (!alive)
+				{
+					if (s >= sEnd) break;
+					curS = s;
+					s += sStep;
+					ray = primary;
+					T = mk(1.0f, 1.0f, 1.0f);
+					Lo = mk(0.0f, 0.0f, 0.0f);
+					depth = 0;
+					canHitLight = true;
+					alive = true;
+				}
+				HitD h;
+				closestHit<TRAV>(S, ray, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+				tl.closest++;
+				bool done = true;
+				if (h.id == RTB_MISS_ID)
+				{
+					if (INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_ALBEDO)
+						Lo = Lo + backgroundEval(S, ray.d); // un-weighted (Renderer.h:390)
+				}
+				else
+				{
+					ShadeD sd;
+					calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), ray, sd);
+					if (INTEGRATOR == RTB_INT_NORMALS)
+					{
+						Lo = mk(fabsf(sd.sN.x), fabsf(sd.sN.y), fabsf(sd.sN.z)); // Renderer.h:572-581
+					}
+					else
+					{
+						rtb_material m = S.mats[sd.mat];
+						if (m.flags & RTB_MAT_LIGHT)
+						{
+							if (INTEGRATOR == RTB_INT_PATH)
+							{
+								if (canHitLight) Lo = Lo + (T * mk(m.emission));
+							}
+							else
+								Lo = mk(m.emission);
+						}
+						else if (INTEGRATOR == RTB_INT_ALBEDO)
+						{
+							Lo = bsdfEvaluate(S, m, sd, mk(0.0f, 1.0f, 0.0f)); // Renderer.h:558-571
+						}
+						else
+						{
+							float4 ua = rngBlock(P.seed, pixel, curS, 2u * (uint32_t)depth);
+							V3 direct = computeDirect<TRAV>(S, P, sd, m, ua.x, ua.y, ua.z, tl);
+							if (INTEGRATOR == RTB_INT_DIRECT)
+							{
+								Lo = direct; // Renderer.h:393-407
+							}
+							else
+							{
+								Lo = Lo + (T * direct);
+								if (!(depth > P.max_depth))
+								{
+									float rr = selMin(lum(T), P.rr_cap); // Renderer.h:353
+									if (ua.w < rr)
+									{
+										T = T / rr;
+										float4 ub = rngBlock(P.seed, pixel, curS, 2u * (uint32_t)depth + 1u);
+										V3 f;
+										float pdf;
+										V3 wi = bsdfSample(S, m, sd, ub.x, ub.y, ub.z, f, pdf);
+										bool spec = (m.flags & RTB_MAT_SPECULAR) != 0;
+										if (spec) T = (T * f) / pdf;
+										else T = ((T * f) * fabsf(dot(wi, sd.sN))) / pdf;
+										ray = mkRay(sd.x + (wi * P.epsilon), wi);
+										canHitLight = spec;
+										depth++;
+										done = false;
+									}
+								}
+							}
+						}
+					}
+				}
+				if (done)
+				{
+					acc = acc + Lo;
+					tl.samples++;
+					alive = false;
+				}
+			}
+			float* f = A.film + (size_t)pixel * 3;
+			f[0] += acc.x;
+			f[1] += acc.y;
+			f[2] += acc.z;
+		}
+	}
+	flushTally(tl, A.counters);
+}
+
+// ---------------------------------------------------------------------------------------
+// Parity kernels
+// ---------------------------------------------------------------------------------------
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_primary(const __grid_constant__ DevScene S, float eps, float cull,
+                                                 uint32_t width, uint32_t height, uint32_t* ids, float* ts,
+                                                 rtb_ray* rays, unsigned long long* counters)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	Tally tl = {0, 0, 0, 0, 0};
+	if (i < width * height)
+	{
+		uint32_t px = i % width, py = i / width;
+		RayD r = generateRay(S.cam, (float)px + 0.5f, (float)py + 0.5f);
+		HitD h;
+		closestHit<TRAV>(S, r, eps, cull, h, tl.box, tl.tri);
+		tl.closest++;
+		if (ids) ids[i] = h.id;
+		if (ts) ts[i] = h.t;
+		if (rays)
+		{
+			rtb_ray o;
+			o.o[0] = r.o.x, o.o[1] = r.o.y, o.o[2] = r.o.z, o.tmax = FLT_MAX;
+			o.d[0] = r.d.x, o.d[1] = r.d.y, o.d[2] = r.d.z, o.pad_ = 0.0f;
+			rays[i] = o;
+		}
+	}
+	flushTally(tl, counters);
+}
+
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DevScene S, float eps, float cull, int anyHit,
+                                               const rtb_ray* __restrict__ rays, uint64_t n, rtb_hit* hits,
+                                               unsigned long long* counters)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	Tally tl = {0, 0, 0, 0, 0};
+	if (i < n)
+	{
+		rtb_ray q = rays[i];
+		RayD r = mkRay(mk(q.o), mk(q.d));
+		rtb_hit o;
+		if (anyHit)
+		{
+			bool vis = anyVisible<TRAV>(S, r, eps, q.tmax, cull, tl.box, tl.tri);
+			tl.shadow++;
+			o.id = vis ? 0u : 1u;
+			o.t = o.alpha = o.beta = o.gamma = 0.0f;
+		}
+		else
+		{
+			HitD h;
+			closestHit<TRAV>(S, r, eps, cull, h, tl.box, tl.tri);
+			tl.closest++;
+			o.id = h.id, o.t = h.t;
+			if (h.id == RTB_MISS_ID) o.alpha = o.beta = o.gamma = 0.0f;
+			else o.alpha = h.alpha, o.beta = h.beta, o.gamma = 1.0f - (h.alpha + h.beta);
+		}
+		hits[i] = o;
+	}
+	flushTally(tl, counters);
+}
+
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_visible(const __grid_constant__ DevScene S, float eps, float cull,
+                                                 const float* __restrict__ p1p2, uint64_t n, uint8_t* out,
+                                                 unsigned long long* counters)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	Tally tl = {0, 0, 0, 0, 0};
+	if (i < n)
+	{
+		const float* p = p1p2 + i * 6;
+		bool vis = sceneVisible<TRAV>(S, mk(p), mk(p + 3), eps, cull, tl.box, tl.tri);
+		tl.shadow++;
+		out[i] = vis ? 1 : 0;
+	}
+	flushTally(tl, counters);
+}
+
+RTB_DEV void storeShading(const ShadeD& sd, rtb_shading& o)
+{
+	o.x[0] = sd.x.x, o.x[1] = sd.x.y, o.x[2] = sd.x.z;
+	o.wo[0] = sd.wo.x, o.wo[1] = sd.wo.y, o.wo[2] = sd.wo.z;
+	o.s_normal[0] = sd.sN.x, o.s_normal[1] = sd.sN.y, o.s_normal[2] = sd.sN.z;
+	o.g_normal[0] = sd.gN.x, o.g_normal[1] = sd.gN.y, o.g_normal[2] = sd.gN.z;
+	o.tu = sd.tu, o.tv = sd.tv;
+	o.frame_u[0] = sd.fu.x, o.frame_u[1] = sd.fu.y, o.frame_u[2] = sd.fu.z;
+	o.frame_v[0] = sd.fv.x, o.frame_v[1] = sd.fv.y, o.frame_v[2] = sd.fv.z;
+	o.frame_w[0] = sd.fw.x, o.frame_w[1] = sd.fw.y, o.frame_w[2] = sd.fw.z;
+	o.t = sd.t;
+	o.material = sd.mat;
+}
+RTB_DEV void loadShading(const rtb_shading& o, ShadeD& sd)
+{
+	sd.x = mk(o.x), sd.wo = mk(o.wo), sd.sN = mk(o.s_normal), sd.gN = mk(o.g_normal);
+	sd.tu = o.tu, sd.tv = o.tv;
+	sd.fu = mk(o.frame_u), sd.fv = mk(o.frame_v), sd.fw = mk(o.frame_w);
+	sd.t = o.t, sd.mat = o.material;
+}
+
+__global__ void __launch_bounds__(128) k_shading(const __grid_constant__ DevScene S, const rtb_ray* __restrict__ rays,
+                                                 const rtb_hit* __restrict__ hits, uint64_t n, rtb_shading* out)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	rtb_ray q = rays[i];
+	rtb_hit h = hits[i];
+	RayD r = mkRay(mk(q.o), mk(q.d));
+	rtb_shading o;
+	memset(&o, 0, sizeof(o));
+	if (h.t < FLT_MAX && h.id < S.n_tris)
+	{
+		ShadeD sd;
+		calcShading(S, h.id, h.t, h.alpha, h.beta, h.gamma, r, sd);
+		storeShading(sd, o);
+	}
+	else
+	{
+		// Scene.h:197-201: only wo and t are set on a miss
+		V3 wo = -r.d;
+		o.wo[0] = wo.x, o.wo[1] = wo.y, o.wo[2] = wo.z;
+		o.t = h.t;
+		o.material = -1;
+	}
+	out[i] = o;
+}
+
+__global__ void __launch_bounds__(128) k_eval_bsdf(const __grid_constant__ DevScene S,
+                                                   const rtb_shading* __restrict__ sds, const float* __restrict__ wi,
+                                                   const float* __restrict__ u, uint64_t n, float* eval, float* pdf,
+                                                   float* sWi, float* sF, float* sPdf)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	ShadeD sd;
+	loadShading(sds[i], sd);
+	if (sd.mat < 0 || (uint32_t)sd.mat >= S.n_mats) return;
+	rtb_material m = S.mats[sd.mat];
+	V3 w = mk(wi + i * 3);
+	if (eval)
+	{
+		V3 e = bsdfEvaluate(S, m, sd, w);
+		eval[i * 3] = e.x, eval[i * 3 + 1] = e.y, eval[i * 3 + 2] = e.z;
+	}
+	if (pdf) pdf[i] = bsdfPdf(m, sd, w);
+	if (sWi || sF || sPdf)
+	{
+		V3 f;
+		float p;
+		V3 d = bsdfSample(S, m, sd, u[i * 3], u[i * 3 + 1], u[i * 3 + 2], f, p);
+		if (sWi) sWi[i * 3] = d.x, sWi[i * 3 + 1] = d.y, sWi[i * 3 + 2] = d.z;
+		if (sF) sF[i * 3] = f.x, sF[i * 3 + 1] = f.y, sF[i * 3 + 2] = f.z;
+		if (sPdf) sPdf[i] = p;
+	}
+}
+
+// Light::sample / Light::evaluate (RTBase/Lights.h:35-48, 89-100, 143-166), STRICT sampling.
+__global__ void __launch_bounds__(128) k_eval_light(const __grid_constant__ DevScene S,
+                                                    const int32_t* __restrict__ light, const float* __restrict__ wi,
+                                                    const float* __restrict__ u, uint64_t n, float* pOrWi,
+                                                    float* emitted, float* pdf, float* eval)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int li = light[i];
+	if (li < 0 || (uint32_t)li >= S.n_lights) return;
+	rtb_light L = S.lights[li];
+	V3 w = mk(wi + i * 3);
+	V3 p, e, ev;
+	float pd;
+	if (L.type == RTB_LIGHT_AREA)
+	{
+		p = trianglePoint(S, L.triangle, u[i * 2], u[i * 2 + 1]);
+		pd = 1.0f / L.area;
+		e = mk(L.emission);
+		ev = (dot(w, triangleGNormal(S, L.triangle)) < 0.0f) ? mk(L.emission) : mk(0.0f, 0.0f, 0.0f);
+	}
+	else
+	{
+		p = uniformSampleSphere(u[i * 2], u[i * 2 + 1]);
+		pd = (float)(1.0 / (4.0 * RTB_PI_D));
+		e = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, p) : mk(L.emission);
+		ev = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, w) : mk(L.emission);
+	}
+	if (pOrWi) pOrWi[i * 3] = p.x, pOrWi[i * 3 + 1] = p.y, pOrWi[i * 3 + 2] = p.z;
+	if (emitted) emitted[i * 3] = e.x, emitted[i * 3 + 1] = e.y, emitted[i * 3 + 2] = e.z;
+	if (pdf) pdf[i] = pd;
+	if (eval) eval[i * 3] = ev.x, eval[i * 3 + 1] = ev.y, eval[i * 3 + 2] = ev.z;
+}
+
+__global__ void k_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out)
+{
+	uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b * 4 >= n) return;
+	float4 r = rngBlock(seed, pixel, sample, b);
+	float v[4] = {r.x, r.y, r.z, r.w};
+	for (int k = 0; k < 4; k++)
+		if (b * 4 + k < n) out[b * 4 + k] = v[k];
+}
+
+// Film::tonemap (RTBase/Imaging.h:233-242): pixel = film * exposure / SPP;
+// c8 = min(powf(max(c, 0), 1/2.2f) * 255, 255).
+__global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ film, uint32_t nPixels, float spp,
+                                                 float exposure, uint8_t* out)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nPixels * 3) return;
+	float c = (film[i] * exposure) / spp;
+	float v = powf(stdMax(c, 0.0f), 1.0f / 2.2f) * 255.0f;
+	out[i] = (uint8_t)stdMin(v, 255.0f);
+}
+
+// GaussianFilter splat (RTBase/Imaging.h:155-187, 209-232) applied to the accumulated box
+// film.  Samples sit at pixel centres and filter(j, i) receives integer tap offsets, so the
+// splat of every sample of source pixel p is the same (2*size+1)^2 stencil normalised by
+// the sum of p's in-bounds taps: linear in the per-pixel sums.
+__global__ void __launch_bounds__(256) k_gaussian(const float* __restrict__ box, float* out, int width, int height,
+                                                  int size, float radius, float alpha)
+{
+	int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= width * height) return;
+	int qx = q % width, qy = q / width;
+	float g[5];
+	// GaussianFilter::Gaussian (Imaging.h:176-180): exp() on floats is the float overload
+	float er = expf(-alpha * (radius * radius));
+	for (int d = -size; d <= size; d++) g[d + size] = expf(-alpha * ((float)d * (float)d)) - er;
+	float r = 0.0f, gg = 0.0f, b = 0.0f;
+	for (int i = -size; i <= size; i++)
+	{
+		int sy = qy - i; // source row whose tap offset i lands on qy
+		if (sy < 0 || sy >= height) continue;
+		for (int j = -size; j <= size; j++)
+		{
+			int sx = qx - j;
+			if (sx < 0 || sx >= width) continue;
+			// total weight of source (sx, sy): its in-bounds taps, in the reference's loop order
+			float total = 0.0f;
+			for (int ii = -size; ii <= size; ii++)
+				for (int jj = -size; jj <= size; jj++)
+				{
+					int tx = sx + jj, ty = sy + ii;
+					if (tx >= 0 && tx < width && ty >= 0 && ty < height) total += g[jj + size] * g[ii + size];
+				}
+			float w = g[j + size] * g[i + size];
+			const float* s = box + ((size_t)sy * width + sx) * 3;
+			r += (s[0] * w) / total;
+			gg += (s[1] * w) / total;
+			b += (s[2] * w) / total;
+		}
+	}
+	out[(size_t)q * 3] = r, out[(size_t)q * 3 + 1] = gg, out[(size_t)q * 3 + 2] = b;
+}
