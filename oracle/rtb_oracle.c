@@ -1,0 +1,883 @@
+/*
+ * TEST INFRASTRUCTURE (oracle/): plain-C restatement of the reference's path-tracing hot
+ * path on the flat scene arrays of include/rtb.h.  It is the CHECKER for the CUDA path in
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg; the product never links,
+ * loads or calls it.
+ *
+ * Pinned (tests/test_oracle_cpu.py) against the reference itself — oracle/_ref/librtref.so,
+ * the unmodified RTBase headers compiled headless — and against the committed fixtures in
+ * tests/golden/: primary hit IDs and t bit-exact on all bundled scenes, shading data /
+ * BSDF / light vectors within 1e-5 relative, rendered films statistically.
+ *
+ * Each function cites the reference code it follows (paths relative to
+ * /root/reference/RTBase).  Build: gcc -O2 -ffp-contract=off (never -ffast-math): the hit
+ * decisions must round like the reference's g++ -ffp-contract=off build.
+ *
+ * One deliberate difference from the reference: MTRandom (Sampling.h:13-26) is replaced by
+ * the counter-based Philox-4x32-10 stream the CUDA kernels use, keyed by (seed, pixel,
+ * sample) with the fixed dimension layout documented at rng_block() — so a pixel's value
+ * does not depend on thread scheduling and GPU and oracle consume identical uniforms.
+ */
+#include "../include/rtb.h"
+
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float x, y, z; } v3;
+
+static v3 V(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+static v3 Vp(const float* p) { return V(p[0], p[1], p[2]); }
+static v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }            /* Core.h:128 */
+static v3 sub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }            /* Core.h:132 */
+static v3 mul(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }            /* Core.h:57,144 */
+static v3 scl(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }               /* Core.h:136 */
+static v3 dvd(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }               /* Core.h:81 */
+static v3 neg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static float dot3(v3 a, v3 b) { return ((a.x * b.x) + (a.y * b.y)) + (a.z * b.z); } /* Core.h:176 */
+static v3 cross3(v3 a, v3 b)                                                        /* Core.h:170 */
+{
+	return V((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x));
+}
+static v3 norm3(v3 a)                                                               /* Core.h:161 */
+{
+	float l = 1.0f / sqrtf(((a.x * a.x) + (a.y * a.y)) + (a.z * a.z));
+	return V(a.x * l, a.y * l, a.z * l);
+}
+static float lum3(v3 c) { return ((0.2126f * c.x) + (0.7152f * c.y)) + (0.0722f * c.z); } /* Core.h:89 */
+static float std_max(float a, float b) { return (a < b) ? b : a; }
+static float std_min(float a, float b) { return (b < a) ? b : a; }
+static float win_max(float a, float b) { return (a > b) ? a : b; } /* Windows max() / Core.h:187 Max */
+static float win_min(float a, float b) { return (a < b) ? a : b; } /* Windows min() / Core.h:192 Min */
+
+typedef struct { v3 o, d, inv; } ray_t;
+static ray_t make_ray(v3 o, v3 d) /* Geometry.h:21-26 */
+{
+	ray_t r;
+	r.o = o;
+	r.d = d;
+	r.inv = V(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	return r;
+}
+
+typedef struct {
+	uint64_t closest, shadow, samples;
+} tally_t;
+
+/* ---------------- Camera::generateRay, Scene.h:43-54; Core.h:295-309 ------------------ */
+static ray_t generate_ray(const rtb_camera* c, float x, float y)
+{
+	float xprime = x / c->width;
+	float yprime = 1.0f - (y / c->height);
+	const float* m = c->inv_proj;
+	const float* k = c->cam_to_world;
+	v3 d, w;
+	xprime = (xprime * 2.0f) - 1.0f;
+	yprime = (yprime * 2.0f) - 1.0f;
+	d.x = (xprime * m[0] + yprime * m[1] + 1.0f * m[2]) + m[3];
+	d.y = (xprime * m[4] + yprime * m[5] + 1.0f * m[6]) + m[7];
+	d.z = (xprime * m[8] + yprime * m[9] + 1.0f * m[10]) + m[11];
+	w.x = (d.x * k[0] + d.y * k[1] + d.z * k[2]);
+	w.y = (d.x * k[4] + d.y * k[5] + d.z * k[6]);
+	w.z = (d.x * k[8] + d.y * k[9] + d.z * k[10]);
+	return make_ray(Vp(c->origin), norm3(w));
+}
+
+/* ---------------- AABB::rayAABB, Geometry.h:173-184 ----------------------------------- */
+static int ray_aabb(const rtb_ref_node* n, const ray_t* r)
+{
+	v3 tmin = mul(sub(Vp(n->bmin), r->o), r->inv);
+	v3 tmax = mul(sub(Vp(n->bmax), r->o), r->inv);
+	v3 en = V(win_min(tmin.x, tmax.x), win_min(tmin.y, tmax.y), win_min(tmin.z, tmax.z));
+	v3 ex = V(win_max(tmin.x, tmax.x), win_max(tmin.y, tmax.y), win_max(tmin.z, tmax.z));
+	float t_entry = std_max(std_max(en.x, en.y), en.z);
+	float t_exit = std_min(std_min(ex.x, ex.y), ex.z);
+	if (t_exit < t_entry || t_exit < 0) return 0;
+	return 1;
+}
+
+/* ---------------- Triangle::rayIntersect, Geometry.h:89-105 --------------------------- */
+static int tri_intersect(const rtb_tri_isect* q, const ray_t* r, float* t, float* u, float* v)
+{
+	v3 n = Vp(q->n), v0 = Vp(q->v0), v1 = Vp(q->v1), v2 = Vp(q->v2);
+	v3 e1 = sub(v2, v1), e2 = sub(v0, v2), p;
+	float denom = dot3(n, r->d);
+	if (denom == 0) return 0;
+	*t = (q->d - dot3(n, r->o)) / denom;
+	if (*t < 0) return 0;
+	p = add(r->o, scl(r->d, *t));
+	*u = dot3(cross3(e1, sub(p, v1)), n) * q->inv_area;
+	if (*u < 0 || *u > 1.0f) return 0;
+	*v = dot3(cross3(e2, sub(p, v2)), n) * q->inv_area;
+	if (*v < 0 || (*u + *v) > 1.0f) return 0;
+	return 1;
+}
+
+/* ---------------- BVHNode::traverse, Geometry.h:399-427 (recursive, exhaustive) -------- */
+static void bvh_traverse(const rtb_scene_desc* s, int32_t node, const ray_t* r, float eps, rtb_hit* best)
+{
+	const rtb_ref_node* n = &s->ref_nodes[node];
+	if (!ray_aabb(n, r)) return;
+	if (n->a < 0)
+	{
+		int32_t start = ~n->a, end = start + n->b, i;
+		for (i = start; i < end; i++)
+		{
+			float t, u, v;
+			if (tri_intersect(&s->tri_isect[i], r, &t, &u, &v))
+			{
+				if (t < best->t && t > eps)
+				{
+					best->t = t;
+					best->id = (uint32_t)i;
+					best->alpha = u;
+					best->beta = v;
+					best->gamma = 1.0f - (u + v);
+				}
+			}
+		}
+		return;
+	}
+	bvh_traverse(s, n->a, r, eps, best);
+	bvh_traverse(s, n->b, r, eps, best);
+}
+
+static rtb_hit scene_traverse(const rtb_scene_desc* s, const ray_t* r, float eps) /* Scene.h:107-130 */
+{
+	rtb_hit h;
+	h.id = 0xFFFFFFFFu;
+	h.t = FLT_MAX;
+	h.alpha = h.beta = h.gamma = 0;
+	if (s->n_ref_nodes) bvh_traverse(s, 0, r, eps, &h);
+	return h;
+}
+
+/* ---------------- BVHNode::traverseVisible, Geometry.h:435-462 ------------------------ */
+static int bvh_visible(const rtb_scene_desc* s, int32_t node, const ray_t* r, float eps, float maxT)
+{
+	const rtb_ref_node* n = &s->ref_nodes[node];
+	if (!ray_aabb(n, r)) return 1;
+	if (n->a < 0)
+	{
+		int32_t start = ~n->a, end = start + n->b, i;
+		for (i = start; i < end; i++)
+		{
+			float t, u, v;
+			if (tri_intersect(&s->tri_isect[i], r, &t, &u, &v))
+			{
+				if (t >= maxT || t <= eps) continue;
+				return 0;
+			}
+		}
+		return 1;
+	}
+	if (!bvh_visible(s, n->a, r, eps, maxT)) return 0;
+	return bvh_visible(s, n->b, r, eps, maxT);
+}
+
+static int scene_visible(const rtb_scene_desc* s, v3 p1, v3 p2, float eps) /* Scene.h:161-169 */
+{
+	v3 dir = sub(p2, p1);
+	float maxT = sqrtf(dot3(dir, dir)) - (2.0f * eps);
+	ray_t r;
+	dir = norm3(dir);
+	r = make_ray(add(p1, scl(dir, eps)), dir);
+	if (!s->n_ref_nodes) return 1;
+	return bvh_visible(s, 0, &r, eps, maxT);
+}
+
+/* ---------------- ShadingData: Scene.h:174-203, Geometry.h:106-112,127-130, Core.h:513 -- */
+typedef struct {
+	v3 x, wo, sN, gN;
+	float tu, tv;
+	v3 fu, fv, fw;
+	float t;
+	int32_t mat;
+} shade_t;
+
+static void frame_from_vector(v3 n, v3* u, v3* v, v3* w)
+{
+	*w = norm3(n);
+	if (fabsf(w->x) > fabsf(w->y))
+	{
+		float l = 1.0f / sqrtf(w->x * w->x + w->z * w->z);
+		*u = V(w->z * l, 0.0f, -w->x * l);
+	}
+	else
+	{
+		float l = 1.0f / sqrtf(w->y * w->y + w->z * w->z);
+		*u = V(0, w->z * l, -w->y * l);
+	}
+	*v = cross3(*w, *u);
+}
+static v3 to_local(const shade_t* s, v3 a) { return V(dot3(a, s->fu), dot3(a, s->fv), dot3(a, s->fw)); }
+static v3 to_world(const shade_t* s, v3 a) { return add(add(scl(s->fu, a.x), scl(s->fv, a.y)), scl(s->fw, a.z)); }
+
+static void shading_data(const rtb_scene_desc* s, const rtb_hit* h, const ray_t* r, shade_t* sd)
+{
+	memset(sd, 0, sizeof(*sd));
+	sd->mat = -1;
+	if (h->t < FLT_MAX)
+	{
+		const rtb_tri_isect* q = &s->tri_isect[h->id];
+		const rtb_tri_shade* a = &s->tri_shade[h->id];
+		v3 nrm;
+		sd->x = add(r->o, scl(r->d, h->t));
+		sd->gN = scl(Vp(q->n), a->gsign);
+		nrm = add(add(scl(Vp(a->n0), h->alpha), scl(Vp(a->n1), h->beta)), scl(Vp(a->n2), h->gamma));
+		sd->sN = norm3(nrm);
+		sd->tu = a->u0 * h->alpha + a->u1 * h->beta + a->u2 * h->gamma;
+		sd->tv = a->tv0 * h->alpha + a->tv1 * h->beta + a->tv2 * h->gamma;
+		sd->mat = (int32_t)q->material;
+		sd->wo = neg(r->d);
+		if (s->materials[sd->mat].flags & RTB_MAT_TWO_SIDED)
+		{
+			if (dot3(sd->wo, sd->sN) < 0) sd->sN = neg(sd->sN);
+			if (dot3(sd->wo, sd->gN) < 0) sd->gN = neg(sd->gN);
+		}
+		frame_from_vector(sd->sN, &sd->fu, &sd->fv, &sd->fw);
+		sd->t = h->t;
+	}
+	else
+	{
+		sd->wo = neg(r->d);
+		sd->t = h->t;
+	}
+}
+
+/* ---------------- Texture::sample, Imaging.h:72-94 ------------------------------------ */
+static v3 texture_sample(const rtb_scene_desc* s, int tex, float tu, float tv)
+{
+	const rtb_texture* T = &s->textures[tex];
+	const float* px = s->texels + (size_t)T->offset * 3;
+	float u = std_max(0.0f, fabsf(tu)) * T->width;
+	float v = std_max(0.0f, fabsf(tv)) * T->height;
+	int x = (int)floorf(u);
+	int y = (int)floorf(v);
+	float frac_u = u - x;
+	float frac_v = v - y;
+	float w0 = (1.0f - frac_u) * (1.0f - frac_v);
+	float w1 = frac_u * (1.0f - frac_v);
+	float w2 = (1.0f - frac_u) * frac_v;
+	float w3 = frac_u * frac_v;
+	v3 s0, s1, s2, s3;
+	x = x % T->width;
+	y = y % T->height;
+	if (x < 0) x = 0; /* inf/NaN coordinates are UB in the reference; stay in bounds */
+	if (y < 0) y = 0;
+	s0 = Vp(px + 3 * (size_t)(y * T->width + x));
+	s1 = Vp(px + 3 * (size_t)(y * T->width + ((x + 1) % T->width)));
+	s2 = Vp(px + 3 * (size_t)(((y + 1) % T->height) * T->width + x));
+	s3 = Vp(px + 3 * (size_t)(((y + 1) % T->height) * T->width + ((x + 1) % T->width)));
+	return add(add(add(scl(s0, w0), scl(s1, w1)), scl(s2, w2)), scl(s3, w3));
+}
+
+/* ---------------- SamplingDistributions, Sampling.h:29-70; Core.h:547-550 --------------- */
+static v3 spherical_to_world(float theta, float phi)
+{
+	return V(cosf(phi) * sinf(theta), sinf(phi) * sinf(theta), cosf(theta));
+}
+static v3 cosine_sample_hemisphere(float r1, float r2)
+{
+	float theta = acosf(sqrtf(r1));
+	float phi = 2.0f * M_PI * r2;
+	return spherical_to_world(theta, phi);
+}
+static float cosine_hemisphere_pdf(v3 wi) { return (wi.z >= 0.0f) ? (wi.z / M_PI) : 0.0f; }
+static v3 uniform_sample_sphere(float r1, float r2)
+{
+	float theta = acosf(1 - 2 * r1);
+	float phi = 2.0f * M_PI * r2;
+	return spherical_to_world(theta, phi);
+}
+
+/* ---------------- BSDFs as Materials.h actually behaves -------------------- */
+static v3 bsdf_evaluate(const rtb_scene_desc* s, const rtb_material* m, const shade_t* sd)
+{
+	v3 a;
+	if (m->type == RTB_BSDF_GLASS) return V(0, 0, 0);   /* Materials.h:295-299 */
+	a = texture_sample(s, m->tex, sd->tu, sd->tv);
+	if (m->type == RTB_BSDF_MIRROR) return a;           /* Materials.h:178-183 */
+	return dvd(a, (float)M_PI);                          /* :135-138, 227-231, 344-348, 389-393, 442-446 */
+}
+static float bsdf_pdf(const rtb_material* m, const shade_t* sd, v3 wi)
+{
+	if (m->type == RTB_BSDF_GLASS || m->type == RTB_BSDF_MIRROR) return 0.0f; /* :184-188, 300-305 */
+	return cosine_hemisphere_pdf(to_local(sd, wi));
+}
+/* ShadingHelper::fresnelDielectric, Materials.h:55-77 (Fpe denominator as written there) */
+static float fresnel_dielectric(float cosTheta, float iorInt, float iorExt, v3* wt, v3 wol)
+{
+	float ior = iorInt / iorExt;
+	float sinTheta_i = sqrtf(1 - (cosTheta * cosTheta));
+	float sinTheta_t = ior * sinTheta_i;
+	float ior2sin2 = (ior * ior) * (1 - (cosTheta * cosTheta));
+	float cosTheta_t, Fpa, Fpe, average;
+	if (ior2sin2 > 1.0f) return 1.0f;
+	cosTheta_t = sqrtf(1 - (sinTheta_t * sinTheta_t));
+	*wt = V(-ior * wol.x, -ior * wol.y, -cosTheta_t);
+	Fpa = (cosTheta - ior * cosTheta_t) / (cosTheta + ior * cosTheta_t);
+	Fpe = (ior * cosTheta - cosTheta_t) / (ior * cosTheta + ior * cosTheta_t);
+	average = ((Fpa * Fpa) + (Fpe * Fpe)) * 0.5f;
+	return std_max(0.0f, std_min(1.0f, average));
+}
+static v3 bsdf_sample(const rtb_scene_desc* s, const rtb_material* m, const shade_t* sd, float r1, float r2, float r3,
+                      v3* f, float* pdf)
+{
+	v3 albedo = texture_sample(s, m->tex, sd->tu, sd->tv);
+	if (m->type == RTB_BSDF_MIRROR) /* Materials.h:167-177 */
+	{
+		v3 wol = to_local(sd, sd->wo);
+		*pdf = 1.0f;
+		*f = albedo;
+		return to_world(sd, V(-wol.x, -wol.y, wol.z));
+	}
+	if (m->type == RTB_BSDF_GLASS) /* Materials.h:265-294 */
+	{
+		v3 wol = to_local(sd, sd->wo), wt = V(0, 0, 0), wi;
+		float cosTheta_i = fabsf(wol.z);
+		int enter = (wol.z > 0.0f);
+		float etaI = enter ? m->ext_ior : m->int_ior;
+		float etaT = enter ? m->int_ior : m->ext_ior;
+		float R = fresnel_dielectric(cosTheta_i, etaI, etaT, &wt, wol);
+		if (!enter) wt.z = -wt.z;
+		if (R == 1.0f || r3 < R)
+		{
+			wi = V(-wol.x, -wol.y, wol.z);
+			*pdf = R;
+			*f = scl(albedo, R);
+		}
+		else
+		{
+			wi = wt;
+			*pdf = 1.0f - R;
+			*f = scl(albedo, (1.0f - R));
+		}
+		return to_world(sd, wi);
+	}
+	{
+		v3 wl = cosine_sample_hemisphere(r1, r2);
+		/* DiffuseBSDF: cosineHemispherePDF (:130); the stubs: wi.z / M_PI (:222,339,384,437) */
+		*pdf = (m->type == RTB_BSDF_DIFFUSE) ? cosine_hemisphere_pdf(wl) : (float)(wl.z / M_PI);
+		*f = dvd(albedo, (float)M_PI);
+		return to_world(sd, wl);
+	}
+}
+
+/* ---------------- Lights, Lights.h ----------------------------------------------------- */
+static v3 env_evaluate(const rtb_scene_desc* s, int tex, v3 wi) /* Lights.h:158-165 */
+{
+	float u = atan2f(wi.z, wi.x);
+	float v;
+	u = (u < 0.0f) ? u + (2.0f * M_PI) : u;
+	u = u / (2.0f * M_PI);
+	v = acosf(wi.y) / M_PI;
+	return texture_sample(s, tex, u, v);
+}
+static v3 background_evaluate(const rtb_scene_desc* s, v3 wi)
+{
+	if (s->background_type == RTB_LIGHT_ENVMAP) return env_evaluate(s, s->background_tex, wi);
+	return Vp(s->background_colour);
+}
+static v3 triangle_gnormal(const rtb_scene_desc* s, uint32_t id) /* Geometry.h:127-130 */
+{
+	return scl(Vp(s->tri_isect[id].n), s->tri_shade[id].gsign);
+}
+static v3 triangle_sample(const rtb_scene_desc* s, uint32_t id, float r1, float r2, float* pdf) /* Geometry.h:114-126 */
+{
+	const rtb_tri_isect* q = &s->tri_isect[id];
+	float alpha = 1 - sqrtf(r1);
+	float beta = r2 * sqrtf(r1);
+	float gamma = 1.0f - (alpha + beta);
+	*pdf = 1.0f / q->area;
+	return add(add(scl(Vp(q->v0), alpha), scl(Vp(q->v1), beta)), scl(Vp(q->v2), gamma));
+}
+
+/* ---------------- counter-based RNG (replaces MTRandom) --------------------------------
+ * Philox-4x32-10; counter = (pixel, sample, block, 0), key = (seed, 0x52544232).
+ * Vertex at depth k: block 2k = [light pick, light r1, light r2, roulette],
+ *                    block 2k+1 = [bsdf r1, bsdf r2, glass draw, -].
+ * u = ((x >> 9) + 0.5) * 2^-23, strictly inside (0,1).                                   */
+static void philox(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+	int i;
+	for (i = 0; i < 10; i++)
+	{
+		uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+		uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+		uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+		c[0] = n0, c[1] = n1, c[2] = n2, c[3] = n3;
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+}
+static void rng_block(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t block, float u[4])
+{
+	uint32_t c[4];
+	int i;
+	c[0] = pixel, c[1] = sample, c[2] = block, c[3] = 0;
+	philox(c, seed, 0x52544232u);
+	for (i = 0; i < 4; i++) u[i] = ((float)(c[i] >> 9) + 0.5f) * 1.1920928955078125e-7f;
+}
+
+/* ---------------- RayTracer::computeDirect, Renderer.h:423-473; Scene.h:131-140 --------- */
+static v3 compute_direct(const rtb_scene_desc* s, const rtb_params* P, const shade_t* sd, const float u[4], tally_t* tl)
+{
+	const rtb_material* m = &s->materials[sd->mat];
+	const rtb_light* L;
+	float pmf, pdf;
+	int li;
+	if (m->flags & RTB_MAT_SPECULAR) return V(0, 0, 0);
+	if (s->n_lights == 0) return V(0, 0, 0);
+	pmf = 1.f / s->n_lights;
+	li = (int)(s->n_lights * u[0]);
+	if (li > (int)s->n_lights - 1) li = (int)s->n_lights - 1;
+	L = &s->lights[li];
+	if (L->type == RTB_LIGHT_AREA)
+	{
+		v3 p = triangle_sample(s, L->triangle, u[1], u[2], &pdf);
+		v3 wi = sub(p, sd->x);
+		float l = dot3(wi, wi), G;
+		wi = norm3(wi);
+		G = (win_max(dot3(wi, sd->sN), 0.0f) * win_max(-dot3(wi, triangle_gnormal(s, L->triangle)), 0.0f)) / l;
+		if (G > 0)
+		{
+			tl->shadow++;
+			if (scene_visible(s, sd->x, p, P->epsilon))
+				return dvd(scl(mul(bsdf_evaluate(s, m, sd), Vp(L->emission)), G), (pmf * pdf));
+		}
+	}
+	else
+	{
+		v3 wi = uniform_sample_sphere(u[1], u[2]);
+		v3 emitted = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, wi) : Vp(L->emission);
+		float G = win_max(dot3(wi, sd->sN), 0.0f);
+		pdf = 1.0f / (4.0f * M_PI);
+		if (G > 0)
+		{
+			tl->shadow++;
+			if (scene_visible(s, sd->x, add(sd->x, scl(wi, 10000.0f)), P->epsilon))
+				return dvd(scl(mul(bsdf_evaluate(s, m, sd), emitted), G), (pmf * pdf));
+		}
+	}
+	return V(0, 0, 0);
+}
+
+/* ---------------- RayTracer::pathTrace, Renderer.h:328-392 (recursive like the reference) */
+static v3 path_trace(const rtb_scene_desc* s, const rtb_params* P, ray_t* r, v3* T, int depth, uint32_t pixel,
+                     uint32_t sample, int canHitLight, tally_t* tl)
+{
+	rtb_hit h = scene_traverse(s, r, P->epsilon);
+	shade_t sd;
+	tl->closest++;
+	shading_data(s, &h, r, &sd);
+	if (sd.t < FLT_MAX)
+	{
+		const rtb_material* m = &s->materials[sd.mat];
+		float ua[4], ub[4], rr, pdf;
+		v3 direct, f, wi;
+		if (m->flags & RTB_MAT_LIGHT)
+		{
+			if (canHitLight) return mul(*T, Vp(m->emission));
+			return V(0, 0, 0);
+		}
+		rng_block(P->seed, pixel, sample, 2u * (uint32_t)depth, ua);
+		direct = mul(*T, compute_direct(s, P, &sd, ua, tl));
+		if (depth > P->max_depth) return direct;
+		rr = win_min(lum3(*T), P->rr_cap);
+		if (ua[3] < rr) *T = dvd(*T, rr);
+		else return direct;
+		rng_block(P->seed, pixel, sample, 2u * (uint32_t)depth + 1u, ub);
+		wi = bsdf_sample(s, m, &sd, ub[0], ub[1], ub[2], &f, &pdf);
+		if (m->flags & RTB_MAT_SPECULAR) *T = dvd(mul(*T, f), pdf);
+		else *T = dvd(scl(mul(*T, f), fabsf(dot3(wi, sd.sN))), pdf);
+		*r = make_ray(add(sd.x, scl(wi, P->epsilon)), wi);
+		return add(direct, path_trace(s, P, r, T, depth + 1, pixel, sample, (m->flags & RTB_MAT_SPECULAR) != 0, tl));
+	}
+	return background_evaluate(s, r->d);
+}
+
+/* direct(), albedo(), viewNormals(): Renderer.h:393-407, 558-581 */
+static v3 shade_simple(const rtb_scene_desc* s, const rtb_params* P, ray_t* r, uint32_t pixel, uint32_t sample, tally_t* tl)
+{
+	rtb_hit h = scene_traverse(s, r, P->epsilon);
+	shade_t sd;
+	tl->closest++;
+	shading_data(s, &h, r, &sd);
+	if (P->integrator == RTB_INT_NORMALS)
+	{
+		if (h.t < FLT_MAX) return V(fabsf(sd.sN.x), fabsf(sd.sN.y), fabsf(sd.sN.z));
+		return V(0, 0, 0);
+	}
+	if (sd.t < FLT_MAX)
+	{
+		const rtb_material* m = &s->materials[sd.mat];
+		float ua[4];
+		if (m->flags & RTB_MAT_LIGHT) return Vp(m->emission);
+		if (P->integrator == RTB_INT_ALBEDO) return bsdf_evaluate(s, m, &sd);
+		rng_block(P->seed, pixel, sample, 0, ua);
+		return compute_direct(s, P, &sd, ua, tl);
+	}
+	if (P->integrator == RTB_INT_ALBEDO) return background_evaluate(s, r->d);
+	return V(0, 0, 0);
+}
+
+/* ---------------- render: renderTile + Film::splat(BoxFilter), Renderer.h:795-818 -------- */
+typedef struct {
+	const rtb_scene_desc* s;
+	const rtb_params* P;
+	uint32_t spp_begin, spp_count;
+	float* film;
+	int y0, y1;
+	tally_t tl;
+} job_t;
+
+static int pixel_owned(const rtb_params* P, uint32_t W, uint32_t x, uint32_t y)
+{
+	if (P->partition == RTB_PART_TILE && P->part_world > 1)
+	{
+		uint32_t t32x = (W + 31u) >> 5;
+		uint32_t tile = (y >> 5) * t32x + (x >> 5);
+		return (int)(tile % (uint32_t)P->part_world) == P->part_rank;
+	}
+	return 1;
+}
+
+static void* render_rows(void* arg)
+{
+	job_t* j = (job_t*)arg;
+	const rtb_scene_desc* s = j->s;
+	const rtb_params* P = j->P;
+	uint32_t W = (uint32_t)s->camera.width;
+	int y;
+	for (y = j->y0; y < j->y1; y++)
+	{
+		uint32_t x;
+		for (x = 0; x < W; x++)
+		{
+			uint32_t pixel = (uint32_t)y * W + x, smp;
+			v3 acc = V(0, 0, 0);
+			float* f = j->film + (size_t)pixel * 3;
+			if (!pixel_owned(P, W, x, (uint32_t)y)) continue;
+			for (smp = j->spp_begin; smp < j->spp_begin + j->spp_count; smp++)
+			{
+				ray_t r;
+				v3 c;
+				if (P->partition == RTB_PART_SPP && P->part_world > 1 &&
+				    (int)(smp % (uint32_t)P->part_world) != P->part_rank)
+					continue;
+				r = generate_ray(&s->camera, x + 0.5f, y + 0.5f);
+				if (P->integrator == RTB_INT_PATH)
+				{
+					v3 T = V(1.0f, 1.0f, 1.0f);
+					c = path_trace(s, P, &r, &T, 0, pixel, smp, 1, &j->tl);
+				}
+				else
+					c = shade_simple(s, P, &r, pixel, smp, &j->tl);
+				acc = add(acc, c);
+				j->tl.samples++;
+			}
+			f[0] += acc.x, f[1] += acc.y, f[2] += acc.z;
+		}
+	}
+	return NULL;
+}
+
+typedef struct {
+	job_t* jobs;
+	int first, step, n;
+} span_t;
+
+static void* span_runner(void* arg)
+{
+	span_t* sp = (span_t*)arg;
+	int c;
+	for (c = sp->first; c < sp->n; c += sp->step) render_rows(&sp->jobs[c]);
+	return NULL;
+}
+
+/* spp_count samples per pixel accumulated into film_sum (running sums like Film::film);
+ * rows are dealt to `threads` workers in interleaved blocks of 4 (no shared sampler state:
+ * the result does not depend on the thread count). */
+int oracle_render(const rtb_scene_desc* s, const rtb_params* P, uint32_t spp_begin, uint32_t spp_count, int threads,
+                  float* film_sum, uint64_t* stats /* samples, closest, shadow */)
+{
+	int H = (int)s->camera.height, i, c;
+	int nt = threads < 1 ? 1 : (threads > 256 ? 256 : threads);
+	int chunks = (H + 3) / 4;
+	job_t* jobs = (job_t*)calloc((size_t)chunks, sizeof(job_t));
+	pthread_t* th = (pthread_t*)calloc((size_t)nt, sizeof(pthread_t));
+	span_t* spans = (span_t*)calloc((size_t)nt, sizeof(span_t));
+	for (c = 0; c < chunks; c++)
+	{
+		jobs[c].s = s, jobs[c].P = P, jobs[c].spp_begin = spp_begin, jobs[c].spp_count = spp_count;
+		jobs[c].film = film_sum, jobs[c].y0 = c * 4, jobs[c].y1 = (c * 4 + 4 < H) ? c * 4 + 4 : H;
+	}
+	for (i = 0; i < nt; i++)
+	{
+		spans[i].jobs = jobs, spans[i].first = i, spans[i].step = nt, spans[i].n = chunks;
+		if (nt == 1) span_runner(&spans[i]);
+		else pthread_create(&th[i], NULL, span_runner, &spans[i]);
+	}
+	if (nt > 1)
+		for (i = 0; i < nt; i++) pthread_join(th[i], NULL);
+	if (stats)
+	{
+		stats[0] = stats[1] = stats[2] = 0;
+		for (c = 0; c < chunks; c++)
+		{
+			stats[0] += jobs[c].tl.samples, stats[1] += jobs[c].tl.closest, stats[2] += jobs[c].tl.shadow;
+		}
+	}
+	free(spans);
+	free(jobs);
+	free(th);
+	return 0;
+}
+
+/* ---------------- batched entry points mirroring include/rtb.h -------------------------- */
+int oracle_primary_hits(const rtb_scene_desc* s, float eps, uint32_t* ids, float* t, rtb_ray* rays)
+{
+	uint32_t W = (uint32_t)s->camera.width, H = (uint32_t)s->camera.height, x, y;
+	for (y = 0; y < H; y++)
+		for (x = 0; x < W; x++)
+		{
+			ray_t r = generate_ray(&s->camera, x + 0.5f, y + 0.5f);
+			rtb_hit h = scene_traverse(s, &r, eps);
+			size_t i = (size_t)y * W + x;
+			if (ids) ids[i] = h.id;
+			if (t) t[i] = h.t;
+			if (rays)
+			{
+				rays[i].o[0] = r.o.x, rays[i].o[1] = r.o.y, rays[i].o[2] = r.o.z, rays[i].tmax = FLT_MAX;
+				rays[i].d[0] = r.d.x, rays[i].d[1] = r.d.y, rays[i].d[2] = r.d.z, rays[i].pad_ = 0;
+			}
+		}
+	return 0;
+}
+
+int oracle_trace(const rtb_scene_desc* s, float eps, int any_hit, const rtb_ray* rays, uint64_t n, rtb_hit* hits)
+{
+	uint64_t i;
+	for (i = 0; i < n; i++)
+	{
+		ray_t r = make_ray(Vp(rays[i].o), Vp(rays[i].d));
+		if (any_hit)
+		{
+			int vis = s->n_ref_nodes ? bvh_visible(s, 0, &r, eps, rays[i].tmax) : 1;
+			memset(&hits[i], 0, sizeof(rtb_hit));
+			hits[i].id = vis ? 0u : 1u;
+		}
+		else
+			hits[i] = scene_traverse(s, &r, eps);
+	}
+	return 0;
+}
+
+int oracle_visible(const rtb_scene_desc* s, float eps, const float* p1p2, uint64_t n, uint8_t* out)
+{
+	uint64_t i;
+	for (i = 0; i < n; i++) out[i] = (uint8_t)scene_visible(s, Vp(p1p2 + i * 6), Vp(p1p2 + i * 6 + 3), eps);
+	return 0;
+}
+
+static void store_shading(const shade_t* sd, rtb_shading* o)
+{
+	memset(o, 0, sizeof(*o));
+	o->x[0] = sd->x.x, o->x[1] = sd->x.y, o->x[2] = sd->x.z;
+	o->wo[0] = sd->wo.x, o->wo[1] = sd->wo.y, o->wo[2] = sd->wo.z;
+	o->s_normal[0] = sd->sN.x, o->s_normal[1] = sd->sN.y, o->s_normal[2] = sd->sN.z;
+	o->g_normal[0] = sd->gN.x, o->g_normal[1] = sd->gN.y, o->g_normal[2] = sd->gN.z;
+	o->tu = sd->tu, o->tv = sd->tv;
+	o->frame_u[0] = sd->fu.x, o->frame_u[1] = sd->fu.y, o->frame_u[2] = sd->fu.z;
+	o->frame_v[0] = sd->fv.x, o->frame_v[1] = sd->fv.y, o->frame_v[2] = sd->fv.z;
+	o->frame_w[0] = sd->fw.x, o->frame_w[1] = sd->fw.y, o->frame_w[2] = sd->fw.z;
+	o->t = sd->t;
+	o->material = sd->mat;
+}
+static void load_shading(const rtb_shading* o, shade_t* sd)
+{
+	sd->x = Vp(o->x), sd->wo = Vp(o->wo), sd->sN = Vp(o->s_normal), sd->gN = Vp(o->g_normal);
+	sd->tu = o->tu, sd->tv = o->tv;
+	sd->fu = Vp(o->frame_u), sd->fv = Vp(o->frame_v), sd->fw = Vp(o->frame_w);
+	sd->t = o->t, sd->mat = o->material;
+}
+
+int oracle_shading_data(const rtb_scene_desc* s, const rtb_ray* rays, const rtb_hit* hits, uint64_t n, rtb_shading* out)
+{
+	uint64_t i;
+	for (i = 0; i < n; i++)
+	{
+		ray_t r = make_ray(Vp(rays[i].o), Vp(rays[i].d));
+		shade_t sd;
+		shading_data(s, &hits[i], &r, &sd);
+		store_shading(&sd, &out[i]);
+	}
+	return 0;
+}
+
+int oracle_eval_bsdf(const rtb_scene_desc* s, const rtb_shading* sds, const float* wi, const float* u, uint64_t n,
+                     float* eval, float* pdf, float* s_wi, float* s_f, float* s_pdf)
+{
+	uint64_t i;
+	for (i = 0; i < n; i++)
+	{
+		shade_t sd;
+		const rtb_material* m;
+		load_shading(&sds[i], &sd);
+		if (sd.mat < 0 || (uint32_t)sd.mat >= s->n_materials) return -1;
+		m = &s->materials[sd.mat];
+		if (eval)
+		{
+			v3 e = bsdf_evaluate(s, m, &sd);
+			eval[i * 3] = e.x, eval[i * 3 + 1] = e.y, eval[i * 3 + 2] = e.z;
+		}
+		if (pdf) pdf[i] = bsdf_pdf(m, &sd, Vp(wi + i * 3));
+		if (s_wi || s_f || s_pdf)
+		{
+			v3 f, d;
+			float p;
+			d = bsdf_sample(s, m, &sd, u[i * 3], u[i * 3 + 1], u[i * 3 + 2], &f, &p);
+			if (s_wi) s_wi[i * 3] = d.x, s_wi[i * 3 + 1] = d.y, s_wi[i * 3 + 2] = d.z;
+			if (s_f) s_f[i * 3] = f.x, s_f[i * 3 + 1] = f.y, s_f[i * 3 + 2] = f.z;
+			if (s_pdf) s_pdf[i] = p;
+		}
+	}
+	return 0;
+}
+
+int oracle_eval_light(const rtb_scene_desc* s, const int32_t* light, const float* wi, const float* u, uint64_t n,
+                      float* p_or_wi, float* emitted, float* pdf, float* eval)
+{
+	uint64_t i;
+	for (i = 0; i < n; i++)
+	{
+		const rtb_light* L;
+		v3 p, e, ev, w = Vp(wi + i * 3);
+		float pd;
+		if (light[i] < 0 || (uint32_t)light[i] >= s->n_lights) return -1;
+		L = &s->lights[light[i]];
+		if (L->type == RTB_LIGHT_AREA)
+		{
+			p = triangle_sample(s, L->triangle, u[i * 2], u[i * 2 + 1], &pd);
+			e = Vp(L->emission);
+			ev = (dot3(w, triangle_gnormal(s, L->triangle)) < 0) ? Vp(L->emission) : V(0, 0, 0); /* Lights.h:40-47 */
+		}
+		else
+		{
+			p = uniform_sample_sphere(u[i * 2], u[i * 2 + 1]);
+			pd = 1.0f / (4.0f * M_PI);
+			e = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, p) : Vp(L->emission);
+			ev = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, w) : Vp(L->emission);
+		}
+		if (p_or_wi) p_or_wi[i * 3] = p.x, p_or_wi[i * 3 + 1] = p.y, p_or_wi[i * 3 + 2] = p.z;
+		if (emitted) emitted[i * 3] = e.x, emitted[i * 3 + 1] = e.y, emitted[i * 3 + 2] = e.z;
+		if (pdf) pdf[i] = pd;
+		if (eval) eval[i * 3] = ev.x, eval[i * 3 + 1] = ev.y, eval[i * 3 + 2] = ev.z;
+	}
+	return 0;
+}
+
+int oracle_rng_draws(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float* out)
+{
+	uint32_t b, k;
+	for (b = 0; b * 4 < n; b++)
+	{
+		float u[4];
+		rng_block(seed, pixel, sample, b, u);
+		for (k = 0; k < 4 && b * 4 + k < n; k++) out[b * 4 + k] = u[k];
+	}
+	return 0;
+}
+
+/* Film::tonemap, Imaging.h:233-242 */
+int oracle_tonemap(const float* film_sum, uint32_t n_pixels, int spp, float exposure, uint8_t* rgb8)
+{
+	uint32_t i;
+	for (i = 0; i < n_pixels * 3; i++)
+	{
+		float c = film_sum[i] * exposure / (float)spp;
+		rgb8[i] = (uint8_t)std_min(powf(std_max(c, 0.0f), 1.0f / 2.2f) * 255, 255.0f);
+	}
+	return 0;
+}
+
+/* Film::splat with GaussianFilter (Imaging.h:155-187, 209-232), one splat per pixel of an
+ * image of per-pixel colours (sample positions are pixel centres, Renderer.h:806-807). */
+int oracle_gaussian_splat(int width, int height, float radius, float alpha, const float* colours, float* film_sum)
+{
+	int size = (int)ceilf(radius), x, y, i, j;
+	if (size > 2) size = 2;
+	memset(film_sum, 0, (size_t)width * height * 3 * sizeof(float));
+	for (y = 0; y < height; y++)
+		for (x = 0; x < width; x++)
+		{
+			float w[25], total = 0;
+			int idx[25], used = 0, k;
+			const float* L = colours + ((size_t)y * width + x) * 3;
+			for (i = -size; i <= size; i++)
+				for (j = -size; j <= size; j++)
+				{
+					int px = x + j, py = y + i;
+					if (px >= 0 && px < width && py >= 0 && py < height)
+					{
+						float gx = expf(-alpha * ((float)j * (float)j)) - expf(-alpha * (radius * radius));
+						float gy = expf(-alpha * ((float)i * (float)i)) - expf(-alpha * (radius * radius));
+						idx[used] = py * width + px;
+						w[used] = gx * gy;
+						total += w[used];
+						used++;
+					}
+				}
+			for (k = 0; k < used; k++)
+			{
+				float* f = film_sum + (size_t)idx[k] * 3;
+				f[0] = f[0] + (L[0] * w[k] / total);
+				f[1] = f[1] + (L[1] * w[k] / total);
+				f[2] = f[2] + (L[2] * w[k] / total);
+			}
+		}
+	return 0;
+}
+
+/* ---------------- raw primitives for known-answer tests -------------------------------- */
+int oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+	uint32_t c[4];
+	memcpy(c, ctr, sizeof(c));
+	philox(c, key[0], key[1]);
+	memcpy(out, c, sizeof(c));
+	return 0;
+}
+
+/* AABB::rayAABB(const Ray&) on a free-standing box (the RTtest `RayAABB` case, RTtest.cpp:49-60) */
+int oracle_ray_aabb(const float bmin[3], const float bmax[3], const float o[3], const float d[3])
+{
+	rtb_ref_node n;
+	ray_t r = make_ray(Vp(o), Vp(d));
+	memcpy(n.bmin, bmin, 12);
+	memcpy(n.bmax, bmax, 12);
+	n.a = n.b = 0;
+	return ray_aabb(&n, &r);
+}
+
+/* Triangle::init + Triangle::rayIntersect on a free-standing triangle (Geometry.h:72-105);
+ * out = t, u, v.  The plane stage is Plane::rayIntersect (RTtest.cpp:21-48). */
+int oracle_ray_triangle(const float v0[3], const float v1[3], const float v2[3], const float o[3], const float d[3],
+                        float out[3])
+{
+	rtb_tri_isect q;
+	ray_t r = make_ray(Vp(o), Vp(d));
+	v3 e1 = sub(Vp(v2), Vp(v1)), e2 = sub(Vp(v0), Vp(v2));
+	v3 c = cross3(e1, e2), n = norm3(c);
+	memset(&q, 0, sizeof(q));
+	memcpy(q.v0, v0, 12), memcpy(q.v1, v1, 12), memcpy(q.v2, v2, 12);
+	q.n[0] = n.x, q.n[1] = n.y, q.n[2] = n.z;
+	q.area = sqrtf(dot3(c, c)) * 0.5f;
+	q.d = dot3(n, Vp(v0));
+	q.inv_area = 1.0f / dot3(c, n);
+	out[0] = out[1] = out[2] = 0;
+	return tri_intersect(&q, &r, &out[0], &out[1], &out[2]);
+}

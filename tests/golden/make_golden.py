@@ -1,0 +1,147 @@
+#!/usr/bin/env python3
+"""Regenerates the committed fixtures in tests/golden/ from the reference itself
+(oracle/_ref/librtref.so, built by oracle/build_ref.py from /root/reference).  Run in the
+build container only:  python tests/golden/make_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ref  # noqa: E402
+from raytracingrenderer_b200 import abi, imageio  # noqa: E402
+import raysets  # noqa: E402
+
+SCENES = ["cornell-box", "MaterialsScene", "materialball", "coffee", "bathroom"]
+
+
+def fingerprints():
+    out = {}
+    for name in SCENES:
+        s = ref.RefScene(name)
+        ids, t = s.primary_hits()
+        hit = ids != abi.MISS_ID
+        out[name] = dict(width=s.width, height=s.height, n_tris=s.n_tris, n_lights=s.n_lights,
+                         n_materials=s.n_materials,
+                         ids_sha256_16=hashlib.sha256(ids.tobytes()).hexdigest()[:16],
+                         t_sha256_16=hashlib.sha256(t.tobytes()).hexdigest()[:16],
+                         sum_ids=int(ids[hit].astype(np.uint64).sum()), misses=int((~hit).sum()),
+                         distinct_ids=int(len(np.unique(ids[hit]))))
+        print(name, out[name])
+    json.dump(out, open(os.path.join(HERE, "fingerprints.json"), "w"), indent=1)
+
+
+def cornell():
+    s = ref.RefScene("cornell-box")
+    flat = s.flatten(os.path.join(HERE, "cornell-box.rtbs"))
+    ids, t, rays = s.primary_hits(True)
+    hits = s.trace(rays)
+    sets = raysets.mixed_set(rays, hits, seed=20261018, n_each=400)
+    closest_hits = s.trace(sets["closest"])
+    any_hits = s.trace(sets["anyhit"], any_hit=True)
+    vis = s.visible(sets["segments"])
+    sd = s.shading_data(sets["closest"], closest_hits)
+    ok = closest_hits["id"] != abi.MISS_ID
+    rng = np.random.default_rng(7)
+    n = int(ok.sum())
+    wi = raysets.unit(rng.normal(size=(n, 3)))
+    u = rng.random((n, 3), dtype=np.float32)
+    b = s.eval_bsdf(sd[ok], wi, u)
+    li = rng.integers(0, s.n_lights, n).astype(np.int32)
+    L = s.eval_light(li, wi, u[:, :2])
+    np.savez_compressed(os.path.join(HERE, "cornell_vectors.npz"), closest=sets["closest"], closest_hits=closest_hits,
+                        anyhit=sets["anyhit"], anyhit_occluded=any_hits["id"].astype(np.uint8),
+                        segments=sets["segments"], visible=vis, shading=sd, hit_mask=ok, wi=wi, u=u,
+                        bsdf_eval=b["eval"], bsdf_pdf=b["pdf"], bsdf_s_wi=b["s_wi"], bsdf_s_f=b["s_f"],
+                        bsdf_s_pdf=b["s_pdf"], light=li, light_p=L["p_or_wi"], light_emitted=L["emitted"],
+                        light_pdf=L["pdf"], light_eval=L["eval"],
+                        aov_albedo_blocks=raysets.block_mean(s.aov("albedo")),
+                        aov_normals_blocks=raysets.block_mean(s.aov("normals")))
+    # image statistics: two independent 32-spp halves of the reference renderer (all threads;
+    # the reference is not deterministic across runs) + the committed 144-spp render
+    a, na, _ = s.render(32, 0, fresh=True)
+    bb, nb, _ = s.render(32, 0, fresh=False)  # continues the same RayTracer: film holds 64 spp
+    bsum = bb - a
+    r144 = imageio.read_hdr(os.path.join(ref.REF_DIR, "..", "..", "..", "reference", "RTBase", "result_144.hdr")) \
+        if False else imageio.read_hdr("/root/reference/RTBase/result_144.hdr")
+    np.savez_compressed(os.path.join(HERE, "cornell_ref_blocks.npz"),
+                        half_a=raysets.block_mean(a / 32.0), half_b=raysets.block_mean(bsum / 32.0),
+                        mean_a=(a / 32.0).mean(axis=(0, 1)), mean_b=(bsum / 32.0).mean(axis=(0, 1)),
+                        result_144=raysets.block_mean(r144), result_144_mean=r144.mean(axis=(0, 1)),
+                        pixel_rmse_halves=np.sqrt(np.mean((a / 32.0 - bsum / 32.0) ** 2)))
+    print("cornell halves mean", (a / 32).mean(axis=(0, 1)), (bsum / 32).mean(axis=(0, 1)), "r144", r144.mean(axis=(0, 1)))
+
+
+def all_bsdfs():
+    """BSDF vectors over every material class the loader can produce (MaterialsScene has
+    mirror/diffuse/plastic/conductor/orennayar/glass; the materialball override adds the
+    rough dielectric), with the material + texture tables needed to re-create them."""
+    mats, texs, texels, sds, wis, us, outs = [], [], [], [], [], [], []
+    rng = np.random.default_rng(11)
+    for name in ["MaterialsScene", "materialball_dielectric", "materialball_glass"]:
+        s = ref.RefScene(name)
+        flat = s.flatten("/tmp/_golden_%s.rtbs" % name)
+        ids, t, rays = s.primary_hits(True)
+        hits = s.trace(rays)
+        pts, m = raysets.hit_points(rays, hits)
+        # primary + one random bounce (inside-glass paths need rays that start inside)
+        sub = rng.choice(np.where(m)[0], 1500, replace=False)
+        br = raysets.bounce_rays(pts, rng, 1500)
+        allr = np.concatenate([rays[sub], br])
+        allh = s.trace(allr)
+        ok = allh["id"] != abi.MISS_ID
+        sd = s.shading_data(allr[ok], allh[ok])
+        # keep <= 120 records per material
+        keep = []
+        for mi in np.unique(sd["material"]):
+            w = np.where(sd["material"] == mi)[0]
+            keep.extend(w[:120])
+        sd = sd[np.array(sorted(keep))]
+        n = len(sd)
+        wi = raysets.unit(rng.normal(size=(n, 3)))
+        u = rng.random((n, 3), dtype=np.float32)
+        o = s.eval_bsdf(sd, wi, u)
+        # re-base material/texture indices into the concatenated tables; only material
+        # textures (1x1 PNGs) are kept, never the env map
+        mat_tex = flat.materials["tex"]
+        used_tex = sorted(set(int(x) for x in mat_tex))
+        tex_map = {}
+        for ti in used_tex:
+            T = flat.textures[ti]
+            px = flat.texels.reshape(-1, 3)[T["offset"]:T["offset"] + T["width"] * T["height"]]
+            nt = np.zeros((), abi.texture_dt)
+            nt["offset"], nt["width"], nt["height"] = sum(len(x) for x in texels), T["width"], T["height"]
+            tex_map[ti] = len(texs)
+            texs.append(nt)
+            texels.append(px.copy())
+        base = len(mats)
+        for mrec in flat.materials:
+            mrec = mrec.copy()
+            mrec["tex"] = tex_map[int(mrec["tex"])]
+            mats.append(mrec)
+        sd = sd.copy()
+        sd["material"] += base
+        sds.append(sd), wis.append(wi), us.append(u), outs.append(o)
+    np.savez_compressed(os.path.join(HERE, "bsdf_vectors.npz"), materials=np.array(mats, abi.material_dt),
+                        textures=np.array(texs, abi.texture_dt), texels=np.concatenate(texels).astype(np.float32),
+                        shading=np.concatenate(sds), wi=np.concatenate(wis), u=np.concatenate(us),
+                        **{k: np.concatenate([o[k] for o in outs]) for k in outs[0]})
+    types = np.array(mats, abi.material_dt)["type"]
+    print("bsdf vectors:", sum(len(x) for x in sds), "records; material types", sorted(set(int(x) for x in types)))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["fingerprints", "cornell", "bsdfs"]
+    if "fingerprints" in what:
+        fingerprints()
+    if "cornell" in what:
+        cornell()
+    if "bsdfs" in what:
+        all_bsdfs()

@@ -1,0 +1,267 @@
+"""Pins the plain-C restatement (oracle/rtb_oracle.c):
+  * always: against the committed golden vectors in tests/golden/ (made from the reference by
+    tests/golden/make_golden.py) and published known answers (Random123 Philox KATs, the
+    reference's own RTtest cases);
+  * when oracle/_ref is present (the build container, and the GPU box via gpurun): live
+    against the UNMODIFIED reference on all five bundled scenes."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import raysets
+from conftest import BUNDLED, GOLDEN, flat_scene, ref_scene, rel_err, synthetic_scene
+from raytracingrenderer_b200 import abi
+
+FP = json.load(open(os.path.join(GOLDEN, "fingerprints.json")))
+
+# fingerprints of the reference's primary-hit arrays as measured by the survey
+SURVEY_FP = {
+    "cornell-box": ("0e060cc6996f198b", "1227c2cf5a6229a9", 20973784),
+    "MaterialsScene": ("2c6a8dfc102f241f", "a3ae64ee99087822", 2569174758),
+    "materialball": ("9ea96184403144e1", "f718fe7ce43b579f", 388335202),
+    "coffee": ("efd809cda7c3fedb", "85b1ae4e30a68c4a", 15856427522),
+    "bathroom": ("db110afd090402da", "135270a34b0189ec", 237852995515),
+}
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def test_committed_fingerprints_equal_the_surveys():
+    for name, (i, t, s) in SURVEY_FP.items():
+        assert (FP[name]["ids_sha256_16"], FP[name]["t_sha256_16"], FP[name]["sum_ids"]) == (i, t, s)
+
+
+# ---------------------------------------------------------------- known answers
+def test_philox_known_answers(oracle_mod):
+    """Random123 kat_vectors, philox4x32 10 rounds."""
+    L = oracle_mod.lib()
+    kats = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+            ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+            ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+             [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kats:
+        c, k, o = np.array(ctr, "u4"), np.array(key, "u4"), np.zeros(4, "u4")
+        L.oracle_philox(C.c_void_p(c.ctypes.data), C.c_void_p(k.ctypes.data), C.c_void_p(o.ctypes.data))
+        assert list(o) == want
+
+
+def test_uniforms_strictly_inside_unit_interval(oracle_mod):
+    u = oracle_mod.rng_draws(1, 123, 7, 4096)
+    assert u.min() > 0.0 and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 0.02
+    # counter-based: the same (seed, pixel, sample) always gives the same stream
+    assert np.array_equal(u, oracle_mod.rng_draws(1, 123, 7, 4096))
+    assert not np.array_equal(u, oracle_mod.rng_draws(2, 123, 7, 4096))
+
+
+def _f3(*v):
+    a = np.array(v, "<f4")
+    return a, C.c_void_p(a.ctypes.data)
+
+
+def test_rttest_known_answers(oracle_mod):
+    """The reference's own unit tests that touch the hot path (RTtest/RTtest.cpp): RayAABB
+    (:49-60) and the two plane cases (:21-48; Triangle::rayIntersect's plane stage is
+    Plane::rayIntersect, Geometry.h:44-56 vs :91-95)."""
+    L = oracle_mod.lib()
+    keep = []
+
+    def p(*v):
+        a, ptr = _f3(*v)
+        keep.append(a)
+        return ptr
+    assert L.oracle_ray_aabb(p(0, 0, 0), p(1, 1, 1), p(0, 0, 0), p(1, 1, 1)) == 1
+    assert L.oracle_ray_aabb(p(0, 0, 0), p(1, 1, 1), p(2, 2, 2), p(1, 1, 1)) == 0   # behind the ray
+    out = np.zeros(3, "<f4")
+    big = (p(-50, 1, -50), p(50, 1, -50), p(0, 1, 80))  # a large triangle in the plane y = 1
+    assert L.oracle_ray_triangle(*big, p(0, 0, 0), p(1, 1, 1), C.c_void_p(out.ctypes.data)) == 1
+    assert out[0] == pytest.approx(1.0, abs=1e-4)                                   # Plane1: t = 1
+    assert L.oracle_ray_triangle(*big, p(0, 2, 0), p(1, 1, 1), C.c_void_p(out.ctypes.data)) == 0  # Plane2: t < 0
+
+
+# ---------------------------------------------------------------- golden vectors (always run)
+@pytest.fixture(scope="module")
+def cornell(oracle_mod):
+    return oracle_mod.Oracle(flat_scene("cornell-box"))
+
+
+@pytest.fixture(scope="module")
+def cv():
+    return np.load(os.path.join(GOLDEN, "cornell_vectors.npz"))
+
+
+def test_cornell_primary_hits_fingerprint(cornell):
+    ids, t = cornell.primary_hits()
+    assert sha16(ids) == FP["cornell-box"]["ids_sha256_16"]
+    assert sha16(t) == FP["cornell-box"]["t_sha256_16"]
+    assert int((ids == abi.MISS_ID).sum()) == FP["cornell-box"]["misses"] == 19
+
+
+def test_cornell_golden_traversal(cornell, cv):
+    hits = cornell.trace(cv["closest"])
+    assert hits.tobytes() == cv["closest_hits"].tobytes()           # id, t, alpha, beta, gamma bit-exact
+    occ = cornell.trace(cv["anyhit"], any_hit=True)["id"].astype(np.uint8)
+    assert np.array_equal(occ, cv["anyhit_occluded"])
+    assert np.array_equal(cornell.visible(cv["segments"]), cv["visible"])
+    # the degenerate-ray case must be present in the fixture: axis rays that miss everything
+    d = cv["closest"]["d"]
+    axis = (d == 0).any(axis=1)
+    assert axis.sum() > 100 and (cv["closest_hits"]["id"][axis] == abi.MISS_ID).any()
+
+
+def test_cornell_golden_shading_bsdf_light(cornell, cv):
+    m = cv["hit_mask"]
+    sd = cornell.shading_data(cv["closest"], cv["closest_hits"])
+    for f in abi.shading_dt.names:
+        assert sd[f][m].tobytes() == cv["shading"][f][m].tobytes(), f
+    # on a miss only wo and t are defined (Scene.h:197-201)
+    assert sd["wo"][~m].tobytes() == cv["shading"]["wo"][~m].tobytes()
+    b = cornell.eval_bsdf(cv["shading"][m], cv["wi"], cv["u"])
+    for k in ("eval", "pdf", "s_wi", "s_f", "s_pdf"):
+        assert rel_err(b[k], cv["bsdf_" + k]) <= 1e-5, k
+    L = cornell.eval_light(cv["light"], cv["wi"], cv["u"][:, :2])
+    for k, g in (("p_or_wi", "light_p"), ("emitted", "light_emitted"), ("pdf", "light_pdf"), ("eval", "light_eval")):
+        assert rel_err(L[k], cv[g]) <= 1e-5, k
+
+
+def test_all_bsdf_classes_golden(oracle_mod):
+    """sample / evaluate / PDF of every BSDF class the reference loader can create, against
+    vectors produced by the reference (MaterialsScene + materialball overrides)."""
+    g = np.load(os.path.join(GOLDEN, "bsdf_vectors.npz"))
+    s = flat_scene("cornell-box")
+    t = abi.FlatScene()
+    t.camera, t.ref_nodes, t.tri_isect, t.tri_shade = s.camera, s.ref_nodes, s.tri_isect.copy(), s.tri_shade
+    t.tri_isect["material"] = 0
+    t.materials, t.textures, t.texels = g["materials"], g["textures"], g["texels"].ravel()
+    o = oracle_mod.Oracle(t)
+    assert sorted(set(int(x) for x in g["materials"]["type"])) == list(range(7))
+    b = o.eval_bsdf(g["shading"], g["wi"], g["u"])
+    for k in ("eval", "pdf", "s_wi", "s_f", "s_pdf"):
+        assert rel_err(b[k], g[k]) <= 1e-5, k
+    # both glass branches and TIR are exercised
+    glass = g["materials"]["type"][g["shading"]["material"]] == abi.BSDF_GLASS
+    assert glass.sum() > 50 and (g["s_pdf"][glass] == 1.0).any() and (g["s_pdf"][glass] < 0.5).any()
+
+
+def test_cornell_image_against_reference_statistics(cornell):
+    """Converged-image gate against two independent 32-spp halves of the
+    reference renderer and the reference's committed 144-spp render (result_144.hdr)."""
+    g = np.load(os.path.join(GOLDEN, "cornell_ref_blocks.npz"))
+    spp = 16
+    film, st = cornell.render(spp)
+    img = film / spp
+    ref_mean = 0.5 * (g["mean_a"] + g["mean_b"])
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / ref_mean - 1) < 0.01)
+    blocks = raysets.block_mean(img)
+    ref_blocks = 0.5 * (g["half_a"] + g["half_b"])
+    # noise floor of a 32-spp block image from the two halves; ours is 16 spp vs their 64
+    floor32 = np.sqrt(np.mean((g["half_a"] - g["half_b"]) ** 2) / 2)
+    expect = floor32 * np.sqrt(32) * np.sqrt(1 / spp + 1 / 64)
+    rmse = np.sqrt(np.mean((blocks - ref_blocks) ** 2))
+    assert rmse < 3 * expect, (rmse, expect)
+    rmse144 = np.sqrt(np.mean((blocks - g["result_144"]) ** 2))
+    assert rmse144 < 0.006, rmse144        # oracle@32 spp scored 0.0020 in the survey
+    assert st["samples"] == 1024 * 1024 * spp
+    rps = (st["closest_rays"] + st["shadow_rays"]) / st["samples"]
+    assert 4.2 < rps < 4.45                # 4.33 rays per sample
+
+
+def test_render_is_thread_count_independent(oracle_mod):
+    s = synthetic_scene()
+    a, _ = oracle_mod.Oracle(s).render(3, threads=1)
+    b, _ = oracle_mod.Oracle(s).render(3, threads=5)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_partitions_compose(oracle_mod):
+    s = synthetic_scene()
+    full, _ = oracle_mod.Oracle(s).render(4)
+    tiles = sum(oracle_mod.Oracle(s, partition=abi.PART_TILE, part_rank=r, part_world=3).render(4)[0] for r in range(3))
+    assert tiles.tobytes() == full.tobytes()
+    spp = sum(oracle_mod.Oracle(s, partition=abi.PART_SPP, part_rank=r, part_world=2).render(4)[0] for r in range(2))
+    assert np.allclose(spp, full, rtol=1e-5, atol=1e-6)
+
+
+def test_gaussian_and_tonemap_against_reference(oracle_mod):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not available")
+    rng = np.random.default_rng(5)
+    img = (rng.random((21, 33, 3)) ** 3 * 4).astype(np.float32)
+    a = oracle_mod.gaussian_splat(img, 2.0, 0.1)
+    b = ref.gaussian_splat(img, 2.0, 0.1)
+    assert np.allclose(a, b, rtol=1e-6, atol=1e-7)
+    rs = ref_scene("cornell-box")
+    film = (rng.random((rs.height, rs.width, 3)) ** 2 * 3).astype(np.float32) * 7
+    assert np.array_equal(oracle_mod.tonemap(film, 7), rs.tonemap(film, 7))
+
+
+# ---------------------------------------------------------------- live against the reference
+@pytest.mark.parametrize("name", BUNDLED)
+def test_primary_hits_equal_the_reference(oracle_mod, name):
+    rs = ref_scene(name)
+    o = oracle_mod.Oracle(flat_scene(name))
+    ids, t = o.primary_hits()
+    assert sha16(ids) == FP[name]["ids_sha256_16"] and sha16(t) == FP[name]["t_sha256_16"]
+    rid, rt = rs.primary_hits()
+    assert np.array_equal(ids, rid) and t.tobytes() == rt.tobytes()
+
+
+@pytest.mark.parametrize("name", ["MaterialsScene", "materialball", "coffee", "bathroom", "materialball_dielectric"])
+def test_traversal_shading_bsdf_light_equal_the_reference(oracle_mod, name):
+    rs = ref_scene(name)
+    o = oracle_mod.Oracle(flat_scene(name))
+    ids, t, rays = rs.primary_hits(want_rays=True)
+    ph = rs.trace(rays[::53])
+    sets = raysets.mixed_set(rays[::53], ph, seed=99, n_each=300)
+    rh = rs.trace(sets["closest"])
+    assert o.trace(sets["closest"]).tobytes() == rh.tobytes()
+    assert np.array_equal(o.trace(sets["anyhit"], any_hit=True)["id"], rs.trace(sets["anyhit"], any_hit=True)["id"])
+    assert np.array_equal(o.visible(sets["segments"]), rs.visible(sets["segments"]))
+    m = rh["id"] != abi.MISS_ID
+    sd_r, sd_o = rs.shading_data(sets["closest"][m], rh[m]), o.shading_data(sets["closest"][m], rh[m])
+    assert sd_r.tobytes() == sd_o.tobytes()
+    rng = np.random.default_rng(3)
+    n = int(m.sum())
+    wi, u = raysets.unit(rng.normal(size=(n, 3))), rng.random((n, 3), dtype=np.float32)
+    a, b = rs.eval_bsdf(sd_r, wi, u), o.eval_bsdf(sd_r, wi, u)
+    for k in a:
+        assert rel_err(b[k], a[k]) <= 1e-5, k
+    li = rng.integers(0, rs.n_lights, n).astype(np.int32)
+    a, b = rs.eval_light(li, wi, u[:, :2]), o.eval_light(li, wi, u[:, :2])
+    for k in a:
+        assert rel_err(b[k], a[k]) <= 1e-5, k
+
+
+@pytest.mark.parametrize("name,spp", [("MaterialsScene", 8), ("materialball", 8)])
+def test_rendered_image_statistics_equal_the_reference(oracle_mod, name, spp):
+    """Same estimator, different RNG: mean radiance within 1.5 % and 8x8-block RMSE within 3x
+    the noise floor measured between two independent reference runs."""
+    rs = ref_scene(name)
+    o = oracle_mod.Oracle(flat_scene(name))
+    a, _, _ = rs.render(spp, 0, fresh=True)
+    b2, _, _ = rs.render(spp, 0, fresh=False)
+    b = b2 - a
+    mine, st = o.render(spp)
+    ra, rb, mo = a / spp, b / spp, mine / spp
+    ref_mean = 0.5 * (ra + rb).mean(axis=(0, 1))
+    assert np.all(np.abs(mo.mean(axis=(0, 1)) / ref_mean - 1) < 0.015)
+    ba, bb, bo = raysets.block_mean(ra), raysets.block_mean(rb), raysets.block_mean(mo)
+    floor = np.sqrt(np.mean((ba - bb) ** 2))            # rmse between two spp-sample images
+    rmse = np.sqrt(np.mean((bo - 0.5 * (ba + bb)) ** 2))  # spp vs 2*spp samples: floor*sqrt(3/4)
+    assert rmse < 3 * floor, (rmse, floor)
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "MaterialsScene"])
+def test_aovs_equal_the_reference(oracle_mod, name):
+    rs = ref_scene(name)
+    for kind, integ in (("albedo", abi.INT_ALBEDO), ("normals", abi.INT_NORMALS)):
+        o = oracle_mod.Oracle(flat_scene(name), integrator=integ)
+        img, _ = o.render(1)
+        assert np.allclose(img, rs.aov(kind), rtol=1e-5, atol=1e-6), kind
