@@ -72,3 +72,24 @@ def block_mean(img, b=8):
     h, w, c = img.shape
     hh, ww = (h // b) * b, (w // b) * b
     return img[:hh, :ww].reshape(hh // b, b, ww // b, b, c).mean(axis=(1, 3))
+
+
+def env_lookup_slack(scene, tex, dirs, delta_texels):
+    """Per-direction, per-channel bound on how much EnvironmentMap::evaluate (Lights.h:158-165 +
+    Imaging.h:72-94) can change when the texel coordinate moves by `delta_texels`: delta x the
+    value range of the 3x3 texels around the lookup."""
+    T = scene.textures[tex]
+    W, H = int(T["width"]), int(T["height"])
+    px = scene.texels.reshape(-1, 3)[int(T["offset"]):int(T["offset"]) + W * H].reshape(H, W, 3)
+    d = np.asarray(dirs, np.float64)
+    u = np.arctan2(d[:, 2], d[:, 0])
+    u = np.where(u < 0, u + 2 * np.pi, u) / (2 * np.pi)
+    v = np.arccos(np.clip(d[:, 1], -1, 1)) / np.pi
+    x, y = np.floor(u * W).astype(int), np.floor(v * H).astype(int)
+    lo = np.full((len(d), 3), np.inf)
+    hi = np.full((len(d), 3), -np.inf)
+    for dy in (-1, 0, 1, 2):
+        for dx in (-1, 0, 1, 2):
+            t = px[(y + dy) % H, (x + dx) % W]
+            lo, hi = np.minimum(lo, t), np.maximum(hi, t)
+    return delta_texels * (hi - lo)
