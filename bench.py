@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""bench.py — throughput of the path-tracing hot path (RayTracer::render and below,
+RTBase/Renderer.h:328-473, 795-885) on N B200s, and of the reference CPU renderer beside it.
+
+Workload (BASELINE.json configs[1]): materialball, 1280x720, 256 spp, MAX_DEPTH 4, rendered
+once per BSDF class the scene format can express — the 7 per-instance overrides diffuse,
+conductor, glass, dielectric, orennayar, plastic, layered.  One STEP = those 7
+renders (7 x 921 600 px x 256 spp = 1.65 G samples per GPU).  N GPUs: weak scaling — every rank
+renders the same 7 films with its own 256 disjoint sample indices (spp slice, RNG keyed by the
+global sample index), then the films are summed to rank 0 with NCCL (the path has no other
+exchange step).
+
+  value : Msamples/s, scenes resident in HBM, device-timed (CUDA events), max over ranks.
+  e2e   : the same through the C ABI with HOST buffers: per render rtb_update_camera (host
+          struct -> device), rtb_clear, rtb_render, rtb_read_film into pinned host memory.
+  --impl reference : the UNMODIFIED reference renderer (oracle/_ref, RayTracer::render) on all
+          host threads, same scenes, a bounded spp sample per step.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VARIANTS = ["diffuse", "conductor", "glass", "dielectric", "orennayar", "plastic", "layered"]
+CACHE = os.path.join(ROOT, "scenes", "_cache")
+METRIC = "Msamples/s (path-traced pixel samples per second; Mrays/s alongside)"
+
+
+def load_workload(scene, log):
+    """-> (name, [(label, FlatScene)]).  Flat scenes staged at build time (scenes/_cache)."""
+    import numpy as np
+    from raytracingrenderer_b200 import abi
+    base_path = os.path.join(CACHE, "materialball.rtbs")
+    var_path = os.path.join(CACHE, "materialball_variants.npz")
+    if scene == "materialball7" and os.path.isfile(base_path) and os.path.isfile(var_path):
+        base = abi.FlatScene.load(base_path)
+        tables = np.load(var_path)
+        out = []
+        for v in VARIANTS:
+            s = abi.FlatScene()
+            s.__dict__.update(base.__dict__)
+            s.materials = tables[v]
+            out.append((v, s))
+        return "materialball 1280x720 x 7 BSDF overrides (%s), 256 spp each, max_depth 4" % ",".join(VARIANTS), out
+    path = os.path.join(CACHE, scene + ".rtbs")
+    if scene != "materialball7" and os.path.isfile(path):
+        s = abi.FlatScene.load(path)
+        return "%s %dx%d" % (scene, s.width, s.height), [(scene, s)]
+    log("WARNING: staged scene data for %r not found under scenes/_cache; falling back to the committed "
+        "cornell-box fixture" % scene)
+    s = abi.FlatScene.load(os.path.join(ROOT, "tests", "golden", "cornell-box.rtbs"))
+    return "cornell-box 1024x1024 (fallback: staged materialball data missing)", [("cornell-box", s)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        import statistics
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2])), pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: RayTracer::render() of the unmodified reference on the host cores."""
+    if rank != 0:
+        return
+    from oracle import ref
+    kind = "reference"
+    spp = args.ref_spp
+    name, scenes = None, []
+    if ref.available() and all(ref.have_scene("materialball_" + v) for v in VARIANTS) and args.scene == "materialball7":
+        scenes = [ref.RefScene("materialball_" + v) for v in VARIANTS]
+        name = "materialball 1280x720 x 7 BSDF overrides (%s), 256 spp each, max_depth 4" % ",".join(VARIANTS)
+        threads = scenes[0].hw_threads
+
+        def step():
+            n = 0
+            for s in scenes:
+                s.render(spp, 0, fresh=True)
+                n += s.width * s.height * spp
+            return n
+    else:
+        # the reference build did not travel: time the C restatement instead (kind "port")
+        from oracle import port
+        kind = "port"
+        name, flats = load_workload(args.scene, lambda m: print(m, file=sys.stderr))
+        oracles = [port.Oracle(s) for _, s in flats]
+        threads = os.cpu_count() or 1
+
+        def step():
+            n = 0
+            for o in oracles:
+                o.render(spp, threads=threads)
+                n += o.width * o.height * spp
+            return n
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        total += step()
+    dt = time.perf_counter() - t0
+    val = total / dt / 1e6
+    sample = "%d spp per scene per step (of the workload's 256), RayTracer::render() incl. its per-spp thread " \
+             "spawn + tonemap" % spp
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "spp_per_step_sample": spp},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(args, log):
+    """Bounded sample of the same workload on the host cores (rank 0, N=1)."""
+    from oracle import ref
+    spp = args.cpu_spp
+    t_budget = time.perf_counter()
+    if ref.available() and args.scene == "materialball7" and all(ref.have_scene("materialball_" + v) for v in VARIANTS):
+        total, secs, threads = 0, 0.0, 1
+        for v in VARIANTS:
+            s = ref.RefScene("materialball_" + v)
+            threads = s.hw_threads
+            s.render(1, 0, fresh=True)           # warm: page in, thread pool paths
+            _, _, dt = s.render(spp, 0, fresh=True)
+            total += s.width * s.height * spp
+            secs += dt
+        return {"value": total / secs / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+                "sample": "the 7 materialball variants at %d spp each (of 256) through the unmodified "
+                          "RayTracer::render(), g++ -O2 -ffp-contract=off, %.1f s" % (spp, time.perf_counter() - t_budget)}
+    from oracle import port
+    name, flats = load_workload(args.scene, log)
+    threads = os.cpu_count() or 1
+    total, secs = 0, 0.0
+    for _, s in flats:
+        o = port.Oracle(s)
+        t0 = time.perf_counter()
+        o.render(spp, threads=threads)
+        secs += time.perf_counter() - t0
+        total += o.width * o.height * spp
+    return {"value": total / secs / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": "%s at %d spp through oracle/rtb_oracle.c" % (name, spp)}
+
+
+class _CudaArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import raytracingrenderer_b200 as rtb
+    from raytracingrenderer_b200 import abi
+
+    def log(msg):
+        if rank == 0:
+            print(msg, file=sys.stderr, flush=True)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    name, flats = load_workload(args.scene, log)
+    spp = args.spp
+    rts = []
+    stream = torch.cuda.current_stream()
+    for label, s in flats:
+        rt = rtb.RayTracer(local_rank)
+        rt.set_stream(stream.cuda_stream)
+        rt.init(s)
+        rt.set_params(traversal=abi.TRAV_FAST, partition=abi.PART_SPP if world > 1 else abi.PART_NONE,
+                      part_rank=rank, part_world=world)
+        rts.append(rt)
+    films = []
+    for rt in rts:
+        ptr, n = rt.film_device_ptr()
+        films.append(torch.as_tensor(_CudaArray(ptr, n), device="cuda"))
+    host = [torch.empty(f.numel(), dtype=torch.float32).pin_memory() for f in films] if rank == 0 else []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+    total_spp = spp * world
+
+    def render_all():
+        # rank r renders global sample indices {s : s % world == r}, spp of them
+        for rt in rts:
+            rt.clear()
+            rt.render(total_spp, 0)
+
+    def reduce_all():
+        if dist is not None:
+            for f in films:
+                dist.reduce(f, dst=0, op=dist.ReduceOp.SUM)
+
+    def step_device():
+        flush.zero_()
+        render_all()
+        reduce_all()
+
+    def step_e2e():
+        flush.zero_()
+        for i, rt in enumerate(rts):
+            rt.update_camera(rt.scene.camera)        # host struct through the ABI
+            rt.clear()
+            rt.render(total_spp, 0)
+            if dist is not None:
+                dist.reduce(films[i], dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                rt.read_film(host[i].numpy().reshape(rt.height, rt.width, 3))   # D2H into pinned memory
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step_device()
+    barrier()
+    launches0 = sum(rt.stats()["kernel_launches"] for rt in rts)
+    for rt in rts:
+        rt.clear()                       # also resets the per-context kernel timers / ray counters
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clk = clocks.stop() if clocks else None
+    # per-launch kernel time + work counters of the LAST step (clear() resets them each step)
+    st = [rt.stats() for rt in rts]
+    launches = sum(s["kernel_launches"] for s in st) - launches0
+    kern_ms = sum(s["render_ms"] for s in st)
+    n_launch_last = len(rts)
+    samples_rank = sum(s["samples"] for s in st)
+    rays_rank = sum(s["closest_rays"] + s["shadow_rays"] for s in st)
+    box, tri = sum(s["box_tests"] for s in st), sum(s["tri_tests"] for s in st)
+    samples_step = samples_rank * world
+    value = samples_step * args.steps / (ms_total / 1e3) / 1e6
+    mrays = rays_rank * world * args.steps / (ms_total / 1e3) / 1e6
+
+    # ---- e2e through the C ABI with host buffers
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = samples_step * args.e2e_steps / float(dt.item()) / 1e6
+    h2d = 160 * len(rts)
+    d2h = sum(f.numel() * 4 for f in films)
+
+    if rank == 0:
+        hbm, sm_max, how = measured_peaks()
+        # algorithmic bytes: 32 B per box test, 64 B per triangle test, 48 B per ray
+        # (32-B ray in, 16-B hit out), 24 B film read-modify-write per sample
+        alg_bytes = 32.0 * box + 64.0 * tri + 48.0 * rays_rank + 24.0 * samples_rank
+        alg_flops = 24.0 * box + 60.0 * tri
+        per_launch_ms = kern_ms / max(n_launch_last, 1)
+        achieved = alg_bytes / max(n_launch_last, 1) / (per_launch_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get("k_render_dram_bytes_per_launch")
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "spp_per_gpu": spp, "spp_total": total_spp, "partition": "spp slice",
+                       "traversal": "fast", "sampling": "strict", "l2": "flushed between steps (256 MiB memset)",
+                       "scene_source": "flat scenes staged at build time by the product flattener"},
+            "mrays_per_s": mrays, "rays_per_sample": rays_rank / max(samples_rank, 1),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": traffic, "peak_source": how, "kernel": "k_render<FAST,PATH>",
+                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kern_ms / (ms_total / args.steps),
+                         "alg_bytes_per_launch": alg_bytes / max(n_launch_last, 1),
+                         "note": "scene is L2-resident: the binding limit is FP32 issue, see roofline_fp32"},
+            "roofline_fp32": {"achieved_tflops": alg_flops / (kern_ms / 1e3) / 1e12, "peak_tflops": fp32_peak,
+                              "frac": alg_flops / (kern_ms / 1e3) / 1e12 / fp32_peak,
+                              "box_tests_per_ray": box / max(rays_rank, 1), "tri_tests_per_ray": tri / max(rays_rank, 1)},
+            "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": args.e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args, log)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="materialball7")
+    ap.add_argument("--spp", type=int, default=256)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
+    ap.add_argument("--ref-spp", type=int, default=4, help="spp per scene per step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,17 @@
+"""Tiny driver for ncu: one scene, a few spp, launches k_render twice (warm + profiled)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import raytracingrenderer_b200 as rtb
+from raytracingrenderer_b200 import abi
+name = sys.argv[1] if len(sys.argv) > 1 else "materialball"
+spp = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+trav = abi.TRAV_EXACT if (len(sys.argv) > 3 and sys.argv[3] == "exact") else abi.TRAV_FAST
+s = abi.FlatScene.load(os.path.join("scenes", "_cache", name + ".rtbs"))
+rt = rtb.RayTracer(0)
+rt.init(s)
+rt.set_params(traversal=trav)
+for i in range(2):
+    rt.clear(); rt.render(spp, 0); rt.synchronize()
+st = rt.stats()
+print(name, spp, "Msamples/s %.1f  Mrays/s %.1f  box/ray %.2f tri/ray %.2f" % (st["samples"]/st["render_ms"]/1e3, (st["closest_rays"]+st["shadow_rays"])/st["render_ms"]/1e3,
+      st["box_tests"]/(st["closest_rays"]+st["shadow_rays"]), st["tri_tests"]/(st["closest_rays"]+st["shadow_rays"])))
