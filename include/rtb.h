@@ -189,6 +189,11 @@ typedef enum rtb_filter {
 	RTB_FILTER_GAUSSIAN = 1 /* GaussianFilter(radius, alpha) (Imaging.h:155-187)       */
 } rtb_filter;
 
+typedef enum rtb_scheduler {
+	RTB_SCHED_WAVEFRONT = 0, /* staged extend / shade / shadow kernels over a pool of path slots  */
+	RTB_SCHED_MEGAKERNEL = 1 /* one thread per pixel runs whole paths (kept for A/B profiling)    */
+} rtb_scheduler;
+
 typedef enum rtb_partition {
 	RTB_PART_NONE = 0,
 	RTB_PART_SPP = 1, /* this rank renders sample indices s with s % world == rank      */
@@ -208,7 +213,8 @@ typedef struct rtb_params {
 	int32_t partition;  /* rtb_partition                                             */
 	int32_t part_rank, part_world;
 	float cull_rel;     /* FAST traversal: relative slack of the t-cull (1e-5)       */
-	int32_t reserved_[2];
+	int32_t scheduler;  /* rtb_scheduler                                             */
+	int32_t reserved_;
 } rtb_params; /* 64 B */
 
 /* Ray / hit records of the batched parity entry points. */

@@ -55,6 +55,7 @@ SAMPLING_STRICT, SAMPLING_IMPORTANCE = 0, 1
 TRAV_EXACT, TRAV_FAST = 0, 1
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 PART_NONE, PART_SPP, PART_TILE = 0, 1, 2
+SCHED_WAVEFRONT, SCHED_MEGAKERNEL = 0, 1
 MISS_ID = 0xFFFFFFFF
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -82,7 +83,7 @@ class Params(C.Structure):
         ("sampling", C.c_int32), ("traversal", C.c_int32), ("filter", C.c_int32),
         ("filter_radius", C.c_float), ("filter_alpha", C.c_float), ("seed", C.c_uint32),
         ("partition", C.c_int32), ("part_rank", C.c_int32), ("part_world", C.c_int32),
-        ("cull_rel", C.c_float), ("reserved_", C.c_int32 * 2),
+        ("cull_rel", C.c_float), ("scheduler", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

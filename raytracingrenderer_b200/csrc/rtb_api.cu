@@ -2,7 +2,7 @@
 // launch wrappers.  Device code: rtb_kernels.cuh.  Build: see raytracingrenderer_b200/build.py
 // (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo).
 #include "rtb_accel.hpp"
-#include "rtb_kernels.cuh"
+#include "rtb_wavefront.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -46,6 +46,13 @@ struct rtb_ctx
 	std::vector<EventPair> pending;
 	std::vector<cudaEvent_t> eventPool;
 	uint32_t fastDepth = 0;
+	// wavefront pool (allocated on first use, sized by film and spp)
+	void* wfState = nullptr;
+	size_t wfStateBytes = 0;
+	WfCtrl* wfCtrl = nullptr;
+	uint32_t wfCtrlEntries = 0;
+	int smCount = 148;
+	int extendBlocksPerSM[2] = {0, 0}, shadowBlocksPerSM[2] = {0, 0};
 };
 
 namespace
@@ -84,6 +91,10 @@ void freeScene(rtb_ctx* ctx)
 	if (ctx->film) cudaFree(ctx->film);
 	if (ctx->filmFiltered) cudaFree(ctx->filmFiltered);
 	if (ctx->tone) cudaFree(ctx->tone);
+	if (ctx->wfState) cudaFree(ctx->wfState);
+	if (ctx->wfCtrl) cudaFree(ctx->wfCtrl);
+	ctx->wfState = nullptr, ctx->wfStateBytes = 0;
+	ctx->wfCtrl = nullptr, ctx->wfCtrlEntries = 0;
 	ctx->film = ctx->filmFiltered = nullptr;
 	ctx->tone = nullptr;
 	ctx->haveScene = false;
@@ -181,6 +192,141 @@ static void launchRender(rtb_ctx* ctx, const RenderArgs& A, dim3 grid, dim3 bloc
 	}
 }
 
+
+static int renderMegakernel(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
+{
+	RenderArgs A;
+	A.film = ctx->film;
+	A.counters = ctx->counters;
+	A.spp_begin = spp_begin, A.spp_count = spp_count;
+	A.width = ctx->width, A.height = ctx->height;
+	A.P = ctx->params;
+	uint32_t warps = ((ctx->width + 7) / 8) * ((ctx->height + 3) / 4);
+	dim3 block(64), grid((warps + 1) / 2);
+	EventPair ev = {getEvent(ctx), getEvent(ctx)};
+	cudaEventRecord(ev.a, ctx->stream);
+	if (ctx->params.traversal == RTB_TRAV_EXACT) launchRender<RTB_TRAV_EXACT>(ctx, A, grid, block);
+	else launchRender<RTB_TRAV_FAST>(ctx, A, grid, block);
+	cudaEventRecord(ev.b, ctx->stream);
+	ctx->pending.push_back(ev);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	return RTB_OK;
+}
+
+template <int INTEGRATOR>
+static void launchShade(rtb_ctx* ctx, const WfArgs& A, uint32_t iter)
+{
+	k_wf_shade<INTEGRATOR><<<(A.nSlots + 127) / 128, 128, 0, ctx->stream>>>(ctx->S, A, iter);
+}
+
+// Wavefront schedule (rtb_wavefront.cuh).  Everything is enqueued up front on ctx->stream: the
+// iteration count is bounded by samples-per-stream x vertices-per-path and kernels of
+// iterations after the pool has drained return at once (they read ctrl[iter-1].alive).
+static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
+{
+	const rtb_params& P = ctx->params;
+	// local sample ordinals n -> global sample index sFirst + n * sStep
+	uint32_t sFirst = spp_begin, sStep = 1, sCount = spp_count;
+	if (P.partition == RTB_PART_SPP && P.part_world > 1)
+	{
+		uint32_t w = (uint32_t)P.part_world, r = (uint32_t)P.part_rank;
+		sFirst = spp_begin + (r + w - (spp_begin % w)) % w;
+		sStep = w;
+		uint64_t end = (uint64_t)spp_begin + spp_count;
+		sCount = (sFirst < end) ? (uint32_t)((end - 1 - sFirst) / w + 1) : 0u;
+	}
+	if (sCount == 0) return RTB_OK;
+	uint32_t tiles = ((ctx->width + 7) / 8) * ((ctx->height + 3) / 4);
+	uint32_t nPix = tiles * 32;
+	const uint32_t targetSlots = 4u << 20;
+	uint32_t streams = (targetSlots + nPix - 1) / nPix;
+	if (streams > 64) streams = 64;
+	if (streams > sCount) streams = sCount;
+	if (streams < 1) streams = 1;
+	uint64_t nSlots64 = (uint64_t)nPix * streams;
+	if (nSlots64 > 0x7FFFFFFFull) return fail(ctx, RTB_ERR_ARG, "film too large for the slot pool");
+	uint32_t nSlots = (uint32_t)nSlots64;
+	size_t need = (size_t)nSlots * 8 * sizeof(float4);
+	if (need > ctx->wfStateBytes)
+	{
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->wfState) cudaFree(ctx->wfState);
+		ctx->wfState = nullptr, ctx->wfStateBytes = 0;
+		CK(cudaMalloc(&ctx->wfState, need));
+		ctx->wfStateBytes = need;
+	}
+	uint32_t perStream = (sCount + streams - 1) / streams;
+	uint32_t vertices = (P.integrator == RTB_INT_PATH) ? (uint32_t)P.max_depth + 2u : 1u;
+	uint64_t iters64 = (uint64_t)perStream * vertices;
+	if (iters64 > (1u << 20)) return fail(ctx, RTB_ERR_ARG, "too many samples per call (%u per stream); split the render", perStream);
+	uint32_t iters = (uint32_t)iters64;
+	if (iters + 1 > ctx->wfCtrlEntries)
+	{
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->wfCtrl) cudaFree(ctx->wfCtrl);
+		ctx->wfCtrl = nullptr, ctx->wfCtrlEntries = 0;
+		CK(cudaMalloc((void**)&ctx->wfCtrl, (size_t)(iters + 1) * sizeof(WfCtrl)));
+		ctx->wfCtrlEntries = iters + 1;
+	}
+	CK(cudaMemsetAsync(ctx->wfCtrl, 0, (size_t)(iters + 1) * sizeof(WfCtrl), ctx->stream));
+	if (!ctx->extendBlocksPerSM[0])
+	{
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, ctx->device));
+		ctx->smCount = prop.multiProcessorCount;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extendBlocksPerSM[0], k_wf_extend<RTB_TRAV_EXACT>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extendBlocksPerSM[1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->shadowBlocksPerSM[0], k_wf_shadow<RTB_TRAV_EXACT>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->shadowBlocksPerSM[1], k_wf_shadow<RTB_TRAV_FAST>, 128, 0));
+	}
+	WfArgs A;
+	float4* base = (float4*)ctx->wfState;
+	A.rayO = base, A.rayD = base + (size_t)nSlots, A.hit = base + (size_t)nSlots * 2, A.thr = base + (size_t)nSlots * 3;
+	A.acc = base + (size_t)nSlots * 4, A.shO = base + (size_t)nSlots * 5, A.shD = base + (size_t)nSlots * 6;
+	A.shC = base + (size_t)nSlots * 7;
+	A.ctrl = ctx->wfCtrl;
+	A.counters = ctx->counters;
+	A.film = ctx->film;
+	A.nSlots = nSlots, A.nPix = nPix, A.streams = streams;
+	A.width = ctx->width, A.height = ctx->height;
+	A.sFirst = sFirst, A.sStep = sStep, A.sCount = sCount;
+	A.P = P;
+	int ti = (P.traversal == RTB_TRAV_EXACT) ? 0 : 1;
+	unsigned gridExtend = (unsigned)(ctx->smCount * (ctx->extendBlocksPerSM[ti] > 0 ? ctx->extendBlocksPerSM[ti] : 1));
+	unsigned gridShadow = (unsigned)(ctx->smCount * (ctx->shadowBlocksPerSM[ti] > 0 ? ctx->shadowBlocksPerSM[ti] : 1));
+	bool shadows = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_DIRECT);
+	EventPair ev = {getEvent(ctx), getEvent(ctx)};
+	cudaEventRecord(ev.a, ctx->stream);
+	k_wf_init<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(ctx->S, A);
+	ctx->launches++;
+	for (uint32_t it = 0; it < iters; it++)
+	{
+		if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
+		else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
+		switch (P.integrator)
+		{
+		case RTB_INT_DIRECT: launchShade<RTB_INT_DIRECT>(ctx, A, it); break;
+		case RTB_INT_ALBEDO: launchShade<RTB_INT_ALBEDO>(ctx, A, it); break;
+		case RTB_INT_NORMALS: launchShade<RTB_INT_NORMALS>(ctx, A, it); break;
+		default: launchShade<RTB_INT_PATH>(ctx, A, it); break;
+		}
+		ctx->launches += 2;
+		if (shadows)
+		{
+			if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridShadow, 128, 0, ctx->stream>>>(ctx->S, A, it);
+			else k_wf_shadow<RTB_TRAV_FAST><<<gridShadow, 128, 0, ctx->stream>>>(ctx->S, A, it);
+			ctx->launches++;
+		}
+	}
+	k_wf_resolve<<<(nPix + 255) / 256, 256, 0, ctx->stream>>>(A);
+	ctx->launches++;
+	cudaEventRecord(ev.b, ctx->stream);
+	ctx->pending.push_back(ev);
+	CK(cudaGetLastError());
+	return RTB_OK;
+}
+
 static int filteredFilm(rtb_ctx* ctx, const float** src)
 {
 	*src = ctx->film;
@@ -220,6 +366,7 @@ void rtb_default_params(rtb_params* p)
 	p->part_rank = 0;
 	p->part_world = 1;
 	p->cull_rel = 1e-5f;
+	p->scheduler = RTB_SCHED_WAVEFRONT;
 }
 
 int rtb_create(int device, rtb_ctx** out)
@@ -289,6 +436,8 @@ int rtb_set_params(rtb_ctx* ctx, const rtb_params* p)
 	if (p->partition < RTB_PART_NONE || p->partition > RTB_PART_TILE) return fail(ctx, RTB_ERR_ARG, "bad partition %d", p->partition);
 	if (p->partition != RTB_PART_NONE && (p->part_world < 1 || p->part_rank < 0 || p->part_rank >= p->part_world))
 		return fail(ctx, RTB_ERR_ARG, "bad partition rank %d of %d", p->part_rank, p->part_world);
+	if (p->scheduler != RTB_SCHED_WAVEFRONT && p->scheduler != RTB_SCHED_MEGAKERNEL) return fail(ctx, RTB_ERR_ARG, "bad scheduler %d", p->scheduler);
+	if (p->max_depth > 200) return fail(ctx, RTB_ERR_ARG, "max_depth too large");
 	if (p->max_depth < 0 || !(p->epsilon >= 0.0f)) return fail(ctx, RTB_ERR_ARG, "bad max_depth/epsilon");
 	ctx->params = *p;
 	return RTB_OK;
@@ -436,22 +585,9 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	if (spp_count == 0) return RTB_OK;
 	if ((uint64_t)spp_begin + spp_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "sample index overflow");
 	if (int rc = bind(ctx)) return rc;
-	RenderArgs A;
-	A.film = ctx->film;
-	A.counters = ctx->counters;
-	A.spp_begin = spp_begin, A.spp_count = spp_count;
-	A.width = ctx->width, A.height = ctx->height;
-	A.P = ctx->params;
-	uint32_t warps = ((ctx->width + 7) / 8) * ((ctx->height + 3) / 4);
-	dim3 block(64), grid((warps + 1) / 2);
-	EventPair ev = {getEvent(ctx), getEvent(ctx)};
-	cudaEventRecord(ev.a, ctx->stream);
-	if (ctx->params.traversal == RTB_TRAV_EXACT) launchRender<RTB_TRAV_EXACT>(ctx, A, grid, block);
-	else launchRender<RTB_TRAV_FAST>(ctx, A, grid, block);
-	cudaEventRecord(ev.b, ctx->stream);
-	ctx->pending.push_back(ev);
-	ctx->launches++;
-	CK(cudaGetLastError());
+	int rc = (ctx->params.scheduler == RTB_SCHED_MEGAKERNEL) ? renderMegakernel(ctx, spp_begin, spp_count)
+	                                                           : renderWavefront(ctx, spp_begin, spp_count);
+	if (rc) return rc;
 	ctx->spp += spp_count;
 	return RTB_OK;
 }

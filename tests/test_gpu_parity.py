@@ -255,6 +255,23 @@ def test_exact_and_fast_render_identical_films(rtb):
         assert rt.read_film().tobytes() == a.tobytes()
 
 
+def test_megakernel_and_wavefront_schedules_agree(rtb):
+    """Same samples, same RNG streams; only the summation order differs."""
+    for name in ("synthetic", "cornell-box"):
+        rt = gpu_scene(rtb, name)
+        rt.render(4, 0)
+        a = rt.read_film().copy()
+        sa = rt.stats()
+        rt.set_params(scheduler=abi.SCHED_MEGAKERNEL)
+        rt.clear()
+        rt.render(4, 0)
+        b = rt.read_film()
+        sb = rt.stats()
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+        for k in ("samples", "closest_rays", "shadow_rays"):
+            assert sa[k] == sb[k], k
+
+
 def test_cornell_image_against_reference_statistics(rtb):
     g = np.load(os.path.join(GOLDEN, "cornell_ref_blocks.npz"))
     rt = gpu_scene(rtb, "cornell-box")
