@@ -284,15 +284,24 @@ int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam);
 int rtb_clear(rtb_ctx* ctx);
 /* spp_count calls of RayTracer::render() (Renderer.h:876-885) in one go: accumulates the
  * samples with global indices [spp_begin, spp_begin + spp_count) of every pixel this rank
- * owns (see rtb_params.partition) into the device sum-film.  Asynchronous.  Resumable:
- * the RNG is keyed by (seed, pixel, sample index), not by call order.                    */
+ * owns (see rtb_params.partition) into the device sum-film.  Returns once the last batch of
+ * kernels is enqueued on the context's stream (it may wait for earlier batches; the final
+ * kernels still run asynchronously).  Resumable: the RNG is keyed by (seed, pixel, sample
+ * index), not by call order.                                                              */
 int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count);
 /* Film::film (Imaging.h:204): waits for the device and copies the running SUM (not the
  * mean; Film::save divides by SPP, Imaging.h:262-271) as width*height*3 floats (r,g,b per
  * pixel, row-major) to host memory; *spp receives Film::SPP.  Either may be NULL.         */
 int rtb_read_film(rtb_ctx* ctx, float* rgb_sum, uint32_t* spp);
-/* Device address of the sum film (width*height*3 floats) for the caller's NCCL reduce.   */
+/* Device address of the sum film (width*height*3 floats), e.g. for an NCCL reduce.         */
 int rtb_film_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_floats);
+/* The film's master copy: width*height*3 signed 64-bit FIXED-POINT sums in units of 2^-32
+ * (integer addition is associative: the film is bit-reproducible whatever the scheduling, and
+ * an int64 SUM-reduce of this buffer over the ranks of a tile- or spp-partitioned render gives
+ * exactly the single-GPU film).  After reducing into it, call rtb_set_spp with the global
+ * sample count; the float film is re-derived on the next read.                             */
+int rtb_accum_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_int64);
+int rtb_set_spp(rtb_ctx* ctx, uint32_t spp);
 /* Film::tonemap for every pixel (Imaging.h:233-242; what presentFilmToCanvas draws,
  * Renderer.h:69-80): width*height*3 bytes r,g,b.                                          */
 int rtb_tonemap(rtb_ctx* ctx, uint8_t* rgb8, float exposure);

@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "librtb200.so")
 ABI_SYMBOLS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_stream", "rtb_synchronize",
     "rtb_default_params", "rtb_set_params", "rtb_get_params", "rtb_upload_scene", "rtb_update_camera",
-    "rtb_clear", "rtb_render", "rtb_read_film", "rtb_film_device_ptr", "rtb_tonemap", "rtb_get_stats",
+    "rtb_clear", "rtb_render", "rtb_read_film", "rtb_film_device_ptr", "rtb_accum_device_ptr", "rtb_set_spp", "rtb_tonemap", "rtb_get_stats",
     "rtb_film_size", "rtb_primary_hits", "rtb_trace", "rtb_visible", "rtb_shading_data", "rtb_eval_bsdf",
     "rtb_eval_light", "rtb_rng_draws",
 ]
@@ -65,6 +65,8 @@ def lib():
         L.rtb_render.argtypes = [vp, u32, u32]
         L.rtb_read_film.argtypes = [vp, vp, C.POINTER(u32)]
         L.rtb_film_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.rtb_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.rtb_set_spp.argtypes = [vp, u32]
         L.rtb_tonemap.argtypes = [vp, vp, C.c_float]
         L.rtb_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
         L.rtb_film_size.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
@@ -185,6 +187,15 @@ class RayTracer:
         p, n = C.c_void_p(), C.c_uint64()
         self._ck(self._L.rtb_film_device_ptr(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def accum_device_ptr(self):
+        """(device pointer, count) of the int64 fixed-point film sums (2^-32 units)."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._L.rtb_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_spp(self, spp):
+        self._ck(self._L.rtb_set_spp(self._h, int(spp)))
 
     def tonemap(self, exposure=1.0):
         out = np.empty((self.height, self.width, 3), np.uint8)

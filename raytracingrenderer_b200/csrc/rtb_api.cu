@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -46,13 +47,21 @@ struct rtb_ctx
 	std::vector<EventPair> pending;
 	std::vector<cudaEvent_t> eventPool;
 	uint32_t fastDepth = 0;
-	// wavefront pool (allocated on first use, sized by film and spp)
+	long long* accum = nullptr; // fixed-point film sums (master copy; `film` is derived)
+	bool filmDirty = false;     // accum changed since the last resolve
+	// wavefront pool (allocated on first use)
 	void* wfState = nullptr;
 	size_t wfStateBytes = 0;
 	WfCtrl* wfCtrl = nullptr;
 	uint32_t wfCtrlEntries = 0;
+	WfGlobal* wfGlobal = nullptr;
+	uint32_t* wfTiles = nullptr;
+	uint32_t wfTileCount = 0;
+	int wfTilePart[3] = {-1, -1, -1}; // partition, rank, world the tile list was built for
+	unsigned long long* hostProbe = nullptr; // pinned: {nextJob, alive}
 	int smCount = 148;
-	int extendBlocksPerSM[2] = {0, 0}, shadowBlocksPerSM[2] = {0, 0};
+	uint32_t poolSlots = 1u << 20;
+	uint64_t wfIterations = 0, wfHostSyncs = 0;
 };
 
 namespace
@@ -93,8 +102,14 @@ void freeScene(rtb_ctx* ctx)
 	if (ctx->tone) cudaFree(ctx->tone);
 	if (ctx->wfState) cudaFree(ctx->wfState);
 	if (ctx->wfCtrl) cudaFree(ctx->wfCtrl);
+	if (ctx->wfGlobal) cudaFree(ctx->wfGlobal);
+	if (ctx->wfTiles) cudaFree(ctx->wfTiles);
+	if (ctx->accum) cudaFree(ctx->accum);
 	ctx->wfState = nullptr, ctx->wfStateBytes = 0;
 	ctx->wfCtrl = nullptr, ctx->wfCtrlEntries = 0;
+	ctx->wfGlobal = nullptr, ctx->wfTiles = nullptr, ctx->wfTileCount = 0;
+	ctx->wfTilePart[0] = ctx->wfTilePart[1] = ctx->wfTilePart[2] = -1;
+	ctx->accum = nullptr;
 	ctx->film = ctx->filmFiltered = nullptr;
 	ctx->tone = nullptr;
 	ctx->haveScene = false;
@@ -196,7 +211,7 @@ static void launchRender(rtb_ctx* ctx, const RenderArgs& A, dim3 grid, dim3 bloc
 static int renderMegakernel(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 {
 	RenderArgs A;
-	A.film = ctx->film;
+	A.accum = ctx->accum;
 	A.counters = ctx->counters;
 	A.spp_begin = spp_begin, A.spp_count = spp_count;
 	A.width = ctx->width, A.height = ctx->height;
@@ -211,22 +226,34 @@ static int renderMegakernel(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count
 	ctx->pending.push_back(ev);
 	ctx->launches++;
 	CK(cudaGetLastError());
+	ctx->filmDirty = true;
 	return RTB_OK;
 }
 
 template <int INTEGRATOR>
-static void launchShade(rtb_ctx* ctx, const WfArgs& A, uint32_t iter)
+static void launchShade(rtb_ctx* ctx, const WfArgs& A, uint32_t iter, unsigned grid)
 {
-	k_wf_shade<INTEGRATOR><<<(A.nSlots + 127) / 128, 128, 0, ctx->stream>>>(ctx->S, A, iter);
+	k_wf_shade<INTEGRATOR><<<grid, 128, 0, ctx->stream>>>(ctx->S, A, iter);
 }
 
-// Wavefront schedule (rtb_wavefront.cuh).  Everything is enqueued up front on ctx->stream: the
-// iteration count is bounded by samples-per-stream x vertices-per-path and kernels of
-// iterations after the pool has drained return at once (they read ctrl[iter-1].alive).
+// float film <- fixed-point sums (only when they changed)
+static int resolveFilm(rtb_ctx* ctx)
+{
+	if (!ctx->filmDirty) return RTB_OK;
+	uint32_t n = ctx->width * ctx->height * 3;
+	k_wf_resolve<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, ctx->film, n);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	ctx->filmDirty = false;
+	return RTB_OK;
+}
+
+// Wavefront schedule (rtb_wavefront.cuh).  The number of iterations depends on the paths, so
+// the launches are enqueued in batches sized from the measured job rate; between batches the
+// host reads {jobs claimed, slots alive} (one 16-byte copy + stream sync, a handful per call).
 static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 {
 	const rtb_params& P = ctx->params;
-	// local sample ordinals n -> global sample index sFirst + n * sStep
 	uint32_t sFirst = spp_begin, sStep = 1, sCount = spp_count;
 	if (P.partition == RTB_PART_SPP && P.part_world > 1)
 	{
@@ -237,17 +264,37 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		sCount = (sFirst < end) ? (uint32_t)((end - 1 - sFirst) / w + 1) : 0u;
 	}
 	if (sCount == 0) return RTB_OK;
-	uint32_t tiles = ((ctx->width + 7) / 8) * ((ctx->height + 3) / 4);
-	uint32_t nPix = tiles * 32;
-	const uint32_t targetSlots = 4u << 20;
-	uint32_t streams = (targetSlots + nPix - 1) / nPix;
-	if (streams > 64) streams = 64;
-	if (streams > sCount) streams = sCount;
-	if (streams < 1) streams = 1;
-	uint64_t nSlots64 = (uint64_t)nPix * streams;
-	if (nSlots64 > 0x7FFFFFFFull) return fail(ctx, RTB_ERR_ARG, "film too large for the slot pool");
-	uint32_t nSlots = (uint32_t)nSlots64;
-	size_t need = (size_t)nSlots * 8 * sizeof(float4);
+	// ---- owned 8x4 tiles (TILE_SIZE 32 tiles dealt round-robin, Renderer.h:18)
+	int part[3] = {P.partition == RTB_PART_TILE ? 1 : 0, P.partition == RTB_PART_TILE ? P.part_rank : 0,
+	               P.partition == RTB_PART_TILE ? P.part_world : 1};
+	if (!ctx->wfTiles || memcmp(part, ctx->wfTilePart, sizeof(part)) != 0)
+	{
+		uint32_t tilesX = (ctx->width + 7) / 8, tilesY = (ctx->height + 3) / 4, t32x = (ctx->width + 31) / 32;
+		std::vector<uint32_t> tiles;
+		tiles.reserve((size_t)tilesX * tilesY);
+		for (uint32_t ty = 0; ty < tilesY; ty++)
+			for (uint32_t tx = 0; tx < tilesX; tx++)
+			{
+				uint32_t tile32 = ((ty * 4) >> 5) * t32x + ((tx * 8) >> 5);
+				if (part[0] && part[2] > 1 && (int)(tile32 % (uint32_t)part[2]) != part[1]) continue;
+				tiles.push_back(ty * tilesX + tx);
+			}
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->wfTiles) cudaFree(ctx->wfTiles);
+		ctx->wfTiles = nullptr;
+		ctx->wfTileCount = (uint32_t)tiles.size();
+		if (!tiles.empty())
+		{
+			CK(cudaMalloc((void**)&ctx->wfTiles, tiles.size() * sizeof(uint32_t)));
+			CK(cudaMemcpy(ctx->wfTiles, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		}
+		memcpy(ctx->wfTilePart, part, sizeof(part));
+	}
+	if (ctx->wfTileCount == 0) return RTB_OK;
+	unsigned long long totalJobs = (unsigned long long)ctx->wfTileCount * 32ull * sCount;
+	uint32_t nSlots = ctx->poolSlots;
+	if ((unsigned long long)nSlots > totalJobs) nSlots = (uint32_t)((totalJobs + 31ull) & ~31ull);
+	size_t need = (size_t)nSlots * 7 * sizeof(float4);
 	if (need > ctx->wfStateBytes)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -256,79 +303,114 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		CK(cudaMalloc(&ctx->wfState, need));
 		ctx->wfStateBytes = need;
 	}
-	uint32_t perStream = (sCount + streams - 1) / streams;
+	if (!ctx->wfGlobal) CK(cudaMalloc((void**)&ctx->wfGlobal, sizeof(WfGlobal)));
+	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, 2 * sizeof(unsigned long long)));
 	uint32_t vertices = (P.integrator == RTB_INT_PATH) ? (uint32_t)P.max_depth + 2u : 1u;
-	uint64_t iters64 = (uint64_t)perStream * vertices;
-	if (iters64 > (1u << 20)) return fail(ctx, RTB_ERR_ARG, "too many samples per call (%u per stream); split the render", perStream);
-	uint32_t iters = (uint32_t)iters64;
-	if (iters + 1 > ctx->wfCtrlEntries)
+	// list-scheduling bound on the iterations: total work / slots + longest job
+	unsigned long long bound64 = (totalJobs * vertices + nSlots - 1) / nSlots + vertices + 1;
+	if (bound64 > (1ull << 22)) return fail(ctx, RTB_ERR_ARG, "too many samples per call; split the render");
+	uint32_t bound = (uint32_t)bound64;
+	if (bound > ctx->wfCtrlEntries)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->wfCtrl) cudaFree(ctx->wfCtrl);
 		ctx->wfCtrl = nullptr, ctx->wfCtrlEntries = 0;
-		CK(cudaMalloc((void**)&ctx->wfCtrl, (size_t)(iters + 1) * sizeof(WfCtrl)));
-		ctx->wfCtrlEntries = iters + 1;
+		CK(cudaMalloc((void**)&ctx->wfCtrl, (size_t)bound * sizeof(WfCtrl)));
+		ctx->wfCtrlEntries = bound;
 	}
-	CK(cudaMemsetAsync(ctx->wfCtrl, 0, (size_t)(iters + 1) * sizeof(WfCtrl), ctx->stream));
-	if (!ctx->extendBlocksPerSM[0])
+	CK(cudaMemsetAsync(ctx->wfCtrl, 0, (size_t)bound * sizeof(WfCtrl), ctx->stream));
+	CK(cudaMemsetAsync(ctx->wfGlobal, 0, sizeof(WfGlobal), ctx->stream));
+	WfArgs A;
+	float4* base = (float4*)ctx->wfState;
+	A.rayO = base, A.rayD = base + (size_t)nSlots, A.hit = base + (size_t)nSlots * 2, A.thr = base + (size_t)nSlots * 3;
+	A.shO = base + (size_t)nSlots * 4, A.shD = base + (size_t)nSlots * 5, A.shC = base + (size_t)nSlots * 6;
+	A.ctrl = ctx->wfCtrl;
+	A.glob = ctx->wfGlobal;
+	A.tileList = ctx->wfTiles;
+	A.counters = ctx->counters;
+	A.accum = ctx->accum;
+	A.nSlots = nSlots, A.nTiles = ctx->wfTileCount;
+	A.width = ctx->width, A.height = ctx->height;
+	A.sFirst = sFirst, A.sStep = sStep, A.sCount = sCount;
+	A.totalJobs = totalJobs;
+	A.P = P;
+	int ti = (P.traversal == RTB_TRAV_EXACT) ? 0 : 1;
+	if (ctx->smCount <= 0 || !ctx->wfIterations)
 	{
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, ctx->device));
 		ctx->smCount = prop.multiProcessorCount;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extendBlocksPerSM[0], k_wf_extend<RTB_TRAV_EXACT>, 128, 0));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->extendBlocksPerSM[1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->shadowBlocksPerSM[0], k_wf_shadow<RTB_TRAV_EXACT>, 128, 0));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->shadowBlocksPerSM[1], k_wf_shadow<RTB_TRAV_FAST>, 128, 0));
 	}
-	WfArgs A;
-	float4* base = (float4*)ctx->wfState;
-	A.rayO = base, A.rayD = base + (size_t)nSlots, A.hit = base + (size_t)nSlots * 2, A.thr = base + (size_t)nSlots * 3;
-	A.acc = base + (size_t)nSlots * 4, A.shO = base + (size_t)nSlots * 5, A.shD = base + (size_t)nSlots * 6;
-	A.shC = base + (size_t)nSlots * 7;
-	A.ctrl = ctx->wfCtrl;
-	A.counters = ctx->counters;
-	A.film = ctx->film;
-	A.nSlots = nSlots, A.nPix = nPix, A.streams = streams;
-	A.width = ctx->width, A.height = ctx->height;
-	A.sFirst = sFirst, A.sStep = sStep, A.sCount = sCount;
-	A.P = P;
-	int ti = (P.traversal == RTB_TRAV_EXACT) ? 0 : 1;
-	unsigned gridExtend = (unsigned)(ctx->smCount * (ctx->extendBlocksPerSM[ti] > 0 ? ctx->extendBlocksPerSM[ti] : 1));
-	unsigned gridShadow = (unsigned)(ctx->smCount * (ctx->shadowBlocksPerSM[ti] > 0 ? ctx->shadowBlocksPerSM[ti] : 1));
+	// grid-stride kernels: enough blocks to fill the machine, never more than the work
+	unsigned maxBlocks = (unsigned)ctx->smCount * 16u;
+	unsigned gridSlots = (nSlots + 127) / 128;
+	if (gridSlots > maxBlocks) gridSlots = maxBlocks;
 	bool shadows = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_DIRECT);
 	EventPair ev = {getEvent(ctx), getEvent(ctx)};
 	cudaEventRecord(ev.a, ctx->stream);
 	k_wf_init<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(ctx->S, A);
 	ctx->launches++;
-	for (uint32_t it = 0; it < iters; it++)
+	uint32_t it = 0;
+	uint32_t batch = vertices * 4 < 16 ? 16 : vertices * 4;
+	bool drained = false;
+	while (!drained && it < bound)
 	{
-		if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
-		else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
-		switch (P.integrator)
+		uint32_t end = it + batch;
+		if (end > bound) end = bound;
+		for (; it < end; it++)
 		{
-		case RTB_INT_DIRECT: launchShade<RTB_INT_DIRECT>(ctx, A, it); break;
-		case RTB_INT_ALBEDO: launchShade<RTB_INT_ALBEDO>(ctx, A, it); break;
-		case RTB_INT_NORMALS: launchShade<RTB_INT_NORMALS>(ctx, A, it); break;
-		default: launchShade<RTB_INT_PATH>(ctx, A, it); break;
+			if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
+			else k_wf_extend<RTB_TRAV_FAST><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
+			switch (P.integrator)
+			{
+			case RTB_INT_DIRECT: launchShade<RTB_INT_DIRECT>(ctx, A, it, gridSlots); break;
+			case RTB_INT_ALBEDO: launchShade<RTB_INT_ALBEDO>(ctx, A, it, gridSlots); break;
+			case RTB_INT_NORMALS: launchShade<RTB_INT_NORMALS>(ctx, A, it, gridSlots); break;
+			default: launchShade<RTB_INT_PATH>(ctx, A, it, gridSlots); break;
+			}
+			ctx->launches += 2;
+			if (shadows)
+			{
+				if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
+				else k_wf_shadow<RTB_TRAV_FAST><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
+				ctx->launches++;
+			}
 		}
-		ctx->launches += 2;
-		if (shadows)
+		ctx->wfIterations += batch;
+		// probe: jobs claimed so far and slots alive after the last enqueued iteration
+		CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(&ctx->hostProbe[1], &ctx->wfCtrl[it - 1], sizeof(WfCtrl), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		ctx->wfHostSyncs++;
+		unsigned long long claimed = ctx->hostProbe[0];
+		uint32_t alive = (uint32_t)(ctx->hostProbe[1] >> 32); // WfCtrl{nShadow, alive}: alive is the high word
+		if (alive == 0)
 		{
-			if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridShadow, 128, 0, ctx->stream>>>(ctx->S, A, it);
-			else k_wf_shadow<RTB_TRAV_FAST><<<gridShadow, 128, 0, ctx->stream>>>(ctx->S, A, it);
-			ctx->launches++;
+			drained = true;
+			break;
 		}
+		// predict the remaining iterations from the job rate seen so far
+		unsigned long long started = claimed < totalJobs ? claimed : totalJobs;
+		double perIter = (started > nSlots) ? (double)(started - nSlots) / (double)it : 0.0;
+		double remaining = (double)(totalJobs - started);
+		double predict = (perIter > 0.0) ? remaining / perIter : (double)batch * 2.0;
+		uint32_t next = (uint32_t)(predict * 0.9);
+		if (remaining == 0.0) next = vertices; // tail: the last paths finish within `vertices` iterations
+		if (next < 4) next = 4;
+		if (next > 4096) next = 4096;
+		batch = next;
 	}
-	k_wf_resolve<<<(nPix + 255) / 256, 256, 0, ctx->stream>>>(A);
-	ctx->launches++;
 	cudaEventRecord(ev.b, ctx->stream);
 	ctx->pending.push_back(ev);
 	CK(cudaGetLastError());
+	if (!drained) return fail(ctx, RTB_ERR_STATE, "wavefront did not drain within its iteration bound (%u)", bound);
+	ctx->filmDirty = true;
 	return RTB_OK;
 }
 
 static int filteredFilm(rtb_ctx* ctx, const float** src)
 {
+	if (int rc = resolveFilm(ctx)) return rc;
 	*src = ctx->film;
 	if (ctx->params.filter != RTB_FILTER_GAUSSIAN) return RTB_OK;
 	size_t npx = (size_t)ctx->width * ctx->height;
@@ -406,6 +488,7 @@ void rtb_destroy(rtb_ctx* ctx)
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
 	freeScene(ctx);
 	if (ctx->counters) cudaFree(ctx->counters);
+	if (ctx->hostProbe) cudaFreeHost(ctx->hostProbe);
 	delete ctx;
 }
 
@@ -546,6 +629,14 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 	size_t npx = (size_t)ctx->width * ctx->height;
 	CK(cudaMalloc((void**)&ctx->film, npx * 3 * sizeof(float)));
 	CK(cudaMemsetAsync(ctx->film, 0, npx * 3 * sizeof(float), ctx->stream));
+	CK(cudaMalloc((void**)&ctx->accum, npx * 3 * sizeof(long long)));
+	CK(cudaMemsetAsync(ctx->accum, 0, npx * 3 * sizeof(long long), ctx->stream));
+	ctx->filmDirty = false;
+	if (const char* e = getenv("RTB_POOL_SLOTS"))
+	{
+		long v = atol(e);
+		if (v >= 1024 && v <= (64l << 20)) ctx->poolSlots = (uint32_t)v & ~31u;
+	}
 	CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
 	ctx->spp = 0;
 	ctx->renderMs = 0.0;
@@ -571,6 +662,8 @@ int rtb_clear(rtb_ctx* ctx)
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = bind(ctx)) return rc;
 	CK(cudaMemsetAsync(ctx->film, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(float), ctx->stream));
+	CK(cudaMemsetAsync(ctx->accum, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(long long), ctx->stream));
+	ctx->filmDirty = false;
 	CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
 	resolveTimings(ctx);
 	ctx->spp = 0;
@@ -612,8 +705,27 @@ int rtb_film_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_floats)
 {
 	if (!ctx || !dptr) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = bind(ctx)) return rc;
+	if (int rc = resolveFilm(ctx)) return rc;
 	*dptr = ctx->film;
 	if (n_floats) *n_floats = (uint64_t)ctx->width * ctx->height * 3;
+	return RTB_OK;
+}
+
+int rtb_accum_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_int64)
+{
+	if (!ctx || !dptr) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	*dptr = ctx->accum;
+	if (n_int64) *n_int64 = (uint64_t)ctx->width * ctx->height * 3;
+	ctx->filmDirty = true; // the caller may reduce into it
+	return RTB_OK;
+}
+
+int rtb_set_spp(rtb_ctx* ctx, uint32_t spp)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	ctx->spp = spp;
 	return RTB_OK;
 }
 

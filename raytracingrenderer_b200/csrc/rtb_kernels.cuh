@@ -7,7 +7,7 @@
 
 struct RenderArgs
 {
-	float* film;                   // width*height*3 running sums (Film::film)
+	long long* accum;              // width*height*3 fixed-point running sums (Film::film, see filmAdd)
 	unsigned long long* counters;  // [0] samples [1] closest rays [2] shadow rays [3] box tests [4] tri tests
 	uint32_t spp_begin, spp_count;
 	uint32_t width, height;
@@ -29,6 +29,27 @@ RTB_DEV void flushTally(const Tally& c, unsigned long long* counters)
 		for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
 		if ((threadIdx.x & 31) == 0 && x) atomicAdd(&counters[k], (unsigned long long)x);
 	}
+}
+
+// ---------------------------------------------------------------------------------------
+// fixed-point film
+// ---------------------------------------------------------------------------------------
+#define RTB_FIX_SCALE 4294967296.0f /* 2^32 */
+#define RTB_FIX_LIMIT 1073741824.0f /* 2^30: a single contribution is clamped to +-1e9 */
+
+RTB_DEV long long toFixed(float c)
+{
+	// NaN contributes nothing (the reference would poison the pixel for good); +-inf clamps
+	if (!(c == c)) return 0ll;
+	c = fminf(fmaxf(c, -RTB_FIX_LIMIT), RTB_FIX_LIMIT);
+	return __float2ll_rn(c * RTB_FIX_SCALE);
+}
+RTB_DEV void filmAdd(long long* accum, uint32_t pixel, V3 c)
+{
+	long long* a = accum + (size_t)pixel * 3;
+	if (c.x != 0.0f) atomicAdd((unsigned long long*)a, (unsigned long long)toFixed(c.x));
+	if (c.y != 0.0f) atomicAdd((unsigned long long*)a + 1, (unsigned long long)toFixed(c.y));
+	if (c.z != 0.0f) atomicAdd((unsigned long long*)a + 2, (unsigned long long)toFixed(c.z));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -171,7 +192,7 @@ __global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene 
 		{
 			uint32_t pixel = py * A.width + px;
 			RayD primary = generateRay(S.cam, (float)px + 0.5f, (float)py + 0.5f);
-			V3 acc = mk(0.0f, 0.0f, 0.0f);
+			long long accX = 0, accY = 0, accZ = 0; // fixed point: the same film whatever the schedule
 			uint32_t s = sBegin, curS = 0;
 			bool alive = false;
 			RayD ray = primary;
@@ -261,15 +282,15 @@ __global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene 
 				}
 				if (done)
 				{
-					acc = acc + Lo;
+					accX += toFixed(Lo.x), accY += toFixed(Lo.y), accZ += toFixed(Lo.z);
 					tl.samples++;
 					alive = false;
 				}
 			}
-			float* f = A.film + (size_t)pixel * 3;
-			f[0] += acc.x;
-			f[1] += acc.y;
-			f[2] += acc.z;
+			long long* f = A.accum + (size_t)pixel * 3; // this thread owns the pixel during the launch
+			f[0] += accX;
+			f[1] += accY;
+			f[2] += accZ;
 		}
 	}
 	flushTally(tl, A.counters);
