@@ -59,8 +59,9 @@ struct rtb_ctx
 	uint32_t wfTileCount = 0;
 	int wfTilePart[3] = {-1, -1, -1}; // partition, rank, world the tile list was built for
 	unsigned long long* hostProbe = nullptr; // pinned: {nextJob, alive}
-	int smCount = 148;
-	uint32_t poolSlots = 1u << 20;
+	int smCount = 0;
+	int travBlocksPerSM[2][2] = {{0, 0}, {0, 0}}; // [extend|shadow][exact|fast]
+	uint32_t poolSlots = 1u << 21;
 	uint64_t wfIterations = 0, wfHostSyncs = 0;
 };
 
@@ -304,7 +305,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		ctx->wfStateBytes = need;
 	}
 	if (!ctx->wfGlobal) CK(cudaMalloc((void**)&ctx->wfGlobal, sizeof(WfGlobal)));
-	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, 2 * sizeof(unsigned long long)));
+	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, 4 * sizeof(unsigned long long)));
 	uint32_t vertices = (P.integrator == RTB_INT_PATH) ? (uint32_t)P.max_depth + 2u : 1u;
 	// list-scheduling bound on the iterations: total work / slots + longest job
 	unsigned long long bound64 = (totalJobs * vertices + nSlots - 1) / nSlots + vertices + 1;
@@ -335,12 +336,18 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	A.totalJobs = totalJobs;
 	A.P = P;
 	int ti = (P.traversal == RTB_TRAV_EXACT) ? 0 : 1;
-	if (ctx->smCount <= 0 || !ctx->wfIterations)
+	if (ctx->smCount <= 0)
 	{
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, ctx->device));
 		ctx->smCount = prop.multiProcessorCount;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0][0], k_wf_extend<RTB_TRAV_EXACT>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0][1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1][0], k_wf_shadow<RTB_TRAV_EXACT>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1][1], k_wf_shadow<RTB_TRAV_FAST>, 128, 0));
 	}
+	// persistent traversal kernels: exactly one resident wave
+	unsigned gridExtend = (unsigned)(ctx->smCount * (ctx->travBlocksPerSM[0][ti] > 0 ? ctx->travBlocksPerSM[0][ti] : 1));
 	// grid-stride kernels: enough blocks to fill the machine, never more than the work
 	unsigned maxBlocks = (unsigned)ctx->smCount * 16u;
 	unsigned gridSlots = (nSlots + 127) / 128;
@@ -357,10 +364,11 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	{
 		uint32_t end = it + batch;
 		if (end > bound) end = bound;
+		ctx->wfIterations += end - it;
 		for (; it < end; it++)
 		{
-			if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
-			else k_wf_extend<RTB_TRAV_FAST><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
+			if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
+			else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
 			switch (P.integrator)
 			{
 			case RTB_INT_DIRECT: launchShade<RTB_INT_DIRECT>(ctx, A, it, gridSlots); break;
@@ -376,10 +384,9 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 				ctx->launches++;
 			}
 		}
-		ctx->wfIterations += batch;
 		// probe: jobs claimed so far and slots alive after the last enqueued iteration
 		CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(&ctx->hostProbe[1], &ctx->wfCtrl[it - 1], sizeof(WfCtrl), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(&ctx->hostProbe[1], &ctx->wfCtrl[it - 1], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
 		ctx->wfHostSyncs++;
 		unsigned long long claimed = ctx->hostProbe[0];

@@ -32,8 +32,10 @@
 
 struct WfCtrl
 {
-	unsigned int nShadow; // shadow rays queued by k_wf_shade of this iteration
-	unsigned int alive;   // slots alive after k_wf_shade of this iteration
+	unsigned int nShadow;    // shadow rays queued by k_wf_shade of this iteration
+	unsigned int alive;      // slots alive after k_wf_shade of this iteration
+	unsigned int extendHead; // next unclaimed chunk of slots (k_wf_extend)
+	unsigned int shadowHead; // next unclaimed chunk of shadow rays (k_wf_shadow)
 };
 
 struct WfGlobal
@@ -263,32 +265,211 @@ RTB_DEV bool visibleFastBody(const DevScene& S, const RayD& r, float eps, float 
 	}
 }
 
+// ---------------------------------------------------------------------------------------
+// Persistent traversal kernels.  profiles/r01_v3_wavefront_dynjobs_summary.txt: one thread per
+// ray keeps 8.7 of 32 lanes busy (a warp lasts as long as its longest ray).  Here every warp
+// owns a contiguous range of slots and keeps all lanes fed: each lane holds its CURRENT ray and
+// a PREFETCHED next one (loads issued long before they are consumed, no atomics); a lane that
+// finishes swaps the prefetched ray in.  Inside a warp, interior-node steps and leaf steps are
+// scheduled by majority vote so that at least half of the busy lanes take part in every step.
+// The per-ray decisions are those of closestFastBody / visibleFastBody.
+// ---------------------------------------------------------------------------------------
+#define WF_REFILL_IDLE 6 /* refill once this many lanes are idle */
+#define WF_CHUNK 128u
+#define WF_CHUNK_SHADOW 64u
+
+template <bool ANYHIT>
+struct LaneTrav
+{
+	RayD r;
+	float bestT; // closest: best t so far; any-hit: maxT
+	uint32_t bestId;
+	float bestU, bestV;
+	int32_t cur;
+	int sp;
+};
+
+template <bool ANYHIT>
+RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const int32_t* stackNode, const float* stackT, float cullRel)
+{
+	t.cur = RTB_TRAV_DONE_;
+	while (t.sp > 0)
+	{
+		t.sp--;
+		float te = stackT[t.sp];
+		bool cull = ANYHIT ? ((te - fabsf(te) * cullRel) >= t.bestT) : ((te - fabsf(te) * cullRel) > t.bestT);
+		if (cull) continue;
+		t.cur = stackNode[t.sp];
+		break;
+	}
+}
+
+template <bool ANYHIT>
+RTB_DEV void laneInterior(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel,
+                          uint32_t& nBox)
+{
+	const float4* nd = S.fnodes + (size_t)t.cur * 4;
+	float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
+	float t0, t1;
+	nBox += 2;
+	bool h0 = slabTestNoNaN(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, t.r, t0);
+	bool h1 = slabTestNoNaN(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, t.r, t1);
+	if (ANYHIT)
+	{
+		h0 = h0 && !((t0 - fabsf(t0) * cullRel) >= t.bestT);
+		h1 = h1 && !((t1 - fabsf(t1) * cullRel) >= t.bestT);
+	}
+	else
+	{
+		h0 = h0 && !((t0 - fabsf(t0) * cullRel) > t.bestT);
+		h1 = h1 && !((t1 - fabsf(t1) * cullRel) > t.bestT);
+	}
+	int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
+	if (h0 && h1)
+	{
+		bool swap = !ANYHIT && (t1 < t0);
+		stackNode[t.sp] = swap ? c0 : c1;
+		stackT[t.sp] = swap ? t0 : t1;
+		t.sp++;
+		t.cur = swap ? c1 : c0;
+	}
+	else if (h0) t.cur = c0;
+	else if (h1) t.cur = c1;
+	else lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
+}
+
 template <int TRAV>
 __global__ void __launch_bounds__(128) k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
 	const rtb_params& P = A.P;
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
 	Tally tl = {0, 0, 0, 0, 0};
-	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.nSlots; slot += gridDim.x * blockDim.x)
+	if (TRAV == RTB_TRAV_EXACT || S.fast_root < 0)
 	{
-		float4 d = A.rayD[slot];
-		if (!(__float_as_uint(d.w) & WF_ALIVE)) continue;
-		float4 o = A.rayO[slot];
-		RayD r = mkRay(mk(o), mk(d));
-		HitD h;
-		tl.closest++;
-		if (TRAV == RTB_TRAV_EXACT || rayIsDegenerate(r) || S.fast_root < 0) closestExact(S, r, P.epsilon, h, tl.box, tl.tri);
-		else closestFastBody(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
-		A.hit[slot] = make_float4(__uint_as_float(h.id), h.t, h.alpha, h.beta);
+		// parity path: the reference's own tree, one thread per slot
+		for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.nSlots; slot += gridDim.x * blockDim.x)
+		{
+			float4 d = A.rayD[slot];
+			if (!(__float_as_uint(d.w) & WF_ALIVE)) continue;
+			float4 o = A.rayO[slot];
+			RayD r = mkRay(mk(o), mk(d));
+			HitD h;
+			tl.closest++;
+			closestExact(S, r, P.epsilon, h, tl.box, tl.tri);
+			A.hit[slot] = make_float4(__uint_as_float(h.id), h.t, h.alpha, h.beta);
+		}
+		flushTally(tl, A.counters);
+		return;
+	}
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t ltMask = (1u << lane) - 1u;
+	// work is claimed in chunks of WF_CHUNK consecutive slots (one atomic per chunk and warp)
+	uint32_t cursor = 0, end = 0;
+	bool exhausted = false;
+	int32_t stackNode[RTB_STACK];
+	float stackT[RTB_STACK];
+	LaneTrav<false> t;
+	t.cur = RTB_TRAV_DONE_;
+	t.sp = 0;
+	uint32_t slot = 0, preSlot = 0;
+	float4 preO = make_float4(0, 0, 0, 0), preD = make_float4(0, 0, 0, 0);
+	bool have = false, pre = false;
+	for (;;)
+	{
+		// ---- promote the prefetched ray of every idle lane
+		if (!have && pre)
+		{
+			pre = false;
+			if (__float_as_uint(preD.w) & WF_ALIVE)
+			{
+				t.r = mkRay(mk(preO), mk(preD));
+				t.bestT = FLT_MAX, t.bestId = RTB_MISS_ID, t.bestU = t.bestV = 0.0f;
+				t.sp = 0;
+				slot = preSlot;
+				have = true;
+				tl.closest++;
+				if (rayIsDegenerate(t.r))
+				{
+					// 0*inf = NaN rays take the reference's own tree
+					HitD h;
+					closestExact(S, t.r, P.epsilon, h, tl.box, tl.tri);
+					A.hit[slot] = make_float4(__uint_as_float(h.id), h.t, h.alpha, h.beta);
+					have = false;
+				}
+				else
+					t.cur = S.fast_root;
+			}
+		}
+		// ---- issue the next prefetches from the warp's chunk
+		unsigned want = __ballot_sync(0xFFFFFFFFu, !pre);
+		if (want && cursor >= end && !exhausted)
+		{
+			uint32_t c = 0;
+			if (lane == 0) c = atomicAdd(&A.ctrl[iter].extendHead, (unsigned)WF_CHUNK);
+			c = __shfl_sync(0xFFFFFFFFu, c, 0);
+			if (c >= A.nSlots) exhausted = true;
+			else
+			{
+				cursor = c;
+				end = (c + WF_CHUNK < A.nSlots) ? c + WF_CHUNK : A.nSlots;
+			}
+		}
+		if (want && cursor < end)
+		{
+			uint32_t idx = cursor + __popc(want & ltMask);
+			if (!pre && idx < end)
+			{
+				preO = A.rayO[idx];
+				preD = A.rayD[idx];
+				preSlot = idx;
+				pre = true;
+			}
+			cursor += __popc(want);
+		}
+		unsigned busy = __ballot_sync(0xFFFFFFFFu, have);
+		if (!busy)
+		{
+			if (!__ballot_sync(0xFFFFFFFFu, pre) && cursor >= end && exhausted) break;
+			continue;
+		}
+		// ---- traverse until enough lanes are idle to make a refill worthwhile
+		for (;;)
+		{
+			unsigned mI = __ballot_sync(0xFFFFFFFFu, have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_);
+			unsigned mL = __ballot_sync(0xFFFFFFFFu, have && t.cur < 0);
+			if (__popc(mI) >= __popc(mL))
+			{
+				if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) laneInterior<false>(S, t, stackNode, stackT, P.cull_rel, tl.box);
+			}
+			else if (have && t.cur < 0)
+			{
+				HitD h;
+				h.id = t.bestId, h.t = t.bestT, h.alpha = t.bestU, h.beta = t.bestV;
+				leafClosest(S, t.cur, t.r, P.epsilon, h, tl.tri);
+				t.bestId = h.id, t.bestT = h.t, t.bestU = h.alpha, t.bestV = h.beta;
+				lanePop<false>(t, stackNode, stackT, P.cull_rel);
+			}
+			if (have && t.cur == RTB_TRAV_DONE_)
+			{
+				A.hit[slot] = make_float4(__uint_as_float(t.bestId), t.bestT, t.bestU, t.bestV);
+				have = false;
+			}
+			unsigned idle = __ballot_sync(0xFFFFFFFFu, !have);
+			if (idle == 0xFFFFFFFFu) break;
+			if (__popc(idle) >= WF_REFILL_IDLE && (__ballot_sync(0xFFFFFFFFu, pre) & idle)) break;
+		}
 	}
 	flushTally(tl, A.counters);
 }
 
+// Shadow rays: one thread per queued ray.  (A persistent/prefetching variant like k_wf_extend was
+// measured slower here — profiles/r01_v4_persistent_traversal.txt: the queue holds only ~0.2 rays
+// per slot and any-hit rays are short, so the refill bookkeeping outweighs the regained lanes.)
 template <int TRAV>
 __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
 	const rtb_params& P = A.P;
-	uint32_t n = A.ctrl[iter].nShadow;
+	const uint32_t n = A.ctrl[iter].nShadow;
 	Tally tl = {0, 0, 0, 0, 0};
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{
