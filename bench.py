@@ -199,16 +199,11 @@ def cpu_baseline(args, log):
             "sample": "%s at %d spp through oracle/rtb_oracle.c" % (name, spp)}
 
 
-class _CudaArray:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
     import raytracingrenderer_b200 as rtb
-    from raytracingrenderer_b200 import abi
+    from raytracingrenderer_b200 import abi, distributed as D
 
     def log(msg):
         if rank == 0:
@@ -229,14 +224,10 @@ def run_ours(args, rank, world, local_rank):
         rt = rtb.RayTracer(local_rank)
         rt.set_stream(stream.cuda_stream)
         rt.init(s)
-        rt.set_params(traversal=abi.TRAV_FAST, partition=abi.PART_SPP if world > 1 else abi.PART_NONE,
-                      part_rank=rank, part_world=world)
+        rt.set_params(traversal=abi.TRAV_FAST, **D.partition_params(rank, world, "spp"))
         rts.append(rt)
-    films = []
-    for rt in rts:
-        ptr, n = rt.film_device_ptr()
-        films.append(torch.as_tensor(_CudaArray(ptr, n), device="cuda"))
-    host = [torch.empty(f.numel(), dtype=torch.float32).pin_memory() for f in films] if rank == 0 else []
+    accs = [D.accum_tensor(rt) for rt in rts]      # int64 fixed-point film sums (exact reduction)
+    host = [torch.empty(a.numel(), dtype=torch.float32).pin_memory() for a in accs] if rank == 0 else []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
     total_spp = spp * world
 
@@ -248,8 +239,8 @@ def run_ours(args, rank, world, local_rank):
 
     def reduce_all():
         if dist is not None:
-            for f in films:
-                dist.reduce(f, dst=0, op=dist.ReduceOp.SUM)
+            for rt in rts:
+                D.reduce_film(rt, total_spp)
 
     def step_device():
         flush.zero_()
@@ -263,7 +254,7 @@ def run_ours(args, rank, world, local_rank):
             rt.clear()
             rt.render(total_spp, 0)
             if dist is not None:
-                dist.reduce(films[i], dst=0, op=dist.ReduceOp.SUM)
+                D.reduce_film(rt, total_spp)
             if rank == 0:
                 rt.read_film(host[i].numpy().reshape(rt.height, rt.width, 3))   # D2H into pinned memory
 
@@ -291,14 +282,18 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clk = clocks.stop() if clocks else None
-    # per-launch kernel time + work counters of the LAST step (clear() resets them each step)
+    # per-stage kernel time + work counters of the LAST step (clear() resets them each step)
     st = [rt.stats() for rt in rts]
     launches = sum(s["kernel_launches"] for s in st) - launches0
     kern_ms = sum(s["render_ms"] for s in st)
-    n_launch_last = len(rts)
     samples_rank = sum(s["samples"] for s in st)
-    rays_rank = sum(s["closest_rays"] + s["shadow_rays"] for s in st)
+    closest, shadow = sum(s["closest_rays"] for s in st), sum(s["shadow_rays"] for s in st)
+    rays_rank = closest + shadow
     box, tri = sum(s["box_tests"] for s in st), sum(s["tri_tests"] for s in st)
+    sbox, stri = sum(s["shadow_box_tests"] for s in st), sum(s["shadow_tri_tests"] for s in st)
+    iters = sum(s["iterations"] for s in st)
+    timed = max(sum(s["timed_iterations"] for s in st), 1)
+    stage_ms = {k: sum(s[k + "_ms"] for s in st) / timed for k in ("extend", "shade", "shadow")}   # avg per launch
     samples_step = samples_rank * world
     value = samples_step * args.steps / (ms_total / 1e3) / 1e6
     mrays = rays_rank * world * args.steps / (ms_total / 1e3) / 1e6
@@ -316,20 +311,27 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_val = samples_step * args.e2e_steps / float(dt.item()) / 1e6
     h2d = 160 * len(rts)
-    d2h = sum(f.numel() * 4 for f in films)
+    d2h = sum(a.numel() * 4 for a in accs)
 
     if rank == 0:
         hbm, sm_max, how = measured_peaks()
-        # algorithmic bytes: 32 B per box test, 64 B per triangle test, 48 B per ray
-        # (32-B ray in, 16-B hit out), 24 B film read-modify-write per sample
-        alg_bytes = 32.0 * box + 64.0 * tri + 48.0 * rays_rank + 24.0 * samples_rank
-        alg_flops = 24.0 * box + 60.0 * tri
-        per_launch_ms = kern_ms / max(n_launch_last, 1)
-        achieved = alg_bytes / max(n_launch_last, 1) / (per_launch_ms / 1e3) / 1e9
+        # Dominant kernel = the stage with the largest measured share.  Algorithmic bytes per
+        # launch: traversal stages 32 B per box test + 64 B per triangle test + 48 B
+        # per ray (32-B ray in, 16-B hit out); shade stage 64 B slot state in + 48 B out + 24 B
+        # film read-modify-write per vertex.
+        n_iter = max(iters, 1)
+        alg = {"extend": (32.0 * box + 64.0 * tri + 48.0 * closest) / n_iter,
+               "shadow": (32.0 * sbox + 64.0 * stri + 48.0 * shadow) / n_iter,
+               "shade": (64.0 + 48.0 + 24.0) * closest / n_iter}
+        dom = max(stage_ms, key=lambda k: stage_ms[k])
+        per_launch_ms = stage_ms[dom]
+        achieved = alg[dom] / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+        stage_total = sum(stage_ms.values())
+        alg_flops = 24.0 * (box + sbox) + 60.0 * (tri + stri)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get("k_render_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("k_wf_%s_dram_bytes_per_launch" % dom)
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -340,13 +342,16 @@ def run_ours(args, rank, world, local_rank):
                        "scene_source": "flat scenes staged at build time by the product flattener"},
             "mrays_per_s": mrays, "rays_per_sample": rays_rank / max(samples_rank, 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": how, "kernel": "k_render<FAST,PATH>",
-                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kern_ms / (ms_total / args.steps),
-                         "alg_bytes_per_launch": alg_bytes / max(n_launch_last, 1),
-                         "note": "scene is L2-resident: the binding limit is FP32 issue, see roofline_fp32"},
+                         "traffic": traffic, "peak_source": how, "kernel": "k_wf_%s" % dom,
+                         "kernel_ms_per_launch": per_launch_ms,
+                         "kernel_share_of_step": stage_ms[dom] / stage_total if stage_total else None,
+                         "stage_ms_per_launch": stage_ms, "launches_per_render": n_iter / max(len(rts), 1),
+                         "alg_bytes_per_launch": alg[dom],
+                         "note": "scene (<= 10 MB) and slot pool are L2/L1 traffic; the stages are latency/divergence "
+                                 "bound, not HBM bound - see roofline_fp32 and profiles/"},
             "roofline_fp32": {"achieved_tflops": alg_flops / (kern_ms / 1e3) / 1e12, "peak_tflops": fp32_peak,
                               "frac": alg_flops / (kern_ms / 1e3) / 1e12 / fp32_peak,
-                              "box_tests_per_ray": box / max(rays_rank, 1), "tri_tests_per_ray": tri / max(rays_rank, 1)},
+                              "box_tests_per_ray": (box + sbox) / max(rays_rank, 1), "tri_tests_per_ray": (tri + stri) / max(rays_rank, 1)},
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps},
             "gpu_launches": int(launches),

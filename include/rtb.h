@@ -245,8 +245,13 @@ typedef struct rtb_stats {
 	uint64_t closest_rays;  /* Scene::traverse calls                               */
 	uint64_t shadow_rays;   /* Scene::visible calls                                */
 	uint64_t kernel_launches; /* kernels of this library launched since create     */
-	double render_ms;       /* device time of the render kernels since last clear  */
-	uint64_t box_tests, tri_tests; /* only when built with RTB_COUNT_TESTS          */
+	double render_ms;       /* device time of the render calls since last clear    */
+	uint64_t box_tests, tri_tests; /* closest-hit traversal work (both children of a visited node count) */
+	uint64_t shadow_box_tests, shadow_tri_tests; /* any-hit traversal work          */
+	/* wavefront schedule: device time of the three stage kernels, measured with CUDA events
+	 * on every 8th iteration (timed_iterations of them) since the last clear             */
+	double extend_ms, shade_ms, shadow_ms;
+	uint64_t timed_iterations, iterations, host_syncs;
 } rtb_stats;
 
 /* ------------------------------------------------------------------------------------

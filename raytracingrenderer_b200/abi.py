@@ -91,7 +91,9 @@ class Stats(C.Structure):
     _fields_ = [
         ("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("box_tests", C.c_uint64),
-        ("tri_tests", C.c_uint64),
+        ("tri_tests", C.c_uint64), ("shadow_box_tests", C.c_uint64), ("shadow_tri_tests", C.c_uint64),
+        ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("shadow_ms", C.c_double),
+        ("timed_iterations", C.c_uint64), ("iterations", C.c_uint64), ("host_syncs", C.c_uint64),
     ]
 
 

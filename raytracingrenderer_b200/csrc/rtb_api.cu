@@ -25,6 +25,10 @@ struct EventPair
 {
 	cudaEvent_t a, b;
 };
+struct StageEvents
+{
+	cudaEvent_t e[4]; // before extend, after extend, after shade, after shadow
+};
 } // namespace
 
 struct rtb_ctx
@@ -45,6 +49,9 @@ struct rtb_ctx
 	uint64_t launches = 0;
 	double renderMs = 0.0;
 	std::vector<EventPair> pending;
+	std::vector<StageEvents> pendingStages;
+	double stageMs[3] = {0, 0, 0};
+	uint64_t timedIterations = 0;
 	std::vector<cudaEvent_t> eventPool;
 	uint32_t fastDepth = 0;
 	long long* accum = nullptr; // fixed-point film sums (master copy; `film` is derived)
@@ -187,6 +194,20 @@ void resolveTimings(rtb_ctx* ctx)
 		ctx->eventPool.push_back(p.b);
 	}
 	ctx->pending.clear();
+	for (StageEvents& s : ctx->pendingStages)
+	{
+		if (cudaEventSynchronize(s.e[3]) == cudaSuccess)
+		{
+			for (int k = 0; k < 3; k++)
+			{
+				float ms = 0.0f;
+				if (cudaEventElapsedTime(&ms, s.e[k], s.e[k + 1]) == cudaSuccess) ctx->stageMs[k] += ms;
+			}
+			ctx->timedIterations++;
+		}
+		for (int k = 0; k < 4; k++) ctx->eventPool.push_back(s.e[k]);
+	}
+	ctx->pendingStages.clear();
 }
 
 int checkTrav(rtb_ctx* ctx, int traversal)
@@ -367,8 +388,16 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		ctx->wfIterations += end - it;
 		for (; it < end; it++)
 		{
+			bool timed = (it % 8u) == 4u;
+			StageEvents se;
+			if (timed)
+			{
+				for (int k = 0; k < 4; k++) se.e[k] = getEvent(ctx);
+				cudaEventRecord(se.e[0], ctx->stream);
+			}
 			if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
 			else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
+			if (timed) cudaEventRecord(se.e[1], ctx->stream);
 			switch (P.integrator)
 			{
 			case RTB_INT_DIRECT: launchShade<RTB_INT_DIRECT>(ctx, A, it, gridSlots); break;
@@ -377,11 +406,17 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 			default: launchShade<RTB_INT_PATH>(ctx, A, it, gridSlots); break;
 			}
 			ctx->launches += 2;
+			if (timed) cudaEventRecord(se.e[2], ctx->stream);
 			if (shadows)
 			{
 				if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
 				else k_wf_shadow<RTB_TRAV_FAST><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
 				ctx->launches++;
+			}
+			if (timed)
+			{
+				cudaEventRecord(se.e[3], ctx->stream);
+				ctx->pendingStages.push_back(se);
 			}
 		}
 		// probe: jobs claimed so far and slots alive after the last enqueued iteration
@@ -675,6 +710,8 @@ int rtb_clear(rtb_ctx* ctx)
 	resolveTimings(ctx);
 	ctx->spp = 0;
 	ctx->renderMs = 0.0;
+	ctx->stageMs[0] = ctx->stageMs[1] = ctx->stageMs[2] = 0.0;
+	ctx->timedIterations = 0, ctx->wfIterations = 0, ctx->wfHostSyncs = 0;
 	return RTB_OK;
 }
 
@@ -772,8 +809,13 @@ int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out)
 	memset(out, 0, sizeof(*out));
 	out->samples = c[0], out->closest_rays = c[1], out->shadow_rays = c[2];
 	out->box_tests = c[3], out->tri_tests = c[4];
+	out->shadow_box_tests = c[5], out->shadow_tri_tests = c[6];
 	out->kernel_launches = ctx->launches;
 	out->render_ms = ctx->renderMs;
+	out->extend_ms = ctx->stageMs[0], out->shade_ms = ctx->stageMs[1], out->shadow_ms = ctx->stageMs[2];
+	out->timed_iterations = ctx->timedIterations;
+	out->iterations = ctx->wfIterations;
+	out->host_syncs = ctx->wfHostSyncs;
 	return RTB_OK;
 }
 

@@ -8,7 +8,7 @@
 struct RenderArgs
 {
 	long long* accum;              // width*height*3 fixed-point running sums (Film::film, see filmAdd)
-	unsigned long long* counters;  // [0] samples [1] closest rays [2] shadow rays [3] box tests [4] tri tests
+	unsigned long long* counters;  // [0] samples [1] closest rays [2] shadow rays [3] box [4] tri (closest) [5] box [6] tri (shadow)
 	uint32_t spp_begin, spp_count;
 	uint32_t width, height;
 	rtb_params P;
@@ -16,14 +16,14 @@ struct RenderArgs
 
 struct Tally
 {
-	uint32_t samples, closest, shadow, box, tri;
+	uint32_t samples, closest, shadow, box, tri, sbox, stri;
 };
 
 RTB_DEV void flushTally(const Tally& c, unsigned long long* counters)
 {
-	uint32_t v[5] = {c.samples, c.closest, c.shadow, c.box, c.tri};
+	uint32_t v[7] = {c.samples, c.closest, c.shadow, c.box, c.tri, c.sbox, c.stri};
 #pragma unroll
-	for (int k = 0; k < 5; k++)
+	for (int k = 0; k < 7; k++)
 	{
 		uint32_t x = v[k];
 		for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
@@ -80,7 +80,7 @@ RTB_DEV V3 computeDirect(const DevScene& S, const rtb_params& P, const ShadeD& s
 		if (G > 0.0f)
 		{
 			tl.shadow++;
-			if (sceneVisible<TRAV>(S, sd.x, p, P.epsilon, P.cull_rel, tl.box, tl.tri))
+			if (sceneVisible<TRAV>(S, sd.x, p, P.epsilon, P.cull_rel, tl.sbox, tl.stri))
 			{
 				return ((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G) / (pmf * pdf);
 			}
@@ -141,7 +141,7 @@ RTB_DEV V3 computeDirect(const DevScene& S, const rtb_params& P, const ShadeD& s
 	if (G > 0.0f)
 	{
 		tl.shadow++;
-		if (sceneVisible<TRAV>(S, sd.x, sd.x + (wi * 10000.0f), P.epsilon, P.cull_rel, tl.box, tl.tri))
+		if (sceneVisible<TRAV>(S, sd.x, sd.x + (wi * 10000.0f), P.epsilon, P.cull_rel, tl.sbox, tl.stri))
 		{
 			return ((bsdfEvaluate(S, m, sd, wi) * emitted) * G) / (pmf * pdf);
 		}
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene 
 	uint32_t lane = threadIdx.x & 31u;
 	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	uint32_t tilesX = (A.width + 7u) >> 3, tilesY = (A.height + 3u) >> 2;
-	Tally tl = {0, 0, 0, 0, 0};
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
 	if (warp < tilesX * tilesY)
 	{
 		uint32_t px = (warp % tilesX) * 8u + (lane & 7u);
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128) k_primary(const __grid_constant__ DevScen
                                                  rtb_ray* rays, unsigned long long* counters)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	Tally tl = {0, 0, 0, 0, 0};
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
 	if (i < width * height)
 	{
 		uint32_t px = i % width, py = i / width;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DevScene 
                                                unsigned long long* counters)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	Tally tl = {0, 0, 0, 0, 0};
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
 	if (i < n)
 	{
 		rtb_ray q = rays[i];
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DevScene 
 		rtb_hit o;
 		if (anyHit)
 		{
-			bool vis = anyVisible<TRAV>(S, r, eps, q.tmax, cull, tl.box, tl.tri);
+			bool vis = anyVisible<TRAV>(S, r, eps, q.tmax, cull, tl.sbox, tl.stri);
 			tl.shadow++;
 			o.id = vis ? 0u : 1u;
 			o.t = o.alpha = o.beta = o.gamma = 0.0f;
@@ -365,11 +365,11 @@ __global__ void __launch_bounds__(128) k_visible(const __grid_constant__ DevScen
                                                  unsigned long long* counters)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	Tally tl = {0, 0, 0, 0, 0};
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
 	if (i < n)
 	{
 		const float* p = p1p2 + i * 6;
-		bool vis = sceneVisible<TRAV>(S, mk(p), mk(p + 3), eps, cull, tl.box, tl.tri);
+		bool vis = sceneVisible<TRAV>(S, mk(p), mk(p + 3), eps, cull, tl.sbox, tl.stri);
 		tl.shadow++;
 		out[i] = vis ? 1 : 0;
 	}

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) k_wf_extend(const __grid_constant__ DevSc
 {
 	const rtb_params& P = A.P;
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
-	Tally tl = {0, 0, 0, 0, 0};
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
 	if (TRAV == RTB_TRAV_EXACT || S.fast_root < 0)
 	{
 		// parity path: the reference's own tree, one thread per slot
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevSc
 {
 	const rtb_params& P = A.P;
 	const uint32_t n = A.ctrl[iter].nShadow;
-	Tally tl = {0, 0, 0, 0, 0};
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{
 		float4 o = A.shO[i], d = A.shD[i];
@@ -478,8 +478,8 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevSc
 		float maxT = o.w;
 		tl.shadow++;
 		bool vis;
-		if (TRAV == RTB_TRAV_EXACT || rayIsDegenerate(r) || S.fast_root < 0) vis = visibleExact(S, r, P.epsilon, maxT, tl.box, tl.tri);
-		else vis = visibleFastBody(S, r, P.epsilon, maxT, P.cull_rel, tl.box, tl.tri);
+		if (TRAV == RTB_TRAV_EXACT || rayIsDegenerate(r) || S.fast_root < 0) vis = visibleExact(S, r, P.epsilon, maxT, tl.sbox, tl.stri);
+		else vis = visibleFastBody(S, r, P.epsilon, maxT, P.cull_rel, tl.sbox, tl.stri);
 		if (vis) filmAdd(A.accum, __float_as_uint(d.w), mk(A.shC[i]));
 	}
 	flushTally(tl, A.counters);

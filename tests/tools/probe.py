@@ -35,8 +35,8 @@ for name in scenes:
         res["render_" + tname] = {"s": tb - ta, "msamples_s": st["samples"] / (tb - ta) / 1e6,
             "mrays_s": (st["closest_rays"] + st["shadow_rays"]) / (tb - ta) / 1e6, "mean": film.mean(axis=(0, 1)).tolist(),
             "rays_per_sample": (st["closest_rays"] + st["shadow_rays"]) / max(st["samples"], 1),
-            "box_per_ray": st["box_tests"] / max(st["closest_rays"] + st["shadow_rays"], 1),
-            "tri_per_ray": st["tri_tests"] / max(st["closest_rays"] + st["shadow_rays"], 1),
+            "box_per_ray": (st["box_tests"] + st["shadow_box_tests"]) / max(st["closest_rays"] + st["shadow_rays"], 1),
+            "tri_per_ray": (st["tri_tests"] + st["shadow_tri_tests"]) / max(st["closest_rays"] + st["shadow_rays"], 1),
             "render_ms": st["render_ms"], "nan": int(np.isnan(film).sum())}
     rspp = 4 if name != "bathroom" else 1
     rf, n, secs = rs.render(rspp, 0)

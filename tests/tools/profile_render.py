@@ -14,4 +14,7 @@ for i in range(2):
     rt.clear(); rt.render(spp, 0); rt.synchronize()
 st = rt.stats()
 print(name, spp, "Msamples/s %.1f  Mrays/s %.1f  box/ray %.2f tri/ray %.2f" % (st["samples"]/st["render_ms"]/1e3, (st["closest_rays"]+st["shadow_rays"])/st["render_ms"]/1e3,
-      st["box_tests"]/(st["closest_rays"]+st["shadow_rays"]), st["tri_tests"]/(st["closest_rays"]+st["shadow_rays"])))
+      (st["box_tests"]+st["shadow_box_tests"])/(st["closest_rays"]+st["shadow_rays"]), (st["tri_tests"]+st["shadow_tri_tests"])/(st["closest_rays"]+st["shadow_rays"])))
+print("  stage ms/launch: extend %.4f shade %.4f shadow %.4f  iterations %d host syncs %d launches %d" % (
+    st["extend_ms"]/max(st["timed_iterations"],1), st["shade_ms"]/max(st["timed_iterations"],1), st["shadow_ms"]/max(st["timed_iterations"],1),
+    st["iterations"], st["host_syncs"], st["kernel_launches"]))
