@@ -9,6 +9,9 @@
 #define RTB_MISS_ID 0xFFFFFFFFu
 #define RTB_PI_F 3.14159274101257324f   /* (float)M_PI */
 #define RTB_PI_D 3.14159265358979323846 /* M_PI */
+#define RTB_2PI_F 6.28318548202514648f  /* (float)(2 M_PI) */
+#define RTB_INV_PI_F 0.318309873342514038f
+#define RTB_INV_2PI_F 0.159154936671257019f
 
 // Device view of an uploaded scene; passed to kernels by value (__grid_constant__).
 struct DevScene
@@ -496,17 +499,25 @@ RTB_DEV V3 sampleTexture(const DevScene& S, int tex, float tu, float tv)
 	rtb_texture T = S.texs[tex];
 	float u = stdMax(0.0f, fabsf(tu)) * (float)T.width;
 	float v = stdMax(0.0f, fabsf(tv)) * (float)T.height;
-	int x = (int)floorf(u);
-	int y = (int)floorf(v);
-	float fu = u - (float)x;
-	float fv = v - (float)y;
+	float flu = floorf(u), flv = floorf(v);
+	float fu = u - flu;
+	float fv = v - flv;
 	float w0 = (1.0f - fu) * (1.0f - fv);
 	float w1 = fu * (1.0f - fv);
 	float w2 = (1.0f - fu) * fv;
 	float w3 = fu * fv;
-	x = x % T.width;
-	y = y % T.height;
-	int x1 = (x + 1) % T.width, y1 = (y + 1) % T.height;
+	if (T.width == 1 && T.height == 1)
+	{
+		// constant-colour textures (most materials): all four taps are texel 0
+		V3 a = texel(S.texels, T.offset, 0);
+		return (((a * w0) + (a * w1)) + (a * w2)) + (a * w3);
+	}
+	int x = (int)flu;
+	int y = (int)flv;
+	// x % width, (x + 1) % width with x >= 0; coordinates inside [0, 1) need no division
+	if (x >= T.width) x = x % T.width;
+	if (y >= T.height) y = y % T.height;
+	int x1 = (x + 1 == T.width) ? 0 : x + 1, y1 = (y + 1 == T.height) ? 0 : y + 1;
 	V3 a = texel(S.texels, T.offset, y * T.width + x);
 	V3 b = texel(S.texels, T.offset, y * T.width + x1);
 	V3 c = texel(S.texels, T.offset, y1 * T.width + x);
@@ -516,8 +527,10 @@ RTB_DEV V3 sampleTexture(const DevScene& S, int tex, float tu, float tv)
 
 // ---------------------------------------------------------------------------------------
 // SamplingDistributions (RTBase/Sampling.h:29-70) + sphericalToWorld (Core.h:547-550).
-// `2.0f * M_PI * r2` is a double product in the reference; a float product differs by
-// <= 1 ulp of phi, far inside the 1e-5 evaluation tolerance.
+// `2.0f * M_PI * r2` is a double product in the reference; the float product used here differs
+// by <= 1 ulp of phi, far inside the 1e-5 evaluation tolerance.  The same holds for the other
+// places where the reference's arithmetic silently promotes to double (x / M_PI): they are done
+// in float with a reciprocal multiply (<= 1.5 ulp).
 // ---------------------------------------------------------------------------------------
 RTB_DEV V3 sphericalToWorld(float theta, float phi)
 {
@@ -529,13 +542,13 @@ RTB_DEV V3 sphericalToWorld(float theta, float phi)
 RTB_DEV V3 cosineSampleHemisphere(float r1, float r2)
 {
 	float theta = acosf(sqrtf(r1));
-	float phi = (float)(2.0 * RTB_PI_D * (double)r2);
+	float phi = RTB_2PI_F * r2;
 	return sphericalToWorld(theta, phi);
 }
 RTB_DEV V3 uniformSampleSphere(float r1, float r2)
 {
 	float theta = acosf(1.0f - 2.0f * r1);
-	float phi = (float)(2.0 * RTB_PI_D * (double)r2);
+	float phi = RTB_2PI_F * r2;
 	return sphericalToWorld(theta, phi);
 }
 
@@ -554,14 +567,14 @@ RTB_DEV V3 bsdfEvaluate(const DevScene& S, const rtb_material& m, const ShadeD& 
 	(void)wi;
 	if (m.type == RTB_BSDF_GLASS) return mk(0.0f, 0.0f, 0.0f);     // Materials.h:295-299
 	if (m.type == RTB_BSDF_MIRROR) return bsdfAlbedo(S, m, sd);     // Materials.h:178-183 (sic)
-	return bsdfAlbedo(S, m, sd) / RTB_PI_F;                         // albedo / M_PI
+	return bsdfAlbedo(S, m, sd) * RTB_INV_PI_F;                     // albedo / M_PI
 }
 
 RTB_DEV float bsdfPdf(const rtb_material& m, const ShadeD& sd, V3 wi)
 {
 	if (m.type == RTB_BSDF_GLASS || m.type == RTB_BSDF_MIRROR) return 0.0f;
 	V3 l = toLocal(sd, wi);
-	return (l.z >= 0.0f) ? (float)((double)l.z / RTB_PI_D) : 0.0f; // cosineHemispherePDF, Sampling.h:44-48
+	return (l.z >= 0.0f) ? l.z * RTB_INV_PI_F : 0.0f; // cosineHemispherePDF, Sampling.h:44-48
 }
 
 // ShadingHelper::fresnelDielectric (Materials.h:55-77), including its non-standard Fpe
@@ -624,10 +637,10 @@ RTB_DEV V3 bsdfSample(const DevScene& S, const rtb_material& m, const ShadeD& sd
 	// Lambert-like stubs.  DiffuseBSDF clamps the pdf (Materials.h:130), the others use
 	// pdf = wi.z / M_PI un-clamped (:222, :339, :384, :437).
 	V3 wl = cosineSampleHemisphere(r1, r2);
-	float p = (float)((double)wl.z / RTB_PI_D);
+	float p = wl.z * RTB_INV_PI_F;
 	if (m.type == RTB_BSDF_DIFFUSE && !(wl.z >= 0.0f)) p = 0.0f;
 	pdf = p;
-	f = bsdfAlbedo(S, m, sd) / RTB_PI_F;
+	f = bsdfAlbedo(S, m, sd) * RTB_INV_PI_F;
 	return toWorld(sd, wl);
 }
 
@@ -638,9 +651,9 @@ RTB_DEV V3 bsdfSample(const DevScene& S, const rtb_material& m, const ShadeD& sd
 RTB_DEV V3 envLookup(const DevScene& S, int tex, V3 wi)
 {
 	float u = atan2f(wi.z, wi.x);
-	u = (u < 0.0f) ? (float)((double)u + (2.0 * RTB_PI_D)) : u;
-	u = (float)((double)u / (2.0 * RTB_PI_D));
-	float v = (float)((double)acosf(wi.y) / RTB_PI_D);
+	u = (u < 0.0f) ? u + RTB_2PI_F : u;
+	u = u * RTB_INV_2PI_F;
+	float v = acosf(wi.y) * RTB_INV_PI_F;
 	return sampleTexture(S, tex, u, v);
 }
 // Scene::background->evaluate(dir)

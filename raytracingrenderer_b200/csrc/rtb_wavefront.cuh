@@ -129,6 +129,33 @@ RTB_DEV bool wfClaimJob(const DevScene& S, const WfArgs& A, uint32_t slot, bool 
 	return live;
 }
 
+
+// One global atomic per BLOCK: every thread asks for `want` (0 or 1) consecutive items of the
+// counter; returns the thread's item index.  All threads of the block must call it.
+template <class CounterT>
+RTB_DEV CounterT blockReserve(CounterT* counter, bool want, CounterT* sBase, uint32_t* sWarpCount)
+{
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+	unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
+	if (lane == 0) sWarpCount[warp] = __popc(mask);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t total = 0;
+		for (uint32_t i = 0; i < nWarps; i++)
+		{
+			uint32_t c = sWarpCount[i];
+			sWarpCount[i] = total;
+			total += c;
+		}
+		*sBase = total ? atomicAdd(counter, (CounterT)total) : (CounterT)0;
+	}
+	__syncthreads();
+	CounterT at = *sBase + (CounterT)sWarpCount[warp] + (CounterT)__popc(mask & ((1u << lane) - 1u));
+	__syncthreads(); // the shared words are reused by the next call
+	return at;
+}
+
 __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A)
 {
 	uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,7 +536,7 @@ RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& 
 		V3 nL = triangleGNormal(S, L.triangle);
 		float G = (selMax(dot(wi, sd.sN), 0.0f) * selMax(-dot(wi, nL), 0.0f)) / l;
 		if (!(G > 0.0f)) return false;
-		contrib = ((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G) / (pmf * pdf);
+		contrib = divFast((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G, pmf * pdf);
 		p1 = sd.x;
 		p2 = p;
 		return true;
@@ -555,12 +582,12 @@ RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& 
 	else
 	{
 		wi = uniformSampleSphere(r1, r2);
-		pdf = (float)(1.0 / (4.0 * RTB_PI_D));
+		pdf = 0.0795774683356285095f; // 1 / (4 pi)
 		emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
 	}
 	float G = selMax(dot(wi, sd.sN), 0.0f);
 	if (!(G > 0.0f)) return false;
-	contrib = ((bsdfEvaluate(S, m, sd, wi) * emitted) * G) / (pmf * pdf);
+	contrib = divFast((bsdfEvaluate(S, m, sd, wi) * emitted) * G, pmf * pdf);
 	p1 = sd.x;
 	p2 = sd.x + (wi * 10000.0f);
 	return true;
@@ -573,7 +600,10 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DevSce
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
 	const uint32_t lane = threadIdx.x & 31u;
 	uint32_t nAlive = 0, nDone = 0;
-	// whole warps stride together: the cooperative queue/job operations below need every lane
+	__shared__ uint32_t sWarpCount[4];
+	__shared__ unsigned int sBase32;
+	__shared__ unsigned long long sBase64;
+	// whole blocks stride together: the cooperative queue/job operations below need every lane
 	uint32_t nRounds = (A.nSlots + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
 	for (uint32_t round = 0; round < nRounds; round++)
 	{
@@ -652,14 +682,14 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DevSce
 								float rr = selMin(lum(T), P.rr_cap);
 								if (ua.w < rr)
 								{
-									T = T / rr;
+									T = divFast(T, rr);
 									float4 ub = rngBlock(P.seed, pixel, sample, 2u * depth + 1u);
 									V3 f;
 									float pdf;
 									V3 wi = bsdfSample(S, m, sd, ub.x, ub.y, ub.z, f, pdf);
 									bool spec = (m.flags & RTB_MAT_SPECULAR) != 0;
-									if (spec) T = (T * f) / pdf;
-									else T = ((T * f) * fabsf(dot(wi, sd.sN))) / pdf;
+									if (spec) T = divFast(T * f, pdf);
+									else T = divFast((T * f) * fabsf(dot(wi, sd.sN)), pdf);
 									V3 o = sd.x + (wi * P.epsilon);
 									A.rayO[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(q));
 									A.rayD[slot] = make_float4(wi.x, wi.y, wi.z,
@@ -675,23 +705,28 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DevSce
 				filmAdd(A.accum, pixel, add);
 			}
 		}
-		// ---- compact append of this warp's shadow rays
-		unsigned sm = __ballot_sync(0xFFFFFFFFu, haveShadow);
-		if (sm)
+		// ---- compact append of the block's shadow rays (one atomic per block)
 		{
-			int leader = __ffs(sm) - 1;
-			uint32_t base = 0;
-			if ((int)lane == leader) base = atomicAdd(&A.ctrl[iter].nShadow, (unsigned)__popc(sm));
-			base = __shfl_sync(0xFFFFFFFFu, base, leader);
-			if (haveShadow)
-			{
-				uint32_t at = base + __popc(sm & ((1u << lane) - 1u));
-				A.shO[at] = sO, A.shD[at] = sD, A.shC[at] = sC;
-			}
+			uint32_t at = blockReserve<unsigned int>(&A.ctrl[iter].nShadow, haveShadow, &sBase32, sWarpCount);
+			if (haveShadow) A.shO[at] = sO, A.shD[at] = sD, A.shC[at] = sC;
 		}
-		// ---- regeneration: finished paths take the next jobs of the render
+		// ---- regeneration: finished paths take the next jobs of the render (one atomic per
+		// block; the rare lanes that drew a padding pixel of an edge tile retry warp-wise)
 		if (done) nDone++;
-		bool live = wfClaimJob(S, A, inRange ? slot : 0u, done);
+		bool live = false;
+		{
+			unsigned long long j = blockReserve<unsigned long long>(&A.glob->nextJob, done, &sBase64, sWarpCount);
+			bool retry = false;
+			if (done)
+			{
+				if (j < A.totalJobs)
+				{
+					live = wfStartJob(S, A, slot, j);
+					retry = !live;
+				}
+			}
+			if (__any_sync(0xFFFFFFFFu, retry)) live = wfClaimJob(S, A, inRange ? slot : 0u, retry) || live;
+		}
 		if (done && !live) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
 		if (aliveAfter || live) nAlive++;
 	}
