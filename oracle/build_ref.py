@@ -76,6 +76,27 @@ def make_shadow(name, patch_depth=False):
     return d
 
 
+def make_dropin_shadow():
+    """Like make_shadow, but Renderer.h is the PRODUCT's drop-in header."""
+    d = make_shadow("shadow_dropin")
+    os.unlink(os.path.join(d, "Renderer.h"))
+    os.symlink(os.path.join(ROOT, "raytracingrenderer_b200", "host", "Renderer.h"), os.path.join(d, "Renderer.h"))
+    return d
+
+
+def compile_dropin(shadow):
+    """oracle/dropin_main.cpp: reference host program + product RayTracer, linked to librtb200.so."""
+    lib_dir = os.path.join(ROOT, "raytracingrenderer_b200")
+    if not os.path.isfile(os.path.join(lib_dir, "librtb200.so")):
+        return None
+    out = os.path.join(OUT, "dropin_main")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-I", shadow,
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "raytracingrenderer_b200", "host"),
+                           os.path.join(HERE, "dropin_main.cpp"), "-o", out, "-L", lib_dir, "-lrtb200",
+                           "-Wl,-rpath,$ORIGIN/../../raytracingrenderer_b200", "-lpthread"])
+    return out
+
+
 def compile_driver(shadow, out_name, flags):
     out = os.path.join(OUT, out_name)
     cmd = ["g++", "-std=c++17", "-shared", "-fPIC", "-w"] + flags + [
@@ -180,6 +201,11 @@ def build(force=False):
         compile_driver(shadow, "librtref_fast.so", ["-O3", "-march=native", "-ffast-math"])
         compile_driver(shadow_d0, "librtref_d0.so", ["-O2", "-ffp-contract=off", "-DRT_MAX_DEPTH=0"])
         compile_driver(shadow, "librtref.so", ["-O2", "-ffp-contract=off"])
+    dropin_srcs = [os.path.join(HERE, "dropin_main.cpp"), os.path.join(ROOT, "raytracingrenderer_b200", "host", "Renderer.h"),
+                   os.path.join(ROOT, "raytracingrenderer_b200", "host", "rtb_flatten.hpp"), os.path.join(ROOT, "include", "rtb.h")]
+    dropin = os.path.join(OUT, "dropin_main")
+    if not os.path.isfile(dropin) or any(os.path.getmtime(dropin) < os.path.getmtime(x) for x in dropin_srcs):
+        compile_dropin(make_dropin_shadow())
     if not os.path.isfile(os.path.join(OUT, "staged.json")) or not fresh:
         stage_scenes()
     return True

@@ -1,0 +1,163 @@
+// Renderer.h — drop-in replacement for RTBase/Renderer.h: the same `RayTracer` class surface
+// (RTBase/Renderer.h:30-67, 876-898: scene, canvas, film, numProcs; init, clear, render, getSPP,
+// saveHDR, savePNG), with everything below render() running on a B200 through the C ABI of
+// librtb200.so (include/rtb.h).
+//
+// Use: put this file where RTBase/Renderer.h was (RTBase/SceneLoader.h and Main.cpp include it
+// by that name), keep the rest of RTBase/ untouched, add <repo>/include and
+// <repo>/raytracingrenderer_b200/host to the include path, link -lrtb200.  See INTEGRATION.md.
+//
+// Like the original it expects GamesEngineeringBase.h (Window) to be available; headless builds
+// may pass a null canvas.  Not part of the original surface (additions, all optional):
+//   render(n)            n samples per pixel in one call (render() == render(1))
+//   setPresentEveryFrame the original tonemaps and draws the film after every sample
+//                        (presentFilmToCanvas, Renderer.h:69-80); switch it off for batch work
+//   params()             the rtb_params the GPU uses (defaults = the reference's constants)
+//   syncFilm()           copy the GPU film sums into film->film (done by saveHDR automatically)
+#pragma once
+
+#include "Core.h"
+#include "Sampling.h"
+#include "Geometry.h"
+#include "Imaging.h"
+#include "Materials.h"
+#include "Lights.h"
+#include "Scene.h"
+#include "GamesEngineeringBase.h"
+
+#include "rtb.h"
+#include "rtb_flatten.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+const int TILE_SIZE = 32; // RTBase/Renderer.h:18 (the tile partition of rtb_params uses the same size)
+const int MAX_DEPTH = 4;  // RTBase/Renderer.h:20 -> rtb_params.max_depth
+
+class RayTracer
+{
+public:
+	Scene* scene = NULL;
+	GamesEngineeringBase::Window* canvas = NULL;
+	Film* film = NULL;
+	MTRandom* samplers = NULL; // kept for source compatibility; the GPU uses a counter-based RNG
+	int numProcs = 0;          // number of GPUs driving this RayTracer (1)
+
+	void init(Scene* _scene, GamesEngineeringBase::Window* _canvas)
+	{
+		init(_scene, _canvas, 0);
+	}
+	void init(Scene* _scene, GamesEngineeringBase::Window* _canvas, int device)
+	{
+		scene = _scene;
+		canvas = _canvas;
+		film = new Film();
+		film->init((unsigned int)scene->camera.width, (unsigned int)scene->camera.height, new BoxFilter());
+		numProcs = 1;
+		samplers = new MTRandom[1];
+		check(rtb_create(device, &ctx), "rtb_create");
+		rtb_default_params(&prm);
+		prm.max_depth = MAX_DEPTH;
+		prm.epsilon = EPSILON;
+		check(rtb_set_params(ctx, &prm), "rtb_set_params");
+		upload();
+		clear();
+	}
+	// Scene geometry / materials changed: flatten and upload again.
+	void upload()
+	{
+		rtb::FlatScene flat = rtb::flatten(*scene);
+		rtb_scene_desc d = flat.desc();
+		check(rtb_upload_scene(ctx, &d), "rtb_upload_scene");
+		camera = flat.camera;
+	}
+	void clear()
+	{
+		film->clear();
+		// the camera may have moved (RTCamera::updateCamera -> Camera::updateView)
+		rtb_camera now = currentCamera();
+		if (memcmp(&now, &camera, sizeof(now)) != 0)
+		{
+			camera = now;
+			check(rtb_update_camera(ctx, &camera), "rtb_update_camera");
+		}
+		check(rtb_clear(ctx), "rtb_clear");
+		filmOnHost = true;
+	}
+	void render() { render(1); }
+	void render(int n)
+	{
+		if (n <= 0) return;
+		uint32_t begin = (uint32_t)film->SPP;
+		for (int i = 0; i < n; i++) film->incrementSPP();
+		check(rtb_render(ctx, begin, (uint32_t)n), "rtb_render");
+		filmOnHost = false;
+		if (presentEveryFrame && canvas) presentFilmToCanvas();
+	}
+	void presentFilmToCanvas()
+	{
+		if (!canvas) return;
+		std::vector<uint8_t> rgb((size_t)film->width * film->height * 3);
+		check(rtb_tonemap(ctx, rgb.data(), 1.0f), "rtb_tonemap");
+		for (unsigned int y = 0; y < film->height; y++)
+			for (unsigned int x = 0; x < film->width; x++)
+			{
+				const uint8_t* p = &rgb[((size_t)y * film->width + x) * 3];
+				canvas->draw(x, y, p[0], p[1], p[2]);
+			}
+	}
+	int getSPP() { return film->SPP; }
+	void syncFilm()
+	{
+		if (filmOnHost) return;
+		uint32_t spp = 0;
+		check(rtb_read_film(ctx, (float*)film->film, &spp), "rtb_read_film"); // Colour = 3 packed floats
+		filmOnHost = true;
+	}
+	void saveHDR(std::string filename)
+	{
+		syncFilm();
+		film->save(filename);
+	}
+	void savePNG(std::string filename)
+	{
+		if (!canvas) return;
+		presentFilmToCanvas();
+		stbi_write_png(filename.c_str(), canvas->getWidth(), canvas->getHeight(), 3, canvas->getBackBuffer(), canvas->getWidth() * 3);
+	}
+	void setPresentEveryFrame(bool on) { presentEveryFrame = on; }
+	rtb_params& params() { return prm; }
+	void applyParams() { check(rtb_set_params(ctx, &prm), "rtb_set_params"); }
+	rtb_ctx* context() { return ctx; }
+	~RayTracer()
+	{
+		if (ctx) rtb_destroy(ctx);
+	}
+
+private:
+	rtb_ctx* ctx = NULL;
+	rtb_params prm;
+	rtb_camera camera;
+	bool presentEveryFrame = true;
+	bool filmOnHost = true;
+
+	rtb_camera currentCamera()
+	{
+		rtb_camera c;
+		memset(&c, 0, sizeof(c));
+		memcpy(c.inv_proj, scene->camera.inverseProjectionMatrix.m, 16 * sizeof(float));
+		memcpy(c.cam_to_world, scene->camera.camera.m, 16 * sizeof(float));
+		c.origin[0] = scene->camera.origin.x, c.origin[1] = scene->camera.origin.y, c.origin[2] = scene->camera.origin.z;
+		c.width = scene->camera.width, c.height = scene->camera.height;
+		return c;
+	}
+	void check(int rc, const char* what)
+	{
+		if (rc == RTB_OK) return;
+		// the reference's own error handling is "print and exit" (GEMLoader.h:349-354)
+		fprintf(stderr, "%s failed (%d): %s\n", what, rc, rtb_last_error(ctx));
+		exit(1);
+	}
+};

@@ -431,3 +431,29 @@ def test_camera_update(rtb, oracle_mod):
     oid, ot = oracle_mod.Oracle(moved).primary_hits()
     assert np.array_equal(ids, oid) and t.tobytes() == ot.tobytes()
     rt.update_camera(s.camera)
+
+
+# ------------------------------------------------------------------ the drop-in boundary itself
+def test_reference_host_program_renders_through_the_drop_in_header(rtb, tmp_path):
+    """oracle/_ref/dropin_main = the reference's host program shape (Main.cpp) compiled against the
+    UNMODIFIED RTBase headers with host/Renderer.h in place of RTBase/Renderer.h: loadScene ->
+    RayTracer::init -> render() -> saveHDR on the GPU.  Its film must equal the film the Python
+    mirror produces from the same scene, bit for bit."""
+    import subprocess
+    from oracle import ref
+    from raytracingrenderer_b200 import imageio
+    exe = os.path.join(ref.REF_DIR, "dropin_main")
+    if not os.path.isfile(exe) or not ref.have_scene("cornell-box"):
+        pytest.skip("oracle/_ref/dropin_main not built")
+    hdr, raw = str(tmp_path / "out.hdr"), str(tmp_path / "film.bin")
+    out = subprocess.run([exe, ref.scene_dir("cornell-box"), "8", hdr, raw], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "SPP: 8" in out.stdout
+    rt = gpu_scene(rtb, "cornell-box")
+    rt.render(8, 0)
+    want = rt.read_film()
+    got = np.fromfile(raw, "<f4").reshape(want.shape)
+    assert got.tobytes() == want.tobytes()
+    img = imageio.read_hdr(hdr)                         # Film::save: film / SPP as RGBE
+    assert np.all(np.abs(img - want / 8) <= (want / 8).max(axis=-1, keepdims=True) / 100 + 1e-6)
+    assert os.path.getsize(hdr + ".png") > 1000          # savePNG after a camera move + clear
