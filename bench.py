@@ -30,34 +30,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 VARIANTS = ["diffuse", "conductor", "glass", "dielectric", "orennayar", "plastic", "layered"]
-CACHE = os.path.join(ROOT, "scenes", "_cache")
+STAGED = os.path.join(ROOT, "scenes", "_staged")
 METRIC = "Msamples/s (path-traced pixel samples per second; Mrays/s alongside)"
 
 
 def load_workload(scene, log):
-    """-> (name, [(label, FlatScene)]).  Flat scenes staged at build time (scenes/_cache)."""
-    import numpy as np
-    from raytracingrenderer_b200 import abi
-    base_path = os.path.join(CACHE, "materialball.rtbs")
-    var_path = os.path.join(CACHE, "materialball_variants.npz")
-    if scene == "materialball7" and os.path.isfile(base_path) and os.path.isfile(var_path):
-        base = abi.FlatScene.load(base_path)
-        tables = np.load(var_path)
-        out = []
-        for v in VARIANTS:
-            s = abi.FlatScene()
-            s.__dict__.update(base.__dict__)
-            s.materials = tables[v]
-            out.append((v, s))
+    """-> (name, [(label, FlatScene)]) loaded by the product's own host layer
+    (raytracingrenderer_b200.host_api = loadScene + BVH build + flatten in librtb200_host.so) from
+    the scene assets staged at build time under scenes/_staged/ (git-ignored input data)."""
+    from raytracingrenderer_b200 import abi, host_api
+    if scene == "materialball7" and all(os.path.isfile(os.path.join(STAGED, "materialball_" + v, "scene.json")) for v in VARIANTS):
+        out = [(v, host_api.load_scene(os.path.join(STAGED, "materialball_" + v))) for v in VARIANTS]
         return "materialball 1280x720 x 7 BSDF overrides (%s), 256 spp each, max_depth 4" % ",".join(VARIANTS), out
-    path = os.path.join(CACHE, scene + ".rtbs")
+    if scene.startswith("soup"):
+        n = int(scene[4:] or 20)
+        s, secs = host_api.build_soup(1 << n, 3840, 2160)
+        log("soup 2^%d: %d triangles, host BVH build %.1f s" % (n, s.n_tris, secs))
+        return "synthetic soup 2^%d triangles 3840x2160, max_depth 0" % n, [(scene, s)]
+    path = os.path.join(STAGED, scene, "scene.json")
     if scene != "materialball7" and os.path.isfile(path):
-        s = abi.FlatScene.load(path)
+        s = host_api.load_scene(os.path.dirname(path))
         return "%s %dx%d" % (scene, s.width, s.height), [(scene, s)]
-    log("WARNING: staged scene data for %r not found under scenes/_cache; falling back to the committed "
+    log("WARNING: staged scene assets for %r not found under scenes/_staged; falling back to the committed "
         "cornell-box fixture" % scene)
     s = abi.FlatScene.load(os.path.join(ROOT, "tests", "golden", "cornell-box.rtbs"))
-    return "cornell-box 1024x1024 (fallback: staged materialball data missing)", [("cornell-box", s)]
+    return "cornell-box 1024x1024 (fallback: staged materialball assets missing)", [("cornell-box", s)]
 
 
 class ClockSampler:
@@ -339,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "spp_per_gpu": spp, "spp_total": total_spp, "partition": "spp slice",
                        "traversal": "fast", "sampling": "strict", "l2": "flushed between steps (256 MiB memset)",
-                       "scene_source": "flat scenes staged at build time by the product flattener"},
+                       "scene_source": "product host loader (librtb200_host.so) on the staged scene assets"},
             "mrays_per_s": mrays, "rays_per_sample": rays_rank / max(samples_rank, 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "peak_source": how, "kernel": "k_wf_%s" % dom,

@@ -12,8 +12,12 @@ GPU box with gpurun):
   oracle/_ref/librtref_fast.so   same, -O3 -march=native -ffast-math (speed only; mirrors the
                              reference's MSVC /fp:fast /arch:AVX, RTBase/RTBase.vcxproj:123-124)
   oracle/_ref/librtref_d0.so     MAX_DEPTH = 0 variant of the parity build
-  oracle/_ref/scenes/<name>/ filtered copies of the bundled scenes (assets listed in
-                             /root/reference/.MISSING_LARGE_BLOBS removed from scene.json)
+  oracle/_ref/dropin_main    oracle/dropin_main.cpp: reference host program + the product's
+                             host/Renderer.h, linked to librtb200.so (drop-in test)
+  scenes/_staged/<name>/     filtered copies of the bundled scene ASSETS (instances whose mesh is
+                             listed in /root/reference/.MISSING_LARGE_BLOBS removed from
+                             scene.json) + BSDF-override variants; git-ignored input data read by
+                             both the oracle and the product's own loader
 
 /root/reference is only read.  On the GPU box (no /root/reference) this script is a no-op
 and the prebuilt files are used.
@@ -30,6 +34,8 @@ ROOT = os.path.dirname(HERE)
 REF = os.environ.get("RTB_REFERENCE_DIR", "/root/reference")
 RTBASE = os.path.join(REF, "RTBase")
 OUT = os.path.join(HERE, "_ref")
+# scene ASSETS (input data, not code) are staged outside oracle/: the product loader reads them too
+STAGED = os.path.join(ROOT, "scenes", "_staged")
 
 REF_HEADERS = [
     "Core.h", "Sampling.h", "Geometry.h", "Imaging.h", "Materials.h", "Lights.h", "Scene.h",
@@ -140,7 +146,7 @@ def _filter_scene_json(src_dir, dst_dir, edit=None, prefix=""):
 
 
 def stage_scenes():
-    scenes_out = os.path.join(OUT, "scenes")
+    scenes_out = STAGED
     os.makedirs(scenes_out, exist_ok=True)
     report = {}
     for name in ["cornell-box", "MaterialsScene", "materialball", "coffee", "bathroom"]:
@@ -179,7 +185,7 @@ def stage_scenes():
                             inst.update(props)
         _filter_scene_json(os.path.join(RTBASE, "materialball"), os.path.join(scenes_out, "materialball_" + vname),
                            edit, prefix="../materialball/")
-    with open(os.path.join(OUT, "staged.json"), "w") as f:
+    with open(os.path.join(STAGED, "staged.json"), "w") as f:
         json.dump({"dropped_instances": report}, f, indent=1)
     return report
 
@@ -206,7 +212,7 @@ def build(force=False):
     dropin = os.path.join(OUT, "dropin_main")
     if not os.path.isfile(dropin) or any(os.path.getmtime(dropin) < os.path.getmtime(x) for x in dropin_srcs):
         compile_dropin(make_dropin_shadow())
-    if not os.path.isfile(os.path.join(OUT, "staged.json")) or not fresh:
+    if not os.path.isfile(os.path.join(STAGED, "staged.json")) or not fresh:
         stage_scenes()
     return True
 

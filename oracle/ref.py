@@ -10,7 +10,7 @@ from raytracingrenderer_b200 import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
-SCENES_DIR = os.path.join(REF_DIR, "scenes")
+SCENES_DIR = os.path.join(os.path.dirname(HERE), "scenes", "_staged")
 
 _libs = {}
 

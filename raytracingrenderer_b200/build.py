@@ -39,7 +39,23 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+HOST_LIB = os.path.join(HERE, "librtb200_host.so")
+HOST_DEPS = ["rtb_host.cpp", "rtb_scene.hpp", "rtb_flatten.hpp"]
+
+
+def build_host(force=False):
+    """Stand-alone host layer (scene loader, reference-order BVH builder, flattener): plain g++."""
+    hdir = os.path.join(HERE, "host")
+    deps = [os.path.join(hdir, d) for d in HOST_DEPS] + [os.path.join(ROOT, "include", "rtb.h")]
+    if not force and os.path.isfile(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
+        return HOST_LIB
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-Wall",
+                           os.path.join(hdir, "rtb_host.cpp"), "-o", HOST_LIB, "-lz"])
+    return HOST_LIB
+
+
 def build(force=False, verbose=False, extra=()):
+    build_host(force)
     if not force and up_to_date():
         return LIB
     cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include")]

@@ -457,3 +457,27 @@ def test_reference_host_program_renders_through_the_drop_in_header(rtb, tmp_path
     img = imageio.read_hdr(hdr)                         # Film::save: film / SPP as RGBE
     assert np.all(np.abs(img - want / 8) <= (want / 8).max(axis=-1, keepdims=True) / 100 + 1e-6)
     assert os.path.getsize(hdr + ".png") > 1000          # savePNG after a camera move + clear
+
+
+def test_soup_config_primary_plus_one_bounce(rtb, oracle_mod):
+    """SURVEY 8d cfg 5 at test size: random-triangle soup built by the product's host layer
+    (reference-order BVH), max_depth 0 = primary + one diffuse bounce, white background light."""
+    from raytracingrenderer_b200 import host_api
+    s, _ = host_api.build_soup(1 << 14, 320, 180)
+    rt = rtb.RayTracer(0)
+    rt.init(s)
+    rt.set_params(max_depth=0)
+    o = oracle_mod.Oracle(s, max_depth=0)
+    for trav in TRAVS:
+        ids, t = rt.primary_hits(trav)
+        oid, ot = o.primary_hits()
+        assert np.array_equal(ids, oid) and t.tobytes() == ot.tobytes()
+    rt.render(4, 0)
+    img = rt.read_film()
+    want, st = o.render(4)
+    close = np.isclose(img, want, rtol=2e-4, atol=1e-5).all(axis=-1)
+    assert close.mean() > 0.995
+    g = rt.stats()
+    assert g["closest_rays"] <= 2 * g["samples"] and g["shadow_rays"] <= 2 * g["samples"]
+    assert abs(g["closest_rays"] / st["closest_rays"] - 1) < 2e-3
+    rt.close()

@@ -1,0 +1,62 @@
+"""The stand-alone host layer (host/rtb_scene.hpp via librtb200_host.so) against the reference's
+own loader: the flattened scene — camera matrices, every triangle in BVH order, every BVH node,
+materials, textures, lights — must be byte-identical, because hit-ID parity starts there."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ref_scene
+
+
+@pytest.fixture(scope="module")
+def host():
+    from raytracingrenderer_b200 import host_api
+    host_api.lib()
+    return host_api
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "MaterialsScene", "materialball", "coffee", "MaterialsScene_env",
+                                  "materialball_glass", "materialball_layered", "materialball_conductor"])
+def test_loader_and_builder_equal_the_reference(host, name, tmp_path):
+    rs = ref_scene(name)
+    want = rs.flatten(str(tmp_path / "ref.rtbs"))
+    got = host.load_scene(rs.dir)
+    assert got.camera.tobytes() == want.camera.tobytes()
+    for k in ("ref_nodes", "tri_isect", "tri_shade", "materials", "textures", "lights", "texels"):
+        a, b = getattr(got, k), getattr(want, k)
+        assert len(a) == len(b), k
+        assert a.tobytes() == b.tobytes(), k
+    assert (got.background_type, got.background_tex) == (want.background_type, want.background_tex)
+    assert got.background_colour.tobytes() == want.background_colour.tobytes()
+
+
+def test_jpeg_textures_are_an_error_not_a_silent_default(host):
+    rs = ref_scene("bathroom")
+    with pytest.raises(RuntimeError) as e:
+        host.load_scene(rs.dir)
+    assert "cannot decode" in str(e.value)
+
+
+def test_soup_scene_is_well_formed(host, oracle_mod):
+    from raytracingrenderer_b200 import abi
+    s, secs = host.build_soup(4096, 160, 90)
+    assert 4000 < s.n_tris <= 4096 and len(s.lights) == 1 and s.lights["type"][0] == abi.LIGHT_BACKGROUND
+    leaves = s.ref_nodes[s.ref_nodes["a"] < 0]
+    assert leaves["b"].max() <= 2 and int(leaves["b"].sum()) == s.n_tris          # MAXNODE_TRIANGLES
+    assert sorted((~leaves["a"]).tolist()) == sorted(np.cumsum(np.r_[0, leaves["b"][np.argsort(~leaves["a"])]])[:-1].tolist())
+    o = oracle_mod.Oracle(s, max_depth=0)
+    ids, t = o.primary_hits()
+    assert 0.3 < (ids != abi.MISS_ID).mean() < 1.0
+    film, st = o.render(1)
+    assert np.isfinite(film).all() and st["closest_rays"] <= 2 * st["samples"]     # primary + one bounce
+
+
+def test_camera_matches_the_reference_flattened_camera(host):
+    rs = ref_scene("cornell-box")
+    import json
+    sj = json.load(open(os.path.join(rs.dir, "scene.json")))
+    v = lambda k: [float(x) for x in sj[k].split()]  # noqa: E731
+    cam = host.camera(v("from"), v("to"), v("up"), float(sj["fov"]), int(sj["width"]), int(sj["height"]))
+    want = rs.flatten("/tmp/_cam.rtbs").camera
+    assert cam.tobytes() == want.tobytes()

@@ -6,7 +6,8 @@ from raytracingrenderer_b200 import abi
 name = sys.argv[1] if len(sys.argv) > 1 else "materialball"
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 trav = abi.TRAV_EXACT if (len(sys.argv) > 3 and sys.argv[3] == "exact") else abi.TRAV_FAST
-s = abi.FlatScene.load(os.path.join("scenes", "_cache", name + ".rtbs"))
+from raytracingrenderer_b200 import host_api
+s = host_api.load_scene(os.path.join("scenes", "_staged", name))
 rt = rtb.RayTracer(0)
 rt.init(s)
 rt.set_params(traversal=trav)
