@@ -221,7 +221,8 @@ def run_ours(args, rank, world, local_rank):
         rt = rtb.RayTracer(local_rank)
         rt.set_stream(stream.cuda_stream)
         rt.init(s)
-        rt.set_params(traversal=abi.TRAV_FAST, **D.partition_params(rank, world, "spp"))
+        depth = args.max_depth if args.max_depth is not None else (0 if args.scene.startswith("soup") else 4)
+        rt.set_params(traversal=abi.TRAV_FAST, max_depth=depth, **D.partition_params(rank, world, "spp"))
         rts.append(rt)
     accs = [D.accum_tensor(rt) for rt in rts]      # int64 fixed-point film sums (exact reduction)
     host = [torch.empty(a.numel(), dtype=torch.float32).pin_memory() for a in accs] if rank == 0 else []
@@ -373,6 +374,7 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--ref-spp", type=int, default=4, help="spp per scene per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--max-depth", type=int, default=None, help="rtb_params.max_depth (default 4; soup scenes 0)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -472,6 +472,7 @@ def test_soup_config_primary_plus_one_bounce(rtb, oracle_mod):
         ids, t = rt.primary_hits(trav)
         oid, ot = o.primary_hits()
         assert np.array_equal(ids, oid) and t.tobytes() == ot.tobytes()
+    rt.clear()              # the parity entry points above count rays too
     rt.render(4, 0)
     img = rt.read_film()
     want, st = o.render(4)
