@@ -68,7 +68,10 @@ struct rtb_ctx
 	unsigned long long* hostProbe = nullptr; // pinned: {nextJob, alive}
 	int smCount = 0;
 	int travBlocksPerSM[2][2] = {{0, 0}, {0, 0}}; // [extend|shadow][exact|fast]
-	uint32_t poolSlots = 1u << 21;
+	uint32_t poolSlots = 8u << 20; // profiles/r01_pool_sweep.txt: per-launch ramp/tail amortise up to ~8 M slots
+	cudaStream_t shadowStream = nullptr; // k_wf_shadow(i) overlaps k_wf_extend(i+1)
+	cudaEvent_t evShade = nullptr, evShadow = nullptr;
+	bool overlapShadow = true;
 	uint64_t wfIterations = 0, wfHostSyncs = 0;
 };
 
@@ -326,6 +329,13 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		ctx->wfStateBytes = need;
 	}
 	if (!ctx->wfGlobal) CK(cudaMalloc((void**)&ctx->wfGlobal, sizeof(WfGlobal)));
+	if (!ctx->shadowStream)
+	{
+		CK(cudaStreamCreateWithFlags(&ctx->shadowStream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&ctx->evShade, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&ctx->evShadow, cudaEventDisableTiming));
+		if (const char* e = getenv("RTB_OVERLAP_SHADOW")) ctx->overlapShadow = atoi(e) != 0;
+	}
 	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, 4 * sizeof(unsigned long long)));
 	uint32_t vertices = (P.integrator == RTB_INT_PATH) ? (uint32_t)P.max_depth + 2u : 1u;
 	// list-scheduling bound on the iterations: total work / slots + longest job
@@ -379,6 +389,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	k_wf_init<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(ctx->S, A);
 	ctx->launches++;
 	uint32_t it = 0;
+	bool shadowPending = false;
 	uint32_t batch = vertices * 4 < 16 ? 16 : vertices * 4;
 	bool drained = false;
 	while (!drained && it < bound)
@@ -398,6 +409,11 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 			if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
 			else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
 			if (timed) cudaEventRecord(se.e[1], ctx->stream);
+			if (shadowPending)
+			{
+				cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);
+				shadowPending = false;
+			}
 			switch (P.integrator)
 			{
 			case RTB_INT_DIRECT: launchShade<RTB_INT_DIRECT>(ctx, A, it, gridSlots); break;
@@ -409,15 +425,36 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 			if (timed) cudaEventRecord(se.e[2], ctx->stream);
 			if (shadows)
 			{
-				if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
-				else k_wf_shadow<RTB_TRAV_FAST><<<gridSlots, 128, 0, ctx->stream>>>(ctx->S, A, it);
+				// shadow(it) only depends on shade(it); extend(it+1) does not depend on shadow(it):
+				// run it on the side stream so that it fills extend's ramp-up and tail.  shade(it+1)
+				// (which rewrites the shadow queue) waits for it.  Timed iterations stay serial.
+				// (the iteration before a timed one stays serial too, so stage timings are clean)
+				bool side = ctx->overlapShadow && !timed && ((it + 1) % 8u) != 4u;
+				cudaStream_t ss = side ? ctx->shadowStream : ctx->stream;
+				if (side)
+				{
+					cudaEventRecord(ctx->evShade, ctx->stream);
+					cudaStreamWaitEvent(ctx->shadowStream, ctx->evShade, 0);
+				}
+				if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridSlots, 128, 0, ss>>>(ctx->S, A, it);
+				else k_wf_shadow<RTB_TRAV_FAST><<<gridSlots, 128, 0, ss>>>(ctx->S, A, it);
 				ctx->launches++;
+				if (side)
+				{
+					cudaEventRecord(ctx->evShadow, ctx->shadowStream);
+					shadowPending = true;
+				}
 			}
 			if (timed)
 			{
 				cudaEventRecord(se.e[3], ctx->stream);
 				ctx->pendingStages.push_back(se);
 			}
+		}
+		if (shadowPending)
+		{
+			cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);
+			shadowPending = false;
 		}
 		// probe: jobs claimed so far and slots alive after the last enqueued iteration
 		CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -529,6 +566,9 @@ void rtb_destroy(rtb_ctx* ctx)
 	resolveTimings(ctx);
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
 	freeScene(ctx);
+	if (ctx->shadowStream) cudaStreamDestroy(ctx->shadowStream);
+	if (ctx->evShade) cudaEventDestroy(ctx->evShade);
+	if (ctx->evShadow) cudaEventDestroy(ctx->evShadow);
 	if (ctx->counters) cudaFree(ctx->counters);
 	if (ctx->hostProbe) cudaFreeHost(ctx->hostProbe);
 	delete ctx;
