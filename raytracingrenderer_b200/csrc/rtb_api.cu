@@ -31,6 +31,8 @@ struct StageEvents
 };
 } // namespace
 
+#define RTB_MAX_POOLS 8
+
 struct rtb_ctx
 {
 	int device = 0;
@@ -69,9 +71,11 @@ struct rtb_ctx
 	int smCount = 0;
 	int travBlocksPerSM[2][2] = {{0, 0}, {0, 0}}; // [extend|shadow][exact|fast]
 	uint32_t poolSlots = 8u << 20; // profiles/r01_pool_sweep.txt: per-launch ramp/tail amortise up to ~8 M slots
-	cudaStream_t shadowStream = nullptr; // k_wf_shadow(i) overlaps k_wf_extend(i+1)
-	cudaEvent_t evShade = nullptr, evShadow = nullptr;
-	bool overlapShadow = true;
+	bool simpleExtend = false;
+	int pools = 2; // sub-pools advancing concurrently on their own streams (profiles/r01_pool_sweep.txt)
+	cudaStream_t poolStreams[RTB_MAX_POOLS] = {};
+	cudaEvent_t poolDone[RTB_MAX_POOLS] = {};
+	cudaEvent_t evFork = nullptr;
 	uint64_t wfIterations = 0, wfHostSyncs = 0;
 };
 
@@ -273,9 +277,12 @@ static int resolveFilm(rtb_ctx* ctx)
 	return RTB_OK;
 }
 
-// Wavefront schedule (rtb_wavefront.cuh).  The number of iterations depends on the paths, so
-// the launches are enqueued in batches sized from the measured job rate; between batches the
-// host reads {jobs claimed, slots alive} (one 16-byte copy + stream sync, a handful per call).
+// Wavefront schedule (rtb_wavefront.cuh).  The slot pool is split into K independent sub-pools,
+// each advancing on its own stream (all draw jobs from one counter): a stage kernel ends with a
+// long, thinly occupied tail (its slowest rays), which the other sub-pools' kernels fill.  The
+// number of iterations depends on the paths, so launches are enqueued in batches sized from the
+// measured job rate; between batches the host reads {jobs claimed, slots alive} (a few dozen
+// bytes + a sync, a handful of times per call).  Work is forked from / joined to ctx->stream.
 static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 {
 	const rtb_params& P = ctx->params;
@@ -317,9 +324,28 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	}
 	if (ctx->wfTileCount == 0) return RTB_OK;
 	unsigned long long totalJobs = (unsigned long long)ctx->wfTileCount * 32ull * sCount;
-	uint32_t nSlots = ctx->poolSlots;
-	if ((unsigned long long)nSlots > totalJobs) nSlots = (uint32_t)((totalJobs + 31ull) & ~31ull);
-	size_t need = (size_t)nSlots * 7 * sizeof(float4);
+	// ---- pools
+	if (!ctx->poolStreams[0])
+	{
+		if (const char* e = getenv("RTB_POOLS"))
+		{
+			int v = atoi(e);
+			if (v >= 1 && v <= RTB_MAX_POOLS) ctx->pools = v;
+		}
+		for (int k = 0; k < RTB_MAX_POOLS; k++)
+		{
+			CK(cudaStreamCreateWithFlags(&ctx->poolStreams[k], cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&ctx->poolDone[k], cudaEventDisableTiming));
+		}
+		CK(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+	}
+	uint32_t nSlotsAll = ctx->poolSlots;
+	if ((unsigned long long)nSlotsAll > totalJobs) nSlotsAll = (uint32_t)((totalJobs + 31ull) & ~31ull);
+	int K = ctx->pools;
+	while (K > 1 && nSlotsAll / (uint32_t)K < (1u << 19)) K--; // sub-pools of at least 512 k slots
+	uint32_t perPool = ((nSlotsAll + (uint32_t)K - 1) / (uint32_t)K + 31u) & ~31u;
+	uint32_t nSlotsAlloc = perPool * (uint32_t)K;
+	size_t need = (size_t)nSlotsAlloc * 7 * sizeof(float4);
 	if (need > ctx->wfStateBytes)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -329,44 +355,22 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		ctx->wfStateBytes = need;
 	}
 	if (!ctx->wfGlobal) CK(cudaMalloc((void**)&ctx->wfGlobal, sizeof(WfGlobal)));
-	if (!ctx->shadowStream)
-	{
-		CK(cudaStreamCreateWithFlags(&ctx->shadowStream, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&ctx->evShade, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&ctx->evShadow, cudaEventDisableTiming));
-		if (const char* e = getenv("RTB_OVERLAP_SHADOW")) ctx->overlapShadow = atoi(e) != 0;
-	}
-	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, 4 * sizeof(unsigned long long)));
+	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, (1 + RTB_MAX_POOLS) * sizeof(unsigned long long)));
 	uint32_t vertices = (P.integrator == RTB_INT_PATH) ? (uint32_t)P.max_depth + 2u : 1u;
-	// list-scheduling bound on the iterations: total work / slots + longest job
-	unsigned long long bound64 = (totalJobs * vertices + nSlots - 1) / nSlots + vertices + 1;
+	// list-scheduling bound on the iterations of a sub-pool: total work / slots + longest job
+	unsigned long long bound64 = (totalJobs * vertices + perPool - 1) / perPool + vertices + 1;
 	if (bound64 > (1ull << 22)) return fail(ctx, RTB_ERR_ARG, "too many samples per call; split the render");
 	uint32_t bound = (uint32_t)bound64;
-	if (bound > ctx->wfCtrlEntries)
+	if ((size_t)bound * K > ctx->wfCtrlEntries)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->wfCtrl) cudaFree(ctx->wfCtrl);
 		ctx->wfCtrl = nullptr, ctx->wfCtrlEntries = 0;
-		CK(cudaMalloc((void**)&ctx->wfCtrl, (size_t)bound * sizeof(WfCtrl)));
-		ctx->wfCtrlEntries = bound;
+		CK(cudaMalloc((void**)&ctx->wfCtrl, (size_t)bound * K * sizeof(WfCtrl)));
+		ctx->wfCtrlEntries = (uint32_t)((size_t)bound * K);
 	}
-	CK(cudaMemsetAsync(ctx->wfCtrl, 0, (size_t)bound * sizeof(WfCtrl), ctx->stream));
+	CK(cudaMemsetAsync(ctx->wfCtrl, 0, (size_t)bound * K * sizeof(WfCtrl), ctx->stream));
 	CK(cudaMemsetAsync(ctx->wfGlobal, 0, sizeof(WfGlobal), ctx->stream));
-	WfArgs A;
-	float4* base = (float4*)ctx->wfState;
-	A.rayO = base, A.rayD = base + (size_t)nSlots, A.hit = base + (size_t)nSlots * 2, A.thr = base + (size_t)nSlots * 3;
-	A.shO = base + (size_t)nSlots * 4, A.shD = base + (size_t)nSlots * 5, A.shC = base + (size_t)nSlots * 6;
-	A.ctrl = ctx->wfCtrl;
-	A.glob = ctx->wfGlobal;
-	A.tileList = ctx->wfTiles;
-	A.counters = ctx->counters;
-	A.accum = ctx->accum;
-	A.nSlots = nSlots, A.nTiles = ctx->wfTileCount;
-	A.width = ctx->width, A.height = ctx->height;
-	A.sFirst = sFirst, A.sStep = sStep, A.sCount = sCount;
-	A.totalJobs = totalJobs;
-	A.P = P;
-	int ti = (P.traversal == RTB_TRAV_EXACT) ? 0 : 1;
 	if (ctx->smCount <= 0)
 	{
 		cudaDeviceProp prop;
@@ -374,95 +378,103 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		ctx->smCount = prop.multiProcessorCount;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0][0], k_wf_extend<RTB_TRAV_EXACT>, 128, 0));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0][1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1][0], k_wf_shadow<RTB_TRAV_EXACT>, 128, 0));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1][1], k_wf_shadow<RTB_TRAV_FAST>, 128, 0));
+		if (const char* e = getenv("RTB_SIMPLE_EXTEND")) ctx->simpleExtend = atoi(e) != 0;
 	}
-	// persistent traversal kernels: exactly one resident wave
+	int ti = (P.traversal == RTB_TRAV_EXACT) ? 0 : 1;
+	WfArgs A[RTB_MAX_POOLS];
+	float4* base = (float4*)ctx->wfState;
+	for (int k = 0; k < K; k++)
+	{
+		WfArgs& a = A[k];
+		size_t off = (size_t)k * perPool, n = nSlotsAlloc;
+		a.rayO = base + off, a.rayD = base + n + off, a.hit = base + n * 2 + off, a.thr = base + n * 3 + off;
+		a.shO = base + n * 4 + off, a.shD = base + n * 5 + off, a.shC = base + n * 6 + off;
+		a.ctrl = ctx->wfCtrl + (size_t)k * bound;
+		a.glob = ctx->wfGlobal;
+		a.tileList = ctx->wfTiles;
+		a.counters = ctx->counters;
+		a.accum = ctx->accum;
+		a.nSlots = perPool, a.nTiles = ctx->wfTileCount;
+		a.width = ctx->width, a.height = ctx->height;
+		a.sFirst = sFirst, a.sStep = sStep, a.sCount = sCount;
+		a.totalJobs = totalJobs;
+		a.P = P;
+	}
+	// persistent traversal kernel: one resident wave; grid-stride kernels: enough blocks to fill the machine
 	unsigned gridExtend = (unsigned)(ctx->smCount * (ctx->travBlocksPerSM[0][ti] > 0 ? ctx->travBlocksPerSM[0][ti] : 1));
-	// grid-stride kernels: enough blocks to fill the machine, never more than the work
 	unsigned maxBlocks = (unsigned)ctx->smCount * 16u;
-	unsigned gridSlots = (nSlots + 127) / 128;
+	unsigned gridSlots = (perPool + 127) / 128;
 	if (gridSlots > maxBlocks) gridSlots = maxBlocks;
+	if (gridExtend > (perPool + 127) / 128) gridExtend = (perPool + 127) / 128;
 	bool shadows = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_DIRECT);
 	EventPair ev = {getEvent(ctx), getEvent(ctx)};
 	cudaEventRecord(ev.a, ctx->stream);
-	k_wf_init<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(ctx->S, A);
-	ctx->launches++;
+	// fork
+	cudaEventRecord(ctx->evFork, ctx->stream);
+	for (int k = 0; k < K; k++)
+	{
+		cudaStreamWaitEvent(ctx->poolStreams[k], ctx->evFork, 0);
+		k_wf_init<<<(perPool + 255) / 256, 256, 0, ctx->poolStreams[k]>>>(ctx->S, A[k]);
+		ctx->launches++;
+	}
 	uint32_t it = 0;
-	bool shadowPending = false;
 	uint32_t batch = vertices * 4 < 16 ? 16 : vertices * 4;
 	bool drained = false;
 	while (!drained && it < bound)
 	{
 		uint32_t end = it + batch;
 		if (end > bound) end = bound;
-		ctx->wfIterations += end - it;
+		ctx->wfIterations += (uint64_t)(end - it) * K;
 		for (; it < end; it++)
 		{
-			bool timed = (it % 8u) == 4u;
-			StageEvents se;
-			if (timed)
+			for (int k = 0; k < K; k++)
 			{
-				for (int k = 0; k < 4; k++) se.e[k] = getEvent(ctx);
-				cudaEventRecord(se.e[0], ctx->stream);
-			}
-			if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
-			else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, ctx->stream>>>(ctx->S, A, it);
-			if (timed) cudaEventRecord(se.e[1], ctx->stream);
-			if (shadowPending)
-			{
-				cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);
-				shadowPending = false;
-			}
-			switch (P.integrator)
-			{
-			case RTB_INT_DIRECT: launchShade<RTB_INT_DIRECT>(ctx, A, it, gridSlots); break;
-			case RTB_INT_ALBEDO: launchShade<RTB_INT_ALBEDO>(ctx, A, it, gridSlots); break;
-			case RTB_INT_NORMALS: launchShade<RTB_INT_NORMALS>(ctx, A, it, gridSlots); break;
-			default: launchShade<RTB_INT_PATH>(ctx, A, it, gridSlots); break;
-			}
-			ctx->launches += 2;
-			if (timed) cudaEventRecord(se.e[2], ctx->stream);
-			if (shadows)
-			{
-				// shadow(it) only depends on shade(it); extend(it+1) does not depend on shadow(it):
-				// run it on the side stream so that it fills extend's ramp-up and tail.  shade(it+1)
-				// (which rewrites the shadow queue) waits for it.  Timed iterations stay serial.
-				// (the iteration before a timed one stays serial too, so stage timings are clean)
-				bool side = ctx->overlapShadow && !timed && ((it + 1) % 8u) != 4u;
-				cudaStream_t ss = side ? ctx->shadowStream : ctx->stream;
-				if (side)
+				cudaStream_t st = ctx->poolStreams[k];
+				// stage timing: sub-pool 0, every 8th iteration (other sub-pools run concurrently)
+				bool timed = (k == 0) && (it % 8u) == 4u;
+				StageEvents se;
+				if (timed)
 				{
-					cudaEventRecord(ctx->evShade, ctx->stream);
-					cudaStreamWaitEvent(ctx->shadowStream, ctx->evShade, 0);
+					for (int e = 0; e < 4; e++) se.e[e] = getEvent(ctx);
+					cudaEventRecord(se.e[0], st);
 				}
-				if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridSlots, 128, 0, ss>>>(ctx->S, A, it);
-				else k_wf_shadow<RTB_TRAV_FAST><<<gridSlots, 128, 0, ss>>>(ctx->S, A, it);
-				ctx->launches++;
-				if (side)
+				if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it);
+				else if (ctx->simpleExtend) k_wf_extend_simple<RTB_TRAV_FAST><<<(perPool + 127) / 128, 128, 0, st>>>(ctx->S, A[k], it);
+				else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it);
+				if (timed) cudaEventRecord(se.e[1], st);
+				switch (P.integrator)
 				{
-					cudaEventRecord(ctx->evShadow, ctx->shadowStream);
-					shadowPending = true;
+				case RTB_INT_DIRECT: k_wf_shade<RTB_INT_DIRECT><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
+				case RTB_INT_ALBEDO: k_wf_shade<RTB_INT_ALBEDO><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
+				case RTB_INT_NORMALS: k_wf_shade<RTB_INT_NORMALS><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
+				default: k_wf_shade<RTB_INT_PATH><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
 				}
-			}
-			if (timed)
-			{
-				cudaEventRecord(se.e[3], ctx->stream);
-				ctx->pendingStages.push_back(se);
+				ctx->launches += 2;
+				if (timed) cudaEventRecord(se.e[2], st);
+				if (shadows)
+				{
+					if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);
+					else k_wf_shadow<RTB_TRAV_FAST><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);
+					ctx->launches++;
+				}
+				if (timed)
+				{
+					cudaEventRecord(se.e[3], st);
+					ctx->pendingStages.push_back(se);
+				}
 			}
 		}
-		if (shadowPending)
+		// probe: jobs claimed so far and slots alive after the last enqueued iteration of every sub-pool
+		for (int k = 0; k < K; k++)
 		{
-			cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);
-			shadowPending = false;
+			CK(cudaMemcpyAsync(&ctx->hostProbe[1 + k], &A[k].ctrl[it - 1], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->poolStreams[k]));
 		}
-		// probe: jobs claimed so far and slots alive after the last enqueued iteration
-		CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(&ctx->hostProbe[1], &ctx->wfCtrl[it - 1], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
+		CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->poolStreams[0]));
+		for (int k = 0; k < K; k++) CK(cudaStreamSynchronize(ctx->poolStreams[k]));
 		ctx->wfHostSyncs++;
 		unsigned long long claimed = ctx->hostProbe[0];
-		uint32_t alive = (uint32_t)(ctx->hostProbe[1] >> 32); // WfCtrl{nShadow, alive}: alive is the high word
+		uint32_t alive = 0;
+		for (int k = 0; k < K; k++) alive += (uint32_t)(ctx->hostProbe[1 + k] >> 32); // WfCtrl{nShadow, alive}
 		if (alive == 0)
 		{
 			drained = true;
@@ -470,7 +482,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		}
 		// predict the remaining iterations from the job rate seen so far
 		unsigned long long started = claimed < totalJobs ? claimed : totalJobs;
-		double perIter = (started > nSlots) ? (double)(started - nSlots) / (double)it : 0.0;
+		double perIter = (started > nSlotsAlloc) ? (double)(started - nSlotsAlloc) / (double)it : 0.0;
 		double remaining = (double)(totalJobs - started);
 		double predict = (perIter > 0.0) ? remaining / perIter : (double)batch * 2.0;
 		uint32_t next = (uint32_t)(predict * 0.9);
@@ -478,6 +490,12 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		if (next < 4) next = 4;
 		if (next > 4096) next = 4096;
 		batch = next;
+	}
+	// join
+	for (int k = 0; k < K; k++)
+	{
+		cudaEventRecord(ctx->poolDone[k], ctx->poolStreams[k]);
+		cudaStreamWaitEvent(ctx->stream, ctx->poolDone[k], 0);
 	}
 	cudaEventRecord(ev.b, ctx->stream);
 	ctx->pending.push_back(ev);
@@ -546,8 +564,8 @@ int rtb_create(int device, rtb_ctx** out)
 	ctx->device = device;
 	rtb_default_params(&ctx->params);
 	memset(&ctx->S, 0, sizeof(ctx->S));
-	if (cudaSetDevice(device) != cudaSuccess || cudaMalloc((void**)&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-	    cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)) != cudaSuccess)
+	if (cudaSetDevice(device) != cudaSuccess || cudaMalloc((void**)&ctx->counters, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMemset(ctx->counters, 0, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long)) != cudaSuccess)
 	{
 		int rc = fail(nullptr, RTB_ERR_CUDA, "context creation on device %d failed: %s", device,
 		              cudaGetErrorString(cudaGetLastError()));
@@ -566,9 +584,12 @@ void rtb_destroy(rtb_ctx* ctx)
 	resolveTimings(ctx);
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
 	freeScene(ctx);
-	if (ctx->shadowStream) cudaStreamDestroy(ctx->shadowStream);
-	if (ctx->evShade) cudaEventDestroy(ctx->evShade);
-	if (ctx->evShadow) cudaEventDestroy(ctx->evShadow);
+	for (int k = 0; k < RTB_MAX_POOLS; k++)
+	{
+		if (ctx->poolStreams[k]) cudaStreamDestroy(ctx->poolStreams[k]);
+		if (ctx->poolDone[k]) cudaEventDestroy(ctx->poolDone[k]);
+	}
+	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
 	if (ctx->counters) cudaFree(ctx->counters);
 	if (ctx->hostProbe) cudaFreeHost(ctx->hostProbe);
 	delete ctx;
@@ -719,7 +740,7 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 		long v = atol(e);
 		if (v >= 1024 && v <= (64l << 20)) ctx->poolSlots = (uint32_t)v & ~31u;
 	}
-	CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	CK(cudaMemsetAsync(ctx->counters, 0, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long), ctx->stream));
 	ctx->spp = 0;
 	ctx->renderMs = 0.0;
 	// the host vectors above die at return: finish the async copies first
@@ -746,7 +767,7 @@ int rtb_clear(rtb_ctx* ctx)
 	CK(cudaMemsetAsync(ctx->film, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(float), ctx->stream));
 	CK(cudaMemsetAsync(ctx->accum, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(long long), ctx->stream));
 	ctx->filmDirty = false;
-	CK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	CK(cudaMemsetAsync(ctx->counters, 0, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long), ctx->stream));
 	resolveTimings(ctx);
 	ctx->spp = 0;
 	ctx->renderMs = 0.0;
@@ -842,9 +863,11 @@ int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out)
 {
 	if (!ctx || !out) return RTB_ERR_ARG;
 	if (int rc = bind(ctx)) return rc;
-	unsigned long long c[8];
-	CK(cudaMemcpyAsync(c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+	unsigned long long rows[RTB_COUNTER_STRIPES * 8], c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	CK(cudaMemcpyAsync(rows, ctx->counters, sizeof(rows), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	for (int r = 0; r < RTB_COUNTER_STRIPES; r++)
+		for (int k = 0; k < 8; k++) c[k] += rows[r * 8 + k];
 	resolveTimings(ctx);
 	memset(out, 0, sizeof(*out));
 	out->samples = c[0], out->closest_rays = c[1], out->shadow_rays = c[2];

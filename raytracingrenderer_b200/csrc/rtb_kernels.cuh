@@ -19,8 +19,13 @@ struct Tally
 	uint32_t samples, closest, shadow, box, tri, sbox, stri;
 };
 
+// Work counters are STRIPED: RTB_COUNTER_STRIPES rows of 8 x u64, a block adds to row
+// blockIdx.x % stripes, the host sums the rows.  (One row made ~10^4 same-address atomics per
+// launch serialise in the L2 atomic unit: a fixed cost of tens of microseconds per kernel.)
+#define RTB_COUNTER_STRIPES 64
 RTB_DEV void flushTally(const Tally& c, unsigned long long* counters)
 {
+	counters += (size_t)(blockIdx.x % RTB_COUNTER_STRIPES) * 8;
 	uint32_t v[7] = {c.samples, c.closest, c.shadow, c.box, c.tri, c.sbox, c.stri};
 #pragma unroll
 	for (int k = 0; k < 7; k++)

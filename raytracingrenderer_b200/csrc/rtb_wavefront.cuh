@@ -489,6 +489,30 @@ __global__ void __launch_bounds__(128) k_wf_extend(const __grid_constant__ DevSc
 	flushTally(tl, A.counters);
 }
 
+
+// One thread per slot (the v3 extend stage), kept selectable for A/B measurements against the
+// persistent kernel above (RTB_SIMPLE_EXTEND=1).
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_wf_extend_simple(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
+{
+	const rtb_params& P = A.P;
+	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return;
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.nSlots; slot += gridDim.x * blockDim.x)
+	{
+		float4 d = A.rayD[slot];
+		if (!(__float_as_uint(d.w) & WF_ALIVE)) continue;
+		float4 o = A.rayO[slot];
+		RayD r = mkRay(mk(o), mk(d));
+		HitD h;
+		tl.closest++;
+		if (TRAV == RTB_TRAV_EXACT || rayIsDegenerate(r) || S.fast_root < 0) closestExact(S, r, P.epsilon, h, tl.box, tl.tri);
+		else closestFastBody(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+		A.hit[slot] = make_float4(__uint_as_float(h.id), h.t, h.alpha, h.beta);
+	}
+	flushTally(tl, A.counters);
+}
+
 // Shadow rays: one thread per queued ray.  (A persistent/prefetching variant like k_wf_extend was
 // measured slower here — profiles/r01_v4_persistent_traversal.txt: the queue holds only ~0.2 rays
 // per slot and any-hit rays are short, so the refill bookkeeping outweighs the regained lanes.)
@@ -511,6 +535,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevSc
 	}
 	flushTally(tl, A.counters);
 }
+
 
 // ---------------------------------------------------------------------------------------
 // NEE with deferred visibility: RayTracer::computeDirect (Renderer.h:423-473) up to the
@@ -730,14 +755,20 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DevSce
 		if (done && !live) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
 		if (aliveAfter || live) nAlive++;
 	}
+	// block-level totals: one atomic per block for `alive`, one striped atomic for the sample count
 	for (int o = 16; o > 0; o >>= 1)
 	{
 		nAlive += __shfl_xor_sync(0xFFFFFFFFu, nAlive, o);
 		nDone += __shfl_xor_sync(0xFFFFFFFFu, nDone, o);
 	}
-	if (lane == 0)
+	__shared__ uint32_t sAlive[4], sDone[4];
+	if (lane == 0) sAlive[threadIdx.x >> 5] = nAlive, sDone[threadIdx.x >> 5] = nDone;
+	__syncthreads();
+	if (threadIdx.x == 0)
 	{
-		if (nAlive) atomicAdd(&A.ctrl[iter].alive, nAlive);
-		if (nDone) atomicAdd(&A.counters[0], (unsigned long long)nDone);
+		uint32_t a = 0, d = 0;
+		for (uint32_t i = 0; i < (blockDim.x >> 5); i++) a += sAlive[i], d += sDone[i];
+		if (a) atomicAdd(&A.ctrl[iter].alive, a);
+		if (d) atomicAdd(&A.counters[(size_t)(blockIdx.x % RTB_COUNTER_STRIPES) * 8], (unsigned long long)d);
 	}
 }
