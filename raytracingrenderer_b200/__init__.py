@@ -17,7 +17,8 @@ from . import abi
 from .abi import FlatScene  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+# RTB200_LIB lets a developer A/B an experimental build of the same ABI (never a fallback)
+LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")
 
 # every symbol include/rtb.h declares (tests check the built library exports all of them)
 ABI_SYMBOLS = [

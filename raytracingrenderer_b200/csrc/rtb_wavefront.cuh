@@ -25,6 +25,14 @@
 #pragma once
 #include "rtb_kernels.cuh"
 
+// resident 128-thread blocks per SM the stage kernels are compiled for (register budget)
+#ifndef WF_SHADE_MIN_BLOCKS
+#define WF_SHADE_MIN_BLOCKS 6
+#endif
+#ifndef WF_EXTEND_MIN_BLOCKS
+#define WF_EXTEND_MIN_BLOCKS 8
+#endif
+
 #define WF_ALIVE 0x200u
 #define WF_CANHIT 0x100u
 #define WF_DEPTH_MASK 0xFFu
@@ -366,7 +374,7 @@ RTB_DEV void laneInterior(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stack
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(128) k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
+__global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
 	const rtb_params& P = A.P;
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
@@ -619,7 +627,7 @@ RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& 
 }
 
 template <int INTEGRATOR>
-__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
+__global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
 	const rtb_params& P = A.P;
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
