@@ -180,8 +180,10 @@ typedef enum rtb_sampling {
 
 typedef enum rtb_traversal {
 	RTB_TRAV_EXACT = 0, /* the reference's own tree, exhaustive DFS (Geometry.h:399-427) */
-	RTB_TRAV_FAST = 1   /* accelerated tree over the reference's leaves, ordered + culled;
+	RTB_TRAV_FAST = 1,  /* accelerated binary tree over the reference's leaves, ordered + culled;
 	                       must return identical hits (tests assert it)                */
+	RTB_TRAV_WIDE = 2   /* the same tree collapsed to 4 children per node (selectable; measured
+	                       ~5 % slower than FAST on B200, profiles/r01_wide_tree.txt)     */
 } rtb_traversal;
 
 typedef enum rtb_filter {

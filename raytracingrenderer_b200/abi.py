@@ -52,7 +52,7 @@ MAT_SPECULAR, MAT_TWO_SIDED, MAT_LIGHT, MAT_LAYERED = 1, 2, 4, 8
 LIGHT_AREA, LIGHT_BACKGROUND, LIGHT_ENVMAP = 0, 1, 2
 INT_PATH, INT_DIRECT, INT_ALBEDO, INT_NORMALS = 0, 1, 2, 3
 SAMPLING_STRICT, SAMPLING_IMPORTANCE = 0, 1
-TRAV_EXACT, TRAV_FAST = 0, 1
+TRAV_EXACT, TRAV_FAST, TRAV_WIDE = 0, 1, 2
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 PART_NONE, PART_SPP, PART_TILE = 0, 1, 2
 SCHED_WAVEFRONT, SCHED_MEGAKERNEL = 0, 1

@@ -295,6 +295,109 @@ private:
 	}
 };
 
+
+// ---------------------------------------------------------------------------------------
+// WIDE tree: the FAST binary tree collapsed to 4 children per node (the child with the largest
+// surface area is replaced by its own two children until there are four).  Same boxes, same
+// leaves; half the dependent node fetches per ray.  128-byte nodes, structure of arrays:
+//   [0] min.x[4] [1] max.x[4] [2] min.y[4] [3] max.y[4] [4] min.z[4] [5] max.z[4]
+//   [6] child references [4] (>= 0 node, < 0 leaf, RTB_WIDE_EMPTY unused slot) [7] unused
+// ---------------------------------------------------------------------------------------
+#define RTB_WIDE_EMPTY 0x7FFFFFFE
+
+struct WideTree
+{
+	std::vector<F4> nodes; // 8 x F4 per node
+	int32_t root = 0;
+	uint32_t maxDepth = 0;
+};
+
+class WideBuilder
+{
+public:
+	WideBuilder(const FastTree& t) : B(t) {}
+	void build(WideTree& out)
+	{
+		out.nodes.clear();
+		out.maxDepth = 0;
+		W = &out;
+		if (B.root < 0 || B.nodes.empty())
+		{
+			out.root = B.root; // single leaf / empty scene
+			return;
+		}
+		out.nodes.reserve(B.nodes.size() * 2 / 3 + 8);
+		out.root = emit(B.root, 0);
+	}
+
+private:
+	const FastTree& B;
+	WideTree* W = nullptr;
+	struct Cand
+	{
+		int32_t ref;
+		float mn[3], mx[3];
+		float area() const
+		{
+			float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+			return 2.0f * (dx * dy + dy * dz + dz * dx);
+		}
+	};
+	static uint32_t bits(float f)
+	{
+		uint32_t u;
+		memcpy(&u, &f, 4);
+		return u;
+	}
+	void children(int32_t node, Cand& c0, Cand& c1) const
+	{
+		const F4* nd = &B.nodes[(size_t)node * 4];
+		c0.ref = (int32_t)bits(nd[3].x), c1.ref = (int32_t)bits(nd[3].y);
+		c0.mn[0] = nd[0].x, c0.mx[0] = nd[0].y, c0.mn[1] = nd[0].z, c0.mx[1] = nd[0].w;
+		c1.mn[0] = nd[1].x, c1.mx[0] = nd[1].y, c1.mn[1] = nd[1].z, c1.mx[1] = nd[1].w;
+		c0.mn[2] = nd[2].x, c0.mx[2] = nd[2].y, c1.mn[2] = nd[2].z, c1.mx[2] = nd[2].w;
+	}
+	int32_t emit(int32_t node, uint32_t depth)
+	{
+		if (depth > W->maxDepth) W->maxDepth = depth;
+		Cand c[4];
+		int n = 2;
+		children(node, c[0], c[1]);
+		while (n < 4)
+		{
+			int best = -1;
+			float bestArea = -1.0f;
+			for (int i = 0; i < n; i++)
+				if (c[i].ref >= 0 && c[i].area() > bestArea) bestArea = c[i].area(), best = i;
+			if (best < 0) break;
+			Cand a, b;
+			children(c[best].ref, a, b);
+			c[best] = a;
+			c[n++] = b;
+		}
+		size_t self = W->nodes.size() / 8;
+		W->nodes.resize(W->nodes.size() + 8);
+		int32_t refs[4];
+		for (int i = 0; i < 4; i++)
+		{
+			if (i >= n) refs[i] = RTB_WIDE_EMPTY;
+			else refs[i] = (c[i].ref >= 0) ? emit(c[i].ref, depth + 1) : c[i].ref;
+		}
+		F4* nd = &W->nodes[self * 8];
+		float v[6][4];
+		for (int i = 0; i < 4; i++)
+			for (int k = 0; k < 3; k++)
+			{
+				v[k * 2][i] = (i < n) ? c[i].mn[k] : FLT_MAX;
+				v[k * 2 + 1][i] = (i < n) ? c[i].mx[k] : -FLT_MAX;
+			}
+		for (int r = 0; r < 6; r++) nd[r] = {v[r][0], v[r][1], v[r][2], v[r][3]};
+		nd[6] = {bitsToFloat((uint32_t)refs[0]), bitsToFloat((uint32_t)refs[1]), bitsToFloat((uint32_t)refs[2]), bitsToFloat((uint32_t)refs[3])};
+		nd[7] = {0, 0, 0, 0};
+		return (int32_t)self;
+	}
+};
+
 // ---------------------------------------------------------------------------------------
 // Environment-map sampling tables (RTB_SAMPLING_IMPORTANCE).  EnvironmentMap::evaluate
 // (RTBase/Lights.h:158-165) maps a direction to u = phi/2pi, v = theta/pi and

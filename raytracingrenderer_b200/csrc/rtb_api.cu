@@ -11,6 +11,30 @@
 #include <string>
 #include <vector>
 
+// run __VA_ARGS__ with `TR` bound to the compile-time value of a run-time rtb_traversal
+#define RTB_TRAV_SWITCH(trav, ...)                         \
+	switch (trav)                                          \
+	{                                                      \
+	case RTB_TRAV_EXACT:                                   \
+	{                                                      \
+		constexpr int TR = RTB_TRAV_EXACT;                 \
+		__VA_ARGS__;                                       \
+	}                                                      \
+	break;                                                 \
+	case RTB_TRAV_FAST:                                    \
+	{                                                      \
+		constexpr int TR = RTB_TRAV_FAST;                  \
+		__VA_ARGS__;                                       \
+	}                                                      \
+	break;                                                 \
+	default:                                               \
+	{                                                      \
+		constexpr int TR = RTB_TRAV_WIDE;                  \
+		__VA_ARGS__;                                       \
+	}                                                      \
+	break;                                                 \
+	}
+
 namespace
 {
 thread_local std::string g_createError;
@@ -69,7 +93,7 @@ struct rtb_ctx
 	int wfTilePart[3] = {-1, -1, -1}; // partition, rank, world the tile list was built for
 	unsigned long long* hostProbe = nullptr; // pinned: {nextJob, alive}
 	int smCount = 0;
-	int travBlocksPerSM[2][2] = {{0, 0}, {0, 0}}; // [extend|shadow][exact|fast]
+	int travBlocksPerSM[3] = {0, 0, 0}; // persistent extend kernel, per rtb_traversal
 	uint32_t poolSlots = 8u << 20; // profiles/r01_pool_sweep.txt: per-launch ramp/tail amortise up to ~8 M slots
 	bool simpleExtend = false;
 	int pools = 2; // sub-pools advancing concurrently on their own streams (profiles/r01_pool_sweep.txt)
@@ -219,7 +243,7 @@ void resolveTimings(rtb_ctx* ctx)
 
 int checkTrav(rtb_ctx* ctx, int traversal)
 {
-	if (traversal != RTB_TRAV_EXACT && traversal != RTB_TRAV_FAST) return fail(ctx, RTB_ERR_ARG, "bad traversal %d", traversal);
+	if (traversal < RTB_TRAV_EXACT || traversal > RTB_TRAV_WIDE) return fail(ctx, RTB_ERR_ARG, "bad traversal %d", traversal);
 	return RTB_OK;
 }
 } // namespace
@@ -249,8 +273,7 @@ static int renderMegakernel(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count
 	dim3 block(64), grid((warps + 1) / 2);
 	EventPair ev = {getEvent(ctx), getEvent(ctx)};
 	cudaEventRecord(ev.a, ctx->stream);
-	if (ctx->params.traversal == RTB_TRAV_EXACT) launchRender<RTB_TRAV_EXACT>(ctx, A, grid, block);
-	else launchRender<RTB_TRAV_FAST>(ctx, A, grid, block);
+	RTB_TRAV_SWITCH(ctx->params.traversal, launchRender<TR>(ctx, A, grid, block));
 	cudaEventRecord(ev.b, ctx->stream);
 	ctx->pending.push_back(ev);
 	ctx->launches++;
@@ -376,11 +399,12 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, ctx->device));
 		ctx->smCount = prop.multiProcessorCount;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0][0], k_wf_extend<RTB_TRAV_EXACT>, 128, 0));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0][1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0], k_wf_extend<RTB_TRAV_EXACT>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[2], k_wf_extend<RTB_TRAV_WIDE>, 128, 0));
 		if (const char* e = getenv("RTB_SIMPLE_EXTEND")) ctx->simpleExtend = atoi(e) != 0;
 	}
-	int ti = (P.traversal == RTB_TRAV_EXACT) ? 0 : 1;
+	int ti = P.traversal;
 	WfArgs A[RTB_MAX_POOLS];
 	float4* base = (float4*)ctx->wfState;
 	for (int k = 0; k < K; k++)
@@ -401,7 +425,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		a.P = P;
 	}
 	// persistent traversal kernel: one resident wave; grid-stride kernels: enough blocks to fill the machine
-	unsigned gridExtend = (unsigned)(ctx->smCount * (ctx->travBlocksPerSM[0][ti] > 0 ? ctx->travBlocksPerSM[0][ti] : 1));
+	unsigned gridExtend = (unsigned)(ctx->smCount * (ctx->travBlocksPerSM[ti] > 0 ? ctx->travBlocksPerSM[ti] : 1));
 	unsigned maxBlocks = (unsigned)ctx->smCount * 16u;
 	unsigned gridSlots = (perPool + 127) / 128;
 	if (gridSlots > maxBlocks) gridSlots = maxBlocks;
@@ -438,9 +462,14 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 					for (int e = 0; e < 4; e++) se.e[e] = getEvent(ctx);
 					cudaEventRecord(se.e[0], st);
 				}
-				if (ti == 0) k_wf_extend<RTB_TRAV_EXACT><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it);
-				else if (ctx->simpleExtend) k_wf_extend_simple<RTB_TRAV_FAST><<<(perPool + 127) / 128, 128, 0, st>>>(ctx->S, A[k], it);
-				else k_wf_extend<RTB_TRAV_FAST><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it);
+				if (ctx->simpleExtend)
+				{
+					RTB_TRAV_SWITCH(ti, k_wf_extend_simple<TR><<<(perPool + 127) / 128, 128, 0, st>>>(ctx->S, A[k], it));
+				}
+				else
+				{
+					RTB_TRAV_SWITCH(ti, k_wf_extend<TR><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it));
+				}
 				if (timed) cudaEventRecord(se.e[1], st);
 				switch (P.integrator)
 				{
@@ -453,8 +482,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 				if (timed) cudaEventRecord(se.e[2], st);
 				if (shadows)
 				{
-					if (ti == 0) k_wf_shadow<RTB_TRAV_EXACT><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);
-					else k_wf_shadow<RTB_TRAV_FAST><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);
+					RTB_TRAV_SWITCH(ti, k_wf_shadow<TR><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it));
 					ctx->launches++;
 				}
 				if (timed)
@@ -536,7 +564,7 @@ void rtb_default_params(rtb_params* p)
 	p->rr_cap = 0.9f;     // RTBase/Renderer.h:353
 	p->integrator = RTB_INT_PATH;
 	p->sampling = RTB_SAMPLING_STRICT;
-	p->traversal = RTB_TRAV_FAST;
+	p->traversal = RTB_TRAV_FAST; // profiles/r01_wide_tree.txt: the 4-wide tree measured ~5 % slower
 	p->filter = RTB_FILTER_BOX; // RTBase/Renderer.h:50
 	p->filter_radius = 2.0f;    // RTBase/Renderer.h:51
 	p->filter_alpha = 0.1f;
@@ -680,7 +708,14 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
 	}
-	if (fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u)", fast.maxDepth);
+	rtb_accel::WideTree wide;
+	{
+		rtb_accel::WideBuilder wb(fast);
+		wb.build(wide);
+	}
+	// stack need: one pending sibling per level (binary), up to three per level (4-wide)
+	if (fast.maxDepth + 2 > RTB_STACK || 3 * wide.maxDepth + 6 > RTB_STACK)
+		return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (binary %u, wide %u)", fast.maxDepth, wide.maxDepth);
 
 	CK(cudaStreamSynchronize(ctx->stream));
 	freeScene(ctx);
@@ -697,6 +732,11 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 	S.n_xnodes = sc->n_ref_nodes;
 	S.n_fnodes = (uint32_t)(fast.nodes.size() / 4);
 	S.fast_root = fast.root;
+	const rtb_accel::F4* dw = nullptr;
+	if ((rc = uploadArray(ctx, wide.nodes.data(), wide.nodes.size(), &dw))) return rc;
+	S.wnodes = (const float4*)dw;
+	S.n_wnodes = (uint32_t)(wide.nodes.size() / 8);
+	S.wide_root = wide.root;
 	ctx->fastDepth = fast.maxDepth;
 	const rtb_tri_isect* dti = nullptr;
 	const rtb_tri_shade* dts = nullptr;
@@ -900,10 +940,7 @@ int rtb_primary_hits(rtb_ctx* ctx, int traversal, uint32_t* ids, float* t, rtb_r
 	CK(sc.out(t, n, &dT));
 	CK(sc.out(rays, n, &dR));
 	unsigned grid = (unsigned)((n + 127) / 128);
-	if (traversal == RTB_TRAV_EXACT)
-		k_primary<RTB_TRAV_EXACT><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, ctx->width, ctx->height, dIds, dT, dR, ctx->counters);
-	else
-		k_primary<RTB_TRAV_FAST><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, ctx->width, ctx->height, dIds, dT, dR, ctx->counters);
+	RTB_TRAV_SWITCH(traversal, k_primary<TR><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, ctx->width, ctx->height, dIds, dT, dR, ctx->counters));
 	ctx->launches++;
 	CK(cudaGetLastError());
 	if (ids) CK(cudaMemcpyAsync(ids, dIds, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -927,10 +964,7 @@ int rtb_trace(rtb_ctx* ctx, int traversal, int any_hit, const rtb_ray* rays, uin
 	CK(sc.in(rays, n, &dR, ctx->stream));
 	CK(sc.out(hits, n, &dH));
 	unsigned grid = (unsigned)((n + 127) / 128);
-	if (traversal == RTB_TRAV_EXACT)
-		k_trace<RTB_TRAV_EXACT><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, any_hit, dR, n, dH, ctx->counters);
-	else
-		k_trace<RTB_TRAV_FAST><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, any_hit, dR, n, dH, ctx->counters);
+	RTB_TRAV_SWITCH(traversal, k_trace<TR><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, any_hit, dR, n, dH, ctx->counters));
 	ctx->launches++;
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(hits, dH, n * sizeof(rtb_hit), cudaMemcpyDeviceToHost, ctx->stream));
@@ -952,10 +986,7 @@ int rtb_visible(rtb_ctx* ctx, int traversal, const float* p1p2, uint64_t n, uint
 	CK(sc.in(p1p2, n * 6, &dP, ctx->stream));
 	CK(sc.out(out, n, &dO));
 	unsigned grid = (unsigned)((n + 127) / 128);
-	if (traversal == RTB_TRAV_EXACT)
-		k_visible<RTB_TRAV_EXACT><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, dP, n, dO, ctx->counters);
-	else
-		k_visible<RTB_TRAV_FAST><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, dP, n, dO, ctx->counters);
+	RTB_TRAV_SWITCH(traversal, k_visible<TR><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->params.epsilon, ctx->params.cull_rel, dP, n, dO, ctx->counters));
 	ctx->launches++;
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(out, dO, n, cudaMemcpyDeviceToHost, ctx->stream));

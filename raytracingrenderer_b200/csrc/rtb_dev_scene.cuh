@@ -27,6 +27,8 @@ struct DevScene
 	//   [4i+2] = c0.min.z c0.max.z c1.min.z c1.max.z
 	//   [4i+3] = bits(child0) bits(child1) - -     child >= 0: node index; < 0: ~((start<<2)|count)
 	const float4* fnodes;
+	// WIDE tree: FAST collapsed to 4 children, 8 x float4 per node (layout: rtb_accel.hpp WideBuilder)
+	const float4* wnodes;
 	const float4* tri;  // 4 x float4 per triangle = rtb_tri_isect
 	const float4* tsh;  // 4 x float4 per triangle = rtb_tri_shade
 	const rtb_material* mats;
@@ -39,6 +41,8 @@ struct DevScene
 	const float* env_pdf;      // [H*W] solid-angle pdf of the texel's centre direction
 	uint32_t n_xnodes, n_fnodes, n_tris, n_lights, n_mats, n_texs;
 	int32_t fast_root; // child reference of the FAST root (may itself be a leaf)
+	int32_t wide_root;
+	uint32_t n_wnodes;
 	uint32_t bg_type;
 	float bg_colour[3];
 	int32_t bg_tex;
@@ -188,7 +192,7 @@ RTB_DEV bool visibleExact(const DevScene& S, const RayD& r, float eps, float max
 // leaf, is tested with the reference's exact slab arithmetic, children are visited
 // near-first and popped nodes are dropped when t_entry - |t_entry|*rel > t_best.
 // ---------------------------------------------------------------------------------------
-#define RTB_STACK 64
+#define RTB_STACK 96 /* rtb_upload_scene rejects trees that could need more */
 
 RTB_DEV bool rayIsDegenerate(const RayD& r)
 {
@@ -215,93 +219,146 @@ RTB_DEV void leafClosest(const DevScene& S, int32_t ref, const RayD& r, float ep
 	}
 }
 
-RTB_DEV void closestFast(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox,
-                         uint32_t& nTri)
+// Without NaN operands (no 0*inf: degenerate rays go to the EXACT tree) the selects of
+// RTBase/Core.h:187-195 and fminf/fmaxf agree except for the sign of a zero, which no later
+// comparison can see: same accept decisions as slabTest().
+RTB_DEV bool slabTestNoNaN(float minx, float miny, float minz, float maxx, float maxy, float maxz, const RayD& r,
+                           float& tEntry)
 {
-	if (rayIsDegenerate(r))
+	float ax = (minx - r.o.x) * r.inv.x, ay = (miny - r.o.y) * r.inv.y, az = (minz - r.o.z) * r.inv.z;
+	float bx = (maxx - r.o.x) * r.inv.x, by = (maxy - r.o.y) * r.inv.y, bz = (maxz - r.o.z) * r.inv.z;
+	float te = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+	float tx = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+	tEntry = te;
+	return !(tx < te || tx < 0.0f);
+}
+
+#define RTB_TRAV_DONE_ 0x7FFFFFFF
+#define RTB_WIDE_EMPTY 0x7FFFFFFE
+
+// Per-ray traversal state shared by the one-thread-per-ray loops below and the persistent
+// warp kernels of rtb_wavefront.cuh.  `bestT` is the best t so far (closest hit) or maxT (any hit).
+template <bool ANYHIT>
+struct LaneTrav
+{
+	RayD r;
+	float bestT;
+	uint32_t bestId;
+	float bestU, bestV;
+	int32_t cur; // >= 0 interior node, < 0 leaf reference, RTB_TRAV_DONE_ finished
+	int sp;
+};
+
+template <bool ANYHIT>
+RTB_DEV bool travCull(float te, float lim, float cullRel)
+{
+	// closest: drop if entered beyond the best hit; any-hit: at or beyond maxT (t < maxT is needed)
+	float lo = te - fabsf(te) * cullRel;
+	return ANYHIT ? (lo >= lim) : (lo > lim);
+}
+
+template <bool ANYHIT>
+RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const int32_t* stackNode, const float* stackT, float cullRel)
+{
+	t.cur = RTB_TRAV_DONE_;
+	while (t.sp > 0)
 	{
-		closestExact(S, r, eps, h, nBox, nTri);
+		t.sp--;
+		if (travCull<ANYHIT>(stackT[t.sp], t.bestT, cullRel)) continue;
+		t.cur = stackNode[t.sp];
+		break;
+	}
+}
+
+// One interior step of the binary FAST tree: both child boxes, near child next, far child pushed.
+template <bool ANYHIT>
+RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel, uint32_t& nBox)
+{
+	const float4* nd = S.fnodes + (size_t)t.cur * 4;
+	float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
+	float t0, t1;
+	nBox += 2;
+	bool h0 = slabTestNoNaN(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, t.r, t0);
+	bool h1 = slabTestNoNaN(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, t.r, t1);
+	h0 = h0 && !travCull<ANYHIT>(t0, t.bestT, cullRel);
+	h1 = h1 && !travCull<ANYHIT>(t1, t.bestT, cullRel);
+	int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
+	if (h0 && h1)
+	{
+		bool swap = !ANYHIT && (t1 < t0);
+		stackNode[t.sp] = swap ? c0 : c1;
+		stackT[t.sp] = swap ? t0 : t1;
+		t.sp++;
+		t.cur = swap ? c1 : c0;
+	}
+	else if (h0) t.cur = c0;
+	else if (h1) t.cur = c1;
+	else lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
+}
+
+// One interior step of the 4-wide tree (rtb_accel.hpp WideBuilder): four child boxes from one
+// 128-byte structure-of-arrays node.  Closest hit: children are visited near to far.  The order
+// comes from sorting four keys = float bits of max(t_entry, 0) with the child slot in the two
+// low mantissa bits (a 5-comparator network on unsigned integers); the t pushed on the stack is
+// that key with the slot bits cleared: never larger than the true t_entry, so culling stays
+// conservative.
+RTB_DEV void cswap(uint32_t& a, uint32_t& b)
+{
+	uint32_t lo = min(a, b), hi = max(a, b);
+	a = lo, b = hi;
+}
+template <bool ANYHIT>
+RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel, uint32_t& nBox)
+{
+	const float4* nd = S.wnodes + (size_t)t.cur * 8;
+	float4 mnx = ldg4(nd), mxx = ldg4(nd + 1), mny = ldg4(nd + 2), mxy = ldg4(nd + 3), mnz = ldg4(nd + 4), mxz = ldg4(nd + 5);
+	float4 rf = ldg4(nd + 6);
+	int32_t c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
+	float e0, e1, e2, e3;
+	bool h0 = slabTestNoNaN(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, t.r, e0);
+	bool h1 = slabTestNoNaN(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, t.r, e1);
+	bool h2 = slabTestNoNaN(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, t.r, e2) && c2 != RTB_WIDE_EMPTY;
+	bool h3 = slabTestNoNaN(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, t.r, e3) && c3 != RTB_WIDE_EMPTY;
+	nBox += 2u + (c2 != RTB_WIDE_EMPTY) + (c3 != RTB_WIDE_EMPTY);
+	h0 = h0 && !travCull<ANYHIT>(e0, t.bestT, cullRel);
+	h1 = h1 && !travCull<ANYHIT>(e1, t.bestT, cullRel);
+	h2 = h2 && !travCull<ANYHIT>(e2, t.bestT, cullRel);
+	h3 = h3 && !travCull<ANYHIT>(e3, t.bestT, cullRel);
+	if (ANYHIT)
+	{
+		// order is irrelevant for the result; push every admitted child, continue with the last
+		if (h0) stackNode[t.sp] = c0, stackT[t.sp] = e0, t.sp++;
+		if (h1) stackNode[t.sp] = c1, stackT[t.sp] = e1, t.sp++;
+		if (h2) stackNode[t.sp] = c2, stackT[t.sp] = e2, t.sp++;
+		if (h3) stackNode[t.sp] = c3, stackT[t.sp] = e3, t.sp++;
+		lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
 		return;
 	}
-	h.id = RTB_MISS_ID;
-	h.t = FLT_MAX;
-	h.alpha = h.beta = 0.0f;
-	if (S.n_xnodes == 0) return;
-	int32_t stackNode[RTB_STACK];
-	float stackT[RTB_STACK];
-	int sp = 0;
-	int32_t cur = S.fast_root;
-	if (cur < 0)
-	{
-		// single-leaf scene: the root box is the leaf box
-		float4 A = ldg4(S.xnodes), B = ldg4(S.xnodes + 1);
-		float te;
-		nBox++;
-		if (slabTest(A.x, A.y, A.z, B.x, B.y, B.z, r, te)) leafClosest(S, cur, r, eps, h, nTri);
-		return;
-	}
-	for (;;)
-	{
-		// cur is an interior node: test both children
-		const float4* nd = S.fnodes + (size_t)cur * 4;
-		float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
-		float t0, t1;
-		nBox += 2;
-		bool h0 = slabTest(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, r, t0);
-		bool h1 = slabTest(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, r, t1);
-		int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
-		// cull against the current best
-		h0 = h0 && !((t0 - fabsf(t0) * cullRel) > h.t);
-		h1 = h1 && !((t1 - fabsf(t1) * cullRel) > h.t);
-		// leaves are intersected immediately (their box test is the exact leaf test)
-		if (h0 && c0 < 0)
-		{
-			leafClosest(S, c0, r, eps, h, nTri);
-			h0 = false;
-		}
-		if (h1 && c1 < 0)
-		{
-			leafClosest(S, c1, r, eps, h, nTri);
-			h1 = false;
-		}
-		if (h0 && h1)
-		{
-			// near child first, far child on the stack
-			bool swap = t1 < t0;
-			int32_t nearC = swap ? c1 : c0, farC = swap ? c0 : c1;
-			float farT = swap ? t0 : t1;
-			if (sp < RTB_STACK)
-			{
-				stackNode[sp] = farC;
-				stackT[sp] = farT;
-				sp++;
-			}
-			cur = nearC;
-			continue;
-		}
-		if (h0)
-		{
-			cur = c0;
-			continue;
-		}
-		if (h1)
-		{
-			cur = c1;
-			continue;
-		}
-		// pop
-		bool found = false;
-		while (sp > 0)
-		{
-			sp--;
-			float te = stackT[sp];
-			if ((te - fabsf(te) * cullRel) > h.t) continue;
-			cur = stackNode[sp];
-			found = true;
-			break;
-		}
-		if (!found) break;
-	}
+	uint32_t k0 = h0 ? ((__float_as_uint(fmaxf(e0, 0.0f)) & ~3u) | 0u) : 0xFFFFFFFFu;
+	uint32_t k1 = h1 ? ((__float_as_uint(fmaxf(e1, 0.0f)) & ~3u) | 1u) : 0xFFFFFFFFu;
+	uint32_t k2 = h2 ? ((__float_as_uint(fmaxf(e2, 0.0f)) & ~3u) | 2u) : 0xFFFFFFFFu;
+	uint32_t k3 = h3 ? ((__float_as_uint(fmaxf(e3, 0.0f)) & ~3u) | 3u) : 0xFFFFFFFFu;
+	cswap(k0, k1), cswap(k2, k3), cswap(k0, k2), cswap(k1, k3), cswap(k1, k2);
+	// farthest first onto the stack, nearest becomes the next node
+#define RTB_WIDE_REF(k) (((k) & 3u) == 0u ? c0 : ((k) & 3u) == 1u ? c1 : ((k) & 3u) == 2u ? c2 : c3)
+	if (k3 != 0xFFFFFFFFu) stackNode[t.sp] = RTB_WIDE_REF(k3), stackT[t.sp] = __uint_as_float(k3 & ~3u), t.sp++;
+	if (k2 != 0xFFFFFFFFu) stackNode[t.sp] = RTB_WIDE_REF(k2), stackT[t.sp] = __uint_as_float(k2 & ~3u), t.sp++;
+	if (k1 != 0xFFFFFFFFu) stackNode[t.sp] = RTB_WIDE_REF(k1), stackT[t.sp] = __uint_as_float(k1 & ~3u), t.sp++;
+	if (k0 != 0xFFFFFFFFu) t.cur = RTB_WIDE_REF(k0);
+	else lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
+#undef RTB_WIDE_REF
+}
+
+template <int TRAV, bool ANYHIT>
+RTB_DEV void stepInterior(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel, uint32_t& nBox)
+{
+	if (TRAV == RTB_TRAV_WIDE) stepWide<ANYHIT>(S, t, stackNode, stackT, cullRel, nBox);
+	else stepFast<ANYHIT>(S, t, stackNode, stackT, cullRel, nBox);
+}
+template <int TRAV>
+RTB_DEV int32_t travRoot(const DevScene& S)
+{
+	return TRAV == RTB_TRAV_WIDE ? S.wide_root : S.fast_root;
 }
 
 RTB_DEV bool leafOccludes(const DevScene& S, int32_t ref, const RayD& r, float eps, float maxT, uint32_t& nTri)
@@ -321,64 +378,57 @@ RTB_DEV bool leafOccludes(const DevScene& S, int32_t ref, const RayD& r, float e
 	return false;
 }
 
-RTB_DEV bool visibleFast(const DevScene& S, const RayD& r, float eps, float maxT, float cullRel, uint32_t& nBox,
-                         uint32_t& nTri)
+
+// One thread runs one ray to the end (parity entry points, shadow stage, megakernel).
+template <int TRAV>
+RTB_DEV void closestAccel(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox,
+                          uint32_t& nTri)
 {
-	if (rayIsDegenerate(r)) return visibleExact(S, r, eps, maxT, nBox, nTri);
-	if (S.n_xnodes == 0) return true;
-	int32_t stackNode[RTB_STACK];
-	int sp = 0;
-	int32_t cur = S.fast_root;
-	if (cur < 0)
+	if (rayIsDegenerate(r) || travRoot<TRAV>(S) < 0)
 	{
-		float4 A = ldg4(S.xnodes), B = ldg4(S.xnodes + 1);
-		float te;
-		nBox++;
-		if (slabTest(A.x, A.y, A.z, B.x, B.y, B.z, r, te)) return !leafOccludes(S, cur, r, eps, maxT, nTri);
-		return true;
+		// 0*inf = NaN rays and single-leaf scenes take the reference's own tree
+		closestExact(S, r, eps, h, nBox, nTri);
+		return;
 	}
+	int32_t stackNode[RTB_STACK];
+	float stackT[RTB_STACK];
+	LaneTrav<false> t;
+	t.r = r;
+	t.bestT = FLT_MAX, t.bestId = RTB_MISS_ID, t.bestU = t.bestV = 0.0f;
+	t.sp = 0;
+	t.cur = travRoot<TRAV>(S);
 	for (;;)
 	{
-		const float4* nd = S.fnodes + (size_t)cur * 4;
-		float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
-		float t0, t1;
-		nBox += 2;
-		bool h0 = slabTest(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, r, t0);
-		bool h1 = slabTest(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, r, t1);
-		int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
-		// a box entered at or beyond maxT cannot hold an occluder (t < maxT needed)
-		h0 = h0 && !((t0 - fabsf(t0) * cullRel) >= maxT);
-		h1 = h1 && !((t1 - fabsf(t1) * cullRel) >= maxT);
-		if (h0 && c0 < 0)
-		{
-			if (leafOccludes(S, c0, r, eps, maxT, nTri)) return false;
-			h0 = false;
-		}
-		if (h1 && c1 < 0)
-		{
-			if (leafOccludes(S, c1, r, eps, maxT, nTri)) return false;
-			h1 = false;
-		}
-		if (h0 && h1)
-		{
-			if (sp < RTB_STACK) stackNode[sp++] = c1;
-			cur = c0;
-			continue;
-		}
-		if (h0)
-		{
-			cur = c0;
-			continue;
-		}
-		if (h1)
-		{
-			cur = c1;
-			continue;
-		}
-		if (sp == 0) break;
-		cur = stackNode[--sp];
+		while (t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stackNode, stackT, cullRel, nBox);
+		if (t.cur == RTB_TRAV_DONE_) break;
+		HitD b;
+		b.id = t.bestId, b.t = t.bestT, b.alpha = t.bestU, b.beta = t.bestV;
+		leafClosest(S, t.cur, t.r, eps, b, nTri);
+		t.bestId = b.id, t.bestT = b.t, t.bestU = b.alpha, t.bestV = b.beta;
+		lanePop<false>(t, stackNode, stackT, cullRel);
 	}
-	return true;
+	h.id = t.bestId, h.t = t.bestT, h.alpha = t.bestU, h.beta = t.bestV;
+}
+
+template <int TRAV>
+RTB_DEV bool visibleAccel(const DevScene& S, const RayD& r, float eps, float maxT, float cullRel, uint32_t& nBox,
+                          uint32_t& nTri)
+{
+	if (rayIsDegenerate(r) || travRoot<TRAV>(S) < 0) return visibleExact(S, r, eps, maxT, nBox, nTri);
+	int32_t stackNode[RTB_STACK];
+	float stackT[RTB_STACK];
+	LaneTrav<true> t;
+	t.r = r;
+	t.bestT = maxT;
+	t.sp = 0;
+	t.cur = travRoot<TRAV>(S);
+	for (;;)
+	{
+		while (t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, true>(S, t, stackNode, stackT, cullRel, nBox);
+		if (t.cur == RTB_TRAV_DONE_) return true;
+		if (leafOccludes(S, t.cur, t.r, eps, maxT, nTri)) return false;
+		lanePop<true>(t, stackNode, stackT, cullRel);
+	}
 }
 
 template <int TRAV>
@@ -386,7 +436,7 @@ RTB_DEV void closestHit(const DevScene& S, const RayD& r, float eps, float cullR
                         uint32_t& nTri)
 {
 	if (TRAV == RTB_TRAV_EXACT) closestExact(S, r, eps, h, nBox, nTri);
-	else closestFast(S, r, eps, cullRel, h, nBox, nTri);
+	else closestAccel<TRAV>(S, r, eps, cullRel, h, nBox, nTri);
 }
 
 template <int TRAV>
@@ -394,7 +444,7 @@ RTB_DEV bool anyVisible(const DevScene& S, const RayD& r, float eps, float maxT,
                         uint32_t& nTri)
 {
 	if (TRAV == RTB_TRAV_EXACT) return visibleExact(S, r, eps, maxT, nBox, nTri);
-	return visibleFast(S, r, eps, maxT, cullRel, nBox, nTri);
+	return visibleAccel<TRAV>(S, r, eps, maxT, cullRel, nBox, nTri);
 }
 
 // Scene::visible (RTBase/Scene.h:161-169)

@@ -36,7 +36,6 @@
 #define WF_ALIVE 0x200u
 #define WF_CANHIT 0x100u
 #define WF_DEPTH_MASK 0xFFu
-#define RTB_TRAV_DONE_ 0x7FFFFFFF
 
 struct WfCtrl
 {
@@ -173,134 +172,6 @@ __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScen
 }
 
 // ---------------------------------------------------------------------------------------
-// FAST traversal bodies for non-degenerate rays.  Same accept decisions as slabTest():
-// without NaN operands (no 0*inf: degenerate rays go to the EXACT tree) the selects of
-// RTBase/Core.h:187-195 and fminf/fmaxf agree except for the sign of a zero, which no later
-// comparison can see.
-// ---------------------------------------------------------------------------------------
-RTB_DEV bool slabTestNoNaN(float minx, float miny, float minz, float maxx, float maxy, float maxz, const RayD& r,
-                           float& tEntry)
-{
-	float ax = (minx - r.o.x) * r.inv.x, ay = (miny - r.o.y) * r.inv.y, az = (minz - r.o.z) * r.inv.z;
-	float bx = (maxx - r.o.x) * r.inv.x, by = (maxy - r.o.y) * r.inv.y, bz = (maxz - r.o.z) * r.inv.z;
-	float te = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-	float tx = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-	tEntry = te;
-	return !(tx < te || tx < 0.0f);
-}
-
-RTB_DEV void closestFastBody(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox,
-                             uint32_t& nTri)
-{
-	int32_t stackNode[RTB_STACK];
-	float stackT[RTB_STACK];
-	int sp = 0;
-	int32_t cur = S.fast_root;
-	h.id = RTB_MISS_ID, h.t = FLT_MAX, h.alpha = h.beta = 0.0f;
-	for (;;)
-	{
-		while (cur >= 0)
-		{
-			const float4* nd = S.fnodes + (size_t)cur * 4;
-			float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
-			float t0, t1;
-			nBox += 2;
-			bool h0 = slabTestNoNaN(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, r, t0);
-			bool h1 = slabTestNoNaN(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, r, t1);
-			h0 = h0 && !((t0 - fabsf(t0) * cullRel) > h.t);
-			h1 = h1 && !((t1 - fabsf(t1) * cullRel) > h.t);
-			int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
-			if (h0 && h1)
-			{
-				bool swap = t1 < t0;
-				stackNode[sp] = swap ? c0 : c1;
-				stackT[sp] = swap ? t0 : t1;
-				sp++;
-				cur = swap ? c1 : c0;
-				continue;
-			}
-			if (h0)
-			{
-				cur = c0;
-				continue;
-			}
-			if (h1)
-			{
-				cur = c1;
-				continue;
-			}
-			// pop
-			cur = RTB_TRAV_DONE_;
-			while (sp > 0)
-			{
-				sp--;
-				float te = stackT[sp];
-				if ((te - fabsf(te) * cullRel) > h.t) continue;
-				cur = stackNode[sp];
-				break;
-			}
-			if (cur == RTB_TRAV_DONE_) return;
-		}
-		// leaf (<= 2 triangles; the box that admitted it was its exact leaf box)
-		leafClosest(S, cur, r, eps, h, nTri);
-		cur = RTB_TRAV_DONE_;
-		while (sp > 0)
-		{
-			sp--;
-			float te = stackT[sp];
-			if ((te - fabsf(te) * cullRel) > h.t) continue;
-			cur = stackNode[sp];
-			break;
-		}
-		if (cur == RTB_TRAV_DONE_) return;
-	}
-}
-
-RTB_DEV bool visibleFastBody(const DevScene& S, const RayD& r, float eps, float maxT, float cullRel, uint32_t& nBox,
-                             uint32_t& nTri)
-{
-	int32_t stackNode[RTB_STACK];
-	int sp = 0;
-	int32_t cur = S.fast_root;
-	for (;;)
-	{
-		while (cur >= 0)
-		{
-			const float4* nd = S.fnodes + (size_t)cur * 4;
-			float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
-			float t0, t1;
-			nBox += 2;
-			bool h0 = slabTestNoNaN(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, r, t0);
-			bool h1 = slabTestNoNaN(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, r, t1);
-			h0 = h0 && !((t0 - fabsf(t0) * cullRel) >= maxT);
-			h1 = h1 && !((t1 - fabsf(t1) * cullRel) >= maxT);
-			int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
-			if (h0 && h1)
-			{
-				stackNode[sp++] = c1;
-				cur = c0;
-				continue;
-			}
-			if (h0)
-			{
-				cur = c0;
-				continue;
-			}
-			if (h1)
-			{
-				cur = c1;
-				continue;
-			}
-			if (sp == 0) return true;
-			cur = stackNode[--sp];
-		}
-		if (leafOccludes(S, cur, r, eps, maxT, nTri)) return false;
-		if (sp == 0) return true;
-		cur = stackNode[--sp];
-	}
-}
-
-// ---------------------------------------------------------------------------------------
 // Persistent traversal kernels.  profiles/r01_v3_wavefront_dynjobs_summary.txt: one thread per
 // ray keeps 8.7 of 32 lanes busy (a warp lasts as long as its longest ray).  Here every warp
 // owns a contiguous range of slots and keeps all lanes fed: each lane holds its CURRENT ray and
@@ -313,73 +184,13 @@ RTB_DEV bool visibleFastBody(const DevScene& S, const RayD& r, float eps, float 
 #define WF_CHUNK 128u
 #define WF_CHUNK_SHADOW 64u
 
-template <bool ANYHIT>
-struct LaneTrav
-{
-	RayD r;
-	float bestT; // closest: best t so far; any-hit: maxT
-	uint32_t bestId;
-	float bestU, bestV;
-	int32_t cur;
-	int sp;
-};
-
-template <bool ANYHIT>
-RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const int32_t* stackNode, const float* stackT, float cullRel)
-{
-	t.cur = RTB_TRAV_DONE_;
-	while (t.sp > 0)
-	{
-		t.sp--;
-		float te = stackT[t.sp];
-		bool cull = ANYHIT ? ((te - fabsf(te) * cullRel) >= t.bestT) : ((te - fabsf(te) * cullRel) > t.bestT);
-		if (cull) continue;
-		t.cur = stackNode[t.sp];
-		break;
-	}
-}
-
-template <bool ANYHIT>
-RTB_DEV void laneInterior(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel,
-                          uint32_t& nBox)
-{
-	const float4* nd = S.fnodes + (size_t)t.cur * 4;
-	float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
-	float t0, t1;
-	nBox += 2;
-	bool h0 = slabTestNoNaN(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, t.r, t0);
-	bool h1 = slabTestNoNaN(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, t.r, t1);
-	if (ANYHIT)
-	{
-		h0 = h0 && !((t0 - fabsf(t0) * cullRel) >= t.bestT);
-		h1 = h1 && !((t1 - fabsf(t1) * cullRel) >= t.bestT);
-	}
-	else
-	{
-		h0 = h0 && !((t0 - fabsf(t0) * cullRel) > t.bestT);
-		h1 = h1 && !((t1 - fabsf(t1) * cullRel) > t.bestT);
-	}
-	int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
-	if (h0 && h1)
-	{
-		bool swap = !ANYHIT && (t1 < t0);
-		stackNode[t.sp] = swap ? c0 : c1;
-		stackT[t.sp] = swap ? t0 : t1;
-		t.sp++;
-		t.cur = swap ? c1 : c0;
-	}
-	else if (h0) t.cur = c0;
-	else if (h1) t.cur = c1;
-	else lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
-}
-
 template <int TRAV>
 __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
 	const rtb_params& P = A.P;
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
 	Tally tl = {0, 0, 0, 0, 0, 0, 0};
-	if (TRAV == RTB_TRAV_EXACT || S.fast_root < 0)
+	if (TRAV == RTB_TRAV_EXACT || travRoot<TRAV>(S) < 0)
 	{
 		// parity path: the reference's own tree, one thread per slot
 		for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.nSlots; slot += gridDim.x * blockDim.x)
@@ -432,7 +243,7 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 					have = false;
 				}
 				else
-					t.cur = S.fast_root;
+					t.cur = travRoot<TRAV>(S);
 			}
 		}
 		// ---- issue the next prefetches from the warp's chunk
@@ -474,7 +285,7 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 			unsigned mL = __ballot_sync(0xFFFFFFFFu, have && t.cur < 0);
 			if (__popc(mI) >= __popc(mL))
 			{
-				if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) laneInterior<false>(S, t, stackNode, stackT, P.cull_rel, tl.box);
+				if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stackNode, stackT, P.cull_rel, tl.box);
 			}
 			else if (have && t.cur < 0)
 			{
@@ -514,8 +325,7 @@ __global__ void __launch_bounds__(128) k_wf_extend_simple(const __grid_constant_
 		RayD r = mkRay(mk(o), mk(d));
 		HitD h;
 		tl.closest++;
-		if (TRAV == RTB_TRAV_EXACT || rayIsDegenerate(r) || S.fast_root < 0) closestExact(S, r, P.epsilon, h, tl.box, tl.tri);
-		else closestFastBody(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+		closestHit<TRAV>(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
 		A.hit[slot] = make_float4(__uint_as_float(h.id), h.t, h.alpha, h.beta);
 	}
 	flushTally(tl, A.counters);
@@ -536,9 +346,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevSc
 		RayD r = mkRay(mk(o), mk(d));
 		float maxT = o.w;
 		tl.shadow++;
-		bool vis;
-		if (TRAV == RTB_TRAV_EXACT || rayIsDegenerate(r) || S.fast_root < 0) vis = visibleExact(S, r, P.epsilon, maxT, tl.sbox, tl.stri);
-		else vis = visibleFastBody(S, r, P.epsilon, maxT, P.cull_rel, tl.sbox, tl.stri);
+		bool vis = anyVisible<TRAV>(S, r, P.epsilon, maxT, P.cull_rel, tl.sbox, tl.stri);
 		if (vis) filmAdd(A.accum, __float_as_uint(d.w), mk(A.shC[i]));
 	}
 	flushTally(tl, A.counters);

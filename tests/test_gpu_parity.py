@@ -16,7 +16,7 @@ from raytracingrenderer_b200 import abi
 pytestmark = pytest.mark.gpu
 
 FP = json.load(open(os.path.join(GOLDEN, "fingerprints.json")))
-TRAVS = [abi.TRAV_EXACT, abi.TRAV_FAST]
+TRAVS = [abi.TRAV_EXACT, abi.TRAV_FAST, abi.TRAV_WIDE]
 
 
 def sha16(a):
@@ -249,10 +249,11 @@ def test_exact_and_fast_render_identical_films(rtb):
         rt.set_params(traversal=abi.TRAV_EXACT)
         rt.render(4, 0)
         a = rt.read_film().copy()
-        rt.set_params(traversal=abi.TRAV_FAST)
-        rt.clear()
-        rt.render(4, 0)
-        assert rt.read_film().tobytes() == a.tobytes()
+        for trav in (abi.TRAV_FAST, abi.TRAV_WIDE):
+            rt.set_params(traversal=trav)
+            rt.clear()
+            rt.render(4, 0)
+            assert rt.read_film().tobytes() == a.tobytes(), trav
 
 
 def test_megakernel_and_wavefront_schedules_agree(rtb):
