@@ -242,6 +242,7 @@ template <bool ANYHIT>
 struct LaneTrav
 {
 	RayD r;
+	float cullT; // cull threshold derived from bestT (travSetBest)
 	float bestT;
 	uint32_t bestId;
 	float bestU, bestV;
@@ -249,12 +250,21 @@ struct LaneTrav
 	int sp;
 };
 
+// Culling: a box entered beyond the best hit cannot matter, but t_entry (slab
+// arithmetic) and the triangle's t (plane arithmetic) are rounded differently, so the comparison
+// needs slack: a subtree is dropped only if t_entry > bestT * (1 + 2 rel) (closest hit) or
+// t_entry >= maxT * (1 + 2 rel) (any hit, where t < maxT is required).  The threshold is kept in
+// a register and refreshed when bestT changes: one compare per box.
 template <bool ANYHIT>
-RTB_DEV bool travCull(float te, float lim, float cullRel)
+RTB_DEV void travSetBest(LaneTrav<ANYHIT>& t, float best, float cullRel)
 {
-	// closest: drop if entered beyond the best hit; any-hit: at or beyond maxT (t < maxT is needed)
-	float lo = te - fabsf(te) * cullRel;
-	return ANYHIT ? (lo >= lim) : (lo > lim);
+	t.bestT = best;
+	t.cullT = best + fabsf(best) * (2.0f * cullRel);
+}
+template <bool ANYHIT>
+RTB_DEV bool travCull(float te, float cullT)
+{
+	return ANYHIT ? (te >= cullT) : (te > cullT);
 }
 
 template <bool ANYHIT>
@@ -264,7 +274,7 @@ RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const int32_t* stackNode, const float*
 	while (t.sp > 0)
 	{
 		t.sp--;
-		if (travCull<ANYHIT>(stackT[t.sp], t.bestT, cullRel)) continue;
+		if (travCull<ANYHIT>(stackT[t.sp], t.cullT)) continue;
 		t.cur = stackNode[t.sp];
 		break;
 	}
@@ -280,8 +290,8 @@ RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode
 	nBox += 2;
 	bool h0 = slabTestNoNaN(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, t.r, t0);
 	bool h1 = slabTestNoNaN(n1.x, n1.z, nz.z, n1.y, n1.w, nz.w, t.r, t1);
-	h0 = h0 && !travCull<ANYHIT>(t0, t.bestT, cullRel);
-	h1 = h1 && !travCull<ANYHIT>(t1, t.bestT, cullRel);
+	h0 = h0 && !travCull<ANYHIT>(t0, t.cullT);
+	h1 = h1 && !travCull<ANYHIT>(t1, t.cullT);
 	int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
 	if (h0 && h1)
 	{
@@ -320,10 +330,10 @@ RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode
 	bool h2 = slabTestNoNaN(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, t.r, e2) && c2 != RTB_WIDE_EMPTY;
 	bool h3 = slabTestNoNaN(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, t.r, e3) && c3 != RTB_WIDE_EMPTY;
 	nBox += 2u + (c2 != RTB_WIDE_EMPTY) + (c3 != RTB_WIDE_EMPTY);
-	h0 = h0 && !travCull<ANYHIT>(e0, t.bestT, cullRel);
-	h1 = h1 && !travCull<ANYHIT>(e1, t.bestT, cullRel);
-	h2 = h2 && !travCull<ANYHIT>(e2, t.bestT, cullRel);
-	h3 = h3 && !travCull<ANYHIT>(e3, t.bestT, cullRel);
+	h0 = h0 && !travCull<ANYHIT>(e0, t.cullT);
+	h1 = h1 && !travCull<ANYHIT>(e1, t.cullT);
+	h2 = h2 && !travCull<ANYHIT>(e2, t.cullT);
+	h3 = h3 && !travCull<ANYHIT>(e3, t.cullT);
 	if (ANYHIT)
 	{
 		// order is irrelevant for the result; push every admitted child, continue with the last
@@ -394,7 +404,8 @@ RTB_DEV void closestAccel(const DevScene& S, const RayD& r, float eps, float cul
 	float stackT[RTB_STACK];
 	LaneTrav<false> t;
 	t.r = r;
-	t.bestT = FLT_MAX, t.bestId = RTB_MISS_ID, t.bestU = t.bestV = 0.0f;
+	travSetBest<false>(t, FLT_MAX, cullRel);
+	t.bestId = RTB_MISS_ID, t.bestU = t.bestV = 0.0f;
 	t.sp = 0;
 	t.cur = travRoot<TRAV>(S);
 	for (;;)
@@ -404,7 +415,8 @@ RTB_DEV void closestAccel(const DevScene& S, const RayD& r, float eps, float cul
 		HitD b;
 		b.id = t.bestId, b.t = t.bestT, b.alpha = t.bestU, b.beta = t.bestV;
 		leafClosest(S, t.cur, t.r, eps, b, nTri);
-		t.bestId = b.id, t.bestT = b.t, t.bestU = b.alpha, t.bestV = b.beta;
+		t.bestId = b.id, t.bestU = b.alpha, t.bestV = b.beta;
+		travSetBest<false>(t, b.t, cullRel);
 		lanePop<false>(t, stackNode, stackT, cullRel);
 	}
 	h.id = t.bestId, h.t = t.bestT, h.alpha = t.bestU, h.beta = t.bestV;
@@ -419,7 +431,7 @@ RTB_DEV bool visibleAccel(const DevScene& S, const RayD& r, float eps, float max
 	float stackT[RTB_STACK];
 	LaneTrav<true> t;
 	t.r = r;
-	t.bestT = maxT;
+	travSetBest<true>(t, maxT, cullRel);
 	t.sp = 0;
 	t.cur = travRoot<TRAV>(S);
 	for (;;)

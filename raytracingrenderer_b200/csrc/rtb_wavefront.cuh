@@ -26,6 +26,9 @@
 #include "rtb_kernels.cuh"
 
 // resident 128-thread blocks per SM the stage kernels are compiled for (register budget)
+#ifndef WF_VOTE
+#define WF_VOTE 1
+#endif
 #ifndef WF_SHADE_MIN_BLOCKS
 #define WF_SHADE_MIN_BLOCKS 6
 #endif
@@ -229,7 +232,8 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 			if (__float_as_uint(preD.w) & WF_ALIVE)
 			{
 				t.r = mkRay(mk(preO), mk(preD));
-				t.bestT = FLT_MAX, t.bestId = RTB_MISS_ID, t.bestU = t.bestV = 0.0f;
+				travSetBest<false>(t, FLT_MAX, P.cull_rel);
+				t.bestId = RTB_MISS_ID, t.bestU = t.bestV = 0.0f;
 				t.sp = 0;
 				slot = preSlot;
 				have = true;
@@ -281,9 +285,16 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 		// ---- traverse until enough lanes are idle to make a refill worthwhile
 		for (;;)
 		{
+#if WF_VOTE
+			// majority vote: the step kind (interior / leaf) that more lanes wait for runs next
 			unsigned mI = __ballot_sync(0xFFFFFFFFu, have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_);
 			unsigned mL = __ballot_sync(0xFFFFFFFFu, have && t.cur < 0);
-			if (__popc(mI) >= __popc(mL))
+			bool doInterior = __popc(mI) >= __popc(mL);
+#else
+			// while-while: interior steps until no lane has an interior node, then the leaves
+			bool doInterior = __any_sync(0xFFFFFFFFu, have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_);
+#endif
+			if (doInterior)
 			{
 				if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stackNode, stackT, P.cull_rel, tl.box);
 			}
@@ -292,7 +303,8 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 				HitD h;
 				h.id = t.bestId, h.t = t.bestT, h.alpha = t.bestU, h.beta = t.bestV;
 				leafClosest(S, t.cur, t.r, P.epsilon, h, tl.tri);
-				t.bestId = h.id, t.bestT = h.t, t.bestU = h.alpha, t.bestV = h.beta;
+				t.bestId = h.id, t.bestU = h.alpha, t.bestV = h.beta;
+				travSetBest<false>(t, h.t, P.cull_rel);
 				lanePop<false>(t, stackNode, stackT, P.cull_rel);
 			}
 			if (have && t.cur == RTB_TRAV_DONE_)
