@@ -183,9 +183,12 @@ __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScen
 // scheduled by majority vote so that at least half of the busy lanes take part in every step.
 // The per-ray decisions are those of closestFastBody / visibleFastBody.
 // ---------------------------------------------------------------------------------------
-#define WF_REFILL_IDLE 6 /* refill once this many lanes are idle */
-#define WF_CHUNK 128u
-#define WF_CHUNK_SHADOW 64u
+#ifndef WF_REFILL_IDLE
+#define WF_REFILL_IDLE 12 /* refill once this many lanes are idle (6..16 measured within 4 %) */
+#endif
+#ifndef WF_CHUNK
+#define WF_CHUNK 128u /* slots a warp claims per atomic */
+#endif
 
 template <int TRAV>
 __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
