@@ -50,7 +50,7 @@ def build_host(force=False):
     if not force and os.path.isfile(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
         return HOST_LIB
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-Wall",
-                           os.path.join(hdir, "rtb_host.cpp"), "-o", HOST_LIB, "-lz"])
+                           os.path.join(hdir, "rtb_host.cpp"), "-o", HOST_LIB, "-lz", "-lpthread"])
     return HOST_LIB
 
 

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace rtb_accel
@@ -153,9 +154,14 @@ public:
 			return;
 		}
 		out.nodes.reserve((size_t)(n - 1) * 4);
-		tree = &out;
+		unsigned hw = std::thread::hardware_concurrency();
+		int par = 0; // top levels of the recursion that build the two halves concurrently
+		while ((1u << par) < hw && par < 5) par++;
+		if (n < 100000) par = 0;
 		Box b;
-		out.root = recurse(0, n, 0, b);
+		uint32_t depthSeen = 0;
+		out.root = recurse(out.nodes, 0, n, 0, b, par, depthSeen);
+		out.maxDepth = depthSeen;
 	}
 
 private:
@@ -164,14 +170,30 @@ private:
 	const std::vector<RefLeaf>& L;
 	std::vector<uint32_t> idx;
 	std::vector<float> cen;
-	FastTree* tree = nullptr;
 
 	int32_t leafRef(uint32_t prim) const { return ~(int32_t)((L[prim].start << 2) | L[prim].count); }
 
-	// returns the child reference and the exact box of the subtree (= union of leaf boxes)
-	int32_t recurse(uint32_t lo, uint32_t hi, uint32_t depth, Box& box)
+	static void writeNode(F4* nd, const Box& b0, const Box& b1, int32_t c0, int32_t c1)
 	{
-		if (depth > tree->maxDepth) tree->maxDepth = depth;
+		nd[0] = {b0.mn[0], b0.mx[0], b0.mn[1], b0.mx[1]};
+		nd[1] = {b1.mn[0], b1.mx[0], b1.mn[1], b1.mx[1]};
+		nd[2] = {b0.mn[2], b0.mx[2], b1.mn[2], b1.mx[2]};
+		nd[3] = {bitsToFloat((uint32_t)c0), bitsToFloat((uint32_t)c1), 0.0f, 0.0f};
+	}
+	static uint32_t floatBits(float f)
+	{
+		uint32_t u;
+		memcpy(&u, &f, 4);
+		return u;
+	}
+
+	// Builds the subtree of idx[lo, hi) into `nodes` (indices relative to that vector); returns the
+	// child reference and the exact box of the subtree (= union of leaf boxes).  With par > 0 the
+	// two halves are built concurrently into private vectors (disjoint slices of idx) and spliced
+	// in afterwards: the tree does not depend on the thread count.
+	int32_t recurse(std::vector<F4>& nodes, uint32_t lo, uint32_t hi, uint32_t depth, Box& box, int par, uint32_t& depthSeen)
+	{
+		if (depth > depthSeen) depthSeen = depth;
 		uint32_t n = hi - lo;
 		box.reset();
 		if (n == 1)
@@ -180,16 +202,40 @@ private:
 			return leafRef(idx[lo]);
 		}
 		uint32_t mid = split(lo, hi, depth);
-		size_t self = tree->nodes.size() / 4;
-		tree->nodes.resize(tree->nodes.size() + 4);
+		size_t self = nodes.size() / 4;
+		nodes.resize(nodes.size() + 4);
 		Box b0, b1;
-		int32_t c0 = recurse(lo, mid, depth + 1, b0);
-		int32_t c1 = recurse(mid, hi, depth + 1, b1);
-		F4* nd = &tree->nodes[self * 4];
-		nd[0] = {b0.mn[0], b0.mx[0], b0.mn[1], b0.mx[1]};
-		nd[1] = {b1.mn[0], b1.mx[0], b1.mn[1], b1.mx[1]};
-		nd[2] = {b0.mn[2], b0.mx[2], b1.mn[2], b1.mx[2]};
-		nd[3] = {bitsToFloat((uint32_t)c0), bitsToFloat((uint32_t)c1), 0.0f, 0.0f};
+		int32_t c0, c1;
+		if (par > 0 && n > 50000)
+		{
+			std::vector<F4> left, right;
+			uint32_t dl = 0, dr = 0;
+			std::thread th([&]() { c0 = recurse(left, lo, mid, depth + 1, b0, par - 1, dl); });
+			c1 = recurse(right, mid, hi, depth + 1, b1, par - 1, dr);
+			th.join();
+			if (dl > depthSeen) depthSeen = dl;
+			if (dr > depthSeen) depthSeen = dr;
+			auto splice = [&](std::vector<F4>& sub, int32_t& ref) {
+				int32_t off = (int32_t)(nodes.size() / 4);
+				for (size_t i = 0; i < sub.size(); i += 4)
+				{
+					int32_t a = (int32_t)floatBits(sub[i + 3].x), b = (int32_t)floatBits(sub[i + 3].y);
+					if (a >= 0) sub[i + 3].x = bitsToFloat((uint32_t)(a + off));
+					if (b >= 0) sub[i + 3].y = bitsToFloat((uint32_t)(b + off));
+				}
+				if (ref >= 0) ref += off;
+				nodes.insert(nodes.end(), sub.begin(), sub.end());
+				std::vector<F4>().swap(sub);
+			};
+			splice(left, c0);
+			splice(right, c1);
+		}
+		else
+		{
+			c0 = recurse(nodes, lo, mid, depth + 1, b0, 0, depthSeen);
+			c1 = recurse(nodes, mid, hi, depth + 1, b1, 0, depthSeen);
+		}
+		writeNode(&nodes[self * 4], b0, b1, c0, c1);
 		box.grow(b0);
 		box.grow(b1);
 		return (int32_t)self;

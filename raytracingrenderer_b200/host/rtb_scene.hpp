@@ -32,6 +32,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #include <zlib.h>
 
@@ -546,7 +547,13 @@ public:
 			b.extend(inputTriangles[i].vertices[2].p);
 			w.bmin[i] = b.min, w.bmax[i] = b.max;
 		}
-		buildRecursive(w, 0, (int)n);
+		unsigned hw = std::thread::hardware_concurrency();
+		int par = 0; // levels of the recursion that fork a thread for the left subtree
+		while ((1u << par) < hw && par < 5) par++;
+		if (n < 200000) par = 0;
+		if (const char* e = getenv("RTB_HOST_BUILD_SERIAL"))
+			if (atoi(e) != 0) par = 0;
+		buildRecursive(w, 0, (int)n, par);
 		std::vector<Triangle> sorted(n);
 		for (size_t i = 0; i < n; i++) sorted[i] = inputTriangles[w.order[i]];
 		outputTriangles.swap(sorted);
@@ -559,14 +566,15 @@ private:
 		std::vector<uint32_t> order;
 		std::vector<float> cx, cy, cz;
 		std::vector<Vec3> bmin, bmax;
-		std::vector<AABB> left, right; // scratch of the SAH sweep
 	};
 	struct Key
 	{
 		float k;
 		uint32_t id;
 	};
-	void buildRecursive(Work& w, int start, int end)
+	// Sub-ranges are independent (disjoint slices of `order`, read-only keys and boxes), so the two
+	// recursive calls may run concurrently without changing any decision.
+	void buildRecursive(Work& w, int start, int end, int par)
 	{
 		bounds.reset();
 		for (int i = start; i < end; i++)
@@ -591,30 +599,30 @@ private:
 		for (int i = 0; i < numTri; i++) keys[i] = {key[w.order[start + i]], w.order[start + i]};
 		std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.k < b.k; });
 		for (int i = 0; i < numTri; i++) w.order[start + i] = keys[i].id;
-		if ((int)w.left.size() < numTri) w.left.resize(numTri), w.right.resize(numTri);
+		std::vector<AABB> left((size_t)numTri), right((size_t)numTri); // prefix / suffix boxes of the SAH sweep
 		auto triBox = [&](int i) {
 			AABB b;
 			b.min = w.bmin[w.order[start + i]], b.max = w.bmax[w.order[start + i]];
 			return b;
 		};
-		w.left[0] = triBox(0);
-		w.right[numTri - 1] = triBox(numTri - 1);
+		left[0] = triBox(0);
+		right[numTri - 1] = triBox(numTri - 1);
 		for (int i = 1; i < numTri; i++)
 		{
-			w.left[i] = w.left[i - 1];
-			w.left[i].extend(triBox(i));
+			left[i] = left[i - 1];
+			left[i].extend(triBox(i));
 		}
 		for (int i = numTri - 2; i >= 0; i--)
 		{
-			w.right[i] = w.right[i + 1];
-			w.right[i].extend(triBox(i));
+			right[i] = right[i + 1];
+			right[i].extend(triBox(i));
 		}
 		float cost_min = FLT_MAX;
 		int split_index = 0;
 		for (int i = 1; i < numTri; i++)
 		{
 			float num_left = (float)i, num_right = (float)(numTri - i);
-			float cost = w.left[i - 1].area() * num_left + w.right[i].area() * num_right;
+			float cost = left[i - 1].area() * num_left + right[i].area() * num_right;
 			if (cost < cost_min)
 			{
 				cost_min = cost;
@@ -624,8 +632,24 @@ private:
 		int mid = start + split_index;
 		l = new BVHNode();
 		r = new BVHNode();
-		l->buildRecursive(w, start, mid);
-		r->buildRecursive(w, mid, end);
+		{
+			// release the sweep scratch before descending
+			std::vector<AABB>().swap(left);
+			std::vector<AABB>().swap(right);
+			std::vector<Key>().swap(keys);
+		}
+		if (par > 0 && numTri > 50000)
+		{
+			BVHNode* lp = l;
+			std::thread th([&w, lp, start, mid, par]() { lp->buildRecursive(w, start, mid, par - 1); });
+			r->buildRecursive(w, mid, end, par - 1);
+			th.join();
+		}
+		else
+		{
+			l->buildRecursive(w, start, mid, 0);
+			r->buildRecursive(w, mid, end, 0);
+		}
 	}
 };
 

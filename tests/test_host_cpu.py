@@ -60,3 +60,12 @@ def test_camera_matches_the_reference_flattened_camera(host):
     cam = host.camera(v("from"), v("to"), v("up"), float(sj["fov"]), int(sj["width"]), int(sj["height"]))
     want = rs.flatten("/tmp/_cam.rtbs").camera
     assert cam.tobytes() == want.tobytes()
+
+
+def test_parallel_build_equals_serial_build(host, tmp_path, monkeypatch):
+    """The reference-order builder forks threads for disjoint sub-ranges above 200 k triangles; the
+    tree and triangle order must not depend on that."""
+    a, _ = host.build_soup(1 << 18, 64, 36)
+    monkeypatch.setenv("RTB_HOST_BUILD_SERIAL", "1")
+    b, _ = host.build_soup(1 << 18, 64, 36)
+    assert a.ref_nodes.tobytes() == b.ref_nodes.tobytes() and a.tri_isect.tobytes() == b.tri_isect.tobytes()
