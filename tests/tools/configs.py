@@ -1,0 +1,54 @@
+"""All BASELINE.json configs on one B200 + the reference CPU renderer beside them (run under gpurun).
+Writes gpurun_out/configs.json.  Test tool: uses the oracle for the CPU numbers and for bathroom
+(its JPEG textures are not decoded by the product loader yet)."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import raytracingrenderer_b200 as rtb
+from raytracingrenderer_b200 import abi, host_api
+from oracle import ref
+
+def gpu_run(flat, spp, max_depth=4, repeats=2):
+    rt = rtb.RayTracer(0)
+    t0 = time.time(); rt.init(flat); up = time.time() - t0
+    rt.set_params(max_depth=max_depth)
+    rt.render(min(spp, 8), 0); rt.synchronize()
+    best = None
+    for _ in range(repeats):
+        rt.clear(); t0 = time.time(); rt.render(spp, 0); rt.synchronize(); dt = time.time() - t0
+        st = rt.stats()
+        if best is None or dt < best[0]:
+            best = (dt, st)
+    dt, st = best
+    film = rt.read_film() / spp
+    rays = st["closest_rays"] + st["shadow_rays"]
+    out = dict(spp=spp, seconds=dt, upload_s=up, msamples_s=st["samples"] / dt / 1e6, mrays_s=rays / dt / 1e6,
+               rays_per_sample=rays / st["samples"], box_per_ray=(st["box_tests"] + st["shadow_box_tests"]) / rays,
+               tri_per_ray=(st["tri_tests"] + st["shadow_tri_tests"]) / rays, mean=film.mean(axis=(0, 1)).tolist(),
+               iterations=st["iterations"], host_syncs=st["host_syncs"])
+    rt.close()
+    return out, film
+
+res = {}
+cfgs = [("cornell-box", 64), ("materialball", 256), ("MaterialsScene", 512), ("MaterialsScene_env", 512), ("coffee", 1024), ("bathroom", 1024)]
+for name, spp in cfgs:
+    rs = ref.RefScene(name)
+    flat = rs.flatten("/tmp/cfg_%s.rtbs" % name) if name == "bathroom" else host_api.load_scene(ref.scene_dir(name))
+    g, film = gpu_run(flat, spp)
+    rspp = 2 if name == "bathroom" else 4
+    rs.render(1, 0, fresh=True)
+    rf, n, secs = rs.render(rspp, 0, fresh=True)
+    g["ref_cpu"] = dict(spp=rspp, seconds=secs, msamples_s=rs.width * rs.height * rspp / secs / 1e6, threads=rs.hw_threads,
+                        mean=(rf / rspp).mean(axis=(0, 1)).tolist())
+    g["speedup"] = g["msamples_s"] / g["ref_cpu"]["msamples_s"]
+    g["tris"] = rs.n_tris; g["res"] = [rs.width, rs.height]
+    res[name] = g
+    print(name, json.dumps(g), flush=True)
+for lg in (20, 22):
+    t0 = time.time(); flat, bsecs = host_api.build_soup(1 << lg, 3840, 2160); t1 = time.time()
+    g, film = gpu_run(flat, 4, max_depth=0, repeats=2)
+    g["host_ref_order_build_s"] = bsecs; g["tris"] = flat.n_tris; g["res"] = [3840, 2160]
+    res["soup2^%d" % lg] = g
+    print("soup", lg, json.dumps(g), flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/configs.json", "w"), indent=1)
