@@ -483,3 +483,73 @@ def test_soup_config_primary_plus_one_bounce(rtb, oracle_mod):
     assert g["closest_rays"] <= 2 * g["samples"] and g["shadow_rays"] <= 2 * g["samples"]
     assert abs(g["closest_rays"] / st["closest_rays"] - 1) < 2e-3
     rt.close()
+
+
+# ------------------------------------------------------------------ edge cases
+def _tiny_scene(n_tris, width, height, background=(0.25, 0.5, 1.0)):
+    """0, 1 or a few triangles in front of the camera, constant background light, odd film size."""
+    import refbvh
+    F = np.float32
+    mats, texs, texels = refbvh.standard_materials()
+    v0 = np.array([[-1, -1, 0], [0.2, -0.8, 0.5], [-0.9, 0.1, -0.4]], F)[:n_tris]
+    v1 = np.array([[1, -1, 0], [0.9, -0.7, 0.6], [-0.2, 0.2, -0.5]], F)[:n_tris]
+    v2 = np.array([[0, 1, 0], [0.5, 0.4, 0.4], [-0.6, 0.9, -0.3]], F)[:n_tris]
+    nrm = np.tile(np.array([[0, 0, 1]], F), (n_tris, 1))
+    uv = np.zeros((n_tris, 3, 2), F)
+    ti, ts = refbvh._tri_records(v0, v1, v2, nrm, nrm, nrm, uv, np.zeros(n_tris, np.uint32))
+    cam = refbvh.look_at_camera([0.1, 0.2, 4.0], [0, 0, 0], [0, 1, 0], 45.0, width, height)
+    return refbvh.assemble(ti, ts, mats, texs, texels, cam, None, background)
+
+
+@pytest.mark.parametrize("n_tris", [0, 1, 3])
+@pytest.mark.parametrize("size", [(13, 7), (33, 5)])
+def test_degenerate_scenes_and_ragged_film_sizes(rtb, oracle_mod, n_tris, size):
+    """Empty scene, single-leaf scene (the root is a leaf), film sizes that are not multiples of the
+    8x4 pixel tiles, every traversal and both schedules."""
+    s = _tiny_scene(n_tris, *size)
+    rt = rtb.RayTracer(0)
+    rt.init(s)
+    o = oracle_mod.Oracle(s)
+    oid, ot = o.primary_hits()
+    want, st = o.render(3)
+    for trav in TRAVS:
+        ids, t = rt.primary_hits(trav)
+        assert np.array_equal(ids, oid) and t.tobytes() == ot.tobytes()
+        for sched in (abi.SCHED_WAVEFRONT, abi.SCHED_MEGAKERNEL):
+            rt.set_params(traversal=trav, scheduler=sched)
+            rt.clear()
+            rt.render(3, 0)
+            img = rt.read_film()
+            assert img.shape == (size[1], size[0], 3)
+            assert np.allclose(img, want, rtol=2e-4, atol=1e-5), (trav, sched)
+            assert rt.stats()["samples"] == size[0] * size[1] * 3
+    if n_tris == 0:
+        assert np.allclose(want / 3, np.array([0.25, 0.5, 1.0], np.float32))     # every ray sees the background
+    rt.close()
+
+
+def test_more_ranks_than_samples_and_late_sample_indices(rtb, oracle_mod):
+    """spp partition with world > spp (some ranks get nothing) and a render that resumes at a large
+    sample index: the RNG is keyed by the global sample index."""
+    rt = gpu_scene(rtb, "synthetic")
+    rt.render(2, 1000)
+    full = rt.read_film().copy()
+    want, _ = oracle_mod.Oracle(rt.scene).render(2, spp_begin=1000)
+    assert np.isclose(full, want, rtol=2e-4, atol=1e-5).all(axis=-1).mean() > 0.995
+    acc = np.zeros_like(full)
+    empty = 0
+    for r in range(5):
+        rt.set_params(partition=abi.PART_SPP, part_rank=r, part_world=5)
+        rt.clear()
+        rt.render(2, 1000)
+        part = rt.read_film()
+        empty += int(not part.any())
+        acc += part
+    assert empty == 3                                       # samples 1000, 1001 -> ranks 0 and 1
+    assert np.allclose(acc, full, rtol=1e-6, atol=1e-7)
+
+
+def test_every_mode_combination_runs(rtb):
+    """tests/tools/sanitize_case.py as a test: all traversals x integrators x schedules x partitions."""
+    import runpy
+    runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "sanitize_case.py"), run_name="__main__")
