@@ -39,12 +39,6 @@ namespace
 {
 thread_local std::string g_createError;
 
-struct DevBuf
-{
-	void* p = nullptr;
-	size_t bytes = 0;
-};
-
 struct EventPair
 {
 	cudaEvent_t a, b;
@@ -280,12 +274,6 @@ static int renderMegakernel(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count
 	CK(cudaGetLastError());
 	ctx->filmDirty = true;
 	return RTB_OK;
-}
-
-template <int INTEGRATOR>
-static void launchShade(rtb_ctx* ctx, const WfArgs& A, uint32_t iter, unsigned grid)
-{
-	k_wf_shade<INTEGRATOR><<<grid, 128, 0, ctx->stream>>>(ctx->S, A, iter);
 }
 
 // float film <- fixed-point sums (only when they changed)

@@ -35,10 +35,9 @@ struct DevScene
 	const rtb_texture* texs;
 	const float* texels;
 	const rtb_light* lights;
-	// env-map importance tables (RTB_SAMPLING_IMPORTANCE): see rtb_api.cu buildEnvTables
+	// env-map importance tables (RTB_SAMPLING_IMPORTANCE): rtb_accel.hpp buildEnvTables
 	const float* env_marginal; // [H+1] cdf over rows
 	const float* env_cond;     // [H*(W+1)] cdf over columns of each row
-	const float* env_pdf;      // [H*W] solid-angle pdf of the texel's centre direction
 	uint32_t n_xnodes, n_fnodes, n_tris, n_lights, n_mats, n_texs;
 	int32_t fast_root; // child reference of the FAST root (may itself be a leaf)
 	int32_t wide_root;
