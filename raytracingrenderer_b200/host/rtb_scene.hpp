@@ -14,9 +14,9 @@
 //     <= 2 triangles, longest axis with the same tie rule, std::sort by centroid (the same
 //     libstdc++ algorithm sees the same comparison results, so it produces the same permutation
 //     although only 8-byte keys move), full SAH sweep with a strict '<';
-//   * PNG (8-bit, non-interlaced) and Radiance .hdr decode to the values stb_image produces.
-//     JPEG is not decoded yet (bathroom needs it): loading such a texture is an error, never a
-//     silent default.
+//   * PNG (8-bit, non-interlaced), JPEG (host/rtb_jpeg.hpp: baseline + progressive) and Radiance
+//     .hdr decode to the values stb_image produces.  A file that exists but cannot be decoded is
+//     an error, never a silent default.
 // Build with -ffp-contract=off.
 #pragma once
 
@@ -35,6 +35,8 @@
 #include <thread>
 #include <vector>
 #include <zlib.h>
+
+#include "rtb_jpeg.hpp"
 
 #ifndef EPSILON
 #define EPSILON 1e-4f /* RTBase/Geometry.h:60 */
@@ -407,8 +409,9 @@ public:
 			return;
 		}
 		std::vector<unsigned char> px;
-		if (!rtb_img::decodePNG(file, width, height, channels, px))
-			throw std::runtime_error("cannot decode " + filename + " (only 8-bit non-interlaced PNG and Radiance .hdr so far)");
+		bool isJPEG = file.size() > 2 && file[0] == 0xFF && file[1] == 0xD8;
+		if (!(isJPEG ? rtb_img::decodeJPEG(file, width, height, channels, px) : rtb_img::decodePNG(file, width, height, channels, px)))
+			throw std::runtime_error("cannot decode " + filename + " (8-bit non-interlaced PNG, Huffman JPEG and Radiance .hdr are supported)");
 		if (channels < 3) throw std::runtime_error(filename + ": grey textures are read out of bounds by the reference (Imaging.h:60)");
 		texels = new Colour[(size_t)width * height];
 		for (size_t i = 0; i < (size_t)width * height; i++)

@@ -17,7 +17,8 @@ def host():
 
 
 @pytest.mark.parametrize("name", ["cornell-box", "MaterialsScene", "materialball", "coffee", "MaterialsScene_env",
-                                  "materialball_glass", "materialball_layered", "materialball_conductor"])
+                                  "materialball_glass", "materialball_layered", "materialball_conductor",
+                                  "bathroom"])   # bathroom: baseline + progressive JPEG textures
 def test_loader_and_builder_equal_the_reference(host, name, tmp_path):
     rs = ref_scene(name)
     want = rs.flatten(str(tmp_path / "ref.rtbs"))
@@ -31,10 +32,21 @@ def test_loader_and_builder_equal_the_reference(host, name, tmp_path):
     assert got.background_colour.tobytes() == want.background_colour.tobytes()
 
 
-def test_jpeg_textures_are_an_error_not_a_silent_default(host):
+def test_undecodable_textures_are_an_error_not_a_silent_default(host, tmp_path):
+    """A texture file that exists but cannot be decoded (here: a JPEG cut off inside its header)
+    must raise; only a MISSING file becomes the reference's 1x1 white default."""
+    import shutil
     rs = ref_scene("bathroom")
+    d = tmp_path / "scene"
+    shutil.copytree(rs.dir, d, symlinks=False)
+    jpgs = sorted(p for p in os.listdir(d) if p.lower().endswith((".jpg", ".jpeg")))
+    assert jpgs
+    victim = d / jpgs[0]
+    data = open(victim, "rb").read()
+    os.remove(victim)
+    open(victim, "wb").write(data[:64])
     with pytest.raises(RuntimeError) as e:
-        host.load_scene(rs.dir)
+        host.load_scene(str(d))
     assert "cannot decode" in str(e.value)
 
 

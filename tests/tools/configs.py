@@ -1,6 +1,6 @@
 """All BASELINE.json configs on one B200 + the reference CPU renderer beside them (run under gpurun).
-Writes gpurun_out/configs.json.  Test tool: uses the oracle for the CPU numbers and for bathroom
-(its JPEG textures are not decoded by the product loader yet)."""
+Writes gpurun_out/configs.json.  Test tool: uses the oracle for the CPU numbers; every scene is loaded
+by the product host loader."""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -33,7 +33,7 @@ res = {}
 cfgs = [("cornell-box", 64), ("materialball", 256), ("MaterialsScene", 512), ("MaterialsScene_env", 512), ("coffee", 1024), ("bathroom", 1024)]
 for name, spp in cfgs:
     rs = ref.RefScene(name)
-    flat = rs.flatten("/tmp/cfg_%s.rtbs" % name) if name == "bathroom" else host_api.load_scene(ref.scene_dir(name))
+    flat = host_api.load_scene(ref.scene_dir(name))
     g, film = gpu_run(flat, spp)
     rspp = 2 if name == "bathroom" else 4
     rs.render(1, 0, fresh=True)
