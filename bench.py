@@ -222,7 +222,10 @@ def run_ours(args, rank, world, local_rank):
         rt.set_stream(stream.cuda_stream)
         rt.init(s)
         depth = args.max_depth if args.max_depth is not None else (0 if args.scene.startswith("soup") else 4)
-        rt.set_params(traversal=abi.TRAV_FAST, max_depth=depth, **D.partition_params(rank, world, "spp"))
+        # headline: every sample traces its own camera ray (the rays the reference traces); the
+        # product default (one camera ray per pixel and render call) is timed separately below
+        rt.set_params(traversal=abi.TRAV_FAST, max_depth=depth, primary_reuse=args.primary_reuse,
+                      **D.partition_params(rank, world, "spp"))
         rts.append(rt)
     accs = [D.accum_tensor(rt) for rt in rts]      # int64 fixed-point film sums (exact reduction)
     host = [torch.empty(a.numel(), dtype=torch.float32).pin_memory() for a in accs] if rank == 0 else []
@@ -311,6 +314,29 @@ def run_ours(args, rank, world, local_rank):
     h2d = 160 * len(rts)
     d2h = sum(a.numel() * 4 for a in accs)
 
+    # ---- the same step with the primary-hit table (rtb_params.primary_reuse = 1, the library default)
+    reuse = None
+    if not args.primary_reuse:
+        for rt in rts:
+            rt.set_params(primary_reuse=1)
+        step_device()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.steps):
+            step_device()
+        r1.record()
+        barrier()
+        rms = torch.tensor([r0.elapsed_time(r1)], device="cuda")
+        if dist is not None:
+            dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+        rst = [rt.stats() for rt in rts]
+        reuse = {"value": samples_step * args.steps / (float(rms.item()) / 1e3) / 1e6, "unit": "Msamples/s",
+                 "ms_per_step": float(rms.item()) / args.steps,
+                 "rays_per_sample": sum(s["closest_rays"] + s["shadow_rays"] for s in rst) / max(sum(s["samples"] for s in rst), 1),
+                 "note": "rtb_params.primary_reuse=1 (library default): each pixel's camera ray is traced once per "
+                         "rtb_render call instead of once per sample; film bit-identical (tests/test_gpu_parity.py)"}
+
     if rank == 0:
         hbm, sm_max, how = measured_peaks()
         # Dominant kernel = the stage with the largest measured share.  Algorithmic bytes per
@@ -355,6 +381,9 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clk,
         }
+        line["config"]["primary_reuse"] = int(args.primary_reuse)
+        if reuse is not None:
+            line["with_primary_hit_table"] = reuse
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, log)
         print(json.dumps(line), flush=True)
@@ -374,6 +403,8 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--ref-spp", type=int, default=4, help="spp per scene per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--primary-reuse", type=int, default=0, choices=[0, 1],
+                    help="rtb_params.primary_reuse for the headline value / e2e (default 0: per-sample camera rays)")
     ap.add_argument("--max-depth", type=int, default=None, help="rtb_params.max_depth (default 4; soup scenes 0)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -216,7 +216,11 @@ typedef struct rtb_params {
 	int32_t part_rank, part_world;
 	float cull_rel;     /* FAST traversal: relative slack of the t-cull (1e-5)       */
 	int32_t scheduler;  /* rtb_scheduler                                             */
-	int32_t reserved_;
+	int32_t primary_reuse; /* wavefront: trace each pixel's camera ray once per rtb_render call and let
+	                        * every sample of the pixel start from that hit.  Exact: the reference samples
+	                        * pixel centres only (Renderer.h:806-807) and generateRay draws no random
+	                        * numbers, so all samples of a pixel share one primary ray.  0 = trace it per
+	                        * sample like the reference does; the film is bit-identical either way. */
 } rtb_params; /* 64 B */
 
 /* Ray / hit records of the batched parity entry points. */

@@ -83,7 +83,7 @@ class Params(C.Structure):
         ("sampling", C.c_int32), ("traversal", C.c_int32), ("filter", C.c_int32),
         ("filter_radius", C.c_float), ("filter_alpha", C.c_float), ("seed", C.c_uint32),
         ("partition", C.c_int32), ("part_rank", C.c_int32), ("part_world", C.c_int32),
-        ("cull_rel", C.c_float), ("scheduler", C.c_int32), ("reserved_", C.c_int32),
+        ("cull_rel", C.c_float), ("scheduler", C.c_int32), ("primary_reuse", C.c_int32),
     ]
 
 

@@ -83,6 +83,8 @@ struct rtb_ctx
 	uint32_t wfCtrlEntries = 0;
 	WfGlobal* wfGlobal = nullptr;
 	uint32_t* wfTiles = nullptr;
+	float4* wfPrimary = nullptr; // per-pixel primary hits (params.primary_reuse), rebuilt by every render call
+	int primaryPasses = 2; // profiles/r01_primary_reuse.txt
 	uint32_t wfTileCount = 0;
 	int wfTilePart[3] = {-1, -1, -1}; // partition, rank, world the tile list was built for
 	unsigned long long* hostProbe = nullptr; // pinned: {nextJob, alive}
@@ -137,10 +139,12 @@ void freeScene(rtb_ctx* ctx)
 	if (ctx->wfCtrl) cudaFree(ctx->wfCtrl);
 	if (ctx->wfGlobal) cudaFree(ctx->wfGlobal);
 	if (ctx->wfTiles) cudaFree(ctx->wfTiles);
+	if (ctx->wfPrimary) cudaFree(ctx->wfPrimary);
 	if (ctx->accum) cudaFree(ctx->accum);
 	ctx->wfState = nullptr, ctx->wfStateBytes = 0;
 	ctx->wfCtrl = nullptr, ctx->wfCtrlEntries = 0;
 	ctx->wfGlobal = nullptr, ctx->wfTiles = nullptr, ctx->wfTileCount = 0;
+	ctx->wfPrimary = nullptr;
 	ctx->wfTilePart[0] = ctx->wfTilePart[1] = ctx->wfTilePart[2] = -1;
 	ctx->accum = nullptr;
 	ctx->film = ctx->filmFiltered = nullptr;
@@ -391,8 +395,14 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[2], k_wf_extend<RTB_TRAV_WIDE>, 128, 0));
 		if (const char* e = getenv("RTB_SIMPLE_EXTEND")) ctx->simpleExtend = atoi(e) != 0;
+		if (const char* e = getenv("RTB_PRIMARY_PASSES"))
+		{
+			int v = atoi(e);
+			if (v >= 1 && v <= 64) ctx->primaryPasses = v;
+		}
 	}
 	int ti = P.traversal;
+	if (P.primary_reuse && !ctx->wfPrimary) CK(cudaMalloc((void**)&ctx->wfPrimary, (size_t)ctx->width * ctx->height * sizeof(float4)));
 	WfArgs A[RTB_MAX_POOLS];
 	float4* base = (float4*)ctx->wfState;
 	for (int k = 0; k < K; k++)
@@ -404,6 +414,8 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		a.ctrl = ctx->wfCtrl + (size_t)k * bound;
 		a.glob = ctx->wfGlobal;
 		a.tileList = ctx->wfTiles;
+		a.primary = P.primary_reuse ? ctx->wfPrimary : nullptr;
+		a.primaryPasses = (uint32_t)ctx->primaryPasses;
 		a.counters = ctx->counters;
 		a.accum = ctx->accum;
 		a.nSlots = perPool, a.nTiles = ctx->wfTileCount;
@@ -421,6 +433,15 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	bool shadows = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_DIRECT);
 	EventPair ev = {getEvent(ctx), getEvent(ctx)};
 	cudaEventRecord(ev.a, ctx->stream);
+	if (P.primary_reuse)
+	{
+		unsigned warps = ((ctx->width + 7) / 8) * ((ctx->height + 3) / 4);
+		unsigned grid = (warps + 3) / 4;
+		if (grid > maxBlocks) grid = maxBlocks;
+		RTB_TRAV_SWITCH(ti, k_wf_primary<TR><<<grid, 128, 0, ctx->stream>>>(ctx->S, ctx->wfPrimary, ctx->width, ctx->height, P.epsilon,
+		                                                                   P.cull_rel, ctx->counters));
+		ctx->launches++;
+	}
 	// fork
 	cudaEventRecord(ctx->evFork, ctx->stream);
 	for (int k = 0; k < K; k++)
@@ -562,6 +583,7 @@ void rtb_default_params(rtb_params* p)
 	p->part_world = 1;
 	p->cull_rel = 1e-5f;
 	p->scheduler = RTB_SCHED_WAVEFRONT;
+	p->primary_reuse = 1;
 }
 
 int rtb_create(int device, rtb_ctx** out)

@@ -36,6 +36,7 @@
 #define WF_EXTEND_MIN_BLOCKS 8
 #endif
 
+#define WF_PREHIT 0x400u /* hit[slot] already holds the vertex (primary-hit table): k_wf_extend skips the slot */
 #define WF_ALIVE 0x200u
 #define WF_CANHIT 0x100u
 #define WF_DEPTH_MASK 0xFFu
@@ -65,6 +66,8 @@ struct WfArgs
 	WfCtrl* ctrl;  // [iterations], zeroed before the render
 	WfGlobal* glob;
 	const uint32_t* tileList; // owned 8x4 tiles (row-major tile ids)
+	const float4* primary;    // per-pixel primary hit (bits(id), t, alpha, beta), or NULL: trace every camera ray
+	uint32_t primaryPasses;   // fresh primary vertices a shade thread may take on per launch
 	unsigned long long* counters;
 	long long* accum; // [width*height*3] fixed-point film sums
 	uint32_t nSlots, nTiles;
@@ -93,25 +96,44 @@ RTB_DEV bool wfJobPixel(const WfArgs& A, uint32_t q, uint32_t& px, uint32_t& py)
 	return px < A.width && py < A.height;
 }
 
-// Starts job j in `slot`; returns false (slot untouched) when j is a padding pixel of an edge tile.
-RTB_DEV bool wfStartJob(const DevScene& S, const WfArgs& A, uint32_t slot, unsigned long long j)
+// job j -> (sample ordinal n, pixel ordinal q); false when q is a padding pixel of an edge tile.
+RTB_DEV bool wfDecodeJob(const WfArgs& A, unsigned long long j, uint32_t& n, uint32_t& q)
 {
 	uint32_t Q = A.nTiles * 32u;
-	uint32_t n = (uint32_t)(j / Q), q = (uint32_t)(j % Q);
+	n = (uint32_t)(j / Q), q = (uint32_t)(j % Q);
 	uint32_t px, py;
-	if (!wfJobPixel(A, q, px, py)) return false;
+	return wfJobPixel(A, q, px, py);
+}
+
+// The first vertex of job (n, q) as slot state.  Every sample of a pixel has the SAME camera ray
+// (pixel centres only, Renderer.h:806-807, and generateRay draws no random numbers), so with a
+// primary-hit table the closest hit is looked up instead of traced.
+RTB_DEV void wfFirstVertex(const DevScene& S, const WfArgs& A, uint32_t n, uint32_t q, float4& ro, float4& rd, float4& hh, float4& tq)
+{
+	uint32_t px, py;
+	wfJobPixel(A, q, px, py);
 	RayD r = generateRay(S.cam, (float)px + 0.5f, (float)py + 0.5f);
-	A.rayO[slot] = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(q));
-	A.rayD[slot] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(WF_ALIVE | WF_CANHIT));
-	A.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(n));
-	return true;
+	ro = make_float4(r.o.x, r.o.y, r.o.z, __uint_as_float(q));
+	rd = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(WF_ALIVE | WF_CANHIT | (A.primary ? WF_PREHIT : 0u)));
+	tq = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(n));
+	if (A.primary) hh = __ldg(A.primary + (size_t)py * A.width + px);
+}
+
+RTB_DEV void wfWriteJob(const DevScene& S, const WfArgs& A, uint32_t slot, uint32_t n, uint32_t q)
+{
+	float4 ro, rd, hh, tq;
+	wfFirstVertex(S, A, n, q, ro, rd, hh, tq);
+	A.rayO[slot] = ro;
+	A.rayD[slot] = rd;
+	A.thr[slot] = tq;
+	if (A.primary) A.hit[slot] = hh;
 }
 
 // Warp-cooperative: every lane with `need` claims jobs until it holds a valid one or the render
-// has no jobs left.  One atomic per warp and round.  Returns true if the lane's slot is live.
-RTB_DEV bool wfClaimJob(const DevScene& S, const WfArgs& A, uint32_t slot, bool need)
+// has no jobs left.  One atomic per warp and round.  Returns true if the lane got a job (n, q).
+RTB_DEV bool wfClaimJob(const WfArgs& A, bool need, uint32_t& n, uint32_t& q)
 {
-	bool live = false;
+	bool got = false;
 	for (;;)
 	{
 		unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
@@ -126,52 +148,51 @@ RTB_DEV bool wfClaimJob(const DevScene& S, const WfArgs& A, uint32_t slot, bool 
 			unsigned long long j = base + __popc(mask & ((1u << (threadIdx.x & 31u)) - 1u));
 			if (j < A.totalJobs)
 			{
-				if (wfStartJob(S, A, slot, j))
+				if (wfDecodeJob(A, j, n, q))
 				{
 					need = false;
-					live = true;
+					got = true;
 				}
 			}
 			else
 				need = false;
 		}
 	}
-	return live;
+	return got;
 }
 
 
-// One global atomic per BLOCK: every thread asks for `want` (0 or 1) consecutive items of the
-// counter; returns the thread's item index.  All threads of the block must call it.
-template <class CounterT>
-RTB_DEV CounterT blockReserve(CounterT* counter, bool want, CounterT* sBase, uint32_t* sWarpCount)
+// The primary-hit table: Scene::traverse of the ONE camera ray of every pixel (8x4 pixels per warp),
+// computed at the start of each render call when params.primary_reuse is set.
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_wf_primary(const __grid_constant__ DevScene S, float4* table, uint32_t width, uint32_t height,
+                                                    float epsilon, float cullRel, unsigned long long* counters)
 {
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-	unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
-	if (lane == 0) sWarpCount[warp] = __popc(mask);
-	__syncthreads();
-	if (threadIdx.x == 0)
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	uint32_t tilesX = (width + 7u) >> 3, tilesY = (height + 3u) >> 2;
+	uint32_t nWarps = tilesX * tilesY;
+	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nWarps; w += (gridDim.x * blockDim.x) >> 5)
 	{
-		uint32_t total = 0;
-		for (uint32_t i = 0; i < nWarps; i++)
-		{
-			uint32_t c = sWarpCount[i];
-			sWarpCount[i] = total;
-			total += c;
-		}
-		*sBase = total ? atomicAdd(counter, (CounterT)total) : (CounterT)0;
+		uint32_t l = threadIdx.x & 31u;
+		uint32_t px = (w % tilesX) * 8u + (l & 7u), py = (w / tilesX) * 4u + (l >> 3);
+		if (px >= width || py >= height) continue;
+		RayD r = generateRay(S.cam, (float)px + 0.5f, (float)py + 0.5f);
+		HitD h;
+		tl.closest++;
+		closestHit<TRAV>(S, r, epsilon, cullRel, h, tl.box, tl.tri);
+		table[(size_t)py * width + px] = make_float4(__uint_as_float(h.id), h.t, h.alpha, h.beta);
 	}
-	__syncthreads();
-	CounterT at = *sBase + (CounterT)sWarpCount[warp] + (CounterT)__popc(mask & ((1u << lane) - 1u));
-	__syncthreads(); // the shared words are reused by the next call
-	return at;
+	flushTally(tl, counters);
 }
 
 __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A)
 {
 	uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	bool inRange = slot < A.nSlots;
-	bool live = wfClaimJob(S, A, inRange ? slot : 0u, inRange);
-	if (inRange && !live) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+	uint32_t n = 0, q = 0;
+	bool live = wfClaimJob(A, inRange, n, q);
+	if (live) wfWriteJob(S, A, slot, n, q);
+	else if (inRange) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 		for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.nSlots; slot += gridDim.x * blockDim.x)
 		{
 			float4 d = A.rayD[slot];
-			if (!(__float_as_uint(d.w) & WF_ALIVE)) continue;
+			if ((__float_as_uint(d.w) & (WF_ALIVE | WF_PREHIT)) != WF_ALIVE) continue;
 			float4 o = A.rayO[slot];
 			RayD r = mkRay(mk(o), mk(d));
 			HitD h;
@@ -232,7 +253,7 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 		if (!have && pre)
 		{
 			pre = false;
-			if (__float_as_uint(preD.w) & WF_ALIVE)
+			if ((__float_as_uint(preD.w) & (WF_ALIVE | WF_PREHIT)) == WF_ALIVE)
 			{
 				t.r = mkRay(mk(preO), mk(preD));
 				travSetBest<false>(t, FLT_MAX, P.cull_rel);
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(128) k_wf_extend_simple(const __grid_constant_
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < A.nSlots; slot += gridDim.x * blockDim.x)
 	{
 		float4 d = A.rayD[slot];
-		if (!(__float_as_uint(d.w) & WF_ALIVE)) continue;
+		if ((__float_as_uint(d.w) & (WF_ALIVE | WF_PREHIT)) != WF_ALIVE) continue;
 		float4 o = A.rayO[slot];
 		RayD r = mkRay(mk(o), mk(d));
 		HitD h;
@@ -455,27 +476,39 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 	const rtb_params& P = A.P;
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
 	const uint32_t lane = threadIdx.x & 31u;
-	uint32_t nAlive = 0, nDone = 0;
-	__shared__ uint32_t sWarpCount[4];
-	__shared__ unsigned int sBase32;
-	__shared__ unsigned long long sBase64;
+	uint32_t nAlive = 0, nDone = 0, phase = 0;
+	__shared__ uint32_t sCountS[2][4], sCountJ[2][4];
+	__shared__ unsigned int sBaseS[2];
+	__shared__ unsigned long long sBaseJ[2];
 	// whole blocks stride together: the cooperative queue/job operations below need every lane
 	uint32_t nRounds = (A.nSlots + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
 	for (uint32_t round = 0; round < nRounds; round++)
 	{
 		uint32_t slot = round * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
 		bool inRange = slot < A.nSlots;
-		bool done = false, aliveAfter = false, haveShadow = false;
-		float4 sO, sD, sC;
+		bool haveVertex = false, slotLive = false;
+		float4 ro, rd, hh, tq;
 		if (inRange)
 		{
-			float4 rd = A.rayD[slot];
-			uint32_t flags = __float_as_uint(rd.w);
-			if (flags & WF_ALIVE)
+			rd = A.rayD[slot];
+			if (__float_as_uint(rd.w) & WF_ALIVE)
 			{
-				float4 ro = A.rayO[slot];
-				float4 hh = A.hit[slot];
-				float4 tq = A.thr[slot];
+				ro = A.rayO[slot];
+				hh = A.hit[slot];
+				tq = A.thr[slot];
+				haveVertex = true;
+			}
+		}
+		// pass 0 shades the slot's vertex; with a primary-hit table, a thread whose path ended
+		// shades the first vertex of its next job in the following pass instead of parking it in
+		// the slot for a whole iteration (a primary miss then never touches slot memory)
+		for (uint32_t pass = 0;; pass++)
+		{
+			bool done = false, haveShadow = false;
+			float4 sO, sD, sC;
+			if (haveVertex)
+			{
+				uint32_t flags = __float_as_uint(rd.w);
 				uint32_t q = __float_as_uint(ro.w), n = __float_as_uint(tq.w);
 				uint32_t depth = flags & WF_DEPTH_MASK;
 				bool canHitLight = (flags & WF_CANHIT) != 0;
@@ -552,7 +585,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 									                           __uint_as_float(WF_ALIVE | (spec ? WF_CANHIT : 0u) | (depth + 1u)));
 									A.thr[slot] = make_float4(T.x, T.y, T.z, __uint_as_float(n));
 									done = false;
-									aliveAfter = true;
+									slotLive = true;
 								}
 							}
 						}
@@ -560,31 +593,69 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 				}
 				filmAdd(A.accum, pixel, add);
 			}
-		}
-		// ---- compact append of the block's shadow rays (one atomic per block)
-		{
-			uint32_t at = blockReserve<unsigned int>(&A.ctrl[iter].nShadow, haveShadow, &sBase32, sWarpCount);
-			if (haveShadow) A.shO[at] = sO, A.shD[at] = sD, A.shC[at] = sC;
-		}
-		// ---- regeneration: finished paths take the next jobs of the render (one atomic per
-		// block; the rare lanes that drew a padding pixel of an edge tile retry warp-wise)
-		if (done) nDone++;
-		bool live = false;
-		{
-			unsigned long long j = blockReserve<unsigned long long>(&A.glob->nextJob, done, &sBase64, sWarpCount);
-			bool retry = false;
-			if (done)
+			haveVertex = false;
+			// ---- one cooperative step reserves the block's shadow-queue entries AND its next jobs:
+			// two ballots, two barriers, one atomic per counter and block (shared words are
+			// double-buffered, so the next pass may write while stragglers still read)
+			if (done) nDone++;
+			const uint32_t warp = threadIdx.x >> 5, ph = (phase++) & 1u;
+			unsigned mS = __ballot_sync(0xFFFFFFFFu, haveShadow), mJ = __ballot_sync(0xFFFFFFFFu, done);
+			if (lane == 0) sCountS[ph][warp] = __popc(mS), sCountJ[ph][warp] = __popc(mJ);
+			__syncthreads();
+			if (threadIdx.x == 0)
 			{
-				if (j < A.totalJobs)
-				{
-					live = wfStartJob(S, A, slot, j);
-					retry = !live;
-				}
+				uint32_t tot = sCountS[ph][0] + sCountS[ph][1] + sCountS[ph][2] + sCountS[ph][3];
+				sBaseS[ph] = tot ? atomicAdd(&A.ctrl[iter].nShadow, tot) : 0u;
 			}
-			if (__any_sync(0xFFFFFFFFu, retry)) live = wfClaimJob(S, A, inRange ? slot : 0u, retry) || live;
+			if (threadIdx.x == 32)
+			{
+				uint32_t tot = sCountJ[ph][0] + sCountJ[ph][1] + sCountJ[ph][2] + sCountJ[ph][3];
+				sBaseJ[ph] = tot ? atomicAdd(&A.glob->nextJob, (unsigned long long)tot) : 0ull;
+			}
+			bool anyDone = __syncthreads_or(done) != 0;
+			if (haveShadow)
+			{
+				uint32_t at = sBaseS[ph] + __popc(mS & ((1u << lane) - 1u));
+				for (uint32_t w = 0; w < warp; w++) at += sCountS[ph][w];
+				A.shO[at] = sO, A.shD[at] = sD, A.shC[at] = sC;
+			}
+			// ---- regeneration: finished paths take the next jobs of the render (the rare lanes that
+			// drew a padding pixel of an edge tile retry warp-wise)
+			bool fresh = false;
+			uint32_t n = 0, q = 0;
+			{
+				bool retry = false;
+				if (done)
+				{
+					unsigned long long j = sBaseJ[ph] + __popc(mJ & ((1u << lane) - 1u));
+					for (uint32_t w = 0; w < warp; w++) j += sCountJ[ph][w];
+					if (j < A.totalJobs)
+					{
+						fresh = wfDecodeJob(A, j, n, q);
+						retry = !fresh;
+					}
+				}
+				if (__any_sync(0xFFFFFFFFu, retry)) fresh = wfClaimJob(A, retry, n, q) || fresh;
+			}
+			if (done && !fresh) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+			bool morePasses = A.primary != nullptr && pass + 1u < A.primaryPasses;
+			if (!morePasses)
+			{
+				if (fresh)
+				{
+					wfWriteJob(S, A, slot, n, q);
+					slotLive = true;
+				}
+				break;
+			}
+			if (!anyDone) break; // no thread of the block can hold a fresh vertex
+			if (fresh)
+			{
+				wfFirstVertex(S, A, n, q, ro, rd, hh, tq);
+				haveVertex = true;
+			}
 		}
-		if (done && !live) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-		if (aliveAfter || live) nAlive++;
+		if (slotLive) nAlive++;
 	}
 	// block-level totals: one atomic per block for `alive`, one striped atomic for the sample count
 	for (int o = 16; o > 0; o >>= 1)

@@ -34,7 +34,7 @@ def gpu_scene(rtb, name):
         _rt_cache[name] = rt
     rt = _rt_cache[name]
     p = rtb.default_params()
-    rt.set_params(**{k: getattr(p, k) for k, _ in abi.Params._fields_ if k != "reserved_"})
+    rt.set_params(**{k: getattr(p, k) for k, _ in abi.Params._fields_})
     rt.clear()
     return rt
 
@@ -230,6 +230,7 @@ def test_render_equals_the_oracle_sample_for_sample(rtb, oracle_mod, name):
     ulp (acosf / sincosf / atan2f) flips a discrete path decision."""
     rt = gpu_scene(rtb, name)
     spp = 2
+    rt.set_params(primary_reuse=0)        # every sample traces its own camera ray, like the reference
     rt.render(spp, 0)
     img = rt.read_film()
     want, st = oracle_mod.Oracle(rt.scene).render(spp)
@@ -241,6 +242,33 @@ def test_render_equals_the_oracle_sample_for_sample(rtb, oracle_mod, name):
     assert g["samples"] == st["samples"] == rt.width * rt.height * spp
     assert abs(g["closest_rays"] / st["closest_rays"] - 1) < 2e-3
     assert abs(g["shadow_rays"] / st["shadow_rays"] - 1) < 2e-3
+
+
+@pytest.mark.parametrize("name,spp", [("synthetic", 3), ("cornell-box", 5), ("materialball", 3), ("MaterialsScene", 2)])
+def test_primary_hit_table_changes_no_bit_of_the_film(rtb, name, spp, monkeypatch):
+    """params.primary_reuse traces each pixel's camera ray once per render call (all samples of a
+    pixel share it: pixel centres only, Renderer.h:806-807).  The film must be bit-identical to
+    tracing it per sample, for any number of shade passes, and exactly W*H*(spp-1) closest-hit rays
+    must disappear from the counters."""
+    rt = gpu_scene(rtb, name)
+    rt.set_params(primary_reuse=0)
+    rt.clear()
+    rt.render(spp, 0)
+    a = rt.read_film().copy()
+    sa = rt.stats()
+    for passes in ("1", "2", "7"):
+        monkeypatch.setenv("RTB_PRIMARY_PASSES", passes)
+        rt2 = rtb.RayTracer(0)
+        rt2.init(rt.scene)
+        rt2.set_params(primary_reuse=1)
+        rt2.render(spp, 0)
+        b = rt2.read_film()
+        sb = rt2.stats()
+        rt2.close()
+        assert np.array_equal(a, b), passes
+        assert sb["samples"] == sa["samples"]
+        assert sb["shadow_rays"] == sa["shadow_rays"]
+        assert sa["closest_rays"] - sb["closest_rays"] == rt.width * rt.height * (spp - 1), passes
 
 
 def test_exact_and_fast_render_identical_films(rtb):
@@ -260,6 +288,7 @@ def test_megakernel_and_wavefront_schedules_agree(rtb):
     """Same samples, same RNG streams; only the summation order differs."""
     for name in ("synthetic", "cornell-box"):
         rt = gpu_scene(rtb, name)
+        rt.set_params(primary_reuse=0)      # the megakernel traces every camera ray
         rt.render(4, 0)
         a = rt.read_film().copy()
         sa = rt.stats()
@@ -467,7 +496,7 @@ def test_soup_config_primary_plus_one_bounce(rtb, oracle_mod):
     s, _ = host_api.build_soup(1 << 14, 320, 180)
     rt = rtb.RayTracer(0)
     rt.init(s)
-    rt.set_params(max_depth=0)
+    rt.set_params(max_depth=0, primary_reuse=0)
     o = oracle_mod.Oracle(s, max_depth=0)
     for trav in TRAVS:
         ids, t = rt.primary_hits(trav)

@@ -11,6 +11,8 @@ s = host_api.load_scene(os.path.join("scenes", "_staged", name))
 rt = rtb.RayTracer(0)
 rt.init(s)
 rt.set_params(traversal=trav)
+if "RTB_REUSE" in os.environ:
+    rt.set_params(primary_reuse=int(os.environ["RTB_REUSE"]))
 for i in range(2):
     rt.clear(); rt.render(spp, 0); rt.synchronize()
 st = rt.stats()
