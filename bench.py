@@ -344,14 +344,29 @@ def run_ours(args, rank, world, local_rank):
         # per ray (32-B ray in, 16-B hit out); shade stage 64 B slot state in + 48 B out + 24 B
         # film read-modify-write per vertex.
         n_iter = max(iters, 1)
-        alg = {"extend": (32.0 * box + 64.0 * tri + 48.0 * closest) / n_iter,
-               "shadow": (32.0 * sbox + 64.0 * stri + 48.0 * shadow) / n_iter,
-               "shade": (64.0 + 48.0 + 24.0) * closest / n_iter}
+        # per-ray figures of the CANONICAL traversal (profiles/canonical_counts.json, written by
+        # tests/tools/canonical_counts.py) x the rays this run traced; the kernels' own counters are
+        # the fallback for scenes the tool has not been run on
+        canon, alg_source = {}, "canonical traversal (profiles/canonical_counts.json)"
+        cp = os.path.join(ROOT, "profiles", "canonical_counts.json")
+        if os.path.isfile(cp):
+            canon = json.load(open(cp))
+        keys = [("materialball_" + lab) if args.scene == "materialball7" else lab for lab, _ in flats]
+        if all(k in canon for k in keys):
+            ext_b = sum(s_["closest_rays"] * canon[k]["closest_bytes_per_ray"] for s_, k in zip(st, keys))
+            sha_b = sum(s_["shadow_rays"] * canon[k]["shadow_bytes_per_ray"] for s_, k in zip(st, keys))
+            alg_flops = sum(s_["closest_rays"] * canon[k]["closest_flops_per_ray"] + s_["shadow_rays"] * canon[k]["shadow_flops_per_ray"]
+                            for s_, k in zip(st, keys))
+        else:
+            alg_source = "this run's own traversal counters (scene not in profiles/canonical_counts.json)"
+            ext_b = 32.0 * box + 64.0 * tri + 48.0 * closest
+            sha_b = 32.0 * sbox + 64.0 * stri + 48.0 * shadow
+            alg_flops = 24.0 * (box + sbox) + 60.0 * (tri + stri)
+        alg = {"extend": ext_b / n_iter, "shadow": sha_b / n_iter, "shade": (64.0 + 48.0 + 24.0) * closest / n_iter}
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         per_launch_ms = stage_ms[dom]
         achieved = alg[dom] / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
         stage_total = sum(stage_ms.values())
-        alg_flops = 24.0 * (box + sbox) + 60.0 * (tri + stri)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
@@ -370,7 +385,7 @@ def run_ours(args, rank, world, local_rank):
                          "kernel_ms_per_launch": per_launch_ms,
                          "kernel_share_of_step": stage_ms[dom] / stage_total if stage_total else None,
                          "stage_ms_per_launch": stage_ms, "launches_per_render": n_iter / max(len(rts), 1),
-                         "alg_bytes_per_launch": alg[dom],
+                         "alg_bytes_per_launch": alg[dom], "alg_source": alg_source,
                          "note": "scene (<= 10 MB) and slot pool are L2/L1 traffic; the stages are latency/divergence "
                                  "bound, not HBM bound - see roofline_fp32 and profiles/"},
             "roofline_fp32": {"achieved_tflops": alg_flops / (kern_ms / 1e3) / 1e12, "peak_tflops": fp32_peak,

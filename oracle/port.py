@@ -39,6 +39,7 @@ def lib():
         L = C.CDLL(LIB)
         vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
         L.oracle_render.argtypes = [vp, vp, u32, u32, i32, vp, vp]
+        L.oracle_render_counts.argtypes = [vp, vp, u32, u32, i32, vp, vp]
         L.oracle_primary_hits.argtypes = [vp, f32, vp, vp, vp]
         L.oracle_trace.argtypes = [vp, f32, i32, vp, u64, vp]
         L.oracle_visible.argtypes = [vp, f32, vp, u64, vp]
@@ -109,6 +110,16 @@ class Oracle:
         self.L.oracle_render(C.addressof(self.desc), C.addressof(self.params), int(spp_begin), int(spp), int(threads),
                              _p(film), _p(st))
         return film, dict(samples=int(st[0]), closest_rays=int(st[1]), shadow_rays=int(st[2]))
+
+    def render_counts(self, spp, spp_begin=0, threads=None):
+        """render() + the CANONICAL traversal work of every ray it traced."""
+        film = np.zeros((self.height, self.width, 3), "<f4")
+        threads = threads or os.cpu_count() or 1
+        st = np.zeros(7, np.uint64)
+        self.L.oracle_render_counts(C.addressof(self.desc), C.addressof(self.params), int(spp_begin), int(spp),
+                                    int(threads), _p(film), _p(st))
+        keys = ("samples", "closest_rays", "shadow_rays", "closest_box", "closest_tri", "shadow_box", "shadow_tri")
+        return film, {k: int(v) for k, v in zip(keys, st)}
 
     def primary_hits(self, want_rays=False):
         n = self.width * self.height

@@ -64,7 +64,10 @@ static ray_t make_ray(v3 o, v3 d) /* Geometry.h:21-26 */
 
 typedef struct {
 	uint64_t closest, shadow, samples;
+	uint64_t cbox, ctri, sbox, stri; /* canonical-traversal work (oracle_render_counts only) */
 } tally_t;
+
+static int g_count_canonical = 0;
 
 /* ---------------- Camera::generateRay, Scene.h:43-54; Core.h:295-309 ------------------ */
 static ray_t generate_ray(const rtb_camera* c, float x, float y)
@@ -186,6 +189,102 @@ static int scene_visible(const rtb_scene_desc* s, v3 p1, v3 p2, float eps) /* Sc
 	r = make_ray(add(p1, scl(dir, eps)), dir);
 	if (!s->n_ref_nodes) return 1;
 	return bvh_visible(s, 0, &r, eps, maxT);
+}
+
+/* ---------------- canonical traversal work counter -------------------------
+ * The per-ray figures the roofline's algorithmic bytes/flops are defined on: iterative DFS on the
+ * reference tree; at an interior node BOTH child boxes get the exact slab test; nearer child first;
+ * a node is dropped when t_entry - |t_entry|*1e-5 > t_best (closest) or >= maxT (shadow); leaves
+ * test all their triangles; shadow rays stop at the first accepted hit.  It only counts; the hit
+ * decisions of the render stay those of bvh_traverse / bvh_visible above.                        */
+static int slab_entry(const rtb_ref_node* n, const ray_t* r, float* t_in)
+{
+	v3 tmin = mul(sub(Vp(n->bmin), r->o), r->inv);
+	v3 tmax = mul(sub(Vp(n->bmax), r->o), r->inv);
+	v3 en = V(win_min(tmin.x, tmax.x), win_min(tmin.y, tmax.y), win_min(tmin.z, tmax.z));
+	v3 ex = V(win_max(tmin.x, tmax.x), win_max(tmin.y, tmax.y), win_max(tmin.z, tmax.z));
+	float t_entry = std_max(std_max(en.x, en.y), en.z);
+	float t_exit = std_min(std_min(ex.x, ex.y), ex.z);
+	if (t_exit < t_entry || t_exit < 0) return 0;
+	*t_in = t_entry;
+	return 1;
+}
+
+static void canonical_count(const rtb_scene_desc* s, const ray_t* r, float eps, int any_hit, float maxT, uint64_t* nbox, uint64_t* ntri)
+{
+	int32_t stack[256];
+	float stackT[256];
+	int sp = 0;
+	float best = any_hit ? maxT : FLT_MAX, t0;
+	if (!s->n_ref_nodes) return;
+	(*nbox)++;
+	if (!slab_entry(&s->ref_nodes[0], r, &t0)) return;
+	stack[sp] = 0, stackT[sp] = t0, sp++;
+	while (sp > 0)
+	{
+		int32_t node = stack[--sp];
+		float te = stackT[sp];
+		const rtb_ref_node* n = &s->ref_nodes[node];
+		float lim = te - fabsf(te) * 1e-5f;
+		if (any_hit ? (lim >= best) : (lim > best)) continue;
+		if (n->a < 0)
+		{
+			int32_t start = ~n->a, end = start + n->b, i;
+			for (i = start; i < end; i++)
+			{
+				float t, u, v;
+				(*ntri)++;
+				if (!tri_intersect(&s->tri_isect[i], r, &t, &u, &v)) continue;
+				if (any_hit)
+				{
+					if (t < maxT && t > eps) return;
+				}
+				else if (t < best && t > eps)
+					best = t;
+			}
+			continue;
+		}
+		{
+			float ta = 0, tb = 0;
+			int ha, hb;
+			(*nbox) += 2;
+			ha = slab_entry(&s->ref_nodes[n->a], r, &ta);
+			hb = slab_entry(&s->ref_nodes[n->b], r, &tb);
+			if (ha && hb)
+			{
+				int32_t nearN = (tb < ta) ? n->b : n->a, farN = (tb < ta) ? n->a : n->b;
+				float nearT = (tb < ta) ? tb : ta, farT = (tb < ta) ? ta : tb;
+				if (sp + 2 > 256) return;
+				stack[sp] = farN, stackT[sp] = farT, sp++;
+				stack[sp] = nearN, stackT[sp] = nearT, sp++;
+			}
+			else if (ha || hb)
+			{
+				if (sp + 1 > 256) return;
+				stack[sp] = ha ? n->a : n->b, stackT[sp] = ha ? ta : tb, sp++;
+			}
+		}
+	}
+}
+
+static rtb_hit scene_traverse_tl(const rtb_scene_desc* s, const ray_t* r, float eps, tally_t* tl)
+{
+	if (g_count_canonical) canonical_count(s, r, eps, 0, FLT_MAX, &tl->cbox, &tl->ctri);
+	return scene_traverse(s, r, eps);
+}
+
+static int scene_visible_tl(const rtb_scene_desc* s, v3 p1, v3 p2, float eps, tally_t* tl)
+{
+	if (g_count_canonical)
+	{
+		v3 dir = sub(p2, p1);
+		float maxT = sqrtf(dot3(dir, dir)) - (2.0f * eps);
+		ray_t r;
+		dir = norm3(dir);
+		r = make_ray(add(p1, scl(dir, eps)), dir);
+		canonical_count(s, &r, eps, 1, maxT, &tl->sbox, &tl->stri);
+	}
+	return scene_visible(s, p1, p2, eps);
 }
 
 /* ---------------- ShadingData: Scene.h:174-203, Geometry.h:106-112,127-130, Core.h:513 -- */
@@ -445,7 +544,7 @@ static v3 compute_direct(const rtb_scene_desc* s, const rtb_params* P, const sha
 		if (G > 0)
 		{
 			tl->shadow++;
-			if (scene_visible(s, sd->x, p, P->epsilon))
+			if (scene_visible_tl(s, sd->x, p, P->epsilon, tl))
 				return dvd(scl(mul(bsdf_evaluate(s, m, sd), Vp(L->emission)), G), (pmf * pdf));
 		}
 	}
@@ -458,7 +557,7 @@ static v3 compute_direct(const rtb_scene_desc* s, const rtb_params* P, const sha
 		if (G > 0)
 		{
 			tl->shadow++;
-			if (scene_visible(s, sd->x, add(sd->x, scl(wi, 10000.0f)), P->epsilon))
+			if (scene_visible_tl(s, sd->x, add(sd->x, scl(wi, 10000.0f)), P->epsilon, tl))
 				return dvd(scl(mul(bsdf_evaluate(s, m, sd), emitted), G), (pmf * pdf));
 		}
 	}
@@ -469,7 +568,7 @@ static v3 compute_direct(const rtb_scene_desc* s, const rtb_params* P, const sha
 static v3 path_trace(const rtb_scene_desc* s, const rtb_params* P, ray_t* r, v3* T, int depth, uint32_t pixel,
                      uint32_t sample, int canHitLight, tally_t* tl)
 {
-	rtb_hit h = scene_traverse(s, r, P->epsilon);
+	rtb_hit h = scene_traverse_tl(s, r, P->epsilon, tl);
 	shade_t sd;
 	tl->closest++;
 	shading_data(s, &h, r, &sd);
@@ -502,7 +601,7 @@ static v3 path_trace(const rtb_scene_desc* s, const rtb_params* P, ray_t* r, v3*
 /* direct(), albedo(), viewNormals(): Renderer.h:393-407, 558-581 */
 static v3 shade_simple(const rtb_scene_desc* s, const rtb_params* P, ray_t* r, uint32_t pixel, uint32_t sample, tally_t* tl)
 {
-	rtb_hit h = scene_traverse(s, r, P->epsilon);
+	rtb_hit h = scene_traverse_tl(s, r, P->epsilon, tl);
 	shade_t sd;
 	tl->closest++;
 	shading_data(s, &h, r, &sd);
@@ -626,15 +725,31 @@ int oracle_render(const rtb_scene_desc* s, const rtb_params* P, uint32_t spp_beg
 	if (stats)
 	{
 		stats[0] = stats[1] = stats[2] = 0;
+		if (g_count_canonical) stats[3] = stats[4] = stats[5] = stats[6] = 0;
 		for (c = 0; c < chunks; c++)
 		{
 			stats[0] += jobs[c].tl.samples, stats[1] += jobs[c].tl.closest, stats[2] += jobs[c].tl.shadow;
+			if (g_count_canonical)
+				stats[3] += jobs[c].tl.cbox, stats[4] += jobs[c].tl.ctri, stats[5] += jobs[c].tl.sbox, stats[6] += jobs[c].tl.stri;
 		}
 	}
 	free(spans);
 	free(jobs);
 	free(th);
 	return 0;
+}
+
+/* oracle_render + the canonical-traversal work of every ray it traced.
+ * stats = samples, closest, shadow, closest box tests, closest tri tests, shadow box, shadow tri.
+ * Not re-entrant (one process-wide switch): tests/tools/canonical_counts.py is its only caller. */
+int oracle_render_counts(const rtb_scene_desc* s, const rtb_params* P, uint32_t spp_begin, uint32_t spp_count, int threads,
+                         float* film_sum, uint64_t* stats7)
+{
+	int rc;
+	g_count_canonical = 1;
+	rc = oracle_render(s, P, spp_begin, spp_count, threads, film_sum, stats7);
+	g_count_canonical = 0;
+	return rc;
 }
 
 /* ---------------- batched entry points mirroring include/rtb.h -------------------------- */
