@@ -168,8 +168,16 @@ typedef enum rtb_integrator {
 	RTB_INT_PATH = 0,    /* RayTracer::pathTrace   Renderer.h:328-392 (the default)   */
 	RTB_INT_DIRECT = 1,  /* RayTracer::direct      Renderer.h:393-407                */
 	RTB_INT_ALBEDO = 2,  /* RayTracer::albedo      Renderer.h:558-571                */
-	RTB_INT_NORMALS = 3  /* RayTracer::viewNormals Renderer.h:572-581                */
+	RTB_INT_NORMALS = 3, /* RayTracer::viewNormals Renderer.h:572-581                */
+	RTB_INT_PATH_MIS = 4 /* pathTrace with computeDirectMIS (Renderer.h:474-557) in place of
+	                      * computeDirect: the estimator the reference ships but leaves switched
+	                      * off.  Runs on the megakernel schedule (its BSDF-strategy probe ray is
+	                      * traced in place).                                                 */
 } rtb_integrator;
+
+/* Philox block index of computeDirectMIS's BSDF-strategy uniforms at path depth k: RTB_RNG_MIS_BLOCK + k
+ * (blocks 2k and 2k+1 belong to pathTrace's own draws). */
+#define RTB_RNG_MIS_BLOCK 0x40000000u
 
 typedef enum rtb_sampling {
 	RTB_SAMPLING_STRICT = 0,    /* sampling decisions exactly as the reference: uniform

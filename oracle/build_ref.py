@@ -12,6 +12,9 @@ GPU box with gpurun):
   oracle/_ref/librtref_fast.so   same, -O3 -march=native -ffast-math (speed only; mirrors the
                              reference's MSVC /fp:fast /arch:AVX, RTBase/RTBase.vcxproj:123-124)
   oracle/_ref/librtref_d0.so     MAX_DEPTH = 0 variant of the parity build
+  oracle/_ref/librtref_mis.so    parity build whose pathTrace calls computeDirectMIS (Renderer.h:474-557,
+                                 shipped but switched off) instead of computeDirect: a build-time patched
+                                 COPY of Renderer.h in the git-ignored shadow dir, like _d0
   oracle/_ref/dropin_main    oracle/dropin_main.cpp: reference host program + the product's
                              host/Renderer.h, linked to librtb200.so (drop-in test)
   scenes/_staged/<name>/     filtered copies of the bundled scene ASSETS (instances whose mesh is
@@ -60,7 +63,7 @@ def have_reference():
     return os.path.isfile(os.path.join(RTBASE, "Renderer.h"))
 
 
-def make_shadow(name, patch_depth=False):
+def make_shadow(name, patch_depth=False, patch_mis=False):
     d = os.path.join(OUT, name)
     if os.path.isdir(d):
         shutil.rmtree(d)
@@ -68,11 +71,17 @@ def make_shadow(name, patch_depth=False):
     for h in REF_HEADERS:
         src = os.path.join(RTBASE, h)
         dst = os.path.join(d, h)
-        if patch_depth and h == "Renderer.h":
+        if (patch_depth or patch_mis) and h == "Renderer.h":
             text = open(src, encoding="utf-8-sig").read()
-            needle = "const int MAX_DEPTH = 4;"
-            assert text.count(needle) == 1, "Renderer.h:20 changed"
-            text = text.replace(needle, "const int MAX_DEPTH = RT_MAX_DEPTH;")
+            if patch_depth:
+                needle = "const int MAX_DEPTH = 4;"
+                assert text.count(needle) == 1, "Renderer.h:20 changed"
+                text = text.replace(needle, "const int MAX_DEPTH = RT_MAX_DEPTH;")
+            if patch_mis:
+                # pathTrace calls the estimator the reference ships switched off (Renderer.h:346)
+                needle = "Colour direct = pathThroughput * computeDirect(shadingData, sampler);"
+                assert text.count(needle) == 1, "Renderer.h:346 changed"
+                text = text.replace(needle, "Colour direct = pathThroughput * computeDirectMIS(shadingData, sampler);")
             open(dst, "w", encoding="utf-8").write(text)
         else:
             os.symlink(src, dst)
@@ -199,6 +208,7 @@ def build(force=False):
             os.path.join(ROOT, "raytracingrenderer_b200", "host", "rtb_flatten.hpp"),
             os.path.join(ROOT, "include", "rtb.h"), os.path.abspath(__file__)]
     fresh = (not force and os.path.isfile(stamp) and os.path.isfile(os.path.join(OUT, "librtref_d0.so"))
+             and os.path.isfile(os.path.join(OUT, "librtref_mis.so"))
              and os.path.isfile(os.path.join(OUT, "librtref_fast.so"))
              and all(os.path.getmtime(stamp) >= os.path.getmtime(s) for s in srcs))
     if not fresh:
@@ -206,6 +216,7 @@ def build(force=False):
         shadow_d0 = make_shadow("shadow_d0", patch_depth=True)
         compile_driver(shadow, "librtref_fast.so", ["-O3", "-march=native", "-ffast-math"])
         compile_driver(shadow_d0, "librtref_d0.so", ["-O2", "-ffp-contract=off", "-DRT_MAX_DEPTH=0"])
+        compile_driver(make_shadow("shadow_mis", patch_mis=True), "librtref_mis.so", ["-O2", "-ffp-contract=off"])
         compile_driver(shadow, "librtref.so", ["-O2", "-ffp-contract=off"])
     dropin_srcs = [os.path.join(HERE, "dropin_main.cpp"), os.path.join(ROOT, "raytracingrenderer_b200", "host", "Renderer.h"),
                    os.path.join(ROOT, "raytracingrenderer_b200", "host", "rtb_flatten.hpp"), os.path.join(ROOT, "include", "rtb.h")]

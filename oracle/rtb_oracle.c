@@ -564,6 +564,86 @@ static v3 compute_direct(const rtb_scene_desc* s, const rtb_params* P, const sha
 	return V(0, 0, 0);
 }
 
+/* ---------------- RayTracer::computeDirectMIS, Renderer.h:474-557 (+ balanceHeuristic :408-410,
+ * convertPDFAreaToSolidAngle :411-422).  Unused by the reference's render(); selectable here as
+ * RTB_INT_PATH_MIS.  Its quirks are kept: a visible NON-area light returns at once without a weight
+ * and without the BSDF strategy; the BSDF strategy converts the area pdf of the light that was
+ * SAMPLED (not of the emitter that was hit).  um = the BSDF strategy's own uniforms.           */
+static float balance_heuristic(float a, float b) { return a / (a + b); }
+static float pdf_area_to_solid_angle(float pdfArea, float dist2, float costheta)
+{
+	return (costheta > 0.0f) ? (pdfArea * dist2 / costheta) : 0.0f;
+}
+
+static v3 compute_direct_mis(const rtb_scene_desc* s, const rtb_params* P, const shade_t* sd, const float u[4], const float um[4],
+                             tally_t* tl)
+{
+	const rtb_material* m = &s->materials[sd->mat];
+	const rtb_light* L;
+	float pmf, pdf, pdf_bsdf;
+	int li;
+	v3 result = V(0, 0, 0), val_bsdf, wi_bsdf;
+	ray_t r;
+	rtb_hit h;
+	shade_t sh;
+	if (m->flags & RTB_MAT_SPECULAR) return V(0, 0, 0);
+	if (s->n_lights == 0) return V(0, 0, 0);
+	pmf = 1.f / s->n_lights;
+	li = (int)(s->n_lights * u[0]);
+	if (li > (int)s->n_lights - 1) li = (int)s->n_lights - 1;
+	L = &s->lights[li];
+	if (L->type == RTB_LIGHT_AREA)
+	{
+		v3 p = triangle_sample(s, L->triangle, u[1], u[2], &pdf);
+		v3 wi = sub(p, sd->x);
+		float l = dot3(wi, wi), cs, cl, G;
+		wi = norm3(wi);
+		cs = win_max(dot3(wi, sd->sN), 0.0f);
+		cl = win_max(-dot3(wi, triangle_gnormal(s, L->triangle)), 0.0f);
+		G = cs * cl / l;
+		if (G > 0)
+		{
+			tl->shadow++;
+			if (scene_visible_tl(s, sd->x, p, P->epsilon, tl))
+			{
+				float pdfB = bsdf_pdf(m, sd, wi);
+				float pdfL = pdf_area_to_solid_angle(pdf * pmf, l, cl);
+				float w = balance_heuristic(pdfL, pdfB);
+				result = add(result, dvd(scl(scl(mul(bsdf_evaluate(s, m, sd), Vp(L->emission)), G), w), (pmf * pdf)));
+			}
+		}
+	}
+	else
+	{
+		v3 wi = uniform_sample_sphere(u[1], u[2]);
+		v3 emitted = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, wi) : Vp(L->emission);
+		float G = win_max(dot3(wi, sd->sN), 0.0f);
+		pdf = 1.0f / (4.0f * M_PI);
+		if (G > 0)
+		{
+			tl->shadow++;
+			if (scene_visible_tl(s, sd->x, add(sd->x, scl(wi, 10000.0f)), P->epsilon, tl))
+				return dvd(scl(mul(bsdf_evaluate(s, m, sd), emitted), G), (pmf * pdf));
+		}
+	}
+	wi_bsdf = bsdf_sample(s, m, sd, um[0], um[1], um[2], &val_bsdf, &pdf_bsdf);
+	r = make_ray(add(sd->x, scl(wi_bsdf, P->epsilon)), wi_bsdf);
+	h = scene_traverse_tl(s, &r, P->epsilon, tl);
+	tl->closest++;
+	shading_data(s, &h, &r, &sh);
+	if (sh.t < FLT_MAX && (s->materials[sh.mat].flags & RTB_MAT_LIGHT))
+	{
+		v3 wi = sub(sh.x, sd->x);
+		float dist2 = dot3(wi, wi), cl, pdfL, w;
+		wi = norm3(wi);
+		cl = win_max(0.0f, dot3(neg(wi), sh.sN));
+		pdfL = pdf_area_to_solid_angle(pdf * pmf, dist2, cl);
+		w = balance_heuristic(pdf_bsdf, pdfL);
+		result = add(result, dvd(scl(scl(mul(val_bsdf, Vp(s->materials[sh.mat].emission)), win_max(0.0f, dot3(wi_bsdf, sd->sN))), w), pdf_bsdf));
+	}
+	return result;
+}
+
 /* ---------------- RayTracer::pathTrace, Renderer.h:328-392 (recursive like the reference) */
 static v3 path_trace(const rtb_scene_desc* s, const rtb_params* P, ray_t* r, v3* T, int depth, uint32_t pixel,
                      uint32_t sample, int canHitLight, tally_t* tl)
@@ -583,7 +663,14 @@ static v3 path_trace(const rtb_scene_desc* s, const rtb_params* P, ray_t* r, v3*
 			return V(0, 0, 0);
 		}
 		rng_block(P->seed, pixel, sample, 2u * (uint32_t)depth, ua);
-		direct = mul(*T, compute_direct(s, P, &sd, ua, tl));
+		if (P->integrator == RTB_INT_PATH_MIS)
+		{
+			float um[4];
+			rng_block(P->seed, pixel, sample, RTB_RNG_MIS_BLOCK + (uint32_t)depth, um);
+			direct = mul(*T, compute_direct_mis(s, P, &sd, ua, um, tl));
+		}
+		else
+			direct = mul(*T, compute_direct(s, P, &sd, ua, tl));
 		if (depth > P->max_depth) return direct;
 		rr = win_min(lum3(*T), P->rr_cap);
 		if (ua[3] < rr) *T = dvd(*T, rr);
@@ -668,7 +755,7 @@ static void* render_rows(void* arg)
 				    (int)(smp % (uint32_t)P->part_world) != P->part_rank)
 					continue;
 				r = generate_ray(&s->camera, x + 0.5f, y + 0.5f);
-				if (P->integrator == RTB_INT_PATH)
+				if (P->integrator == RTB_INT_PATH || P->integrator == RTB_INT_PATH_MIS)
 				{
 					v3 T = V(1.0f, 1.0f, 1.0f);
 					c = path_trace(s, P, &r, &T, 0, pixel, smp, 1, &j->tl);

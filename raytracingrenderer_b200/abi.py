@@ -50,7 +50,8 @@ assert file_header_dt.itemsize == 224
 BSDF_DIFFUSE, BSDF_MIRROR, BSDF_CONDUCTOR, BSDF_GLASS, BSDF_DIELECTRIC, BSDF_ORENNAYAR, BSDF_PLASTIC = range(7)
 MAT_SPECULAR, MAT_TWO_SIDED, MAT_LIGHT, MAT_LAYERED = 1, 2, 4, 8
 LIGHT_AREA, LIGHT_BACKGROUND, LIGHT_ENVMAP = 0, 1, 2
-INT_PATH, INT_DIRECT, INT_ALBEDO, INT_NORMALS = 0, 1, 2, 3
+INT_PATH, INT_DIRECT, INT_ALBEDO, INT_NORMALS, INT_PATH_MIS = 0, 1, 2, 3, 4
+RNG_MIS_BLOCK = 0x40000000
 SAMPLING_STRICT, SAMPLING_IMPORTANCE = 0, 1
 TRAV_EXACT, TRAV_FAST, TRAV_WIDE = 0, 1, 2
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1

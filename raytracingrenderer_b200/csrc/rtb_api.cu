@@ -254,6 +254,7 @@ static void launchRender(rtb_ctx* ctx, const RenderArgs& A, dim3 grid, dim3 bloc
 	case RTB_INT_DIRECT: k_render<TRAV, RTB_INT_DIRECT><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
 	case RTB_INT_ALBEDO: k_render<TRAV, RTB_INT_ALBEDO><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
 	case RTB_INT_NORMALS: k_render<TRAV, RTB_INT_NORMALS><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
+	case RTB_INT_PATH_MIS: k_render<TRAV, RTB_INT_PATH_MIS><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
 	default: k_render<TRAV, RTB_INT_PATH><<<grid, block, 0, ctx->stream>>>(ctx->S, A); break;
 	}
 }
@@ -653,7 +654,7 @@ int rtb_synchronize(rtb_ctx* ctx)
 int rtb_set_params(rtb_ctx* ctx, const rtb_params* p)
 {
 	if (!ctx || !p) return fail(ctx, RTB_ERR_ARG, "rtb_set_params: NULL argument");
-	if (p->integrator < RTB_INT_PATH || p->integrator > RTB_INT_NORMALS) return fail(ctx, RTB_ERR_ARG, "bad integrator %d", p->integrator);
+	if (p->integrator < RTB_INT_PATH || p->integrator > RTB_INT_PATH_MIS) return fail(ctx, RTB_ERR_ARG, "bad integrator %d", p->integrator);
 	if (p->sampling != RTB_SAMPLING_STRICT && p->sampling != RTB_SAMPLING_IMPORTANCE) return fail(ctx, RTB_ERR_ARG, "bad sampling %d", p->sampling);
 	if (int rc = checkTrav(ctx, p->traversal)) return rc;
 	if (p->filter != RTB_FILTER_BOX && p->filter != RTB_FILTER_GAUSSIAN) return fail(ctx, RTB_ERR_ARG, "bad filter %d", p->filter);
@@ -833,7 +834,9 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	if (spp_count == 0) return RTB_OK;
 	if ((uint64_t)spp_begin + spp_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "sample index overflow");
 	if (int rc = bind(ctx)) return rc;
-	int rc = (ctx->params.scheduler == RTB_SCHED_MEGAKERNEL) ? renderMegakernel(ctx, spp_begin, spp_count)
+	// computeDirectMIS traces its BSDF-strategy probe ray in place: megakernel schedule only
+	bool mega = ctx->params.scheduler == RTB_SCHED_MEGAKERNEL || ctx->params.integrator == RTB_INT_PATH_MIS;
+	int rc = mega ? renderMegakernel(ctx, spp_begin, spp_count)
 	                                                           : renderWavefront(ctx, spp_begin, spp_count);
 	if (rc) return rc;
 	ctx->spp += spp_count;

@@ -155,6 +155,88 @@ RTB_DEV V3 computeDirect(const DevScene& S, const rtb_params& P, const ShadeD& s
 }
 
 // ---------------------------------------------------------------------------------------
+// RayTracer::computeDirectMIS (Renderer.h:474-557): light strategy + BSDF strategy combined with
+// the balance heuristic (:408-410) after converting the light's area pdf to solid angle
+// (:411-422).  The reference's quirks are kept: a visible
+// non-area light returns un-weighted at once; the BSDF strategy uses the pdf of the light that
+// was SAMPLED.  um = (bsdf r1, r2, r3) of the BSDF strategy.
+// ---------------------------------------------------------------------------------------
+template <int TRAV>
+RTB_DEV V3 computeDirectMIS(const DevScene& S, const rtb_params& P, const ShadeD& sd, const rtb_material& m, float uPick,
+                            float r1, float r2, float4 um, Tally& tl)
+{
+	V3 zero = mk(0.0f, 0.0f, 0.0f);
+	if (m.flags & RTB_MAT_SPECULAR) return zero;
+	if (S.n_lights == 0) return zero;
+	float nl = (float)S.n_lights;
+	float pmf = 1.0f / nl;
+	int li = (int)(nl * uPick);
+	if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+	rtb_light L = S.lights[li];
+	V3 result = zero;
+	float pdf;
+	if (L.type == RTB_LIGHT_AREA)
+	{
+		V3 p = trianglePoint(S, L.triangle, r1, r2);
+		pdf = 1.0f / L.area;
+		V3 wi = p - sd.x;
+		float l = lengthSq(wi);
+		wi = normalize(wi);
+		float cs = selMax(dot(wi, sd.sN), 0.0f);
+		float cl = selMax(-dot(wi, triangleGNormal(S, L.triangle)), 0.0f);
+		float G = cs * cl / l;
+		if (G > 0.0f)
+		{
+			tl.shadow++;
+			if (sceneVisible<TRAV>(S, sd.x, p, P.epsilon, P.cull_rel, tl.sbox, tl.stri))
+			{
+				float pdfB = bsdfPdf(m, sd, wi);
+				float pdfL = (cl > 0.0f) ? ((pdf * pmf) * l / cl) : 0.0f;
+				float w = pdfL / (pdfL + pdfB);
+				result = result + ((((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G) * w) / (pmf * pdf));
+			}
+		}
+	}
+	else
+	{
+		V3 wi = uniformSampleSphere(r1, r2);
+		pdf = (float)(1.0 / (4.0 * RTB_PI_D));
+		V3 emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
+		float G = selMax(dot(wi, sd.sN), 0.0f);
+		if (G > 0.0f)
+		{
+			tl.shadow++;
+			if (sceneVisible<TRAV>(S, sd.x, sd.x + (wi * 10000.0f), P.epsilon, P.cull_rel, tl.sbox, tl.stri))
+				return ((bsdfEvaluate(S, m, sd, wi) * emitted) * G) / (pmf * pdf);
+		}
+	}
+	V3 f;
+	float pdfBsdf;
+	V3 wiB = bsdfSample(S, m, sd, um.x, um.y, um.z, f, pdfBsdf);
+	RayD r = mkRay(sd.x + (wiB * P.epsilon), wiB);
+	HitD h;
+	closestHit<TRAV>(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+	tl.closest++;
+	if (h.id != RTB_MISS_ID)
+	{
+		ShadeD sh;
+		calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), r, sh);
+		rtb_material mh = S.mats[sh.mat];
+		if (mh.flags & RTB_MAT_LIGHT)
+		{
+			V3 wi = sh.x - sd.x;
+			float dist2 = lengthSq(wi);
+			wi = normalize(wi);
+			float cl = selMax(0.0f, dot(mk(-wi.x, -wi.y, -wi.z), sh.sN));
+			float pdfL = (cl > 0.0f) ? ((pdf * pmf) * dist2 / cl) : 0.0f;
+			float w = pdfBsdf / (pdfBsdf + pdfL);
+			result = result + ((((f * mk(mh.emission)) * selMax(0.0f, dot(wiB, sd.sN))) * w) / pdfBsdf);
+		}
+	}
+	return result;
+}
+
+// ---------------------------------------------------------------------------------------
 // k_render: one thread per pixel (a warp = an 8x4 pixel tile); each thread runs its pixel's
 // samples back to back, so a lane whose path ends early immediately regenerates the next
 // sample instead of idling ("path regeneration").  The pixel's colour is summed in
@@ -224,7 +306,7 @@ __global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene 
 				bool done = true;
 				if (h.id == RTB_MISS_ID)
 				{
-					if (INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_ALBEDO)
+					if (INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_PATH_MIS || INTEGRATOR == RTB_INT_ALBEDO)
 						Lo = Lo + backgroundEval(S, ray.d); // un-weighted (Renderer.h:390)
 				}
 				else
@@ -240,7 +322,7 @@ __global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene 
 						rtb_material m = S.mats[sd.mat];
 						if (m.flags & RTB_MAT_LIGHT)
 						{
-							if (INTEGRATOR == RTB_INT_PATH)
+							if (INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_PATH_MIS)
 							{
 								if (canHitLight) Lo = Lo + (T * mk(m.emission));
 							}
@@ -254,7 +336,12 @@ __global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene 
 						else
 						{
 							float4 ua = rngBlock(P.seed, pixel, curS, 2u * (uint32_t)depth);
-							V3 direct = computeDirect<TRAV>(S, P, sd, m, ua.x, ua.y, ua.z, tl);
+							V3 direct;
+							if (INTEGRATOR == RTB_INT_PATH_MIS)
+								direct = computeDirectMIS<TRAV>(S, P, sd, m, ua.x, ua.y, ua.z,
+								                                rngBlock(P.seed, pixel, curS, RTB_RNG_MIS_BLOCK + (uint32_t)depth), tl);
+							else
+								direct = computeDirect<TRAV>(S, P, sd, m, ua.x, ua.y, ua.z, tl);
 							if (INTEGRATOR == RTB_INT_DIRECT)
 							{
 								Lo = direct; // Renderer.h:393-407

@@ -77,6 +77,21 @@ def cornell():
                         result_144=raysets.block_mean(r144), result_144_mean=r144.mean(axis=(0, 1)),
                         pixel_rmse_halves=np.sqrt(np.mean((a / 32.0 - bsum / 32.0) ** 2)))
     print("cornell halves mean", (a / 32).mean(axis=(0, 1)), (bsum / 32).mean(axis=(0, 1)), "r144", r144.mean(axis=(0, 1)))
+    cornell_mis()
+
+
+def cornell_mis():
+    """pathTrace with computeDirectMIS (Renderer.h:474-557; oracle/_ref/librtref_mis.so): two
+    independent 16-spp halves, 16x16-pixel block means."""
+    m = ref.RefScene("cornell-box", "_mis")
+    a, _, _ = m.render(16, 0, fresh=True)
+    bb, _, _ = m.render(16, 0, fresh=False)
+    b = bb - a
+    np.savez_compressed(os.path.join(HERE, "cornell_mis_blocks.npz"),
+                        half_a=raysets.block_mean(a / 16.0, 16).astype(np.float32),
+                        half_b=raysets.block_mean(b / 16.0, 16).astype(np.float32),
+                        mean_a=(a / 16.0).mean(axis=(0, 1)), mean_b=(b / 16.0).mean(axis=(0, 1)))
+    print("cornell MIS halves mean", (a / 16).mean(axis=(0, 1)), (b / 16).mean(axis=(0, 1)))
 
 
 def all_bsdfs():

@@ -244,6 +244,31 @@ def test_render_equals_the_oracle_sample_for_sample(rtb, oracle_mod, name):
     assert abs(g["shadow_rays"] / st["shadow_rays"] - 1) < 2e-3
 
 
+@pytest.mark.parametrize("name", ["synthetic", "cornell-box", "materialball"])
+def test_mis_estimator_equals_the_oracle_sample_for_sample(rtb, oracle_mod, name):
+    """RTB_INT_PATH_MIS (computeDirectMIS, Renderer.h:474-557): same uniforms on both sides."""
+    rt = gpu_scene(rtb, name)
+    spp = 2
+    rt.set_params(integrator=abi.INT_PATH_MIS)
+    rt.render(spp, 0)
+    img = rt.read_film()
+    want, st = oracle_mod.Oracle(rt.scene, integrator=abi.INT_PATH_MIS).render(spp)
+    assert not np.isnan(img).any()
+    close = np.isclose(img, want, rtol=2e-4, atol=1e-5).all(axis=-1)
+    assert close.mean() > 0.995, close.mean()
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / want.mean(axis=(0, 1)) - 1) < 5e-3)
+    g = rt.stats()
+    assert g["samples"] == st["samples"]
+    assert abs(g["closest_rays"] / st["closest_rays"] - 1) < 2e-3
+    assert abs(g["shadow_rays"] / st["shadow_rays"] - 1) < 2e-3
+    if name == "cornell-box":
+        gm = np.load(os.path.join(GOLDEN, "cornell_mis_blocks.npz"))
+        rt.clear()
+        rt.render(16, 0)
+        m = (rt.read_film() / 16).mean(axis=(0, 1))
+        assert np.all(np.abs(m / (0.5 * (gm["mean_a"] + gm["mean_b"])) - 1) < 0.01)
+
+
 @pytest.mark.parametrize("name,spp", [("synthetic", 3), ("cornell-box", 5), ("materialball", 3), ("MaterialsScene", 2)])
 def test_primary_hit_table_changes_no_bit_of_the_film(rtb, name, spp, monkeypatch):
     """params.primary_reuse traces each pixel's camera ray once per render call (all samples of a

@@ -172,6 +172,44 @@ def test_cornell_image_against_reference_statistics(cornell):
     assert 4.2 < rps < 4.45                # 4.33 rays per sample
 
 
+def test_mis_estimator_against_the_reference_statistics(oracle_mod):
+    """RTB_INT_PATH_MIS = pathTrace calling computeDirectMIS (Renderer.h:474-557, shipped switched
+    off).  Golden: two independent 16-spp halves of the reference built with that one call swapped
+    (oracle/_ref/librtref_mis.so, tests/golden/make_golden.py).  The estimator is NOT equivalent
+    to computeDirect (its weights are inconsistent, the image is ~15 % brighter), so agreeing with
+    the golden is a real check."""
+    g = np.load(os.path.join(GOLDEN, "cornell_mis_blocks.npz"))
+    spp = 8
+    o = oracle_mod.Oracle(flat_scene("cornell-box"), integrator=abi.INT_PATH_MIS)
+    film, st = o.render(spp)
+    img = film / spp
+    ref_mean = 0.5 * (g["mean_a"] + g["mean_b"])
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / ref_mean - 1) < 0.01)
+    plain = 0.5 * (np.load(os.path.join(GOLDEN, "cornell_ref_blocks.npz"))["mean_a"] +
+                   np.load(os.path.join(GOLDEN, "cornell_ref_blocks.npz"))["mean_b"])
+    assert np.all(ref_mean / plain > 1.1)                      # the two estimators really differ
+    blocks = raysets.block_mean(img, 16)
+    floor16 = np.sqrt(np.mean((g["half_a"] - g["half_b"]) ** 2) / 2)   # noise of one 16-spp block image
+    expect = floor16 * np.sqrt(16) * np.sqrt(1 / spp + 1 / 32)
+    rmse = np.sqrt(np.mean((blocks - 0.5 * (g["half_a"] + g["half_b"])) ** 2))
+    assert rmse < 3 * expect, (rmse, expect)
+    assert st["closest_rays"] > 1.5 * 2.69 * st["samples"]     # one BSDF-strategy probe ray per diffuse vertex
+
+
+def test_canonical_work_counter_matches_the_surveys_probe(cornell):
+    """canonical traversal of cornell-box = 24.2 box tests and 3.8 triangle tests per
+    closest-hit ray, 2.69 + 1.64 rays per sample.  The counter must not change the render."""
+    film, st = cornell.render_counts(1)
+    plain, st0 = cornell.render(1)
+    assert film.tobytes() == plain.tobytes()
+    assert (st["samples"], st["closest_rays"], st["shadow_rays"]) == (st0["samples"], st0["closest_rays"], st0["shadow_rays"])
+    assert abs(st["closest_box"] / st["closest_rays"] - 24.2) < 0.15
+    assert abs(st["closest_tri"] / st["closest_rays"] - 3.8) < 0.15
+    assert abs(st["closest_rays"] / st["samples"] - 2.69) < 0.02 and abs(st["shadow_rays"] / st["samples"] - 1.64) < 0.02
+    committed = json.load(open(os.path.join(os.path.dirname(GOLDEN), "..", "profiles", "canonical_counts.json")))["cornell-box"]
+    assert abs(committed["closest_box"] - st["closest_box"] / st["closest_rays"]) < 1e-9
+
+
 def test_render_is_thread_count_independent(oracle_mod):
     s = synthetic_scene()
     a, _ = oracle_mod.Oracle(s).render(3, threads=1)
