@@ -308,6 +308,17 @@ int rtb_clear(rtb_ctx* ctx);
  * kernels still run asynchronously).  Resumable: the RNG is keyed by (seed, pixel, sample
  * index), not by call order.                                                              */
 int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count);
+/* RayTracer::adaptiveRender (Renderer.h:679-749; shipped commented out at :880), one call = one
+ * render(): (1) adaptiveSampling (:583-641): init_samples (INIT_SAMPLES = 2, :23) paths per pixel,
+ * per 32x32 tile the variance of the pixel means around the tile mean; (2) weight = variance share,
+ * samples = max((int)(sqrt(weight) * max_samples), min_samples) (MAX_SAMPLES = 10240, MIN_SAMPLES = 1,
+ * :21-22, :649-653); (3) sampleTileWithWeight (:645-677): that many FRESH samples per pixel of the tile,
+ * their mean is splatted, i.e. the film sum grows by one mean image and SPP by one.  The initial samples
+ * only steer (sample indices 0..init-1), the splatted ones use indices init.. .  tile_samples /
+ * tile_variance (tilesX*tilesY entries, row-major 32x32 tiles; may be NULL) receive the plan.
+ * Wavefront schedule, single device per image.  Synchronous (the plan goes through the host).      */
+int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_samples, uint32_t max_samples,
+                        uint32_t* tile_samples, float* tile_variance);
 /* Film::film (Imaging.h:204): waits for the device and copies the running SUM (not the
  * mean; Film::save divides by SPP, Imaging.h:262-271) as width*height*3 floats (r,g,b per
  * pixel, row-major) to host memory; *spp receives Film::SPP.  Either may be NULL.         */

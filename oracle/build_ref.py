@@ -181,6 +181,11 @@ def stage_scenes():
         scene["envmap"] = "../materialball/envmap.hdr"
     _filter_scene_json(os.path.join(RTBASE, "MaterialsScene"), os.path.join(scenes_out, "MaterialsScene_env"),
                        env_edit, prefix="../MaterialsScene/")
+    # cornell-box at 256x256 (64 tiles): small enough for the reference's adaptiveRender in a test
+    def small_edit(scene):
+        scene["width"], scene["height"] = "256", "256"
+    _filter_scene_json(os.path.join(RTBASE, "cornell-box"), os.path.join(scenes_out, "cornell-box_256"),
+                       small_edit, prefix="../cornell-box/")
     # materialball with Mesh001's BSDF overridden
     for vname, props in MATERIALBALL_VARIANTS.items():
         def edit(scene, props=props):

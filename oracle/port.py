@@ -40,6 +40,7 @@ def lib():
         vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
         L.oracle_render.argtypes = [vp, vp, u32, u32, i32, vp, vp]
         L.oracle_render_counts.argtypes = [vp, vp, u32, u32, i32, vp, vp]
+        L.oracle_render_adaptive.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp, vp]
         L.oracle_primary_hits.argtypes = [vp, f32, vp, vp, vp]
         L.oracle_trace.argtypes = [vp, f32, i32, vp, u64, vp]
         L.oracle_visible.argtypes = [vp, f32, vp, u64, vp]
@@ -110,6 +111,16 @@ class Oracle:
         self.L.oracle_render(C.addressof(self.desc), C.addressof(self.params), int(spp_begin), int(spp), int(threads),
                              _p(film), _p(st))
         return film, dict(samples=int(st[0]), closest_rays=int(st[1]), shadow_rays=int(st[2]))
+
+    def render_adaptive(self, init_samples=2, min_samples=1, max_samples=10240, threads=None, film=None):
+        """RayTracer::adaptiveRender -> (film_sum + one mean image, tile_samples, tile_variance)"""
+        if film is None:
+            film = np.zeros((self.height, self.width, 3), "<f4")
+        ty, tx = (self.height + 31) // 32, (self.width + 31) // 32
+        samples, var = np.zeros((ty, tx), np.uint32), np.zeros((ty, tx), np.float32)
+        self.L.oracle_render_adaptive(C.addressof(self.desc), C.addressof(self.params), int(init_samples), int(min_samples),
+                                      int(max_samples), int(threads or os.cpu_count() or 1), _p(film), _p(samples), _p(var))
+        return film, samples, var
 
     def render_counts(self, spp, spp_begin=0, threads=None):
         """render() + the CANONICAL traversal work of every ray it traced."""

@@ -44,6 +44,7 @@ def _lib(variant=""):
         lib.ref_eval_light.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, vp, vp, vp]
         lib.ref_eval_background.argtypes = [vp, vp, C.c_uint64, vp]
         lib.ref_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        lib.ref_render_adaptive.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
         lib.ref_aov.argtypes = [vp, C.c_int, vp]
         lib.ref_tonemap.argtypes = [vp, vp, C.c_int, C.c_float, vp]
         lib.ref_gaussian_splat.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]
@@ -147,6 +148,15 @@ class RefScene:
         secs = C.c_double(0)
         total = self.lib.ref_render(self.h, int(spp), int(threads), 1 if fresh else 0, _p(film), C.addressof(secs))
         return film, total, secs.value
+
+    def render_adaptive(self, threads=0, fresh=True):
+        """One render() with adaptiveRender switched on -> (film_sum, tile_samples, tile_variance, seconds)."""
+        film = np.zeros((self.height, self.width, 3), "<f4")
+        ty, tx = (self.height + 31) // 32, (self.width + 31) // 32
+        var, cnt = np.zeros((ty, tx), "<f4"), np.zeros((ty, tx), np.int32)
+        secs = C.c_double(0)
+        self.lib.ref_render_adaptive(self.h, int(threads), 1 if fresh else 0, _p(film), _p(var), _p(cnt), C.addressof(secs))
+        return film, cnt, var, secs.value
 
     def aov(self, kind):
         k = {"albedo": 0, "normals": 1, "direct": 2}[kind]

@@ -395,6 +395,49 @@ int ref_render(void* handle, int spp, int threads, int fresh, float* film_sum, d
 	return h->rt->getSPP();
 }
 
+// One RayTracer::render() with the adaptive path switched on: film->incrementSPP() +
+// adaptiveRender() (Renderer.h:679-749, :876-881).  tile_var = tileVariances; tile_samples = the counts
+// sampleTileWithWeight derives (and prints) from tileWeights (:649-653).
+int ref_render_adaptive(void* handle, int threads, int fresh, float* film_sum, float* tile_var, int* tile_samples, double* seconds)
+{
+	RefScene* h = (RefScene*)handle;
+	ensureRT(h, threads);
+	if (fresh)
+	{
+		h->rt->clear();
+		for (int i = 0; i < h->rt->numProcs; i++) h->rt->samplers[i] = MTRandom();
+	}
+	std::streambuf* old = std::cout.rdbuf(nullptr); // sampleTileWithWeight prints one line per tile
+	auto t0 = std::chrono::steady_clock::now();
+	h->rt->film->incrementSPP();
+	h->rt->adaptiveRender();
+	auto t1 = std::chrono::steady_clock::now();
+	std::cout.rdbuf(old);
+	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	for (int i = 0; i < h->rt->totalTiles; i++)
+	{
+		if (tile_var) tile_var[i] = h->rt->tileVariances[i];
+		if (tile_samples)
+		{
+			float weight = h->rt->tileWeights[i];
+			weight = sqrt(weight);
+			int sample = (int)(weight * MAX_SAMPLES);
+			tile_samples[i] = sample > MIN_SAMPLES ? sample : MIN_SAMPLES;
+		}
+	}
+	if (film_sum)
+	{
+		size_t n = (size_t)h->rt->film->width * h->rt->film->height;
+		for (size_t i = 0; i < n; i++)
+		{
+			film_sum[i * 3] = h->rt->film->film[i].r;
+			film_sum[i * 3 + 1] = h->rt->film->film[i].g;
+			film_sum[i * 3 + 2] = h->rt->film->film[i].b;
+		}
+	}
+	return h->rt->getSPP();
+}
+
 // RayTracer::albedo (kind 0, Renderer.h:558-571) / viewNormals (kind 1, :572-581) /
 // direct() with a fresh seed-1 MTRandom (kind 2, :393-407) at pixel centres.
 int ref_aov(void* handle, int kind, float* out)

@@ -720,6 +720,10 @@ typedef struct {
 	tally_t tl;
 } job_t;
 
+/* oracle_render_adaptive: per 32x32 tile sample counts replacing spp_count (not re-entrant) */
+static const uint32_t* g_tile_count = NULL;
+static uint32_t g_tile_tx = 0;
+
 static int pixel_owned(const rtb_params* P, uint32_t W, uint32_t x, uint32_t y)
 {
 	if (P->partition == RTB_PART_TILE && P->part_world > 1)
@@ -747,7 +751,8 @@ static void* render_rows(void* arg)
 			v3 acc = V(0, 0, 0);
 			float* f = j->film + (size_t)pixel * 3;
 			if (!pixel_owned(P, W, x, (uint32_t)y)) continue;
-			for (smp = j->spp_begin; smp < j->spp_begin + j->spp_count; smp++)
+			uint32_t count = g_tile_count ? g_tile_count[((uint32_t)y >> 5) * g_tile_tx + (x >> 5)] : j->spp_count;
+			for (smp = j->spp_begin; smp < j->spp_begin + count; smp++)
 			{
 				ray_t r;
 				v3 c;
@@ -823,6 +828,76 @@ int oracle_render(const rtb_scene_desc* s, const rtb_params* P, uint32_t spp_beg
 	free(spans);
 	free(jobs);
 	free(th);
+	return 0;
+}
+
+/* ---------------- RayTracer::adaptiveRender, Renderer.h:583-749 ---------------------------
+ * adaptiveSampling (:583-641): INIT samples per pixel -> per 32x32 tile the variance of the pixel
+ * means around the tile mean, ((sum.r + sum.g + sum.b) / 3) / (n - 1), float arithmetic in pixel
+ * order like the reference; adaptiveRender (:709-719): weight = variance / total; sampleTileWithWeight
+ * (:645-677): samples = max((int)(sqrt(weight) * MAX), MIN) fresh samples per pixel, mean splatted.
+ * Sample indices: 0..init-1 steer, init.. are splatted (the reference's per-thread MTRandom simply
+ * runs on).  film_sum += one mean image.  tile_samples / tile_variance may be NULL.             */
+int oracle_render_adaptive(const rtb_scene_desc* s, const rtb_params* P, uint32_t init_samples, uint32_t min_samples,
+                           uint32_t max_samples, int threads, float* film_sum, uint32_t* tile_samples, float* tile_variance)
+{
+	uint32_t W = (uint32_t)s->camera.width, H = (uint32_t)s->camera.height;
+	uint32_t tx = (W + 31u) / 32u, ty = (H + 31u) / 32u, nT = tx * ty, t;
+	size_t npx = (size_t)W * H, i;
+	float* est = (float*)calloc(npx * 3, sizeof(float));
+	float* var = (float*)calloc(nT, sizeof(float));
+	uint32_t* cnt = (uint32_t*)calloc(nT, sizeof(uint32_t));
+	uint32_t maxCount = 0;
+	float total = 0.0f;
+	uint64_t st[3];
+	oracle_render(s, P, 0, init_samples, threads, est, st);
+	for (t = 0; t < nT; t++)
+	{
+		uint32_t x0 = (t % tx) * 32u, y0 = (t / tx) * 32u, x1 = x0 + 32u < W ? x0 + 32u : W, y1 = y0 + 32u < H ? y0 + 32u : H, x, y;
+		uint32_t n = (x1 - x0) * (y1 - y0);
+		v3 sum = V(0, 0, 0), gt, sq = V(0, 0, 0);
+		for (y = y0; y < y1; y++)
+			for (x = x0; x < x1; x++)
+			{
+				const float* e = est + ((size_t)y * W + x) * 3;
+				sum = add(sum, dvd(V(e[0], e[1], e[2]), (float)init_samples));
+			}
+		gt = dvd(sum, (float)n);
+		for (y = y0; y < y1; y++)
+			for (x = x0; x < x1; x++)
+			{
+				const float* e = est + ((size_t)y * W + x) * 3;
+				v3 d = sub(dvd(V(e[0], e[1], e[2]), (float)init_samples), gt);
+				sq = add(sq, mul(d, d));
+			}
+		var[t] = ((sq.x + sq.y + sq.z) / 3.0f) / (float)(n - 1u);
+	}
+	for (t = 0; t < nT; t++) total += var[t];
+	for (t = 0; t < nT; t++)
+	{
+		float w = (total > 0.0f) ? var[t] / total : 0.0f;
+		int sample;
+		w = sqrtf(w);
+		sample = (int)(w * (float)max_samples);
+		cnt[t] = (uint32_t)(sample > (int)min_samples ? sample : (int)min_samples);
+		if (cnt[t] > maxCount) maxCount = cnt[t];
+	}
+	/* fresh samples init .. init + count(tile) - 1 */
+	memset(est, 0, npx * 3 * sizeof(float));
+	g_tile_count = cnt, g_tile_tx = tx;
+	oracle_render(s, P, init_samples, maxCount, threads, est, st);
+	g_tile_count = NULL;
+	for (i = 0; i < npx; i++)
+	{
+		uint32_t x = (uint32_t)(i % W), y = (uint32_t)(i / W);
+		float k = (float)cnt[(y >> 5) * tx + (x >> 5)];
+		film_sum[i * 3] += est[i * 3] / k, film_sum[i * 3 + 1] += est[i * 3 + 1] / k, film_sum[i * 3 + 2] += est[i * 3 + 2] / k;
+	}
+	if (tile_samples) memcpy(tile_samples, cnt, nT * sizeof(uint32_t));
+	if (tile_variance) memcpy(tile_variance, var, nT * sizeof(float));
+	free(est);
+	free(var);
+	free(cnt);
 	return 0;
 }
 

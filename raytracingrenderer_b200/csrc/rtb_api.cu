@@ -83,6 +83,11 @@ struct rtb_ctx
 	uint32_t wfCtrlEntries = 0;
 	WfGlobal* wfGlobal = nullptr;
 	uint32_t* wfTiles = nullptr;
+	long long* accumScratch = nullptr; // rtb_render_adaptive: per-phase sums
+	uint32_t* wfTilesAdaptive = nullptr; // 32 sub-tiles (8x4 pixels) per 32x32 tile, 0xFFFFFFFF outside the image
+	unsigned long long* adaptJobBase = nullptr;
+	uint32_t* adaptSamples = nullptr;
+	float* adaptVariance = nullptr;
 	float4* wfPrimary = nullptr; // per-pixel primary hits (params.primary_reuse), rebuilt by every render call
 	int primaryPasses = 2; // profiles/r01_primary_reuse.txt
 	uint32_t wfTileCount = 0;
@@ -140,6 +145,13 @@ void freeScene(rtb_ctx* ctx)
 	if (ctx->wfGlobal) cudaFree(ctx->wfGlobal);
 	if (ctx->wfTiles) cudaFree(ctx->wfTiles);
 	if (ctx->wfPrimary) cudaFree(ctx->wfPrimary);
+	if (ctx->accumScratch) cudaFree(ctx->accumScratch);
+	if (ctx->wfTilesAdaptive) cudaFree(ctx->wfTilesAdaptive);
+	if (ctx->adaptJobBase) cudaFree(ctx->adaptJobBase);
+	if (ctx->adaptSamples) cudaFree(ctx->adaptSamples);
+	if (ctx->adaptVariance) cudaFree(ctx->adaptVariance);
+	ctx->accumScratch = nullptr, ctx->wfTilesAdaptive = nullptr, ctx->adaptJobBase = nullptr, ctx->adaptSamples = nullptr;
+	ctx->adaptVariance = nullptr;
 	if (ctx->accum) cudaFree(ctx->accum);
 	ctx->wfState = nullptr, ctx->wfStateBytes = 0;
 	ctx->wfCtrl = nullptr, ctx->wfCtrlEntries = 0;
@@ -299,11 +311,17 @@ static int resolveFilm(rtb_ctx* ctx)
 // number of iterations depends on the paths, so launches are enqueued in batches sized from the
 // measured job rate; between batches the host reads {jobs claimed, slots alive} (a few dozen
 // bytes + a sync, a handful of times per call).  Work is forked from / joined to ctx->stream.
-static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
+struct AdaptivePlan
+{
+	unsigned long long totalJobs; // sum over tiles of 1024 * samples
+	uint32_t nTiles32;
+};
+
+static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count, const AdaptivePlan* plan = nullptr)
 {
 	const rtb_params& P = ctx->params;
 	uint32_t sFirst = spp_begin, sStep = 1, sCount = spp_count;
-	if (P.partition == RTB_PART_SPP && P.part_world > 1)
+	if (!plan && P.partition == RTB_PART_SPP && P.part_world > 1)
 	{
 		uint32_t w = (uint32_t)P.part_world, r = (uint32_t)P.part_rank;
 		sFirst = spp_begin + (r + w - (spp_begin % w)) % w;
@@ -339,7 +357,8 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		memcpy(ctx->wfTilePart, part, sizeof(part));
 	}
 	if (ctx->wfTileCount == 0) return RTB_OK;
-	unsigned long long totalJobs = (unsigned long long)ctx->wfTileCount * 32ull * sCount;
+	unsigned long long totalJobs = plan ? plan->totalJobs : (unsigned long long)ctx->wfTileCount * 32ull * sCount;
+	if (totalJobs == 0) return RTB_OK;
 	// ---- pools
 	if (!ctx->poolStreams[0])
 	{
@@ -414,12 +433,14 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 		a.shO = base + n * 4 + off, a.shD = base + n * 5 + off, a.shC = base + n * 6 + off;
 		a.ctrl = ctx->wfCtrl + (size_t)k * bound;
 		a.glob = ctx->wfGlobal;
-		a.tileList = ctx->wfTiles;
+		a.tileList = plan ? ctx->wfTilesAdaptive : ctx->wfTiles;
+		a.tileJobBase = plan ? ctx->adaptJobBase : nullptr;
+		a.nTiles32 = plan ? plan->nTiles32 : 0u;
 		a.primary = P.primary_reuse ? ctx->wfPrimary : nullptr;
 		a.primaryPasses = (uint32_t)ctx->primaryPasses;
 		a.counters = ctx->counters;
 		a.accum = ctx->accum;
-		a.nSlots = perPool, a.nTiles = ctx->wfTileCount;
+		a.nSlots = perPool, a.nTiles = plan ? plan->nTiles32 * 32u : ctx->wfTileCount;
 		a.width = ctx->width, a.height = ctx->height;
 		a.sFirst = sFirst, a.sStep = sStep, a.sCount = sCount;
 		a.totalJobs = totalJobs;
@@ -481,13 +502,20 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 					RTB_TRAV_SWITCH(ti, k_wf_extend<TR><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it));
 				}
 				if (timed) cudaEventRecord(se.e[1], st);
+#define RTB_SHADE_LAUNCH(INTEG)                                                                      \
+	do                                                                                               \
+	{                                                                                                \
+		if (A[k].primary) k_wf_shade<INTEG, true><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);      \
+		else k_wf_shade<INTEG, false><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);                  \
+	} while (0)
 				switch (P.integrator)
 				{
-				case RTB_INT_DIRECT: k_wf_shade<RTB_INT_DIRECT><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
-				case RTB_INT_ALBEDO: k_wf_shade<RTB_INT_ALBEDO><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
-				case RTB_INT_NORMALS: k_wf_shade<RTB_INT_NORMALS><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
-				default: k_wf_shade<RTB_INT_PATH><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it); break;
+				case RTB_INT_DIRECT: RTB_SHADE_LAUNCH(RTB_INT_DIRECT); break;
+				case RTB_INT_ALBEDO: RTB_SHADE_LAUNCH(RTB_INT_ALBEDO); break;
+				case RTB_INT_NORMALS: RTB_SHADE_LAUNCH(RTB_INT_NORMALS); break;
+				default: RTB_SHADE_LAUNCH(RTB_INT_PATH); break;
 				}
+#undef RTB_SHADE_LAUNCH
 				ctx->launches += 2;
 				if (timed) cudaEventRecord(se.e[2], st);
 				if (shadows)
@@ -840,6 +868,88 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	                                                           : renderWavefront(ctx, spp_begin, spp_count);
 	if (rc) return rc;
 	ctx->spp += spp_count;
+	return RTB_OK;
+}
+
+// RayTracer::adaptiveRender (Renderer.h:679-749) on the wavefront schedule.
+int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_samples, uint32_t max_samples, uint32_t* tile_samples,
+                        float* tile_variance)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_adaptive before rtb_upload_scene");
+	const rtb_params& P = ctx->params;
+	if (init_samples < 1 || min_samples < 1 || max_samples < min_samples || max_samples > (1u << 20))
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: need 1 <= init, 1 <= min <= max <= 2^20");
+	if (P.scheduler != RTB_SCHED_WAVEFRONT || P.integrator == RTB_INT_PATH_MIS)
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive runs on the wavefront schedule");
+	if (P.partition != RTB_PART_NONE && P.part_world > 1)
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: the tile sample counts come from the whole image; use one device per image");
+	if (int rc = bind(ctx)) return rc;
+	const uint32_t W = ctx->width, H = ctx->height, t32x = (W + 31) / 32, t32y = (H + 31) / 32, nT = t32x * t32y;
+	const size_t accBytes = (size_t)W * H * 3 * sizeof(long long);
+	if (!ctx->accumScratch)
+	{
+		CK(cudaMalloc((void**)&ctx->accumScratch, accBytes));
+		CK(cudaMalloc((void**)&ctx->adaptJobBase, (size_t)(nT + 1) * sizeof(unsigned long long)));
+		CK(cudaMalloc((void**)&ctx->adaptSamples, (size_t)nT * sizeof(uint32_t)));
+		CK(cudaMalloc((void**)&ctx->adaptVariance, (size_t)nT * sizeof(float)));
+		std::vector<uint32_t> sub((size_t)nT * 32);
+		uint32_t tilesX = (W + 7) / 8, tilesY = (H + 3) / 4;
+		for (uint32_t t = 0; t < nT; t++)
+			for (uint32_t k = 0; k < 32; k++)
+			{
+				uint32_t tx = (t % t32x) * 4 + (k & 3u), ty = (t / t32x) * 8 + (k >> 2);
+				sub[(size_t)t * 32 + k] = (tx < tilesX && ty < tilesY) ? ty * tilesX + tx : 0xFFFFFFFFu;
+			}
+		CK(cudaMalloc((void**)&ctx->wfTilesAdaptive, sub.size() * sizeof(uint32_t)));
+		CK(cudaMemcpy(ctx->wfTilesAdaptive, sub.data(), sub.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
+	// ---- phase 1 (adaptiveSampling): init_samples per pixel into the scratch sums, tile variances
+	long long* film = ctx->accum;
+	std::vector<unsigned long long> base(nT + 1);
+	for (uint32_t t = 0; t <= nT; t++) base[t] = (unsigned long long)t * 1024ull * init_samples;
+	CK(cudaMemsetAsync(ctx->accumScratch, 0, accBytes, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->adaptJobBase, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	AdaptivePlan plan = {base[nT], nT};
+	ctx->accum = ctx->accumScratch;
+	int rc = renderWavefront(ctx, 0, init_samples, &plan);
+	ctx->accum = film;
+	if (rc) return rc;
+	k_tile_variance<<<nT, 256, 0, ctx->stream>>>(ctx->accumScratch, W, H, init_samples, ctx->adaptVariance);
+	ctx->launches++;
+	std::vector<float> var(nT);
+	CK(cudaMemcpyAsync(var.data(), ctx->adaptVariance, nT * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	// ---- weights and sample counts exactly like adaptiveRender / sampleTileWithWeight (float arithmetic)
+	float total = 0.0f;
+	for (float v : var) total += v;
+	std::vector<uint32_t> samples(nT);
+	for (uint32_t t = 0; t < nT; t++)
+	{
+		float w = (total > 0.0f) ? var[t] / total : 0.0f;
+		w = sqrtf(w);
+		int sample = (int)(w * (float)max_samples);
+		samples[t] = (uint32_t)((sample > (int)min_samples) ? sample : (int)min_samples);
+	}
+	base[0] = 0;
+	for (uint32_t t = 0; t < nT; t++) base[t + 1] = base[t] + 1024ull * samples[t];
+	// ---- phase 2 (sampleTileWithWeight): fresh samples (indices init_samples...), film += their mean
+	CK(cudaMemsetAsync(ctx->accumScratch, 0, accBytes, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->adaptJobBase, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->adaptSamples, samples.data(), nT * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	plan.totalJobs = base[nT];
+	ctx->accum = ctx->accumScratch;
+	rc = renderWavefront(ctx, init_samples, max_samples, &plan);
+	ctx->accum = film;
+	if (rc) return rc;
+	k_adaptive_merge<<<(W * H + 255) / 256, 256, 0, ctx->stream>>>(ctx->accumScratch, ctx->accum, W, H, ctx->adaptSamples);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(ctx->stream)); // `base` / `samples` are pageable host memory
+	ctx->filmDirty = true;
+	ctx->spp += 1; // Film::incrementSPP once per render() (Renderer.h:878)
+	if (tile_samples) memcpy(tile_samples, samples.data(), nT * sizeof(uint32_t));
+	if (tile_variance) memcpy(tile_variance, var.data(), nT * sizeof(float));
 	return RTB_OK;
 }
 

@@ -66,6 +66,8 @@ struct WfArgs
 	WfCtrl* ctrl;  // [iterations], zeroed before the render
 	WfGlobal* glob;
 	const uint32_t* tileList; // owned 8x4 tiles (row-major tile ids)
+	const unsigned long long* tileJobBase; // adaptive plan: first job of every 32x32 tile (+ total), or NULL
+	uint32_t nTiles32;                     //                number of 32x32 tiles
 	const float4* primary;    // per-pixel primary hit (bits(id), t, alpha, beta), or NULL: trace every camera ray
 	uint32_t primaryPasses;   // fresh primary vertices a shade thread may take on per launch
 	unsigned long long* counters;
@@ -91,6 +93,7 @@ RTB_DEV bool wfJobPixel(const WfArgs& A, uint32_t q, uint32_t& px, uint32_t& py)
 {
 	uint32_t tilesX = (A.width + 7u) >> 3;
 	uint32_t tile = __ldg(A.tileList + (q >> 5)), lane = q & 31u;
+	if (tile == 0xFFFFFFFFu) return false; // adaptive plan: sub-tile outside the image
 	px = (tile % tilesX) * 8u + (lane & 7u);
 	py = (tile / tilesX) * 4u + (lane >> 3);
 	return px < A.width && py < A.height;
@@ -99,8 +102,26 @@ RTB_DEV bool wfJobPixel(const WfArgs& A, uint32_t q, uint32_t& px, uint32_t& py)
 // job j -> (sample ordinal n, pixel ordinal q); false when q is a padding pixel of an edge tile.
 RTB_DEV bool wfDecodeJob(const WfArgs& A, unsigned long long j, uint32_t& n, uint32_t& q)
 {
-	uint32_t Q = A.nTiles * 32u;
-	n = (uint32_t)(j / Q), q = (uint32_t)(j % Q);
+	if (A.tileJobBase)
+	{
+		// adaptive plan (RayTracer::sampleTileWithWeight, Renderer.h:645-677): every 32x32 tile has
+		// its own sample count; its jobs are 1024 pixel slots x count, sample-major
+		uint32_t lo = 0, hi = A.nTiles32;
+		while (hi - lo > 1u)
+		{
+			uint32_t mid = (lo + hi) >> 1;
+			if (__ldg(A.tileJobBase + mid) <= j) lo = mid;
+			else hi = mid;
+		}
+		unsigned long long l = j - __ldg(A.tileJobBase + lo);
+		n = (uint32_t)(l >> 10);
+		q = lo * 1024u + (uint32_t)(l & 1023ull);
+	}
+	else
+	{
+		uint32_t Q = A.nTiles * 32u;
+		n = (uint32_t)(j / Q), q = (uint32_t)(j % Q);
+	}
 	uint32_t px, py;
 	return wfJobPixel(A, q, px, py);
 }
@@ -161,6 +182,77 @@ RTB_DEV bool wfClaimJob(const WfArgs& A, bool need, uint32_t& n, uint32_t& q)
 	return got;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// RayTracer::adaptiveSampling (Renderer.h:583-641): per 32x32 tile, the variance of the pixels'
+// initial estimates around the tile mean: ((sum_r + sum_g + sum_b) / 3) / (n - 1).  One block per
+// tile; sums in double from the exact fixed-point accumulators.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tile_variance(const long long* __restrict__ accum, uint32_t width, uint32_t height, uint32_t initSamples,
+                                                       float* __restrict__ variance)
+{
+	__shared__ double sRed[3][8];
+	__shared__ double sMean[3];
+	uint32_t t32x = (width + 31u) >> 5;
+	uint32_t x0 = (blockIdx.x % t32x) * 32u, y0 = (blockIdx.x / t32x) * 32u;
+	uint32_t w = min(32u, width - x0), h = min(32u, height - y0), n = w * h;
+	const double scale = 1.0 / (4294967296.0 * (double)initSamples);
+	double v[4][3];
+	double s0 = 0, s1 = 0, s2 = 0;
+	for (int k = 0; k < 4; k++)
+	{
+		uint32_t i = threadIdx.x + k * 256u;
+		uint32_t lx = i & 31u, ly = i >> 5;
+		bool in = lx < w && ly < h;
+		for (int c = 0; c < 3; c++) v[k][c] = in ? (double)accum[((size_t)(y0 + ly) * width + x0 + lx) * 3 + c] * scale : 0.0;
+		s0 += v[k][0], s1 += v[k][1], s2 += v[k][2];
+	}
+	auto blockSum = [&](double a, double b, double c, double* out) {
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+			b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+			c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+		}
+		__syncthreads();
+		if ((threadIdx.x & 31u) == 0) sRed[0][threadIdx.x >> 5] = a, sRed[1][threadIdx.x >> 5] = b, sRed[2][threadIdx.x >> 5] = c;
+		__syncthreads();
+		for (int ch = 0; ch < 3; ch++)
+		{
+			double t = 0;
+			for (int k = 0; k < 8; k++) t += sRed[ch][k];
+			out[ch] = t;
+		}
+	};
+	double tot[3];
+	blockSum(s0, s1, s2, tot);
+	if (threadIdx.x == 0)
+		for (int c = 0; c < 3; c++) sMean[c] = tot[c] / (double)n;
+	__syncthreads();
+	double d0 = 0, d1 = 0, d2 = 0;
+	for (int k = 0; k < 4; k++)
+	{
+		uint32_t i = threadIdx.x + k * 256u;
+		if ((i & 31u) < w && (i >> 5) < h)
+		{
+			double a = v[k][0] - sMean[0], b = v[k][1] - sMean[1], c = v[k][2] - sMean[2];
+			d0 += a * a, d1 += b * b, d2 += c * c;
+		}
+	}
+	blockSum(d0, d1, d2, tot);
+	if (threadIdx.x == 0) variance[blockIdx.x] = (float)(((tot[0] + tot[1] + tot[2]) / 3.0) / (double)(n - 1u));
+}
+
+// film += (sum of the tile's `count` samples) / count  (sampleTileWithWeight's col / sample, then splat)
+__global__ void __launch_bounds__(256) k_adaptive_merge(const long long* __restrict__ scratch, long long* __restrict__ accum, uint32_t width,
+                                                        uint32_t height, const uint32_t* __restrict__ tileSamples)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= width * height) return;
+	uint32_t x = i % width, y = i / width, t32x = (width + 31u) >> 5;
+	double inv = 1.0 / (double)tileSamples[(y >> 5) * t32x + (x >> 5)];
+	for (int c = 0; c < 3; c++) accum[(size_t)i * 3 + c] += __double2ll_rn((double)scratch[(size_t)i * 3 + c] * inv);
+}
 
 // The primary-hit table: Scene::traverse of the ONE camera ray of every pixel (8x4 pixels per warp),
 // computed at the start of each render call when params.primary_reuse is set.
@@ -470,13 +562,14 @@ RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& 
 	return true;
 }
 
-template <int INTEGRATOR>
+template <int INTEGRATOR, bool REUSE>
 __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
 	const rtb_params& P = A.P;
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
 	const uint32_t lane = threadIdx.x & 31u;
 	uint32_t nAlive = 0, nDone = 0, phase = 0;
+	__shared__ float4 sStage[3][128]; // the thread's shadow-ray record waits here across the reservation barriers (12 registers)
 	__shared__ uint32_t sCountS[2][4], sCountJ[2][4];
 	__shared__ unsigned int sBaseS[2];
 	__shared__ unsigned long long sBaseJ[2];
@@ -505,7 +598,6 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 		for (uint32_t pass = 0;; pass++)
 		{
 			bool done = false, haveShadow = false;
-			float4 sO, sD, sC;
 			if (haveVertex)
 			{
 				uint32_t flags = __float_as_uint(rd.w);
@@ -561,9 +653,9 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 								dir = normalize(dir);
 								V3 o = p1 + (dir * P.epsilon);
 								V3 c = (INTEGRATOR == RTB_INT_DIRECT) ? contrib : (T * contrib);
-								sO = make_float4(o.x, o.y, o.z, maxT);
-								sD = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
-								sC = make_float4(c.x, c.y, c.z, 0.0f);
+								sStage[0][threadIdx.x] = make_float4(o.x, o.y, o.z, maxT);
+								sStage[1][threadIdx.x] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
+								sStage[2][threadIdx.x] = make_float4(c.x, c.y, c.z, 0.0f);
 								haveShadow = true;
 							}
 							if (INTEGRATOR == RTB_INT_PATH && !((int)depth > P.max_depth))
@@ -598,7 +690,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 			// two ballots, two barriers, one atomic per counter and block (shared words are
 			// double-buffered, so the next pass may write while stragglers still read)
 			if (done) nDone++;
-			const uint32_t warp = threadIdx.x >> 5, ph = (phase++) & 1u;
+			const uint32_t warp = threadIdx.x >> 5, ph = REUSE ? ((phase++) & 1u) : (round & 1u);
 			unsigned mS = __ballot_sync(0xFFFFFFFFu, haveShadow), mJ = __ballot_sync(0xFFFFFFFFu, done);
 			if (lane == 0) sCountS[ph][warp] = __popc(mS), sCountJ[ph][warp] = __popc(mJ);
 			__syncthreads();
@@ -617,7 +709,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 			{
 				uint32_t at = sBaseS[ph] + __popc(mS & ((1u << lane) - 1u));
 				for (uint32_t w = 0; w < warp; w++) at += sCountS[ph][w];
-				A.shO[at] = sO, A.shD[at] = sD, A.shC[at] = sC;
+				A.shO[at] = sStage[0][threadIdx.x], A.shD[at] = sStage[1][threadIdx.x], A.shC[at] = sStage[2][threadIdx.x];
 			}
 			// ---- regeneration: finished paths take the next jobs of the render (the rare lanes that
 			// drew a padding pixel of an edge tile retry warp-wise)
@@ -638,8 +730,8 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 				if (__any_sync(0xFFFFFFFFu, retry)) fresh = wfClaimJob(A, retry, n, q) || fresh;
 			}
 			if (done && !fresh) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-			bool morePasses = A.primary != nullptr && pass + 1u < A.primaryPasses;
-			if (!morePasses)
+			// REUSE = false compiles to the single-pass kernel (no loop-carried vertex state)
+			if (!REUSE || pass + 1u >= A.primaryPasses)
 			{
 				if (fresh)
 				{

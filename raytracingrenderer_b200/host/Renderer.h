@@ -14,6 +14,7 @@
 //                        (presentFilmToCanvas, Renderer.h:69-80); switch it off for batch work
 //   params()             the rtb_params the GPU uses (defaults = the reference's constants)
 //   syncFilm()           copy the GPU film sums into film->film (done by saveHDR automatically)
+//   renderAdaptive()     render() with the original's commented-out adaptiveRender() switched on (:880)
 #pragma once
 
 #include "Core.h"
@@ -35,6 +36,9 @@
 
 const int TILE_SIZE = 32; // RTBase/Renderer.h:18 (the tile partition of rtb_params uses the same size)
 const int MAX_DEPTH = 4;  // RTBase/Renderer.h:20 -> rtb_params.max_depth
+const int MAX_SAMPLES = 10240; // RTBase/Renderer.h:21-23 -> the arguments of rtb_render_adaptive
+const int MIN_SAMPLES = 1;
+const int INIT_SAMPLES = 2;
 
 class RayTracer
 {
@@ -44,6 +48,9 @@ public:
 	Film* film = NULL;
 	MTRandom* samplers = NULL; // kept for source compatibility; the GPU uses a counter-based RNG
 	int numProcs = 0;          // number of GPUs driving this RayTracer (1)
+	int tilesNumX = 0, tilesNumY = 0, totalTiles = 0;  // 32x32 tiles (RTBase/Renderer.h:40, 57-61)
+	std::vector<float> tileVariances, tileWeights;     // filled by adaptiveRender()
+	std::vector<uint32_t> tileSamples;                 // the counts sampleTileWithWeight derives (:649-653)
 
 	void init(Scene* _scene, GamesEngineeringBase::Window* _canvas)
 	{
@@ -57,6 +64,12 @@ public:
 		film->init((unsigned int)scene->camera.width, (unsigned int)scene->camera.height, new BoxFilter());
 		numProcs = 1;
 		samplers = new MTRandom[1];
+		tilesNumX = (film->width + TILE_SIZE - 1) / TILE_SIZE;
+		tilesNumY = (film->height + TILE_SIZE - 1) / TILE_SIZE;
+		totalTiles = tilesNumX * tilesNumY;
+		tileVariances = std::vector<float>(totalTiles, 0.0f);
+		tileWeights = std::vector<float>(totalTiles, 0.0f);
+		tileSamples = std::vector<uint32_t>(totalTiles, 0u);
 		check(rtb_create(device, &ctx), "rtb_create");
 		rtb_default_params(&prm);
 		prm.max_depth = MAX_DEPTH;
@@ -95,6 +108,24 @@ public:
 		check(rtb_render(ctx, begin, (uint32_t)n), "rtb_render");
 		filmOnHost = false;
 		if (presentEveryFrame && canvas) presentFilmToCanvas();
+	}
+	// RTBase/Renderer.h:679-749.  Like the original it is meant to be called from render() in place of
+	// pathTracerTileBased() (:880), after film->incrementSPP(); renderAdaptive() does both.
+	void adaptiveRender()
+	{
+		check(rtb_render_adaptive(ctx, INIT_SAMPLES, MIN_SAMPLES, MAX_SAMPLES, tileSamples.data(), tileVariances.data()),
+		      "rtb_render_adaptive");
+		check(rtb_set_spp(ctx, (uint32_t)film->SPP), "rtb_set_spp");
+		float totalVariance = 0.0f;
+		for (float v : tileVariances) totalVariance += v;
+		for (int i = 0; i < totalTiles; i++) tileWeights[i] = (totalVariance > 0.0f) ? tileVariances[i] / totalVariance : 0.0f;
+		filmOnHost = false;
+		if (presentEveryFrame && canvas) presentFilmToCanvas();
+	}
+	void renderAdaptive()
+	{
+		film->incrementSPP();
+		adaptiveRender();
 	}
 	void presentFilmToCanvas()
 	{

@@ -78,6 +78,18 @@ def cornell():
                         pixel_rmse_halves=np.sqrt(np.mean((a / 32.0 - bsum / 32.0) ** 2)))
     print("cornell halves mean", (a / 32).mean(axis=(0, 1)), (bsum / 32).mean(axis=(0, 1)), "r144", r144.mean(axis=(0, 1)))
     cornell_mis()
+    cornell_adaptive()
+
+
+def cornell_adaptive():
+    """RayTracer::adaptiveRender (Renderer.h:679-749) of the unmodified reference on cornell-box at
+    256x256 (scenes/_staged/cornell-box_256: the bundled scene.json with width/height edited)."""
+    s = ref.RefScene("cornell-box_256")
+    s.flatten(os.path.join(HERE, "cornell-box_256.rtbs"))
+    film, cnt, var, secs = s.render_adaptive()
+    np.savez_compressed(os.path.join(HERE, "cornell256_adaptive.npz"), tile_samples=cnt, tile_variance=var,
+                        film_blocks=raysets.block_mean(film, 8).astype(np.float32), film_mean=film.mean(axis=(0, 1)))
+    print("cornell 256 adaptive: %.1f s, mean count %.1f, film mean" % (secs, cnt.mean()), film.mean(axis=(0, 1)))
 
 
 def cornell_mis():

@@ -269,6 +269,67 @@ def test_mis_estimator_equals_the_oracle_sample_for_sample(rtb, oracle_mod, name
         assert np.all(np.abs(m / (0.5 * (gm["mean_a"] + gm["mean_b"])) - 1) < 0.01)
 
 
+def test_adaptive_render_equals_the_oracle_and_the_reference(rtb, oracle_mod):
+    """rtb_render_adaptive = RayTracer::adaptiveRender (Renderer.h:583-749).  Against the oracle the
+    uniforms are identical: tile variances to 1e-3, sample counts equal up to one sample where the
+    float rounding of the variance sums differs, pixels of equally-sampled tiles sample for sample.
+    Against the reference's own run (golden): the statistics of test_oracle_cpu."""
+    g = np.load(os.path.join(GOLDEN, "cornell256_adaptive.npz"))
+    s = abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box_256.rtbs"))
+    rt = rtb.RayTracer(0)
+    rt.init(s)
+    cnt, var = rt.adaptiveRender(2, 1, 10240)
+    img = rt.read_film()
+    assert rt.getSPP() == 1
+    want, ocnt, ovar = oracle_mod.Oracle(s).render_adaptive(2, 1, 10240)
+    assert np.allclose(var, ovar, rtol=1e-3, atol=1e-7)
+    d = np.abs(cnt.astype(np.int64) - ocnt.astype(np.int64))
+    assert d.max() <= 1 and (d == 0).mean() > 0.9, (d.max(), (d == 0).mean())
+    same = np.kron(d == 0, np.ones((32, 32), bool))[:rt.height, :rt.width]
+    close = np.isclose(img, want, rtol=5e-4, atol=1e-5).all(axis=-1)
+    assert close[same].mean() > 0.99, close[same].mean()
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / want.mean(axis=(0, 1)) - 1) < 5e-3)
+    st = rt.stats()
+    assert st["samples"] == 256 * 256 * 2 + int(cnt.astype(np.int64).sum()) * 1024
+    # the reference itself
+    big = g["tile_variance"] > 0.01 * g["tile_variance"].max()
+    assert np.all(np.abs(var[big] / g["tile_variance"][big] - 1) < 0.02)
+    assert np.all(np.abs(cnt[big].astype(float) / g["tile_samples"][big] - 1) < 0.01)
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / g["film_mean"] - 1) < 0.01)
+    # a second call adds a second mean image; primary_reuse off gives the same bits
+    rt.adaptiveRender(2, 1, 10240)
+    assert rt.getSPP() == 2
+    assert np.all(np.abs(rt.read_film().mean(axis=(0, 1)) / (2 * g["film_mean"]) - 1) < 0.01)
+    rt.clear()
+    rt.set_params(primary_reuse=0)
+    cnt0, _ = rt.adaptiveRender(2, 1, 10240)
+    assert np.array_equal(cnt0, cnt) and np.array_equal(rt.read_film(), img)
+    # argument / state errors
+    with pytest.raises(rtb.RtbError):
+        rt.adaptiveRender(0, 1, 16)
+    rt.set_params(scheduler=abi.SCHED_MEGAKERNEL)
+    with pytest.raises(rtb.RtbError):
+        rt.adaptiveRender(2, 1, 16)
+    rt.close()
+
+
+def test_adaptive_render_on_a_ragged_image(rtb, oracle_mod):
+    """Width and height that are not multiples of 32 (edge tiles, padded pixel slots)."""
+    s = synthetic_scene(width=100, height=70)
+    rt = rtb.RayTracer(0)
+    rt.init(s)
+    cnt, var = rt.adaptiveRender(2, 1, 64)
+    img = rt.read_film()
+    want, ocnt, ovar = oracle_mod.Oracle(s).render_adaptive(2, 1, 64)
+    assert cnt.shape == ((rt.height + 31) // 32, (rt.width + 31) // 32)
+    assert np.allclose(var, ovar, rtol=1e-3, atol=1e-7)
+    d = np.abs(cnt.astype(np.int64) - ocnt.astype(np.int64))
+    assert d.max() <= 1
+    assert not np.isnan(img).any()
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / want.mean(axis=(0, 1)) - 1) < 2e-2)
+    rt.close()
+
+
 @pytest.mark.parametrize("name,spp", [("synthetic", 3), ("cornell-box", 5), ("materialball", 3), ("MaterialsScene", 2)])
 def test_primary_hit_table_changes_no_bit_of_the_film(rtb, name, spp, monkeypatch):
     """params.primary_reuse traces each pixel's camera ray once per render call (all samples of a

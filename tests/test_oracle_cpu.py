@@ -196,6 +196,29 @@ def test_mis_estimator_against_the_reference_statistics(oracle_mod):
     assert st["closest_rays"] > 1.5 * 2.69 * st["samples"]     # one BSDF-strategy probe ray per diffuse vertex
 
 
+def test_adaptive_render_against_the_reference(oracle_mod):
+    """RayTracer::adaptiveRender (Renderer.h:583-749).  Golden = the unmodified reference on
+    cornell-box at 256x256 (tests/golden/make_golden.py).  Different RNG, and the plan is built
+    from 2 samples per pixel, so: tile variances of the tiles that matter (the light, >99 % of the
+    total) within 2 %, their sample counts within 1 %, all counts within noise, film mean within 1 %."""
+    g = np.load(os.path.join(GOLDEN, "cornell256_adaptive.npz"))
+    s = abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box_256.rtbs"))
+    film, cnt, var = oracle_mod.Oracle(s).render_adaptive(2, 1, 10240)
+    big = g["tile_variance"] > 0.01 * g["tile_variance"].max()
+    assert big.sum() >= 2
+    assert np.all(np.abs(var[big] / g["tile_variance"][big] - 1) < 0.02)
+    assert np.all(np.abs(cnt[big].astype(float) / g["tile_samples"][big] - 1) < 0.01)
+    assert abs(cnt.sum() / g["tile_samples"].sum() - 1) < 0.03
+    assert np.corrcoef(np.log(cnt.ravel()), np.log(g["tile_samples"].ravel()))[0, 1] > 0.97
+    assert cnt.min() >= 1 and cnt.max() <= 10240
+    assert np.all(np.abs(film.mean(axis=(0, 1)) / g["film_mean"] - 1) < 0.01)
+    rmse = np.sqrt(np.mean((raysets.block_mean(film, 8) - g["film_blocks"]) ** 2))
+    assert rmse < 0.02, rmse
+    # film += one mean image per call, like Film::splat of col / sample
+    film2, _, _ = oracle_mod.Oracle(s).render_adaptive(2, 1, 10240, film=film.copy())
+    assert np.all(np.abs(film2.mean(axis=(0, 1)) / (2 * g["film_mean"]) - 1) < 0.01)
+
+
 def test_canonical_work_counter_matches_the_surveys_probe(cornell):
     """canonical traversal of cornell-box = 24.2 box tests and 3.8 triangle tests per
     closest-hit ray, 2.69 + 1.64 rays per sample.  The counter must not change the render."""
