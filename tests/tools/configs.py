@@ -8,10 +8,10 @@ import raytracingrenderer_b200 as rtb
 from raytracingrenderer_b200 import abi, host_api
 from oracle import ref
 
-def gpu_run(flat, spp, max_depth=4, repeats=2):
+def gpu_run(flat, spp, max_depth=4, repeats=2, reuse=0):
     rt = rtb.RayTracer(0)
     t0 = time.time(); rt.init(flat); up = time.time() - t0
-    rt.set_params(max_depth=max_depth)
+    rt.set_params(max_depth=max_depth, primary_reuse=reuse)
     rt.render(min(spp, 8), 0); rt.synchronize()
     best = None
     for _ in range(repeats):
@@ -35,6 +35,9 @@ for name, spp in cfgs:
     rs = ref.RefScene(name)
     flat = host_api.load_scene(ref.scene_dir(name))
     g, film = gpu_run(flat, spp)
+    g1, film1 = gpu_run(flat, spp, reuse=1)
+    assert np.array_equal(film, film1)
+    g["primary_reuse"] = dict(msamples_s=g1["msamples_s"], mrays_s=g1["mrays_s"], rays_per_sample=g1["rays_per_sample"], seconds=g1["seconds"])
     rspp = 2 if name == "bathroom" else 4
     rs.render(1, 0, fresh=True)
     rf, n, secs = rs.render(rspp, 0, fresh=True)
@@ -44,9 +47,12 @@ for name, spp in cfgs:
     g["tris"] = rs.n_tris; g["res"] = [rs.width, rs.height]
     res[name] = g
     print(name, json.dumps(g), flush=True)
-for lg in (20, 22):
+for lg in (20, 22, 24):
     t0 = time.time(); flat, bsecs = host_api.build_soup(1 << lg, 3840, 2160); t1 = time.time()
     g, film = gpu_run(flat, 4, max_depth=0, repeats=2)
+    g1, film1 = gpu_run(flat, 4, max_depth=0, repeats=2, reuse=1)
+    assert np.array_equal(film, film1)
+    g["primary_reuse"] = dict(msamples_s=g1["msamples_s"], mrays_s=g1["mrays_s"], rays_per_sample=g1["rays_per_sample"], seconds=g1["seconds"])
     g["host_ref_order_build_s"] = bsecs; g["tris"] = flat.n_tris; g["res"] = [3840, 2160]
     res["soup2^%d" % lg] = g
     print("soup", lg, json.dumps(g), flush=True)
