@@ -100,6 +100,10 @@ struct rtb_ctx
 	int pools = 2; // sub-pools advancing concurrently on their own streams (profiles/r01_pool_sweep.txt)
 	cudaStream_t poolStreams[RTB_MAX_POOLS] = {};
 	cudaEvent_t poolDone[RTB_MAX_POOLS] = {};
+	// the shadow stage of iteration i runs beside the extend stage of iteration i+1 of the same sub-pool
+	cudaStream_t shadowStreams[RTB_MAX_POOLS] = {};
+	cudaEvent_t evShaded[RTB_MAX_POOLS] = {}, evShadowed[RTB_MAX_POOLS] = {};
+	bool shadowAsync = true;
 	cudaEvent_t evFork = nullptr;
 	uint64_t wfIterations = 0, wfHostSyncs = 0;
 };
@@ -371,7 +375,11 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		{
 			CK(cudaStreamCreateWithFlags(&ctx->poolStreams[k], cudaStreamNonBlocking));
 			CK(cudaEventCreateWithFlags(&ctx->poolDone[k], cudaEventDisableTiming));
+			CK(cudaStreamCreateWithFlags(&ctx->shadowStreams[k], cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&ctx->evShaded[k], cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&ctx->evShadowed[k], cudaEventDisableTiming));
 		}
+		if (const char* e = getenv("RTB_SHADOW_ASYNC")) ctx->shadowAsync = atoi(e) != 0;
 		CK(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
 	}
 	uint32_t nSlotsAll = ctx->poolSlots;
@@ -502,6 +510,8 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 					RTB_TRAV_SWITCH(ti, k_wf_extend<TR><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it));
 				}
 				if (timed) cudaEventRecord(se.e[1], st);
+				// the shade stage refills the shadow queue: the previous iteration's shadow stage must be done with it
+				if (shadows && ctx->shadowAsync) cudaStreamWaitEvent(st, ctx->evShadowed[k], 0);
 #define RTB_SHADE_LAUNCH(INTEG)                                                                      \
 	do                                                                                               \
 	{                                                                                                \
@@ -518,14 +528,22 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 #undef RTB_SHADE_LAUNCH
 				ctx->launches += 2;
 				if (timed) cudaEventRecord(se.e[2], st);
+				cudaStream_t sst = st;
 				if (shadows)
 				{
-					RTB_TRAV_SWITCH(ti, k_wf_shadow<TR><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it));
+					if (ctx->shadowAsync)
+					{
+						sst = ctx->shadowStreams[k];
+						cudaEventRecord(ctx->evShaded[k], st);
+						cudaStreamWaitEvent(sst, ctx->evShaded[k], 0);
+					}
+					RTB_TRAV_SWITCH(ti, k_wf_shadow<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
 					ctx->launches++;
+					if (ctx->shadowAsync) cudaEventRecord(ctx->evShadowed[k], sst);
 				}
 				if (timed)
 				{
-					cudaEventRecord(se.e[3], st);
+					cudaEventRecord(se.e[3], sst);
 					ctx->pendingStages.push_back(se);
 				}
 			}
@@ -560,6 +578,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	// join
 	for (int k = 0; k < K; k++)
 	{
+		if (shadows && ctx->shadowAsync) cudaStreamWaitEvent(ctx->poolStreams[k], ctx->evShadowed[k], 0);
 		cudaEventRecord(ctx->poolDone[k], ctx->poolStreams[k]);
 		cudaStreamWaitEvent(ctx->stream, ctx->poolDone[k], 0);
 	}
@@ -655,6 +674,9 @@ void rtb_destroy(rtb_ctx* ctx)
 	{
 		if (ctx->poolStreams[k]) cudaStreamDestroy(ctx->poolStreams[k]);
 		if (ctx->poolDone[k]) cudaEventDestroy(ctx->poolDone[k]);
+		if (ctx->shadowStreams[k]) cudaStreamDestroy(ctx->shadowStreams[k]);
+		if (ctx->evShaded[k]) cudaEventDestroy(ctx->evShaded[k]);
+		if (ctx->evShadowed[k]) cudaEventDestroy(ctx->evShadowed[k]);
 	}
 	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
 	if (ctx->counters) cudaFree(ctx->counters);

@@ -460,8 +460,10 @@ __global__ void __launch_bounds__(128) k_wf_extend_simple(const __grid_constant_
 }
 
 // Shadow rays: one thread per queued ray.  (A persistent/prefetching variant like k_wf_extend was
-// measured slower here — profiles/r01_v4_persistent_traversal.txt: the queue holds only ~0.2 rays
-// per slot and any-hit rays are short, so the refill bookkeeping outweighs the regained lanes.)
+// measured slower on EVERY scene, twice — profiles/r01_v4_persistent_traversal.txt and
+// profiles/r01_shadow_stage.txt: materialball -12 %, coffee -22 %, cornell-box -17 %, bathroom -2 %,
+// soups -6 %: any-hit rays end early, so the refill bookkeeping outweighs the regained lanes, and a
+// kernel that owns every resident block cannot share the SMs with the other streams.)
 template <int TRAV>
 __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
