@@ -340,6 +340,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	if (!ctx->wfTiles || memcmp(part, ctx->wfTilePart, sizeof(part)) != 0)
 	{
 		uint32_t tilesX = (ctx->width + 7) / 8, tilesY = (ctx->height + 3) / 4, t32x = (ctx->width + 31) / 32;
+		if (tilesX > 0xFFFFu || tilesY > 0xFFFEu) return fail(ctx, RTB_ERR_ARG, "film larger than 524280 x 262136 pixels");
 		std::vector<uint32_t> tiles;
 		tiles.reserve((size_t)tilesX * tilesY);
 		for (uint32_t ty = 0; ty < tilesY; ty++)
@@ -347,7 +348,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 			{
 				uint32_t tile32 = ((ty * 4) >> 5) * t32x + ((tx * 8) >> 5);
 				if (part[0] && part[2] > 1 && (int)(tile32 % (uint32_t)part[2]) != part[1]) continue;
-				tiles.push_back(ty * tilesX + tx);
+				tiles.push_back((ty << 16) | tx);
 			}
 		CK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->wfTiles) cudaFree(ctx->wfTiles);
@@ -455,7 +456,13 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		a.P = P;
 	}
 	// persistent traversal kernel: one resident wave; grid-stride kernels: enough blocks to fill the machine
-	unsigned gridExtend = (unsigned)(ctx->smCount * (ctx->travBlocksPerSM[ti] > 0 ? ctx->travBlocksPerSM[ti] : 1));
+	int extendBlocks = ctx->travBlocksPerSM[ti] > 0 ? ctx->travBlocksPerSM[ti] : 1;
+	if (const char* e = getenv("RTB_EXTEND_BLOCKS_PER_SM"))
+	{
+		int v = atoi(e);
+		if (v >= 1 && v < extendBlocks) extendBlocks = v;
+	}
+	unsigned gridExtend = (unsigned)(ctx->smCount * extendBlocks);
 	unsigned maxBlocks = (unsigned)ctx->smCount * 16u;
 	unsigned gridSlots = (perPool + 127) / 128;
 	if (gridSlots > maxBlocks) gridSlots = maxBlocks;
@@ -921,7 +928,7 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 			for (uint32_t k = 0; k < 32; k++)
 			{
 				uint32_t tx = (t % t32x) * 4 + (k & 3u), ty = (t / t32x) * 8 + (k >> 2);
-				sub[(size_t)t * 32 + k] = (tx < tilesX && ty < tilesY) ? ty * tilesX + tx : 0xFFFFFFFFu;
+				sub[(size_t)t * 32 + k] = (tx < tilesX && ty < tilesY) ? ((ty << 16) | tx) : 0xFFFFFFFFu;
 			}
 		CK(cudaMalloc((void**)&ctx->wfTilesAdaptive, sub.size() * sizeof(uint32_t)));
 		CK(cudaMemcpy(ctx->wfTilesAdaptive, sub.data(), sub.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

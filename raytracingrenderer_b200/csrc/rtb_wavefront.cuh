@@ -65,7 +65,7 @@ struct WfArgs
 	float4* shC;   //               contribution if unoccluded
 	WfCtrl* ctrl;  // [iterations], zeroed before the render
 	WfGlobal* glob;
-	const uint32_t* tileList; // owned 8x4 tiles (row-major tile ids)
+	const uint32_t* tileList; // owned 8x4-pixel tiles: (tile row << 16) | tile column
 	const unsigned long long* tileJobBase; // adaptive plan: first job of every 32x32 tile (+ total), or NULL
 	uint32_t nTiles32;                     //                number of 32x32 tiles
 	const float4* primary;    // per-pixel primary hit (bits(id), t, alpha, beta), or NULL: trace every camera ray
@@ -91,11 +91,11 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const long long* __restrict_
 // ---------------------------------------------------------------------------------------
 RTB_DEV bool wfJobPixel(const WfArgs& A, uint32_t q, uint32_t& px, uint32_t& py)
 {
-	uint32_t tilesX = (A.width + 7u) >> 3;
+	// tile list entry = (tile row << 16) | tile column of an 8x4-pixel tile (no division per vertex)
 	uint32_t tile = __ldg(A.tileList + (q >> 5)), lane = q & 31u;
 	if (tile == 0xFFFFFFFFu) return false; // adaptive plan: sub-tile outside the image
-	px = (tile % tilesX) * 8u + (lane & 7u);
-	py = (tile / tilesX) * 4u + (lane >> 3);
+	px = (tile & 0xFFFFu) * 8u + (lane & 7u);
+	py = (tile >> 16) * 4u + (lane >> 3);
 	return px < A.width && py < A.height;
 }
 
@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 	__shared__ uint32_t sCountS[2][4], sCountJ[2][4];
 	__shared__ unsigned int sBaseS[2];
 	__shared__ unsigned long long sBaseJ[2];
+	__shared__ uint32_t sBaseN[2], sBaseQ[2]; // sBaseJ split into (sample ordinal, pixel ordinal): one 64-bit division per block
 	// whole blocks stride together: the cooperative queue/job operations below need every lane
 	uint32_t nRounds = (A.nSlots + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
 	for (uint32_t round = 0; round < nRounds; round++)
@@ -704,7 +705,13 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 			if (threadIdx.x == 32)
 			{
 				uint32_t tot = sCountJ[ph][0] + sCountJ[ph][1] + sCountJ[ph][2] + sCountJ[ph][3];
-				sBaseJ[ph] = tot ? atomicAdd(&A.glob->nextJob, (unsigned long long)tot) : 0ull;
+				unsigned long long b = tot ? atomicAdd(&A.glob->nextJob, (unsigned long long)tot) : 0ull;
+				sBaseJ[ph] = b;
+				if (tot && !A.tileJobBase)
+				{
+					uint32_t Q = A.nTiles * 32u;
+					sBaseN[ph] = (uint32_t)(b / Q), sBaseQ[ph] = (uint32_t)(b % Q);
+				}
 			}
 			bool anyDone = __syncthreads_or(done) != 0;
 			if (haveShadow)
@@ -721,11 +728,20 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 				bool retry = false;
 				if (done)
 				{
-					unsigned long long j = sBaseJ[ph] + __popc(mJ & ((1u << lane) - 1u));
-					for (uint32_t w = 0; w < warp; w++) j += sCountJ[ph][w];
+					uint32_t off = __popc(mJ & ((1u << lane) - 1u));
+					for (uint32_t w = 0; w < warp; w++) off += sCountJ[ph][w];
+					unsigned long long j = sBaseJ[ph] + off;
 					if (j < A.totalJobs)
 					{
-						fresh = wfDecodeJob(A, j, n, q);
+						if (A.tileJobBase) fresh = wfDecodeJob(A, j, n, q);
+						else
+						{
+							// (n, q) = (j / Q, j % Q) from the block's base: off < 128 <= Q
+							uint32_t Q = A.nTiles * 32u, px, py;
+							n = sBaseN[ph], q = sBaseQ[ph] + off;
+							while (q >= Q) q -= Q, n++;
+							fresh = wfJobPixel(A, q, px, py);
+						}
 						retry = !fresh;
 					}
 				}
