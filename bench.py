@@ -212,6 +212,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     name, flats = load_workload(args.scene, log)
     spp = args.spp
