@@ -179,9 +179,25 @@ def cpu_baseline(args, log):
             _, _, dt = s.render(spp, 0, fresh=True)
             total += s.width * s.height * spp
             secs += dt
-        return {"value": total / secs / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "reference",
-                "sample": "the 7 materialball variants at %d spp each (of 256) through the unmodified "
-                          "RayTracer::render(), g++ -O2 -ffp-contract=off, %.1f s" % (spp, time.perf_counter() - t_budget)}
+        out = {"value": total / secs / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+               "sample": "the 7 materialball variants at %d spp each (of 256) through the unmodified "
+                         "RayTracer::render(), g++ -O2 -ffp-contract=off, %.1f s" % (spp, time.perf_counter() - t_budget)}
+        # the same sample with the flags the reference ships with (MSVC /fp:fast /arch:AVX, RTBase.vcxproj:123-124
+        # -> g++ -O3 -march=x86-64-v3 -ffast-math): speed only, its hit IDs differ from the parity build's
+        if os.path.isfile(os.path.join(ref.REF_DIR, "librtref_fast.so")):
+            try:
+                ftotal, fsecs = 0, 0.0
+                for v in VARIANTS:
+                    s = ref.RefScene("materialball_" + v, "_fast")
+                    s.render(1, 0, fresh=True)
+                    _, _, dt = s.render(spp, 0, fresh=True)
+                    ftotal += s.width * s.height * spp
+                    fsecs += dt
+                out["as_shipped_flags"] = {"value": ftotal / fsecs / 1e6, "unit": "Msamples/s",
+                                           "flags": "-O3 -march=x86-64-v3 -ffast-math"}
+            except OSError:
+                pass
+        return out
     from oracle import port
     name, flats = load_workload(args.scene, log)
     threads = os.cpu_count() or 1

@@ -9,7 +9,7 @@ GPU box with gpurun):
                              `const int MAX_DEPTH = 4;` (Renderer.h:20) reads RT_MAX_DEPTH
                              (soup config, SURVEY 8d cfg 5)
   oracle/_ref/librtref.so    oracle/ref_driver.cpp, g++ -O2 -ffp-contract=off  (parity oracle)
-  oracle/_ref/librtref_fast.so   same, -O3 -march=native -ffast-math (speed only; mirrors the
+  oracle/_ref/librtref_fast.so   same, -O3 -march=x86-64-v3 -ffast-math (speed only; mirrors the
                              reference's MSVC /fp:fast /arch:AVX, RTBase/RTBase.vcxproj:123-124)
   oracle/_ref/librtref_d0.so     MAX_DEPTH = 0 variant of the parity build
   oracle/_ref/librtref_mis.so    parity build whose pathTrace calls computeDirectMIS (Renderer.h:474-557,
@@ -219,7 +219,7 @@ def build(force=False):
     if not fresh:
         shadow = make_shadow("shadow")
         shadow_d0 = make_shadow("shadow_d0", patch_depth=True)
-        compile_driver(shadow, "librtref_fast.so", ["-O3", "-march=native", "-ffast-math"])
+        compile_driver(shadow, "librtref_fast.so", ["-O3", "-march=x86-64-v3", "-ffast-math"])
         compile_driver(shadow_d0, "librtref_d0.so", ["-O2", "-ffp-contract=off", "-DRT_MAX_DEPTH=0"])
         compile_driver(make_shadow("shadow_mis", patch_mis=True), "librtref_mis.so", ["-O2", "-ffp-contract=off"])
         compile_driver(shadow, "librtref.so", ["-O2", "-ffp-contract=off"])
