@@ -483,87 +483,6 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevSc
 }
 
 
-// ---------------------------------------------------------------------------------------
-// NEE with deferred visibility: RayTracer::computeDirect (Renderer.h:423-473) up to the
-// scene->visible() call; returns false when no shadow ray is needed (contribution is zero).
-// ---------------------------------------------------------------------------------------
-RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& sd, const rtb_material& m, float uPick,
-                          float r1, float r2, V3& p1, V3& p2, V3& contrib)
-{
-	if (m.flags & RTB_MAT_SPECULAR) return false;
-	if (S.n_lights == 0) return false;
-	float nl = (float)S.n_lights;
-	float pmf = 1.0f / nl;
-	int li = (int)(nl * uPick);
-	if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
-	rtb_light L = S.lights[li];
-	if (L.type == RTB_LIGHT_AREA)
-	{
-		V3 p = trianglePoint(S, L.triangle, r1, r2);
-		float pdf = 1.0f / L.area;
-		V3 wi = p - sd.x;
-		float l = lengthSq(wi);
-		wi = normalize(wi);
-		V3 nL = triangleGNormal(S, L.triangle);
-		float G = (selMax(dot(wi, sd.sN), 0.0f) * selMax(-dot(wi, nL), 0.0f)) / l;
-		if (!(G > 0.0f)) return false;
-		contrib = divFast((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G, pmf * pdf);
-		p1 = sd.x;
-		p2 = p;
-		return true;
-	}
-	V3 wi, emitted;
-	float pdf;
-	if (L.type == RTB_LIGHT_ENVMAP && P.sampling == RTB_SAMPLING_IMPORTANCE && S.env_marginal != nullptr)
-	{
-		int W = S.env_w, H = S.env_h;
-		int lo = 0, hi = H;
-		while (hi - lo > 1)
-		{
-			int mid = (lo + hi) >> 1;
-			if (__ldg(S.env_marginal + mid) <= r1) lo = mid;
-			else hi = mid;
-		}
-		int row = lo;
-		float m0 = __ldg(S.env_marginal + row), m1 = __ldg(S.env_marginal + row + 1);
-		float fr = (m1 > m0) ? (r1 - m0) / (m1 - m0) : 0.5f;
-		const float* cd = S.env_cond + (size_t)row * (W + 1);
-		lo = 0, hi = W;
-		while (hi - lo > 1)
-		{
-			int mid = (lo + hi) >> 1;
-			if (__ldg(cd + mid) <= r2) lo = mid;
-			else hi = mid;
-		}
-		int col = lo;
-		float c0 = __ldg(cd + col), c1 = __ldg(cd + col + 1);
-		float fc = (c1 > c0) ? (r2 - c0) / (c1 - c0) : 0.5f;
-		float v = ((float)row + fr) / (float)H;
-		float u = ((float)col + fc) / (float)W;
-		float theta = v * RTB_PI_F, phi = u * (2.0f * RTB_PI_F);
-		float st, ct, sp, cp;
-		sincosf(theta, &st, &ct);
-		sincosf(phi, &sp, &cp);
-		wi = mk(cp * st, ct, sp * st);
-		float pmfTexel = (m1 - m0) * (c1 - c0);
-		pdf = pmfTexel * ((float)W * (float)H) / (2.0f * RTB_PI_F * RTB_PI_F * fmaxf(st, 1e-8f));
-		if (!(pdf > 0.0f)) return false;
-		emitted = envLookup(S, L.tex, wi);
-	}
-	else
-	{
-		wi = uniformSampleSphere(r1, r2);
-		pdf = 0.0795774683356285095f; // 1 / (4 pi)
-		emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
-	}
-	float G = selMax(dot(wi, sd.sN), 0.0f);
-	if (!(G > 0.0f)) return false;
-	contrib = divFast((bsdfEvaluate(S, m, sd, wi) * emitted) * G, pmf * pdf);
-	p1 = sd.x;
-	p2 = sd.x + (wi * 10000.0f);
-	return true;
-}
-
 template <int INTEGRATOR, bool REUSE>
 __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
