@@ -389,7 +389,9 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	while (K > 1 && nSlotsAll / (uint32_t)K < (1u << 19)) K--; // sub-pools of at least 512 k slots
 	uint32_t perPool = ((nSlotsAll + (uint32_t)K - 1) / (uint32_t)K + 31u) & ~31u;
 	uint32_t nSlotsAlloc = perPool * (uint32_t)K;
-	size_t need = (size_t)nSlotsAlloc * 7 * sizeof(float4);
+	// shadow queue: one entry per slot and launch, WF_SHADOW_PER_SLOT with the multi-pass shade stage
+	const size_t F = P.primary_reuse ? WF_SHADOW_PER_SLOT : 1u;
+	size_t need = (size_t)nSlotsAlloc * (4 + 3 * F) * sizeof(float4);
 	if (need > ctx->wfStateBytes)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -439,7 +441,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		WfArgs& a = A[k];
 		size_t off = (size_t)k * perPool, n = nSlotsAlloc;
 		a.rayO = base + off, a.rayD = base + n + off, a.hit = base + n * 2 + off, a.thr = base + n * 3 + off;
-		a.shO = base + n * 4 + off, a.shD = base + n * 5 + off, a.shC = base + n * 6 + off;
+		a.shO = base + n * 4 + off * F, a.shD = base + n * (4 + F) + off * F, a.shC = base + n * (4 + 2 * F) + off * F;
 		a.ctrl = ctx->wfCtrl + (size_t)k * bound;
 		a.glob = ctx->wfGlobal;
 		a.tileList = plan ? ctx->wfTilesAdaptive : ctx->wfTiles;

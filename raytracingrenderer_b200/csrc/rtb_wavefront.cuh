@@ -36,6 +36,7 @@
 #define WF_EXTEND_MIN_BLOCKS 8
 #endif
 
+#define WF_SHADOW_PER_SLOT 2u /* shadow-queue entries per slot when the shade stage runs several passes */
 #define WF_PREHIT 0x400u /* hit[slot] already holds the vertex (primary-hit table): k_wf_extend skips the slot */
 #define WF_ALIVE 0x200u
 #define WF_CANHIT 0x100u
@@ -502,6 +503,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 		uint32_t slot = round * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
 		bool inRange = slot < A.nSlots;
 		bool haveVertex = false, slotLive = false;
+		uint32_t queued = 0;
 		float4 ro, rd, hh, tq;
 		if (inRange)
 		{
@@ -667,16 +669,18 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 				if (__any_sync(0xFFFFFFFFu, retry)) fresh = wfClaimJob(A, retry, n, q) || fresh;
 			}
 			if (done && !fresh) A.rayD[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-			// REUSE = false compiles to the single-pass kernel (no loop-carried vertex state)
-			if (!REUSE || pass + 1u >= A.primaryPasses)
+			// REUSE = false compiles to the single-pass kernel (no loop-carried vertex state).  A thread that
+			// has queued WF_SHADOW_PER_SLOT shadow rays in this launch parks its next job in the slot instead
+			// of shading it now: that is the capacity of the shadow queue per slot (rtb_api.cu).
+			if (haveShadow) queued++;
+			const bool lastPass = !REUSE || pass + 1u >= A.primaryPasses;
+			if (fresh && (lastPass || queued >= WF_SHADOW_PER_SLOT))
 			{
-				if (fresh)
-				{
-					wfWriteJob(S, A, slot, n, q);
-					slotLive = true;
-				}
-				break;
+				wfWriteJob(S, A, slot, n, q);
+				slotLive = true;
+				fresh = false;
 			}
+			if (lastPass) break;
 			if (!anyDone) break; // no thread of the block can hold a fresh vertex
 			if (fresh)
 			{

@@ -313,6 +313,31 @@ def test_adaptive_render_equals_the_oracle_and_the_reference(rtb, oracle_mod):
     rt.close()
 
 
+def test_adaptive_render_full_resolution_and_shadow_queue_capacity(rtb, monkeypatch):
+    """1024 tiles, tile-major job order: the pool works on a few floor / wall tiles at a time, where
+    nearly every vertex queues a shadow ray and the multi-pass shade stage would queue two per slot
+    (this overflowed a one-entry-per-slot queue once).  Also the extreme: every path ends at its second
+    vertex (max_depth 0) with 7 shade passes."""
+    g = np.load(os.path.join(GOLDEN, "cornell_ref_blocks.npz"))
+    rt = gpu_scene(rtb, "cornell-box")
+    cnt, var = rt.adaptiveRender(2, 1, 10240)
+    assert cnt.shape == (32, 32) and cnt.min() >= 1 and cnt.max() > 1000
+    img = rt.read_film()
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / (0.5 * (g["mean_a"] + g["mean_b"])) - 1) < 0.01)
+    from raytracingrenderer_b200 import host_api
+    s, _ = host_api.build_soup(1 << 12, 640, 360)
+    films = []
+    for reuse, passes in ((0, "1"), (1, "7"), (1, "2")):
+        monkeypatch.setenv("RTB_PRIMARY_PASSES", passes)
+        r2 = rtb.RayTracer(0)
+        r2.init(s)
+        r2.set_params(max_depth=0, primary_reuse=reuse)
+        r2.render(48, 0)
+        films.append(r2.read_film().copy())
+        r2.close()
+    assert np.array_equal(films[0], films[1]) and np.array_equal(films[0], films[2])
+
+
 def test_adaptive_render_on_a_ragged_image(rtb, oracle_mod):
     """Width and height that are not multiples of 32 (edge tiles, padded pixel slots)."""
     s = synthetic_scene(width=100, height=70)
