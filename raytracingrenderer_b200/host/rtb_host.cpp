@@ -128,4 +128,9 @@ int rtbh_build_soup(uint32_t n_tris, int width, int height, const char* out_path
 	}
 }
 
+// Test hook: 1 if the builder's parallel sort reproduces std::sort's permutation (ties included) on `keys`.
+int rtbh_sort_selftest(const float* keys, uint32_t n, int par)
+{
+	return BVHNode::sortSelfTest(keys, n, par) ? 1 : 0;
+}
 } // extern "C"

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -551,15 +552,30 @@ public:
 			w.bmin[i] = b.min, w.bmax[i] = b.max;
 		}
 		unsigned hw = std::thread::hardware_concurrency();
-		int par = 0; // levels of the recursion that fork a thread for the left subtree
-		while ((1u << par) < hw && par < 5) par++;
-		if (n < 200000) par = 0;
+		// par = log2(threads): the top `par` levels also split their own sort / sweep over 2^(par - level)
+		// threads; below that every subtree of more than 50 k triangles still gets its own thread (SAH
+		// splits are unbalanced: many more tasks than cores keeps them busy)
+		int par = 0;
+		while ((1u << par) < hw && par < 6) par++;
+		if (n < 200000) par = -1;
 		if (const char* e = getenv("RTB_HOST_BUILD_SERIAL"))
-			if (atoi(e) != 0) par = 0;
+			if (atoi(e) != 0) par = -1;
 		buildRecursive(w, 0, (int)n, par);
 		std::vector<Triangle> sorted(n);
 		for (size_t i = 0; i < n; i++) sorted[i] = inputTriangles[w.order[i]];
 		outputTriangles.swap(sorted);
+	}
+
+	// test hook: does sortLikeStdSort give std::sort's permutation on these keys (ids = positions)?
+	static bool sortSelfTest(const float* k, uint32_t n, int par)
+	{
+		std::vector<Key> a(n), b(n);
+		for (uint32_t i = 0; i < n; i++) a[i] = b[i] = {k[i], i};
+		std::sort(a.begin(), a.end(), keyLess);
+		sortLikeStdSort(b.data(), b.data() + n, par);
+		for (uint32_t i = 0; i < n; i++)
+			if (a[i].id != b[i].id) return false;
+		return true;
 	}
 
 private:
@@ -575,6 +591,116 @@ private:
 		float k;
 		uint32_t id;
 	};
+	static bool keyLess(const Key& a, const Key& b) { return a.k < b.k; }
+	// AABB without a constructor: the same selects (Core.h:187-195) and the same area expression
+	struct BB
+	{
+		float lo[3], hi[3];
+		void extend(const BB& o)
+		{
+			for (int a = 0; a < 3; a++)
+			{
+				hi[a] = hi[a] > o.lo[a] ? hi[a] : o.lo[a];
+				lo[a] = lo[a] < o.lo[a] ? lo[a] : o.lo[a];
+				hi[a] = hi[a] > o.hi[a] ? hi[a] : o.hi[a];
+				lo[a] = lo[a] < o.hi[a] ? lo[a] : o.hi[a];
+			}
+		}
+		float area() const // Geometry.h:187-191
+		{
+			float sx = hi[0] - lo[0], sy = hi[1] - lo[1], sz = hi[2] - lo[2];
+			return ((sx * sy) + (sy * sz) + (sx * sz)) * 2.0f;
+		}
+	};
+	template <class F>
+	static void parallelFor(int n, F f)
+	{
+		std::vector<std::thread> th;
+		for (int c = 1; c < n; c++) th.emplace_back([c, &f]() { f(c); });
+		f(0);
+		for (auto& t : th) t.join();
+	}
+	// std::sort's permutation (ties included) with its independent sub-ranges sorted concurrently.
+	// libstdc++'s std::sort is: introsort loop (median-of-three to *first, unguarded Hoare partition,
+	// recurse on the right part, iterate on the left, depth limit 2*floor(log2 n) -> heapsort) down to
+	// ranges of <= 16 elements, then ONE insertion-sort pass over the whole array.  After the loop every
+	// element of an earlier range is <= every element of a later one, so that pass never moves an element
+	// out of its range: sorting each small range by insertion where the loop leaves it is the same
+	// permutation.  The partition steps are restated here (they are the algorithm); the heapsort fallback
+	// calls the library's own make_heap / sort_heap.  tests/test_host_cpu.py checks it against std::sort.
+	static void insertionSort(Key* first, Key* last)
+	{
+		if (first == last) return;
+		for (Key* i = first + 1; i != last; ++i)
+		{
+			Key val = *i;
+			Key* j = i;
+			while (j != first && keyLess(val, *(j - 1)))
+			{
+				*j = *(j - 1);
+				--j;
+			}
+			*j = val;
+		}
+	}
+	static Key* partitionPivot(Key* first, Key* last)
+	{
+		Key* mid = first + (last - first) / 2;
+		Key *a = first + 1, *b = mid, *c = last - 1;
+		if (keyLess(*a, *b))
+		{
+			if (keyLess(*b, *c)) std::iter_swap(first, b);
+			else if (keyLess(*a, *c)) std::iter_swap(first, c);
+			else std::iter_swap(first, a);
+		}
+		else if (keyLess(*a, *c)) std::iter_swap(first, a);
+		else if (keyLess(*b, *c)) std::iter_swap(first, c);
+		else std::iter_swap(first, b);
+		Key* lo = first + 1;
+		Key* hi = last;
+		for (;;)
+		{
+			while (keyLess(*lo, *first)) ++lo;
+			--hi;
+			while (keyLess(*first, *hi)) --hi;
+			if (!(lo < hi)) return lo;
+			std::iter_swap(lo, hi);
+			++lo;
+		}
+	}
+	static void introsortLoop(Key* first, Key* last, long depthLimit, int par)
+	{
+		std::vector<std::thread> spawned;
+		while (last - first > 16)
+		{
+			if (depthLimit == 0)
+			{
+				std::make_heap(first, last, keyLess);
+				std::sort_heap(first, last, keyLess);
+				first = last; // nothing left for the insertion sort below
+				break;
+			}
+			--depthLimit;
+			Key* cut = partitionPivot(first, last);
+			if (par > 0 && last - cut > 20000)
+			{
+				--par;
+				spawned.emplace_back([cut, last, depthLimit, par]() { introsortLoop(cut, last, depthLimit, par); });
+			}
+			else
+				introsortLoop(cut, last, depthLimit, 0);
+			last = cut;
+		}
+		insertionSort(first, last);
+		for (auto& t : spawned) t.join();
+	}
+	static void sortLikeStdSort(Key* first, Key* last, int par)
+	{
+		if (first == last) return;
+		long lg = 0;
+		for (size_t n = (size_t)(last - first); n > 1; n >>= 1) lg++;
+		introsortLoop(first, last, lg * 2, par + 2);
+	}
 	// Sub-ranges are independent (disjoint slices of `order`, read-only keys and boxes), so the two
 	// recursive calls may run concurrently without changing any decision.
 	void buildRecursive(Work& w, int start, int end, int par)
@@ -598,60 +724,118 @@ private:
 		if (size.y >= size.x && size.y >= size.z) axis = 1;
 		else if (size.z >= size.x && size.z >= size.y) axis = 2;
 		const std::vector<float>& key = axis == 0 ? w.cx : (axis == 1 ? w.cy : w.cz);
-		std::vector<Key> keys((size_t)numTri);
+		// scratch: the sort keys and the prefix / suffix boxes of the SAH sweep.  Millions of nodes hold a
+		// handful of triangles: those use the stack; plain structs, never value-initialised.
+		const int SMALL = 96;
+		Key keysS[SMALL];
+		BB leftS[SMALL], rightS[SMALL];
+		std::unique_ptr<Key[]> keysH;
+		std::unique_ptr<BB[]> leftH, rightH;
+		Key* keys = keysS;
+		BB *left = leftS, *right = rightS;
+		if (numTri > SMALL)
+		{
+			keysH.reset(new Key[(size_t)numTri]);
+			leftH.reset(new BB[(size_t)numTri]);
+			rightH.reset(new BB[(size_t)numTri]);
+			keys = keysH.get(), left = leftH.get(), right = rightH.get();
+		}
 		for (int i = 0; i < numTri; i++) keys[i] = {key[w.order[start + i]], w.order[start + i]};
-		std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.k < b.k; });
+		// big nodes near the root: the node's own sort and sweep are spread over the threads that have no
+		// subtree of their own yet (2^par of them); the results are those of the serial code
+		const int team = (par > 0 && numTri > 400000) ? (1 << par) : 1;
+		const bool fork = par >= 0 && numTri > 50000;
+		if (team > 1) sortLikeStdSort(keys, keys + numTri, par);
+		else std::sort(keys, keys + numTri, keyLess);
 		for (int i = 0; i < numTri; i++) w.order[start + i] = keys[i].id;
-		std::vector<AABB> left((size_t)numTri), right((size_t)numTri); // prefix / suffix boxes of the SAH sweep
 		auto triBox = [&](int i) {
-			AABB b;
-			b.min = w.bmin[w.order[start + i]], b.max = w.bmax[w.order[start + i]];
+			BB b;
+			const Vec3 &lo = w.bmin[keys[i].id], &hi = w.bmax[keys[i].id];
+			b.lo[0] = lo.x, b.lo[1] = lo.y, b.lo[2] = lo.z, b.hi[0] = hi.x, b.hi[1] = hi.y, b.hi[2] = hi.z;
 			return b;
 		};
-		left[0] = triBox(0);
-		right[numTri - 1] = triBox(numTri - 1);
-		for (int i = 1; i < numTri; i++)
-		{
-			left[i] = left[i - 1];
-			left[i].extend(triBox(i));
-		}
-		for (int i = numTri - 2; i >= 0; i--)
-		{
-			right[i] = right[i + 1];
-			right[i].extend(triBox(i));
-		}
+		auto scanChunk = [&](int a, int b) {
+			left[a] = triBox(a);
+			for (int i = a + 1; i < b; i++)
+			{
+				left[i] = left[i - 1];
+				left[i].extend(triBox(i));
+			}
+			right[b - 1] = triBox(b - 1);
+			for (int i = b - 2; i >= a; i--)
+			{
+				right[i] = right[i + 1];
+				right[i].extend(triBox(i));
+			}
+		};
+		auto bestSplit = [&](int a, int b, float& cm, int& si) {
+			cm = FLT_MAX, si = 0;
+			for (int i = a; i < b; i++)
+			{
+				float num_left = (float)i, num_right = (float)(numTri - i);
+				float cost = left[i - 1].area() * num_left + right[i].area() * num_right;
+				if (cost < cm) cm = cost, si = i;
+			}
+		};
 		float cost_min = FLT_MAX;
 		int split_index = 0;
-		for (int i = 1; i < numTri; i++)
+		if (team > 1)
 		{
-			float num_left = (float)i, num_right = (float)(numTri - i);
-			float cost = left[i - 1].area() * num_left + right[i].area() * num_right;
-			if (cost < cost_min)
+			// chunked scans: box unions are exact min/max, so any grouping gives the serial boxes
+			const int T = team, chunk = (numTri + T - 1) / T;
+			std::vector<BB> headL((size_t)T), headR((size_t)T);
+			parallelFor(T, [&](int c) {
+				int a = c * chunk, b = std::min(numTri, a + chunk);
+				if (a < b) scanChunk(a, b);
+			});
+			for (int c = 0; c < T; c++)
 			{
-				cost_min = cost;
-				split_index = i;
+				int a = c * chunk, b = std::min(numTri, a + chunk);
+				if (a >= b) continue;
+				headL[c] = left[b - 1], headR[c] = right[a];
 			}
+			for (int c = 1; c < T; c++)
+				if (c * chunk < numTri) headL[c].extend(headL[c - 1]);
+			for (int c = T - 2; c >= 0; c--)
+				if ((c + 1) * chunk < numTri) headR[c].extend(headR[c + 1]);
+			parallelFor(T, [&](int c) {
+				int a = c * chunk, b = std::min(numTri, a + chunk);
+				if (a >= b) return;
+				if (c > 0)
+					for (int i = a; i < b; i++) left[i].extend(headL[c - 1]);
+				if (c + 1 < T && (c + 1) * chunk < numTri)
+					for (int i = a; i < b; i++) right[i].extend(headR[c + 1]);
+			});
+			std::vector<float> bestCost((size_t)T, FLT_MAX);
+			std::vector<int> bestIdx((size_t)T, 0);
+			parallelFor(T, [&](int c) {
+				int a = std::max(1, c * chunk), b = std::min(numTri, c * chunk + chunk);
+				if (a < b) bestSplit(a, b, bestCost[c], bestIdx[c]);
+			});
+			for (int c = 0; c < T; c++) // first index of the minimum, like the serial strict '<'
+				if (bestCost[c] < cost_min) cost_min = bestCost[c], split_index = bestIdx[c];
+		}
+		else
+		{
+			scanChunk(0, numTri);
+			bestSplit(1, numTri, cost_min, split_index);
 		}
 		int mid = start + split_index;
 		l = new BVHNode();
 		r = new BVHNode();
+		keysH.reset(), leftH.reset(), rightH.reset(); // release the sweep scratch before descending
+		if (fork)
 		{
-			// release the sweep scratch before descending
-			std::vector<AABB>().swap(left);
-			std::vector<AABB>().swap(right);
-			std::vector<Key>().swap(keys);
-		}
-		if (par > 0 && numTri > 50000)
-		{
+			const int next = par > 0 ? par - 1 : 0;
 			BVHNode* lp = l;
-			std::thread th([&w, lp, start, mid, par]() { lp->buildRecursive(w, start, mid, par - 1); });
-			r->buildRecursive(w, mid, end, par - 1);
+			std::thread th([&w, lp, start, mid, next]() { lp->buildRecursive(w, start, mid, next); });
+			r->buildRecursive(w, mid, end, next);
 			th.join();
 		}
 		else
 		{
-			l->buildRecursive(w, start, mid, 0);
-			r->buildRecursive(w, mid, end, 0);
+			l->buildRecursive(w, start, mid, -1);
+			r->buildRecursive(w, mid, end, -1);
 		}
 	}
 };

@@ -27,6 +27,7 @@ def lib():
         L.rtbh_matrix_invert.argtypes = [C.c_void_p, C.c_void_p]
         L.rtbh_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.rtbh_build_soup.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
+        L.rtbh_sort_selftest.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
         _lib = L
     return _lib
 
@@ -81,3 +82,9 @@ def build_soup(n_tris, width=3840, height=2160, rtbs_path=None):
     finally:
         if tmp and os.path.exists(tmp):
             os.unlink(tmp)
+
+
+def sort_selftest(keys, par=3):
+    """True if the builder's parallel sort gives std::sort's permutation on `keys` (float32)."""
+    k = np.ascontiguousarray(keys, np.float32)
+    return bool(lib().rtbh_sort_selftest(k.ctypes.data, len(k), int(par)))

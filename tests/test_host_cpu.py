@@ -81,3 +81,25 @@ def test_parallel_build_equals_serial_build(host, tmp_path, monkeypatch):
     monkeypatch.setenv("RTB_HOST_BUILD_SERIAL", "1")
     b, _ = host.build_soup(1 << 18, 64, 36)
     assert a.ref_nodes.tobytes() == b.ref_nodes.tobytes() and a.tri_isect.tobytes() == b.tri_isect.tobytes()
+
+
+def test_parallel_sort_reproduces_std_sort_ties_included(host):
+    """Triangle IDs are positions after the reference builder's std::sort by centroid, and equal
+    centroids are common, so the builder's concurrent sort must give std::sort's exact permutation."""
+    rng = np.random.default_rng(5)
+    n = 300000
+    cases = {
+        "random": rng.random(n, dtype=np.float32),
+        "heavy ties": np.floor(rng.random(n) * 97).astype(np.float32),
+        "all equal": np.zeros(n, np.float32),
+        "sorted": np.arange(n, dtype=np.float32),
+        "reversed": np.arange(n, dtype=np.float32)[::-1],
+        "sawtooth": (np.arange(n) % 1000).astype(np.float32),
+        "organ pipe": np.minimum(np.arange(n), n - np.arange(n)).astype(np.float32),
+        "two values": (rng.random(n) < 0.5).astype(np.float32),
+        "tiny": rng.random(11, dtype=np.float32),
+        "17": np.floor(rng.random(17) * 3).astype(np.float32),
+    }
+    for name, k in cases.items():
+        for par in (0, 1, 4):
+            assert host.sort_selftest(k, par), (name, par)
