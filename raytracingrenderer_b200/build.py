@@ -40,7 +40,8 @@ def up_to_date():
 
 
 HOST_LIB = os.path.join(HERE, "librtb200_host.so")
-HOST_DEPS = ["rtb_host.cpp", "rtb_scene.hpp", "rtb_flatten.hpp"]
+HOST_DEPS = ["rtb_host.cpp", "rtb_scene.hpp", "rtb_flatten.hpp", "rtb_jpeg.hpp"]
+CLI = os.path.join(HERE, "rtb_render")
 
 
 def build_host(force=False):
@@ -54,9 +55,25 @@ def build_host(force=False):
     return HOST_LIB
 
 
+def build_cli(force=False):
+    """tools/rtb_render.cpp: the headless Main.cpp counterpart built only from this repository
+    (host/standalone shims + host/Renderer.h + librtb200.so)."""
+    hdir = os.path.join(HERE, "host")
+    src = os.path.join(ROOT, "tools", "rtb_render.cpp")
+    deps = [src, LIB, os.path.join(hdir, "Renderer.h"), os.path.join(hdir, "rtb_standalone.hpp"),
+            os.path.join(hdir, "rtb_scene.hpp"), os.path.join(hdir, "rtb_flatten.hpp"), os.path.join(hdir, "rtb_jpeg.hpp")]
+    if not force and os.path.isfile(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
+        return CLI
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wno-unused",
+                           "-I", os.path.join(hdir, "standalone"), "-I", hdir, "-I", os.path.join(ROOT, "include"),
+                           src, "-o", CLI, "-L", HERE, "-lrtb200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"])
+    return CLI
+
+
 def build(force=False, verbose=False, extra=()):
     build_host(force)
     if not force and up_to_date():
+        build_cli(force)
         return LIB
     cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include")]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
@@ -64,6 +81,7 @@ def build(force=False, verbose=False, extra=()):
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    build_cli(True)
     return LIB
 
 

@@ -469,6 +469,7 @@ public:
 		SPP = 0;
 	}
 	void incrementSPP() { SPP++; }
+	void save(std::string filename); // Imaging.h:262-271: film / SPP as Radiance .hdr (rtb_standalone.hpp)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,4 @@
+// Stand-alone build of the C++ host layer: code written against RTBase's headers (#include "GEMLoader.h")
+// resolves here and gets the product's own scene API (host/rtb_scene.hpp) instead of the reference's.
+#pragma once
+#include "../rtb_standalone.hpp"

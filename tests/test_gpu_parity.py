@@ -600,6 +600,45 @@ def test_reference_host_program_renders_through_the_drop_in_header(rtb, tmp_path
     assert os.path.getsize(hdr + ".png") > 1000          # savePNG after a camera move + clear
 
 
+def test_standalone_cpp_program_without_any_reference_code(rtb, tmp_path):
+    """raytracingrenderer_b200/rtb_render (tools/rtb_render.cpp): Main.cpp's shape built ONLY from this
+    repository — host/standalone shims -> rtb_scene.hpp loader + reference-order builder, host/Renderer.h,
+    librtb200.so.  Film bit-identical to the Python mirror's; HDR / PNG written by the product's own writers;
+    --adaptive and --mis reach the two optional estimators."""
+    import subprocess
+    from oracle import ref
+    from raytracingrenderer_b200 import imageio, build
+    exe = build.CLI
+    if not os.path.isfile(exe) or not ref.have_scene("cornell-box"):
+        pytest.skip("rtb_render or the staged cornell-box scene is missing")
+    hdr, raw, png = str(tmp_path / "out.hdr"), str(tmp_path / "film.bin"), str(tmp_path / "out.png")
+    out = subprocess.run([exe, ref.scene_dir("cornell-box"), "8", hdr, "--raw", raw, "--png", png], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "SPP 8" in out.stdout
+    rt = gpu_scene(rtb, "cornell-box")
+    rt.render(8, 0)
+    want = rt.read_film()
+    got = np.fromfile(raw, "<f4").reshape(want.shape)
+    assert got.tobytes() == want.tobytes()
+    img = imageio.read_hdr(hdr)
+    assert np.all(np.abs(img - want / 8) <= (want / 8).max(axis=-1, keepdims=True) / 100 + 1e-6)
+    assert open(png, "rb").read(8) == b"\x89PNG\r\n\x1a\n" and os.path.getsize(png) > 1000
+    g = np.load(os.path.join(GOLDEN, "cornell_mis_blocks.npz"))
+    out = subprocess.run([exe, ref.scene_dir("cornell-box"), "16", hdr, "--mis", "--raw", raw], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    m = (np.fromfile(raw, "<f4").reshape(want.shape) / 16).mean(axis=(0, 1))
+    assert np.all(np.abs(m / (0.5 * (g["mean_a"] + g["mean_b"])) - 1) < 0.01)
+    out = subprocess.run([exe, ref.scene_dir("cornell-box"), "2", hdr, "--adaptive", "--raw", raw], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "SPP 2" in out.stdout
+    plain = np.load(os.path.join(GOLDEN, "cornell_ref_blocks.npz"))
+    m = (np.fromfile(raw, "<f4").reshape(want.shape) / 2).mean(axis=(0, 1))
+    assert np.all(np.abs(m / (0.5 * (plain["mean_a"] + plain["mean_b"])) - 1) < 0.01)
+    # a scene directory that does not exist is an error message and a non-zero exit, not a crash
+    out = subprocess.run([exe, str(tmp_path / "nowhere"), "1", hdr], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0
+
+
 def test_soup_config_primary_plus_one_bounce(rtb, oracle_mod):
     """SURVEY 8d cfg 5 at test size: random-triangle soup built by the product's host layer
     (reference-order BVH), max_depth 0 = primary + one diffuse bounce, white background light."""
