@@ -45,6 +45,7 @@ def _lib(variant=""):
         lib.ref_eval_background.argtypes = [vp, vp, C.c_uint64, vp]
         lib.ref_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.ref_render_adaptive.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        lib.ref_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_uint64]
         lib.ref_aov.argtypes = [vp, C.c_int, vp]
         lib.ref_tonemap.argtypes = [vp, vp, C.c_int, C.c_float, vp]
         lib.ref_gaussian_splat.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]
@@ -169,3 +170,14 @@ class RefScene:
         out = np.zeros((self.height, self.width, 3), np.uint8)
         self.lib.ref_tonemap(self.h, _p(f), int(spp), float(exposure), _p(out))
         return out
+
+
+def decode_image(path):
+    """stbi_load of the reference on one file -> uint8 [H, W, channels]."""
+    lib = _lib("")
+    w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    if lib.ref_decode_image(path.encode(), C.byref(w), C.byref(h), C.byref(c), None, 0) != 0:
+        raise RuntimeError("stbi_load failed on " + path)
+    out = np.zeros((h.value, w.value, c.value), np.uint8)
+    lib.ref_decode_image(path.encode(), C.byref(w), C.byref(h), C.byref(c), _p(out), out.size)
+    return out

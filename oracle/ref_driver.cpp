@@ -438,6 +438,23 @@ int ref_render_adaptive(void* handle, int threads, int fresh, float* film_sum, f
 	return h->rt->getSPP();
 }
 
+// stbi_load (the decoder behind Texture::load, Imaging.h:51) on one file: the golden for the product's
+// own PNG / JPEG decoders.  out may be NULL to query the size.
+int ref_decode_image(const char* path, int* w, int* h, int* channels, unsigned char* out, uint64_t cap)
+{
+	unsigned char* d = stbi_load(path, w, h, channels, 0);
+	if (!d) return -1;
+	uint64_t n = (uint64_t)(*w) * (*h) * (*channels);
+	int rc = 0;
+	if (out)
+	{
+		if (n > cap) rc = -2;
+		else memcpy(out, d, n);
+	}
+	stbi_image_free(d);
+	return rc;
+}
+
 // RayTracer::albedo (kind 0, Renderer.h:558-571) / viewNormals (kind 1, :572-581) /
 // direct() with a fresh seed-1 MTRandom (kind 2, :393-407) at pixel centres.
 int ref_aov(void* handle, int kind, float* out)

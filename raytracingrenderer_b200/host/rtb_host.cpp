@@ -128,6 +128,24 @@ int rtbh_build_soup(uint32_t n_tris, int width, int height, const char* out_path
 	}
 }
 
+// Decode a PNG / JPEG file with the loader's own decoders (what Texture::load does before the float
+// conversion).  out may be NULL to query the size.  Returns 0, -1 (cannot read / decode), -2 (cap too small).
+int rtbh_decode_image(const char* path, int* w, int* h, int* channels, unsigned char* out, uint64_t cap)
+{
+	std::vector<unsigned char> file = rtb_img::readFile(path);
+	if (file.empty()) return -1;
+	std::vector<unsigned char> px;
+	bool isJPEG = file.size() > 2 && file[0] == 0xFF && file[1] == 0xD8;
+	bool ok = isJPEG ? rtb_img::decodeJPEG(file, *w, *h, *channels, px) : rtb_img::decodePNG(file, *w, *h, *channels, px);
+	if (!ok) return -1;
+	if (out)
+	{
+		if (px.size() > cap) return -2;
+		memcpy(out, px.data(), px.size());
+	}
+	return 0;
+}
+
 // Test hook: 1 if the builder's parallel sort reproduces std::sort's permutation (ties included) on `keys`.
 int rtbh_sort_selftest(const float* keys, uint32_t n, int par)
 {

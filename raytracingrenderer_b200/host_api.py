@@ -28,6 +28,7 @@ def lib():
         L.rtbh_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.rtbh_build_soup.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
         L.rtbh_sort_selftest.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+        L.rtbh_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -88,3 +89,14 @@ def sort_selftest(keys, par=3):
     """True if the builder's parallel sort gives std::sort's permutation on `keys` (float32)."""
     k = np.ascontiguousarray(keys, np.float32)
     return bool(lib().rtbh_sort_selftest(k.ctypes.data, len(k), int(par)))
+
+
+def decode_image(path):
+    """PNG / JPEG -> uint8 [H, W, channels] with the loader's own decoders; raises on failure."""
+    w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    if lib().rtbh_decode_image(path.encode(), C.byref(w), C.byref(h), C.byref(c), None, 0) != 0:
+        raise RuntimeError("cannot decode " + path)
+    out = np.zeros((h.value, w.value, c.value), np.uint8)
+    if lib().rtbh_decode_image(path.encode(), C.byref(w), C.byref(h), C.byref(c), out.ctypes.data, out.size) != 0:
+        raise RuntimeError("cannot decode " + path)
+    return out

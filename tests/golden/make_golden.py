@@ -79,6 +79,54 @@ def cornell():
     print("cornell halves mean", (a / 32).mean(axis=(0, 1)), (bsum / 32).mean(axis=(0, 1)), "r144", r144.mean(axis=(0, 1)))
     cornell_mis()
     cornell_adaptive()
+    images()
+
+
+def images():
+    """Synthetic PNG / JPEG files (written with Pillow: baseline and progressive, 4:4:4 / 4:2:2 / 4:2:0, odd
+    sizes, 1x1, optimised tables, restart intervals, grey) and the bytes the reference's stb_image decodes
+    from them (oracle/_ref: ref_decode_image = stbi_load): the golden for the product's own decoders."""
+    import hashlib, json
+    from PIL import Image
+    out = os.path.join(HERE, "images")
+    os.makedirs(out, exist_ok=True)
+    rng = np.random.default_rng(11)
+
+    def pattern(w, h):
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([(x * 255 // max(w - 1, 1)), (y * 255 // max(h - 1, 1)), ((x * 7 + y * 13) % 256)], -1).astype(np.uint8)
+        img[h // 4:h // 2, w // 4:w // 2] = rng.integers(0, 256, (h // 2 - h // 4, w // 2 - w // 4, 3), dtype=np.uint8)
+        img[h // 2:, :w // 3] = [250, 10, 10]
+        return img
+    cases = []
+
+    def jpg(name, w, h, **kw):
+        Image.fromarray(pattern(w, h)).save(os.path.join(out, name), "JPEG", **kw)
+        cases.append(name)
+    jpg("base_444_q90.jpg", 64, 48, quality=90, subsampling=0)
+    jpg("base_422_q75.jpg", 70, 50, quality=75, subsampling=1)
+    jpg("base_420_q60_odd.jpg", 67, 45, quality=60, subsampling=2)
+    jpg("base_420_q95_1px.jpg", 1, 1, quality=95, subsampling=2)
+    jpg("base_420_17x9.jpg", 17, 9, quality=85, subsampling=2)
+    jpg("prog_420_q80.jpg", 96, 80, quality=80, subsampling=2, progressive=True)
+    jpg("prog_444_q50_odd.jpg", 53, 61, quality=50, subsampling=0, progressive=True)
+    jpg("prog_422_q92.jpg", 40, 72, quality=92, subsampling=1, progressive=True)
+    jpg("base_420_opt_q30.jpg", 128, 40, quality=30, subsampling=2, optimize=True)
+    jpg("base_420_restart.jpg", 90, 40, quality=80, subsampling=2, restart_marker_blocks=3)
+    jpg("prog_420_restart.jpg", 90, 40, quality=80, subsampling=2, progressive=True, restart_marker_rows=1)
+    Image.fromarray(pattern(48, 40)[:, :, 0]).save(os.path.join(out, "grey_q80.jpg"), "JPEG", quality=80)
+    cases.append("grey_q80.jpg")
+    Image.fromarray(pattern(33, 29)).save(os.path.join(out, "rgb.png"), "PNG")
+    cases.append("rgb.png")
+    rgba = np.dstack([pattern(31, 17), (np.arange(31 * 17).reshape(17, 31) % 256).astype(np.uint8)])
+    Image.fromarray(rgba, "RGBA").save(os.path.join(out, "rgba.png"), "PNG")
+    cases.append("rgba.png")
+    gold = {}
+    for c in cases:
+        a = ref.decode_image(os.path.join(out, c))
+        gold[c] = {"shape": list(a.shape), "sha256": hashlib.sha256(a.tobytes()).hexdigest()}
+    json.dump(gold, open(os.path.join(out, "stb_image_golden.json"), "w"), indent=1)
+    print("images:", len(cases))
 
 
 def cornell_adaptive():

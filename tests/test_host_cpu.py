@@ -103,3 +103,32 @@ def test_parallel_sort_reproduces_std_sort_ties_included(host):
     for name, k in cases.items():
         for par in (0, 1, 4):
             assert host.sort_selftest(k, par), (name, par)
+
+
+def test_image_decoders_against_the_stb_image_golden(host):
+    """PNG and JPEG (baseline / progressive, 4:4:4 / 4:2:2 / 4:2:0, odd sizes, restart intervals, optimised
+    tables, grey) decode to exactly the bytes the reference's stb_image produces (golden written by
+    tests/golden/make_golden.py: images()), and to stb_image's live output when oracle/_ref is present."""
+    import hashlib, json
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "images")
+    gold = json.load(open(os.path.join(d, "stb_image_golden.json")))
+    assert len(gold) >= 14
+    from oracle import ref
+    for name, g in gold.items():
+        a = host.decode_image(os.path.join(d, name))
+        assert list(a.shape) == g["shape"], name
+        assert hashlib.sha256(a.tobytes()).hexdigest() == g["sha256"], name
+        if ref.available():
+            assert np.array_equal(a, ref.decode_image(os.path.join(d, name))), name
+    # truncated and corrupt files are errors, not crashes
+    data = open(os.path.join(d, "prog_420_q80.jpg"), "rb").read()
+    for cut in (2, 20, 200):
+        p = os.path.join(d, "..", "..", "..", "gpurun_out")
+        os.makedirs(p, exist_ok=True)
+        f = os.path.join(p, "_cut.jpg")
+        open(f, "wb").write(data[:cut])
+        try:
+            host.decode_image(f)
+        except RuntimeError:
+            pass
+    os.remove(f)
