@@ -171,8 +171,8 @@ typedef enum rtb_integrator {
 	RTB_INT_NORMALS = 3, /* RayTracer::viewNormals Renderer.h:572-581                */
 	RTB_INT_PATH_MIS = 4 /* pathTrace with computeDirectMIS (Renderer.h:474-557) in place of
 	                      * computeDirect: the estimator the reference ships but leaves switched
-	                      * off.  Runs on the megakernel schedule (its BSDF-strategy probe ray is
-	                      * traced in place).                                                 */
+	                      * off.  Wavefront: the light strategy's segment and the BSDF strategy's
+	                      * probe ray share one queue record (k_wf_mis).                        */
 } rtb_integrator;
 
 /* Philox block index of computeDirectMIS's BSDF-strategy uniforms at path depth k: RTB_RNG_MIS_BLOCK + k

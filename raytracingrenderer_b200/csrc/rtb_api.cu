@@ -391,7 +391,8 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	uint32_t nSlotsAlloc = perPool * (uint32_t)K;
 	// shadow queue: one entry per slot and launch, WF_SHADOW_PER_SLOT with the multi-pass shade stage
 	const size_t F = P.primary_reuse ? WF_SHADOW_PER_SLOT : 1u;
-	size_t need = (size_t)nSlotsAlloc * (4 + 3 * F) * sizeof(float4);
+	const size_t R = (P.integrator == RTB_INT_PATH_MIS) ? 6u : 3u; // float4 per queue record
+	size_t need = (size_t)nSlotsAlloc * (4 + R * F) * sizeof(float4);
 	if (need > ctx->wfStateBytes)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -402,7 +403,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	}
 	if (!ctx->wfGlobal) CK(cudaMalloc((void**)&ctx->wfGlobal, sizeof(WfGlobal)));
 	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, (1 + RTB_MAX_POOLS) * sizeof(unsigned long long)));
-	uint32_t vertices = (P.integrator == RTB_INT_PATH) ? (uint32_t)P.max_depth + 2u : 1u;
+	uint32_t vertices = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_PATH_MIS) ? (uint32_t)P.max_depth + 2u : 1u;
 	// list-scheduling bound on the iterations of a sub-pool: total work / slots + longest job
 	unsigned long long bound64 = (totalJobs * vertices + perPool - 1) / perPool + vertices + 1;
 	if (bound64 > (1ull << 22)) return fail(ctx, RTB_ERR_ARG, "too many samples per call; split the render");
@@ -442,6 +443,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		size_t off = (size_t)k * perPool, n = nSlotsAlloc;
 		a.rayO = base + off, a.rayD = base + n + off, a.hit = base + n * 2 + off, a.thr = base + n * 3 + off;
 		a.shO = base + n * 4 + off * F, a.shD = base + n * (4 + F) + off * F, a.shC = base + n * (4 + 2 * F) + off * F;
+		a.misA = base + n * (4 + 3 * F) + off * F, a.misB = base + n * (4 + 4 * F) + off * F, a.misC = base + n * (4 + 5 * F) + off * F;
 		a.ctrl = ctx->wfCtrl + (size_t)k * bound;
 		a.glob = ctx->wfGlobal;
 		a.tileList = plan ? ctx->wfTilesAdaptive : ctx->wfTiles;
@@ -469,7 +471,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	unsigned gridSlots = (perPool + 127) / 128;
 	if (gridSlots > maxBlocks) gridSlots = maxBlocks;
 	if (gridExtend > (perPool + 127) / 128) gridExtend = (perPool + 127) / 128;
-	bool shadows = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_DIRECT);
+	bool shadows = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_DIRECT || P.integrator == RTB_INT_PATH_MIS);
 	EventPair ev = {getEvent(ctx), getEvent(ctx)};
 	cudaEventRecord(ev.a, ctx->stream);
 	if (P.primary_reuse)
@@ -532,6 +534,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 				case RTB_INT_DIRECT: RTB_SHADE_LAUNCH(RTB_INT_DIRECT); break;
 				case RTB_INT_ALBEDO: RTB_SHADE_LAUNCH(RTB_INT_ALBEDO); break;
 				case RTB_INT_NORMALS: RTB_SHADE_LAUNCH(RTB_INT_NORMALS); break;
+				case RTB_INT_PATH_MIS: RTB_SHADE_LAUNCH(RTB_INT_PATH_MIS); break;
 				default: RTB_SHADE_LAUNCH(RTB_INT_PATH); break;
 				}
 #undef RTB_SHADE_LAUNCH
@@ -546,7 +549,14 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 						cudaEventRecord(ctx->evShaded[k], st);
 						cudaStreamWaitEvent(sst, ctx->evShaded[k], 0);
 					}
-					RTB_TRAV_SWITCH(ti, k_wf_shadow<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
+					if (P.integrator == RTB_INT_PATH_MIS)
+					{
+						RTB_TRAV_SWITCH(ti, k_wf_mis<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
+					}
+					else
+					{
+						RTB_TRAV_SWITCH(ti, k_wf_shadow<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
+					}
 					ctx->launches++;
 					if (ctx->shadowAsync) cudaEventRecord(ctx->evShadowed[k], sst);
 				}
@@ -893,8 +903,7 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	if (spp_count == 0) return RTB_OK;
 	if ((uint64_t)spp_begin + spp_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "sample index overflow");
 	if (int rc = bind(ctx)) return rc;
-	// computeDirectMIS traces its BSDF-strategy probe ray in place: megakernel schedule only
-	bool mega = ctx->params.scheduler == RTB_SCHED_MEGAKERNEL || ctx->params.integrator == RTB_INT_PATH_MIS;
+	bool mega = ctx->params.scheduler == RTB_SCHED_MEGAKERNEL;
 	int rc = mega ? renderMegakernel(ctx, spp_begin, spp_count)
 	                                                           : renderWavefront(ctx, spp_begin, spp_count);
 	if (rc) return rc;
@@ -911,8 +920,7 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 	const rtb_params& P = ctx->params;
 	if (init_samples < 1 || min_samples < 1 || max_samples < min_samples || max_samples > (1u << 20))
 		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: need 1 <= init, 1 <= min <= max <= 2^20");
-	if (P.scheduler != RTB_SCHED_WAVEFRONT || P.integrator == RTB_INT_PATH_MIS)
-		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive runs on the wavefront schedule");
+	if (P.scheduler != RTB_SCHED_WAVEFRONT) return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive runs on the wavefront schedule");
 	if (P.partition != RTB_PART_NONE && P.part_world > 1)
 		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: the tile sample counts come from the whole image; use one device per image");
 	if (int rc = bind(ctx)) return rc;

@@ -235,6 +235,60 @@ RTB_DEV V3 computeDirectMIS(const DevScene& S, const rtb_params& P, const ShadeD
 	return result;
 }
 
+// The light strategy of computeDirectMIS (Renderer.h:483-529) up to the scene->visible() call, for the
+// wavefront schedule.  Returns false for specular surfaces / scenes without lights (computeDirectMIS
+// returns black there and traces nothing).  Otherwise: haveSeg = a visibility segment sd.x -> p2 is needed;
+// contrib = what to add if it is unoccluded (balance weight applied for area lights); nonArea = a visible
+// light ends the estimator without the BSDF strategy (:516-527); pdfAreaPmf = pdf * pmf of the sampled
+// light, which the BSDF strategy converts to solid angle at whatever emitter it hits (:548).
+RTB_DEV bool misLightSample(const DevScene& S, const rtb_params& P, const ShadeD& sd, const rtb_material& m, float uPick, float r1,
+                            float r2, bool& haveSeg, V3& p2, V3& contrib, bool& nonArea, float& pdfAreaPmf)
+{
+	haveSeg = false, nonArea = false;
+	if (m.flags & RTB_MAT_SPECULAR) return false;
+	if (S.n_lights == 0) return false;
+	float nl = (float)S.n_lights;
+	float pmf = 1.0f / nl;
+	int li = (int)(nl * uPick);
+	if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+	rtb_light L = S.lights[li];
+	if (L.type == RTB_LIGHT_AREA)
+	{
+		V3 p = trianglePoint(S, L.triangle, r1, r2);
+		float pdf = 1.0f / L.area;
+		pdfAreaPmf = pdf * pmf;
+		V3 wi = p - sd.x;
+		float l = lengthSq(wi);
+		wi = normalize(wi);
+		float cs = selMax(dot(wi, sd.sN), 0.0f);
+		float cl = selMax(-dot(wi, triangleGNormal(S, L.triangle)), 0.0f);
+		float G = cs * cl / l;
+		if (G > 0.0f)
+		{
+			float pdfB = bsdfPdf(m, sd, wi);
+			float pdfL = (cl > 0.0f) ? (pdfAreaPmf * l / cl) : 0.0f;
+			float w = pdfL / (pdfL + pdfB);
+			contrib = (((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G) * w) / (pmf * pdf);
+			p2 = p;
+			haveSeg = true;
+		}
+		return true;
+	}
+	nonArea = true;
+	V3 wi = uniformSampleSphere(r1, r2);
+	float pdf = (float)(1.0 / (4.0 * RTB_PI_D));
+	pdfAreaPmf = pdf * pmf;
+	V3 emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
+	float G = selMax(dot(wi, sd.sN), 0.0f);
+	if (G > 0.0f)
+	{
+		contrib = ((bsdfEvaluate(S, m, sd, wi) * emitted) * G) / (pmf * pdf);
+		p2 = sd.x + (wi * 10000.0f);
+		haveSeg = true;
+	}
+	return true;
+}
+
 // ---------------------------------------------------------------------------------------
 // k_render: one thread per pixel (a warp = an 8x4 pixel tile); each thread runs its pixel's
 // samples back to back, so a lane whose path ends early immediately regenerates the next

@@ -63,7 +63,10 @@ struct WfArgs
 	float4* thr;   // throughput.xyz, bits(sample ordinal)
 	float4* shO;   // shadow queue: origin, maxT
 	float4* shD;   //               direction, bits(film pixel index)
-	float4* shC;   //               contribution if unoccluded
+	float4* shC;   //               contribution if unoccluded, bits(MIS flags)
+	float4* misA;  // RTB_INT_PATH_MIS only: shading point x, pdf of the BSDF-strategy direction
+	float4* misB;  //                        BSDF-strategy direction, pdf * pmf of the sampled light
+	float4* misC;  //                        T * f * max(dot(wi, sN), 0) / pdf_bsdf (what an emitter's Le is multiplied by)
 	WfCtrl* ctrl;  // [iterations], zeroed before the render
 	WfGlobal* glob;
 	const uint32_t* tileList; // owned 8x4-pixel tiles: (tile row << 16) | tile column
@@ -486,6 +489,52 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevSc
 }
 
 
+// RTB_INT_PATH_MIS: resolves one queue record of computeDirectMIS (Renderer.h:474-557) per thread — the
+// light strategy's visibility test, then (unless a visible non-area light ended the estimator, :516-527)
+// the BSDF strategy's probe ray: closest hit, and if that is an emitter its radiance with the balance weight
+// against the sampled light's pdf converted to solid angle at the hit (:535-552).
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_wf_mis(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
+{
+	const rtb_params& P = A.P;
+	const uint32_t n = A.ctrl[iter].nShadow;
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		float4 o = A.shO[i], d = A.shD[i], c = A.shC[i];
+		uint32_t flags = __float_as_uint(c.w), pixel = __float_as_uint(d.w);
+		if (flags & 1u)
+		{
+			RayD r = mkRay(mk(o), mk(d));
+			tl.shadow++;
+			if (anyVisible<TRAV>(S, r, P.epsilon, o.w, P.cull_rel, tl.sbox, tl.stri))
+			{
+				filmAdd(A.accum, pixel, mk(c));
+				if (flags & 2u) continue;
+			}
+		}
+		float4 xa = A.misA[i], wb = A.misB[i];
+		V3 x = mk(xa), wiB = mk(wb);
+		RayD pr = mkRay(x + (wiB * P.epsilon), wiB);
+		HitD h;
+		closestHit<TRAV>(S, pr, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+		tl.closest++;
+		if (h.id == RTB_MISS_ID) continue;
+		ShadeD sh;
+		calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), pr, sh);
+		rtb_material mh = S.mats[sh.mat];
+		if (!(mh.flags & RTB_MAT_LIGHT)) continue;
+		V3 wi = sh.x - x;
+		float dist2 = lengthSq(wi);
+		wi = normalize(wi);
+		float cl = selMax(0.0f, dot(mk(-wi.x, -wi.y, -wi.z), sh.sN));
+		float pdfL = (cl > 0.0f) ? (wb.w * dist2 / cl) : 0.0f;
+		float wgt = xa.w / (xa.w + pdfL);
+		filmAdd(A.accum, pixel, (mk(A.misC[i]) * mk(mh.emission)) * wgt);
+	}
+	flushTally(tl, A.counters);
+}
+
 template <int INTEGRATOR, bool REUSE>
 __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
@@ -493,7 +542,8 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 	if (iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
 	const uint32_t lane = threadIdx.x & 31u;
 	uint32_t nAlive = 0, nDone = 0, phase = 0;
-	__shared__ float4 sStage[3][128]; // the thread's shadow-ray record waits here across the reservation barriers (12 registers)
+	constexpr int NREC = (INTEGRATOR == RTB_INT_PATH_MIS) ? 6 : 3;
+	__shared__ float4 sStage[NREC][128]; // the thread's queue record waits here across the reservation barriers (12 / 24 registers)
 	__shared__ uint32_t sCountS[2][4], sCountJ[2][4];
 	__shared__ unsigned int sBaseS[2];
 	__shared__ unsigned long long sBaseJ[2];
@@ -541,7 +591,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 				uint32_t id = __float_as_uint(hh.x);
 				if (id == RTB_MISS_ID)
 				{
-					if (INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_ALBEDO) add = backgroundEval(S, ray.d);
+					if (INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_PATH_MIS || INTEGRATOR == RTB_INT_ALBEDO) add = backgroundEval(S, ray.d);
 				}
 				else
 				{
@@ -556,7 +606,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 						rtb_material m = S.mats[sd.mat];
 						if (m.flags & RTB_MAT_LIGHT)
 						{
-							if (INTEGRATOR == RTB_INT_PATH)
+							if (INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_PATH_MIS)
 							{
 								if (canHitLight) add = T * mk(m.emission);
 							}
@@ -571,7 +621,39 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 						{
 							float4 ua = rngBlock(P.seed, pixel, sample, 2u * depth);
 							V3 p1, p2, contrib;
-							if (directSample(S, P, sd, m, ua.x, ua.y, ua.z, p1, p2, contrib))
+							if (INTEGRATOR == RTB_INT_PATH_MIS)
+							{
+								// computeDirectMIS (Renderer.h:474-557): the light strategy's segment and the BSDF
+								// strategy's probe ray go into ONE queue record, resolved by k_wf_mis
+								bool haveSeg, nonArea;
+								float pdfAreaPmf;
+								if (misLightSample(S, P, sd, m, ua.x, ua.y, ua.z, haveSeg, p2, contrib, nonArea, pdfAreaPmf))
+								{
+									float4 um = rngBlock(P.seed, pixel, sample, RTB_RNG_MIS_BLOCK + depth);
+									V3 fB;
+									float pdfB;
+									V3 wiB = bsdfSample(S, m, sd, um.x, um.y, um.z, fB, pdfB);
+									V3 payload = ((T * fB) * selMax(0.0f, dot(wiB, sd.sN))) / pdfB;
+									V3 dir = mk(0.0f, 0.0f, 0.0f), o = sd.x, c = mk(0.0f, 0.0f, 0.0f);
+									float maxT = 0.0f;
+									if (haveSeg)
+									{
+										dir = p2 - sd.x;
+										maxT = sqrtf(lengthSq(dir)) - (2.0f * P.epsilon);
+										dir = normalize(dir);
+										o = sd.x + (dir * P.epsilon);
+										c = T * contrib;
+									}
+									sStage[0][threadIdx.x] = make_float4(o.x, o.y, o.z, maxT);
+									sStage[1][threadIdx.x] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
+									sStage[2][threadIdx.x] = make_float4(c.x, c.y, c.z, __uint_as_float((haveSeg ? 1u : 0u) | (nonArea ? 2u : 0u)));
+									sStage[NREC - 3][threadIdx.x] = make_float4(sd.x.x, sd.x.y, sd.x.z, pdfB);
+									sStage[NREC - 2][threadIdx.x] = make_float4(wiB.x, wiB.y, wiB.z, pdfAreaPmf);
+									sStage[NREC - 1][threadIdx.x] = make_float4(payload.x, payload.y, payload.z, 0.0f);
+									haveShadow = true;
+								}
+							}
+							else if (directSample(S, P, sd, m, ua.x, ua.y, ua.z, p1, p2, contrib))
 							{
 								// Scene::visible's ray (Scene.h:161-169); traced by k_wf_shadow
 								V3 dir = p2 - p1;
@@ -584,7 +666,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 								sStage[2][threadIdx.x] = make_float4(c.x, c.y, c.z, 0.0f);
 								haveShadow = true;
 							}
-							if (INTEGRATOR == RTB_INT_PATH && !((int)depth > P.max_depth))
+							if ((INTEGRATOR == RTB_INT_PATH || INTEGRATOR == RTB_INT_PATH_MIS) && !((int)depth > P.max_depth))
 							{
 								float rr = selMin(lum(T), P.rr_cap);
 								if (ua.w < rr)
@@ -642,6 +724,8 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 				uint32_t at = sBaseS[ph] + __popc(mS & ((1u << lane) - 1u));
 				for (uint32_t w = 0; w < warp; w++) at += sCountS[ph][w];
 				A.shO[at] = sStage[0][threadIdx.x], A.shD[at] = sStage[1][threadIdx.x], A.shC[at] = sStage[2][threadIdx.x];
+				if (INTEGRATOR == RTB_INT_PATH_MIS)
+					A.misA[at] = sStage[NREC - 3][threadIdx.x], A.misB[at] = sStage[NREC - 2][threadIdx.x], A.misC[at] = sStage[NREC - 1][threadIdx.x];
 			}
 			// ---- regeneration: finished paths take the next jobs of the render (the rare lanes that
 			// drew a padding pixel of an edge tile retry warp-wise)

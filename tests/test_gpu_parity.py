@@ -249,7 +249,7 @@ def test_mis_estimator_equals_the_oracle_sample_for_sample(rtb, oracle_mod, name
     """RTB_INT_PATH_MIS (computeDirectMIS, Renderer.h:474-557): same uniforms on both sides."""
     rt = gpu_scene(rtb, name)
     spp = 2
-    rt.set_params(integrator=abi.INT_PATH_MIS)
+    rt.set_params(integrator=abi.INT_PATH_MIS, primary_reuse=0)
     rt.render(spp, 0)
     img = rt.read_film()
     want, st = oracle_mod.Oracle(rt.scene, integrator=abi.INT_PATH_MIS).render(spp)
@@ -261,6 +261,18 @@ def test_mis_estimator_equals_the_oracle_sample_for_sample(rtb, oracle_mod, name
     assert g["samples"] == st["samples"]
     assert abs(g["closest_rays"] / st["closest_rays"] - 1) < 2e-3
     assert abs(g["shadow_rays"] / st["shadow_rays"] - 1) < 2e-3
+    # the megakernel schedule traces the probe ray in place: same samples, same counters
+    rt.set_params(scheduler=abi.SCHED_MEGAKERNEL)
+    rt.clear()
+    rt.render(spp, 0)
+    mk = rt.read_film()
+    assert np.allclose(mk, img, rtol=1e-4, atol=1e-5)
+    gm_ = rt.stats()
+    assert (gm_["closest_rays"], gm_["shadow_rays"]) == (g["closest_rays"], g["shadow_rays"])
+    rt.set_params(scheduler=abi.SCHED_WAVEFRONT, primary_reuse=1)
+    rt.clear()
+    rt.render(spp, 0)
+    assert np.array_equal(rt.read_film(), img)           # primary-hit table: same bits
     if name == "cornell-box":
         gm = np.load(os.path.join(GOLDEN, "cornell_mis_blocks.npz"))
         rt.clear()
