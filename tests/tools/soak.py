@@ -61,5 +61,23 @@ for name, spp in (("cornell-box", 96), ("materialball", 48), ("materialball_glas
     a, _ = render(rt, 4, sampling=abi.SAMPLING_IMPORTANCE)
     check("%s importance sampling finite" % name, np.isfinite(a).all())
     rt.close()
+# context create / upload / render / destroy many times: device memory must come back
+import torch
+flat = host_api.load_scene(os.path.join("scenes", "_staged", "materialball"))
+free0 = None
+for i in range(12):
+    rt = rtb.RayTracer(0)
+    rt.init(flat)
+    rt.set_params(primary_reuse=i & 1, integrator=abi.INT_PATH_MIS if i % 3 == 0 else abi.INT_PATH)
+    rt.render(4, 0)
+    if i % 4 == 1:
+        rt.adaptiveRender(2, 1, 16)
+    rt.read_film()
+    rt.close()
+    torch.cuda.synchronize()
+    free = torch.cuda.mem_get_info()[0]
+    if i == 1:
+        free0 = free
+check("12 x create/render/destroy: no device memory growth (%.1f MB)" % ((free0 - free) / 1e6), free0 - free < 64e6)
 print("FAILURES:", bad)
 sys.exit(1 if bad else 0)
