@@ -228,7 +228,9 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keeps NCCL's version banner off stdout (one JSON line)
+        # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout: send it to a file so that
+        # stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "rtb200_nccl_%h_%p.log"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     name, flats = load_workload(args.scene, log)
     spp = args.spp
