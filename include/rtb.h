@@ -19,6 +19,7 @@
 #define RTB_H_
 
 #include <stddef.h>
+#include <math.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -51,6 +52,70 @@ typedef struct rtb_camera {
 	float width, height;    /* Camera::width/height (floats, as in the reference)    */
 	float pad_[3];
 } rtb_camera; /* 160 B */
+
+/* What Camera::init / Camera::updateView (RTBase/Scene.h:22-41) derive besides the fields above; only
+ * light tracing (connectToCamera, Renderer.h:233-260) needs them.  rtb_camera carries the two matrices the
+ * camera rays need bit-exactly; the rest is re-derived from them here — one definition, used by the library
+ * and by its test oracle.  Matrices are row-major like RTBase's Matrix::m (Core.h:238-262). */
+typedef struct rtb_camera_ext {
+	float proj[16];         /* Camera::projectionMatrix = inverse of inv_proj         */
+	float world_to_cam[16]; /* Camera::cameraToView     = inverse of cam_to_world     */
+	float view_dir[3];      /* Camera::viewDirection                                  */
+	float afilm;            /* Camera::Afilm                                          */
+} rtb_camera_ext;
+
+static inline int rtb_invert4(const float* m, float* out)
+{
+	double a[4][8];
+	int i, j, k;
+	for (i = 0; i < 4; i++)
+		for (j = 0; j < 4; j++) a[i][j] = m[i * 4 + j], a[i][4 + j] = (i == j) ? 1.0 : 0.0;
+	for (i = 0; i < 4; i++)
+	{
+		int piv = i;
+		double best = a[i][i] < 0 ? -a[i][i] : a[i][i], f;
+		for (k = i + 1; k < 4; k++)
+		{
+			double v = a[k][i] < 0 ? -a[k][i] : a[k][i];
+			if (v > best) best = v, piv = k;
+		}
+		if (best == 0.0) return 0;
+		if (piv != i)
+			for (j = 0; j < 8; j++) f = a[i][j], a[i][j] = a[piv][j], a[piv][j] = f;
+		f = 1.0 / a[i][i];
+		for (j = 0; j < 8; j++) a[i][j] *= f;
+		for (k = 0; k < 4; k++)
+			if (k != i && a[k][i] != 0.0)
+			{
+				f = a[k][i];
+				for (j = 0; j < 8; j++) a[k][j] -= f * a[i][j];
+			}
+	}
+	for (i = 0; i < 4; i++)
+		for (j = 0; j < 4; j++) out[i * 4 + j] = (float)a[i][4 + j];
+	return 1;
+}
+
+static inline int rtb_camera_derive(const rtb_camera* c, rtb_camera_ext* e)
+{
+	const float* ip = c->inv_proj;
+	const float* cw = c->cam_to_world;
+	float vx, vy, vz, w, dx, dy, dz, l, wlens, aspect;
+	if (!rtb_invert4(ip, e->proj) || !rtb_invert4(cw, e->world_to_cam)) return 0;
+	/* viewDirection = normalize(camera.mulVec(inverseProjection.mulPointAndPerspectiveDivide((0,0,1)))) */
+	w = 1.0f / (ip[14] + ip[15]);
+	vx = (ip[2] + ip[3]) * w, vy = (ip[6] + ip[7]) * w, vz = (ip[10] + ip[11]) * w;
+	dx = (vx * cw[0] + vy * cw[1]) + vz * cw[2];
+	dy = (vx * cw[4] + vy * cw[5]) + vz * cw[6];
+	dz = (vx * cw[8] + vy * cw[9]) + vz * cw[10];
+	l = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
+	e->view_dir[0] = dx * l, e->view_dir[1] = dy * l, e->view_dir[2] = dz * l;
+	/* Afilm = Wlens * Hlens, Wlens = 2 / P[1][1], Hlens = Wlens * (P[0][0] / P[1][1])  (Scene.h:28-31) */
+	wlens = 2.0f / e->proj[5];
+	aspect = e->proj[0] / e->proj[5];
+	e->afilm = wlens * (wlens * aspect);
+	return 1;
+}
 
 /* One node of the reference BVH (RTBase/Geometry.h:294-313 `BVHNode`), flattened in
  * pre-order (left subtree directly follows its parent).  The device needs the reference's
@@ -319,6 +384,12 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count);
  * Wavefront schedule, single device per image.  Synchronous (the plan goes through the host).      */
 int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_samples, uint32_t max_samples,
                         uint32_t* tile_samples, float* tile_variance);
+/* pass_count x RayTracer::lightTracer() (Renderer.h:220-326; a commented-out alternative in render(), :883):
+ * each pass traces width*height paths FROM the area lights and connects every diffuse vertex to the camera
+ * (connectToCamera, :233-260); splats land anywhere on the film (box filter).  Passes are numbered for the
+ * counter-based RNG like samples are; SPP grows by pass_count.  Scenes without area lights add nothing.
+ * Single device per image (shard passes, not pixels).  Asynchronous.                                   */
+int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count);
 /* Film::film (Imaging.h:204): waits for the device and copies the running SUM (not the
  * mean; Film::save divides by SPP, Imaging.h:262-271) as width*height*3 floats (r,g,b per
  * pixel, row-major) to host memory; *spp receives Film::SPP.  Either may be NULL.         */

@@ -45,6 +45,7 @@ def _lib(variant=""):
         lib.ref_eval_background.argtypes = [vp, vp, C.c_uint64, vp]
         lib.ref_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.ref_render_adaptive.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        lib.ref_render_light.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         lib.ref_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_uint64]
         lib.ref_aov.argtypes = [vp, C.c_int, vp]
         lib.ref_tonemap.argtypes = [vp, vp, C.c_int, C.c_float, vp]
@@ -158,6 +159,13 @@ class RefScene:
         secs = C.c_double(0)
         self.lib.ref_render_adaptive(self.h, int(threads), 1 if fresh else 0, _p(film), _p(var), _p(cnt), C.addressof(secs))
         return film, cnt, var, secs.value
+
+    def render_light(self, passes, fresh=True):
+        """passes x lightTracer() -> (film_sum, seconds)."""
+        film = np.zeros((self.height, self.width, 3), "<f4")
+        secs = C.c_double(0)
+        self.lib.ref_render_light(self.h, int(passes), 1 if fresh else 0, _p(film), C.addressof(secs))
+        return film, secs.value
 
     def aov(self, kind):
         k = {"albedo": 0, "normals": 1, "direct": 2}[kind]

@@ -438,6 +438,35 @@ int ref_render_adaptive(void* handle, int threads, int fresh, float* film_sum, f
 	return h->rt->getSPP();
 }
 
+// `passes` x { film->incrementSPP(); lightTracer(); } (Renderer.h:220-231, 876-884: the commented-out
+// alternative of render()).  Single-threaded in the reference (samplers[0]).
+int ref_render_light(void* handle, int passes, int fresh, float* film_sum, double* seconds)
+{
+	RefScene* h = (RefScene*)handle;
+	ensureRT(h, 1);
+	if (fresh)
+	{
+		h->rt->clear();
+		for (int i = 0; i < h->rt->numProcs; i++) h->rt->samplers[i] = MTRandom();
+	}
+	auto t0 = std::chrono::steady_clock::now();
+	for (int i = 0; i < passes; i++)
+	{
+		h->rt->film->incrementSPP();
+		h->rt->lightTracer();
+	}
+	auto t1 = std::chrono::steady_clock::now();
+	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	size_t n = (size_t)h->rt->film->width * h->rt->film->height;
+	for (size_t i = 0; i < n; i++)
+	{
+		film_sum[i * 3] = h->rt->film->film[i].r;
+		film_sum[i * 3 + 1] = h->rt->film->film[i].g;
+		film_sum[i * 3 + 2] = h->rt->film->film[i].b;
+	}
+	return h->rt->getSPP();
+}
+
 // stbi_load (the decoder behind Texture::load, Imaging.h:51) on one file: the golden for the product's
 // own PNG / JPEG decoders.  out may be NULL to query the size.
 int ref_decode_image(const char* path, int* w, int* h, int* channels, unsigned char* out, uint64_t cap)

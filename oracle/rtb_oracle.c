@@ -901,6 +901,128 @@ int oracle_render_adaptive(const rtb_scene_desc* s, const rtb_params* P, uint32_
 	return 0;
 }
 
+/* ---------------- RayTracer::lightTracer, Renderer.h:220-326 ------------------------------
+ * One pass = width*height light paths (:223-229).  lightTrace_init (:262-288): uniform light pick; only
+ * area lights emit paths; position on the triangle, cosine direction about its geometric normal
+ * (Lights.h:67-82); Le = evaluate(-wi) * cos / (pmf * pdfDir * pdfPos); the light vertex and every
+ * non-specular, non-emitting hit are connected to the camera (connectToCamera :233-260: projection,
+ * G term, visibility, W_e = 1 / (Afilm cos^4), box-filter splat at ((int)x, (int)y)); Russian roulette
+ * with min(Lum(T), 0.9) and no depth limit (:307-315); T *= f |cos| / pdf (:321).
+ * RNG: Philox counter (path, pass, block, 1): block 0 = [pick, pos r1, pos r2, dir r1], block 1 = [dir r2],
+ * vertex k: block 2 + k = [roulette, bsdf r1, bsdf r2, bsdf r3].                                     */
+static void rng_block_lt(uint32_t seed, uint32_t path, uint32_t pass, uint32_t block, float u[4])
+{
+	uint32_t c[4];
+	int i;
+	c[0] = path, c[1] = pass, c[2] = block, c[3] = 1;
+	philox(c, seed, 0x52544232u);
+	for (i = 0; i < 4; i++) u[i] = ((float)(c[i] >> 9) + 0.5f) * 1.1920928955078125e-7f;
+}
+
+static v3 mul_point(const float* m, v3 v) /* Core.h:302-309 */
+{
+	return V((v.x * m[0] + v.y * m[1] + v.z * m[2]) + m[3], (v.x * m[4] + v.y * m[5] + v.z * m[6]) + m[7],
+	         (v.x * m[8] + v.y * m[9] + v.z * m[10]) + m[11]);
+}
+
+static void connect_to_camera(const rtb_scene_desc* s, const rtb_params* P, const rtb_camera_ext* ce, v3 p, v3 n, v3 col, float* film,
+                              tally_t* tl)
+{
+	/* Camera::projectOntoCamera, Scene.h:55-69 */
+	v3 pv = mul_point(ce->world_to_cam, p), v1 = mul_point(ce->proj, pv), dir;
+	const float* m = ce->proj;
+	float w = (m[12] * pv.x) + (m[13] * pv.y) + (m[14] * pv.z) + m[15], x, y, dist2, cs, cc, G, We;
+	int px, py;
+	w = 1.0f / w;
+	v1 = scl(v1, w);
+	x = (v1.x + 1.0f) * 0.5f;
+	y = (v1.y + 1.0f) * 0.5f;
+	if (x < 0 || x > 1.0f || y < 0 || y > 1.0f) return;
+	x = x * s->camera.width;
+	y = 1.0f - y;
+	y = y * s->camera.height;
+	dir = sub(Vp(s->camera.origin), p);
+	dist2 = dot3(dir, dir);
+	dir = norm3(dir);
+	cs = dot3(n, dir);
+	cc = dot3(Vp(ce->view_dir), neg(dir));
+	if (cs < 0.0f || cc < 0.0f) return;
+	G = (cs * cc) / dist2;
+	tl->shadow++;
+	if (!scene_visible_tl(s, p, Vp(s->camera.origin), P->epsilon, tl)) return;
+	We = 1 / (ce->afilm * ((cc * cc) * (cc * cc)));
+	col = scl(scl(col, We), G);
+	px = (int)x, py = (int)y;
+	if (px >= 0 && px < (int)s->camera.width && py >= 0 && py < (int)s->camera.height)
+	{
+		float* f = film + ((size_t)py * (size_t)s->camera.width + px) * 3;
+		f[0] += col.x, f[1] += col.y, f[2] += col.z;
+	}
+}
+
+int oracle_render_light(const rtb_scene_desc* s, const rtb_params* P, uint32_t pass_begin, uint32_t pass_count, float* film_sum,
+                        uint64_t* stats /* paths, closest, shadow (camera connections) */)
+{
+	rtb_camera_ext ce;
+	uint32_t W = (uint32_t)s->camera.width, H = (uint32_t)s->camera.height, pass, path;
+	tally_t tl;
+	memset(&tl, 0, sizeof(tl));
+	if (!rtb_camera_derive(&s->camera, &ce)) return -1;
+	for (pass = pass_begin; pass < pass_begin + pass_count; pass++)
+		for (path = 0; path < W * H; path++)
+		{
+			float u0[4], u1[4], pdfPos, pdfDir, pmf, cosTheta;
+			const rtb_light* L;
+			v3 p, wl, wi, nL, Le, T = V(1.0f, 1.0f, 1.0f), fu, fv, fw;
+			ray_t r;
+			int li, k;
+			tl.samples++;
+			if (s->n_lights == 0) continue;
+			rng_block_lt(P->seed, path, pass, 0, u0);
+			rng_block_lt(P->seed, path, pass, 1, u1);
+			pmf = 1.f / s->n_lights;
+			li = (int)(s->n_lights * u0[0]);
+			if (li > (int)s->n_lights - 1) li = (int)s->n_lights - 1;
+			L = &s->lights[li];
+			if (L->type != RTB_LIGHT_AREA) continue;
+			p = triangle_sample(s, L->triangle, u0[1], u0[2], &pdfPos);
+			wl = cosine_sample_hemisphere(u0[3], u1[0]);
+			pdfDir = cosine_hemisphere_pdf(wl);
+			nL = triangle_gnormal(s, L->triangle);
+			frame_from_vector(nL, &fu, &fv, &fw);
+			wi = add(add(scl(fu, wl.x), scl(fv, wl.y)), scl(fw, wl.z));
+			cosTheta = dot3(nL, wi);
+			/* AreaLight::evaluate(-wi): emission if dot(-wi, gNormal) < 0 (Lights.h:41-48) */
+			Le = (dot3(neg(wi), nL) < 0) ? Vp(L->emission) : V(0, 0, 0);
+			Le = dvd(scl(Le, cosTheta), (pmf * pdfDir * pdfPos));
+			connect_to_camera(s, P, &ce, p, nL, Le, film_sum, &tl);
+			r = make_ray(p, wi);
+			for (k = 0; k < 100000; k++)
+			{
+				rtb_hit h = scene_traverse_tl(s, &r, P->epsilon, &tl);
+				shade_t sd;
+				const rtb_material* m;
+				float uk[4], rr, pdf;
+				v3 f, wi2;
+				tl.closest++;
+				shading_data(s, &h, &r, &sd);
+				if (!(sd.t < FLT_MAX)) break;
+				m = &s->materials[sd.mat];
+				if ((m->flags & RTB_MAT_LIGHT) || (m->flags & RTB_MAT_SPECULAR)) break;
+				connect_to_camera(s, P, &ce, sd.x, sd.sN, mul(mul(T, bsdf_evaluate(s, m, &sd)), Le), film_sum, &tl);
+				rng_block_lt(P->seed, path, pass, 2u + (uint32_t)k, uk);
+				rr = win_min(lum3(T), P->rr_cap);
+				if (uk[0] < rr) T = dvd(T, rr);
+				else break;
+				wi2 = bsdf_sample(s, m, &sd, uk[1], uk[2], uk[3], &f, &pdf);
+				T = dvd(scl(mul(T, f), fabsf(dot3(wi2, sd.sN))), pdf);
+				r = make_ray(add(sd.x, scl(wi2, P->epsilon)), wi2);
+			}
+		}
+	if (stats) stats[0] = tl.samples, stats[1] = tl.closest, stats[2] = tl.shadow;
+	return 0;
+}
+
 /* oracle_render + the canonical-traversal work of every ray it traced.
  * stats = samples, closest, shadow, closest box tests, closest tri tests, shadow box, shadow tri.
  * Not re-entrant (one process-wide switch): tests/tools/canonical_counts.py is its only caller. */

@@ -104,6 +104,7 @@ struct rtb_ctx
 	cudaStream_t shadowStreams[RTB_MAX_POOLS] = {};
 	cudaEvent_t evShaded[RTB_MAX_POOLS] = {}, evShadowed[RTB_MAX_POOLS] = {};
 	bool shadowAsync = true;
+	unsigned lightGrid = 0;
 	cudaEvent_t evFork = nullptr;
 	uint64_t wfIterations = 0, wfHostSyncs = 0;
 };
@@ -908,6 +909,45 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	                                                           : renderWavefront(ctx, spp_begin, spp_count);
 	if (rc) return rc;
 	ctx->spp += spp_count;
+	return RTB_OK;
+}
+
+// pass_count x RayTracer::lightTracer() (Renderer.h:220-231).
+int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_light before rtb_upload_scene");
+	if (pass_count == 0) return RTB_OK;
+	if ((uint64_t)pass_begin + pass_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "pass index overflow");
+	if (ctx->params.partition != RTB_PART_NONE && ctx->params.part_world > 1)
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_light: light paths land anywhere on the film; shard the passes over devices instead");
+	if (int rc = bind(ctx)) return rc;
+	rtb_camera_ext ce;
+	if (!rtb_camera_derive(&ctx->S.cam, &ce)) return fail(ctx, RTB_ERR_ARG, "camera matrices are singular");
+	RenderArgs A;
+	A.accum = ctx->accum;
+	A.counters = ctx->counters;
+	A.spp_begin = pass_begin, A.spp_count = pass_count;
+	A.width = ctx->width, A.height = ctx->height;
+	A.P = ctx->params;
+	if (!ctx->lightGrid)
+	{
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, ctx->device));
+		ctx->lightGrid = (unsigned)prop.multiProcessorCount * 16u;
+	}
+	unsigned long long total = (unsigned long long)ctx->width * ctx->height * pass_count;
+	unsigned grid = ctx->lightGrid;
+	if ((unsigned long long)grid * 128ull > total) grid = (unsigned)((total + 127ull) / 128ull);
+	EventPair ev = {getEvent(ctx), getEvent(ctx)};
+	cudaEventRecord(ev.a, ctx->stream);
+	RTB_TRAV_SWITCH(ctx->params.traversal, k_light_trace<TR><<<grid, 128, 0, ctx->stream>>>(ctx->S, A, ce));
+	cudaEventRecord(ev.b, ctx->stream);
+	ctx->pending.push_back(ev);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	ctx->filmDirty = true;
+	ctx->spp += pass_count; // Film::incrementSPP once per render() (Renderer.h:878)
 	return RTB_OK;
 }
 

@@ -762,8 +762,9 @@ RTB_DEV uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1)
 	return c;
 }
 RTB_DEV float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-7f; }
-RTB_DEV float4 rngBlock(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t block)
+// stream 0 = camera paths (pixel, sample, block); stream 1 = light paths (path, pass, block)
+RTB_DEV float4 rngBlock(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t block, uint32_t stream = 0u)
 {
-	uint4 r = philox4x32_10(make_uint4(pixel, sample, block, 0u), seed, 0x52544232u);
+	uint4 r = philox4x32_10(make_uint4(pixel, sample, block, stream), seed, 0x52544232u);
 	return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
 }

@@ -442,6 +442,110 @@ __global__ void __launch_bounds__(64) k_render(const __grid_constant__ DevScene 
 }
 
 // ---------------------------------------------------------------------------------------
+// RayTracer::lightTracer (Renderer.h:220-326): one thread per light path, width*height paths per pass.
+// lightTrace_init (:262-288): uniform light pick, only area lights emit; position on the triangle, cosine
+// direction about its geometric normal (Lights.h:67-82).  The light vertex and every non-specular,
+// non-emitting hit are connected to the camera (connectToCamera :233-260) and splatted with the box filter
+// (Imaging.h:209-232) — an atomic add into the fixed-point film.  Russian roulette min(Lum(T), 0.9), no depth
+// limit (:307-315).  RNG stream 1: block 0 = [pick, pos r1, pos r2, dir r1], block 1 = [dir r2],
+// vertex k: block 2 + k = [roulette, bsdf r1, r2, r3].
+// ---------------------------------------------------------------------------------------
+RTB_DEV V3 mulPoint(const float* m, V3 v) // Core.h:302-309
+{
+	return mk((v.x * m[0] + v.y * m[1] + v.z * m[2]) + m[3], (v.x * m[4] + v.y * m[5] + v.z * m[6]) + m[7],
+	          (v.x * m[8] + v.y * m[9] + v.z * m[10]) + m[11]);
+}
+
+template <int TRAV>
+RTB_DEV void connectToCamera(const DevScene& S, const rtb_params& P, const rtb_camera_ext& ce, long long* accum, V3 p, V3 n, V3 col,
+                             Tally& tl)
+{
+	// Camera::projectOntoCamera, Scene.h:55-69
+	V3 pv = mulPoint(ce.world_to_cam, p), v1 = mulPoint(ce.proj, pv);
+	const float* m = ce.proj;
+	float w = (m[12] * pv.x) + (m[13] * pv.y) + (m[14] * pv.z) + m[15];
+	w = 1.0f / w;
+	v1 = v1 * w;
+	float x = (v1.x + 1.0f) * 0.5f, y = (v1.y + 1.0f) * 0.5f;
+	if (x < 0.0f || x > 1.0f || y < 0.0f || y > 1.0f) return;
+	x = x * S.cam.width;
+	y = 1.0f - y;
+	y = y * S.cam.height;
+	V3 origin = mk(S.cam.origin);
+	V3 dir = origin - p;
+	float dist2 = lengthSq(dir);
+	dir = normalize(dir);
+	float cs = dot(n, dir);
+	float cc = dot(mk(ce.view_dir), -dir);
+	if (cs < 0.0f || cc < 0.0f) return;
+	float G = (cs * cc) / dist2;
+	tl.shadow++;
+	if (!sceneVisible<TRAV>(S, p, origin, P.epsilon, P.cull_rel, tl.sbox, tl.stri)) return;
+	float We = 1.0f / (ce.afilm * ((cc * cc) * (cc * cc)));
+	col = (col * We) * G;
+	int px = (int)x, py = (int)y;
+	if (px >= 0 && px < (int)S.cam.width && py >= 0 && py < (int)S.cam.height) filmAdd(accum, (uint32_t)py * (uint32_t)S.cam.width + (uint32_t)px, col);
+}
+
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_light_trace(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
+                                                     const __grid_constant__ rtb_camera_ext ce)
+{
+	const rtb_params& P = A.P;
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	const unsigned long long perPass = (unsigned long long)A.width * A.height, total = perPass * A.spp_count;
+	for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (unsigned long long)gridDim.x * blockDim.x)
+	{
+		uint32_t pass = A.spp_begin + (uint32_t)(j / perPass), path = (uint32_t)(j % perPass);
+		tl.samples++;
+		if (S.n_lights == 0) continue;
+		float4 u0 = rngBlock(P.seed, path, pass, 0u, 1u), u1 = rngBlock(P.seed, path, pass, 1u, 1u);
+		float nl = (float)S.n_lights;
+		float pmf = 1.0f / nl;
+		int li = (int)(nl * u0.x);
+		if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+		rtb_light L = S.lights[li];
+		if (L.type != RTB_LIGHT_AREA) continue;
+		V3 p = trianglePoint(S, L.triangle, u0.y, u0.z);
+		float pdfPos = 1.0f / L.area;
+		V3 wl = cosineSampleHemisphere(u0.w, u1.x);
+		float pdfDir = (wl.z >= 0.0f) ? (wl.z * RTB_INV_PI_F) : 0.0f;
+		V3 nL = triangleGNormal(S, L.triangle);
+		V3 fu, fv, fw;
+		frameFromVector(nL, fu, fv, fw);
+		V3 wi = ((fu * wl.x) + (fv * wl.y)) + (fw * wl.z);
+		float cosTheta = dot(nL, wi);
+		V3 Le = (dot(-wi, nL) < 0.0f) ? mk(L.emission) : mk(0.0f, 0.0f, 0.0f); // AreaLight::evaluate(-wi), Lights.h:41-48
+		Le = (Le * cosTheta) / (pmf * pdfDir * pdfPos);
+		connectToCamera<TRAV>(S, P, ce, A.accum, p, nL, Le, tl);
+		RayD r = mkRay(p, wi);
+		V3 T = mk(1.0f, 1.0f, 1.0f);
+		for (uint32_t k = 0; k < 100000u; k++)
+		{
+			HitD h;
+			closestHit<TRAV>(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+			tl.closest++;
+			if (h.id == RTB_MISS_ID) break;
+			ShadeD sd;
+			calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), r, sd);
+			rtb_material m = S.mats[sd.mat];
+			if (m.flags & (RTB_MAT_LIGHT | RTB_MAT_SPECULAR)) break;
+			connectToCamera<TRAV>(S, P, ce, A.accum, sd.x, sd.sN, (T * bsdfEvaluate(S, m, sd, mk(0.0f, 1.0f, 0.0f))) * Le, tl);
+			float4 uk = rngBlock(P.seed, path, pass, 2u + k, 1u);
+			float rr = selMin(lum(T), P.rr_cap);
+			if (!(uk.x < rr)) break;
+			T = T / rr;
+			V3 f;
+			float pdf;
+			V3 wi2 = bsdfSample(S, m, sd, uk.y, uk.z, uk.w, f, pdf);
+			T = ((T * f) * fabsf(dot(wi2, sd.sN))) / pdf;
+			r = mkRay(sd.x + (wi2 * P.epsilon), wi2);
+		}
+	}
+	flushTally(tl, A.counters);
+}
+
+// ---------------------------------------------------------------------------------------
 // Parity kernels
 // ---------------------------------------------------------------------------------------
 template <int TRAV>

@@ -122,6 +122,23 @@ public:
 		filmOnHost = false;
 		if (presentEveryFrame && canvas) presentFilmToCanvas();
 	}
+	// RTBase/Renderer.h:220-231 (render()'s commented-out alternative at :883): one light-tracing pass.
+	void lightTracer()
+	{
+		uint32_t pass = film->SPP > 0 ? (uint32_t)film->SPP - 1u : 0u; // render() has incremented SPP already
+		check(rtb_render_light(ctx, pass, 1), "rtb_render_light");
+		check(rtb_set_spp(ctx, (uint32_t)film->SPP), "rtb_set_spp");
+		filmOnHost = false;
+		if (presentEveryFrame && canvas) presentFilmToCanvas();
+	}
+	void renderLight(int n = 1)
+	{
+		for (int i = 0; i < n; i++)
+		{
+			film->incrementSPP();
+			lightTracer();
+		}
+	}
 	void renderAdaptive()
 	{
 		film->incrementSPP();

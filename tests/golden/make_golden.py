@@ -79,7 +79,21 @@ def cornell():
     print("cornell halves mean", (a / 32).mean(axis=(0, 1)), (bsum / 32).mean(axis=(0, 1)), "r144", r144.mean(axis=(0, 1)))
     cornell_mis()
     cornell_adaptive()
+    cornell_light()
     images()
+
+
+def cornell_light():
+    """RayTracer::lightTracer (Renderer.h:220-326) of the unmodified reference on cornell-box 256x256: two
+    independent halves of 48 passes, 16x16-pixel block means."""
+    s = ref.RefScene("cornell-box_256")
+    a, _ = s.render_light(48, fresh=True)
+    bb, _ = s.render_light(48, fresh=False)
+    b = bb - a
+    np.savez_compressed(os.path.join(HERE, "cornell256_light_blocks.npz"),
+                        half_a=raysets.block_mean(a / 48.0, 16).astype(np.float32), half_b=raysets.block_mean(b / 48.0, 16).astype(np.float32),
+                        mean_a=(a / 48.0).mean(axis=(0, 1)), mean_b=(b / 48.0).mean(axis=(0, 1)))
+    print("cornell 256 light tracing halves mean", (a / 48).mean(axis=(0, 1)), (b / 48).mean(axis=(0, 1)))
 
 
 def images():

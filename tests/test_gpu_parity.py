@@ -325,6 +325,49 @@ def test_adaptive_render_equals_the_oracle_and_the_reference(rtb, oracle_mod):
     rt.close()
 
 
+def test_light_tracer_equals_the_oracle_and_the_reference(rtb, oracle_mod):
+    """rtb_render_light = RayTracer::lightTracer (Renderer.h:220-326).  Same uniforms as the oracle: the
+    splats land in the same pixels with the same values except where an ulp of the projection crosses a
+    pixel border; against the reference's own run (golden block means) statistically."""
+    g = np.load(os.path.join(GOLDEN, "cornell256_light_blocks.npz"))
+    s = abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box_256.rtbs"))
+    rt = rtb.RayTracer(0)
+    rt.init(s)
+    rt.lightTracer(2)
+    img = rt.read_film()
+    assert rt.getSPP() == 2
+    want, st = oracle_mod.Oracle(s).render_light(2)
+    close = np.isclose(img, want, rtol=5e-4, atol=1e-4).all(axis=-1)
+    assert close.mean() > 0.99, close.mean()
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / want.mean(axis=(0, 1)) - 1) < 5e-3)
+    gs = rt.stats()
+    assert gs["samples"] == st["paths"]
+    assert abs(gs["closest_rays"] / st["closest_rays"] - 1) < 2e-3 and abs(gs["shadow_rays"] / st["shadow_rays"] - 1) < 2e-3
+    rt.clear()
+    rt.lightTracer(48)
+    m = (rt.read_film() / 48).mean(axis=(0, 1))
+    assert np.all(np.abs(m / (0.5 * (g["mean_a"] + g["mean_b"])) - 1) < 0.01)
+    blocks = raysets.block_mean(rt.read_film() / 48, 16)
+    floor48 = np.sqrt(np.mean((g["half_a"] - g["half_b"]) ** 2) / 2)
+    rmse = np.sqrt(np.mean((blocks - 0.5 * (g["half_a"] + g["half_b"])) ** 2))
+    assert rmse < 3 * floor48 * np.sqrt(1 + 0.5), (rmse, floor48)
+    # resumable, and the three traversals give the same bits
+    rt.clear()
+    rt.lightTracer(1, 0)
+    rt.lightTracer(1, 1)
+    two = rt.read_film().copy()
+    for trav in (abi.TRAV_EXACT, abi.TRAV_WIDE):
+        rt.set_params(traversal=trav)
+        rt.clear()
+        rt.lightTracer(2, 0)
+        assert np.array_equal(rt.read_film(), two)
+    # a scene without area lights adds nothing
+    r2 = gpu_scene(rtb, "materialball")
+    r2.lightTracer(1)
+    assert not r2.read_film().any()
+    rt.close()
+
+
 def test_adaptive_render_full_resolution_and_shadow_queue_capacity(rtb, monkeypatch):
     """1024 tiles, tile-major job order: the pool works on a few floor / wall tiles at a time, where
     nearly every vertex queues a shadow ray and the multi-pass shade stage would queue two per slot

@@ -219,6 +219,31 @@ def test_adaptive_render_against_the_reference(oracle_mod):
     assert np.all(np.abs(film2.mean(axis=(0, 1)) / (2 * g["film_mean"]) - 1) < 0.01)
 
 
+def test_light_tracer_against_the_reference_statistics(oracle_mod):
+    """RayTracer::lightTracer (Renderer.h:220-326).  Golden: two independent 48-pass halves of the
+    unmodified reference on cornell-box 256x256 (block means).  Note its mean (0.36) is NOT the path
+    tracer's (0.19): the estimator has its own normalisation, so agreement is a real check."""
+    g = np.load(os.path.join(GOLDEN, "cornell256_light_blocks.npz"))
+    s = abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box_256.rtbs"))
+    passes = 24
+    film, st = oracle_mod.Oracle(s).render_light(passes)
+    img = film / passes
+    ref_mean = 0.5 * (g["mean_a"] + g["mean_b"])
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / ref_mean - 1) < 0.01)
+    assert ref_mean[0] > 0.3
+    blocks = raysets.block_mean(img, 16)
+    floor48 = np.sqrt(np.mean((g["half_a"] - g["half_b"]) ** 2) / 2)
+    expect = floor48 * np.sqrt(48) * np.sqrt(1 / passes + 1 / 96)
+    rmse = np.sqrt(np.mean((blocks - 0.5 * (g["half_a"] + g["half_b"])) ** 2))
+    assert rmse < 3 * expect, (rmse, expect)
+    assert st["paths"] == 256 * 256 * passes
+    # passes are resumable and additive
+    a, _ = oracle_mod.Oracle(s).render_light(2)
+    b, _ = oracle_mod.Oracle(s).render_light(1)
+    c, _ = oracle_mod.Oracle(s).render_light(1, pass_begin=1, film=b.copy())
+    assert np.allclose(a, c, rtol=1e-5, atol=1e-6)
+
+
 def test_canonical_work_counter_matches_the_surveys_probe(cornell):
     """canonical traversal of cornell-box = 24.2 box tests and 3.8 triangle tests per
     closest-hit ray, 2.69 + 1.64 rays per sample.  The counter must not change the render."""
