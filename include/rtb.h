@@ -390,6 +390,12 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
  * counter-based RNG like samples are; SPP grows by pass_count.  Scenes without area lights add nothing.
  * Single device per image (shard passes, not pixels).  Asynchronous.                                   */
 int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count);
+/* pass_count x RayTracer::instantRadiosity() (Renderer.h:82-218; a commented-out alternative in render(), :884):
+ * per pass n_paths light paths (MAX_VPL = 50, :24) leave virtual point lights at their diffuse vertices
+ * (traceVPLs / VPLTracePath, :159-218), then every pixel's primary hit gathers all of them with one visibility
+ * ray each (computeVPLsContribution, :124-158).  SPP grows by pass_count.  Single device per image (shard the
+ * passes, not the pixels).  Asynchronous.                                                                 */
+int rtb_render_ir(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths);
 /* Film::film (Imaging.h:204): waits for the device and copies the running SUM (not the
  * mean; Film::save divides by SPP, Imaging.h:262-271) as width*height*3 floats (r,g,b per
  * pixel, row-major) to host memory; *spp receives Film::SPP.  Either may be NULL.         */

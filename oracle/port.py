@@ -42,6 +42,7 @@ def lib():
         L.oracle_render_counts.argtypes = [vp, vp, u32, u32, i32, vp, vp]
         L.oracle_render_adaptive.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp, vp]
         L.oracle_render_light.argtypes = [vp, vp, u32, u32, vp, vp]
+        L.oracle_render_ir.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp]
         L.oracle_primary_hits.argtypes = [vp, f32, vp, vp, vp]
         L.oracle_trace.argtypes = [vp, f32, i32, vp, u64, vp]
         L.oracle_visible.argtypes = [vp, f32, vp, u64, vp]
@@ -130,6 +131,15 @@ class Oracle:
         st = np.zeros(3, np.uint64)
         self.L.oracle_render_light(C.addressof(self.desc), C.addressof(self.params), int(pass_begin), int(passes), _p(film), _p(st))
         return film, dict(paths=int(st[0]), closest_rays=int(st[1]), shadow_rays=int(st[2]))
+
+    def render_ir(self, passes, pass_begin=0, n_paths=50, threads=None, film=None):
+        """RayTracer::instantRadiosity x passes -> (film_sum, stats)."""
+        if film is None:
+            film = np.zeros((self.height, self.width, 3), "<f4")
+        st = np.zeros(4, np.uint64)
+        self.L.oracle_render_ir(C.addressof(self.desc), C.addressof(self.params), int(pass_begin), int(passes), int(n_paths),
+                                int(threads or os.cpu_count() or 1), _p(film), _p(st))
+        return film, dict(pixels=int(st[0]), closest_rays=int(st[1]), shadow_rays=int(st[2]), vpls=int(st[3]))
 
     def render_counts(self, spp, spp_begin=0, threads=None):
         """render() + the CANONICAL traversal work of every ray it traced."""

@@ -46,6 +46,7 @@ def _lib(variant=""):
         lib.ref_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
         lib.ref_render_adaptive.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
         lib.ref_render_light.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+        lib.ref_render_ir.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         lib.ref_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_uint64]
         lib.ref_aov.argtypes = [vp, C.c_int, vp]
         lib.ref_tonemap.argtypes = [vp, vp, C.c_int, C.c_float, vp]
@@ -166,6 +167,14 @@ class RefScene:
         secs = C.c_double(0)
         self.lib.ref_render_light(self.h, int(passes), 1 if fresh else 0, _p(film), C.addressof(secs))
         return film, secs.value
+
+    def render_ir(self, passes, threads=0, fresh=True):
+        """passes x instantRadiosity() -> (film_sum, seconds, total VPLs)."""
+        film = np.zeros((self.height, self.width, 3), "<f4")
+        secs = C.c_double(0)
+        nv = C.c_uint64(0)
+        self.lib.ref_render_ir(self.h, int(passes), int(threads), 1 if fresh else 0, _p(film), C.addressof(secs), C.addressof(nv))
+        return film, secs.value, nv.value
 
     def aov(self, kind):
         k = {"albedo": 0, "normals": 1, "direct": 2}[kind]

@@ -467,6 +467,38 @@ int ref_render_light(void* handle, int passes, int fresh, float* film_sum, doubl
 	return h->rt->getSPP();
 }
 
+// `passes` x { film->incrementSPP(); instantRadiosity(); } (Renderer.h:102-123, render()'s other commented-out
+// alternative, :884).  *vpls = total number of VPLs stored over the passes.
+int ref_render_ir(void* handle, int passes, int threads, int fresh, float* film_sum, double* seconds, uint64_t* vpls)
+{
+	RefScene* h = (RefScene*)handle;
+	ensureRT(h, threads);
+	if (fresh)
+	{
+		h->rt->clear();
+		for (int i = 0; i < h->rt->numProcs; i++) h->rt->samplers[i] = MTRandom();
+	}
+	uint64_t nv = 0;
+	auto t0 = std::chrono::steady_clock::now();
+	for (int i = 0; i < passes; i++)
+	{
+		h->rt->film->incrementSPP();
+		h->rt->instantRadiosity();
+		nv += h->rt->vpls.size();
+	}
+	auto t1 = std::chrono::steady_clock::now();
+	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	if (vpls) *vpls = nv;
+	size_t n = (size_t)h->rt->film->width * h->rt->film->height;
+	for (size_t i = 0; i < n; i++)
+	{
+		film_sum[i * 3] = h->rt->film->film[i].r;
+		film_sum[i * 3 + 1] = h->rt->film->film[i].g;
+		film_sum[i * 3 + 2] = h->rt->film->film[i].b;
+	}
+	return h->rt->getSPP();
+}
+
 // stbi_load (the decoder behind Texture::load, Imaging.h:51) on one file: the golden for the product's
 // own PNG / JPEG decoders.  out may be NULL to query the size.
 int ref_decode_image(const char* path, int* w, int* h, int* channels, unsigned char* out, uint64_t cap)

@@ -1023,6 +1023,176 @@ int oracle_render_light(const rtb_scene_desc* s, const rtb_params* P, uint32_t p
 	return 0;
 }
 
+/* ---------------- RayTracer::instantRadiosity, Renderer.h:82-218 ---------------------------
+ * traceVPLs (:159-184): n_paths (MAX_VPL = 50, :24) light paths per pass; a VPL on the light itself
+ * (Le = evaluate(-wi) / (pmf pdfPos N)) and, by VPLTracePath (:185-218), one at every hit that is neither an
+ * emitter nor specular (Le = T * Le' * f * |cos|, Le' = evaluate(-wi) cos_light / (pmf pdfPos N)); the walk
+ * goes on through emitters and specular surfaces alike: Russian roulette min(Lum(T), 0.9), BSDF sample,
+ * T *= f |cos| / pdf, no depth limit.  Second pass (:82-101, computeVPLsContribution :124-158): every pixel's
+ * primary hit gathers all VPLs: skip dist^2 < 1e-4 and back-facing pairs, G = cos cos / dist^2, visibility,
+ * col += Le_vpl * f * G; splat at the pixel.
+ * RNG: Philox counter (path, pass, block, 2), same block layout as the light tracer.                   */
+typedef struct { v3 x, n, Le; } vpl_t;
+
+static void rng_block_stream(uint32_t seed, uint32_t a, uint32_t b, uint32_t block, uint32_t stream, float u[4])
+{
+	uint32_t c[4];
+	int i;
+	c[0] = a, c[1] = b, c[2] = block, c[3] = stream;
+	philox(c, seed, 0x52544232u);
+	for (i = 0; i < 4; i++) u[i] = ((float)(c[i] >> 9) + 0.5f) * 1.1920928955078125e-7f;
+}
+
+static int trace_vpls(const rtb_scene_desc* s, const rtb_params* P, uint32_t pass, uint32_t n_paths, vpl_t* out, int cap, tally_t* tl)
+{
+	int n = 0;
+	uint32_t i;
+	for (i = 0; i < n_paths; i++)
+	{
+		float u0[4], u1[4], pdfPos, pmf;
+		const rtb_light* L;
+		v3 p, wl, wi, nL, Lev, Le, T = V(1.0f, 1.0f, 1.0f), fu, fv, fw;
+		ray_t r;
+		int li, k;
+		if (s->n_lights == 0) continue;
+		rng_block_stream(P->seed, i, pass, 0, 2, u0);
+		rng_block_stream(P->seed, i, pass, 1, 2, u1);
+		pmf = 1.f / s->n_lights;
+		li = (int)(s->n_lights * u0[0]);
+		if (li > (int)s->n_lights - 1) li = (int)s->n_lights - 1;
+		L = &s->lights[li];
+		if (L->type != RTB_LIGHT_AREA) continue;
+		p = triangle_sample(s, L->triangle, u0[1], u0[2], &pdfPos);
+		wl = cosine_sample_hemisphere(u0[3], u1[0]);
+		nL = triangle_gnormal(s, L->triangle);
+		frame_from_vector(nL, &fu, &fv, &fw);
+		wi = add(add(scl(fu, wl.x), scl(fv, wl.y)), scl(fw, wl.z));
+		Lev = (dot3(neg(wi), nL) < 0) ? Vp(L->emission) : V(0, 0, 0);
+		if (n < cap) out[n].x = p, out[n].n = nL, out[n].Le = dvd(Lev, (pmf * pdfPos * (float)n_paths)), n++;
+		Le = dvd(scl(Lev, dot3(wi, nL)), (pmf * pdfPos * (float)n_paths));
+		r = make_ray(p, wi);
+		for (k = 0; k < 100000; k++)
+		{
+			rtb_hit h = scene_traverse_tl(s, &r, P->epsilon, tl);
+			shade_t sd;
+			const rtb_material* m;
+			float uk[4], rr, pdf;
+			v3 f, wi2;
+			tl->closest++;
+			shading_data(s, &h, &r, &sd);
+			if (!(sd.t < FLT_MAX)) break;
+			m = &s->materials[sd.mat];
+			if (!(m->flags & RTB_MAT_LIGHT) && !(m->flags & RTB_MAT_SPECULAR))
+			{
+				if (n < cap)
+				{
+					out[n].x = sd.x, out[n].n = sd.sN;
+					out[n].Le = scl(mul(mul(T, Le), bsdf_evaluate(s, m, &sd)), fabsf(dot3(neg(r.d), sd.sN)));
+					n++;
+				}
+			}
+			rng_block_stream(P->seed, i, pass, 2u + (uint32_t)k, 2, uk);
+			rr = win_min(lum3(T), P->rr_cap);
+			if (uk[0] < rr) T = dvd(T, rr);
+			else break;
+			wi2 = bsdf_sample(s, m, &sd, uk[1], uk[2], uk[3], &f, &pdf);
+			T = dvd(scl(mul(T, f), fabsf(dot3(wi2, sd.sN))), pdf);
+			r = make_ray(add(sd.x, scl(wi2, P->epsilon)), wi2);
+		}
+	}
+	return n;
+}
+
+typedef struct {
+	const rtb_scene_desc* s;
+	const rtb_params* P;
+	const vpl_t* vpls;
+	int n_vpl, y0, y1;
+	float* film;
+	tally_t tl;
+} ir_job_t;
+
+static void* ir_rows(void* arg)
+{
+	ir_job_t* j = (ir_job_t*)arg;
+	const rtb_scene_desc* s = j->s;
+	uint32_t W = (uint32_t)s->camera.width;
+	int y, i;
+	for (y = j->y0; y < j->y1; y++)
+	{
+		uint32_t x;
+		for (x = 0; x < W; x++)
+		{
+			ray_t r = generate_ray(&s->camera, x + 0.5f, y + 0.5f);
+			rtb_hit h = scene_traverse_tl(s, &r, j->P->epsilon, &j->tl);
+			shade_t sd;
+			const rtb_material* m;
+			v3 col = V(0, 0, 0);
+			float* f = j->film + ((size_t)y * W + x) * 3;
+			j->tl.closest++;
+			j->tl.samples++;
+			shading_data(s, &h, &r, &sd);
+			if (!(sd.t < FLT_MAX)) continue;
+			m = &s->materials[sd.mat];
+			if ((m->flags & RTB_MAT_LIGHT) || (m->flags & RTB_MAT_SPECULAR)) continue;
+			for (i = 0; i < j->n_vpl; i++)
+			{
+				const vpl_t* v = &j->vpls[i];
+				v3 d = sub(v->x, sd.x);
+				float dist2 = dot3(d, d), cv, cx, G;
+				if (dist2 < 1e-4f) continue;
+				d = norm3(d);
+				cv = dot3(v->n, neg(d));
+				cx = dot3(sd.sN, d);
+				if (cv <= 0.0f || cx <= 0.0f) continue;
+				G = (cv * cx) / dist2;
+				j->tl.shadow++;
+				if (!scene_visible_tl(s, sd.x, v->x, j->P->epsilon, &j->tl)) continue;
+				col = add(col, scl(mul(v->Le, bsdf_evaluate(s, m, &sd)), G));
+			}
+			f[0] += col.x, f[1] += col.y, f[2] += col.z;
+		}
+	}
+	return NULL;
+}
+
+int oracle_render_ir(const rtb_scene_desc* s, const rtb_params* P, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths, int threads,
+                     float* film_sum, uint64_t* stats /* pixels, closest, shadow, vpls */)
+{
+	int H = (int)s->camera.height, nt = threads < 1 ? 1 : (threads > 256 ? 256 : threads), cap = (int)n_paths * 256, i;
+	vpl_t* vpls = (vpl_t*)calloc((size_t)cap, sizeof(vpl_t));
+	ir_job_t* jobs = (ir_job_t*)calloc((size_t)nt, sizeof(ir_job_t));
+	pthread_t* th = (pthread_t*)calloc((size_t)nt, sizeof(pthread_t));
+	uint64_t tot[4] = {0, 0, 0, 0};
+	uint32_t pass;
+	for (pass = pass_begin; pass < pass_begin + pass_count; pass++)
+	{
+		tally_t tl;
+		int n, rows = (H + nt - 1) / nt;
+		memset(&tl, 0, sizeof(tl));
+		n = trace_vpls(s, P, pass, n_paths, vpls, cap, &tl);
+		tot[1] += tl.closest, tot[3] += (uint64_t)n;
+		for (i = 0; i < nt; i++)
+		{
+			memset(&jobs[i], 0, sizeof(ir_job_t));
+			jobs[i].s = s, jobs[i].P = P, jobs[i].vpls = vpls, jobs[i].n_vpl = n, jobs[i].film = film_sum;
+			jobs[i].y0 = i * rows < H ? i * rows : H, jobs[i].y1 = (i + 1) * rows < H ? (i + 1) * rows : H;
+			if (nt == 1) ir_rows(&jobs[i]);
+			else pthread_create(&th[i], NULL, ir_rows, &jobs[i]);
+		}
+		for (i = 0; i < nt; i++)
+		{
+			if (nt > 1) pthread_join(th[i], NULL);
+			tot[0] += jobs[i].tl.samples, tot[1] += jobs[i].tl.closest, tot[2] += jobs[i].tl.shadow;
+		}
+	}
+	if (stats) memcpy(stats, tot, sizeof(tot));
+	free(vpls);
+	free(jobs);
+	free(th);
+	return 0;
+}
+
 /* oracle_render + the canonical-traversal work of every ray it traced.
  * stats = samples, closest, shadow, closest box tests, closest tri tests, shadow box, shadow tri.
  * Not re-entrant (one process-wide switch): tests/tools/canonical_counts.py is its only caller. */

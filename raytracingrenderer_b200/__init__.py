@@ -24,7 +24,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")
 ABI_SYMBOLS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_stream", "rtb_synchronize",
     "rtb_default_params", "rtb_set_params", "rtb_get_params", "rtb_upload_scene", "rtb_update_camera",
-    "rtb_clear", "rtb_render", "rtb_render_adaptive", "rtb_render_light", "rtb_read_film", "rtb_film_device_ptr", "rtb_accum_device_ptr", "rtb_set_spp", "rtb_tonemap", "rtb_get_stats",
+    "rtb_clear", "rtb_render", "rtb_render_adaptive", "rtb_render_light", "rtb_render_ir", "rtb_read_film", "rtb_film_device_ptr", "rtb_accum_device_ptr", "rtb_set_spp", "rtb_tonemap", "rtb_get_stats",
     "rtb_film_size", "rtb_primary_hits", "rtb_trace", "rtb_visible", "rtb_shading_data", "rtb_eval_bsdf",
     "rtb_eval_light", "rtb_rng_draws",
 ]
@@ -66,6 +66,7 @@ def lib():
         L.rtb_render.argtypes = [vp, u32, u32]
         L.rtb_render_adaptive.argtypes = [vp, u32, u32, u32, vp, vp]
         L.rtb_render_light.argtypes = [vp, u32, u32]
+        L.rtb_render_ir.argtypes = [vp, u32, u32, u32]
         L.rtb_read_film.argtypes = [vp, vp, C.POINTER(u32)]
         L.rtb_film_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.rtb_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
@@ -177,6 +178,11 @@ class RayTracer:
         """`passes` x RayTracer::lightTracer (Renderer.h:220-231).  Asynchronous."""
         begin = self.getSPP() if pass_begin is None else int(pass_begin)
         self._ck(self._L.rtb_render_light(self._h, begin, int(passes)))
+
+    def instantRadiosity(self, passes=1, pass_begin=None, n_paths=50):
+        """`passes` x RayTracer::instantRadiosity (Renderer.h:102-123; MAX_VPL = 50 light paths).  Asynchronous."""
+        begin = self.getSPP() if pass_begin is None else int(pass_begin)
+        self._ck(self._L.rtb_render_ir(self._h, begin, int(passes), int(n_paths)))
 
     def adaptiveRender(self, init_samples=2, min_samples=1, max_samples=10240):
         """RayTracer::adaptiveRender (Renderer.h:679-749) -> (tile_samples, tile_variance) as

@@ -105,6 +105,9 @@ struct rtb_ctx
 	cudaEvent_t evShaded[RTB_MAX_POOLS] = {}, evShadowed[RTB_MAX_POOLS] = {};
 	bool shadowAsync = true;
 	unsigned lightGrid = 0;
+	void* vpls = nullptr; // rtb_render_ir: n_paths segments of RTB_VPL_SEGMENT VPLs
+	uint32_t* vplCounts = nullptr;
+	uint32_t vplPaths = 0;
 	cudaEvent_t evFork = nullptr;
 	uint64_t wfIterations = 0, wfHostSyncs = 0;
 };
@@ -150,6 +153,9 @@ void freeScene(rtb_ctx* ctx)
 	if (ctx->wfGlobal) cudaFree(ctx->wfGlobal);
 	if (ctx->wfTiles) cudaFree(ctx->wfTiles);
 	if (ctx->wfPrimary) cudaFree(ctx->wfPrimary);
+	if (ctx->vpls) cudaFree(ctx->vpls);
+	if (ctx->vplCounts) cudaFree(ctx->vplCounts);
+	ctx->vpls = nullptr, ctx->vplCounts = nullptr, ctx->vplPaths = 0;
 	if (ctx->accumScratch) cudaFree(ctx->accumScratch);
 	if (ctx->wfTilesAdaptive) cudaFree(ctx->wfTilesAdaptive);
 	if (ctx->adaptJobBase) cudaFree(ctx->adaptJobBase);
@@ -945,6 +951,52 @@ int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 	cudaEventRecord(ev.b, ctx->stream);
 	ctx->pending.push_back(ev);
 	ctx->launches++;
+	CK(cudaGetLastError());
+	ctx->filmDirty = true;
+	ctx->spp += pass_count; // Film::incrementSPP once per render() (Renderer.h:878)
+	return RTB_OK;
+}
+
+// pass_count x RayTracer::instantRadiosity() (Renderer.h:102-123).
+int rtb_render_ir(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_ir before rtb_upload_scene");
+	if (pass_count == 0) return RTB_OK;
+	if (n_paths < 1 || n_paths > 65536) return fail(ctx, RTB_ERR_ARG, "rtb_render_ir: 1 <= n_paths <= 65536 light paths per pass");
+	if ((uint64_t)pass_begin + pass_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "pass index overflow");
+	if (ctx->params.partition != RTB_PART_NONE && ctx->params.part_world > 1)
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_ir: shard the passes over devices (a pass is one VPL set for the whole image)");
+	if (int rc = bind(ctx)) return rc;
+	if (ctx->vplPaths < n_paths)
+	{
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->vpls) cudaFree(ctx->vpls);
+		if (ctx->vplCounts) cudaFree(ctx->vplCounts);
+		ctx->vpls = nullptr, ctx->vplCounts = nullptr, ctx->vplPaths = 0;
+		CK(cudaMalloc((void**)&ctx->vpls, (size_t)n_paths * RTB_VPL_SEGMENT * sizeof(VplD)));
+		CK(cudaMalloc((void**)&ctx->vplCounts, (size_t)n_paths * sizeof(uint32_t)));
+		ctx->vplPaths = n_paths;
+	}
+	RenderArgs A;
+	A.accum = ctx->accum;
+	A.counters = ctx->counters;
+	A.spp_begin = pass_begin, A.spp_count = pass_count;
+	A.width = ctx->width, A.height = ctx->height;
+	A.P = ctx->params;
+	uint32_t warps = ((ctx->width + 7) / 8) * ((ctx->height + 3) / 4);
+	EventPair ev = {getEvent(ctx), getEvent(ctx)};
+	cudaEventRecord(ev.a, ctx->stream);
+	for (uint32_t pass = pass_begin; pass < pass_begin + pass_count; pass++)
+	{
+		RTB_TRAV_SWITCH(ctx->params.traversal,
+		                k_ir_vpls<TR><<<(n_paths + 63) / 64, 64, 0, ctx->stream>>>(ctx->S, A, pass, n_paths, (VplD*)ctx->vpls, ctx->vplCounts));
+		RTB_TRAV_SWITCH(ctx->params.traversal,
+		                k_ir_gather<TR><<<(warps + 3) / 4, 128, 0, ctx->stream>>>(ctx->S, A, n_paths, (const VplD*)ctx->vpls, ctx->vplCounts));
+		ctx->launches += 2;
+	}
+	cudaEventRecord(ev.b, ctx->stream);
+	ctx->pending.push_back(ev);
 	CK(cudaGetLastError());
 	ctx->filmDirty = true;
 	ctx->spp += pass_count; // Film::incrementSPP once per render() (Renderer.h:878)

@@ -546,6 +546,135 @@ __global__ void __launch_bounds__(128) k_light_trace(const __grid_constant__ Dev
 }
 
 // ---------------------------------------------------------------------------------------
+// RayTracer::instantRadiosity (Renderer.h:82-218).  k_ir_vpls = traceVPLs + VPLTracePath (:159-218): one
+// thread per light path (MAX_VPL = 50 of them), each writing its VPLs into its own segment so that the list
+// order (path, vertex) does not depend on scheduling.  k_ir_gather = renderBlockinstantRadiosity +
+// computeVPLsContribution (:82-101, 124-158): one thread per pixel (a warp = an 8x4 tile) sums all VPLs, one
+// visibility ray each — the lanes of a warp shoot at the same VPL.  RNG stream 2, light-tracer block layout.
+// ---------------------------------------------------------------------------------------
+struct VplD
+{
+	float4 x;  // position, -
+	float4 n;  // normal, -
+	float4 le; // Le, -
+};
+#define RTB_VPL_SEGMENT 256 /* VPLs one light path may store: survival <= 0.9 per vertex */
+
+template <int TRAV>
+__global__ void __launch_bounds__(64) k_ir_vpls(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A, uint32_t pass,
+                                                uint32_t nPaths, VplD* vpls, uint32_t* counts)
+{
+	const rtb_params& P = A.P;
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nPaths; i += gridDim.x * blockDim.x)
+	{
+		VplD* out = vpls + (size_t)i * RTB_VPL_SEGMENT;
+		uint32_t n = 0;
+		counts[i] = 0;
+		if (S.n_lights == 0) continue;
+		float4 u0 = rngBlock(P.seed, i, pass, 0u, 2u), u1 = rngBlock(P.seed, i, pass, 1u, 2u);
+		float nl = (float)S.n_lights;
+		float pmf = 1.0f / nl;
+		int li = (int)(nl * u0.x);
+		if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+		rtb_light L = S.lights[li];
+		if (L.type != RTB_LIGHT_AREA) continue;
+		V3 p = trianglePoint(S, L.triangle, u0.y, u0.z);
+		float pdfPos = 1.0f / L.area;
+		V3 wl = cosineSampleHemisphere(u0.w, u1.x);
+		V3 nL = triangleGNormal(S, L.triangle);
+		V3 fu, fv, fw;
+		frameFromVector(nL, fu, fv, fw);
+		V3 wi = ((fu * wl.x) + (fv * wl.y)) + (fw * wl.z);
+		V3 Lev = (dot(-wi, nL) < 0.0f) ? mk(L.emission) : mk(0.0f, 0.0f, 0.0f);
+		float norm = pmf * pdfPos * (float)nPaths;
+		V3 l0 = Lev / norm;
+		out[n].x = make_float4(p.x, p.y, p.z, 0.0f), out[n].n = make_float4(nL.x, nL.y, nL.z, 0.0f), out[n].le = make_float4(l0.x, l0.y, l0.z, 0.0f);
+		n++;
+		V3 Le = (Lev * dot(wi, nL)) / norm;
+		RayD r = mkRay(p, wi);
+		V3 T = mk(1.0f, 1.0f, 1.0f);
+		for (uint32_t kk = 0; kk < 100000u; kk++)
+		{
+			HitD h;
+			closestHit<TRAV>(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+			tl.closest++;
+			if (h.id == RTB_MISS_ID) break;
+			ShadeD sd;
+			calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), r, sd);
+			rtb_material m = S.mats[sd.mat];
+			if (!(m.flags & (RTB_MAT_LIGHT | RTB_MAT_SPECULAR)) && n < RTB_VPL_SEGMENT)
+			{
+				V3 le = ((T * Le) * bsdfEvaluate(S, m, sd, -r.d)) * fabsf(dot(-r.d, sd.sN));
+				out[n].x = make_float4(sd.x.x, sd.x.y, sd.x.z, 0.0f), out[n].n = make_float4(sd.sN.x, sd.sN.y, sd.sN.z, 0.0f);
+				out[n].le = make_float4(le.x, le.y, le.z, 0.0f);
+				n++;
+			}
+			float4 uk = rngBlock(P.seed, i, pass, 2u + kk, 2u);
+			float rr = selMin(lum(T), P.rr_cap);
+			if (!(uk.x < rr)) break;
+			T = T / rr;
+			V3 f;
+			float pdf;
+			V3 wi2 = bsdfSample(S, m, sd, uk.y, uk.z, uk.w, f, pdf);
+			T = ((T * f) * fabsf(dot(wi2, sd.sN))) / pdf;
+			r = mkRay(sd.x + (wi2 * P.epsilon), wi2);
+		}
+		counts[i] = n;
+	}
+	flushTally(tl, A.counters);
+}
+
+template <int TRAV>
+__global__ void __launch_bounds__(128) k_ir_gather(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A, uint32_t nPaths,
+                                                   const VplD* __restrict__ vpls, const uint32_t* __restrict__ counts)
+{
+	const rtb_params& P = A.P;
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	uint32_t tilesX = (A.width + 7u) >> 3, tilesY = (A.height + 3u) >> 2;
+	uint32_t lane = threadIdx.x & 31u;
+	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < tilesX * tilesY; w += (gridDim.x * blockDim.x) >> 5)
+	{
+		uint32_t px = (w % tilesX) * 8u + (lane & 7u), py = (w / tilesX) * 4u + (lane >> 3);
+		if (px >= A.width || py >= A.height) continue;
+		RayD r = generateRay(S.cam, (float)px + 0.5f, (float)py + 0.5f);
+		HitD h;
+		closestHit<TRAV>(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+		tl.closest++;
+		tl.samples++;
+		if (h.id == RTB_MISS_ID) continue;
+		ShadeD sd;
+		calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), r, sd);
+		rtb_material m = S.mats[sd.mat];
+		if (m.flags & (RTB_MAT_LIGHT | RTB_MAT_SPECULAR)) continue;
+		V3 f = bsdfEvaluate(S, m, sd, mk(0.0f, 1.0f, 0.0f));
+		V3 col = mk(0.0f, 0.0f, 0.0f);
+		for (uint32_t i = 0; i < nPaths; i++)
+		{
+			uint32_t cnt = __ldg(counts + i);
+			const VplD* seg = vpls + (size_t)i * RTB_VPL_SEGMENT;
+			for (uint32_t k = 0; k < cnt; k++)
+			{
+				V3 vx = mk(__ldg(&seg[k].x)), vn = mk(__ldg(&seg[k].n));
+				V3 d = vx - sd.x;
+				float dist2 = lengthSq(d);
+				if (dist2 < 1e-4f) continue;
+				d = normalize(d);
+				float cv = dot(vn, -d), cx = dot(sd.sN, d);
+				if (cv <= 0.0f || cx <= 0.0f) continue;
+				float G = (cv * cx) / dist2;
+				tl.shadow++;
+				if (!sceneVisible<TRAV>(S, sd.x, vx, P.epsilon, P.cull_rel, tl.sbox, tl.stri)) continue;
+				col = col + ((mk(__ldg(&seg[k].le)) * f) * G);
+			}
+		}
+		long long* a = A.accum + ((size_t)py * A.width + px) * 3; // this thread owns the pixel during the launch
+		a[0] += toFixed(col.x), a[1] += toFixed(col.y), a[2] += toFixed(col.z);
+	}
+	flushTally(tl, A.counters);
+}
+
+// ---------------------------------------------------------------------------------------
 // Parity kernels
 // ---------------------------------------------------------------------------------------
 template <int TRAV>

@@ -39,6 +39,7 @@ const int MAX_DEPTH = 4;  // RTBase/Renderer.h:20 -> rtb_params.max_depth
 const int MAX_SAMPLES = 10240; // RTBase/Renderer.h:21-23 -> the arguments of rtb_render_adaptive
 const int MIN_SAMPLES = 1;
 const int INIT_SAMPLES = 2;
+const int MAX_VPL = 50; // RTBase/Renderer.h:24 -> n_paths of rtb_render_ir
 
 class RayTracer
 {
@@ -130,6 +131,23 @@ public:
 		check(rtb_set_spp(ctx, (uint32_t)film->SPP), "rtb_set_spp");
 		filmOnHost = false;
 		if (presentEveryFrame && canvas) presentFilmToCanvas();
+	}
+	// RTBase/Renderer.h:102-123 (render()'s commented-out alternative at :884): one instant-radiosity pass.
+	void instantRadiosity()
+	{
+		uint32_t pass = film->SPP > 0 ? (uint32_t)film->SPP - 1u : 0u;
+		check(rtb_render_ir(ctx, pass, 1, MAX_VPL), "rtb_render_ir");
+		check(rtb_set_spp(ctx, (uint32_t)film->SPP), "rtb_set_spp");
+		filmOnHost = false;
+		if (presentEveryFrame && canvas) presentFilmToCanvas();
+	}
+	void renderInstantRadiosity(int n = 1)
+	{
+		for (int i = 0; i < n; i++)
+		{
+			film->incrementSPP();
+			instantRadiosity();
+		}
 	}
 	void renderLight(int n = 1)
 	{

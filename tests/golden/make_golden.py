@@ -80,6 +80,7 @@ def cornell():
     cornell_mis()
     cornell_adaptive()
     cornell_light()
+    cornell_ir()
     images()
 
 
@@ -94,6 +95,19 @@ def cornell_light():
                         half_a=raysets.block_mean(a / 48.0, 16).astype(np.float32), half_b=raysets.block_mean(b / 48.0, 16).astype(np.float32),
                         mean_a=(a / 48.0).mean(axis=(0, 1)), mean_b=(b / 48.0).mean(axis=(0, 1)))
     print("cornell 256 light tracing halves mean", (a / 48).mean(axis=(0, 1)), (b / 48).mean(axis=(0, 1)))
+
+
+def cornell_ir():
+    """RayTracer::instantRadiosity (Renderer.h:82-218) of the unmodified reference on cornell-box 256x256: two
+    independent halves of 64 passes (50 light paths each), 16x16-pixel block means."""
+    s = ref.RefScene("cornell-box_256")
+    a, _, na = s.render_ir(64, fresh=True)
+    bb, _, nb = s.render_ir(64, fresh=False)
+    b = bb - a
+    np.savez_compressed(os.path.join(HERE, "cornell256_ir_blocks.npz"),
+                        half_a=raysets.block_mean(a / 64.0, 16).astype(np.float32), half_b=raysets.block_mean(b / 64.0, 16).astype(np.float32),
+                        mean_a=(a / 64.0).mean(axis=(0, 1)), mean_b=(b / 64.0).mean(axis=(0, 1)), vpls_per_pass=(na + nb) / 128.0)
+    print("cornell 256 instant radiosity halves mean", (a / 64).mean(axis=(0, 1)), (b / 64).mean(axis=(0, 1)), "VPLs/pass", (na + nb) / 128.0)
 
 
 def images():

@@ -368,6 +368,50 @@ def test_light_tracer_equals_the_oracle_and_the_reference(rtb, oracle_mod):
     rt.close()
 
 
+def test_instant_radiosity_equals_the_oracle_and_the_reference(rtb, oracle_mod):
+    """rtb_render_ir = RayTracer::instantRadiosity (Renderer.h:82-218).  Same uniforms and the same VPL
+    order as the oracle: per-pixel sums agree to float rounding; the reference's own run statistically."""
+    g = np.load(os.path.join(GOLDEN, "cornell256_ir_blocks.npz"))
+    s = abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box_256.rtbs"))
+    rt = rtb.RayTracer(0)
+    rt.init(s)
+    rt.instantRadiosity(2)
+    img = rt.read_film()
+    assert rt.getSPP() == 2
+    want, st = oracle_mod.Oracle(s).render_ir(2)
+    close = np.isclose(img, want, rtol=5e-4, atol=1e-6).all(axis=-1)
+    assert close.mean() > 0.995, close.mean()
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / want.mean(axis=(0, 1)) - 1) < 2e-3)
+    gs = rt.stats()
+    assert abs(gs["closest_rays"] / st["closest_rays"] - 1) < 2e-3 and abs(gs["shadow_rays"] / st["shadow_rays"] - 1) < 2e-3
+    rt.clear()
+    rt.instantRadiosity(64)
+    m = (rt.read_film() / 64).mean(axis=(0, 1))
+    halves = np.abs(g["mean_a"] / g["mean_b"] - 1).max()
+    assert np.all(np.abs(m / (0.5 * (g["mean_a"] + g["mean_b"])) - 1) < max(0.03, 4 * halves))
+    # resumable; the three traversals give the same bits; argument errors
+    rt.clear()
+    rt.instantRadiosity(1, 0)
+    rt.instantRadiosity(1, 1)
+    two = rt.read_film().copy()
+    # WIDE == FAST bit for bit.  EXACT (the reference's un-culled walk) differs in a few hundred pixels by
+    # ~3e-7: a VPL and a shading point on the SAME wall give a visibility ray lying in that wall's plane
+    # (cos ~ 1e-8 passes the "<= 0" test), whose plane-intersection t is rounding noise — the one case where
+    # the culled trees and the reference's exhaustive walk may accept different triangles (SURVEY A.3 / F10).
+    for trav in (abi.TRAV_EXACT, abi.TRAV_WIDE):
+        rt.set_params(traversal=trav)
+        rt.clear()
+        rt.instantRadiosity(2, 0)
+        if trav == abi.TRAV_WIDE:
+            assert np.array_equal(rt.read_film(), two)
+        else:
+            assert np.allclose(rt.read_film(), two, rtol=1e-3, atol=2e-6)
+            assert (rt.read_film() != two).any(axis=-1).mean() < 0.02
+    with pytest.raises(rtb.RtbError):
+        rt.instantRadiosity(1, 0, n_paths=0)
+    rt.close()
+
+
 def test_adaptive_render_full_resolution_and_shadow_queue_capacity(rtb, monkeypatch):
     """1024 tiles, tile-major job order: the pool works on a few floor / wall tiles at a time, where
     nearly every vertex queues a shadow ray and the multi-pass shade stage would queue two per slot

@@ -244,6 +244,31 @@ def test_light_tracer_against_the_reference_statistics(oracle_mod):
     assert np.allclose(a, c, rtol=1e-5, atol=1e-6)
 
 
+def test_instant_radiosity_against_the_reference_statistics(oracle_mod):
+    """RayTracer::instantRadiosity (Renderer.h:82-218).  Golden: two independent 64-pass halves of the
+    unmodified reference on cornell-box 256x256.  A pass is ONE set of ~150 VPLs for the whole image, so
+    passes are strongly correlated across pixels: the tolerance comes from the two halves themselves."""
+    g = np.load(os.path.join(GOLDEN, "cornell256_ir_blocks.npz"))
+    s = abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box_256.rtbs"))
+    passes = 32
+    film, st = oracle_mod.Oracle(s).render_ir(passes)
+    img = film / passes
+    ref_mean = 0.5 * (g["mean_a"] + g["mean_b"])
+    halves = np.abs(g["mean_a"] / g["mean_b"] - 1).max()             # how far two 64-pass runs of the reference are apart
+    assert np.all(np.abs(img.mean(axis=(0, 1)) / ref_mean - 1) < max(0.03, 4 * halves))
+    assert abs(st["vpls"] / passes / float(g["vpls_per_pass"]) - 1) < 0.1
+    blocks = raysets.block_mean(img, 16)
+    floor64 = np.sqrt(np.mean((g["half_a"] - g["half_b"]) ** 2) / 2)
+    expect = floor64 * np.sqrt(64) * np.sqrt(1 / passes + 1 / 128)
+    rmse = np.sqrt(np.mean((blocks - 0.5 * (g["half_a"] + g["half_b"])) ** 2))
+    assert rmse < 3 * expect, (rmse, expect)
+    assert st["pixels"] == 256 * 256 * passes
+    # light sources and missed pixels receive nothing; thread count does not matter
+    a, _ = oracle_mod.Oracle(s).render_ir(1, threads=1)
+    b, _ = oracle_mod.Oracle(s).render_ir(1, threads=5)
+    assert a.tobytes() == b.tobytes()
+
+
 def test_canonical_work_counter_matches_the_surveys_probe(cornell):
     """canonical traversal of cornell-box = 24.2 box tests and 3.8 triangle tests per
     closest-hit ray, 2.69 + 1.64 rays per sample.  The counter must not change the render."""

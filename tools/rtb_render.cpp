@@ -3,7 +3,7 @@
 // names to the product's own scene API and loader, host/Renderer.h is the drop-in RayTracer, and the
 // path tracing runs on the GPU through librtb200.so.  No reference code is compiled in.
 //
-//   rtb_render <scene dir> <spp> <out.hdr> [--adaptive] [--mis] [--light] [--png out.png] [--raw film.bin]
+//   rtb_render <scene dir> <spp> <out.hdr> [--adaptive] [--mis] [--light] [--ir] [--png out.png] [--raw film.bin]
 #include "GamesEngineeringBase.h"
 
 #include "GEMLoader.h"
@@ -16,10 +16,10 @@ int main(int argc, char** argv)
 {
 	if (argc < 4)
 	{
-		fprintf(stderr, "usage: rtb_render <scene dir> <spp> <out.hdr> [--adaptive] [--mis] [--light] [--png out.png] [--raw film.bin]\n");
+		fprintf(stderr, "usage: rtb_render <scene dir> <spp> <out.hdr> [--adaptive] [--mis] [--light] [--ir] [--png out.png] [--raw film.bin]\n");
 		return 2;
 	}
-	bool adaptive = false, mis = false, light = false;
+	bool adaptive = false, mis = false, light = false, ir = false;
 	std::string png, raw;
 	for (int i = 4; i < argc; i++)
 	{
@@ -27,6 +27,7 @@ int main(int argc, char** argv)
 		if (a == "--adaptive") adaptive = true;
 		else if (a == "--mis") mis = true;
 		else if (a == "--light") light = true;
+		else if (a == "--ir") ir = true;
 		else if (a == "--png" && i + 1 < argc) png = argv[++i];
 		else if (a == "--raw" && i + 1 < argc) raw = argv[++i];
 	}
@@ -47,6 +48,7 @@ int main(int argc, char** argv)
 		auto t1 = std::chrono::steady_clock::now();
 		int spp = atoi(argv[2]);
 		if (light) rt.renderLight(spp); // lightTracer() per "sample", like Renderer.h:883
+		else if (ir) rt.renderInstantRadiosity(spp); // instantRadiosity() per "sample", like Renderer.h:884
 		else if (adaptive)
 			for (int i = 0; i < spp; i++) rt.renderAdaptive(); // one adaptiveRender() per "sample", like Renderer.h:880
 		else
