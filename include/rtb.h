@@ -400,6 +400,10 @@ int rtb_render_ir(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32
  * mean; Film::save divides by SPP, Imaging.h:262-271) as width*height*3 floats (r,g,b per
  * pixel, row-major) to host memory; *spp receives Film::SPP.  Either may be NULL.         */
 int rtb_read_film(rtb_ctx* ctx, float* rgb_sum, uint32_t* spp);
+/* The inverse of rtb_read_film: the film sums become rgb_sum (width*height*3 floats).  This is the hook for
+ * RayTracer::denoise (Renderer.h:750-792), which copies film->film out, runs an external filter (OIDN there)
+ * and copies the result back: read, filter with anything, write.  SPP is unchanged.  Synchronous.          */
+int rtb_write_film(rtb_ctx* ctx, const float* rgb_sum);
 /* Device address of the sum film (width*height*3 floats), e.g. for an NCCL reduce.         */
 int rtb_film_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_floats);
 /* The film's master copy: width*height*3 signed 64-bit FIXED-POINT sums in units of 2^-32

@@ -24,7 +24,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")
 ABI_SYMBOLS = [
     "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_stream", "rtb_synchronize",
     "rtb_default_params", "rtb_set_params", "rtb_get_params", "rtb_upload_scene", "rtb_update_camera",
-    "rtb_clear", "rtb_render", "rtb_render_adaptive", "rtb_render_light", "rtb_render_ir", "rtb_read_film", "rtb_film_device_ptr", "rtb_accum_device_ptr", "rtb_set_spp", "rtb_tonemap", "rtb_get_stats",
+    "rtb_clear", "rtb_render", "rtb_render_adaptive", "rtb_render_light", "rtb_render_ir", "rtb_read_film", "rtb_write_film", "rtb_film_device_ptr", "rtb_accum_device_ptr", "rtb_set_spp", "rtb_tonemap", "rtb_get_stats",
     "rtb_film_size", "rtb_primary_hits", "rtb_trace", "rtb_visible", "rtb_shading_data", "rtb_eval_bsdf",
     "rtb_eval_light", "rtb_rng_draws",
 ]
@@ -68,6 +68,7 @@ def lib():
         L.rtb_render_light.argtypes = [vp, u32, u32]
         L.rtb_render_ir.argtypes = [vp, u32, u32, u32]
         L.rtb_read_film.argtypes = [vp, vp, C.POINTER(u32)]
+        L.rtb_write_film.argtypes = [vp, vp]
         L.rtb_film_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.rtb_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.rtb_set_spp.argtypes = [vp, u32]
@@ -193,6 +194,13 @@ class RayTracer:
         self._ck(self._L.rtb_render_adaptive(self._h, int(init_samples), int(min_samples), int(max_samples),
                                              samples.ctypes.data, var.ctypes.data))
         return samples, var
+
+    def write_film(self, rgb_sum):
+        """Replace Film::film (running sums) — the second half of a denoise hook (Renderer.h:784-790)."""
+        a = np.ascontiguousarray(rgb_sum, np.float32)
+        if a.shape != (self.height, self.width, 3):
+            raise ValueError("film must be [height, width, 3]")
+        self._ck(self._L.rtb_write_film(self._h, a.ctypes.data))
 
     def getSPP(self):
         n = C.c_uint32(0)

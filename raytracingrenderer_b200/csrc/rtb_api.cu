@@ -1100,6 +1100,23 @@ int rtb_read_film(rtb_ctx* ctx, float* rgb_sum, uint32_t* spp)
 	return RTB_OK;
 }
 
+// The inverse of rtb_read_film: replaces the film sums (what RayTracer::denoise does to film->film after
+// its filter ran, Renderer.h:784-790).
+int rtb_write_film(rtb_ctx* ctx, const float* rgb_sum)
+{
+	if (!ctx || !rgb_sum) return fail(ctx, RTB_ERR_ARG, "rtb_write_film: NULL argument");
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = bind(ctx)) return rc;
+	uint32_t n = ctx->width * ctx->height * 3;
+	CK(cudaMemcpyAsync(ctx->film, rgb_sum, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	k_film_import<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->film, ctx->accum, n);
+	ctx->launches++;
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(ctx->stream)); // rgb_sum may be pageable
+	ctx->filmDirty = true;                  // the float film is re-derived from the fixed-point sums
+	return RTB_OK;
+}
+
 int rtb_film_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_floats)
 {
 	if (!ctx || !dptr) return RTB_ERR_ARG;

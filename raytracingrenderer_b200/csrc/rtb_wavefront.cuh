@@ -90,6 +90,14 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const long long* __restrict_
 	film[i] = (float)((double)accum[i] * (1.0 / 4294967296.0));
 }
 
+// the inverse of k_wf_resolve: host-provided float sums become the fixed-point master copy (rtb_write_film)
+__global__ void __launch_bounds__(256) k_film_import(const float* __restrict__ film, long long* accum, uint32_t n)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	accum[i] = toFixed(film[i]);
+}
+
 // ---------------------------------------------------------------------------------------
 // jobs
 // ---------------------------------------------------------------------------------------

@@ -162,6 +162,18 @@ public:
 		film->incrementSPP();
 		adaptiveRender();
 	}
+	// RTBase/Renderer.h:750-792 runs OIDN on film->film in place.  Here the filter is whatever the caller
+	// installs (e.g. a lambda around oidn::FilterRef): it sees the film sums on the host and edits them in
+	// place; they are written back to the GPU.  Without a filter denoise() is a no-op.
+	typedef void (*DenoiseFn)(Colour* film, unsigned int width, unsigned int height, void* user);
+	void setDenoiser(DenoiseFn fn, void* user = NULL) { denoiseFn = fn, denoiseUser = user; }
+	void denoise()
+	{
+		if (!denoiseFn) return;
+		syncFilm();
+		denoiseFn(film->film, film->width, film->height, denoiseUser);
+		check(rtb_write_film(ctx, (const float*)film->film), "rtb_write_film");
+	}
 	void presentFilmToCanvas()
 	{
 		if (!canvas) return;
@@ -194,6 +206,8 @@ public:
 		stbi_write_png(filename.c_str(), canvas->getWidth(), canvas->getHeight(), 3, canvas->getBackBuffer(), canvas->getWidth() * 3);
 	}
 	void setPresentEveryFrame(bool on) { presentEveryFrame = on; }
+	DenoiseFn denoiseFn = NULL;
+	void* denoiseUser = NULL;
 	rtb_params& params() { return prm; }
 	void applyParams() { check(rtb_set_params(ctx, &prm), "rtb_set_params"); }
 	rtb_ctx* context() { return ctx; }

@@ -412,6 +412,27 @@ def test_instant_radiosity_equals_the_oracle_and_the_reference(rtb, oracle_mod):
     rt.close()
 
 
+def test_write_film_is_the_inverse_of_read_film(rtb):
+    """rtb_write_film: the hook for RayTracer::denoise (Renderer.h:750-792: film out, external filter,
+    film back).  Values round-trip through the 2^-32 fixed-point sums; rendering continues on top."""
+    rt = gpu_scene(rtb, "synthetic")
+    rt.render(3, 0)
+    a = rt.read_film().copy()
+    blurred = a.copy()
+    blurred[1:-1, 1:-1] = (a[:-2, 1:-1] + a[2:, 1:-1] + a[1:-1, :-2] + a[1:-1, 2:] + a[1:-1, 1:-1]) / 5
+    rt.write_film(blurred)
+    assert rt.getSPP() == 3
+    b = rt.read_film()
+    assert np.allclose(b, blurred, rtol=0, atol=2.0 ** -31)
+    rt.render(1, 3)
+    c = rt.read_film()
+    rt.clear()
+    rt.render(1, 3)
+    assert np.allclose(c - blurred, rt.read_film(), rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        rt.write_film(np.zeros((2, 2, 3), np.float32))
+
+
 def test_adaptive_render_full_resolution_and_shadow_queue_capacity(rtb, monkeypatch):
     """1024 tiles, tile-major job order: the pool works on a few floor / wall tiles at a time, where
     nearly every vertex queues a shadow ray and the multi-pass shade stage would queue two per slot
