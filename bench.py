@@ -222,15 +222,16 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             print(msg, file=sys.stderr, flush=True)
 
+    # stdout carries the ONE JSON line: anything libraries print there (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout: send it to a file so that
-        # stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "rtb200_nccl_%h_%p.log"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     name, flats = load_workload(args.scene, log)
     spp = args.spp
@@ -430,7 +431,8 @@ def run_ours(args, rank, world, local_rank):
             line["with_primary_hit_table"] = reuse
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, log)
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if dist is not None:
         dist.destroy_process_group()
 

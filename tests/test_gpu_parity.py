@@ -754,6 +754,12 @@ def test_standalone_cpp_program_without_any_reference_code(rtb, tmp_path):
     plain = np.load(os.path.join(GOLDEN, "cornell_ref_blocks.npz"))
     m = (np.fromfile(raw, "<f4").reshape(want.shape) / 2).mean(axis=(0, 1))
     assert np.all(np.abs(m / (0.5 * (plain["mean_a"] + plain["mean_b"])) - 1) < 0.01)
+    for flag in ("--light", "--ir"):
+        out = subprocess.run([exe, ref.scene_dir("cornell-box"), "2", hdr, flag, "--raw", raw], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        assert "SPP 2" in out.stdout
+        f = np.fromfile(raw, "<f4").reshape(want.shape)
+        assert np.isfinite(f).all() and f.mean() > 0.01, flag
     # a scene directory that does not exist is an error message and a non-zero exit, not a crash
     out = subprocess.run([exe, str(tmp_path / "nowhere"), "1", hdr], capture_output=True, text=True, timeout=60)
     assert out.returncode != 0
