@@ -17,7 +17,11 @@
 //                computeDirect's light sample with visibility deferred to a compact queue of
 //                shadow rays / Russian roulette / BSDF sample / regeneration.
 //   k_wf_shadow  Scene::visible (Scene.h:161-169) for the queued segments; adds the already
-//                weighted NEE contribution when unoccluded.
+//                weighted NEE contribution when unoccluded.  (RTB_INT_PATH_MIS: k_wf_mis instead, which
+//                also traces computeDirectMIS's BSDF-strategy probe ray of the same queue record.)
+// Variations on the same pool: a per-pixel primary-hit table (k_wf_primary, WF_PREHIT slots, a second
+// shade pass per launch), per-tile job plans for RayTracer::adaptiveRender (WfArgs::tileJobBase,
+// k_tile_variance, k_adaptive_merge).
 // Film::splat with BoxFilter (Imaging.h:139-154, 209-232) is an atomic add into per-pixel
 // 64-bit FIXED-POINT sums (2^-32 units): integer addition is associative, so the film is
 // bit-reproducible whatever the scheduling, and tile- or spp-partitioned renders compose to
