@@ -68,7 +68,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -98,7 +98,7 @@ class ClockSampler:
                 if v.strip().lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), sm_min_mhz=min(sm), reasons=sorted(reasons), samples=len(sm),
                        power_w_max=max(pw))
         return out
 
@@ -232,7 +232,11 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if os.environ.get("RTB_BENCH_DIAG") == "gloo":      # diagnosis only: no NCCL in the process, no film reduce
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    red_dev = "cpu" if os.environ.get("RTB_BENCH_DIAG") == "gloo" else "cuda"
     name, flats = load_workload(args.scene, log)
     spp = args.spp
     rts = []
@@ -250,7 +254,8 @@ def run_ours(args, rank, world, local_rank):
     accs = [D.accum_tensor(rt) for rt in rts]      # int64 fixed-point film sums (exact reduction)
     host = [torch.empty(a.numel(), dtype=torch.float32).pin_memory() for a in accs] if rank == 0 else []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
-    total_spp = spp * world
+    # weak scaling (the contract's default): every GPU renders `spp` samples per pixel; strong: `spp` in total
+    total_spp = spp * world if args.scaling == "weak" else spp
 
     def render_all():
         # rank r renders global sample indices {s : s % world == r}, spp of them
@@ -259,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
             rt.render(total_spp, 0)
 
     def reduce_all():
-        if dist is not None:
+        if dist is not None and os.environ.get("RTB_BENCH_DIAG") != "gloo":
             for rt in rts:
                 D.reduce_film(rt, total_spp)
 
@@ -274,7 +279,7 @@ def run_ours(args, rank, world, local_rank):
             rt.update_camera(rt.scene.camera)        # host struct through the ABI
             rt.clear()
             rt.render(total_spp, 0)
-            if dist is not None:
+            if dist is not None and os.environ.get("RTB_BENCH_DIAG") != "gloo":
                 D.reduce_film(rt, total_spp)
             if rank == 0:
                 rt.read_film(host[i].numpy().reshape(rt.height, rt.width, 3))   # D2H into pinned memory
@@ -290,7 +295,7 @@ def run_ours(args, rank, world, local_rank):
     launches0 = sum(rt.stats()["kernel_launches"] for rt in rts)
     for rt in rts:
         rt.clear()                       # also resets the per-context kernel timers / ray counters
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank)            # every rank watches its own GPU; rank 0's goes into `clocks`
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -298,11 +303,11 @@ def run_ours(args, rank, world, local_rank):
         step_device()
     e1.record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    ms = torch.tensor([e0.elapsed_time(e1)], device=red_dev)
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop()
     # per-stage kernel time + work counters of the LAST step (clear() resets them each step)
     st = [rt.stats() for rt in rts]
     launches = sum(s["kernel_launches"] for s in st) - launches0
@@ -315,6 +320,14 @@ def run_ours(args, rank, world, local_rank):
     iters = sum(s["iterations"] for s in st)
     timed = max(sum(s["timed_iterations"] for s in st), 1)
     stage_ms = {k: sum(s[k + "_ms"] for s in st) / timed for k in ("extend", "shade", "shadow")}   # avg per launch
+    # what each rank's GPU did in the last step (its renders' device time, no waiting for other ranks) and its
+    # clocks: the step ends with the slowest rank, and on a full box that is often a power-capped GPU
+    per_rank = None
+    if dist is not None:
+        mine = {"rank": rank, "render_ms_last_step": kern_ms, "clocks": clk}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     samples_step = samples_rank * world
     value = samples_step * args.steps / (ms_total / 1e3) / 1e6
     mrays = rays_rank * world * args.steps / (ms_total / 1e3) / 1e6
@@ -327,7 +340,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.e2e_steps):
         step_e2e()
     barrier()
-    dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dt = torch.tensor([time.perf_counter() - t0], device=red_dev)
     if dist is not None:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_val = samples_step * args.e2e_steps / float(dt.item()) / 1e6
@@ -347,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
             step_device()
         r1.record()
         barrier()
-        rms = torch.tensor([r0.elapsed_time(r1)], device="cuda")
+        rms = torch.tensor([r0.elapsed_time(r1)], device=red_dev)
         if dist is not None:
             dist.all_reduce(rms, op=dist.ReduceOp.MAX)
         rst = [rt.stats() for rt in rts]
@@ -401,9 +414,9 @@ def run_ours(args, rank, world, local_rank):
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "spp_per_gpu": spp, "spp_total": total_spp, "partition": "spp slice",
+            "config": {"workload": name, "spp_per_gpu": total_spp / world, "spp_total": total_spp, "partition": "spp slice",
                        "traversal": "fast", "sampling": "strict", "l2": "flushed between steps (256 MiB memset)",
                        "scene_source": "product host loader (librtb200_host.so) on the staged scene assets"},
             "mrays_per_s": mrays, "rays_per_sample": rays_rank / max(samples_rank, 1),
@@ -427,6 +440,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk,
         }
         line["config"]["primary_reuse"] = int(args.primary_reuse)
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if reuse is not None:
             line["with_primary_hit_table"] = reuse
         if world == 1 and not args.no_cpu:
@@ -449,6 +464,8 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--ref-spp", type=int, default=4, help="spp per scene per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --spp samples per pixel on EVERY GPU (default); strong: --spp in total, sliced over the GPUs")
     ap.add_argument("--primary-reuse", type=int, default=0, choices=[0, 1],
                     help="rtb_params.primary_reuse for the headline value / e2e (default 0: per-sample camera rays)")
     ap.add_argument("--max-depth", type=int, default=None, help="rtb_params.max_depth (default 4; soup scenes 0)")
