@@ -105,11 +105,23 @@ RTB_DEV bool triTest(const float4* __restrict__ tri, uint32_t id, const RayD& r,
 // tree, every node whose box passes, left before right, no culling; stack-free through the
 // pre-order skip links.  Leaf acceptance `t < best && t > EPSILON` (:412).
 // ---------------------------------------------------------------------------------------
+// A NaN in the origin or the direction (the reference's glass / normalise paths can produce one) makes
+// every triangle's plane distance t NaN: (d - n.o) / (n.d) has a NaN operand whichever component it is, and
+// 0 * NaN = NaN.  Triangle::rayIntersect then "hits" (all its rejects are comparisons, false on NaN) but
+// `t < best && t > EPSILON` (Geometry.h:412) is false: the reference's exhaustive walk returns a miss.
+// Walking 10^5 boxes that all pass to learn that would cost one thread tens of milliseconds — and a
+// persistent warp, hence the launch, with it (one such ray in bathroom sample 861 cost 0.35 s).
+RTB_DEV bool rayHasNaN(const RayD& r)
+{
+	return isnan(r.o.x) || isnan(r.o.y) || isnan(r.o.z) || isnan(r.d.x) || isnan(r.d.y) || isnan(r.d.z);
+}
+
 RTB_DEV void closestExact(const DevScene& S, const RayD& r, float eps, HitD& h, uint32_t& nBox, uint32_t& nTri)
 {
 	h.id = RTB_MISS_ID;
 	h.t = FLT_MAX;
 	h.alpha = h.beta = 0.0f;
+	if (rayHasNaN(r)) return;
 	uint32_t i = 0;
 	while (i < S.n_xnodes)
 	{
@@ -195,8 +207,9 @@ RTB_DEV bool visibleExact(const DevScene& S, const RayD& r, float eps, float max
 
 RTB_DEV bool rayIsDegenerate(const RayD& r)
 {
-	// an infinite reciprocal: direction component +-0 or so small that 1/d overflows
-	return isinf(r.inv.x) || isinf(r.inv.y) || isinf(r.inv.z);
+	// an infinite reciprocal (direction component +-0 or so small that 1/d overflows) or a NaN anywhere:
+	// the accelerated trees assume finite slab arithmetic
+	return !(fabsf(r.inv.x) <= FLT_MAX) || !(fabsf(r.inv.y) <= FLT_MAX) || !(fabsf(r.inv.z) <= FLT_MAX) || rayHasNaN(r);
 }
 
 RTB_DEV void leafClosest(const DevScene& S, int32_t ref, const RayD& r, float eps, HitD& h, uint32_t& nTri)

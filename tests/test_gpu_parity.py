@@ -118,6 +118,33 @@ def test_all_ray_kinds_equal_the_oracle(rtb, oracle_mod, name):
         assert np.array_equal(rt.visible(sets["segments"], traversal=trav), want_vis), trav
 
 
+@pytest.mark.parametrize("name", ["cornell-box", "coffee"])
+def test_nan_rays_behave_like_the_reference_and_cost_nothing(rtb, oracle_mod, name):
+    """A NaN in a ray's origin or direction (the reference's glass / normalise code can produce one) can
+    never be accepted as a closest hit (t is NaN for every triangle) and is "occluded" by the first triangle
+    an any-hit walk tests.  Same answers as the oracle's exhaustive walk — without walking the whole tree
+    (one such ray in bathroom sample 861 used to hold a persistent warp for 0.35 s)."""
+    import time
+    rt = gpu_scene(rtb, name)
+    o = oracle_mod.Oracle(rt.scene)
+    _, _, rays = rt.primary_hits(abi.TRAV_EXACT, want_rays=True)
+    rng = np.random.default_rng(9)
+    base = rays[rng.choice(len(rays), 600, replace=False)].copy()
+    for k, comp in enumerate((("o", 0), ("o", 1), ("o", 2), ("d", 0), ("d", 1), ("d", 2))):
+        base[comp[0]][k * 100:(k + 1) * 100, comp[1]] = np.nan
+    want = o.trace(base)
+    assert np.all(want["id"] == abi.MISS_ID)
+    want_any = o.trace(base, any_hit=True)["id"]
+    big = np.tile(base, (400, 1))                   # 240 k NaN rays: seconds if each walked the tree
+    for trav in TRAVS:
+        got = rt.trace(base, traversal=trav)
+        assert np.array_equal(got["id"], want["id"]) and got["t"].tobytes() == want["t"].tobytes(), trav
+        assert np.array_equal(rt.trace(base, any_hit=True, traversal=trav)["id"], want_any), trav
+        t0 = time.time()
+        rt.trace(big, traversal=trav)
+        assert time.time() - t0 < 1.0, trav
+
+
 # ------------------------------------------------------------------ gate 2: evaluations <= 1e-5
 def test_cornell_golden_shading_bsdf_light(rtb):
     rt = gpu_scene(rtb, "cornell-box")
