@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScen
 // a PREFETCHED next one (loads issued long before they are consumed, no atomics); a lane that
 // finishes swaps the prefetched ray in.  Inside a warp, interior-node steps and leaf steps are
 // scheduled by majority vote so that at least half of the busy lanes take part in every step.
-// The per-ray decisions are those of closestFastBody / visibleFastBody.  (Parking a reached leaf and
+// The per-ray decisions are those of closestAccel / visibleAccel (rtb_dev_scene.cuh).  (Parking a reached leaf and
 // descending on — "speculative traversal" — was measured 3 % slower on every scene: the delayed
 // t_best costs more box tests than the fuller leaf steps save, profiles/r01_v8_final_summary.md.)
 // ---------------------------------------------------------------------------------------
