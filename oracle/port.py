@@ -43,6 +43,7 @@ def lib():
         L.oracle_render_adaptive.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp, vp]
         L.oracle_render_light.argtypes = [vp, vp, u32, u32, vp, vp]
         L.oracle_render_ir.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp]
+        L.oracle_camera_derive.argtypes = [vp, vp]
         L.oracle_primary_hits.argtypes = [vp, f32, vp, vp, vp]
         L.oracle_trace.argtypes = [vp, f32, i32, vp, u64, vp]
         L.oracle_visible.argtypes = [vp, f32, vp, u64, vp]
@@ -140,6 +141,13 @@ class Oracle:
         self.L.oracle_render_ir(C.addressof(self.desc), C.addressof(self.params), int(pass_begin), int(passes), int(n_paths),
                                 int(threads or os.cpu_count() or 1), _p(film), _p(st))
         return film, dict(pixels=int(st[0]), closest_rays=int(st[1]), shadow_rays=int(st[2]), vpls=int(st[3]))
+
+    def camera_ext(self):
+        """include/rtb.h: rtb_camera_derive -> float32[36] = proj, world_to_cam, view_dir, afilm."""
+        out = np.zeros(36, "<f4")
+        if not self.L.oracle_camera_derive(C.addressof(self.desc.camera), _p(out)):
+            raise ValueError("singular camera matrices")
+        return out
 
     def render_counts(self, spp, spp_begin=0, threads=None):
         """render() + the CANONICAL traversal work of every ray it traced."""

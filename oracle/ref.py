@@ -47,6 +47,7 @@ def _lib(variant=""):
         lib.ref_render_adaptive.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
         lib.ref_render_light.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         lib.ref_render_ir.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        lib.ref_camera_ext.argtypes = [vp, vp]
         lib.ref_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_uint64]
         lib.ref_aov.argtypes = [vp, C.c_int, vp]
         lib.ref_tonemap.argtypes = [vp, vp, C.c_int, C.c_float, vp]
@@ -175,6 +176,12 @@ class RefScene:
         nv = C.c_uint64(0)
         self.lib.ref_render_ir(self.h, int(passes), int(threads), 1 if fresh else 0, _p(film), C.addressof(secs), C.addressof(nv))
         return film, secs.value, nv.value
+
+    def camera_ext(self):
+        """Camera::projectionMatrix, cameraToView, viewDirection, Afilm as one float32[36]."""
+        out = np.zeros(36, "<f4")
+        self.lib.ref_camera_ext(self.h, _p(out))
+        return out
 
     def aov(self, kind):
         k = {"albedo": 0, "normals": 1, "direct": 2}[kind]

@@ -499,6 +499,17 @@ int ref_render_ir(void* handle, int passes, int threads, int fresh, float* film_
 	return h->rt->getSPP();
 }
 
+// Camera::projectionMatrix (16), cameraToView (16), viewDirection (3), Afilm (1): Scene.h:11-41.
+int ref_camera_ext(void* handle, float* out36)
+{
+	RefScene* h = (RefScene*)handle;
+	Camera& c = h->scene->camera;
+	for (int i = 0; i < 16; i++) out36[i] = c.projectionMatrix.m[i], out36[16 + i] = c.cameraToView.m[i];
+	out36[32] = c.viewDirection.x, out36[33] = c.viewDirection.y, out36[34] = c.viewDirection.z;
+	out36[35] = c.Afilm;
+	return 0;
+}
+
 // stbi_load (the decoder behind Texture::load, Imaging.h:51) on one file: the golden for the product's
 // own PNG / JPEG decoders.  out may be NULL to query the size.
 int ref_decode_image(const char* path, int* w, int* h, int* channels, unsigned char* out, uint64_t cap)

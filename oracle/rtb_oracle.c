@@ -1193,6 +1193,13 @@ int oracle_render_ir(const rtb_scene_desc* s, const rtb_params* P, uint32_t pass
 	return 0;
 }
 
+/* include/rtb.h's rtb_camera_derive (what light tracing re-derives from the two camera matrices), exported so that
+ * tests can compare it with the reference's own Camera fields. */
+int oracle_camera_derive(const rtb_camera* c, rtb_camera_ext* e)
+{
+	return rtb_camera_derive(c, e);
+}
+
 /* oracle_render + the canonical-traversal work of every ray it traced.
  * stats = samples, closest, shadow, closest box tests, closest tri tests, shadow box, shadow tri.
  * Not re-entrant (one process-wide switch): tests/tools/canonical_counts.py is its only caller. */

@@ -219,6 +219,20 @@ def test_adaptive_render_against_the_reference(oracle_mod):
     assert np.all(np.abs(film2.mean(axis=(0, 1)) / (2 * g["film_mean"]) - 1) < 0.01)
 
 
+@pytest.mark.parametrize("name", ["cornell-box", "coffee", "materialball"])
+def test_camera_quantities_derived_for_light_tracing_equal_the_references(oracle_mod, name):
+    """include/rtb.h: rtb_camera_derive re-derives projectionMatrix, cameraToView, viewDirection and Afilm
+    (Scene.h:22-41) from the two matrices rtb_camera carries; they must be the reference Camera's own values
+    to float rounding (a matrix inverse in double on one side, the reference's float cofactors on the other)."""
+    rs = ref_scene(name)
+    want = rs.camera_ext()
+    got = oracle_mod.Oracle(flat_scene(name)).camera_ext()
+    scale = np.abs(want).max()
+    assert np.allclose(got[:32], want[:32], rtol=1e-4, atol=1e-5 * scale)
+    assert np.allclose(got[32:35], want[32:35], rtol=0, atol=1e-6) and abs(np.linalg.norm(got[32:35]) - 1) < 1e-6
+    assert abs(got[35] / want[35] - 1) < 1e-5
+
+
 def test_light_tracer_against_the_reference_statistics(oracle_mod):
     """RayTracer::lightTracer (Renderer.h:220-326).  Golden: two independent 48-pass halves of the
     unmodified reference on cornell-box 256x256 (block means).  Note its mean (0.36) is NOT the path
