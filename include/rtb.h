@@ -12,7 +12,9 @@
  * and the message of the last error is available from rtb_last_error().
  *
  * A context owns ONE device (one process per GPU is the deployment model; the film
- * reduction across GPUs is done by the caller with NCCL on rtb_film_device_ptr()).
+ * reduction across GPUs is done by the caller with NCCL on rtb_accum_device_ptr(): an exact
+ * integer SUM).  RayTracer::render's alternatives that the reference ships commented out
+ * (adaptiveRender, lightTracer, instantRadiosity, computeDirectMIS) are here too.
  * A context is not thread-safe.
  */
 #ifndef RTB_H_
