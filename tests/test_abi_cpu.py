@@ -112,3 +112,19 @@ def test_hdr_roundtrip(tmp_path):
     assert back.shape == img.shape
     # RGBE: 8-bit mantissa shared exponent
     assert np.all(np.abs(back - img) <= img.max(axis=-1, keepdims=True) / 128 + 1e-6)
+
+
+def test_standalone_cpp_program_is_built_and_fails_loudly_without_a_gpu(rtb):
+    """tools/rtb_render.cpp (Main.cpp's shape from this repository only) is part of the build; without a CUDA
+    device it reports the library's error and exits non-zero."""
+    import subprocess
+    import torch
+    from raytracingrenderer_b200 import build
+    assert os.path.isfile(build.CLI), "run python -m raytracingrenderer_b200.build"
+    out = subprocess.run([build.CLI], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "usage: rtb_render" in out.stderr
+    scene = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scenes", "_staged", "cornell-box")
+    if torch.cuda.is_available() or not os.path.isdir(scene):
+        return
+    out = subprocess.run([build.CLI, scene, "1", "/tmp/_rtb_render_test.hdr"], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
