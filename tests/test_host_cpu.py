@@ -132,3 +132,36 @@ def test_image_decoders_against_the_stb_image_golden(host):
         except RuntimeError:
             pass
     os.remove(f)
+
+
+def test_jpeg_decoder_on_random_images_against_stb_image(host, tmp_path):
+    """Beyond the committed fixtures: 60 random images (size 1..97, smooth / noisy / flat content) written by
+    Pillow with random quality, chroma subsampling, progressive / optimised / restart settings, decoded by the
+    product and by the reference's stb_image (needs oracle/_ref and Pillow: skipped otherwise)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(2026)
+    for i in range(60):
+        w, h = int(rng.integers(1, 98)), int(rng.integers(1, 98))
+        kind = i % 3
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif kind == 1:
+            y, x = np.mgrid[0:h, 0:w]
+            img = np.stack([(x * 5 + y * 3) % 256, (x * y) % 256, 255 - (x + y) % 256], -1).astype(np.uint8)
+        else:
+            img = np.full((h, w, 3), rng.integers(0, 256, 3), np.uint8)
+        kw = dict(quality=int(rng.integers(5, 100)), subsampling=int(rng.integers(0, 3)))
+        if rng.random() < 0.5:
+            kw["progressive"] = True
+        if rng.random() < 0.3:
+            kw["optimize"] = True
+        if rng.random() < 0.3:
+            kw["restart_marker_blocks"] = int(rng.integers(1, 9))
+        grey = rng.random() < 0.15
+        f = str(tmp_path / ("r%02d.jpg" % i))
+        (Image.fromarray(img[:, :, 0]) if grey else Image.fromarray(img)).save(f, "JPEG", **kw)
+        a, b = host.decode_image(f), ref.decode_image(f)
+        assert a.shape == b.shape and np.array_equal(a, b), (i, w, h, kw, grey)
