@@ -14,8 +14,8 @@
 //     <= 2 triangles, longest axis with the same tie rule, std::sort by centroid (the same
 //     libstdc++ algorithm sees the same comparison results, so it produces the same permutation
 //     although only 8-byte keys move), full SAH sweep with a strict '<';
-//   * PNG (8-bit, non-interlaced), JPEG (host/rtb_jpeg.hpp: baseline + progressive) and Radiance
-//     .hdr decode to the values stb_image produces.  A file that exists but cannot be decoded is
+//   * PNG (all colour types and bit depths, tRNS, Adam7), JPEG (host/rtb_jpeg.hpp: baseline +
+//     progressive) and Radiance .hdr decode to the values stb_image produces.  A file that exists but cannot be decoded is
 //     an error, never a silent default.
 // Build with -ffp-contract=off.
 #pragma once
@@ -223,71 +223,193 @@ inline std::vector<unsigned char> readFile(const std::string& path)
 inline uint32_t be32(const unsigned char* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 // 8-bit, non-interlaced PNG of colour type 0 (grey), 2 (RGB), 4 (grey+alpha), 6 (RGBA).
+// PNG -> 8-bit interleaved pixels with the channel count stb_image reports for req_comp = 0: every colour type
+// (grey, RGB, palette, grey+alpha, RGBA), bit depths 1/2/4/8/16, tRNS, Adam7 interlacing.  The conventions
+// that PNG leaves to the reader are stb_image's, because the reference decodes with it: sub-byte grey is
+// scaled to 0..255 (x255, x85, x17), 16-bit samples keep their high byte, a tRNS colour adds an alpha channel
+// of 0 / 255, a palette expands to RGB (RGBA with tRNS).
+inline bool pngUnfilter(const unsigned char* src, size_t srcLen, size_t& used, int x, int y, int pixelBits, std::vector<unsigned char>& rows)
+{
+	size_t rowBytes = ((size_t)x * pixelBits + 7) >> 3;
+	int bpp = pixelBits >= 8 ? pixelBits / 8 : 1; // filter unit in bytes
+	if (used + (rowBytes + 1) * (size_t)y > srcLen) return false;
+	rows.assign(rowBytes * (size_t)y, 0);
+	for (int j = 0; j < y; j++)
+	{
+		const unsigned char* in = src + used;
+		unsigned char* dst = &rows[rowBytes * (size_t)j];
+		const unsigned char* up = j ? dst - rowBytes : nullptr;
+		int filter = in[0];
+		in++;
+		used += rowBytes + 1;
+		for (size_t i = 0; i < rowBytes; i++)
+		{
+			int a = i >= (size_t)bpp ? dst[i - bpp] : 0;
+			int bb = up ? up[i] : 0;
+			int c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
+			int v = in[i];
+			switch (filter)
+			{
+			case 0: break;
+			case 1: v += a; break;
+			case 2: v += bb; break;
+			case 3: v += (a + bb) >> 1; break;
+			case 4:
+			{
+				int pp = a + bb - c, pa = abs(pp - a), pb = abs(pp - bb), pc = abs(pp - c);
+				v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? bb : c);
+				break;
+			}
+			default: return false;
+			}
+			dst[i] = (unsigned char)v;
+		}
+	}
+	return true;
+}
+
 inline bool decodePNG(const std::vector<unsigned char>& file, int& w, int& h, int& channels, std::vector<unsigned char>& out)
 {
 	static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
 	if (file.size() < 8 || memcmp(file.data(), sig, 8) != 0) return false;
 	size_t pos = 8;
 	std::vector<unsigned char> idat;
-	int bitDepth = 0, colourType = 0, interlace = 0;
+	int depth = 0, colourType = 0, interlace = 0;
+	unsigned char palette[256][4];
+	int palLen = 0;
+	bool hasTrans = false, palTrans = false;
+	unsigned tc[3] = {0, 0, 0};
 	w = h = 0;
 	while (pos + 12 <= file.size())
 	{
 		uint32_t len = be32(&file[pos]);
 		const unsigned char* type = &file[pos + 4];
 		const unsigned char* data = &file[pos + 8];
-		if (pos + 12 + len > file.size()) return false;
+		if (pos + 12 + (size_t)len > file.size()) return false;
 		if (!memcmp(type, "IHDR", 4))
 		{
+			if (len != 13) return false;
 			w = (int)be32(data), h = (int)be32(data + 4);
-			bitDepth = data[8], colourType = data[9], interlace = data[12];
+			depth = data[8], colourType = data[9], interlace = data[12];
+			if (data[10] != 0 || data[11] != 0 || interlace > 1) return false;
+		}
+		else if (!memcmp(type, "PLTE", 4))
+		{
+			if (len > 256 * 3 || len % 3) return false;
+			palLen = (int)(len / 3);
+			for (int i = 0; i < palLen; i++)
+				palette[i][0] = data[i * 3], palette[i][1] = data[i * 3 + 1], palette[i][2] = data[i * 3 + 2], palette[i][3] = 255;
+		}
+		else if (!memcmp(type, "tRNS", 4))
+		{
+			if (colourType == 3)
+			{
+				if (palLen == 0 || (int)len > palLen) return false;
+				for (uint32_t i = 0; i < len; i++) palette[i][3] = data[i];
+				palTrans = true;
+			}
+			else
+			{
+				int n = (colourType & 2) ? 3 : 1;
+				if ((colourType & 4) || (int)len != n * 2) return false;
+				for (int k = 0; k < n; k++) tc[k] = ((unsigned)data[k * 2] << 8) | data[k * 2 + 1];
+				hasTrans = true;
+			}
 		}
 		else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
 		else if (!memcmp(type, "IEND", 4)) break;
-		pos += 12 + len;
+		pos += 12 + (size_t)len;
 	}
-	if (w <= 0 || h <= 0 || bitDepth != 8 || interlace != 0) return false;
+	if (w <= 0 || h <= 0) return false;
+	if (depth != 1 && depth != 2 && depth != 4 && depth != 8 && depth != 16) return false;
+	int imgN;
 	switch (colourType)
 	{
-	case 0: channels = 1; break;
-	case 2: channels = 3; break;
-	case 4: channels = 2; break;
-	case 6: channels = 4; break;
-	default: return false; // palette images are not used by the scene format's exporters
+	case 0: imgN = 1; break;
+	case 2: imgN = 3; break;
+	case 3: imgN = 1; break;
+	case 4: imgN = 2; break;
+	case 6: imgN = 4; break;
+	default: return false;
 	}
-	size_t stride = (size_t)w * channels;
-	std::vector<unsigned char> raw((stride + 1) * (size_t)h);
-	uLongf rawLen = (uLongf)raw.size();
-	if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) return false;
-	out.assign(stride * (size_t)h, 0);
-	for (int y = 0; y < h; y++)
-	{
-		const unsigned char* src = &raw[(stride + 1) * (size_t)y];
-		unsigned char* dst = &out[stride * (size_t)y];
-		const unsigned char* up = y ? dst - stride : nullptr;
-		int filter = src[0];
-		src++;
-		for (size_t i = 0; i < stride; i++)
+	if (colourType == 3 && (depth == 16 || palLen == 0)) return false;
+	if ((colourType == 2 || colourType == 4 || colourType == 6) && depth < 8) return false;
+	// inflate
+	const int pixelBits = imgN * depth;
+	size_t rawCap = 0;
+	static const int xo[7] = {0, 4, 0, 2, 0, 1, 0}, yo[7] = {0, 0, 4, 0, 2, 0, 1}, xs[7] = {8, 8, 4, 4, 2, 2, 1}, ys[7] = {8, 8, 8, 4, 4, 2, 2};
+	if (!interlace) rawCap = ((((size_t)w * pixelBits + 7) >> 3) + 1) * (size_t)h;
+	else
+		for (int p = 0; p < 7; p++)
 		{
-			int a = i >= (size_t)channels ? dst[i - channels] : 0;
-			int b = up ? up[i] : 0;
-			int c = (up && i >= (size_t)channels) ? up[i - channels] : 0;
-			int v = src[i];
-			switch (filter)
+			int x = (w - xo[p] + xs[p] - 1) / xs[p], y = (h - yo[p] + ys[p] - 1) / ys[p];
+			if (x > 0 && y > 0) rawCap += ((((size_t)x * pixelBits + 7) >> 3) + 1) * (size_t)y;
+		}
+	std::vector<unsigned char> raw(rawCap);
+	uLongf rawLen = (uLongf)raw.size();
+	if (idat.empty() || uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) return false;
+	// samples as 16-bit values (so that one code path serves all depths), imgN per pixel
+	std::vector<uint16_t> px((size_t)w * h * imgN);
+	static const int depthScale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+	const int scale = (colourType == 0 && depth < 8) ? depthScale[depth] : 1;
+	size_t used = 0;
+	std::vector<unsigned char> rows;
+	for (int p = 0; p < (interlace ? 7 : 1); p++)
+	{
+		int x = interlace ? (w - xo[p] + xs[p] - 1) / xs[p] : w, y = interlace ? (h - yo[p] + ys[p] - 1) / ys[p] : h;
+		if (x <= 0 || y <= 0) continue;
+		if (!pngUnfilter(raw.data(), raw.size(), used, x, y, pixelBits, rows)) return false;
+		size_t rowBytes = ((size_t)x * pixelBits + 7) >> 3;
+		for (int j = 0; j < y; j++)
+			for (int i = 0; i < x; i++)
 			{
-			case 0: break;
-			case 1: v += a; break;
-			case 2: v += b; break;
-			case 3: v += (a + b) >> 1; break;
-			case 4:
-			{
-				int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
-				v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-				break;
+				int ox = interlace ? i * xs[p] + xo[p] : i, oy = interlace ? j * ys[p] + yo[p] : j;
+				uint16_t* d = &px[((size_t)oy * w + ox) * imgN];
+				const unsigned char* r = &rows[rowBytes * (size_t)j];
+				for (int k = 0; k < imgN; k++)
+				{
+					size_t sidx = (size_t)i * imgN + k;
+					if (depth == 16) d[k] = (uint16_t)((r[sidx * 2] << 8) | r[sidx * 2 + 1]);
+					else if (depth == 8) d[k] = r[sidx];
+					else
+					{
+						size_t bit = sidx * depth;
+						int v = (r[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+						d[k] = (uint16_t)(v * scale);
+					}
+				}
 			}
-			default: return false;
-			}
-			dst[i] = (unsigned char)v;
+	}
+	// to 8-bit output
+	const size_t n = (size_t)w * h;
+	if (colourType == 3)
+	{
+		channels = palTrans ? 4 : 3;
+		out.assign(n * channels, 0);
+		for (size_t i = 0; i < n; i++)
+		{
+			// stb_image reads palette[index] without a range check; its table has 256 zero-initialised-or-stale
+			// entries, so an out-of-range index is an invalid file: reject it
+			if ((int)px[i] >= palLen) return false;
+			for (int k = 0; k < channels; k++) out[i * channels + k] = palette[px[i]][k];
+		}
+		return true;
+	}
+	channels = imgN + (hasTrans ? 1 : 0);
+	out.assign(n * channels, 0);
+	unsigned key[3] = {tc[0], tc[1], tc[2]};
+	if (hasTrans && depth < 16)
+		for (int k = 0; k < 3; k++) key[k] = ((tc[k] & 255u) * (unsigned)(depth < 8 ? depthScale[depth] : 1)) & 255u; // stb: (uc)(v & 255) * scale
+	for (size_t i = 0; i < n; i++)
+	{
+		const uint16_t* sp = &px[i * imgN];
+		unsigned char* d = &out[i * channels];
+		for (int k = 0; k < imgN; k++) d[k] = depth == 16 ? (unsigned char)(sp[k] >> 8) : (unsigned char)sp[k];
+		if (hasTrans)
+		{
+			bool same = true;
+			for (int k = 0; k < imgN; k++) same = same && sp[k] == key[k];
+			d[imgN] = same ? 0 : 255;
 		}
 	}
 	return true;
@@ -412,7 +534,7 @@ public:
 		std::vector<unsigned char> px;
 		bool isJPEG = file.size() > 2 && file[0] == 0xFF && file[1] == 0xD8;
 		if (!(isJPEG ? rtb_img::decodeJPEG(file, width, height, channels, px) : rtb_img::decodePNG(file, width, height, channels, px)))
-			throw std::runtime_error("cannot decode " + filename + " (8-bit non-interlaced PNG, Huffman JPEG and Radiance .hdr are supported)");
+			throw std::runtime_error("cannot decode " + filename + " (PNG, Huffman JPEG and Radiance .hdr are supported)");
 		if (channels < 3) throw std::runtime_error(filename + ": grey textures are read out of bounds by the reference (Imaging.h:60)");
 		texels = new Colour[(size_t)width * height];
 		for (size_t i = 0; i < (size_t)width * height; i++)

@@ -165,3 +165,108 @@ def test_jpeg_decoder_on_random_images_against_stb_image(host, tmp_path):
         (Image.fromarray(img[:, :, 0]) if grey else Image.fromarray(img)).save(f, "JPEG", **kw)
         a, b = host.decode_image(f), ref.decode_image(f)
         assert a.shape == b.shape and np.array_equal(a, b), (i, w, h, kw, grey)
+
+
+def _write_png(path, w, h, ctype, depth, samples, interlace=False, palette=None, trns=None, rng=None):
+    """Minimal PNG encoder for tests: `samples` is uint16 [h, w, n] (n = channels of the colour type, values <
+    2^depth), every scanline gets a random filter type, Adam7 optional."""
+    import struct, zlib
+    n = samples.shape[2]
+
+    def pack(rows):                      # rows: [y, x, n] -> bytes per scanline
+        out = []
+        for r in rows:
+            v = r.reshape(-1)
+            if depth == 16:
+                b = v.astype(">u2").tobytes()
+            elif depth == 8:
+                b = v.astype(np.uint8).tobytes()
+            else:
+                bits = np.zeros(len(v) * depth, np.uint8)
+                for k in range(depth):
+                    bits[k::depth] = (v >> (depth - 1 - k)) & 1
+                b = np.packbits(bits).tobytes()
+            out.append(b)
+        return out
+
+    def filt(lines, bpp):
+        res, prev = b"", None
+        for line in lines:
+            cur = np.frombuffer(line, np.uint8).astype(np.int32)
+            up = np.zeros_like(cur) if prev is None else prev
+            a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+            c = np.concatenate([np.zeros(bpp, np.int32), up[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+            if len(cur) <= bpp:
+                a = np.zeros_like(cur); c = np.zeros_like(cur)
+            ft = int(rng.integers(0, 5)) if rng is not None else 0
+            if ft == 0: o = cur
+            elif ft == 1: o = cur - a
+            elif ft == 2: o = cur - up
+            elif ft == 3: o = cur - ((a + up) >> 1)
+            else:
+                pp = a + up - c
+                pa, pb, pc = np.abs(pp - a), np.abs(pp - up), np.abs(pp - c)
+                pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, up, c))
+                o = cur - pred
+            res += bytes([ft]) + (o & 255).astype(np.uint8).tobytes()
+            prev = cur
+        return res
+    bpp = max(1, n * depth // 8)
+    if not interlace:
+        raw = filt(pack(samples), bpp)
+    else:
+        raw = b""
+        for xo, yo, xs, ys in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            sub = samples[yo::ys, xo::xs]
+            if sub.shape[0] and sub.shape[1]:
+                raw += filt(pack(sub), bpp)
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        data += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    if trns is not None:
+        data += chunk(b"tRNS", trns)
+    half = len(raw) // 2 if len(raw) > 40 else len(raw)
+    z = zlib.compress(raw, 6)
+    data += chunk(b"IDAT", z[:len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b"")
+    open(path, "wb").write(data)
+
+
+def test_png_decoder_all_colour_types_depths_interlace_against_stb_image(host, tmp_path):
+    """Every PNG colour type x bit depth x {plain, Adam7} x {no tRNS, tRNS}, random scanline filters, odd sizes —
+    against the reference's stb_image (needs oracle/_ref: skipped otherwise)."""
+    from oracle import ref
+    import struct
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(77)
+    combos = [(0, d) for d in (1, 2, 4, 8, 16)] + [(2, 8), (2, 16)] + [(3, d) for d in (1, 2, 4, 8)] + [(4, 8), (4, 16), (6, 8), (6, 16)]
+    count = 0
+    for ctype, depth in combos:
+        n = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+        for interlace in (False, True):
+            for with_trns in (False, True):
+                if with_trns and ctype in (4, 6):
+                    continue
+                w, h = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+                palette = None
+                hi = 1 << depth
+                if ctype == 3:
+                    palette = rng.integers(0, 256, (hi, 3))
+                samples = rng.integers(0, hi, (h, w, n)).astype(np.uint16)
+                if rng.random() < 0.5 and w > 3:
+                    samples[:, : w // 2] = samples[0, 0]                  # flat region: makes the tRNS colour occur
+                trns = None
+                if with_trns:
+                    if ctype == 3:
+                        trns = bytes(rng.integers(0, 256, int(rng.integers(1, hi + 1))).astype(np.uint8))
+                    else:
+                        trns = b"".join(struct.pack(">H", int(v)) for v in samples[0, 0])
+                f = str(tmp_path / ("c%d_d%d_i%d_t%d.png" % (ctype, depth, interlace, with_trns)))
+                _write_png(f, w, h, ctype, depth, samples, interlace, palette, trns, rng)
+                a, b = host.decode_image(f), ref.decode_image(f)
+                assert a.shape == b.shape and np.array_equal(a, b), (ctype, depth, interlace, with_trns, w, h)
+                count += 1
+    assert count >= 48
