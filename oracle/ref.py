@@ -48,6 +48,7 @@ def _lib(variant=""):
         lib.ref_render_light.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         lib.ref_render_ir.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         lib.ref_camera_ext.argtypes = [vp, vp]
+        lib.ref_decode_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_uint64]
         lib.ref_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_uint64]
         lib.ref_aov.argtypes = [vp, C.c_int, vp]
         lib.ref_tonemap.argtypes = [vp, vp, C.c_int, C.c_float, vp]
@@ -204,4 +205,15 @@ def decode_image(path):
         raise RuntimeError("stbi_load failed on " + path)
     out = np.zeros((h.value, w.value, c.value), np.uint8)
     lib.ref_decode_image(path.encode(), C.byref(w), C.byref(h), C.byref(c), _p(out), out.size)
+    return out
+
+
+def decode_hdr(path):
+    """stbi_loadf of the reference on one .hdr file -> float32 [H, W, channels]."""
+    lib = _lib("")
+    w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    if lib.ref_decode_hdr(path.encode(), C.byref(w), C.byref(h), C.byref(c), None, 0) != 0:
+        raise RuntimeError("stbi_loadf failed on " + path)
+    out = np.zeros((h.value, w.value, c.value), "<f4")
+    lib.ref_decode_hdr(path.encode(), C.byref(w), C.byref(h), C.byref(c), _p(out), out.size)
     return out

@@ -499,6 +499,22 @@ int ref_render_ir(void* handle, int passes, int threads, int fresh, float* film_
 	return h->rt->getSPP();
 }
 
+// stbi_loadf (Texture::load's .hdr branch, Imaging.h:37) on one file.  out may be NULL to query the size.
+int ref_decode_hdr(const char* path, int* w, int* h, int* channels, float* out, uint64_t cap_floats)
+{
+	float* d = stbi_loadf(path, w, h, channels, 0);
+	if (!d) return -1;
+	uint64_t n = (uint64_t)(*w) * (*h) * (*channels);
+	int rc = 0;
+	if (out)
+	{
+		if (n > cap_floats) rc = -2;
+		else memcpy(out, d, n * sizeof(float));
+	}
+	stbi_image_free(d);
+	return rc;
+}
+
 // Camera::projectionMatrix (16), cameraToView (16), viewDirection (3), Afilm (1): Scene.h:11-41.
 int ref_camera_ext(void* handle, float* out36)
 {

@@ -146,6 +146,21 @@ int rtbh_decode_image(const char* path, int* w, int* h, int* channels, unsigned 
 	return 0;
 }
 
+// Radiance .hdr with the loader's own decoder -> float RGB (what Texture::load stores).  out may be NULL.
+int rtbh_decode_hdr(const char* path, int* w, int* h, float* out, uint64_t cap_floats)
+{
+	std::vector<unsigned char> file = rtb_img::readFile(path);
+	if (file.empty()) return -1;
+	std::vector<float> px;
+	if (!rtb_img::decodeHDR(file, *w, *h, px)) return -1;
+	if (out)
+	{
+		if (px.size() > cap_floats) return -2;
+		memcpy(out, px.data(), px.size() * sizeof(float));
+	}
+	return 0;
+}
+
 // Test hook: 1 if the builder's parallel sort reproduces std::sort's permutation (ties included) on `keys`.
 int rtbh_sort_selftest(const float* keys, uint32_t n, int par)
 {

@@ -28,6 +28,7 @@ def lib():
         L.rtbh_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.rtbh_build_soup.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
         L.rtbh_sort_selftest.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+        L.rtbh_decode_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_uint64]
         L.rtbh_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
@@ -99,4 +100,14 @@ def decode_image(path):
     out = np.zeros((h.value, w.value, c.value), np.uint8)
     if lib().rtbh_decode_image(path.encode(), C.byref(w), C.byref(h), C.byref(c), out.ctypes.data, out.size) != 0:
         raise RuntimeError("cannot decode " + path)
+    return out
+
+
+def decode_hdr(path):
+    """Radiance .hdr -> float32 [H, W, 3] with the loader's own decoder; raises on failure."""
+    w, h = C.c_int(0), C.c_int(0)
+    if lib().rtbh_decode_hdr(path.encode(), C.byref(w), C.byref(h), None, 0) != 0:
+        raise RuntimeError("cannot decode " + path)
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    lib().rtbh_decode_hdr(path.encode(), C.byref(w), C.byref(h), out.ctypes.data, out.size)
     return out

@@ -270,3 +270,50 @@ def test_png_decoder_all_colour_types_depths_interlace_against_stb_image(host, t
                 assert a.shape == b.shape and np.array_equal(a, b), (ctype, depth, interlace, with_trns, w, h)
                 count += 1
     assert count >= 48
+
+
+def _write_hdr(path, rgbe, rle, tag=b"#?RADIANCE"):
+    """rgbe: uint8 [h, w, 4].  rle = new-style per-channel run-length scanlines, else flat."""
+    h, w, _ = rgbe.shape
+    out = tag + b"\nFORMAT=32-bit_rle_rgbe\n\n" + ("-Y %d +X %d\n" % (h, w)).encode()
+    for y in range(h):
+        if not rle:
+            out += rgbe[y].tobytes()
+            continue
+        out += bytes([2, 2, w >> 8, w & 255])
+        for c in range(4):
+            row = rgbe[y, :, c]
+            x = 0
+            while x < w:
+                run = 1
+                while x + run < w and run < 127 and row[x + run] == row[x]:
+                    run += 1
+                if run >= 3:
+                    out += bytes([128 + run, int(row[x])])
+                    x += run
+                else:
+                    lit = 1
+                    while x + lit < w and lit < 128 and not (x + lit + 2 < w and row[x + lit] == row[x + lit + 1] == row[x + lit + 2]):
+                        lit += 1
+                    out += bytes([lit]) + row[x:x + lit].tobytes()
+                    x += lit
+    open(path, "wb").write(out)
+
+
+def test_hdr_decoder_flat_and_rle_against_stb_image(host, tmp_path):
+    """Radiance .hdr: run-length and flat scanlines, widths below 8 (always flat), zero exponents, both magic
+    lines — float values equal to stbi_loadf's bit for bit (needs oracle/_ref: skipped otherwise)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(31)
+    for i, (w, h, rle) in enumerate(((40, 7, True), (40, 7, False), (5, 9, False), (64, 3, True), (300, 4, True), (8, 8, True), (33, 2, False))):
+        rgbe = rng.integers(0, 256, (h, w, 4)).astype(np.uint8)
+        rgbe[:, : w // 3] = rgbe[0, 0]                      # runs
+        rgbe[0, -1, 3] = 0                                  # a zero exponent
+        rgbe[:, :, 3] = np.clip(rgbe[:, :, 3].astype(int) % 40 + 110, 0, 255)
+        rgbe[0, -1, 3] = 0
+        f = str(tmp_path / ("t%d.hdr" % i))
+        _write_hdr(f, rgbe, rle, b"#?RGBE" if i == 3 else b"#?RADIANCE")
+        a, b = host.decode_hdr(f), ref.decode_hdr(f)
+        assert a.shape == b.shape and a.tobytes() == b.tobytes(), (w, h, rle)
