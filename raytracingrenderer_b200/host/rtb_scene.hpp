@@ -1209,6 +1209,8 @@ struct Json
 		}
 	}
 };
+// Strict enough to reject a damaged scene.json with a position instead of loading an empty scene
+// (the reference's own ad-hoc parser, GEMLoader.h:380-712, reads garbage silently).
 class JsonParser
 {
 	const std::string& s;
@@ -1218,11 +1220,71 @@ class JsonParser
 		while (pos < s.size() && isspace((unsigned char)s[pos])) pos++;
 	}
 	char peek() const { return pos < s.size() ? s[pos] : 0; }
+	[[noreturn]] void fail(const char* what) const
+	{
+		throw std::runtime_error("JSON: " + std::string(what) + " at byte " + std::to_string(pos));
+	}
+	void expect(char c, const char* what)
+	{
+		ws();
+		if (peek() != c) fail(what);
+		pos++;
+	}
+	void literal(const char* word)
+	{
+		size_t n = strlen(word);
+		if (s.compare(pos, n, word) != 0) fail("unknown literal");
+		pos += n;
+	}
+	std::string string()
+	{
+		std::string out;
+		pos++; // opening quote
+		for (;;)
+		{
+			if (pos >= s.size()) fail("unterminated string");
+			char c = s[pos++];
+			if (c == '"') break;
+			if (c == '\\')
+			{
+				if (pos >= s.size()) fail("unterminated escape");
+				char e = s[pos++];
+				switch (e)
+				{
+				case 'n': out.push_back('\n'); break;
+				case 't': out.push_back('\t'); break;
+				case 'r': out.push_back('\r'); break;
+				case 'b': out.push_back('\b'); break;
+				case 'f': out.push_back('\f'); break;
+				case 'u':
+				{
+					if (pos + 4 > s.size()) fail("short \\u escape");
+					unsigned v = (unsigned)strtoul(s.substr(pos, 4).c_str(), nullptr, 16);
+					pos += 4;
+					out.push_back(v < 128 ? (char)v : '?'); // file names in scene.json are ASCII
+					break;
+				}
+				default: out.push_back(e); break; // \" \\ \/
+				}
+			}
+			else
+				out.push_back(c);
+		}
+		return out;
+	}
 
 public:
 	JsonParser(const std::string& text) : s(text) {}
-	Json value()
+	Json document()
 	{
+		Json j = value(0);
+		ws();
+		if (pos != s.size()) fail("trailing characters");
+		return j;
+	}
+	Json value(int depth = 0)
+	{
+		if (depth > 64) fail("nesting too deep");
 		ws();
 		Json j;
 		char c = peek();
@@ -1239,14 +1301,15 @@ public:
 			for (;;)
 			{
 				ws();
-				std::string key = value().str;
-				ws();
-				pos++; // ':'
-				j.obj[key] = value();
+				if (peek() != '"') fail("expected a member name");
+				std::string key = string();
+				expect(':', "expected ':'");
+				j.obj[key] = value(depth + 1);
 				ws();
 				char d = peek();
+				if (d != ',' && d != '}') fail("expected ',' or '}'");
 				pos++;
-				if (d != ',') break;
+				if (d == '}') break;
 			}
 		}
 		else if (c == '[')
@@ -1261,34 +1324,34 @@ public:
 			}
 			for (;;)
 			{
-				j.arr.push_back(value());
+				j.arr.push_back(value(depth + 1));
 				ws();
 				char d = peek();
+				if (d != ',' && d != ']') fail("expected ',' or ']'");
 				pos++;
-				if (d != ',') break;
+				if (d == ']') break;
 			}
 		}
 		else if (c == '"')
 		{
 			j.type = Json::String;
-			pos++;
-			while (pos < s.size() && s[pos] != '"') j.str.push_back(s[pos++]);
-			pos++;
+			j.str = string();
 		}
 		else if (c == 't' || c == 'f')
 		{
 			j.type = Json::Bool;
 			j.b = (c == 't');
-			pos += j.b ? 4 : 5;
+			literal(j.b ? "true" : "false");
 		}
 		else if (c == 'n')
 		{
-			pos += 4;
+			literal("null");
 		}
 		else if (c == '-' || isdigit((unsigned char)c))
 		{
 			size_t start = pos;
 			if (peek() == '-') pos++;
+			if (!isdigit((unsigned char)peek())) fail("malformed number");
 			while (isdigit((unsigned char)peek())) pos++;
 			if (peek() == '.')
 			{
@@ -1305,7 +1368,7 @@ public:
 			j.num = std::stof(s.substr(start, pos - start));
 		}
 		else
-			pos++;
+			fail(c ? "unexpected character" : "unexpected end of input");
 		return j;
 	}
 };
@@ -1322,7 +1385,8 @@ public:
 		std::stringstream buffer;
 		buffer << file.rdbuf();
 		std::string content = buffer.str();
-		Json data = JsonParser(content).value();
+		Json data = JsonParser(content).document();
+		if (data.type != Json::Object) throw std::runtime_error(filename + ": the top level of scene.json must be an object");
 		for (const auto& item : data.obj)
 		{
 			if (item.second.type != Json::Array)

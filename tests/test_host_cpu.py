@@ -317,3 +317,29 @@ def test_hdr_decoder_flat_and_rle_against_stb_image(host, tmp_path):
         _write_hdr(f, rgbe, rle, b"#?RGBE" if i == 3 else b"#?RADIANCE")
         a, b = host.decode_hdr(f), ref.decode_hdr(f)
         assert a.shape == b.shape and a.tobytes() == b.tobytes(), (w, h, rle)
+
+
+def test_damaged_scene_files_are_errors_with_a_reason(host, tmp_path):
+    """A scene.json that is not JSON, is cut off, or is not an object; a mesh file that is missing or cut off:
+    loadScene raises with the reason (the reference prints and exit(0)s, GEMLoader.h:349-354, or reads garbage)."""
+    import shutil
+    rs = ref_scene("cornell-box")
+    d = tmp_path / "s"
+    shutil.copytree(rs.dir, d, symlinks=False)
+    good = open(d / "scene.json").read()
+    for text, why in (("{ this is not json", "JSON"), (good[: len(good) // 2], "JSON"), (good + " x", "trailing"), ("[1, 2]", "object")):
+        open(d / "scene.json", "w").write(text)
+        with pytest.raises(RuntimeError) as e:
+            host.load_scene(str(d))
+        assert why in str(e.value), (text[:20], str(e.value))
+    open(d / "scene.json", "w").write(good)
+    assert host.load_scene(str(d)).n_tris == 36
+    gem = sorted(p for p in os.listdir(d) if p.endswith(".gem"))[0]
+    data = open(d / gem, "rb").read()
+    open(d / gem, "wb").write(data[:100])
+    with pytest.raises(RuntimeError) as e:
+        host.load_scene(str(d))
+    assert "truncated" in str(e.value)
+    os.remove(d / gem)
+    with pytest.raises(RuntimeError):
+        host.load_scene(str(d))
