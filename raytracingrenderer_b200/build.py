@@ -40,7 +40,7 @@ def up_to_date():
 
 
 HOST_LIB = os.path.join(HERE, "librtb200_host.so")
-HOST_DEPS = ["rtb_host.cpp", "rtb_scene.hpp", "rtb_flatten.hpp", "rtb_jpeg.hpp"]
+HOST_DEPS = ["rtb_host.cpp", "rtb_scene.hpp", "rtb_flatten.hpp", "rtb_jpeg.hpp", "rtb_standalone.hpp"]
 CLI = os.path.join(HERE, "rtb_render")
 
 

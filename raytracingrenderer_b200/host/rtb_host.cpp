@@ -2,7 +2,7 @@
 // scene loading / BVH building / flattening without any reference code, used by bench.py,
 // the examples and the parity tests of the loader (tests/test_host_cpu.py).
 // Build: g++ -std=c++17 -O2 -ffp-contract=off -shared -fPIC rtb_host.cpp -lz
-#include "rtb_scene.hpp"
+#include "rtb_standalone.hpp"
 
 #include "rtb_flatten.hpp"
 
@@ -159,6 +159,16 @@ int rtbh_decode_hdr(const char* path, int* w, int* h, float* out, uint64_t cap_f
 		memcpy(out, px.data(), px.size() * sizeof(float));
 	}
 	return 0;
+}
+
+// The stand-alone program's image writers (Film::save's Radiance .hdr, savePNG's 8-bit PNG), callable for tests.
+int rtbh_write_hdr(const char* path, int w, int h, const float* rgb)
+{
+	return rtb_img::writeHDR(path, w, h, rgb) ? 0 : -1;
+}
+int rtbh_write_png(const char* path, int w, int h, int channels, const unsigned char* data)
+{
+	return rtb_img::writePNG(path, w, h, channels, data, w * channels) ? 0 : -1;
 }
 
 // Test hook: 1 if the builder's parallel sort reproduces std::sort's permutation (ties included) on `keys`.

@@ -29,6 +29,8 @@ def lib():
         L.rtbh_build_soup.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
         L.rtbh_sort_selftest.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
         L.rtbh_decode_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_uint64]
+        L.rtbh_write_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+        L.rtbh_write_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.rtbh_decode_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
@@ -111,3 +113,17 @@ def decode_hdr(path):
     out = np.zeros((h.value, w.value, 3), np.float32)
     lib().rtbh_decode_hdr(path.encode(), C.byref(w), C.byref(h), out.ctypes.data, out.size)
     return out
+
+
+def write_hdr(path, rgb):
+    """float32 [H, W, 3] -> Radiance .hdr with the stand-alone program's writer (Film::save)."""
+    a = np.ascontiguousarray(rgb, np.float32)
+    if lib().rtbh_write_hdr(path.encode(), a.shape[1], a.shape[0], a.ctypes.data) != 0:
+        raise IOError("cannot write " + path)
+
+
+def write_png(path, img):
+    """uint8 [H, W, C] (C = 1, 3 or 4) -> PNG with the stand-alone program's writer (savePNG)."""
+    a = np.ascontiguousarray(img, np.uint8)
+    if lib().rtbh_write_png(path.encode(), a.shape[1], a.shape[0], a.shape[2], a.ctypes.data) != 0:
+        raise IOError("cannot write " + path)

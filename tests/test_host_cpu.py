@@ -343,3 +343,28 @@ def test_damaged_scene_files_are_errors_with_a_reason(host, tmp_path):
     os.remove(d / gem)
     with pytest.raises(RuntimeError):
         host.load_scene(str(d))
+
+
+def test_image_writers_round_trip(host, tmp_path):
+    """Film::save's .hdr and savePNG's .png as written by the stand-alone C++ program: the PNG decodes to the
+    same bytes (own decoder, and stb_image when oracle/_ref is there); the RGBE file decodes to the values
+    within the format's 1/256 mantissa step, identically by both decoders."""
+    from oracle import ref
+    rng = np.random.default_rng(12)
+    for c in (1, 3, 4):
+        img = rng.integers(0, 256, (23, 37, c), dtype=np.uint8)
+        f = str(tmp_path / ("w%d.png" % c))
+        host.write_png(f, img)
+        assert np.array_equal(host.decode_image(f), img)
+        if ref.available():
+            assert np.array_equal(ref.decode_image(f), img)
+    rgb = (rng.random((19, 41, 3)) ** 4 * 50).astype(np.float32)
+    rgb[0, 0] = 0
+    rgb[1, 1] = [1e-3, 2.0, 300.0]
+    f = str(tmp_path / "w.hdr")
+    host.write_hdr(f, rgb)
+    back = host.decode_hdr(f)
+    assert np.all(np.abs(back - rgb) <= rgb.max(axis=-1, keepdims=True) / 128 + 1e-30)
+    assert back[0, 0].tolist() == [0, 0, 0]
+    if ref.available():
+        assert back.tobytes() == ref.decode_hdr(f).tobytes()
