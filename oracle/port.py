@@ -153,10 +153,11 @@ class Oracle:
         """render() + the CANONICAL traversal work of every ray it traced."""
         film = np.zeros((self.height, self.width, 3), "<f4")
         threads = threads or os.cpu_count() or 1
-        st = np.zeros(7, np.uint64)
+        st = np.zeros(11, np.uint64)
         self.L.oracle_render_counts(C.addressof(self.desc), C.addressof(self.params), int(spp_begin), int(spp),
                                     int(threads), _p(film), _p(st))
-        keys = ("samples", "closest_rays", "shadow_rays", "closest_box", "closest_tri", "shadow_box", "shadow_tri")
+        keys = ("samples", "closest_rays", "shadow_rays", "closest_box", "closest_tri", "shadow_box", "shadow_tri",
+                "closest_box_max", "shadow_box_max", "closest_rays_over_20k_boxes", "nan_rays")
         return film, {k: int(v) for k, v in zip(keys, st)}
 
     def primary_hits(self, want_rays=False):

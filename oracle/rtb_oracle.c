@@ -65,6 +65,7 @@ static ray_t make_ray(v3 o, v3 d) /* Geometry.h:21-26 */
 typedef struct {
 	uint64_t closest, shadow, samples;
 	uint64_t cbox, ctri, sbox, stri; /* canonical-traversal work (oracle_render_counts only) */
+	uint64_t cmax, smax, cbig, nanrays; /* largest box count of one closest / shadow ray, rays above 20 x 2^10 boxes, NaN rays */
 } tally_t;
 
 static int g_count_canonical = 0;
@@ -269,7 +270,15 @@ static void canonical_count(const rtb_scene_desc* s, const ray_t* r, float eps, 
 
 static rtb_hit scene_traverse_tl(const rtb_scene_desc* s, const ray_t* r, float eps, tally_t* tl)
 {
-	if (g_count_canonical) canonical_count(s, r, eps, 0, FLT_MAX, &tl->cbox, &tl->ctri);
+	if (g_count_canonical)
+	{
+		uint64_t b0 = tl->cbox, nb;
+		canonical_count(s, r, eps, 0, FLT_MAX, &tl->cbox, &tl->ctri);
+		nb = tl->cbox - b0;
+		if (nb > tl->cmax) tl->cmax = nb;
+		if (nb > 20480) tl->cbig++;
+		if (r->o.x != r->o.x || r->o.y != r->o.y || r->o.z != r->o.z || r->d.x != r->d.x || r->d.y != r->d.y || r->d.z != r->d.z) tl->nanrays++;
+	}
 	return scene_traverse(s, r, eps);
 }
 
@@ -282,7 +291,11 @@ static int scene_visible_tl(const rtb_scene_desc* s, v3 p1, v3 p2, float eps, ta
 		ray_t r;
 		dir = norm3(dir);
 		r = make_ray(add(p1, scl(dir, eps)), dir);
-		canonical_count(s, &r, eps, 1, maxT, &tl->sbox, &tl->stri);
+		{
+			uint64_t b0 = tl->sbox;
+			canonical_count(s, &r, eps, 1, maxT, &tl->sbox, &tl->stri);
+			if (tl->sbox - b0 > tl->smax) tl->smax = tl->sbox - b0;
+		}
 	}
 	return scene_visible(s, p1, p2, eps);
 }
@@ -817,12 +830,17 @@ int oracle_render(const rtb_scene_desc* s, const rtb_params* P, uint32_t spp_beg
 	if (stats)
 	{
 		stats[0] = stats[1] = stats[2] = 0;
-		if (g_count_canonical) stats[3] = stats[4] = stats[5] = stats[6] = 0;
+		if (g_count_canonical) stats[3] = stats[4] = stats[5] = stats[6] = stats[7] = stats[8] = stats[9] = stats[10] = 0;
 		for (c = 0; c < chunks; c++)
 		{
 			stats[0] += jobs[c].tl.samples, stats[1] += jobs[c].tl.closest, stats[2] += jobs[c].tl.shadow;
 			if (g_count_canonical)
+			{
 				stats[3] += jobs[c].tl.cbox, stats[4] += jobs[c].tl.ctri, stats[5] += jobs[c].tl.sbox, stats[6] += jobs[c].tl.stri;
+				if (jobs[c].tl.cmax > stats[7]) stats[7] = jobs[c].tl.cmax;
+				if (jobs[c].tl.smax > stats[8]) stats[8] = jobs[c].tl.smax;
+				stats[9] += jobs[c].tl.cbig, stats[10] += jobs[c].tl.nanrays;
+			}
 		}
 	}
 	free(spans);
@@ -1204,7 +1222,7 @@ int oracle_camera_derive(const rtb_camera* c, rtb_camera_ext* e)
  * stats = samples, closest, shadow, closest box tests, closest tri tests, shadow box, shadow tri.
  * Not re-entrant (one process-wide switch): tests/tools/canonical_counts.py is its only caller. */
 int oracle_render_counts(const rtb_scene_desc* s, const rtb_params* P, uint32_t spp_begin, uint32_t spp_count, int threads,
-                         float* film_sum, uint64_t* stats7)
+                         float* film_sum, uint64_t* stats7 /* 11 entries: ... + max boxes of a closest / shadow ray, rays > 20480 boxes, NaN rays */)
 {
 	int rc;
 	g_count_canonical = 1;

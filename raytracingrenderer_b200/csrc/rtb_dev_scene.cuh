@@ -665,7 +665,11 @@ RTB_DEV float fresnelDielectric(float cosTheta, float iorInt, float iorExt, V3& 
 	float Fpa = (cosTheta - ior * cosTheta_t) / (cosTheta + ior * cosTheta_t);
 	float Fpe = (ior * cosTheta - cosTheta_t) / (ior * cosTheta + ior * cosTheta_t);
 	float average = ((Fpa * Fpa) + (Fpe * Fpe)) * 0.5f;
-	return stdMax(0.0f, stdMin(1.0f, average)); // clamp(), Materials.h:8-11
+	// clamp() = std::max(0, std::min(1, x)) (Materials.h:8-11) returns 1 for a NaN (cos_i a hair above 1 makes
+	// sqrtf(1 - cos^2) NaN).  nvcc fuses the select pattern into FMUL.SAT, which flushes NaN to 0: the GPU would
+	// refract along a NaN direction where the reference reflects.
+	if (average != average) return 1.0f;
+	return stdMax(0.0f, stdMin(1.0f, average));
 }
 
 // BSDF::sample.  r1, r2: the cosine-hemisphere uniforms; r3: glass reflect/refract draw.

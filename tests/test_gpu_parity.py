@@ -165,6 +165,40 @@ def test_cornell_golden_shading_bsdf_light(rtb):
         assert rel_err(L[k], cv[g]) <= 1e-5, k
 
 
+def test_glass_fresnel_nan_reflects_like_the_reference(rtb, oracle_mod):
+    """|cos_i| a hair above 1 (wo antiparallel to a rounded normal) makes sqrtf(1 - cos^2) NaN inside
+    ShadingHelper::fresnelDielectric; the reference's clamp = std::max(0, std::min(1, NaN)) is 1, i.e. total
+    reflection.  (nvcc fuses that select pattern into FMUL.SAT, which flushes NaN to 0: the GPU used to refract
+    along a NaN direction — the NaN rays of profiles/r01_scaling.md.)"""
+    rt = gpu_scene(rtb, "synthetic")
+    s = rt.scene
+    glass = [i for i, m in enumerate(s.materials) if m["type"] == abi.BSDF_GLASS]
+    assert glass
+    N = 256
+    rng = np.random.default_rng(3)
+    n = rng.normal(size=(N, 3))
+    n = (n / np.linalg.norm(n, axis=1, keepdims=True)).astype(np.float32)
+    a = np.where(np.abs(n[:, :1]) > 0.9, [[0, 1, 0]], [[1, 0, 0]]).astype(np.float32)
+    u = np.cross(n, a)
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    v = np.cross(n, u)
+    sd = np.zeros(N, abi.shading_dt)
+    sd["s_normal"], sd["g_normal"], sd["frame_u"], sd["frame_v"], sd["frame_w"] = n, n, u, v, n
+    sd["t"], sd["material"] = 1, glass[0]
+    wi = np.tile(np.array([[0, 1, 0]], np.float32), (N, 1))
+    uu = rng.random((N, 3), dtype=np.float32)
+    o = oracle_mod.Oracle(s)
+    for scale in (1.0000002, 1.0000005):
+        for sign in (1.0, -1.0):
+            sd["wo"] = (n * np.float32(sign * scale)).astype(np.float32)
+            want = o.eval_bsdf(sd, wi, uu)
+            assert np.all(want["s_pdf"] == 1.0) and np.isfinite(want["s_wi"]).all()       # the reference reflects
+            got = rt.eval_bsdf(sd, wi, uu)
+            assert np.isfinite(got["s_wi"]).all()
+            for k in ("s_wi", "s_f", "s_pdf"):
+                assert rel_err(got[k], want[k]) <= 1e-5, (k, scale, sign)
+
+
 def test_every_bsdf_class_golden(rtb):
     g = np.load(os.path.join(GOLDEN, "bsdf_vectors.npz"))
     s = flat_scene("cornell-box")
