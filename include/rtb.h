@@ -441,7 +441,8 @@ int rtb_shading_data(rtb_ctx* ctx, const rtb_ray* rays, const rtb_hit* hits, uin
 int rtb_eval_bsdf(rtb_ctx* ctx, const rtb_shading* sd, const float* wi, const float* u, uint64_t n,
                   float* eval, float* pdf, float* s_wi, float* s_f, float* s_pdf);
 /* Light::sample with uniforms u[2] (r1, r2) for light `light[i]` -> p_or_wi (n*3),
- * emitted (n*3), pdf (n); Light::evaluate(wi) -> eval (n*3).  STRICT sampling only.       */
+ * emitted (n*3), pdf (n); Light::evaluate(wi) -> eval (n*3).  The direction sample of an environment map
+ * follows rtb_params.sampling (uniform sphere, or the luminance CDF).                      */
 int rtb_eval_light(rtb_ctx* ctx, const int32_t* light, const float* wi, const float* u, uint64_t n,
                    float* p_or_wi, float* emitted, float* pdf, float* eval);
 /* The uniforms the render kernel draws: out[i] = u(pixel, sample, dim i), dims [0, n).    */

@@ -41,6 +41,7 @@ def lib():
         L.oracle_render.argtypes = [vp, vp, u32, u32, i32, vp, vp]
         L.oracle_render_counts.argtypes = [vp, vp, u32, u32, i32, vp, vp]
         L.oracle_render_adaptive.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp, vp]
+        L.oracle_render_adaptive_at.argtypes = [vp, vp, u32, u32, u32, u32, i32, vp, vp, vp]
         L.oracle_render_light.argtypes = [vp, vp, u32, u32, vp, vp]
         L.oracle_render_ir.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp]
         L.oracle_camera_derive.argtypes = [vp, vp]
@@ -50,6 +51,7 @@ def lib():
         L.oracle_shading_data.argtypes = [vp, vp, vp, u64, vp]
         L.oracle_eval_bsdf.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp]
         L.oracle_eval_light.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp]
+        L.oracle_eval_light_p.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]
         L.oracle_rng_draws.argtypes = [u32, u32, u32, u32, vp]
         L.oracle_tonemap.argtypes = [vp, u32, i32, f32, vp]
         L.oracle_gaussian_splat.argtypes = [i32, i32, f32, f32, vp, vp]
@@ -115,14 +117,15 @@ class Oracle:
                              _p(film), _p(st))
         return film, dict(samples=int(st[0]), closest_rays=int(st[1]), shadow_rays=int(st[2]))
 
-    def render_adaptive(self, init_samples=2, min_samples=1, max_samples=10240, threads=None, film=None):
+    def render_adaptive(self, init_samples=2, min_samples=1, max_samples=10240, threads=None, film=None, sample_base=0):
         """RayTracer::adaptiveRender -> (film_sum + one mean image, tile_samples, tile_variance)"""
         if film is None:
             film = np.zeros((self.height, self.width, 3), "<f4")
         ty, tx = (self.height + 31) // 32, (self.width + 31) // 32
         samples, var = np.zeros((ty, tx), np.uint32), np.zeros((ty, tx), np.float32)
-        self.L.oracle_render_adaptive(C.addressof(self.desc), C.addressof(self.params), int(init_samples), int(min_samples),
-                                      int(max_samples), int(threads or os.cpu_count() or 1), _p(film), _p(samples), _p(var))
+        self.L.oracle_render_adaptive_at(C.addressof(self.desc), C.addressof(self.params), int(sample_base), int(init_samples),
+                                         int(min_samples), int(max_samples), int(threads or os.cpu_count() or 1), _p(film),
+                                         _p(samples), _p(var))
         return film, samples, var
 
     def render_light(self, passes, pass_begin=0, film=None):
@@ -207,8 +210,8 @@ class Oracle:
         u = np.ascontiguousarray(u, "<f4").reshape(n, 2)
         out = dict(p_or_wi=np.zeros((n, 3), "<f4"), emitted=np.zeros((n, 3), "<f4"), pdf=np.zeros(n, "<f4"),
                    eval=np.zeros((n, 3), "<f4"))
-        rc = self.L.oracle_eval_light(C.addressof(self.desc), _p(light), _p(wi), _p(u), n, _p(out["p_or_wi"]),
-                                      _p(out["emitted"]), _p(out["pdf"]), _p(out["eval"]))
+        rc = self.L.oracle_eval_light_p(C.addressof(self.desc), C.addressof(self.params), _p(light), _p(wi), _p(u), n,
+                                        _p(out["p_or_wi"]), _p(out["emitted"]), _p(out["pdf"]), _p(out["eval"]))
         if rc != 0:
             raise ValueError("oracle_eval_light: bad light index")
         return out

@@ -507,6 +507,148 @@ static v3 triangle_sample(const rtb_scene_desc* s, uint32_t id, float r1, float 
 	return add(add(scl(Vp(q->v0), alpha), scl(Vp(q->v1), beta)), scl(Vp(q->v2), gamma));
 }
 
+/* ---------------- direction sample of a non-area light -----------------------------------
+ * STRICT: the reference, uniform sphere with pdf 1/4pi (Lights.h:99-100, 143-149).
+ * IMPORTANCE: NOT in the reference (EnvironmentMap::sample is uniform, there is no CDF anywhere);
+ * this restates the product's env-map luminance sampler so that the GPU's (wi, pdf, emitted) can be checked
+ * <= 1e-5 and its expectation against the reference's uniform sampler.  Tables: per texel cell (x, y) the
+ * weight max-luminance-of-the-four-bilinear-taps x sin(theta_centre) + 5 % of the mean (the density is positive
+ * wherever Texture::sample (Imaging.h:72-94) can return radiance); marginal CDF over rows, conditional CDF over
+ * the columns of each row, both stored as floats and made non-decreasing.  Sample: row by r1, column by r2,
+ * uniform inside the cell; (u, v) -> (phi, theta) inverts EnvironmentMap::evaluate's mapping (Lights.h:158-165).
+ * The tables are cached per texel pointer (test infrastructure: not re-entrant across scenes being freed). */
+typedef struct { const float* texels; int W, H; float* marginal; float* cond; } env_tables_t;
+static env_tables_t g_env[8];
+static int g_env_n = 0;
+static pthread_mutex_t g_env_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static double env_lum_at(const float* texels, int W, int H, int x, int y)
+{
+	const float* p = texels + ((size_t)(y % H) * W + (size_t)(x % W)) * 3;
+	return 0.2126 * p[0] + 0.7152 * p[1] + 0.0722 * p[2];
+}
+static double dmax(double a, double b) { return a > b ? a : b; }
+
+static const env_tables_t* env_tables(const rtb_scene_desc* s, int tex)
+{
+	const rtb_texture* T = &s->textures[tex];
+	const float* texels = s->texels + (size_t)T->offset * 3;
+	int W = T->width, H = T->height, x, y, i;
+	env_tables_t* e = NULL;
+	double *w, *rowSum, sum = 0.0, mean, floorW, total = 0.0, acc = 0.0;
+	pthread_mutex_lock(&g_env_lock);
+	for (i = 0; i < g_env_n; i++)
+		if (g_env[i].texels == texels && g_env[i].W == W && g_env[i].H == H) e = &g_env[i];
+	if (e)
+	{
+		pthread_mutex_unlock(&g_env_lock);
+		return e;
+	}
+	e = &g_env[g_env_n < 8 ? g_env_n++ : 7];
+	if (e->marginal) free(e->marginal), free(e->cond);
+	e->texels = texels, e->W = W, e->H = H;
+	e->marginal = (float*)calloc((size_t)H + 1, sizeof(float));
+	e->cond = (float*)calloc((size_t)H * (W + 1), sizeof(float));
+	w = (double*)malloc((size_t)W * H * sizeof(double));
+	rowSum = (double*)malloc((size_t)H * sizeof(double));
+	for (y = 0; y < H; y++)
+	{
+		double st = sin(((double)y + 0.5) / (double)H * 3.14159265358979323846);
+		for (x = 0; x < W; x++)
+		{
+			double l = dmax(dmax(env_lum_at(texels, W, H, x, y), env_lum_at(texels, W, H, x + 1, y)),
+			                dmax(env_lum_at(texels, W, H, x, y + 1), env_lum_at(texels, W, H, x + 1, y + 1)));
+			if (!(l > 0.0)) l = 0.0;
+			w[(size_t)y * W + x] = l * st;
+			sum += l * st;
+		}
+	}
+	mean = sum / ((double)W * H);
+	floorW = (mean > 0.0) ? 0.05 * mean : 1.0;
+	for (y = 0; y < H; y++)
+	{
+		double st = sin(((double)y + 0.5) / (double)H * 3.14159265358979323846), rs = 0.0;
+		for (x = 0; x < W; x++)
+		{
+			w[(size_t)y * W + x] += floorW * st;
+			rs += w[(size_t)y * W + x];
+		}
+		rowSum[y] = rs;
+		total += rs;
+	}
+	for (y = 0; y < H; y++)
+	{
+		double ca = 0.0;
+		float* cd = e->cond + (size_t)y * (W + 1);
+		e->marginal[y] = (float)(acc / total);
+		acc += rowSum[y];
+		for (x = 0; x < W; x++)
+		{
+			cd[x] = (float)(ca / rowSum[y]);
+			ca += w[(size_t)y * W + x];
+		}
+		cd[W] = 1.0f;
+	}
+	e->marginal[H] = 1.0f;
+	for (y = 1; y <= H; y++)
+		if (e->marginal[y] < e->marginal[y - 1]) e->marginal[y] = e->marginal[y - 1];
+	for (y = 0; y < H; y++)
+	{
+		float* cd = e->cond + (size_t)y * (W + 1);
+		for (x = 1; x <= W; x++)
+			if (cd[x] < cd[x - 1]) cd[x] = cd[x - 1];
+	}
+	free(w);
+	free(rowSum);
+	pthread_mutex_unlock(&g_env_lock);
+	return e;
+}
+
+static int cdf_find(const float* cdf, int n, float r)
+{
+	int lo = 0, hi = n;
+	while (hi - lo > 1)
+	{
+		int mid = (lo + hi) >> 1;
+		if (cdf[mid] <= r) lo = mid;
+		else hi = mid;
+	}
+	return lo;
+}
+
+/* returns 0 when the density is not positive */
+static int sample_non_area_light(const rtb_scene_desc* s, const rtb_params* P, const rtb_light* L, float r1, float r2, v3* wi, float* pdf,
+                                 v3* emitted)
+{
+	if (L->type == RTB_LIGHT_ENVMAP && P->sampling == RTB_SAMPLING_IMPORTANCE)
+	{
+		const env_tables_t* e = env_tables(s, L->tex);
+		int W = e->W, H = e->H;
+		int row = cdf_find(e->marginal, H, r1), col;
+		float m0 = e->marginal[row], m1 = e->marginal[row + 1];
+		float fr = (m1 > m0) ? (r1 - m0) / (m1 - m0) : 0.5f;
+		const float* cd = e->cond + (size_t)row * (W + 1);
+		float c0, c1, fc, v, u, theta, phi, st, pmfTexel;
+		col = cdf_find(cd, W, r2);
+		c0 = cd[col], c1 = cd[col + 1];
+		fc = (c1 > c0) ? (r2 - c0) / (c1 - c0) : 0.5f;
+		v = ((float)row + fr) / (float)H;
+		u = ((float)col + fc) / (float)W;
+		theta = v * (float)M_PI, phi = u * (2.0f * (float)M_PI);
+		st = sinf(theta);
+		*wi = V(cosf(phi) * st, cosf(theta), sinf(phi) * st);
+		pmfTexel = (m1 - m0) * (c1 - c0);
+		*pdf = pmfTexel * ((float)W * (float)H) / (2.0f * (float)M_PI * (float)M_PI * fmaxf(st, 1e-8f));
+		if (!(*pdf > 0.0f)) return 0;
+		*emitted = env_evaluate(s, L->tex, *wi);
+		return 1;
+	}
+	*wi = uniform_sample_sphere(r1, r2);
+	*pdf = 1.0f / (4.0f * M_PI);
+	*emitted = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, *wi) : Vp(L->emission);
+	return 1;
+}
+
 /* ---------------- counter-based RNG (replaces MTRandom) --------------------------------
  * Philox-4x32-10; counter = (pixel, sample, block, 0), key = (seed, 0x52544232).
  * Vertex at depth k: block 2k = [light pick, light r1, light r2, roulette],
@@ -563,10 +705,9 @@ static v3 compute_direct(const rtb_scene_desc* s, const rtb_params* P, const sha
 	}
 	else
 	{
-		v3 wi = uniform_sample_sphere(u[1], u[2]);
-		v3 emitted = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, wi) : Vp(L->emission);
-		float G = win_max(dot3(wi, sd->sN), 0.0f);
-		pdf = 1.0f / (4.0f * M_PI);
+		v3 wi, emitted;
+		int ok = sample_non_area_light(s, P, L, u[1], u[2], &wi, &pdf, &emitted);
+		float G = ok ? win_max(dot3(wi, sd->sN), 0.0f) : 0.0f;
 		if (G > 0)
 		{
 			tl->shadow++;
@@ -628,10 +769,9 @@ static v3 compute_direct_mis(const rtb_scene_desc* s, const rtb_params* P, const
 	}
 	else
 	{
-		v3 wi = uniform_sample_sphere(u[1], u[2]);
-		v3 emitted = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, wi) : Vp(L->emission);
-		float G = win_max(dot3(wi, sd->sN), 0.0f);
-		pdf = 1.0f / (4.0f * M_PI);
+		v3 wi, emitted;
+		int ok = sample_non_area_light(s, P, L, u[1], u[2], &wi, &pdf, &emitted);
+		float G = ok ? win_max(dot3(wi, sd->sN), 0.0f) : 0.0f;
 		if (G > 0)
 		{
 			tl->shadow++;
@@ -856,8 +996,18 @@ int oracle_render(const rtb_scene_desc* s, const rtb_params* P, uint32_t spp_beg
  * (:645-677): samples = max((int)(sqrt(weight) * MAX), MIN) fresh samples per pixel, mean splatted.
  * Sample indices: 0..init-1 steer, init.. are splatted (the reference's per-thread MTRandom simply
  * runs on).  film_sum += one mean image.  tile_samples / tile_variance may be NULL.             */
+/* sample_base: first sample index this call draws from.  The reference's MTRandom keeps advancing, so successive
+ * adaptiveRender() calls are independent; with a counter-based RNG every call needs its own index range
+ * (the product uses base = SPP-before-the-call x (init + max)). */
+int oracle_render_adaptive_at(const rtb_scene_desc* s, const rtb_params* P, uint32_t sample_base, uint32_t init_samples, uint32_t min_samples,
+                              uint32_t max_samples, int threads, float* film_sum, uint32_t* tile_samples, float* tile_variance);
 int oracle_render_adaptive(const rtb_scene_desc* s, const rtb_params* P, uint32_t init_samples, uint32_t min_samples,
                            uint32_t max_samples, int threads, float* film_sum, uint32_t* tile_samples, float* tile_variance)
+{
+	return oracle_render_adaptive_at(s, P, 0, init_samples, min_samples, max_samples, threads, film_sum, tile_samples, tile_variance);
+}
+int oracle_render_adaptive_at(const rtb_scene_desc* s, const rtb_params* P, uint32_t sample_base, uint32_t init_samples, uint32_t min_samples,
+                              uint32_t max_samples, int threads, float* film_sum, uint32_t* tile_samples, float* tile_variance)
 {
 	uint32_t W = (uint32_t)s->camera.width, H = (uint32_t)s->camera.height;
 	uint32_t tx = (W + 31u) / 32u, ty = (H + 31u) / 32u, nT = tx * ty, t;
@@ -868,7 +1018,7 @@ int oracle_render_adaptive(const rtb_scene_desc* s, const rtb_params* P, uint32_
 	uint32_t maxCount = 0;
 	float total = 0.0f;
 	uint64_t st[3];
-	oracle_render(s, P, 0, init_samples, threads, est, st);
+	oracle_render(s, P, sample_base, init_samples, threads, est, st);
 	for (t = 0; t < nT; t++)
 	{
 		uint32_t x0 = (t % tx) * 32u, y0 = (t / tx) * 32u, x1 = x0 + 32u < W ? x0 + 32u : W, y1 = y0 + 32u < H ? y0 + 32u : H, x, y;
@@ -903,7 +1053,7 @@ int oracle_render_adaptive(const rtb_scene_desc* s, const rtb_params* P, uint32_
 	/* fresh samples init .. init + count(tile) - 1 */
 	memset(est, 0, npx * 3 * sizeof(float));
 	g_tile_count = cnt, g_tile_tx = tx;
-	oracle_render(s, P, init_samples, maxCount, threads, est, st);
+	oracle_render(s, P, sample_base + init_samples, maxCount, threads, est, st);
 	g_tile_count = NULL;
 	for (i = 0; i < npx; i++)
 	{
@@ -1342,8 +1492,19 @@ int oracle_eval_bsdf(const rtb_scene_desc* s, const rtb_shading* sds, const floa
 	return 0;
 }
 
+/* Light::sample / evaluate; env-map direction samples follow P->sampling (NULL = STRICT, the reference) */
+int oracle_eval_light_p(const rtb_scene_desc* s, const rtb_params* P, const int32_t* light, const float* wi, const float* u, uint64_t n,
+                        float* p_or_wi, float* emitted, float* pdf, float* eval);
 int oracle_eval_light(const rtb_scene_desc* s, const int32_t* light, const float* wi, const float* u, uint64_t n,
                       float* p_or_wi, float* emitted, float* pdf, float* eval)
+{
+	rtb_params P;
+	memset(&P, 0, sizeof(P));
+	P.sampling = RTB_SAMPLING_STRICT;
+	return oracle_eval_light_p(s, &P, light, wi, u, n, p_or_wi, emitted, pdf, eval);
+}
+int oracle_eval_light_p(const rtb_scene_desc* s, const rtb_params* P, const int32_t* light, const float* wi, const float* u, uint64_t n,
+                        float* p_or_wi, float* emitted, float* pdf, float* eval)
 {
 	uint64_t i;
 	for (i = 0; i < n; i++)
@@ -1361,9 +1522,7 @@ int oracle_eval_light(const rtb_scene_desc* s, const int32_t* light, const float
 		}
 		else
 		{
-			p = uniform_sample_sphere(u[i * 2], u[i * 2 + 1]);
-			pd = 1.0f / (4.0f * M_PI);
-			e = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, p) : Vp(L->emission);
+			if (!sample_non_area_light(s, P, L, u[i * 2], u[i * 2 + 1], &p, &pd, &e)) pd = 0.0f, e = V(0, 0, 0);
 			ev = (L->type == RTB_LIGHT_ENVMAP) ? env_evaluate(s, L->tex, w) : Vp(L->emission);
 		}
 		if (p_or_wi) p_or_wi[i * 3] = p.x, p_or_wi[i * 3 + 1] = p.y, p_or_wi[i * 3 + 2] = p.z;

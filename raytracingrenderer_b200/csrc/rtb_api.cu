@@ -740,6 +740,14 @@ int rtb_set_params(rtb_ctx* ctx, const rtb_params* p)
 	if (p->scheduler != RTB_SCHED_WAVEFRONT && p->scheduler != RTB_SCHED_MEGAKERNEL) return fail(ctx, RTB_ERR_ARG, "bad scheduler %d", p->scheduler);
 	if (p->max_depth > 200) return fail(ctx, RTB_ERR_ARG, "max_depth too large");
 	if (p->max_depth < 0 || !(p->epsilon >= 0.0f)) return fail(ctx, RTB_ERR_ARG, "bad max_depth/epsilon");
+	// a zero-initialised rtb_params (instead of rtb_default_params) would end every path at depth 0 (rr_cap 0) and
+	// remove the cull slack that FAST / WIDE hit-ID parity rests on (cull_rel 0): wrong images with RTB_OK
+	if (!(p->rr_cap > 0.0f && p->rr_cap <= 1.0f)) return fail(ctx, RTB_ERR_ARG, "rr_cap %g outside (0, 1]: start from rtb_default_params()", p->rr_cap);
+	if (!(p->cull_rel >= 1e-7f && p->cull_rel <= 1e-2f))
+		return fail(ctx, RTB_ERR_ARG, "cull_rel %g outside [1e-7, 1e-2]: start from rtb_default_params()", p->cull_rel);
+	if (!(p->filter_radius >= 0.0f && p->filter_radius <= 16.0f) || !(fabsf(p->filter_alpha) <= 1e6f))
+		return fail(ctx, RTB_ERR_ARG, "bad Gaussian filter parameters (radius %g, alpha %g)", p->filter_radius, p->filter_alpha);
+	if (p->primary_reuse != 0 && p->primary_reuse != 1) return fail(ctx, RTB_ERR_ARG, "primary_reuse must be 0 or 1");
 	ctx->params = *p;
 	return RTB_OK;
 }
@@ -761,6 +769,9 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 	if (sc->n_tris && (!sc->materials || !sc->n_materials)) return fail(ctx, RTB_ERR_ARG, "materials missing");
 	if (!(sc->camera.width >= 1.0f) || !(sc->camera.height >= 1.0f) || sc->camera.width > 65536.0f || sc->camera.height > 65536.0f)
 		return fail(ctx, RTB_ERR_ARG, "bad film size %g x %g", sc->camera.width, sc->camera.height);
+	// the film kernels (resolve, import, tonemap, Gaussian, adaptive merge) index width*height*3 elements in 32 bits
+	if ((uint64_t)sc->camera.width * (uint64_t)sc->camera.height * 3ull >= (1ull << 32))
+		return fail(ctx, RTB_ERR_ARG, "film %g x %g too large: width*height*3 must stay below 2^32", sc->camera.width, sc->camera.height);
 	for (uint32_t i = 0; i < sc->n_tris; i++)
 		if (sc->tri_isect[i].material >= sc->n_materials) return fail(ctx, RTB_ERR_ARG, "triangle %u: material %u out of range", i, sc->tri_isect[i].material);
 	for (uint32_t i = 0; i < sc->n_materials; i++)
@@ -1016,6 +1027,12 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 	if (P.partition != RTB_PART_NONE && P.part_world > 1)
 		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: the tile sample counts come from the whole image; use one device per image");
 	if (int rc = bind(ctx)) return rc;
+	// Every call draws from its own range of sample indices, like the reference's ever-advancing MTRandom makes
+	// successive adaptiveRender() calls independent: call number k (= Film::SPP before the call, one per call)
+	// uses [k * (init + max), (k + 1) * (init + max)).
+	const uint64_t base64 = (uint64_t)ctx->spp * ((uint64_t)init_samples + max_samples);
+	if (base64 + init_samples + max_samples > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: sample index overflow (clear the film)");
+	const uint32_t sampleBase = (uint32_t)base64;
 	const uint32_t W = ctx->width, H = ctx->height, t32x = (W + 31) / 32, t32y = (H + 31) / 32, nT = t32x * t32y;
 	const size_t accBytes = (size_t)W * H * 3 * sizeof(long long);
 	if (!ctx->accumScratch)
@@ -1043,7 +1060,7 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 	CK(cudaMemcpyAsync(ctx->adaptJobBase, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
 	AdaptivePlan plan = {base[nT], nT};
 	ctx->accum = ctx->accumScratch;
-	int rc = renderWavefront(ctx, 0, init_samples, &plan);
+	int rc = renderWavefront(ctx, sampleBase, init_samples, &plan);
 	ctx->accum = film;
 	if (rc) return rc;
 	k_tile_variance<<<nT, 256, 0, ctx->stream>>>(ctx->accumScratch, W, H, init_samples, ctx->adaptVariance);
@@ -1070,7 +1087,7 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 	CK(cudaMemcpyAsync(ctx->adaptSamples, samples.data(), nT * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 	plan.totalJobs = base[nT];
 	ctx->accum = ctx->accumScratch;
-	rc = renderWavefront(ctx, init_samples, max_samples, &plan);
+	rc = renderWavefront(ctx, sampleBase + init_samples, max_samples, &plan);
 	ctx->accum = film;
 	if (rc) return rc;
 	k_adaptive_merge<<<(W * H + 255) / 256, 256, 0, ctx->stream>>>(ctx->accumScratch, ctx->accum, W, H, ctx->adaptSamples);
@@ -1340,7 +1357,7 @@ int rtb_eval_light(rtb_ctx* ctx, const int32_t* light, const float* wi, const fl
 	CK(sc.out(emitted, n * 3, &dE));
 	CK(sc.out(pdf, n, &dPd));
 	CK(sc.out(eval, n * 3, &dEv));
-	k_eval_light<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->S, dL, dWi, dU, n, dP, dE, dPd, dEv);
+	k_eval_light<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->S, ctx->params, dL, dWi, dU, n, dP, dE, dPd, dEv);
 	ctx->launches++;
 	CK(cudaGetLastError());
 	if (p_or_wi) CK(cudaMemcpyAsync(p_or_wi, dP, n * 12, cudaMemcpyDeviceToHost, ctx->stream));

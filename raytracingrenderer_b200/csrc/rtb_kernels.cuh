@@ -58,40 +58,18 @@ RTB_DEV void filmAdd(long long* accum, uint32_t pixel, V3 c)
 }
 
 // ---------------------------------------------------------------------------------------
-// RayTracer::computeDirect (RTBase/Renderer.h:423-473) with Scene::sampleLight (Scene.h:131-140),
-// split at the scene->visible() call so that the wavefront schedule can defer the shadow ray:
-// directSample returns false when no shadow ray is needed (the contribution is zero), else the
-// segment p1 -> p2 to test and the contribution if it is unoccluded.  u = (light pick, r1, r2).
-// (Queueing the env-map lookups of miss lanes and NEE lanes for one shared call site was measured
-// 4 % SLOWER: the longer live ranges spill at 80 registers.)
+// Direction sample of a non-area light (BackgroundColour / EnvironmentMap).
+//   STRICT     = the reference: uniform sphere, pdf 1/4pi (Lights.h:99-100, 143-149).
+//   IMPORTANCE = env-map luminance CDF (tables: rtb_accel.hpp buildEnvTables): row from the marginal
+//                CDF with r1, column from that row's conditional CDF with r2, uniform inside the texel
+//                cell; pdf = cell pmf x W H / (2 pi^2 sin theta).  Positive wherever the map can be
+//                non-zero, so the estimator's expectation is the reference's.
+// Shared by computeDirect and computeDirectMIS (both schedules) and rtb_eval_light.  Returns false when the
+// density is not positive (nothing to add).
 // ---------------------------------------------------------------------------------------
-RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& sd, const rtb_material& m, float uPick,
-                          float r1, float r2, V3& p1, V3& p2, V3& contrib)
+RTB_DEV bool sampleNonAreaLight(const DevScene& S, const rtb_params& P, const rtb_light& L, float r1, float r2, V3& wi, float& pdf,
+                                V3& emitted)
 {
-	if (m.flags & RTB_MAT_SPECULAR) return false;
-	if (S.n_lights == 0) return false;
-	float nl = (float)S.n_lights;
-	float pmf = 1.0f / nl;
-	int li = (int)(nl * uPick);
-	if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
-	rtb_light L = S.lights[li];
-	if (L.type == RTB_LIGHT_AREA)
-	{
-		V3 p = trianglePoint(S, L.triangle, r1, r2);
-		float pdf = 1.0f / L.area;
-		V3 wi = p - sd.x;
-		float l = lengthSq(wi);
-		wi = normalize(wi);
-		V3 nL = triangleGNormal(S, L.triangle);
-		float G = (selMax(dot(wi, sd.sN), 0.0f) * selMax(-dot(wi, nL), 0.0f)) / l;
-		if (!(G > 0.0f)) return false;
-		contrib = divFast((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G, pmf * pdf);
-		p1 = sd.x;
-		p2 = p;
-		return true;
-	}
-	V3 wi, emitted;
-	float pdf;
 	if (L.type == RTB_LIGHT_ENVMAP && P.sampling == RTB_SAMPLING_IMPORTANCE && S.env_marginal != nullptr)
 	{
 		int W = S.env_w, H = S.env_h;
@@ -127,13 +105,50 @@ RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& 
 		pdf = pmfTexel * ((float)W * (float)H) / (2.0f * RTB_PI_F * RTB_PI_F * fmaxf(st, 1e-8f));
 		if (!(pdf > 0.0f)) return false;
 		emitted = envLookup(S, L.tex, wi);
+		return true;
 	}
-	else
+	wi = uniformSampleSphere(r1, r2);
+	pdf = 0.0795774683356285095f; // 1 / (4 pi)
+	emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
+	return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// RayTracer::computeDirect (RTBase/Renderer.h:423-473) with Scene::sampleLight (Scene.h:131-140),
+// split at the scene->visible() call so that the wavefront schedule can defer the shadow ray:
+// directSample returns false when no shadow ray is needed (the contribution is zero), else the
+// segment p1 -> p2 to test and the contribution if it is unoccluded.  u = (light pick, r1, r2).
+// (Queueing the env-map lookups of miss lanes and NEE lanes for one shared call site was measured
+// 4 % SLOWER: the longer live ranges spill at 80 registers.)
+// ---------------------------------------------------------------------------------------
+RTB_DEV bool directSample(const DevScene& S, const rtb_params& P, const ShadeD& sd, const rtb_material& m, float uPick,
+                          float r1, float r2, V3& p1, V3& p2, V3& contrib)
+{
+	if (m.flags & RTB_MAT_SPECULAR) return false;
+	if (S.n_lights == 0) return false;
+	float nl = (float)S.n_lights;
+	float pmf = 1.0f / nl;
+	int li = (int)(nl * uPick);
+	if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+	rtb_light L = S.lights[li];
+	if (L.type == RTB_LIGHT_AREA)
 	{
-		wi = uniformSampleSphere(r1, r2);
-		pdf = 0.0795774683356285095f; // 1 / (4 pi)
-		emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
+		V3 p = trianglePoint(S, L.triangle, r1, r2);
+		float pdf = 1.0f / L.area;
+		V3 wi = p - sd.x;
+		float l = lengthSq(wi);
+		wi = normalize(wi);
+		V3 nL = triangleGNormal(S, L.triangle);
+		float G = (selMax(dot(wi, sd.sN), 0.0f) * selMax(-dot(wi, nL), 0.0f)) / l;
+		if (!(G > 0.0f)) return false;
+		contrib = divFast((bsdfEvaluate(S, m, sd, wi) * mk(L.emission)) * G, pmf * pdf);
+		p1 = sd.x;
+		p2 = p;
+		return true;
 	}
+	V3 wi, emitted;
+	float pdf;
+	if (!sampleNonAreaLight(S, P, L, r1, r2, wi, pdf, emitted)) return false;
 	float G = selMax(dot(wi, sd.sN), 0.0f);
 	if (!(G > 0.0f)) return false;
 	contrib = divFast((bsdfEvaluate(S, m, sd, wi) * emitted) * G, pmf * pdf);
@@ -198,10 +213,9 @@ RTB_DEV V3 computeDirectMIS(const DevScene& S, const rtb_params& P, const ShadeD
 	}
 	else
 	{
-		V3 wi = uniformSampleSphere(r1, r2);
-		pdf = (float)(1.0 / (4.0 * RTB_PI_D));
-		V3 emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
-		float G = selMax(dot(wi, sd.sN), 0.0f);
+		V3 wi, emitted;
+		bool ok = sampleNonAreaLight(S, P, L, r1, r2, wi, pdf, emitted);
+		float G = ok ? selMax(dot(wi, sd.sN), 0.0f) : 0.0f;
 		if (G > 0.0f)
 		{
 			tl.shadow++;
@@ -275,11 +289,11 @@ RTB_DEV bool misLightSample(const DevScene& S, const rtb_params& P, const ShadeD
 		return true;
 	}
 	nonArea = true;
-	V3 wi = uniformSampleSphere(r1, r2);
-	float pdf = (float)(1.0 / (4.0 * RTB_PI_D));
+	V3 wi, emitted;
+	float pdf;
+	bool ok = sampleNonAreaLight(S, P, L, r1, r2, wi, pdf, emitted);
 	pdfAreaPmf = pdf * pmf;
-	V3 emitted = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, wi) : mk(L.emission);
-	float G = selMax(dot(wi, sd.sN), 0.0f);
+	float G = ok ? selMax(dot(wi, sd.sN), 0.0f) : 0.0f;
 	if (G > 0.0f)
 	{
 		contrib = ((bsdfEvaluate(S, m, sd, wi) * emitted) * G) / (pmf * pdf);
@@ -831,8 +845,9 @@ __global__ void __launch_bounds__(128) k_eval_bsdf(const __grid_constant__ DevSc
 	}
 }
 
-// Light::sample / Light::evaluate (RTBase/Lights.h:35-48, 89-100, 143-166), STRICT sampling.
-__global__ void __launch_bounds__(128) k_eval_light(const __grid_constant__ DevScene S,
+// Light::sample / Light::evaluate (RTBase/Lights.h:35-48, 89-100, 143-166); the direction sample of an
+// environment map follows rtb_params.sampling (sampleNonAreaLight).
+__global__ void __launch_bounds__(128) k_eval_light(const __grid_constant__ DevScene S, const __grid_constant__ rtb_params P,
                                                     const int32_t* __restrict__ light, const float* __restrict__ wi,
                                                     const float* __restrict__ u, uint64_t n, float* pOrWi,
                                                     float* emitted, float* pdf, float* eval)
@@ -854,9 +869,7 @@ __global__ void __launch_bounds__(128) k_eval_light(const __grid_constant__ DevS
 	}
 	else
 	{
-		p = uniformSampleSphere(u[i * 2], u[i * 2 + 1]);
-		pd = (float)(1.0 / (4.0 * RTB_PI_D));
-		e = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, p) : mk(L.emission);
+		if (!sampleNonAreaLight(S, P, L, u[i * 2], u[i * 2 + 1], p, pd, e)) pd = 0.0f, e = mk(0.0f, 0.0f, 0.0f);
 		ev = (L.type == RTB_LIGHT_ENVMAP) ? envLookup(S, L.tex, w) : mk(L.emission);
 	}
 	if (pOrWi) pOrWi[i * 3] = p.x, pOrWi[i * 3 + 1] = p.y, pOrWi[i * 3 + 2] = p.z;

@@ -469,6 +469,7 @@ inline bool decodeHDR(const std::vector<unsigned char>& file, int& w, int& h, st
 			pos += (size_t)w * 4;
 			continue;
 		}
+		if (pos + 4 > file.size()) return false; // truncated before a scanline header
 		if ((((int)file[pos + 2] << 8) | file[pos + 3]) != w) return false;
 		pos += 4;
 		for (int c = 0; c < 4; c++)
@@ -1598,6 +1599,12 @@ inline void loadInstance(std::string sceneName, std::vector<Triangle>& meshTrian
 		int offset = (int)indices.size(); // sic (:221): the offset counts INDICES, as in the reference
 		for (unsigned int idx : meshes[i].indices) indices.push_back(offset + idx);
 	}
+	// a damaged file (or the index-counting offset above on a multi-mesh model) can point past the vertex array:
+	// the reference reads out of bounds there; this loader reports it
+	for (size_t i = 0; i < indices.size(); i++)
+		if (indices[i] >= vertices.size())
+			throw std::runtime_error("mesh index " + std::to_string(i) + " = " + std::to_string(indices[i]) + " is out of range (" +
+			                         std::to_string(vertices.size()) + " vertices)");
 	for (size_t i = 0; i + 2 < indices.size(); i += 3)
 	{
 		Triangle t;

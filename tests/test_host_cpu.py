@@ -340,9 +340,33 @@ def test_damaged_scene_files_are_errors_with_a_reason(host, tmp_path):
     with pytest.raises(RuntimeError) as e:
         host.load_scene(str(d))
     assert "truncated" in str(e.value)
+    # a vertex index past the vertex array (the file ends with the index list): an error naming the index,
+    # where the reference reads out of bounds
+    open(d / gem, "wb").write(data[:-4] + (9999).to_bytes(4, "little"))
+    with pytest.raises(RuntimeError) as e:
+        host.load_scene(str(d))
+    assert "out of range" in str(e.value) and "9999" in str(e.value)
     os.remove(d / gem)
     with pytest.raises(RuntimeError):
         host.load_scene(str(d))
+
+
+def test_truncated_rle_hdr_is_rejected_without_reading_past_the_end(host, tmp_path):
+    """A run-length .hdr cut 1-3 bytes into a scanline header must fail cleanly (it used to read file[pos + 3])."""
+    rng = np.random.default_rng(5)
+    rgbe = rng.integers(100, 140, (6, 40, 4)).astype(np.uint8)
+    f = str(tmp_path / "full.hdr")
+    _write_hdr(f, rgbe, True, b"#?RADIANCE")
+    assert host.decode_hdr(f).shape == (6, 40, 3)
+    data = open(f, "rb").read()
+    # find the start of the last scanline header (2, 2, hi, lo) and cut right after 1..3 of its bytes
+    last = data.rfind(bytes([2, 2, 0, 40]))
+    assert last > 0
+    for keep in (1, 2, 3):
+        g = str(tmp_path / ("cut%d.hdr" % keep))
+        open(g, "wb").write(data[: last + keep])
+        with pytest.raises((RuntimeError, ValueError)):
+            host.decode_hdr(g)
 
 
 def test_image_writers_round_trip(host, tmp_path):

@@ -390,3 +390,56 @@ def test_aovs_equal_the_reference(oracle_mod, name):
         o = oracle_mod.Oracle(flat_scene(name), integrator=integ)
         img, _ = o.render(1)
         assert np.allclose(img, rs.aov(kind), rtol=1e-5, atol=1e-6), kind
+
+
+# ---------------------------------------------------------------- direct() and the env-CDF sampler
+def test_direct_integrator_against_the_reference(oracle_mod):
+    """RTB_INT_DIRECT = RayTracer::direct (Renderer.h:393-407) vs the reference's own direct() at one sample per
+    pixel (cornell-box): the block noise sigma_1 is measured from two oracle runs with disjoint sample indices;
+    RMSE(oracle N spp vs reference 1 spp) must sit at sigma_1 sqrt(1 + 1/N) (+-20 %), the mean within 2 %."""
+    rs = ref_scene("cornell-box")
+    ref1 = rs.aov("direct")
+    o = oracle_mod.Oracle(flat_scene("cornell-box"), integrator=abi.INT_DIRECT)
+    a, _ = o.render(1, 100)
+    b, _ = o.render(1, 200)
+    N = 4
+    m, st = o.render(N, 0)
+    assert st["closest_rays"] == st["samples"]
+    ba, bb, bm, br = (raysets.block_mean(x) for x in (a, b, m / N, ref1))
+    sigma1 = np.sqrt(np.mean((ba - bb) ** 2) / 2)
+    rmse = np.sqrt(np.mean((bm - br) ** 2))
+    expect = sigma1 * np.sqrt(1 + 1 / N)
+    assert 0.8 * expect < rmse < 1.2 * expect, (rmse, expect)
+    assert np.all(np.abs((m / N).mean(axis=(0, 1)) / ref1.mean(axis=(0, 1)) - 1) < 0.02)
+
+
+def test_env_importance_sampler_is_a_density_and_keeps_the_expectation(oracle_mod):
+    """The env-map luminance-CDF sampler (not in the reference: EnvironmentMap::sample is uniform,
+    Lights.h:143-149) restated in the oracle: (1) it is a normalised density: E[1/pdf] over its own samples is
+    the sphere's 4 pi; (2) E[Le/pdf] equals the uniform sampler's (both estimate the integral of the map);
+    (3) rendered with it, the image converges to the strict sampler's."""
+    s = synthetic_scene(width=64, height=48)
+    env = np.flatnonzero(s.lights["type"] == abi.LIGHT_ENVMAP)
+    assert len(env) == 1
+    n = 400000
+    rng = np.random.default_rng(2)
+    u = rng.random((n, 2), dtype=np.float32)
+    li = np.full(n, env[0], np.int32)
+    wi = np.zeros((n, 3), np.float32)
+    wi[:, 1] = 1
+    imp = oracle_mod.Oracle(s, sampling=abi.SAMPLING_IMPORTANCE).eval_light(li, wi, u)
+    uni = oracle_mod.Oracle(s).eval_light(li, wi, u)
+    assert np.all(imp["pdf"] > 0)
+    inv = 1.0 / imp["pdf"].astype(np.float64)
+    assert abs(inv.mean() / (4 * np.pi) - 1) < 5 * inv.std() / np.sqrt(n) / (4 * np.pi)
+    ei = (imp["emitted"].astype(np.float64) / imp["pdf"][:, None]).mean(axis=0)
+    eu = (uni["emitted"].astype(np.float64) / uni["pdf"][:, None]).mean(axis=0)
+    assert np.all(np.abs(ei / eu - 1) < 0.02), (ei, eu)
+    lum = np.array([0.2126, 0.7152, 0.0722])                 # the sampler follows luminance: compare that
+    vi = ((imp["emitted"].astype(np.float64) @ lum) / imp["pdf"]).std()
+    vu = ((uni["emitted"].astype(np.float64) @ lum) / uni["pdf"]).std()
+    assert vi < vu, (vi, vu)
+    for integ in (abi.INT_PATH, abi.INT_PATH_MIS):
+        a, _ = oracle_mod.Oracle(s, integrator=integ).render(256)
+        b, _ = oracle_mod.Oracle(s, integrator=integ, sampling=abi.SAMPLING_IMPORTANCE).render(256)
+        assert np.all(np.abs(b.mean(axis=(0, 1)) / a.mean(axis=(0, 1)) - 1) < 0.02), integ
