@@ -11,11 +11,14 @@
  * exceptions cross; every function returns an rtb_status (0 = OK, <0 = error) unless noted
  * and the message of the last error is available from rtb_last_error().
  *
- * A context owns ONE device (one process per GPU is the deployment model; the film
- * reduction across GPUs is done by the caller with NCCL on rtb_accum_device_ptr(): an exact
- * integer SUM).  RayTracer::render's alternatives that the reference ships commented out
- * (adaptiveRender, lightTracer, instantRadiosity, computeDirectMIS) are here too.
- * A context is not thread-safe.
+ * A context drives ONE device (rtb_create) or a GROUP of up to 8 devices of one box
+ * (rtb_create_multi): like RayTracer::init sizes the reference to every processor of the machine
+ * (Renderer.h:52-55) and pathTracerTileBased fans out over them (:836-853), a group renders every
+ * call on all its GPUs and sums their films at read-out — inside the library, exactly (64-bit
+ * fixed-point sums), over NVLink peer memory or NCCL.  With one process per GPU instead
+ * (rtb_params.partition), the caller reduces rtb_accum_device_ptr() itself (an int64 SUM).
+ * RayTracer::render's alternatives that the reference ships commented out (adaptiveRender,
+ * lightTracer, instantRadiosity, computeDirectMIS) are here too.  A context is not thread-safe.
  */
 #ifndef RTB_H_
 #define RTB_H_
@@ -342,6 +345,26 @@ int rtb_abi_version(void);
 /* Creates a context on CUDA device `device`.  Fails with RTB_ERR_NODEV when there is no
  * such device: there is NO CPU fallback.                                                */
 int rtb_create(int device, rtb_ctx** out);
+/* Number of CUDA devices this process can see (0 = none: there is no renderer without one). */
+int rtb_device_count(void);
+/* A device GROUP: one context that renders on n GPUs of this box (RayTracer::init's numProcs =
+ * every processor, Renderer.h:52-55).  devices = n distinct CUDA device indices, or NULL for the
+ * first n visible devices (n <= 0: all of them).  The scene is replicated; every rtb_render /
+ * rtb_render_light / rtb_render_ir call is split over the members (sample slices — tile slices
+ * when a call has fewer samples than devices or rtb_params.partition asks for tiles — resp.
+ * contiguous pass ranges), each member driven by its own host thread for the duration of the call;
+ * a partition set in rtb_params (one process per node, say) is refined, not replaced.  The film
+ * is read out on devices[0]: rtb_read_film / rtb_tonemap / rtb_*_device_ptr first add the other
+ * members' fixed-point sums to devices[0]'s — one kernel over NVLink peer memory that also converts
+ * to the float film, or ncclReduce (libnccl.so.2, loaded on demand) when a member is not
+ * peer-accessible; RTB_GROUP_REDUCE=nccl|staged forces a path.  Integer sums: the group's film equals
+ * the single-GPU film bit for bit.  rtb_render_adaptive and the parity entry points run on
+ * devices[0] alone.  n = 1 is a plain context.                                             */
+int rtb_create_multi(const int* devices, int n, rtb_ctx** out);
+/* Members of ctx (1 for rtb_create).  rtb_group_info: devices[n], p2p[n] (1 = devices[0] reads that
+ * member's memory directly) and how many read-outs went over peer memory / NCCL; any may be NULL. */
+int rtb_group_size(const rtb_ctx* ctx);
+int rtb_group_info(const rtb_ctx* ctx, int* devices, int* p2p, uint64_t* gathers_p2p, uint64_t* gathers_nccl);
 void rtb_destroy(rtb_ctx* ctx);
 /* Message of the last failing call on ctx (ctx may be NULL: creation errors).  Never NULL. */
 const char* rtb_last_error(const rtb_ctx* ctx);

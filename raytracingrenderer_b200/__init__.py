@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")
 
 # every symbol include/rtb.h declares (tests check the built library exports all of them)
 ABI_SYMBOLS = [
-    "rtb_abi_version", "rtb_create", "rtb_destroy", "rtb_last_error", "rtb_set_stream", "rtb_synchronize",
+    "rtb_abi_version", "rtb_create", "rtb_create_multi", "rtb_device_count", "rtb_group_size", "rtb_group_info", "rtb_destroy", "rtb_last_error", "rtb_set_stream", "rtb_synchronize",
     "rtb_default_params", "rtb_set_params", "rtb_get_params", "rtb_upload_scene", "rtb_update_camera",
     "rtb_clear", "rtb_render", "rtb_render_adaptive", "rtb_render_light", "rtb_render_ir", "rtb_read_film", "rtb_write_film", "rtb_film_device_ptr", "rtb_accum_device_ptr", "rtb_set_spp", "rtb_tonemap", "rtb_get_stats",
     "rtb_film_size", "rtb_primary_hits", "rtb_trace", "rtb_visible", "rtb_shading_data", "rtb_eval_bsdf",
@@ -50,6 +50,10 @@ def lib():
         vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
         L.rtb_abi_version.restype = i32
         L.rtb_create.argtypes = [i32, C.POINTER(vp)]
+        L.rtb_create_multi.argtypes = [vp, i32, C.POINTER(vp)]
+        L.rtb_device_count.restype = i32
+        L.rtb_group_size.argtypes = [vp]
+        L.rtb_group_info.argtypes = [vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]
         L.rtb_destroy.argtypes = [vp]
         L.rtb_destroy.restype = None
         L.rtb_last_error.argtypes = [vp]
@@ -107,13 +111,26 @@ class RayTracer:
     """
 
     def __init__(self, device=0):
+        """device: one CUDA device index, or a list of them / "all" for a device GROUP
+        (rtb_create_multi: the film of every render call is spread over the GPUs and summed at read-out)."""
         self._L = lib()
         h = C.c_void_p()
-        rc = self._L.rtb_create(int(device), C.byref(h))
-        if rc != 0:
-            raise RtbError(rc, self._L.rtb_last_error(None).decode())
-        self._h = h
-        self.device = int(device)
+        if device == "all" or isinstance(device, (list, tuple)):
+            if device == "all":
+                rc = self._L.rtb_create_multi(None, 0, C.byref(h))
+            else:
+                arr = (C.c_int * len(device))(*[int(d) for d in device])
+                rc = self._L.rtb_create_multi(arr, len(device), C.byref(h))
+            if rc != 0:
+                raise RtbError(rc, self._L.rtb_last_error(None).decode())
+            self._h = h
+            self.device = self.group_info()["devices"][0]
+        else:
+            rc = self._L.rtb_create(int(device), C.byref(h))
+            if rc != 0:
+                raise RtbError(rc, self._L.rtb_last_error(None).decode())
+            self._h = h
+            self.device = int(device)
         self.scene = None
         self.width = self.height = 0
 
@@ -132,6 +149,14 @@ class RayTracer:
             self.close()
         except Exception:
             pass
+
+    def group_info(self):
+        """{"devices": [...], "p2p": [...], "gathers_p2p": n, "gathers_nccl": n} of this context's device group."""
+        n = self._L.rtb_group_size(self._h)
+        dev, p2p = (C.c_int * n)(), (C.c_int * n)()
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._L.rtb_group_info(self._h, dev, p2p, C.byref(a), C.byref(b)))
+        return dict(devices=list(dev), p2p=list(p2p), gathers_p2p=a.value, gathers_nccl=b.value)
 
     def set_stream(self, cuda_stream_handle):
         self._ck(self._L.rtb_set_stream(self._h, C.c_void_p(int(cuda_stream_handle))))

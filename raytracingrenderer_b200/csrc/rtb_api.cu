@@ -7,8 +7,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <dlfcn.h>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 // run __VA_ARGS__ with `TR` bound to the compile-time value of a run-time rtb_traversal
@@ -110,6 +112,19 @@ struct rtb_ctx
 	uint32_t vplPaths = 0;
 	cudaEvent_t evFork = nullptr;
 	uint64_t wfIterations = 0, wfHostSyncs = 0;
+	// ---- device group (rtb_create_multi): this context is device 0 of the group and owns the film that is read
+	// out; `peers` are complete single-device contexts on the other GPUs (same scene, their own slot pools and
+	// accumulators).  See the "device groups" section below.
+	std::vector<rtb_ctx*> peers;
+	std::vector<char> peerDirect;   // peers[k]'s accumulators are readable from this device (P2P over NVLink)
+	rtb_params userParams;          // group: what the caller set (members get a composed partition per render call)
+	cudaEvent_t evGroup = nullptr;  // member: "my work so far is done" for the group's read-out
+	bool accumDirty = false;        // member: accumulators changed since the last gather
+	int reduceMode = 0;             // 0 = P2P kernel where peer access exists, NCCL otherwise; 1 = force NCCL; 2 = staged copies
+	void* ncclLib = nullptr;
+	void* ncclComms[8] = {};
+	long long* gatherScratch = nullptr;
+	uint64_t gathers = 0, gatherP2P = 0, gatherNccl = 0;
 };
 
 namespace
@@ -634,135 +649,227 @@ static int filteredFilm(rtb_ctx* ctx, const float** src)
 	return RTB_OK;
 }
 
-extern "C" {
 
-int rtb_abi_version(void) { return RTB_ABI_VERSION; }
+// ======================================================================================
+// Device groups (rtb_create_multi).  RayTracer::init sizes the renderer to every processor of the machine
+// (RTBase/Renderer.h:52-55) and pathTracerTileBased fans the tiles out over them (:836-853); here the
+// "processors" are the GPUs of one box.  A group context is an ordinary context on its first device plus one
+// complete single-device context per further GPU (scene replicated, own slot pool, own fixed-point film).
+//   rtb_render      every member renders its slice of the call's samples (spp slice: perfect balance; tile slice
+//                   when the call has fewer samples than devices or the caller asked for tiles), each driven by
+//                   its own host thread, like the reference's per-call worker threads.
+//   film read-out   the members' accumulators are SUMMED into device 0's: an exact int64 sum, so the film is
+//                   bit-identical to a single-GPU render.  Where device 0 can read a peer's memory (NVLink P2P)
+//                   ONE kernel on device 0 does reduce + int64 -> float conversion in a single pass over peer
+//                   memory (k_film_gather); otherwise ncclReduce over a communicator created with
+//                   ncclCommInitAll (libnccl.so.2 is loaded on demand); last resort: staged peer copies.
+// Nothing else is exchanged between the GPUs.
+// ======================================================================================
+static size_t groupSize(const rtb_ctx* g) { return 1 + g->peers.size(); }
 
-void rtb_default_params(rtb_params* p)
+template <class F>
+static int forEachMember(rtb_ctx* g, F fn)
 {
-	if (!p) return;
-	memset(p, 0, sizeof(*p));
-	p->max_depth = 4;     // MAX_DEPTH, RTBase/Renderer.h:20
-	p->epsilon = 1e-4f;   // EPSILON, RTBase/Geometry.h:60
-	p->rr_cap = 0.9f;     // RTBase/Renderer.h:353
-	p->integrator = RTB_INT_PATH;
-	p->sampling = RTB_SAMPLING_STRICT;
-	p->traversal = RTB_TRAV_FAST; // profiles/r01_wide_tree.txt: the 4-wide tree measured ~5 % slower
-	p->filter = RTB_FILTER_BOX; // RTBase/Renderer.h:50
-	p->filter_radius = 2.0f;    // RTBase/Renderer.h:51
-	p->filter_alpha = 0.1f;
-	p->seed = 1;                // MTRandom(seed = 1), RTBase/Sampling.h:18
-	p->partition = RTB_PART_NONE;
-	p->part_rank = 0;
-	p->part_world = 1;
-	p->cull_rel = 1e-5f;
-	p->scheduler = RTB_SCHED_WAVEFRONT;
-	p->primary_reuse = 1;
+	size_t n = groupSize(g);
+	if (n == 1) return fn(g, 0);
+	std::vector<int> rc(n, 0);
+	std::vector<std::thread> th;
+	th.reserve(n - 1);
+	for (size_t d = 1; d < n; d++) th.emplace_back([&rc, &fn, g, d]() { rc[d] = fn(g->peers[d - 1], (int)d); });
+	rc[0] = fn(g, 0);
+	for (std::thread& t : th) t.join();
+	for (size_t d = 1; d < n; d++)
+		if (rc[d])
+		{
+			g->error = "device " + std::to_string(g->peers[d - 1]->device) + ": " + g->peers[d - 1]->error;
+			return rc[d];
+		}
+	return rc[0];
 }
 
-int rtb_create(int device, rtb_ctx** out)
+// The partition member d of the group renders: the caller's own partition (rank r of w processes, e.g. one
+// process per node) refined n-fold.  s = r (mod w) and (s - r) / w = d (mod n)  <=>  s = r + w d (mod w n).
+static rtb_params composedParams(const rtb_ctx* g, int d, uint32_t units)
 {
-	rtb_ctx* ctx = nullptr;
-	if (!out) return fail(nullptr, RTB_ERR_ARG, "rtb_create: out is NULL");
-	*out = nullptr;
-	int n = 0;
-	cudaError_t e = cudaGetDeviceCount(&n);
-	if (e != cudaSuccess || n == 0)
-		return fail(nullptr, RTB_ERR_NODEV, "no CUDA device (%s); librtb200 has no CPU fallback",
-		            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-	if (device < 0 || device >= n) return fail(nullptr, RTB_ERR_NODEV, "device %d out of range [0,%d)", device, n);
-	ctx = new (std::nothrow) rtb_ctx();
-	if (!ctx) return fail(nullptr, RTB_ERR_OOM, "out of host memory");
-	ctx->device = device;
-	rtb_default_params(&ctx->params);
-	memset(&ctx->S, 0, sizeof(ctx->S));
-	if (cudaSetDevice(device) != cudaSuccess || cudaMalloc((void**)&ctx->counters, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long)) != cudaSuccess ||
-	    cudaMemset(ctx->counters, 0, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long)) != cudaSuccess)
+	rtb_params P = g->userParams;
+	int n = (int)groupSize(g);
+	if (n == 1) return P;
+	int w = (P.partition != RTB_PART_NONE && P.part_world > 1) ? P.part_world : 1;
+	int r = (w > 1) ? P.part_rank : 0;
+	int mode = (P.partition == RTB_PART_TILE) ? RTB_PART_TILE : RTB_PART_SPP;
+	if (P.partition == RTB_PART_NONE && units < (uint32_t)n) mode = RTB_PART_TILE;
+	P.partition = mode;
+	P.part_world = w * n;
+	P.part_rank = r + w * d;
+	return P;
+}
+
+// A device group shards the PASSES of the light-driven estimators (a pass is a unit whose splats land anywhere on
+// the film / one VPL set for the whole image): member d takes a contiguous share of [pass_begin, pass_begin + count).
+template <class F>
+static int splitPasses(rtb_ctx* g, uint32_t pass_begin, uint32_t pass_count, F one)
+{
+	uint32_t n = (uint32_t)groupSize(g), base = pass_count / n, rem = pass_count % n;
+	uint32_t share0 = base + (rem > 0 ? 1u : 0u);
+	int rc = forEachMember(g, [&](rtb_ctx* m, int d) {
+		uint32_t cnt = base + ((uint32_t)d < rem ? 1u : 0u);
+		uint32_t off = (uint32_t)d * base + ((uint32_t)d < rem ? (uint32_t)d : rem);
+		if (cnt == 0) return (int)RTB_OK;
+		m->accumDirty = true;
+		return one(m, pass_begin + off, cnt);
+	});
+	if (rc) return rc;
+	g->spp += pass_count - share0; // Film::SPP counts every pass of the call, not only device 0's share
+	return RTB_OK;
+}
+
+namespace
+{
+struct NcclApi
+{
+	int (*CommInitAll)(void**, int, const int*) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclInt64 = 4, kNcclSum = 0; // ncclDataType_t / ncclRedOp_t (stable across NCCL 2.x)
+} // namespace
+
+static int ncclInit(rtb_ctx* g)
+{
+	if (g->ncclComms[0]) return RTB_OK;
+	if (!g_nccl.Reduce)
 	{
-		int rc = fail(nullptr, RTB_ERR_CUDA, "context creation on device %d failed: %s", device,
-		              cudaGetErrorString(cudaGetLastError()));
-		delete ctx;
-		return rc;
+		void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!h) return fail(g, RTB_ERR_STATE, "device group: no peer access between the GPUs and libnccl.so.2 cannot be loaded (%s)", dlerror());
+		g->ncclLib = h;
+		g_nccl.CommInitAll = (int (*)(void**, int, const int*))dlsym(h, "ncclCommInitAll");
+		g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+		g_nccl.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(h, "ncclReduce");
+		g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+		g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+		g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+		if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.Reduce || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+		{
+			g_nccl = NcclApi();
+			return fail(g, RTB_ERR_STATE, "libnccl.so.2 lacks ncclCommInitAll / ncclReduce");
+		}
 	}
-	*out = ctx;
-	return RTB_OK;
-}
-
-void rtb_destroy(rtb_ctx* ctx)
-{
-	if (!ctx) return;
-	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
-	resolveTimings(ctx);
-	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
-	freeScene(ctx);
-	for (int k = 0; k < RTB_MAX_POOLS; k++)
+	int devs[8];
+	int n = (int)groupSize(g);
+	devs[0] = g->device;
+	for (int d = 1; d < n; d++) devs[d] = g->peers[d - 1]->device;
+	int rc = g_nccl.CommInitAll(g->ncclComms, n, devs);
+	if (rc != 0)
 	{
-		if (ctx->poolStreams[k]) cudaStreamDestroy(ctx->poolStreams[k]);
-		if (ctx->poolDone[k]) cudaEventDestroy(ctx->poolDone[k]);
-		if (ctx->shadowStreams[k]) cudaStreamDestroy(ctx->shadowStreams[k]);
-		if (ctx->evShaded[k]) cudaEventDestroy(ctx->evShaded[k]);
-		if (ctx->evShadowed[k]) cudaEventDestroy(ctx->evShadowed[k]);
+		memset(g->ncclComms, 0, sizeof(g->ncclComms));
+		return fail(g, RTB_ERR_CUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
 	}
-	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
-	if (ctx->counters) cudaFree(ctx->counters);
-	if (ctx->hostProbe) cudaFreeHost(ctx->hostProbe);
-	delete ctx;
-}
-
-const char* rtb_last_error(const rtb_ctx* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
-
-int rtb_set_stream(rtb_ctx* ctx, void* cuda_stream)
-{
-	if (!ctx) return RTB_ERR_ARG;
-	ctx->stream = (cudaStream_t)cuda_stream;
 	return RTB_OK;
 }
 
-int rtb_synchronize(rtb_ctx* ctx)
+// Sum the members' accumulators into device 0's (exact), zero the members'.  Leaves the float film resolved when
+// the P2P kernel did the work.
+static int gatherAccum(rtb_ctx* g)
 {
-	if (!ctx) return RTB_ERR_ARG;
-	if (int rc = bind(ctx)) return rc;
-	CK(cudaStreamSynchronize(ctx->stream));
+	rtb_ctx* ctx = g; // for CK
+	size_t n = groupSize(g);
+	if (n == 1) return RTB_OK;
+	bool any = false;
+	for (rtb_ctx* p : g->peers) any = any || p->accumDirty;
+	if (!any) return RTB_OK;
+	const uint32_t count = g->width * g->height * 3u;
+	const size_t bytes = (size_t)count * sizeof(long long);
+	// device 0's stream waits for every member's work
+	for (rtb_ctx* p : g->peers)
+	{
+		CK(cudaSetDevice(p->device));
+		CK(cudaEventRecord(p->evGroup, p->stream));
+	}
+	CK(cudaSetDevice(g->device));
+	for (rtb_ctx* p : g->peers) CK(cudaStreamWaitEvent(g->stream, p->evGroup, 0));
+	bool allDirect = true;
+	for (char c : g->peerDirect) allDirect = allDirect && c;
+	int mode = g->reduceMode;
+	if (mode == 0 && !allDirect) mode = 1;
+	g->gathers++;
+	if (mode == 0)
+	{
+		GatherSrc src;
+		src.n = 0;
+		for (rtb_ctx* p : g->peers)
+			if (p->accumDirty) src.p[src.n++] = p->accum;
+		unsigned grid = (count + 255u) / 256u;
+		k_film_gather<<<grid, 256, 0, g->stream>>>(g->accum, src, count, g->film);
+		g->launches++;
+		CK(cudaGetLastError());
+		g->filmDirty = false; // the kernel wrote the float film too
+		g->gatherP2P++;
+	}
+	else if (mode == 1)
+	{
+		if (int rc = ncclInit(g)) return rc;
+		// the root's in-place reduce runs on its stream; every member enqueues its part on its own stream
+		int rc = g_nccl.GroupStart();
+		for (size_t d = 0; d < n && rc == 0; d++)
+		{
+			rtb_ctx* m = d == 0 ? g : g->peers[d - 1];
+			cudaSetDevice(m->device);
+			rc = g_nccl.Reduce(m->accum, d == 0 ? g->accum : nullptr, count, kNcclInt64, kNcclSum, 0, g->ncclComms[d], m->stream);
+		}
+		int rc2 = g_nccl.GroupEnd();
+		cudaSetDevice(g->device);
+		if (rc != 0 || rc2 != 0) return fail(g, RTB_ERR_CUDA, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc ? rc : rc2) : "error");
+		g->filmDirty = true;
+		g->gatherNccl++;
+	}
+	else
+	{
+		if (!g->gatherScratch) CK(cudaMalloc((void**)&g->gatherScratch, bytes));
+		for (rtb_ctx* p : g->peers)
+		{
+			if (!p->accumDirty) continue;
+			CK(cudaMemcpyPeerAsync(g->gatherScratch, g->device, p->accum, p->device, bytes, g->stream));
+			GatherSrc src;
+			src.n = 1, src.p[0] = g->gatherScratch;
+			k_film_gather<<<(count + 255u) / 256u, 256, 0, g->stream>>>(g->accum, src, count, g->film);
+			g->launches++;
+		}
+		CK(cudaGetLastError());
+		g->filmDirty = false;
+	}
+	// the members' sums now live in device 0's accumulators: zero theirs (after the gather has read them)
+	CK(cudaEventRecord(g->evGroup, g->stream));
+	for (rtb_ctx* p : g->peers)
+	{
+		if (!p->accumDirty) continue;
+		CK(cudaSetDevice(p->device));
+		CK(cudaStreamWaitEvent(p->stream, g->evGroup, 0));
+		CK(cudaMemsetAsync(p->accum, 0, bytes, p->stream));
+		p->accumDirty = false;
+	}
+	CK(cudaSetDevice(g->device));
 	return RTB_OK;
 }
 
-int rtb_set_params(rtb_ctx* ctx, const rtb_params* p)
+// Host side of rtb_upload_scene: validate the description and build everything derived from it (skip links, the
+// accelerated trees, the env sampling tables) ONCE; a device group uploads the same prepared scene to every member.
+struct PreparedScene
 {
-	if (!ctx || !p) return fail(ctx, RTB_ERR_ARG, "rtb_set_params: NULL argument");
-	if (p->integrator < RTB_INT_PATH || p->integrator > RTB_INT_PATH_MIS) return fail(ctx, RTB_ERR_ARG, "bad integrator %d", p->integrator);
-	if (p->sampling != RTB_SAMPLING_STRICT && p->sampling != RTB_SAMPLING_IMPORTANCE) return fail(ctx, RTB_ERR_ARG, "bad sampling %d", p->sampling);
-	if (int rc = checkTrav(ctx, p->traversal)) return rc;
-	if (p->filter != RTB_FILTER_BOX && p->filter != RTB_FILTER_GAUSSIAN) return fail(ctx, RTB_ERR_ARG, "bad filter %d", p->filter);
-	if (p->partition < RTB_PART_NONE || p->partition > RTB_PART_TILE) return fail(ctx, RTB_ERR_ARG, "bad partition %d", p->partition);
-	if (p->partition != RTB_PART_NONE && (p->part_world < 1 || p->part_rank < 0 || p->part_rank >= p->part_world))
-		return fail(ctx, RTB_ERR_ARG, "bad partition rank %d of %d", p->part_rank, p->part_world);
-	if (p->scheduler != RTB_SCHED_WAVEFRONT && p->scheduler != RTB_SCHED_MEGAKERNEL) return fail(ctx, RTB_ERR_ARG, "bad scheduler %d", p->scheduler);
-	if (p->max_depth > 200) return fail(ctx, RTB_ERR_ARG, "max_depth too large");
-	if (p->max_depth < 0 || !(p->epsilon >= 0.0f)) return fail(ctx, RTB_ERR_ARG, "bad max_depth/epsilon");
-	// a zero-initialised rtb_params (instead of rtb_default_params) would end every path at depth 0 (rr_cap 0) and
-	// remove the cull slack that FAST / WIDE hit-ID parity rests on (cull_rel 0): wrong images with RTB_OK
-	if (!(p->rr_cap > 0.0f && p->rr_cap <= 1.0f)) return fail(ctx, RTB_ERR_ARG, "rr_cap %g outside (0, 1]: start from rtb_default_params()", p->rr_cap);
-	if (!(p->cull_rel >= 1e-7f && p->cull_rel <= 1e-2f))
-		return fail(ctx, RTB_ERR_ARG, "cull_rel %g outside [1e-7, 1e-2]: start from rtb_default_params()", p->cull_rel);
-	if (!(p->filter_radius >= 0.0f && p->filter_radius <= 16.0f) || !(fabsf(p->filter_alpha) <= 1e6f))
-		return fail(ctx, RTB_ERR_ARG, "bad Gaussian filter parameters (radius %g, alpha %g)", p->filter_radius, p->filter_alpha);
-	if (p->primary_reuse != 0 && p->primary_reuse != 1) return fail(ctx, RTB_ERR_ARG, "primary_reuse must be 0 or 1");
-	ctx->params = *p;
-	return RTB_OK;
-}
+	const rtb_scene_desc* sc = nullptr;
+	std::vector<rtb_accel::F4> xnodes;
+	rtb_accel::FastTree fast;
+	rtb_accel::WideTree wide;
+	std::vector<float> marginal, cond;
+	int envW = 0, envH = 0;
+};
 
-int rtb_get_params(const rtb_ctx* ctx, rtb_params* p)
+static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& ps)
 {
-	if (!ctx || !p) return RTB_ERR_ARG;
-	*p = ctx->params;
-	return RTB_OK;
-}
-
-int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
-{
-	if (!ctx || !sc) return fail(ctx, RTB_ERR_ARG, "rtb_upload_scene: NULL argument");
-	if (int rc = bind(ctx)) return rc;
 	if (sc->n_tris && (!sc->tri_isect || !sc->tri_shade)) return fail(ctx, RTB_ERR_ARG, "triangle arrays missing");
 	if (sc->n_ref_nodes && !sc->ref_nodes) return fail(ctx, RTB_ERR_ARG, "ref_nodes missing");
 	if (sc->n_tris && !sc->n_ref_nodes) return fail(ctx, RTB_ERR_ARG, "triangles without a BVH");
@@ -797,16 +904,16 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 		return fail(ctx, RTB_ERR_ARG, "background env texture out of range");
 
 	// host-side acceleration data
-	std::vector<rtb_accel::F4> xnodes;
+	std::vector<rtb_accel::F4>& xnodes = ps.xnodes;
 	std::vector<rtb_accel::RefLeaf> leaves;
 	const char* err = nullptr;
 	if (!rtb_accel::buildExact(sc->ref_nodes, sc->n_ref_nodes, sc->n_tris, xnodes, leaves, &err)) return fail(ctx, RTB_ERR_ARG, "%s", err);
-	rtb_accel::FastTree fast;
+	rtb_accel::FastTree& fast = ps.fast;
 	{
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
 	}
-	rtb_accel::WideTree wide;
+	rtb_accel::WideTree& wide = ps.wide;
 	{
 		rtb_accel::WideBuilder wb(fast);
 		wb.build(wide);
@@ -815,6 +922,27 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 	if (fast.maxDepth + 2 > RTB_STACK || 3 * wide.maxDepth + 6 > RTB_STACK)
 		return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (binary %u, wide %u)", fast.maxDepth, wide.maxDepth);
 
+	for (uint32_t i = 0; i < sc->n_lights; i++)
+	{
+		if (sc->lights[i].type == RTB_LIGHT_ENVMAP)
+		{
+			const rtb_texture& t = sc->textures[sc->lights[i].tex];
+			rtb_accel::buildEnvTables(sc->texels + (size_t)t.offset * 3, t.width, t.height, ps.marginal, ps.cond);
+			ps.envW = t.width, ps.envH = t.height;
+			break;
+		}
+	}
+	ps.sc = sc;
+	return RTB_OK;
+}
+
+static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
+{
+	const rtb_scene_desc* sc = ps.sc;
+	const std::vector<rtb_accel::F4>& xnodes = ps.xnodes;
+	const rtb_accel::FastTree& fast = ps.fast;
+	const rtb_accel::WideTree& wide = ps.wide;
+	if (int rc = bind(ctx)) return rc;
 	CK(cudaStreamSynchronize(ctx->stream));
 	freeScene(ctx);
 	DevScene& S = ctx->S;
@@ -852,18 +980,11 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 	memcpy(S.bg_colour, sc->background_colour, sizeof(S.bg_colour));
 	S.bg_tex = sc->background_tex;
 	// env sampling tables when the environment map is a light
-	std::vector<float> marginal, cond;
-	for (uint32_t i = 0; i < sc->n_lights; i++)
+	if (!ps.marginal.empty())
 	{
-		if (sc->lights[i].type == RTB_LIGHT_ENVMAP)
-		{
-			const rtb_texture& t = sc->textures[sc->lights[i].tex];
-			rtb_accel::buildEnvTables(sc->texels + (size_t)t.offset * 3, t.width, t.height, marginal, cond);
-			S.env_w = t.width, S.env_h = t.height;
-			if ((rc = uploadArray(ctx, marginal.data(), marginal.size(), &S.env_marginal))) return rc;
-			if ((rc = uploadArray(ctx, cond.data(), cond.size(), &S.env_cond))) return rc;
-			break;
-		}
+		S.env_w = ps.envW, S.env_h = ps.envH;
+		if ((rc = uploadArray(ctx, ps.marginal.data(), ps.marginal.size(), &S.env_marginal))) return rc;
+		if ((rc = uploadArray(ctx, ps.cond.data(), ps.cond.size(), &S.env_cond))) return rc;
 	}
 	ctx->width = (uint32_t)sc->camera.width;
 	ctx->height = (uint32_t)sc->camera.height;
@@ -884,7 +1005,233 @@ int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 	// the host vectors above die at return: finish the async copies first
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->haveScene = true;
+	ctx->accumDirty = false;
 	return RTB_OK;
+}
+
+
+extern "C" {
+
+int rtb_abi_version(void) { return RTB_ABI_VERSION; }
+
+void rtb_default_params(rtb_params* p)
+{
+	if (!p) return;
+	memset(p, 0, sizeof(*p));
+	p->max_depth = 4;     // MAX_DEPTH, RTBase/Renderer.h:20
+	p->epsilon = 1e-4f;   // EPSILON, RTBase/Geometry.h:60
+	p->rr_cap = 0.9f;     // RTBase/Renderer.h:353
+	p->integrator = RTB_INT_PATH;
+	p->sampling = RTB_SAMPLING_STRICT;
+	p->traversal = RTB_TRAV_FAST; // profiles/r01_wide_tree.txt: the 4-wide tree measured ~5 % slower
+	p->filter = RTB_FILTER_BOX; // RTBase/Renderer.h:50
+	p->filter_radius = 2.0f;    // RTBase/Renderer.h:51
+	p->filter_alpha = 0.1f;
+	p->seed = 1;                // MTRandom(seed = 1), RTBase/Sampling.h:18
+	p->partition = RTB_PART_NONE;
+	p->part_rank = 0;
+	p->part_world = 1;
+	p->cull_rel = 1e-5f;
+	p->scheduler = RTB_SCHED_WAVEFRONT;
+	p->primary_reuse = 1;
+}
+
+static int createOne(int device, rtb_ctx** out)
+{
+	rtb_ctx* ctx = nullptr;
+	if (!out) return fail(nullptr, RTB_ERR_ARG, "rtb_create: out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return fail(nullptr, RTB_ERR_NODEV, "no CUDA device (%s); librtb200 has no CPU fallback",
+		            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+	if (device < 0 || device >= n) return fail(nullptr, RTB_ERR_NODEV, "device %d out of range [0,%d)", device, n);
+	ctx = new (std::nothrow) rtb_ctx();
+	if (!ctx) return fail(nullptr, RTB_ERR_OOM, "out of host memory");
+	ctx->device = device;
+	rtb_default_params(&ctx->params);
+	ctx->userParams = ctx->params;
+	memset(&ctx->S, 0, sizeof(ctx->S));
+	if (cudaSetDevice(device) != cudaSuccess || cudaMalloc((void**)&ctx->counters, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMemset(ctx->counters, 0, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long)) != cudaSuccess)
+	{
+		int rc = fail(nullptr, RTB_ERR_CUDA, "context creation on device %d failed: %s", device,
+		              cudaGetErrorString(cudaGetLastError()));
+		delete ctx;
+		return rc;
+	}
+	if (cudaEventCreateWithFlags(&ctx->evGroup, cudaEventDisableTiming) != cudaSuccess) ctx->evGroup = nullptr;
+	*out = ctx;
+	return RTB_OK;
+}
+
+int rtb_create(int device, rtb_ctx** out) { return createOne(device, out); }
+
+int rtb_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int rtb_create_multi(const int* devices, int n, rtb_ctx** out)
+{
+	if (!out) return fail(nullptr, RTB_ERR_ARG, "rtb_create_multi: out is NULL");
+	*out = nullptr;
+	int all[8];
+	if (!devices)
+	{
+		// every visible device (RayTracer::init: numProcs = dwNumberOfProcessors, Renderer.h:52-55)
+		int have = rtb_device_count();
+		if (n <= 0 || n > have) n = have;
+		if (n > 8) n = 8;
+		for (int i = 0; i < n; i++) all[i] = i;
+		devices = all;
+	}
+	if (n < 1 || n > 8) return fail(nullptr, n < 1 ? RTB_ERR_NODEV : RTB_ERR_ARG, "rtb_create_multi: %d devices (1..8 supported; no CUDA device means no renderer: there is no CPU fallback)", n);
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < i; j++)
+			if (devices[i] == devices[j]) return fail(nullptr, RTB_ERR_ARG, "rtb_create_multi: device %d listed twice", devices[i]);
+	rtb_ctx* g = nullptr;
+	if (int rc = createOne(devices[0], &g)) return rc;
+	for (int i = 1; i < n; i++)
+	{
+		rtb_ctx* p = nullptr;
+		int rc = createOne(devices[i], &p);
+		if (rc)
+		{
+			rtb_destroy(g);
+			return rc;
+		}
+		g->peers.push_back(p);
+		int can = 0;
+		bool direct = false;
+		if (cudaDeviceCanAccessPeer(&can, g->device, p->device) == cudaSuccess && can)
+		{
+			cudaSetDevice(g->device);
+			cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+			direct = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
+			cudaGetLastError();
+		}
+		g->peerDirect.push_back(direct ? 1 : 0);
+	}
+	if (const char* e = getenv("RTB_GROUP_REDUCE"))
+	{
+		if (!strcmp(e, "nccl")) g->reduceMode = 1;
+		else if (!strcmp(e, "staged")) g->reduceMode = 2;
+	}
+	cudaSetDevice(g->device);
+	*out = g;
+	return RTB_OK;
+}
+
+int rtb_group_size(const rtb_ctx* ctx) { return ctx ? (int)groupSize(ctx) : 0; }
+
+int rtb_group_info(const rtb_ctx* ctx, int* devices, int* p2p, uint64_t* gathers_p2p, uint64_t* gathers_nccl)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	size_t n = groupSize(ctx);
+	for (size_t d = 0; d < n; d++)
+	{
+		if (devices) devices[d] = d == 0 ? ctx->device : ctx->peers[d - 1]->device;
+		if (p2p) p2p[d] = d == 0 ? 1 : (int)ctx->peerDirect[d - 1];
+	}
+	if (gathers_p2p) *gathers_p2p = ctx->gatherP2P;
+	if (gathers_nccl) *gathers_nccl = ctx->gatherNccl;
+	return RTB_OK;
+}
+
+void rtb_destroy(rtb_ctx* ctx)
+{
+	if (!ctx) return;
+	for (int d = 0; d < 8; d++)
+		if (ctx->ncclComms[d] && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->ncclComms[d]);
+	for (rtb_ctx* p : ctx->peers) rtb_destroy(p);
+	ctx->peers.clear();
+	cudaSetDevice(ctx->device);
+	if (ctx->gatherScratch) cudaFree(ctx->gatherScratch);
+	if (ctx->evGroup) cudaEventDestroy(ctx->evGroup);
+	cudaStreamSynchronize(ctx->stream);
+	resolveTimings(ctx);
+	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+	freeScene(ctx);
+	for (int k = 0; k < RTB_MAX_POOLS; k++)
+	{
+		if (ctx->poolStreams[k]) cudaStreamDestroy(ctx->poolStreams[k]);
+		if (ctx->poolDone[k]) cudaEventDestroy(ctx->poolDone[k]);
+		if (ctx->shadowStreams[k]) cudaStreamDestroy(ctx->shadowStreams[k]);
+		if (ctx->evShaded[k]) cudaEventDestroy(ctx->evShaded[k]);
+		if (ctx->evShadowed[k]) cudaEventDestroy(ctx->evShadowed[k]);
+	}
+	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+	if (ctx->counters) cudaFree(ctx->counters);
+	if (ctx->hostProbe) cudaFreeHost(ctx->hostProbe);
+	delete ctx;
+}
+
+const char* rtb_last_error(const rtb_ctx* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+int rtb_set_stream(rtb_ctx* ctx, void* cuda_stream)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	ctx->stream = (cudaStream_t)cuda_stream;
+	return RTB_OK;
+}
+
+int rtb_synchronize(rtb_ctx* ctx)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	for (rtb_ctx* p : ctx->peers)
+	{
+		CK(cudaSetDevice(p->device));
+		CK(cudaStreamSynchronize(p->stream));
+	}
+	if (int rc = bind(ctx)) return rc;
+	CK(cudaStreamSynchronize(ctx->stream));
+	return RTB_OK;
+}
+
+int rtb_set_params(rtb_ctx* ctx, const rtb_params* p)
+{
+	if (!ctx || !p) return fail(ctx, RTB_ERR_ARG, "rtb_set_params: NULL argument");
+	if (p->integrator < RTB_INT_PATH || p->integrator > RTB_INT_PATH_MIS) return fail(ctx, RTB_ERR_ARG, "bad integrator %d", p->integrator);
+	if (p->sampling != RTB_SAMPLING_STRICT && p->sampling != RTB_SAMPLING_IMPORTANCE) return fail(ctx, RTB_ERR_ARG, "bad sampling %d", p->sampling);
+	if (int rc = checkTrav(ctx, p->traversal)) return rc;
+	if (p->filter != RTB_FILTER_BOX && p->filter != RTB_FILTER_GAUSSIAN) return fail(ctx, RTB_ERR_ARG, "bad filter %d", p->filter);
+	if (p->partition < RTB_PART_NONE || p->partition > RTB_PART_TILE) return fail(ctx, RTB_ERR_ARG, "bad partition %d", p->partition);
+	if (p->partition != RTB_PART_NONE && (p->part_world < 1 || p->part_rank < 0 || p->part_rank >= p->part_world))
+		return fail(ctx, RTB_ERR_ARG, "bad partition rank %d of %d", p->part_rank, p->part_world);
+	if (p->scheduler != RTB_SCHED_WAVEFRONT && p->scheduler != RTB_SCHED_MEGAKERNEL) return fail(ctx, RTB_ERR_ARG, "bad scheduler %d", p->scheduler);
+	if (p->max_depth > 200) return fail(ctx, RTB_ERR_ARG, "max_depth too large");
+	if (p->max_depth < 0 || !(p->epsilon >= 0.0f)) return fail(ctx, RTB_ERR_ARG, "bad max_depth/epsilon");
+	// a zero-initialised rtb_params (instead of rtb_default_params) would end every path at depth 0 (rr_cap 0) and
+	// remove the cull slack that FAST / WIDE hit-ID parity rests on (cull_rel 0): wrong images with RTB_OK
+	if (!(p->rr_cap > 0.0f && p->rr_cap <= 1.0f)) return fail(ctx, RTB_ERR_ARG, "rr_cap %g outside (0, 1]: start from rtb_default_params()", p->rr_cap);
+	if (!(p->cull_rel >= 1e-7f && p->cull_rel <= 1e-2f))
+		return fail(ctx, RTB_ERR_ARG, "cull_rel %g outside [1e-7, 1e-2]: start from rtb_default_params()", p->cull_rel);
+	if (!(p->filter_radius >= 0.0f && p->filter_radius <= 16.0f) || !(fabsf(p->filter_alpha) <= 1e6f))
+		return fail(ctx, RTB_ERR_ARG, "bad Gaussian filter parameters (radius %g, alpha %g)", p->filter_radius, p->filter_alpha);
+	if (p->primary_reuse != 0 && p->primary_reuse != 1) return fail(ctx, RTB_ERR_ARG, "primary_reuse must be 0 or 1");
+	ctx->params = *p;
+	ctx->userParams = *p;
+	for (rtb_ctx* m : ctx->peers) m->params = *p, m->userParams = *p;
+	return RTB_OK;
+}
+
+int rtb_get_params(const rtb_ctx* ctx, rtb_params* p)
+{
+	if (!ctx || !p) return RTB_ERR_ARG;
+	*p = ctx->userParams;
+	return RTB_OK;
+}
+
+int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
+{
+	if (!ctx || !sc) return fail(ctx, RTB_ERR_ARG, "rtb_upload_scene: NULL argument");
+	PreparedScene ps;
+	if (int rc = prepareScene(ctx, sc, ps)) return rc;
+	return forEachMember(ctx, [&ps](rtb_ctx* m, int) { return uploadPrepared(m, ps); });
 }
 
 int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam)
@@ -894,14 +1241,15 @@ int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam)
 	if ((uint32_t)cam->width != ctx->width || (uint32_t)cam->height != ctx->height)
 		return fail(ctx, RTB_ERR_ARG, "camera film size differs from the uploaded scene's");
 	ctx->S.cam = *cam;
+	for (rtb_ctx* m : ctx->peers) m->S.cam = *cam;
 	return RTB_OK;
 }
 
-int rtb_clear(rtb_ctx* ctx)
+static int clearOne(rtb_ctx* ctx)
 {
-	if (!ctx) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = bind(ctx)) return rc;
+	ctx->accumDirty = false;
 	CK(cudaMemsetAsync(ctx->film, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(float), ctx->stream));
 	CK(cudaMemsetAsync(ctx->accum, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(long long), ctx->stream));
 	ctx->filmDirty = false;
@@ -914,30 +1262,37 @@ int rtb_clear(rtb_ctx* ctx)
 	return RTB_OK;
 }
 
+int rtb_clear(rtb_ctx* ctx)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	return forEachMember(ctx, [](rtb_ctx* m, int) { return clearOne(m); });
+}
+
 int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 {
 	if (!ctx) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render before rtb_upload_scene");
 	if (spp_count == 0) return RTB_OK;
 	if ((uint64_t)spp_begin + spp_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "sample index overflow");
-	if (int rc = bind(ctx)) return rc;
-	bool mega = ctx->params.scheduler == RTB_SCHED_MEGAKERNEL;
-	int rc = mega ? renderMegakernel(ctx, spp_begin, spp_count)
-	                                                           : renderWavefront(ctx, spp_begin, spp_count);
+	// every member of a device group renders its slice on its own host thread (the reference spawns its worker
+	// threads per render() call too, Renderer.h:842-849); a plain context is a group of one
+	int rc = forEachMember(ctx, [ctx, spp_begin, spp_count](rtb_ctx* m, int d) {
+		if (int rc = bind(m)) return rc;
+		m->params = composedParams(ctx, d, spp_count);
+		bool mega = m->params.scheduler == RTB_SCHED_MEGAKERNEL;
+		int rc = mega ? renderMegakernel(m, spp_begin, spp_count) : renderWavefront(m, spp_begin, spp_count);
+		m->params = ctx->userParams;
+		m->accumDirty = true;
+		return rc;
+	});
 	if (rc) return rc;
 	ctx->spp += spp_count;
 	return RTB_OK;
 }
 
 // pass_count x RayTracer::lightTracer() (Renderer.h:220-231).
-int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
+static int lightOne(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 {
-	if (!ctx) return RTB_ERR_ARG;
-	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_light before rtb_upload_scene");
-	if (pass_count == 0) return RTB_OK;
-	if ((uint64_t)pass_begin + pass_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "pass index overflow");
-	if (ctx->params.partition != RTB_PART_NONE && ctx->params.part_world > 1)
-		return fail(ctx, RTB_ERR_ARG, "rtb_render_light: light paths land anywhere on the film; shard the passes over devices instead");
 	if (int rc = bind(ctx)) return rc;
 	rtb_camera_ext ce;
 	if (!rtb_camera_derive(&ctx->S.cam, &ce)) return fail(ctx, RTB_ERR_ARG, "camera matrices are singular");
@@ -968,16 +1323,20 @@ int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 	return RTB_OK;
 }
 
-// pass_count x RayTracer::instantRadiosity() (Renderer.h:102-123).
-int rtb_render_ir(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths)
+int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 {
 	if (!ctx) return RTB_ERR_ARG;
-	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_ir before rtb_upload_scene");
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_light before rtb_upload_scene");
 	if (pass_count == 0) return RTB_OK;
-	if (n_paths < 1 || n_paths > 65536) return fail(ctx, RTB_ERR_ARG, "rtb_render_ir: 1 <= n_paths <= 65536 light paths per pass");
 	if ((uint64_t)pass_begin + pass_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "pass index overflow");
-	if (ctx->params.partition != RTB_PART_NONE && ctx->params.part_world > 1)
-		return fail(ctx, RTB_ERR_ARG, "rtb_render_ir: shard the passes over devices (a pass is one VPL set for the whole image)");
+	if (ctx->userParams.partition != RTB_PART_NONE && ctx->userParams.part_world > 1)
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_light: light paths land anywhere on the film; shard the passes over devices instead");
+	return splitPasses(ctx, pass_begin, pass_count, [](rtb_ctx* m, uint32_t b, uint32_t c) { return lightOne(m, b, c); });
+}
+
+// pass_count x RayTracer::instantRadiosity() (Renderer.h:102-123).
+static int irOne(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths)
+{
 	if (int rc = bind(ctx)) return rc;
 	if (ctx->vplPaths < n_paths)
 	{
@@ -1012,6 +1371,18 @@ int rtb_render_ir(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32
 	ctx->filmDirty = true;
 	ctx->spp += pass_count; // Film::incrementSPP once per render() (Renderer.h:878)
 	return RTB_OK;
+}
+
+int rtb_render_ir(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths)
+{
+	if (!ctx) return RTB_ERR_ARG;
+	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_ir before rtb_upload_scene");
+	if (pass_count == 0) return RTB_OK;
+	if (n_paths < 1 || n_paths > 65536) return fail(ctx, RTB_ERR_ARG, "rtb_render_ir: 1 <= n_paths <= 65536 light paths per pass");
+	if ((uint64_t)pass_begin + pass_count > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "pass index overflow");
+	if (ctx->userParams.partition != RTB_PART_NONE && ctx->userParams.part_world > 1)
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_ir: shard the passes over devices (a pass is one VPL set for the whole image)");
+	return splitPasses(ctx, pass_begin, pass_count, [n_paths](rtb_ctx* m, uint32_t b, uint32_t c) { return irOne(m, b, c, n_paths); });
 }
 
 // RayTracer::adaptiveRender (Renderer.h:679-749) on the wavefront schedule.
@@ -1106,6 +1477,7 @@ int rtb_read_film(rtb_ctx* ctx, float* rgb_sum, uint32_t* spp)
 	if (!ctx) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = gatherAccum(ctx)) return rc;
 	if (rgb_sum)
 	{
 		const float* src = nullptr;
@@ -1124,6 +1496,14 @@ int rtb_write_film(rtb_ctx* ctx, const float* rgb_sum)
 	if (!ctx || !rgb_sum) return fail(ctx, RTB_ERR_ARG, "rtb_write_film: NULL argument");
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = bind(ctx)) return rc;
+	// a device group: the written film replaces the sum of ALL members' accumulators
+	for (rtb_ctx* m : ctx->peers)
+	{
+		CK(cudaSetDevice(m->device));
+		CK(cudaMemsetAsync(m->accum, 0, (size_t)m->width * m->height * 3 * sizeof(long long), m->stream));
+		m->accumDirty = false;
+	}
+	if (int rc = bind(ctx)) return rc;
 	uint32_t n = ctx->width * ctx->height * 3;
 	CK(cudaMemcpyAsync(ctx->film, rgb_sum, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 	k_film_import<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->film, ctx->accum, n);
@@ -1139,6 +1519,7 @@ int rtb_film_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_floats)
 	if (!ctx || !dptr) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = gatherAccum(ctx)) return rc;
 	if (int rc = resolveFilm(ctx)) return rc;
 	*dptr = ctx->film;
 	if (n_floats) *n_floats = (uint64_t)ctx->width * ctx->height * 3;
@@ -1149,6 +1530,11 @@ int rtb_accum_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_int64)
 {
 	if (!ctx || !dptr) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (!ctx->peers.empty())
+	{
+		if (int rc = bind(ctx)) return rc;
+		if (int rc = gatherAccum(ctx)) return rc; // a group hands out the sum of its members
+	}
 	*dptr = ctx->accum;
 	if (n_int64) *n_int64 = (uint64_t)ctx->width * ctx->height * 3;
 	ctx->filmDirty = true; // the caller may reduce into it
@@ -1175,6 +1561,7 @@ int rtb_tonemap(rtb_ctx* ctx, uint8_t* rgb8, float exposure)
 	if (!ctx || !rgb8) return fail(ctx, RTB_ERR_ARG, "rtb_tonemap: NULL argument");
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = gatherAccum(ctx)) return rc;
 	size_t n = (size_t)ctx->width * ctx->height * 3;
 	if (!ctx->tone) CK(cudaMalloc((void**)&ctx->tone, n));
 	const float* src = nullptr;
@@ -1187,9 +1574,34 @@ int rtb_tonemap(rtb_ctx* ctx, uint8_t* rgb8, float exposure)
 	return RTB_OK;
 }
 
+static int statsOne(rtb_ctx* ctx, rtb_stats* out);
+
 int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out)
 {
 	if (!ctx || !out) return RTB_ERR_ARG;
+	if (int rc = statsOne(ctx, out)) return rc;
+	// a device group: work counters add up, the render time is the slowest member's
+	for (rtb_ctx* m : ctx->peers)
+	{
+		rtb_stats s;
+		if (int rc = statsOne(m, &s))
+		{
+			ctx->error = m->error;
+			return rc;
+		}
+		out->samples += s.samples, out->closest_rays += s.closest_rays, out->shadow_rays += s.shadow_rays;
+		out->kernel_launches += s.kernel_launches;
+		out->box_tests += s.box_tests, out->tri_tests += s.tri_tests;
+		out->shadow_box_tests += s.shadow_box_tests, out->shadow_tri_tests += s.shadow_tri_tests;
+		out->iterations += s.iterations, out->host_syncs += s.host_syncs;
+		if (s.render_ms > out->render_ms) out->render_ms = s.render_ms;
+	}
+	if (!ctx->peers.empty()) cudaSetDevice(ctx->device);
+	return RTB_OK;
+}
+
+static int statsOne(rtb_ctx* ctx, rtb_stats* out)
+{
 	if (int rc = bind(ctx)) return rc;
 	unsigned long long rows[RTB_COUNTER_STRIPES * 8], c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	CK(cudaMemcpyAsync(rows, ctx->counters, sizeof(rows), cudaMemcpyDeviceToHost, ctx->stream));

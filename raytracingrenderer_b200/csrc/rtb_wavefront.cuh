@@ -94,6 +94,24 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const long long* __restrict_
 	film[i] = (float)((double)accum[i] * (1.0 / 4294967296.0));
 }
 
+// Film read-out of a device group (rtb_create_multi): device 0 adds the other GPUs' fixed-point sums to its own —
+// reading them straight from peer memory over NVLink — and converts the total to the float film in the same pass:
+// reduction + finalisation in ONE kernel, no staging buffer, exact (integer sums: the result is the single-GPU film).
+struct GatherSrc
+{
+	const long long* p[8];
+	uint32_t n;
+};
+__global__ void __launch_bounds__(256) k_film_gather(long long* __restrict__ accum, const GatherSrc src, uint32_t n, float* __restrict__ film)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	long long v = accum[i];
+	for (uint32_t k = 0; k < src.n; k++) v += src.p[k][i];
+	accum[i] = v;
+	film[i] = (float)((double)v * (1.0 / 4294967296.0));
+}
+
 // the inverse of k_wf_resolve: host-provided float sums become the fixed-point master copy (rtb_write_film)
 __global__ void __launch_bounds__(256) k_film_import(const float* __restrict__ film, long long* accum, uint32_t n)
 {

@@ -48,30 +48,42 @@ public:
 	GamesEngineeringBase::Window* canvas = NULL;
 	Film* film = NULL;
 	MTRandom* samplers = NULL; // kept for source compatibility; the GPU uses a counter-based RNG
-	int numProcs = 0;          // number of GPUs driving this RayTracer (1)
+	int numProcs = 0;          // number of GPUs driving this RayTracer (RTBase/Renderer.h:52-55: every processor)
 	int tilesNumX = 0, tilesNumY = 0, totalTiles = 0;  // 32x32 tiles (RTBase/Renderer.h:40, 57-61)
 	std::vector<float> tileVariances, tileWeights;     // filled by adaptiveRender()
 	std::vector<uint32_t> tileSamples;                 // the counts sampleTileWithWeight derives (:649-653)
 
+	// Like the original (numProcs = sysInfo.dwNumberOfProcessors, RTBase/Renderer.h:52-55) this uses every
+	// processor of the machine: all visible GPUs as one device group (RTB_NUM_GPUS=n caps it).
 	void init(Scene* _scene, GamesEngineeringBase::Window* _canvas)
 	{
-		init(_scene, _canvas, 0);
+		int n = rtb_device_count();
+		if (const char* e = getenv("RTB_NUM_GPUS"))
+		{
+			int v = atoi(e);
+			if (v >= 1 && v < n) n = v;
+		}
+		init(_scene, _canvas, -1, n);
 	}
-	void init(Scene* _scene, GamesEngineeringBase::Window* _canvas, int device)
+	// one chosen device
+	void init(Scene* _scene, GamesEngineeringBase::Window* _canvas, int device) { init(_scene, _canvas, device, 1); }
+	void init(Scene* _scene, GamesEngineeringBase::Window* _canvas, int device, int nDevices)
 	{
 		scene = _scene;
 		canvas = _canvas;
 		film = new Film();
 		film->init((unsigned int)scene->camera.width, (unsigned int)scene->camera.height, new BoxFilter());
-		numProcs = 1;
-		samplers = new MTRandom[1];
+		numProcs = nDevices > 1 ? nDevices : 1;
+		samplers = new MTRandom[numProcs];
 		tilesNumX = (film->width + TILE_SIZE - 1) / TILE_SIZE;
 		tilesNumY = (film->height + TILE_SIZE - 1) / TILE_SIZE;
 		totalTiles = tilesNumX * tilesNumY;
 		tileVariances = std::vector<float>(totalTiles, 0.0f);
 		tileWeights = std::vector<float>(totalTiles, 0.0f);
 		tileSamples = std::vector<uint32_t>(totalTiles, 0u);
-		check(rtb_create(device, &ctx), "rtb_create");
+		if (device >= 0) check(rtb_create(device, &ctx), "rtb_create");
+		else check(rtb_create_multi(NULL, numProcs, &ctx), "rtb_create_multi");
+		numProcs = rtb_group_size(ctx);
 		rtb_default_params(&prm);
 		prm.max_depth = MAX_DEPTH;
 		prm.epsilon = EPSILON;

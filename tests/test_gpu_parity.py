@@ -906,6 +906,100 @@ def test_nccl_reduced_film_equals_the_single_gpu_film(rtb):
     assert "NCCL_FILM_OK %d" % world in out.stdout
 
 
+def test_device_group_of_one_is_a_plain_context(rtb):
+    rt = gpu_scene(rtb, "synthetic")
+    rt.render(3, 0)
+    a = rt.read_film().copy()
+    g = rtb.RayTracer([0])
+    assert g.group_info() == dict(devices=[0], p2p=[1], gathers_p2p=0, gathers_nccl=0)
+    g.init(rt.scene)
+    g.render(3, 0)
+    assert g.read_film().tobytes() == a.tobytes()
+    g.close()
+    with pytest.raises(rtb.RtbError):
+        rtb.RayTracer([0, 0])
+    with pytest.raises(rtb.RtbError):
+        rtb.RayTracer([0, 4096])
+
+
+def test_device_group_film_equals_the_single_gpu_film(rtb, monkeypatch):
+    """rtb_create_multi: one context, every GPU of the box (RayTracer::init's numProcs, Renderer.h:52-55).  The
+    film after the in-library read-out reduce — the peer-memory kernel, NCCL, and staged copies — must equal the
+    1-GPU film bit for bit for sample-sliced and tile-sliced calls, resumed renders, calls with fewer samples than
+    devices, and the pass-sharded light tracer / instant radiosity.  Needs >= 2 visible GPUs."""
+    n = rtb.lib().rtb_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    devs = list(range(min(n, 4)))
+    for name, spp in (("synthetic", 7), ("cornell-box", 5)):
+        one = gpu_scene(rtb, name)
+        one.render(spp, 0)
+        want = one.read_film().copy()
+        s1 = one.stats()
+        for mode in ("", "nccl", "staged"):
+            if mode:
+                monkeypatch.setenv("RTB_GROUP_REDUCE", mode)
+            else:
+                monkeypatch.delenv("RTB_GROUP_REDUCE", raising=False)
+            g = rtb.RayTracer(devs)
+            info = g.group_info()
+            assert info["devices"] == devs
+            g.init(one.scene)
+            g.render(spp, 0)
+            assert g.read_film().tobytes() == want.tobytes(), (name, mode)
+            assert g.getSPP() == spp
+            sg = g.stats()
+            for k in ("samples", "closest_rays", "shadow_rays"):
+                assert sg[k] == s1[k], (k, mode)
+            info = g.group_info()
+            if mode == "nccl":
+                assert info["gathers_nccl"] >= 1 and info["gathers_p2p"] == 0
+            elif mode == "" and all(info["p2p"]):
+                assert info["gathers_p2p"] >= 1 and info["gathers_nccl"] == 0
+            # resumed in uneven pieces, a piece with fewer samples than devices (tile split), a read-out in between
+            g.clear()
+            g.render(1, 0)
+            part = g.read_film().copy()
+            g.render(spp - 1, 1)
+            assert g.read_film().tobytes() == want.tobytes(), (name, mode, "resumed")
+            one.clear()
+            one.render(1, 0)
+            assert part.tobytes() == one.read_film().tobytes()
+            one.render(spp - 1, 1)
+            # the caller's own partition is refined, not replaced
+            g.set_params(partition=abi.PART_TILE, part_rank=0, part_world=1)
+            g.clear()
+            g.render(spp, 0)
+            assert g.read_film().tobytes() == want.tobytes(), (name, mode, "tiles")
+            acc = np.zeros_like(want, dtype=np.float64)
+            for r in range(3):
+                g.set_params(partition=abi.PART_SPP, part_rank=r, part_world=3)
+                g.clear()
+                g.render(spp, 0)
+                acc += g.read_film()
+            assert np.allclose(acc, want, rtol=1e-6, atol=1e-7)
+            g.close()
+    # the light-driven estimators shard their passes
+    s = abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box_256.rtbs"))
+    monkeypatch.delenv("RTB_GROUP_REDUCE", raising=False)
+    one, g = rtb.RayTracer(0), rtb.RayTracer(devs)
+    one.init(s)
+    g.init(s)
+    one.lightTracer(5, 0)
+    g.lightTracer(5, 0)
+    assert g.read_film().tobytes() == one.read_film().tobytes() and g.getSPP() == 5
+    one.clear()
+    g.clear()
+    one.instantRadiosity(3, 0)
+    g.instantRadiosity(3, 0)
+    assert g.read_film().tobytes() == one.read_film().tobytes() and g.getSPP() == 3
+    # write_film replaces the whole group's film
+    g.write_film(np.ones((256, 256, 3), np.float32))
+    assert np.allclose(g.read_film(), 1.0, atol=1e-9)
+    one.close()
+    g.close()
+
+
 def test_gaussian_filter_and_tonemap(rtb, oracle_mod):
     rt = gpu_scene(rtb, "synthetic")
     rt.render(4, 0)

@@ -1,0 +1,70 @@
+"""A/B probe for kernel work: renders a list of scenes and prints, per scene, Msamples/s, Mrays/s, per-stage
+ms per launch, box / triangle tests per ray and a hash of the fixed-point film (bit-identity across variants).
+  python tests/tools/perf_probe.py [--trav fast|wide|exact|cw] [--reuse 0|1] scene:spp[:max_depth] ...
+scene = a directory under scenes/_staged, or soupNN (2^NN random triangles, 3840x2160).
+RTB200_LIB selects an experimental build of the same ABI.  Test tool (not the product)."""
+import hashlib, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np
+import raytracingrenderer_b200 as rtb
+from raytracingrenderer_b200 import abi, host_api
+
+args = sys.argv[1:]
+trav, reuse, extra = abi.TRAV_FAST, 0, {}
+specs = []
+while args:
+    a = args.pop(0)
+    if a == "--trav":
+        trav = {"exact": 0, "fast": 1, "wide": 2, "cw": 3}[args.pop(0)]
+    elif a == "--reuse":
+        reuse = int(args.pop(0))
+    elif a == "--set":
+        k, v = args.pop(0).split("=")
+        extra[k] = int(v)
+    else:
+        specs.append(a)
+out = {}
+for spec in specs:
+    parts = spec.split(":")
+    name, spp = parts[0], int(parts[1]) if len(parts) > 1 else 16
+    if name.startswith("soup"):
+        s, _ = host_api.build_soup(1 << int(name[4:]), 3840, 2160)
+        depth = 0
+    else:
+        s = host_api.load_scene(os.path.join("scenes", "_staged", name))
+        depth = 4
+    if len(parts) > 2:
+        depth = int(parts[2])
+    rt = rtb.RayTracer(0)
+    t0 = time.time()
+    rt.init(s)
+    up = time.time() - t0
+    rt.set_params(traversal=trav, primary_reuse=reuse, max_depth=depth, **extra)
+    rt.render(min(spp, 4), 0)
+    rt.synchronize()
+    best = None
+    for _ in range(2):
+        rt.clear()
+        t0 = time.time()
+        rt.render(spp, 0)
+        rt.synchronize()
+        dt = time.time() - t0
+        st = rt.stats()
+        if best is None or dt < best[0]:
+            best = (dt, st)
+    dt, st = best
+    film = rt.read_film()
+    rays = st["closest_rays"] + st["shadow_rays"]
+    ti = max(st["timed_iterations"], 1)
+    r = dict(msamples_s=st["samples"] / dt / 1e6, mrays_s=rays / dt / 1e6, seconds=dt, upload_s=up,
+             extend_ms=st["extend_ms"] / ti, shade_ms=st["shade_ms"] / ti, shadow_ms=st["shadow_ms"] / ti,
+             box_per_closest=st["box_tests"] / max(st["closest_rays"], 1), tri_per_closest=st["tri_tests"] / max(st["closest_rays"], 1),
+             box_per_shadow=st["shadow_box_tests"] / max(st["shadow_rays"], 1), tri_per_shadow=st["shadow_tri_tests"] / max(st["shadow_rays"], 1),
+             iterations=st["iterations"], film_sha=hashlib.sha256(film.tobytes()).hexdigest()[:12])
+    out[spec] = r
+    print("%-24s %8.1f Msamples/s %8.1f Mrays/s | ms/launch extend %.3f shade %.3f shadow %.3f | box/closest %.1f tri %.2f box/shadow %.1f tri %.2f | upload %.2fs film %s"
+          % (spec, r["msamples_s"], r["mrays_s"], r["extend_ms"], r["shade_ms"], r["shadow_ms"], r["box_per_closest"], r["tri_per_closest"],
+             r["box_per_shadow"], r["tri_per_shadow"], up, r["film_sha"]), flush=True)
+    rt.close()
+if os.environ.get("PROBE_JSON"):
+    json.dump(out, open(os.environ["PROBE_JSON"], "w"), indent=1)
