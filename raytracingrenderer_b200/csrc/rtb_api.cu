@@ -106,6 +106,12 @@ struct rtb_ctx
 	cudaStream_t shadowStreams[RTB_MAX_POOLS] = {};
 	cudaEvent_t evShaded[RTB_MAX_POOLS] = {}, evShadowed[RTB_MAX_POOLS] = {};
 	bool shadowAsync = true;
+	// ray binning between the stages (k_sort_*): -1 = decide per scene (rtb_upload_scene), 0 / 1 = forced (RTB_SORT_SHADOW / RTB_SORT_EXTEND)
+	int sortShadow = -1, sortExtend = -1;
+	bool sortShadowAuto = false, sortExtendAuto = false;
+	uint32_t* wfPerm = nullptr; // [shadow queue entries + slots]
+	size_t wfPermEntries = 0;
+	uint32_t* wfSortWork = nullptr; // per sub-pool: hist[2][4096], cursor[2][4096]
 	unsigned lightGrid = 0;
 	void* vpls = nullptr; // rtb_render_ir: n_paths segments of RTB_VPL_SEGMENT VPLs
 	uint32_t* vplCounts = nullptr;
@@ -168,6 +174,9 @@ void freeScene(rtb_ctx* ctx)
 	if (ctx->wfGlobal) cudaFree(ctx->wfGlobal);
 	if (ctx->wfTiles) cudaFree(ctx->wfTiles);
 	if (ctx->wfPrimary) cudaFree(ctx->wfPrimary);
+	if (ctx->wfPerm) cudaFree(ctx->wfPerm);
+	if (ctx->wfSortWork) cudaFree(ctx->wfSortWork);
+	ctx->wfPerm = nullptr, ctx->wfPermEntries = 0, ctx->wfSortWork = nullptr;
 	if (ctx->vpls) cudaFree(ctx->vpls);
 	if (ctx->vplCounts) cudaFree(ctx->vplCounts);
 	ctx->vpls = nullptr, ctx->vplCounts = nullptr, ctx->vplPaths = 0;
@@ -423,6 +432,24 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		CK(cudaMalloc(&ctx->wfState, need));
 		ctx->wfStateBytes = need;
 	}
+	if (const char* e = getenv("RTB_SORT_SHADOW")) ctx->sortShadow = atoi(e);
+	if (const char* e = getenv("RTB_SORT_EXTEND")) ctx->sortExtend = atoi(e);
+	const bool sortSh = ctx->sortShadow < 0 ? ctx->sortShadowAuto : ctx->sortShadow != 0;
+	const bool sortEx = ctx->sortExtend < 0 ? ctx->sortExtendAuto : ctx->sortExtend != 0;
+	if (sortSh || sortEx)
+	{
+		size_t entries = (size_t)nSlotsAlloc * (F + 1);
+		if (entries > ctx->wfPermEntries)
+		{
+			CK(cudaStreamSynchronize(ctx->stream));
+			if (ctx->wfPerm) cudaFree(ctx->wfPerm);
+			ctx->wfPerm = nullptr, ctx->wfPermEntries = 0;
+			CK(cudaMalloc((void**)&ctx->wfPerm, entries * sizeof(uint32_t)));
+			ctx->wfPermEntries = entries;
+		}
+		if (!ctx->wfSortWork) CK(cudaMalloc((void**)&ctx->wfSortWork, (size_t)RTB_MAX_POOLS * 4 * WF_SORT_BUCKETS * sizeof(uint32_t)));
+		CK(cudaMemsetAsync(ctx->wfSortWork, 0, (size_t)RTB_MAX_POOLS * 4 * WF_SORT_BUCKETS * sizeof(uint32_t), ctx->stream));
+	}
 	if (!ctx->wfGlobal) CK(cudaMalloc((void**)&ctx->wfGlobal, sizeof(WfGlobal)));
 	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, (1 + RTB_MAX_POOLS) * sizeof(unsigned long long)));
 	uint32_t vertices = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_PATH_MIS) ? (uint32_t)P.max_depth + 2u : 1u;
@@ -471,6 +498,10 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		a.tileList = plan ? ctx->wfTilesAdaptive : ctx->wfTiles;
 		a.tileJobBase = plan ? ctx->adaptJobBase : nullptr;
 		a.nTiles32 = plan ? plan->nTiles32 : 0u;
+		a.shPerm = sortSh ? ctx->wfPerm + off * F : nullptr;
+		a.exPerm = sortEx ? ctx->wfPerm + (size_t)nSlotsAlloc * F + off : nullptr;
+		a.sortHist = ctx->wfSortWork ? ctx->wfSortWork + (size_t)k * 4 * WF_SORT_BUCKETS : nullptr;
+		a.sortCursor = ctx->wfSortWork ? ctx->wfSortWork + (size_t)k * 4 * WF_SORT_BUCKETS + 2 * WF_SORT_BUCKETS : nullptr;
 		a.primary = P.primary_reuse ? ctx->wfPrimary : nullptr;
 		a.primaryPasses = (uint32_t)ctx->primaryPasses;
 		a.counters = ctx->counters;
@@ -490,6 +521,8 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	}
 	unsigned gridExtend = (unsigned)(ctx->smCount * extendBlocks);
 	unsigned maxBlocks = (unsigned)ctx->smCount * 16u;
+	unsigned gridSort = (unsigned)(((size_t)perPool * F + WF_SORT_CHUNK - 1) / WF_SORT_CHUNK);
+	if (gridSort > (unsigned)ctx->smCount * 4u) gridSort = (unsigned)ctx->smCount * 4u;
 	unsigned gridSlots = (perPool + 127) / 128;
 	if (gridSlots > maxBlocks) gridSlots = maxBlocks;
 	if (gridExtend > (perPool + 127) / 128) gridExtend = (perPool + 127) / 128;
@@ -534,6 +567,13 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 					for (int e = 0; e < 4; e++) se.e[e] = getEvent(ctx);
 					cudaEventRecord(se.e[0], st);
 				}
+				if (sortEx && !ctx->simpleExtend && ti != RTB_TRAV_EXACT)
+				{
+					k_sort_count<1><<<gridSort, 256, 0, st>>>(ctx->S, A[k], it);
+					k_sort_scan<1><<<1, 1024, 0, st>>>(A[k], it);
+					k_sort_scatter<1><<<gridSort, 256, 0, st>>>(ctx->S, A[k], it);
+					ctx->launches += 3;
+				}
 				if (ctx->simpleExtend)
 				{
 					RTB_TRAV_SWITCH(ti, k_wf_extend_simple<TR><<<(perPool + 127) / 128, 128, 0, st>>>(ctx->S, A[k], it));
@@ -570,6 +610,13 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 						sst = ctx->shadowStreams[k];
 						cudaEventRecord(ctx->evShaded[k], st);
 						cudaStreamWaitEvent(sst, ctx->evShaded[k], 0);
+					}
+					if (sortSh)
+					{
+						k_sort_count<0><<<gridSort, 256, 0, sst>>>(ctx->S, A[k], it);
+						k_sort_scan<0><<<1, 1024, 0, sst>>>(A[k], it);
+						k_sort_scatter<0><<<gridSort, 256, 0, sst>>>(ctx->S, A[k], it);
+						ctx->launches += 3;
 					}
 					if (P.integrator == RTB_INT_PATH_MIS)
 					{
@@ -979,6 +1026,16 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	S.bg_type = sc->background_type;
 	memcpy(S.bg_colour, sc->background_colour, sizeof(S.bg_colour));
 	S.bg_tex = sc->background_tex;
+	S.area_lights_only = sc->n_lights > 0 ? 1u : 0u;
+	for (uint32_t i = 0; i < sc->n_lights; i++)
+		if (sc->lights[i].type != RTB_LIGHT_AREA) S.area_lights_only = 0u;
+	for (int k = 0; k < 3; k++)
+	{
+		float lo = sc->n_ref_nodes ? sc->ref_nodes[0].bmin[k] : 0.0f, hi = sc->n_ref_nodes ? sc->ref_nodes[0].bmax[k] : 1.0f;
+		float ext = hi - lo;
+		S.bmin[k] = lo;
+		S.bscale[k] = (ext > 0.0f && ext < FLT_MAX) ? 16.0f / ext : 0.0f;
+	}
 	// env sampling tables when the environment map is a light
 	if (!ps.marginal.empty())
 	{

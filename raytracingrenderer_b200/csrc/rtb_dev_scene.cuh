@@ -46,6 +46,10 @@ struct DevScene
 	float bg_colour[3];
 	int32_t bg_tex;
 	int32_t env_w, env_h;
+	// scene bounds (the reference tree's root box) for the ray-binning keys of rtb_wavefront.cuh:
+	// cell = (p - bmin) * bscale, bscale = 16 / extent
+	float bmin[3], bscale[3];
+	uint32_t area_lights_only; // every light is an AreaLight: shadow rays end on a few triangles
 };
 
 struct HitD

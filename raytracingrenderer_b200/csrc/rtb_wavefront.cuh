@@ -52,6 +52,8 @@ struct WfCtrl
 	unsigned int alive;      // slots alive after k_wf_shade of this iteration
 	unsigned int extendHead; // next unclaimed chunk of slots (k_wf_extend)
 	unsigned int shadowHead; // next unclaimed chunk of shadow rays (k_wf_shadow)
+	unsigned int nExtend;    // rays in the binned extend order of this iteration (k_sort_scan)
+	unsigned int pad_[3];
 };
 
 struct WfGlobal
@@ -76,6 +78,11 @@ struct WfArgs
 	const uint32_t* tileList; // owned 8x4-pixel tiles: (tile row << 16) | tile column
 	const unsigned long long* tileJobBase; // adaptive plan: first job of every 32x32 tile (+ total), or NULL
 	uint32_t nTiles32;                     //                number of 32x32 tiles
+	// ray binning (k_sort_*): a permutation of the shadow queue / of the live slots in bucket order, or NULL
+	uint32_t* shPerm;
+	uint32_t* exPerm;
+	uint32_t* sortHist;   // [2][WF_SORT_BUCKETS]: shadow, extend
+	uint32_t* sortCursor; // [2][WF_SORT_BUCKETS]
 	const float4* primary;    // per-pixel primary hit (bits(id), t, alpha, beta), or NULL: trace every camera ray
 	uint32_t primaryPasses;   // fresh primary vertices a shade thread may take on per launch
 	unsigned long long* counters;
@@ -311,6 +318,148 @@ __global__ void __launch_bounds__(128) k_wf_primary(const __grid_constant__ DevS
 	flushTally(tl, counters);
 }
 
+// ---------------------------------------------------------------------------------------
+// Ray binning between the stages ("warp-level ray compaction" taken one step further: not only are dead
+// lanes squeezed out, the survivors are put next to rays that will walk the same part of the tree).
+// profiles/r01_v8_final_summary.md: one thread per queued shadow ray keeps 4.8 of 32 lanes busy, because the
+// rays of a warp share nothing — neighbouring slots hold unrelated paths once the pool has been refilled a few
+// times.  A counting sort by a 12-bit key (Morton cell of the origin in a 16^3 grid over the scene box for
+// scenes lit by a few emitter triangles — origin cell + common target = same way through the tree; 8^3 cells +
+// direction octant otherwise) makes a warp's rays start together and head the same way.  Three small kernels:
+// block-local shared-memory histograms merged into a global one; a 4096-entry scan; a scatter that re-histograms
+// each 4096-ray chunk in shared memory, reserves the chunk's ranges with ONE global atomic per non-empty bucket
+// and writes ray indices (the rays themselves stay where they are: 4 B moved per ray, not 48).  The order inside
+// a bucket is arbitrary — nothing downstream depends on it (the film is an integer sum).
+// ---------------------------------------------------------------------------------------
+#define WF_SORT_BUCKETS 4096u
+#define WF_SORT_CHUNK 4096u /* rays per block and round of k_sort_scatter: 256 threads x 16 */
+
+RTB_DEV uint32_t wfSpread3(uint32_t x) // 4 bits -> every third bit
+{
+	x = (x | (x << 8)) & 0x0300F00Fu;
+	x = (x | (x << 4)) & 0x030C30C3u;
+	x = (x | (x << 2)) & 0x09249249u;
+	return x;
+}
+RTB_DEV uint32_t wfSortKey(const DevScene& S, float ox, float oy, float oz, float dx, float dy, float dz)
+{
+	int cx = (int)((ox - S.bmin[0]) * S.bscale[0]), cy = (int)((oy - S.bmin[1]) * S.bscale[1]), cz = (int)((oz - S.bmin[2]) * S.bscale[2]);
+	cx = min(max(cx, 0), 15), cy = min(max(cy, 0), 15), cz = min(max(cz, 0), 15);
+	if (S.area_lights_only) return wfSpread3((uint32_t)cx) | (wfSpread3((uint32_t)cy) << 1) | (wfSpread3((uint32_t)cz) << 2);
+	uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+	uint32_t m = wfSpread3((uint32_t)cx >> 1) | (wfSpread3((uint32_t)cy >> 1) << 1) | (wfSpread3((uint32_t)cz >> 1) << 2);
+	return (oct << 9) | m;
+}
+
+// WHAT 0: the shadow queue of iteration `iter`; WHAT 1: the live, not yet intersected slots
+template <int WHAT>
+RTB_DEV bool wfSortItem(const DevScene& S, const WfArgs& A, uint32_t i, uint32_t& key)
+{
+	float4 o, d;
+	if (WHAT == 0) o = A.shO[i], d = A.shD[i];
+	else
+	{
+		d = A.rayD[i];
+		if ((__float_as_uint(d.w) & (WF_ALIVE | WF_PREHIT)) != WF_ALIVE) return false;
+		o = A.rayO[i];
+	}
+	key = wfSortKey(S, o.x, o.y, o.z, d.x, d.y, d.z);
+	return true;
+}
+
+template <int WHAT>
+__global__ void __launch_bounds__(256) k_sort_count(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
+{
+	__shared__ uint32_t h[WF_SORT_BUCKETS];
+	if (WHAT == 1 && iter > 0 && A.ctrl[iter - 1].alive == 0) return;
+	const uint32_t n = WHAT == 0 ? A.ctrl[iter].nShadow : A.nSlots;
+	if (blockIdx.x * WF_SORT_CHUNK >= n) return;
+	for (uint32_t k = threadIdx.x; k < WF_SORT_BUCKETS; k += 256u) h[k] = 0u;
+	__syncthreads();
+	for (uint32_t base = blockIdx.x * WF_SORT_CHUNK; base < n; base += gridDim.x * WF_SORT_CHUNK)
+		for (uint32_t j = 0; j < WF_SORT_CHUNK / 256u; j++)
+		{
+			uint32_t i = base + j * 256u + threadIdx.x, key;
+			if (i < n && wfSortItem<WHAT>(S, A, i, key)) atomicAdd(&h[key], 1u);
+		}
+	__syncthreads();
+	uint32_t* hist = A.sortHist + WHAT * WF_SORT_BUCKETS;
+	for (uint32_t k = threadIdx.x; k < WF_SORT_BUCKETS; k += 256u)
+		if (h[k]) atomicAdd(&hist[k], h[k]);
+}
+
+// exclusive scan of the 4096 bucket counts -> cursors; clears the histogram for the next iteration
+template <int WHAT>
+__global__ void __launch_bounds__(1024) k_sort_scan(const __grid_constant__ WfArgs A, uint32_t iter)
+{
+	__shared__ uint32_t warpSum[32];
+	uint32_t* hist = A.sortHist + WHAT * WF_SORT_BUCKETS;
+	uint32_t* cursor = A.sortCursor + WHAT * WF_SORT_BUCKETS;
+	uint32_t t = threadIdx.x, v[4], s = 0;
+	for (int k = 0; k < 4; k++) v[k] = hist[t * 4 + k], s += v[k];
+	uint32_t incl = s;
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if ((t & 31u) >= (uint32_t)o) incl += x;
+	}
+	if ((t & 31u) == 31u) warpSum[t >> 5] = incl;
+	__syncthreads();
+	if (t < 32u)
+	{
+		uint32_t w = warpSum[t], wi = w;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t x = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+			if (t >= (uint32_t)o) wi += x;
+		}
+		warpSum[t] = wi - w;
+		if (WHAT == 1 && t == 31u) A.ctrl[iter].nExtend = wi;
+	}
+	__syncthreads();
+	uint32_t run = warpSum[t >> 5] + incl - s;
+	for (int k = 0; k < 4; k++)
+	{
+		cursor[t * 4 + k] = run;
+		run += v[k];
+		hist[t * 4 + k] = 0u;
+	}
+}
+
+template <int WHAT>
+__global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
+{
+	__shared__ uint32_t h[WF_SORT_BUCKETS];
+	if (WHAT == 1 && iter > 0 && A.ctrl[iter - 1].alive == 0) return;
+	const uint32_t n = WHAT == 0 ? A.ctrl[iter].nShadow : A.nSlots;
+	uint32_t* cursor = A.sortCursor + WHAT * WF_SORT_BUCKETS;
+	uint32_t* perm = WHAT == 0 ? A.shPerm : A.exPerm;
+	for (uint32_t base = blockIdx.x * WF_SORT_CHUNK; base < n; base += gridDim.x * WF_SORT_CHUNK)
+	{
+		for (uint32_t k = threadIdx.x; k < WF_SORT_BUCKETS; k += 256u) h[k] = 0u;
+		__syncthreads();
+		uint32_t kr[WF_SORT_CHUNK / 256u]; // key << 16 | rank inside the chunk's bucket (rank < 4096)
+#pragma unroll
+		for (uint32_t j = 0; j < WF_SORT_CHUNK / 256u; j++)
+		{
+			uint32_t i = base + j * 256u + threadIdx.x, key;
+			kr[j] = 0xFFFFFFFFu;
+			if (i < n && wfSortItem<WHAT>(S, A, i, key)) kr[j] = (key << 16) | atomicAdd(&h[key], 1u);
+		}
+		__syncthreads();
+		for (uint32_t k = threadIdx.x; k < WF_SORT_BUCKETS; k += 256u)
+		{
+			uint32_t c = h[k];
+			if (c) h[k] = atomicAdd(&cursor[k], c);
+		}
+		__syncthreads();
+#pragma unroll
+		for (uint32_t j = 0; j < WF_SORT_CHUNK / 256u; j++)
+			if (kr[j] != 0xFFFFFFFFu) perm[h[kr[j] >> 16] + (kr[j] & 0xFFFFu)] = base + j * 256u + threadIdx.x;
+		__syncthreads();
+	}
+}
+
 __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A)
 {
 	uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,6 +513,8 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 	}
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t ltMask = (1u << lane) - 1u;
+	// binned order (k_sort_*): only the live rays, neighbours start in the same cell and head the same way
+	const uint32_t nItems = A.exPerm ? A.ctrl[iter].nExtend : A.nSlots;
 	// work is claimed in chunks of WF_CHUNK consecutive slots (one atomic per chunk and warp)
 	uint32_t cursor = 0, end = 0;
 	bool exhausted = false;
@@ -409,11 +560,11 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 			uint32_t c = 0;
 			if (lane == 0) c = atomicAdd(&A.ctrl[iter].extendHead, (unsigned)WF_CHUNK);
 			c = __shfl_sync(0xFFFFFFFFu, c, 0);
-			if (c >= A.nSlots) exhausted = true;
+			if (c >= nItems) exhausted = true;
 			else
 			{
 				cursor = c;
-				end = (c + WF_CHUNK < A.nSlots) ? c + WF_CHUNK : A.nSlots;
+				end = (c + WF_CHUNK < nItems) ? c + WF_CHUNK : nItems;
 			}
 		}
 		if (want && cursor < end)
@@ -421,9 +572,10 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 			uint32_t idx = cursor + __popc(want & ltMask);
 			if (!pre && idx < end)
 			{
-				preO = A.rayO[idx];
-				preD = A.rayD[idx];
-				preSlot = idx;
+				const uint32_t sl = A.exPerm ? A.exPerm[idx] : idx;
+				preO = A.rayO[sl];
+				preD = A.rayD[sl];
+				preSlot = sl;
 				pre = true;
 			}
 			cursor += __popc(want);
@@ -506,8 +658,9 @@ __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevSc
 	const rtb_params& P = A.P;
 	const uint32_t n = A.ctrl[iter].nShadow;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0};
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
 	{
+		const uint32_t i = A.shPerm ? A.shPerm[q] : q; // binned order (k_sort_*): a warp's rays start together and head the same way
 		float4 o = A.shO[i], d = A.shD[i];
 		RayD r = mkRay(mk(o), mk(d));
 		float maxT = o.w;
@@ -529,8 +682,9 @@ __global__ void __launch_bounds__(128) k_wf_mis(const __grid_constant__ DevScene
 	const rtb_params& P = A.P;
 	const uint32_t n = A.ctrl[iter].nShadow;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0};
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
 	{
+		const uint32_t i = A.shPerm ? A.shPerm[q] : q;
 		float4 o = A.shO[i], d = A.shD[i], c = A.shC[i];
 		uint32_t flags = __float_as_uint(c.w), pixel = __float_as_uint(d.w);
 		if (flags & 1u)

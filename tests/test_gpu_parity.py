@@ -949,8 +949,10 @@ def test_device_group_film_equals_the_single_gpu_film(rtb, monkeypatch):
             assert g.read_film().tobytes() == want.tobytes(), (name, mode)
             assert g.getSPP() == spp
             sg = g.stats()
-            for k in ("samples", "closest_rays", "shadow_rays"):
+            for k in ("samples", "shadow_rays"):
                 assert sg[k] == s1[k], (k, mode)
+            # every member traces its own primary-hit table (one camera ray per pixel and render call)
+            assert sg["closest_rays"] == s1["closest_rays"] + (len(devs) - 1) * one.width * one.height
             info = g.group_info()
             if mode == "nccl":
                 assert info["gathers_nccl"] >= 1 and info["gathers_p2p"] == 0
