@@ -2,7 +2,7 @@
 """bench.py — throughput of the path-tracing hot path (RayTracer::render and below,
 RTBase/Renderer.h:328-473, 795-885) on N B200s, and of the reference CPU renderer beside it.
 
-Workload (BASELINE.json configs[1]): materialball, 1280x720, 256 spp, MAX_DEPTH 4, rendered
+Headline workload (BASELINE.json configs[1]): materialball, 1280x720, 256 spp, MAX_DEPTH 4, rendered
 once per BSDF class the scene format can express — the 7 per-instance overrides diffuse,
 conductor, glass, dielectric, orennayar, plastic, layered.  One STEP = those 7
 renders (7 x 921 600 px x 256 spp = 1.65 G samples per GPU).  N GPUs: weak scaling — every rank
@@ -10,11 +10,19 @@ renders the same 7 films with its own 256 disjoint sample indices (spp slice, RN
 global sample index), then the films are summed to rank 0 with NCCL (the path has no other
 exchange step).
 
-  value : Msamples/s, scenes resident in HBM, device-timed (CUDA events), max over ranks.
-  e2e   : the same through the C ABI with HOST buffers: per render rtb_update_camera (host
-          struct -> device), rtb_clear, rtb_render, rtb_read_film into pinned host memory.
+  value     : Msamples/s, scenes resident in HBM, device-timed (CUDA events), max over ranks.
+  e2e       : the same through the C ABI with HOST buffers: per render rtb_update_camera (host
+              struct -> device), rtb_clear, rtb_render, rtb_read_film into pinned host memory.
+  roofline  : the dominant stage kernel, timed in a SERIALISED pass (one sub-pool, one stream: a launch's
+              event-to-event time is then the kernel's own), against the FP32 issue peak — every bundled
+              scene is L2-resident, SURVEY 8d — with canonical flops per ray (profiles/canonical_counts.json).
+  per_scene : (N = 1) every BASELINE config — cornell-box 64 spp, materialball x 7 256 spp, MaterialsScene 512,
+              coffee and bathroom 1024, soup 2^20 / 2^22 / 2^24 at 4 spp — with Msamples/s, Mrays/s and the
+              image error against the CPU reference renderer at a stated CPU spp budget (mean
+              luminance, 8x8-block RMSE against the reference's own noise floor, relMSE).
+  strong    : coffee + bathroom at 1024 spp IN TOTAL, sample-sliced over the N GPUs (BASELINE config 4).
   --impl reference : the UNMODIFIED reference renderer (oracle/_ref, RayTracer::render) on all
-          host threads, same scenes, a bounded spp sample per step.
+              host threads, same scenes, a bounded spp sample per step.
 
 Prints ONE JSON line on rank 0.
 """
@@ -32,6 +40,16 @@ sys.path.insert(0, ROOT)
 VARIANTS = ["diffuse", "conductor", "glass", "dielectric", "orennayar", "plastic", "layered"]
 STAGED = os.path.join(ROOT, "scenes", "_staged")
 METRIC = "Msamples/s (path-traced pixel samples per second; Mrays/s alongside)"
+
+# BASELINE.json configs: (key, staged scene directories, spp, CPU spp per half-buffer, max_depth)
+CONFIGS = [
+    ("cornell-box", ["cornell-box"], 64, 8, 4),
+    ("materialball7", ["materialball_" + v for v in VARIANTS], 256, 2, 4),
+    ("MaterialsScene", ["MaterialsScene"], 512, 8, 4),
+    ("coffee", ["coffee"], 1024, 8, 4),
+    ("bathroom", ["bathroom"], 1024, 1, 4),
+]
+SOUPS = [20, 22, 24]
 
 
 def load_workload(scene, log):
@@ -109,6 +127,65 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def canonical_counts():
+    cp = os.path.join(ROOT, "profiles", "canonical_counts.json")
+    return json.load(open(cp)) if os.path.isfile(cp) else {}
+
+
+# ------------------------------------------------------------------------------------------
+# image error against the CPU reference
+def block_mean(img, b=8):
+    h, w, c = img.shape
+    return img[: h // b * b, : w // b * b].reshape(h // b, b, w // b, b, c).mean(axis=(1, 3))
+
+
+def image_error(gpu_mean, n_gpu, half_a, half_b, m_half):
+    """gpu_mean: the GPU's mean image of n_gpu spp; half_a / half_b: two INDEPENDENT CPU mean images of m_half spp
+    each (their difference is the reference estimator's own noise).  Returns the gates of SURVEY A.7."""
+    import numpy as np
+    lum = np.array([0.2126, 0.7152, 0.0722])
+    ref = 0.5 * (half_a + half_b)
+    m = 2 * m_half
+    la, lr = float((gpu_mean @ lum).mean()), float((ref @ lum).mean())
+    ba, bb, bg, br = (block_mean(x) for x in (half_a, half_b, gpu_mean, ref))
+    sigma1 = float(np.sqrt(np.mean((ba - bb) ** 2) / 2 * m_half))         # block noise of ONE sample per pixel
+    expect = sigma1 * float(np.sqrt(1.0 / n_gpu + 1.0 / m))
+    rmse_b = float(np.sqrt(np.mean((bg - br) ** 2)))
+    d = gpu_mean.astype(np.float64) - ref
+    noise_mean = abs(float(((half_a - half_b) @ lum).mean())) / max(lr, 1e-12)
+    return {
+        "mean_luminance": la, "mean_luminance_cpu": lr, "mean_luminance_rel_err": abs(la - lr) / max(lr, 1e-12),
+        "mean_luminance_cpu_halves_rel_diff": noise_mean,
+        "block8_rmse": rmse_b, "block8_rmse_expected_from_noise": expect, "block8_rmse_over_expected": rmse_b / max(expect, 1e-30),
+        "rmse": float(np.sqrt(np.mean(d ** 2))), "relmse": float(np.mean(d ** 2 / (ref.astype(np.float64) ** 2 + 1e-2))),
+        "gate_mean_0p5pct_or_3x_cpu_noise": bool(abs(la - lr) / max(lr, 1e-12) < max(0.005, 3 * noise_mean)),
+        "gate_block_rmse_3x_noise": bool(rmse_b < 3 * expect),
+        "gpu_spp": n_gpu, "cpu_spp": m,
+    }
+
+
+def cpu_reference_halves(scene_dir_name, flat, m_half, max_depth, log):
+    """Two independent CPU mean images of m_half spp + the CPU's Msamples/s.  The unmodified reference
+    (oracle/_ref: RayTracer::render on all host threads) when it travelled to this box, else the C port."""
+    import numpy as np
+    from oracle import ref
+    variant = "" if max_depth == 4 else "_d0"
+    if ref.available(variant) and scene_dir_name and ref.have_scene(scene_dir_name):
+        rs = ref.RefScene(scene_dir_name, variant)
+        a, _, s1 = rs.render(m_half, 0, fresh=True)
+        b2, _, s2 = rs.render(m_half, 0, fresh=False)
+        px = rs.width * rs.height
+        return a / m_half, (b2 - a) / m_half, {"kind": "reference", "cores": rs.hw_threads, "msamples_s": px * 2 * m_half / (s1 + s2) / 1e6}
+    from oracle import port
+    o = port.Oracle(flat, max_depth=max_depth)
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    a, _ = o.render(m_half, 1 << 20, threads=threads)          # sample indices the GPU run does not use
+    b, _ = o.render(m_half, 1 << 21, threads=threads)
+    dt = time.perf_counter() - t0
+    return a / m_half, b / m_half, {"kind": "port", "cores": threads, "msamples_s": o.width * o.height * 2 * m_half / dt / 1e6}
 
 
 # ------------------------------------------------------------------------------------------
@@ -212,11 +289,220 @@ def cpu_baseline(args, log):
             "sample": "%s at %d spp through oracle/rtb_oracle.c" % (name, spp)}
 
 
+# ------------------------------------------------------------------------------------------
+def timed_render(rts, spp, torch, repeats=1):
+    """Device time (CUDA events on the contexts' stream) of clear + render of every context; best of `repeats`."""
+    best = None
+    for _ in range(repeats):
+        for rt in rts:
+            rt.clear()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for rt in rts:
+            rt.render(spp, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if best is None or ms < best:
+            best = ms
+    return best
+
+
+def stats_sum(rts):
+    st = [rt.stats() for rt in rts]
+    keys = ("samples", "closest_rays", "shadow_rays", "box_tests", "tri_tests", "shadow_box_tests", "shadow_tri_tests",
+            "iterations", "timed_iterations", "extend_ms", "shade_ms", "shadow_ms", "render_ms", "kernel_launches")
+    return {k: sum(s[k] for s in st) for k in keys}, st
+
+
+def serial_stage_pass(flats, keys, spp, depth, canon, rtb, abi, torch, stream, sm_max):
+    """One render of every scene with ONE sub-pool on ONE stream (RTB_POOLS=1, RTB_SHADOW_ASYNC=0): the stage kernels
+    run back to back, so the CUDA-event time around a launch is that kernel's own duration (in the production
+    schedule six streams overlap and an event pair also measures the neighbours).  -> roofline record."""
+    old = {k: os.environ.get(k) for k in ("RTB_POOLS", "RTB_SHADOW_ASYNC")}
+    os.environ["RTB_POOLS"], os.environ["RTB_SHADOW_ASYNC"] = "1", "0"
+    try:
+        rts = []
+        for _, s in flats:
+            rt = rtb.RayTracer(torch.cuda.current_device())
+            rt.set_stream(stream.cuda_stream)
+            rt.init(s)
+            rt.set_params(traversal=abi.TRAV_FAST, max_depth=depth, primary_reuse=0)
+            rts.append(rt)
+        for rt in rts:
+            rt.render(min(spp, 8), 0)
+        ms = timed_render(rts, spp, torch)
+        tot, st = stats_sum(rts)
+        for rt in rts:
+            rt.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    timed = max(tot["timed_iterations"], 1)
+    iters = max(tot["iterations"], 1)
+    stage = {k: tot[k + "_ms"] / timed for k in ("extend", "shade", "shadow")}          # own duration per launch
+    # canonical work of the rays this pass traced (SURVEY 8d): 24 flops per box test, 60 per triangle test
+    if all(k in canon for k in keys):
+        f_ext = sum(s_["closest_rays"] * canon[k]["closest_flops_per_ray"] for s_, k in zip(st, keys))
+        f_sha = sum(s_["shadow_rays"] * canon[k]["shadow_flops_per_ray"] for s_, k in zip(st, keys))
+        b_ext = sum(s_["closest_rays"] * canon[k]["closest_bytes_per_ray"] for s_, k in zip(st, keys))
+        b_sha = sum(s_["shadow_rays"] * canon[k]["shadow_bytes_per_ray"] for s_, k in zip(st, keys))
+        src = "canonical traversal of the reference tree (profiles/canonical_counts.json) x the rays traced"
+    else:
+        f_ext = 24.0 * tot["box_tests"] + 60.0 * tot["tri_tests"]
+        f_sha = 24.0 * tot["shadow_box_tests"] + 60.0 * tot["shadow_tri_tests"]
+        b_ext = 32.0 * tot["box_tests"] + 64.0 * tot["tri_tests"] + 48.0 * tot["closest_rays"]
+        b_sha = 32.0 * tot["shadow_box_tests"] + 64.0 * tot["shadow_tri_tests"] + 48.0 * tot["shadow_rays"]
+        src = "this run's own traversal counters (scene not in profiles/canonical_counts.json)"
+    flops = {"extend": f_ext / iters, "shadow": f_sha / iters, "shade": 150.0 * tot["closest_rays"] / iters}
+    byts = {"extend": b_ext / iters, "shadow": b_sha / iters, "shade": (64.0 + 48.0 + 24.0) * tot["closest_rays"] / iters}
+    dom = max(stage, key=lambda k: stage[k])
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    ach = flops[dom] / (stage[dom] / 1e3) / 1e12 if stage[dom] > 0 else 0.0
+    share = stage[dom] * iters / ms if ms > 0 else 0.0
+    return {
+        "bound": "fp32-issue", "kernel": "k_wf_%s" % dom, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+        "traffic": None, "peak_source": "148 SMs x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json)" % sm_max,
+        "kernel_ms_per_launch": stage[dom], "launches": iters, "kernel_share_of_step": share,
+        "serialised_step_ms": ms, "stage_ms_per_launch": stage, "alg_flops_per_launch": flops[dom], "alg_bytes_per_launch": byts[dom],
+        "alg_source": src,
+        "whole_step": {"achieved_tflops": (f_ext + f_sha) / (ms / 1e3) / 1e12, "frac": (f_ext + f_sha) / (ms / 1e3) / 1e12 / fp32_peak},
+        "how": "serialised pass (one sub-pool, one stream): kernel_ms_per_launch x launches = %.1f ms <= the pass's %.1f ms; "
+               "scene + slot state are L1/L2 traffic, so the bound is FP32 issue, not HBM (SURVEY 8d)" % (stage[dom] * iters, ms),
+    }, tot
+
+
+def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm):
+    """(N = 1) every BASELINE config: throughput + image error against the CPU reference."""
+    import numpy as np
+    out = []
+    dev = torch.cuda.current_device()
+
+    def gpu_config(flats, spp, depth):
+        rts = []
+        t0 = time.perf_counter()
+        for _, s in flats:
+            rt = rtb.RayTracer(dev)
+            rt.set_stream(stream.cuda_stream)
+            rt.init(s)
+            rt.set_params(traversal=abi.TRAV_FAST, max_depth=depth, primary_reuse=0)
+            rts.append(rt)
+        torch.cuda.synchronize()
+        upload_s = time.perf_counter() - t0
+        for rt in rts:
+            rt.render(min(spp, 4), 0)
+        ms = timed_render(rts, spp, torch)
+        tot, _ = stats_sum(rts)
+        films = [rt.read_film() / np.float32(spp) for rt in rts]
+        for rt in rts:
+            rt.set_params(primary_reuse=1)
+        ms1 = timed_render(rts, spp, torch)
+        for rt in rts:
+            rt.close()
+        rays = tot["closest_rays"] + tot["shadow_rays"]
+        rec = {"spp": spp, "max_depth": depth, "ms": ms, "msamples_s": tot["samples"] / ms / 1e3, "mrays_s": rays / ms / 1e3,
+               "rays_per_sample": rays / max(tot["samples"], 1), "box_tests_per_ray": (tot["box_tests"] + tot["shadow_box_tests"]) / max(rays, 1),
+               "tri_tests_per_ray": (tot["tri_tests"] + tot["shadow_tri_tests"]) / max(rays, 1),
+               "with_primary_hit_table_msamples_s": tot["samples"] / ms1 / 1e3, "upload_s": upload_s}
+        return rec, films
+
+    for key, dirs, spp, m_half, depth in CONFIGS:
+        if not all(os.path.isfile(os.path.join(STAGED, d, "scene.json")) for d in dirs):
+            out.append({"scene": key, "skipped": "staged assets missing"})
+            continue
+        flats = [(d, host_api.load_scene(os.path.join(STAGED, d))) for d in dirs]
+        rec, films = gpu_config(flats, spp, depth)
+        rec.update(scene=key, resolution=[flats[0][1].width, flats[0][1].height], triangles=int(flats[0][1].n_tris))
+        if not args.no_cpu:
+            errs, cpu_rate, cpu = [], [], None
+            for (d, s), film in zip(flats, films):
+                ha, hb, cpu = cpu_reference_halves(d, s, m_half, depth, log)
+                errs.append(image_error(film, spp, ha, hb, m_half))
+                cpu_rate.append(cpu["msamples_s"])
+            worst = max(errs, key=lambda e: e["block8_rmse_over_expected"])
+            rec["image_error_vs_cpu"] = worst if len(errs) == 1 else dict(worst, note="worst of the %d variants by block RMSE / expected" % len(errs),
+                                                                          mean_luminance_rel_err_max=max(e["mean_luminance_rel_err"] for e in errs),
+                                                                          relmse_max=max(e["relmse"] for e in errs))
+            rec["cpu"] = dict(cpu, msamples_s=len(cpu_rate) / sum(1.0 / r for r in cpu_rate))
+            rec["speedup_vs_cpu"] = rec["msamples_s"] / rec["cpu"]["msamples_s"]
+        log("per_scene %s: %.0f Msamples/s, %.0f Mrays/s" % (key, rec["msamples_s"], rec["mrays_s"]))
+        out.append(rec)
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp))
+    for lg in SOUPS:
+        if lg > args.max_soup:
+            continue
+        s, secs = host_api.build_soup(1 << lg, 3840, 2160)
+        rec, films = gpu_config([("soup%d" % lg, s)], 4, 0)
+        rec.update(scene="soup2^%d" % lg, resolution=[3840, 2160], triangles=int(s.n_tris), host_reference_order_build_s=secs)
+        # HBM-resident regime (SURVEY 8d): nodes + triangles no longer fit the 126 MB L2 from 2^22 triangles on
+        scene_mb = (s.n_tris * 128 + len(s.ref_nodes) * 32 * 3) / 1e6
+        rec["scene_mbytes"] = scene_mb
+        if lg >= 22:
+            old = {k: os.environ.get(k) for k in ("RTB_POOLS", "RTB_SHADOW_ASYNC")}
+            os.environ["RTB_POOLS"], os.environ["RTB_SHADOW_ASYNC"] = "1", "0"
+            try:
+                rt = rtb.RayTracer(dev)
+                rt.set_stream(stream.cuda_stream)
+                rt.init(s)
+                rt.set_params(traversal=abi.TRAV_FAST, max_depth=0, primary_reuse=0)
+                rt.render(2, 0)
+                ms = timed_render([rt], 4, torch)
+                st = rt.stats()
+                rt.close()
+            finally:
+                for k, v in old.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+            it = max(st["iterations"], 1)
+            ti = max(st["timed_iterations"], 1)
+            ext_ms = st["extend_ms"] / ti
+            alg = (32.0 * st["box_tests"] + 64.0 * st["tri_tests"] + 48.0 * st["closest_rays"]) / it
+            ach = alg / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else 0.0
+            rec["roofline"] = {"bound": "hbm", "kernel": "k_wf_extend", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                               "traffic": traffic.get("soup2^%d_k_wf_extend_dram_bytes_per_launch" % lg),
+                               "kernel_ms_per_launch": ext_ms, "launches": it, "alg_bytes_per_launch": alg,
+                               "alg_source": "32 B per box test + 64 B per triangle test + 48 B per ray of the kernel's own traversal (the "
+                                             "canonical counter replays the reference tree on the CPU: minutes at this size)",
+                               "how": "serialised pass (one sub-pool, one stream)"}
+        if lg == 20 and not args.no_cpu:
+            # image check at a size the CPU finishes in seconds: the same soup at 480x270 against the C port with the SAME
+            # Philox stream (sample for sample), since the reference's own 4K render of a 1 M-triangle tree takes minutes
+            from oracle import port
+            small, _ = host_api.build_soup(1 << lg, 480, 270)
+            rt = rtb.RayTracer(dev)
+            rt.init(small)
+            rt.set_params(max_depth=0, primary_reuse=0)
+            rt.render(4, 0)
+            g = rt.read_film() / np.float32(4)
+            rt.close()
+            t0 = time.perf_counter()
+            want, _ = port.Oracle(small, max_depth=0).render(4)
+            dt = time.perf_counter() - t0
+            want = want / np.float32(4)
+            close = np.isclose(g, want, rtol=2e-4, atol=1e-5).all(axis=-1)
+            rec["image_error_vs_cpu"] = {"how": "480x270, 4 spp, C port with the same RNG stream", "pixels_equal_frac": float(close.mean()),
+                                         "rmse": float(np.sqrt(np.mean((g - want) ** 2))),
+                                         "mean_luminance_rel_err": float(abs(g.mean() / want.mean() - 1))}
+            rec["cpu"] = {"kind": "port", "cores": os.cpu_count() or 1, "msamples_s": 480 * 270 * 4 / dt / 1e6}
+        log("per_scene soup2^%d: %.0f Msamples/s, %.0f Mrays/s" % (lg, rec["msamples_s"], rec["mrays_s"]))
+        out.append(rec)
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
     import raytracingrenderer_b200 as rtb
-    from raytracingrenderer_b200 import abi, distributed as D
+    from raytracingrenderer_b200 import abi, host_api, distributed as D
 
     def log(msg):
         if rank == 0:
@@ -237,15 +523,16 @@ def run_ours(args, rank, world, local_rank):
         else:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     red_dev = "cpu" if os.environ.get("RTB_BENCH_DIAG") == "gloo" else "cuda"
+    use_nccl = dist is not None and os.environ.get("RTB_BENCH_DIAG") != "gloo"
     name, flats = load_workload(args.scene, log)
     spp = args.spp
     rts = []
     stream = torch.cuda.current_stream()
+    depth = args.max_depth if args.max_depth is not None else (0 if args.scene.startswith("soup") else 4)
     for label, s in flats:
         rt = rtb.RayTracer(local_rank)
         rt.set_stream(stream.cuda_stream)
         rt.init(s)
-        depth = args.max_depth if args.max_depth is not None else (0 if args.scene.startswith("soup") else 4)
         # headline: every sample traces its own camera ray (the rays the reference traces); the
         # product default (one camera ray per pixel and render call) is timed separately below
         rt.set_params(traversal=abi.TRAV_FAST, max_depth=depth, primary_reuse=args.primary_reuse,
@@ -257,6 +544,26 @@ def run_ours(args, rank, world, local_rank):
     # weak scaling (the contract's default): every GPU renders `spp` samples per pixel; strong: `spp` in total
     total_spp = spp * world if args.scaling == "weak" else spp
 
+    # ---- on hardware, once: the film after the real NCCL reduce equals the 1-GPU film bit for bit
+    nccl_check = None
+    if use_nccl:
+        rt0 = rts[0]
+        rt0.set_params(partition=abi.PART_NONE, part_rank=0, part_world=1)
+        rt0.clear()
+        rt0.render(world + 1, 0)
+        torch.cuda.synchronize()
+        want = accs[0].clone()
+        rt0.set_params(**D.partition_params(rank, world, "spp"))
+        rt0.clear()
+        rt0.render(world + 1, 0)
+        D.reduce_film(rt0, world + 1)
+        torch.cuda.synchronize()
+        ok = torch.tensor([1 if (rank != 0 or torch.equal(accs[0], want)) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        nccl_check = bool(ok.item())
+        if not nccl_check:
+            raise SystemExit("bench.py: the NCCL-reduced film differs from the single-GPU film")
+
     def render_all():
         # rank r renders global sample indices {s : s % world == r}, spp of them
         for rt in rts:
@@ -264,7 +571,7 @@ def run_ours(args, rank, world, local_rank):
             rt.render(total_spp, 0)
 
     def reduce_all():
-        if dist is not None and os.environ.get("RTB_BENCH_DIAG") != "gloo":
+        if use_nccl:
             for rt in rts:
                 D.reduce_film(rt, total_spp)
 
@@ -279,7 +586,7 @@ def run_ours(args, rank, world, local_rank):
             rt.update_camera(rt.scene.camera)        # host struct through the ABI
             rt.clear()
             rt.render(total_spp, 0)
-            if dist is not None and os.environ.get("RTB_BENCH_DIAG") != "gloo":
+            if use_nccl:
                 D.reduce_film(rt, total_spp)
             if rank == 0:
                 rt.read_film(host[i].numpy().reshape(rt.height, rt.width, 3))   # D2H into pinned memory
@@ -308,18 +615,12 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clk = clocks.stop()
-    # per-stage kernel time + work counters of the LAST step (clear() resets them each step)
-    st = [rt.stats() for rt in rts]
-    launches = sum(s["kernel_launches"] for s in st) - launches0
-    kern_ms = sum(s["render_ms"] for s in st)
-    samples_rank = sum(s["samples"] for s in st)
-    closest, shadow = sum(s["closest_rays"] for s in st), sum(s["shadow_rays"] for s in st)
-    rays_rank = closest + shadow
-    box, tri = sum(s["box_tests"] for s in st), sum(s["tri_tests"] for s in st)
-    sbox, stri = sum(s["shadow_box_tests"] for s in st), sum(s["shadow_tri_tests"] for s in st)
-    iters = sum(s["iterations"] for s in st)
-    timed = max(sum(s["timed_iterations"] for s in st), 1)
-    stage_ms = {k: sum(s[k + "_ms"] for s in st) / timed for k in ("extend", "shade", "shadow")}   # avg per launch
+    # work counters of the LAST step (clear() resets them each step)
+    tot, st = stats_sum(rts)
+    launches = tot["kernel_launches"] - launches0
+    kern_ms = tot["render_ms"]
+    samples_rank = tot["samples"]
+    rays_rank = tot["closest_rays"] + tot["shadow_rays"]
     # what each rank's GPU did in the last step (its renders' device time, no waiting for other ranks) and its
     # clocks: the step ends with the slowest rank, and on a full box that is often a power-capped GPU
     per_rank = None
@@ -363,61 +664,57 @@ def run_ours(args, rank, world, local_rank):
         rms = torch.tensor([r0.elapsed_time(r1)], device=red_dev)
         if dist is not None:
             dist.all_reduce(rms, op=dist.ReduceOp.MAX)
-        rst = [rt.stats() for rt in rts]
+        rtot, _ = stats_sum(rts)
         reuse = {"value": samples_step * args.steps / (float(rms.item()) / 1e3) / 1e6, "unit": "Msamples/s",
                  "ms_per_step": float(rms.item()) / args.steps,
-                 "rays_per_sample": sum(s["closest_rays"] + s["shadow_rays"] for s in rst) / max(sum(s["samples"] for s in rst), 1),
+                 "rays_per_sample": (rtot["closest_rays"] + rtot["shadow_rays"]) / max(rtot["samples"], 1),
                  "note": "rtb_params.primary_reuse=1 (library default): each pixel's camera ray is traced once per "
                          "rtb_render call instead of once per sample; film bit-identical (tests/test_gpu_parity.py)"}
+    for rt in rts:
+        rt.close()
+    del accs
+    rts = []
+
+    # ---- strong scaling sub-record: BASELINE config 4, 1 024 spp IN TOTAL sliced over the N GPUs
+    strong = None
+    if not args.no_strong:
+        strong = {"spp_total": args.strong_spp, "partition": "spp slice", "scenes": []}
+        for sc in ("coffee", "bathroom"):
+            path = os.path.join(STAGED, sc, "scene.json")
+            if not os.path.isfile(path):
+                continue
+            s = host_api.load_scene(os.path.dirname(path))
+            rt = rtb.RayTracer(local_rank)
+            rt.set_stream(stream.cuda_stream)
+            rt.init(s)
+            rt.set_params(traversal=abi.TRAV_FAST, primary_reuse=0, **D.partition_params(rank, world, "spp"))
+            rt.render(4 * world, 0)
+            rt.clear()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            rt.render(args.strong_spp, 0)
+            if use_nccl:
+                D.reduce_film(rt, args.strong_spp)
+            s1.record()
+            barrier()
+            sms = torch.tensor([s0.elapsed_time(s1)], device=red_dev)
+            if dist is not None:
+                dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+            mine_ms = rt.stats()["render_ms"]
+            ranks_ms = [mine_ms]
+            if dist is not None:
+                ranks_ms = [None] * world
+                dist.all_gather_object(ranks_ms, mine_ms)
+            strong["scenes"].append({"scene": sc, "ms": float(sms.item()), "msamples_s": s.width * s.height * args.strong_spp / float(sms.item()) / 1e3,
+                                     "per_rank_render_ms": ranks_ms})
+            rt.close()
 
     if rank == 0:
         hbm, sm_max, how = measured_peaks()
-        # Dominant kernel = the stage with the largest measured share.  Algorithmic bytes per
-        # launch: traversal stages 32 B per box test + 64 B per triangle test + 48 B
-        # per ray (32-B ray in, 16-B hit out); shade stage 64 B slot state in + 48 B out + 24 B
-        # film read-modify-write per vertex.
-        n_iter = max(iters, 1)
-        # per-ray figures of the CANONICAL traversal (profiles/canonical_counts.json, written by
-        # tests/tools/canonical_counts.py) x the rays this run traced; the kernels' own counters are
-        # the fallback for scenes the tool has not been run on
-        canon, alg_source = {}, "canonical traversal (profiles/canonical_counts.json)"
-        cp = os.path.join(ROOT, "profiles", "canonical_counts.json")
-        if os.path.isfile(cp):
-            canon = json.load(open(cp))
+        canon = canonical_counts()
         keys = [("materialball_" + lab) if args.scene == "materialball7" else lab for lab, _ in flats]
-        if all(k in canon for k in keys):
-            ext_b = sum(s_["closest_rays"] * canon[k]["closest_bytes_per_ray"] for s_, k in zip(st, keys))
-            sha_b = sum(s_["shadow_rays"] * canon[k]["shadow_bytes_per_ray"] for s_, k in zip(st, keys))
-            alg_flops = sum(s_["closest_rays"] * canon[k]["closest_flops_per_ray"] + s_["shadow_rays"] * canon[k]["shadow_flops_per_ray"]
-                            for s_, k in zip(st, keys))
-        else:
-            alg_source = "this run's own traversal counters (scene not in profiles/canonical_counts.json)"
-            ext_b = 32.0 * box + 64.0 * tri + 48.0 * closest
-            sha_b = 32.0 * sbox + 64.0 * stri + 48.0 * shadow
-            alg_flops = 24.0 * (box + sbox) + 60.0 * (tri + stri)
-        alg = {"extend": ext_b / n_iter, "shadow": sha_b / n_iter, "shade": (64.0 + 48.0 + 24.0) * closest / n_iter}
-        # Dominant kernel: the serialised ncu launch list (profiles/r01_v8_bench_spp16_summary.txt) puts the extend stage
-        # first (40.6 % of GPU time, shade 34.6 %, shadow 21.0 %).  The live event-to-event times below are taken while
-        # six streams overlap, which stretches all three by similar, fluctuating amounts; they decide only when one
-        # stage is clearly ahead (> 15 %), otherwise the ncu order stands.
-        dom = max(stage_ms, key=lambda k: stage_ms[k])
-        if stage_ms["extend"] >= stage_ms[dom] / 1.15:
-            dom = "extend"
-        stage_total = sum(stage_ms.values())
-        share = stage_ms[dom] / stage_total if stage_total else 0.0
-        # `achieved` follows the contract literally: algorithmic bytes per launch / the launch's own
-        # event-to-event duration.  The three stages of two sub-pools run on six streams and overlap, so that
-        # duration includes the time the kernel shares the SMs with up to five others; the time ATTRIBUTABLE
-        # to it (device time of the render x its share / its launches) is reported beside it.
-        per_launch_ms = stage_ms[dom]
-        achieved = alg[dom] / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
-        attributed_ms = kern_ms * share / n_iter
-        achieved_attr = alg[dom] / (attributed_ms / 1e3) / 1e9 if attributed_ms > 0 else 0.0
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get("k_wf_%s_dram_bytes_per_launch" % dom)
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        roof, _ = serial_stage_pass(flats, keys, spp, depth, canon, rtb, abi, torch, stream, sm_max)
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
@@ -426,35 +723,29 @@ def run_ours(args, rank, world, local_rank):
                        "traversal": "fast", "sampling": "strict", "l2": "flushed between steps (256 MiB memset)",
                        "scene_source": "product host loader (librtb200_host.so) on the staged scene assets"},
             "mrays_per_s": mrays, "rays_per_sample": rays_rank / max(samples_rank, 1),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": how, "kernel": "k_wf_%s" % dom,
-                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": share,
-                         "attributed": {"kernel_ms_per_launch": attributed_ms, "achieved": achieved_attr, "frac": achieved_attr / hbm,
-                                        "how": "device time of the render x the kernel's share / its launches: the stages of "
-                                               "2 sub-pools overlap on 6 streams, so a launch's own event-to-event time "
-                                               "includes time it shares the SMs with up to 5 other kernels"},
-                         "stage_ms_per_launch": stage_ms, "launches_per_render": n_iter / max(len(rts), 1),
-                         "alg_bytes_per_launch": alg[dom], "alg_source": alg_source,
-                         "note": "scene (<= 10 MB) and slot pool are L2/L1 traffic; the stages are latency/divergence "
-                                 "bound, not HBM bound - see roofline_fp32 and profiles/"},
-            "roofline_fp32": {"achieved_tflops": alg_flops / (kern_ms / 1e3) / 1e12, "peak_tflops": fp32_peak,
-                              "frac": alg_flops / (kern_ms / 1e3) / 1e12 / fp32_peak,
-                              "box_tests_per_ray": (box + sbox) / max(rays_rank, 1), "tri_tests_per_ray": (tri + stri) / max(rays_rank, 1)},
+            "roofline": roof,
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clk,
         }
         line["config"]["primary_reuse"] = int(args.primary_reuse)
+        if nccl_check is not None:
+            line["nccl_film_equals_single_gpu"] = nccl_check
         if per_rank is not None:
             line["per_rank"] = per_rank
         if reuse is not None:
             line["with_primary_hit_table"] = reuse
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, log)
+        if world == 1 and not args.no_per_scene:
+            line["per_scene"] = per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm)
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -470,6 +761,10 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--ref-spp", type=int, default=4, help="spp per scene per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-per-scene", action="store_true", help="skip the per_scene array (all BASELINE configs + image errors)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record")
+    ap.add_argument("--strong-spp", type=int, default=1024, help="total spp of the strong-scaling sub-record")
+    ap.add_argument("--max-soup", type=int, default=24, help="largest soup (log2 triangles) in per_scene")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --spp samples per pixel on EVERY GPU (default); strong: --spp in total, sliced over the GPUs")
     ap.add_argument("--primary-reuse", type=int, default=0, choices=[0, 1],

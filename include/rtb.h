@@ -260,8 +260,12 @@ typedef enum rtb_traversal {
 	RTB_TRAV_EXACT = 0, /* the reference's own tree, exhaustive DFS (Geometry.h:399-427) */
 	RTB_TRAV_FAST = 1,  /* accelerated binary tree over the reference's leaves, ordered + culled;
 	                       must return identical hits (tests assert it)                */
-	RTB_TRAV_WIDE = 2   /* the same tree collapsed to 4 children per node (selectable; measured
+	RTB_TRAV_WIDE = 2,  /* the same tree collapsed to 4 children per node (selectable; measured
 	                       ~5 % slower than FAST on B200, profiles/r01_wide_tree.txt)     */
+	RTB_TRAV_CW = 3     /* the same tree collapsed to 8 children per 80-byte node with 8-bit quantised,
+	                       CONSERVATIVE child boxes (compressed wide BVH), children visited in ray-octant
+	                       order, top levels staged in shared memory; the exact reference leaf box is still
+	                       tested before a leaf's triangles, so the hits stay the reference's            */
 } rtb_traversal;
 
 typedef enum rtb_filter {

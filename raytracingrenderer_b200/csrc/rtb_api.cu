@@ -2,6 +2,7 @@
 // launch wrappers.  Device code: rtb_kernels.cuh.  Build: see raytracingrenderer_b200/build.py
 // (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo).
 #include "rtb_accel.hpp"
+#include "rtb_cwbvh.hpp"
 #include "rtb_wavefront.cuh"
 
 #include <cstdarg>
@@ -26,6 +27,12 @@
 	case RTB_TRAV_FAST:                                    \
 	{                                                      \
 		constexpr int TR = RTB_TRAV_FAST;                  \
+		__VA_ARGS__;                                       \
+	}                                                      \
+	break;                                                 \
+	case RTB_TRAV_CW:                                      \
+	{                                                      \
+		constexpr int TR = RTB_TRAV_CW;                    \
 		__VA_ARGS__;                                       \
 	}                                                      \
 	break;                                                 \
@@ -96,7 +103,12 @@ struct rtb_ctx
 	int wfTilePart[3] = {-1, -1, -1}; // partition, rank, world the tile list was built for
 	unsigned long long* hostProbe = nullptr; // pinned: {nextJob, alive}
 	int smCount = 0;
-	int travBlocksPerSM[3] = {0, 0, 0}; // persistent extend kernel, per rtb_traversal
+	int travBlocksPerSM[4] = {0, 0, 0, 0}; // persistent extend kernel, per rtb_traversal
+	// RTB_TRAV_CW: shared-memory staging of the top of the tree (per block), persistent kernels' resident blocks
+	uint32_t cwStageNodes = 0, cwStageLeaves = 0, cwSmemBytes = 0;
+	int cwBlocksPerSM[2] = {0, 0}; // closest hit, any hit
+	int cwStageKB = 32;            // RTB_CW_STAGE_KB
+	int cwShadowPersistent = -1;   // RTB_CW_SHADOW: 1 = persistent any-hit kernel, 0 = one thread per queued ray, -1 = per scene
 	uint32_t poolSlots = 8u << 20; // profiles/r01_pool_sweep.txt: per-launch ramp/tail amortise up to ~8 M slots
 	bool simpleExtend = false;
 	int pools = 2; // sub-pools advancing concurrently on their own streams (profiles/r01_pool_sweep.txt)
@@ -288,7 +300,7 @@ void resolveTimings(rtb_ctx* ctx)
 
 int checkTrav(rtb_ctx* ctx, int traversal)
 {
-	if (traversal < RTB_TRAV_EXACT || traversal > RTB_TRAV_WIDE) return fail(ctx, RTB_ERR_ARG, "bad traversal %d", traversal);
+	if (traversal < RTB_TRAV_EXACT || traversal > RTB_TRAV_CW) return fail(ctx, RTB_ERR_ARG, "bad traversal %d", traversal);
 	return RTB_OK;
 }
 } // namespace
@@ -475,6 +487,13 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[0], k_wf_extend<RTB_TRAV_EXACT>, 128, 0));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[2], k_wf_extend<RTB_TRAV_WIDE>, 128, 0));
+		ctx->travBlocksPerSM[3] = ctx->travBlocksPerSM[1];
+		if (const char* e = getenv("RTB_CW_STAGE_KB"))
+		{
+			int v = atoi(e);
+			if (v >= 0 && v <= 200) ctx->cwStageKB = v;
+		}
+		if (const char* e = getenv("RTB_CW_SHADOW")) ctx->cwShadowPersistent = atoi(e);
 		if (const char* e = getenv("RTB_SIMPLE_EXTEND")) ctx->simpleExtend = atoi(e) != 0;
 		if (const char* e = getenv("RTB_PRIMARY_PASSES"))
 		{
@@ -483,6 +502,24 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		}
 	}
 	int ti = P.traversal;
+	const bool cwKernels = ti == RTB_TRAV_CW && ctx->S.cw_valid && !ctx->simpleExtend;
+	if (cwKernels && ctx->cwBlocksPerSM[0] == 0)
+	{
+		// top of the tree in shared memory: as many breadth-first nodes as the per-block budget holds, then the exact
+		// leaf boxes if ALL of them fit in what is left (small scenes live in shared memory entirely)
+		uint32_t budget = (uint32_t)ctx->cwStageKB * 1024u;
+		uint32_t sn = ctx->S.n_cwnodes < budget / 80u ? ctx->S.n_cwnodes : budget / 80u;
+		uint32_t left = budget - sn * 80u;
+		uint32_t sl = (sn == ctx->S.n_cwnodes && (size_t)ctx->S.n_cwleaves * 32u <= left) ? ctx->S.n_cwleaves : 0u;
+		ctx->cwStageNodes = sn, ctx->cwStageLeaves = sl, ctx->cwSmemBytes = sn * 80u + sl * 32u;
+		// the attribute belongs to the function, not to this context: always the largest budget any context may ask for
+		CK(cudaFuncSetAttribute(k_wf_trace_cw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		CK(cudaFuncSetAttribute(k_wf_trace_cw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->cwBlocksPerSM[0], k_wf_trace_cw<false>, WF_CW_THREADS, ctx->cwSmemBytes));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->cwBlocksPerSM[1], k_wf_trace_cw<true>, WF_CW_THREADS, ctx->cwSmemBytes));
+		if (ctx->cwBlocksPerSM[0] < 1 || ctx->cwBlocksPerSM[1] < 1) return fail(ctx, RTB_ERR_STATE, "RTB_TRAV_CW: %u bytes of shared memory per block do not fit", ctx->cwSmemBytes);
+	}
+	const bool cwShadow = cwKernels && (ctx->cwShadowPersistent < 0 ? true : ctx->cwShadowPersistent != 0) && P.integrator != RTB_INT_PATH_MIS;
 	if (P.primary_reuse && !ctx->wfPrimary) CK(cudaMalloc((void**)&ctx->wfPrimary, (size_t)ctx->width * ctx->height * sizeof(float4)));
 	WfArgs A[RTB_MAX_POOLS];
 	float4* base = (float4*)ctx->wfState;
@@ -578,6 +615,12 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 				{
 					RTB_TRAV_SWITCH(ti, k_wf_extend_simple<TR><<<(perPool + 127) / 128, 128, 0, st>>>(ctx->S, A[k], it));
 				}
+				else if (cwKernels)
+				{
+					unsigned g = (unsigned)(ctx->smCount * ctx->cwBlocksPerSM[0]);
+					unsigned need = (perPool + WF_CW_THREADS - 1) / WF_CW_THREADS;
+					k_wf_trace_cw<false><<<g < need ? g : need, WF_CW_THREADS, ctx->cwSmemBytes, st>>>(ctx->S, A[k], it, ctx->cwStageNodes, ctx->cwStageLeaves);
+				}
 				else
 				{
 					RTB_TRAV_SWITCH(ti, k_wf_extend<TR><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it));
@@ -618,7 +661,12 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 						k_sort_scatter<0><<<gridSort, 256, 0, sst>>>(ctx->S, A[k], it);
 						ctx->launches += 3;
 					}
-					if (P.integrator == RTB_INT_PATH_MIS)
+					if (cwShadow)
+					{
+						unsigned g = (unsigned)(ctx->smCount * ctx->cwBlocksPerSM[1]);
+						k_wf_trace_cw<true><<<g, WF_CW_THREADS, ctx->cwSmemBytes, sst>>>(ctx->S, A[k], it, ctx->cwStageNodes, ctx->cwStageLeaves);
+					}
+					else if (P.integrator == RTB_INT_PATH_MIS)
 					{
 						RTB_TRAV_SWITCH(ti, k_wf_mis<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
 					}
@@ -911,6 +959,7 @@ struct PreparedScene
 	std::vector<rtb_accel::F4> xnodes;
 	rtb_accel::FastTree fast;
 	rtb_accel::WideTree wide;
+	rtb_accel::CwTree cw;
 	std::vector<float> marginal, cond;
 	int envW = 0, envH = 0;
 };
@@ -965,6 +1014,11 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		rtb_accel::WideBuilder wb(fast);
 		wb.build(wide);
 	}
+	{
+		rtb_accel::CwBuilder cb(fast);
+		cb.build(ps.cw);
+		if (ps.cw.maxDepth + 2 > RTB_CW_STACK) ps.cw.valid = false; // RTB_TRAV_CW then walks the FAST tree
+	}
 	// stack need: one pending sibling per level (binary), up to three per level (4-wide)
 	if (fast.maxDepth + 2 > RTB_STACK || 3 * wide.maxDepth + 6 > RTB_STACK)
 		return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (binary %u, wide %u)", fast.maxDepth, wide.maxDepth);
@@ -1011,6 +1065,16 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	S.n_wnodes = (uint32_t)(wide.nodes.size() / 8);
 	S.wide_root = wide.root;
 	ctx->fastDepth = fast.maxDepth;
+	if (ps.cw.valid)
+	{
+		const rtb_accel::F4 *dcn = nullptr, *dcl = nullptr;
+		if ((rc = uploadArray(ctx, ps.cw.nodes.data(), ps.cw.nodes.size(), &dcn))) return rc;
+		if ((rc = uploadArray(ctx, ps.cw.leaves.data(), ps.cw.leaves.size(), &dcl))) return rc;
+		S.cwnodes = (const float4*)dcn, S.cwleaves = (const float4*)dcl;
+		S.n_cwnodes = (uint32_t)(ps.cw.nodes.size() / 5), S.n_cwleaves = (uint32_t)(ps.cw.leaves.size() / 2);
+		S.cw_valid = 1u, S.cw_depth = ps.cw.maxDepth;
+	}
+	ctx->cwBlocksPerSM[0] = ctx->cwBlocksPerSM[1] = 0; // staging is sized per scene
 	const rtb_tri_isect* dti = nullptr;
 	const rtb_tri_shade* dts = nullptr;
 	if ((rc = uploadArray(ctx, sc->tri_isect, sc->n_tris, &dti))) return rc;

@@ -29,6 +29,11 @@ struct DevScene
 	const float4* fnodes;
 	// WIDE tree: FAST collapsed to 4 children, 8 x float4 per node (layout: rtb_accel.hpp WideBuilder)
 	const float4* wnodes;
+	// CW tree: FAST collapsed to 8 children with 8-bit quantised boxes, 5 x float4 per node, breadth-first; exact leaf
+	// boxes as 2 x float4 per leaf record (layout: rtb_cwbvh.hpp).  cw_valid = 0: single-leaf / empty / too deep -> FAST
+	const float4* cwnodes;
+	const float4* cwleaves;
+	uint32_t n_cwnodes, n_cwleaves, cw_valid, cw_depth;
 	const float4* tri;  // 4 x float4 per triangle = rtb_tri_isect
 	const float4* tsh;  // 4 x float4 per triangle = rtb_tri_shade
 	const rtb_material* mats;
@@ -459,11 +464,20 @@ RTB_DEV bool visibleAccel(const DevScene& S, const RayD& r, float eps, float max
 	}
 }
 
+// RTB_TRAV_CW (rtb_dev_cw.cuh), nodes read from global memory; scenes without a CW tree take FAST
+RTB_DEV void closestCwGlobal(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox, uint32_t& nTri);
+RTB_DEV bool visibleCwGlobal(const DevScene& S, const RayD& r, float eps, float maxT, float cullRel, uint32_t& nBox, uint32_t& nTri);
+
 template <int TRAV>
 RTB_DEV void closestHit(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox,
                         uint32_t& nTri)
 {
 	if (TRAV == RTB_TRAV_EXACT) closestExact(S, r, eps, h, nBox, nTri);
+	else if (TRAV == RTB_TRAV_CW)
+	{
+		if (S.cw_valid) closestCwGlobal(S, r, eps, cullRel, h, nBox, nTri);
+		else closestAccel<RTB_TRAV_FAST>(S, r, eps, cullRel, h, nBox, nTri);
+	}
 	else closestAccel<TRAV>(S, r, eps, cullRel, h, nBox, nTri);
 }
 
@@ -472,6 +486,11 @@ RTB_DEV bool anyVisible(const DevScene& S, const RayD& r, float eps, float maxT,
                         uint32_t& nTri)
 {
 	if (TRAV == RTB_TRAV_EXACT) return visibleExact(S, r, eps, maxT, nBox, nTri);
+	if (TRAV == RTB_TRAV_CW)
+	{
+		if (S.cw_valid) return visibleCwGlobal(S, r, eps, maxT, cullRel, nBox, nTri);
+		return visibleAccel<RTB_TRAV_FAST>(S, r, eps, maxT, cullRel, nBox, nTri);
+	}
 	return visibleAccel<TRAV>(S, r, eps, maxT, cullRel, nBox, nTri);
 }
 

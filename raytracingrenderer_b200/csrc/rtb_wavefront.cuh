@@ -28,6 +28,7 @@
 // exactly the single-GPU film.  k_wf_resolve converts the sums to the float film.
 #pragma once
 #include "rtb_kernels.cuh"
+#include "rtb_dev_cw.cuh"
 
 // resident 128-thread blocks per SM the stage kernels are compiled for (register budget)
 #ifndef WF_VOTE
@@ -624,6 +625,162 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 	flushTally(tl, A.counters);
 }
 
+
+
+// ---------------------------------------------------------------------------------------
+// RTB_TRAV_CW: persistent traversal of the 8-wide compressed tree for BOTH ray kinds — the closest-hit rays of the
+// slots (ANYHIT = false: Scene::traverse) and the queued shadow rays (ANYHIT = true: Scene::visible).  Same schedule
+// as k_wf_extend (warps claim chunks, every lane keeps a prefetched next ray, majority vote between node steps and
+// leaf steps), different per-ray machine (rtb_dev_cw.cuh).  At the start every block stages the top of the tree — the
+// first `stageNodes` nodes of the breadth-first array, and the exact leaf boxes when they all fit — into its shared
+// memory with one bulk copy (cp.async.bulk -> mbarrier): the levels every ray passes through are then read with
+// LDS instead of competing for the L1 data pipe, the measured bound of the binary kernels on the heavy scenes.
+// ---------------------------------------------------------------------------------------
+#ifndef WF_CW_THREADS
+#define WF_CW_THREADS 128
+#endif
+#ifndef WF_CW_MIN_BLOCKS
+#define WF_CW_MIN_BLOCKS 5
+#endif
+
+template <bool ANYHIT>
+__global__ void __launch_bounds__(WF_CW_THREADS, WF_CW_MIN_BLOCKS) k_wf_trace_cw(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter,
+                                                                               uint32_t stageNodes, uint32_t stageLeaves)
+{
+	extern __shared__ float4 sStage[];
+	__shared__ unsigned long long sBar;
+	const rtb_params& P = A.P;
+	if (!ANYHIT && iter > 0 && A.ctrl[iter - 1].alive == 0) return; // pool drained
+	const uint32_t nItems = ANYHIT ? A.ctrl[iter].nShadow : (A.exPerm ? A.ctrl[iter].nExtend : A.nSlots);
+	if (nItems == 0) return;
+	CwView V = cwGlobalView(S);
+	if (stageNodes | stageLeaves)
+	{
+		cwStageBulk(sStage, S.cwnodes, stageNodes * 80u, sStage + (size_t)stageNodes * 5, S.cwleaves, stageLeaves * 32u, &sBar);
+		V.sNodes = sStage, V.nShared = stageNodes;
+		if (stageLeaves) V.leaves = sStage + (size_t)stageNodes * 5;
+	}
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t ltMask = (1u << lane) - 1u;
+	unsigned int* head = ANYHIT ? &A.ctrl[iter].shadowHead : &A.ctrl[iter].extendHead;
+	const uint32_t* perm = ANYHIT ? A.shPerm : A.exPerm;
+	const float4* srcO = ANYHIT ? A.shO : A.rayO;
+	const float4* srcD = ANYHIT ? A.shD : A.rayD;
+	uint32_t cursor = 0, end = 0;
+	bool exhausted = false;
+	uint2 stack[RTB_CW_STACK];
+	LaneCw<ANYHIT> t;
+	t.sp = 0;
+	t.ng = t.lg = make_uint2(0u, 0u);
+	uint32_t item = 0, preItem = 0;
+	float4 preO = make_float4(0, 0, 0, 0), preD = make_float4(0, 0, 0, 0);
+	uint32_t curW = 0; // any hit: film pixel of the current ray
+	bool have = false, pre = false;
+	for (;;)
+	{
+		// ---- promote the prefetched ray of every idle lane
+		if (!have && pre)
+		{
+			pre = false;
+			if (ANYHIT || (__float_as_uint(preD.w) & (WF_ALIVE | WF_PREHIT)) == WF_ALIVE)
+			{
+				RayD r = mkRay(mk(preO), mk(preD));
+				item = preItem;
+				if (ANYHIT) tl.shadow++;
+				else tl.closest++;
+				if (cwRayDegenerate(r))
+				{
+					// 0 * inf = NaN and axis-parallel rays take the reference's own tree
+					if (ANYHIT)
+					{
+						if (visibleExact(S, r, P.epsilon, preO.w, tl.sbox, tl.stri)) filmAdd(A.accum, __float_as_uint(preD.w), mk(A.shC[item]));
+					}
+					else
+					{
+						HitD h;
+						closestExact(S, r, P.epsilon, h, tl.box, tl.tri);
+						A.hit[item] = make_float4(__uint_as_float(h.id), h.t, h.alpha, h.beta);
+					}
+				}
+				else
+				{
+					cwStart<ANYHIT>(t, r, ANYHIT ? preO.w : FLT_MAX, P.cull_rel);
+					curW = __float_as_uint(preD.w);
+					have = true;
+				}
+			}
+		}
+		// ---- issue the next prefetches from the warp's chunk
+		unsigned want = __ballot_sync(0xFFFFFFFFu, !pre);
+		if (want && cursor >= end && !exhausted)
+		{
+			uint32_t c = 0;
+			if (lane == 0) c = atomicAdd(head, (unsigned)WF_CHUNK);
+			c = __shfl_sync(0xFFFFFFFFu, c, 0);
+			if (c >= nItems) exhausted = true;
+			else
+			{
+				cursor = c;
+				end = (c + WF_CHUNK < nItems) ? c + WF_CHUNK : nItems;
+			}
+		}
+		if (want && cursor < end)
+		{
+			uint32_t idx = cursor + __popc(want & ltMask);
+			if (!pre && idx < end)
+			{
+				const uint32_t it = perm ? perm[idx] : idx;
+				preO = srcO[it];
+				preD = srcD[it];
+				preItem = it;
+				pre = true;
+			}
+			cursor += __popc(want);
+		}
+		unsigned busy = __ballot_sync(0xFFFFFFFFu, have);
+		if (!busy)
+		{
+			if (!__ballot_sync(0xFFFFFFFFu, pre) && cursor >= end && exhausted) break;
+			continue;
+		}
+		// ---- traverse until enough lanes are idle to make a refill worthwhile
+		for (;;)
+		{
+			const bool wantLeaf = have && (t.lg.y & 0xFFu) != 0u;
+			const bool wantNode = have && !wantLeaf && (t.ng.y & 0xFF000000u) != 0u;
+			unsigned mN = __ballot_sync(0xFFFFFFFFu, wantNode);
+			unsigned mL = __ballot_sync(0xFFFFFFFFu, wantLeaf);
+			bool occluded = false;
+			if (__popc(mN) >= __popc(mL))
+			{
+				if (wantNode) cwNodeStep<ANYHIT>(V, t, stack, ANYHIT ? tl.sbox : tl.box);
+			}
+			else if (wantLeaf)
+				occluded = cwLeafStep<ANYHIT>(S, V, t, P.epsilon, P.cull_rel, ANYHIT ? tl.sbox : tl.box, ANYHIT ? tl.stri : tl.tri);
+			if (have)
+			{
+				cwPop<ANYHIT>(t, stack);
+				if (occluded || cwIdle<ANYHIT>(t))
+				{
+					if (ANYHIT)
+					{
+						if (!occluded) filmAdd(A.accum, curW, mk(A.shC[item]));
+					}
+					else
+						A.hit[item] = make_float4(__uint_as_float(t.bestId), t.bestT, t.bestU, t.bestV);
+					have = false;
+					t.sp = 0;
+					t.ng = t.lg = make_uint2(0u, 0u);
+				}
+			}
+			unsigned idle = __ballot_sync(0xFFFFFFFFu, !have);
+			if (idle == 0xFFFFFFFFu) break;
+			if (__popc(idle) >= WF_REFILL_IDLE && (__ballot_sync(0xFFFFFFFFu, pre) & idle)) break;
+		}
+	}
+	flushTally(tl, A.counters);
+}
 
 // One thread per slot (the v3 extend stage), kept selectable for A/B measurements against the
 // persistent kernel above (RTB_SIMPLE_EXTEND=1).
