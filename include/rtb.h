@@ -262,10 +262,13 @@ typedef enum rtb_traversal {
 	                       must return identical hits (tests assert it)                */
 	RTB_TRAV_WIDE = 2,  /* the same tree collapsed to 4 children per node (selectable; measured
 	                       ~5 % slower than FAST on B200, profiles/r01_wide_tree.txt)     */
-	RTB_TRAV_CW = 3     /* the same tree collapsed to 8 children per 80-byte node with 8-bit quantised,
+	RTB_TRAV_CW = 3,    /* the same tree collapsed to 8 children per 80-byte node with 8-bit quantised,
 	                       CONSERVATIVE child boxes (compressed wide BVH), children visited in ray-octant
 	                       order, top levels staged in shared memory; the exact reference leaf box is still
 	                       tested before a leaf's triangles, so the hits stay the reference's            */
+	RTB_TRAV_Q16 = 4    /* FAST's binary tree in 32-byte nodes: both child boxes quantised conservatively to 16 bits
+	                       per plane on one grid over the scene box (half the node bytes and fetches of FAST, a
+	                       cheaper FMA-form box test); exact reference leaf boxes kept and tested before triangles */
 } rtb_traversal;
 
 typedef enum rtb_filter {

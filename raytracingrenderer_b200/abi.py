@@ -53,7 +53,7 @@ LIGHT_AREA, LIGHT_BACKGROUND, LIGHT_ENVMAP = 0, 1, 2
 INT_PATH, INT_DIRECT, INT_ALBEDO, INT_NORMALS, INT_PATH_MIS = 0, 1, 2, 3, 4
 RNG_MIS_BLOCK = 0x40000000
 SAMPLING_STRICT, SAMPLING_IMPORTANCE = 0, 1
-TRAV_EXACT, TRAV_FAST, TRAV_WIDE, TRAV_CW = 0, 1, 2, 3
+TRAV_EXACT, TRAV_FAST, TRAV_WIDE, TRAV_CW, TRAV_Q16 = 0, 1, 2, 3, 4
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 PART_NONE, PART_SPP, PART_TILE = 0, 1, 2
 SCHED_WAVEFRONT, SCHED_MEGAKERNEL = 0, 1

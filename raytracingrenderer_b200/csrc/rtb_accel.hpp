@@ -445,6 +445,103 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------
+// Q16 tree (RTB_TRAV_Q16): the FAST tree, node for node, in 32 bytes: both child boxes on ONE 16-bit grid over the scene
+// box (plane = qmin + q * qstep), rounded OUTWARDS by two steps — interior boxes only have to be conservative (SURVEY
+// A.3); the exact box of every reference leaf moves to a 32-byte leaf record that the traversal tests with the
+// reference's arithmetic before the leaf's triangles.  Layout: rtb_dev_scene.cuh (DevScene::qnodes / qleaves).
+// ---------------------------------------------------------------------------------------
+struct Q16Tree
+{
+	std::vector<F4> nodes;  // 2 x F4 per node, same indices as FastTree::nodes
+	std::vector<F4> leaves; // 2 x F4 per leaf record
+	int32_t root = 0;       // node index, or ~(leaf record) / ~0 for single-leaf / empty scenes
+	float qmin[3] = {0, 0, 0}, qstep[3] = {1, 1, 1};
+};
+
+inline void buildQ16(const FastTree& B, Q16Tree& out)
+{
+	out.nodes.clear();
+	out.leaves.clear();
+	out.root = B.root;
+	size_t n = B.nodes.size() / 4;
+	if (B.root < 0 || n == 0) return; // the traversal falls back to the reference tree (travRoot < 0)
+	auto fbits = [](float f) {
+		uint32_t u;
+		memcpy(&u, &f, 4);
+		return u;
+	};
+	// scene box = union of the root's two child boxes
+	double lo[3], hi[3];
+	{
+		const F4* r = &B.nodes[(size_t)B.root * 4];
+		lo[0] = std::min(r[0].x, r[1].x), hi[0] = std::max(r[0].y, r[1].y);
+		lo[1] = std::min(r[0].z, r[1].z), hi[1] = std::max(r[0].w, r[1].w);
+		lo[2] = std::min(r[2].x, r[2].z), hi[2] = std::max(r[2].y, r[2].w);
+	}
+	for (int k = 0; k < 3; k++)
+	{
+		double ext = hi[k] - lo[k], mag = std::max(std::fabs(lo[k]), std::fabs(hi[k]));
+		double step = std::max(std::max(ext / 65500.0, mag * 9.5367431640625e-07 /* 2^-20 */), 1e-30);
+		out.qstep[k] = (float)step;
+		if ((double)out.qstep[k] < step) out.qstep[k] = nextafterf(out.qstep[k], FLT_MAX);
+		double m = lo[k] - 8.0 * (double)out.qstep[k];
+		out.qmin[k] = (float)m;
+		if ((double)out.qmin[k] > m) out.qmin[k] = nextafterf(out.qmin[k], -FLT_MAX);
+	}
+	auto qlo = [&](float v, int k) {
+		double q = std::floor(((double)v - (double)out.qmin[k]) / (double)out.qstep[k]) - 2.0;
+		return (uint32_t)std::min(std::max(q, 0.0), 65535.0);
+	};
+	auto qhi = [&](float v, int k) {
+		double q = std::ceil(((double)v - (double)out.qmin[k]) / (double)out.qstep[k]) + 2.0;
+		return (uint32_t)std::min(std::max(q, 0.0), 65535.0);
+	};
+	out.nodes.resize(n * 2);
+	// leaf records in node order (a serial pass assigns their indices, the quantisation itself runs on all cores)
+	std::vector<uint32_t> leafBase(n + 1, 0);
+	for (size_t i = 0; i < n; i++)
+	{
+		const F4* nd = &B.nodes[i * 4];
+		leafBase[i + 1] = leafBase[i] + ((int32_t)fbits(nd[3].x) < 0 ? 1u : 0u) + ((int32_t)fbits(nd[3].y) < 0 ? 1u : 0u);
+	}
+	out.leaves.resize((size_t)leafBase[n] * 2);
+	unsigned hw = std::thread::hardware_concurrency();
+	unsigned nth = n > 100000 ? std::min(std::max(hw, 1u), 32u) : 1u;
+	auto work = [&](size_t a, size_t b) {
+		for (size_t i = a; i < b; i++)
+		{
+			const F4* nd = &B.nodes[i * 4];
+			float mn[2][3] = {{nd[0].x, nd[0].z, nd[2].x}, {nd[1].x, nd[1].z, nd[2].z}};
+			float mx[2][3] = {{nd[0].y, nd[0].w, nd[2].y}, {nd[1].y, nd[1].w, nd[2].w}};
+			int32_t ref[2] = {(int32_t)fbits(nd[3].x), (int32_t)fbits(nd[3].y)};
+			uint32_t nl = leafBase[i];
+			for (int c = 0; c < 2; c++)
+			{
+				uint32_t w[3];
+				for (int k = 0; k < 3; k++) w[k] = qlo(mn[c][k], k) | (qhi(mx[c][k], k) << 16);
+				int32_t r = ref[c];
+				if (r < 0)
+				{
+					F4* lf = &out.leaves[(size_t)nl * 2];
+					lf[0] = {mn[c][0], mn[c][1], mn[c][2], bitsToFloat((uint32_t)(~r))};
+					lf[1] = {mx[c][0], mx[c][1], mx[c][2], 0.0f};
+					r = ~(int32_t)nl;
+					nl++;
+				}
+				out.nodes[i * 2 + c] = {bitsToFloat(w[0]), bitsToFloat(w[1]), bitsToFloat(w[2]), bitsToFloat((uint32_t)r)};
+			}
+		}
+	};
+	if (nth <= 1) work(0, n);
+	else
+	{
+		std::vector<std::thread> th;
+		for (unsigned t = 0; t < nth; t++) th.emplace_back(work, n * t / nth, n * (t + 1) / nth);
+		for (std::thread& t : th) t.join();
+	}
+}
+
+// ---------------------------------------------------------------------------------------
 // Environment-map sampling tables (RTB_SAMPLING_IMPORTANCE).  EnvironmentMap::evaluate
 // (RTBase/Lights.h:158-165) maps a direction to u = phi/2pi, v = theta/pi and
 // Texture::sample (Imaging.h:72-94) blends texels floor(u W), floor(u W)+1 (no half-texel

@@ -36,6 +36,12 @@
 		__VA_ARGS__;                                       \
 	}                                                      \
 	break;                                                 \
+	case RTB_TRAV_Q16:                                     \
+	{                                                      \
+		constexpr int TR = RTB_TRAV_Q16;                   \
+		__VA_ARGS__;                                       \
+	}                                                      \
+	break;                                                 \
 	default:                                               \
 	{                                                      \
 		constexpr int TR = RTB_TRAV_WIDE;                  \
@@ -103,7 +109,7 @@ struct rtb_ctx
 	int wfTilePart[3] = {-1, -1, -1}; // partition, rank, world the tile list was built for
 	unsigned long long* hostProbe = nullptr; // pinned: {nextJob, alive}
 	int smCount = 0;
-	int travBlocksPerSM[4] = {0, 0, 0, 0}; // persistent extend kernel, per rtb_traversal
+	int travBlocksPerSM[5] = {0, 0, 0, 0, 0}; // persistent extend kernel, per rtb_traversal
 	// RTB_TRAV_CW: shared-memory staging of the top of the tree (per block), persistent kernels' resident blocks
 	uint32_t cwStageNodes = 0, cwStageLeaves = 0, cwSmemBytes = 0;
 	int cwBlocksPerSM[2] = {0, 0}; // closest hit, any hit
@@ -300,7 +306,7 @@ void resolveTimings(rtb_ctx* ctx)
 
 int checkTrav(rtb_ctx* ctx, int traversal)
 {
-	if (traversal < RTB_TRAV_EXACT || traversal > RTB_TRAV_CW) return fail(ctx, RTB_ERR_ARG, "bad traversal %d", traversal);
+	if (traversal < RTB_TRAV_EXACT || traversal > RTB_TRAV_Q16) return fail(ctx, RTB_ERR_ARG, "bad traversal %d", traversal);
 	return RTB_OK;
 }
 } // namespace
@@ -488,6 +494,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[1], k_wf_extend<RTB_TRAV_FAST>, 128, 0));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[2], k_wf_extend<RTB_TRAV_WIDE>, 128, 0));
 		ctx->travBlocksPerSM[3] = ctx->travBlocksPerSM[1];
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->travBlocksPerSM[4], k_wf_extend<RTB_TRAV_Q16>, 128, 0));
 		if (const char* e = getenv("RTB_CW_STAGE_KB"))
 		{
 			int v = atoi(e);
@@ -960,6 +967,7 @@ struct PreparedScene
 	rtb_accel::FastTree fast;
 	rtb_accel::WideTree wide;
 	rtb_accel::CwTree cw;
+	rtb_accel::Q16Tree q16;
 	std::vector<float> marginal, cond;
 	int envW = 0, envH = 0;
 };
@@ -1019,6 +1027,7 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		cb.build(ps.cw);
 		if (ps.cw.maxDepth + 2 > RTB_CW_STACK) ps.cw.valid = false; // RTB_TRAV_CW then walks the FAST tree
 	}
+	rtb_accel::buildQ16(fast, ps.q16);
 	// stack need: one pending sibling per level (binary), up to three per level (4-wide)
 	if (fast.maxDepth + 2 > RTB_STACK || 3 * wide.maxDepth + 6 > RTB_STACK)
 		return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (binary %u, wide %u)", fast.maxDepth, wide.maxDepth);
@@ -1075,6 +1084,16 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 		S.cw_valid = 1u, S.cw_depth = ps.cw.maxDepth;
 	}
 	ctx->cwBlocksPerSM[0] = ctx->cwBlocksPerSM[1] = 0; // staging is sized per scene
+	{
+		const rtb_accel::F4 *dqn = nullptr, *dql = nullptr;
+		if ((rc = uploadArray(ctx, ps.q16.nodes.data(), ps.q16.nodes.size(), &dqn))) return rc;
+		if ((rc = uploadArray(ctx, ps.q16.leaves.data(), ps.q16.leaves.size(), &dql))) return rc;
+		S.qnodes = (const float4*)dqn, S.qleaves = (const float4*)dql;
+		S.n_qnodes = (uint32_t)(ps.q16.nodes.size() / 2);
+		S.q16_root = ps.q16.root;
+		memcpy(S.qmin, ps.q16.qmin, sizeof(S.qmin));
+		memcpy(S.qstep, ps.q16.qstep, sizeof(S.qstep));
+	}
 	const rtb_tri_isect* dti = nullptr;
 	const rtb_tri_shade* dts = nullptr;
 	if ((rc = uploadArray(ctx, sc->tri_isect, sc->n_tris, &dti))) return rc;

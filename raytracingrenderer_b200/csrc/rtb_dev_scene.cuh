@@ -34,6 +34,16 @@ struct DevScene
 	const float4* cwnodes;
 	const float4* cwleaves;
 	uint32_t n_cwnodes, n_cwleaves, cw_valid, cw_depth;
+	// Q16 tree: the FAST tree with 32-byte nodes — both child boxes quantised CONSERVATIVELY to 16 bits per plane on
+	// ONE grid over the scene box (plane = qmin + q * qstep), 2 x float4 per node:
+	//   [2i]   = c0: (min.x | max.x << 16) (min.y | max.y << 16) (min.z | max.z << 16) bits(child0)
+	//   [2i+1] = c1: the same, bits(child1)        child >= 0: node index; < 0: ~(leaf record index)
+	// qleaves: 2 x float4 per leaf record = exact min.xyz, bits(start << 2 | count) | exact max.xyz, 0
+	const float4* qnodes;
+	const float4* qleaves;
+	int32_t q16_root;
+	uint32_t n_qnodes;
+	float qmin[3], qstep[3];
 	const float4* tri;  // 4 x float4 per triangle = rtb_tri_isect
 	const float4* tsh;  // 4 x float4 per triangle = rtb_tri_shade
 	const rtb_material* mats;
@@ -212,8 +222,6 @@ RTB_DEV bool visibleExact(const DevScene& S, const RayD& r, float eps, float max
 // leaf, is tested with the reference's exact slab arithmetic, children are visited
 // near-first and popped nodes are dropped when t_entry - |t_entry|*rel > t_best.
 // ---------------------------------------------------------------------------------------
-#define RTB_STACK 96 /* rtb_upload_scene rejects trees that could need more */
-
 RTB_DEV bool rayIsDegenerate(const RayD& r)
 {
 	// an infinite reciprocal (direction component +-0 or so small that 1/d overflows) or a NaN anywhere:
@@ -269,6 +277,46 @@ struct LaneTrav
 	float bestU, bestV;
 	int32_t cur; // >= 0 interior node, < 0 leaf reference, RTB_TRAV_DONE_ finished
 	int sp;
+	// RTB_TRAV_Q16 only (dead registers otherwise): t_plane = (2^23 + q) * qa + qb per axis, and the PRMT selectors that
+	// pick the NEAR plane's 16 bits of a (min | max << 16) word for this ray's direction signs
+	float qa[3], qb[3];
+	uint32_t qsel[3];
+};
+
+// Traversal stacks of (node, t_entry) pairs.  LocalStack: RTB_STACK entries of local memory per thread.  SharedStack
+// (the persistent kernels): the first NS entries live in shared memory, entry-major ([entry][thread]: whatever their
+// depths, the 32 lanes of a warp touch 32 different 8-byte words of 32 banks pairs - 2 wavefronts per access, where
+// a divergent local-memory access costs up to 32 on the L1 data pipe, the measured bound of the extend stage on the
+// heavy scenes); deeper entries spill to local memory.
+#define RTB_STACK 96 /* rtb_upload_scene rejects trees that could need more */
+struct LocalStack
+{
+	int32_t node[RTB_STACK];
+	float t[RTB_STACK];
+	RTB_DEV void put(int i, int32_t n, float te) { node[i] = n, t[i] = te; }
+	RTB_DEV void get(int i, int32_t& n, float& te) const { n = node[i], te = t[i]; }
+};
+template <int NS, int THREADS>
+struct SharedStack
+{
+	float2* s; // this thread's column: entry i at s[i * THREADS]
+	int32_t node[RTB_STACK - NS];
+	float t[RTB_STACK - NS];
+	RTB_DEV void put(int i, int32_t n, float te)
+	{
+		if (i < NS) s[i * THREADS] = make_float2(__int_as_float(n), te);
+		else node[i - NS] = n, t[i - NS] = te;
+	}
+	RTB_DEV void get(int i, int32_t& n, float& te) const
+	{
+		if (i < NS)
+		{
+			float2 v = s[i * THREADS];
+			n = __float_as_int(v.x), te = v.y;
+		}
+		else
+			n = node[i - NS], te = t[i - NS];
+	}
 };
 
 // Culling: a box entered beyond the best hit cannot matter, but t_entry (slab
@@ -288,22 +336,25 @@ RTB_DEV bool travCull(float te, float cullT)
 	return ANYHIT ? (te >= cullT) : (te > cullT);
 }
 
-template <bool ANYHIT>
-RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const int32_t* stackNode, const float* stackT, float cullRel)
+template <bool ANYHIT, class STK>
+RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const STK& stk)
 {
 	t.cur = RTB_TRAV_DONE_;
 	while (t.sp > 0)
 	{
 		t.sp--;
-		if (travCull<ANYHIT>(stackT[t.sp], t.cullT)) continue;
-		t.cur = stackNode[t.sp];
+		int32_t n;
+		float te;
+		stk.get(t.sp, n, te);
+		if (travCull<ANYHIT>(te, t.cullT)) continue;
+		t.cur = n;
 		break;
 	}
 }
 
 // One interior step of the binary FAST tree: both child boxes, near child next, far child pushed.
-template <bool ANYHIT>
-RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel, uint32_t& nBox)
+template <bool ANYHIT, class STK>
+RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
 {
 	const float4* nd = S.fnodes + (size_t)t.cur * 4;
 	float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
@@ -317,14 +368,69 @@ RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode
 	if (h0 && h1)
 	{
 		bool swap = !ANYHIT && (t1 < t0);
-		stackNode[t.sp] = swap ? c0 : c1;
-		stackT[t.sp] = swap ? t0 : t1;
+		stk.put(t.sp, swap ? c0 : c1, swap ? t0 : t1);
 		t.sp++;
 		t.cur = swap ? c1 : c0;
 	}
 	else if (h0) t.cur = c0;
 	else if (h1) t.cur = c1;
-	else lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
+	else lanePop<ANYHIT>(t, stk);
+}
+
+// One interior step of the Q16 tree: the FAST tree's topology in 32-byte nodes (two LDG.128 instead of four, half the
+// cache footprint).  Interior boxes only have to be conservative: every plane is rounded outwards by two
+// steps of a 2^16 grid over the scene box at build time, and the test is the FMA form t = (2^23 + q) * a + b with
+// a = step * invDir and b = (qmin - o) * invDir - 2^23 a per RAY (not per node); PRMT turns 16 bits into the float
+// 2^23 + q and picks near / far by the ray's direction signs at no cost.  Its error against the reference's
+// (plane - o) * invDir — under 0.6 grid steps plus 2^-22 relative — is inside the padding and the relative slack
+// RTB_Q16_SLACK on the entry distance.  The entry distance used for ordering and culling is that lower bound.
+#define RTB_Q16_SLACK 0.99999619f /* 1 - 2^-18 */
+#define RTB_Q16_F(w, sel) __uint_as_float(__byte_perm((w), 0x4B000000u, (sel)))
+template <bool ANYHIT, class STK>
+RTB_DEV void stepQ16(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
+{
+	const float4* nd = S.qnodes + (size_t)t.cur * 2;
+	const float4 A = ldg4(nd), B = ldg4(nd + 1);
+	const uint32_t snx = t.qsel[0], sny = t.qsel[1], snz = t.qsel[2];
+	const uint32_t sfx = snx ^ 0x0022u, sfy = sny ^ 0x0022u, sfz = snz ^ 0x0022u;
+	const uint32_t a0 = __float_as_uint(A.x), a1 = __float_as_uint(A.y), a2 = __float_as_uint(A.z);
+	const uint32_t b0 = __float_as_uint(B.x), b1 = __float_as_uint(B.y), b2 = __float_as_uint(B.z);
+	nBox += 2;
+	float n0 = fmaxf(fmaxf(fmaf(RTB_Q16_F(a0, snx), t.qa[0], t.qb[0]), fmaf(RTB_Q16_F(a1, sny), t.qa[1], t.qb[1])),
+	                 fmaxf(fmaf(RTB_Q16_F(a2, snz), t.qa[2], t.qb[2]), 0.0f));
+	float f0 = fminf(fminf(fmaf(RTB_Q16_F(a0, sfx), t.qa[0], t.qb[0]), fmaf(RTB_Q16_F(a1, sfy), t.qa[1], t.qb[1])),
+	                 fminf(fmaf(RTB_Q16_F(a2, sfz), t.qa[2], t.qb[2]), t.cullT));
+	float n1 = fmaxf(fmaxf(fmaf(RTB_Q16_F(b0, snx), t.qa[0], t.qb[0]), fmaf(RTB_Q16_F(b1, sny), t.qa[1], t.qb[1])),
+	                 fmaxf(fmaf(RTB_Q16_F(b2, snz), t.qa[2], t.qb[2]), 0.0f));
+	float f1 = fminf(fminf(fmaf(RTB_Q16_F(b0, sfx), t.qa[0], t.qb[0]), fmaf(RTB_Q16_F(b1, sfy), t.qa[1], t.qb[1])),
+	                 fminf(fmaf(RTB_Q16_F(b2, sfz), t.qa[2], t.qb[2]), t.cullT));
+	const float t0 = n0 * RTB_Q16_SLACK, t1 = n1 * RTB_Q16_SLACK;
+	const bool h0 = t0 <= f0, h1 = t1 <= f1;
+	const int32_t c0 = __float_as_int(A.w), c1 = __float_as_int(B.w);
+	if (h0 && h1)
+	{
+		bool swap = !ANYHIT && (t1 < t0);
+		stk.put(t.sp, swap ? c0 : c1, swap ? t0 : t1);
+		t.sp++;
+		t.cur = swap ? c1 : c0;
+	}
+	else if (h0) t.cur = c0;
+	else if (h1) t.cur = c1;
+	else lanePop<ANYHIT>(t, stk);
+}
+
+// per-ray constants of stepQ16
+template <bool ANYHIT>
+RTB_DEV void q16Start(const DevScene& S, LaneTrav<ANYHIT>& t)
+{
+	const float inv[3] = {t.r.inv.x, t.r.inv.y, t.r.inv.z}, o[3] = {t.r.o.x, t.r.o.y, t.r.o.z};
+#pragma unroll
+	for (int k = 0; k < 3; k++)
+	{
+		t.qa[k] = S.qstep[k] * inv[k];
+		t.qb[k] = fmaf(-8388608.0f, t.qa[k], (S.qmin[k] - o[k]) * inv[k]);
+		t.qsel[k] = inv[k] >= 0.0f ? 0x7410u : 0x7432u;
+	}
 }
 
 // One interior step of the 4-wide tree (rtb_accel.hpp WideBuilder): four child boxes from one
@@ -338,8 +444,8 @@ RTB_DEV void cswap(uint32_t& a, uint32_t& b)
 	uint32_t lo = min(a, b), hi = max(a, b);
 	a = lo, b = hi;
 }
-template <bool ANYHIT>
-RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel, uint32_t& nBox)
+template <bool ANYHIT, class STK>
+RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
 {
 	const float4* nd = S.wnodes + (size_t)t.cur * 8;
 	float4 mnx = ldg4(nd), mxx = ldg4(nd + 1), mny = ldg4(nd + 2), mxy = ldg4(nd + 3), mnz = ldg4(nd + 4), mxz = ldg4(nd + 5);
@@ -358,11 +464,11 @@ RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode
 	if (ANYHIT)
 	{
 		// order is irrelevant for the result; push every admitted child, continue with the last
-		if (h0) stackNode[t.sp] = c0, stackT[t.sp] = e0, t.sp++;
-		if (h1) stackNode[t.sp] = c1, stackT[t.sp] = e1, t.sp++;
-		if (h2) stackNode[t.sp] = c2, stackT[t.sp] = e2, t.sp++;
-		if (h3) stackNode[t.sp] = c3, stackT[t.sp] = e3, t.sp++;
-		lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
+		if (h0) stk.put(t.sp, c0, e0), t.sp++;
+		if (h1) stk.put(t.sp, c1, e1), t.sp++;
+		if (h2) stk.put(t.sp, c2, e2), t.sp++;
+		if (h3) stk.put(t.sp, c3, e3), t.sp++;
+		lanePop<ANYHIT>(t, stk);
 		return;
 	}
 	uint32_t k0 = h0 ? ((__float_as_uint(fmaxf(e0, 0.0f)) & ~3u) | 0u) : 0xFFFFFFFFu;
@@ -372,24 +478,39 @@ RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode
 	cswap(k0, k1), cswap(k2, k3), cswap(k0, k2), cswap(k1, k3), cswap(k1, k2);
 	// farthest first onto the stack, nearest becomes the next node
 #define RTB_WIDE_REF(k) (((k) & 3u) == 0u ? c0 : ((k) & 3u) == 1u ? c1 : ((k) & 3u) == 2u ? c2 : c3)
-	if (k3 != 0xFFFFFFFFu) stackNode[t.sp] = RTB_WIDE_REF(k3), stackT[t.sp] = __uint_as_float(k3 & ~3u), t.sp++;
-	if (k2 != 0xFFFFFFFFu) stackNode[t.sp] = RTB_WIDE_REF(k2), stackT[t.sp] = __uint_as_float(k2 & ~3u), t.sp++;
-	if (k1 != 0xFFFFFFFFu) stackNode[t.sp] = RTB_WIDE_REF(k1), stackT[t.sp] = __uint_as_float(k1 & ~3u), t.sp++;
+	if (k3 != 0xFFFFFFFFu) stk.put(t.sp, RTB_WIDE_REF(k3), __uint_as_float(k3 & ~3u)), t.sp++;
+	if (k2 != 0xFFFFFFFFu) stk.put(t.sp, RTB_WIDE_REF(k2), __uint_as_float(k2 & ~3u)), t.sp++;
+	if (k1 != 0xFFFFFFFFu) stk.put(t.sp, RTB_WIDE_REF(k1), __uint_as_float(k1 & ~3u)), t.sp++;
 	if (k0 != 0xFFFFFFFFu) t.cur = RTB_WIDE_REF(k0);
-	else lanePop<ANYHIT>(t, stackNode, stackT, cullRel);
+	else lanePop<ANYHIT>(t, stk);
 #undef RTB_WIDE_REF
 }
 
-template <int TRAV, bool ANYHIT>
-RTB_DEV void stepInterior(const DevScene& S, LaneTrav<ANYHIT>& t, int32_t* stackNode, float* stackT, float cullRel, uint32_t& nBox)
+template <int TRAV, bool ANYHIT, class STK>
+RTB_DEV void stepInterior(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
 {
-	if (TRAV == RTB_TRAV_WIDE) stepWide<ANYHIT>(S, t, stackNode, stackT, cullRel, nBox);
-	else stepFast<ANYHIT>(S, t, stackNode, stackT, cullRel, nBox);
+	if (TRAV == RTB_TRAV_WIDE) stepWide<ANYHIT>(S, t, stk, nBox);
+	else if (TRAV == RTB_TRAV_Q16) stepQ16<ANYHIT>(S, t, stk, nBox);
+	else stepFast<ANYHIT>(S, t, stk, nBox);
 }
 template <int TRAV>
 RTB_DEV int32_t travRoot(const DevScene& S)
 {
-	return TRAV == RTB_TRAV_WIDE ? S.wide_root : S.fast_root;
+	return TRAV == RTB_TRAV_WIDE ? S.wide_root : TRAV == RTB_TRAV_Q16 ? S.q16_root : S.fast_root;
+}
+// what a ray needs besides LaneTrav's common fields before its first step
+template <int TRAV, bool ANYHIT>
+RTB_DEV void travStart(const DevScene& S, LaneTrav<ANYHIT>& t)
+{
+	if (TRAV == RTB_TRAV_Q16) q16Start<ANYHIT>(S, t);
+}
+// rays the accelerated trees do not take (they walk the reference's own tree): 0 * inf = NaN rays, and for
+// the FMA-form tests reciprocals so large that step * invDir * 2^23 could overflow (axis-parallel to 1e-28)
+template <int TRAV>
+RTB_DEV bool travDegenerate(const RayD& r)
+{
+	if (TRAV == RTB_TRAV_Q16) return !(fabsf(r.inv.x) <= 1e28f) || !(fabsf(r.inv.y) <= 1e28f) || !(fabsf(r.inv.z) <= 1e28f) || rayHasNaN(r);
+	return rayIsDegenerate(r);
 }
 
 RTB_DEV bool leafOccludes(const DevScene& S, int32_t ref, const RayD& r, float eps, float maxT, uint32_t& nTri)
@@ -410,35 +531,60 @@ RTB_DEV bool leafOccludes(const DevScene& S, int32_t ref, const RayD& r, float e
 }
 
 
+// A reached leaf.  FAST / WIDE: `cur` = ~(start << 2 | count) and the box that admitted it WAS the reference's exact leaf
+// box.  Q16: `cur` = ~(leaf record); the quantised slot box was only conservative, so the reference's exact leaf box
+// (Geometry.h:173-184 arithmetic) is tested here before the leaf's triangles (condition 2).
+template <int TRAV, bool ANYHIT>
+RTB_DEV bool travLeafRef(const DevScene& S, const LaneTrav<ANYHIT>& t, int32_t& ref, uint32_t& nBox)
+{
+	if (TRAV != RTB_TRAV_Q16)
+	{
+		ref = t.cur;
+		return true;
+	}
+	const float4* lf = S.qleaves + (size_t)(uint32_t)(~t.cur) * 2;
+	const float4 A = ldg4(lf), B = ldg4(lf + 1);
+	float te;
+	nBox++;
+	if (!slabTestNoNaN(A.x, A.y, A.z, B.x, B.y, B.z, t.r, te)) return false;
+	if (travCull<ANYHIT>(te, t.cullT)) return false;
+	ref = ~(int32_t)__float_as_uint(A.w);
+	return true;
+}
+
 // One thread runs one ray to the end (parity entry points, shadow stage, megakernel).
 template <int TRAV>
 RTB_DEV void closestAccel(const DevScene& S, const RayD& r, float eps, float cullRel, HitD& h, uint32_t& nBox,
                           uint32_t& nTri)
 {
-	if (rayIsDegenerate(r) || travRoot<TRAV>(S) < 0)
+	if (travDegenerate<TRAV>(r) || travRoot<TRAV>(S) < 0)
 	{
 		// 0*inf = NaN rays and single-leaf scenes take the reference's own tree
 		closestExact(S, r, eps, h, nBox, nTri);
 		return;
 	}
-	int32_t stackNode[RTB_STACK];
-	float stackT[RTB_STACK];
+	LocalStack stk;
 	LaneTrav<false> t;
 	t.r = r;
 	travSetBest<false>(t, FLT_MAX, cullRel);
 	t.bestId = RTB_MISS_ID, t.bestU = t.bestV = 0.0f;
 	t.sp = 0;
 	t.cur = travRoot<TRAV>(S);
+	travStart<TRAV, false>(S, t);
 	for (;;)
 	{
-		while (t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stackNode, stackT, cullRel, nBox);
+		while (t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stk, nBox);
 		if (t.cur == RTB_TRAV_DONE_) break;
-		HitD b;
-		b.id = t.bestId, b.t = t.bestT, b.alpha = t.bestU, b.beta = t.bestV;
-		leafClosest(S, t.cur, t.r, eps, b, nTri);
-		t.bestId = b.id, t.bestU = b.alpha, t.bestV = b.beta;
-		travSetBest<false>(t, b.t, cullRel);
-		lanePop<false>(t, stackNode, stackT, cullRel);
+		int32_t ref;
+		if (travLeafRef<TRAV, false>(S, t, ref, nBox))
+		{
+			HitD b;
+			b.id = t.bestId, b.t = t.bestT, b.alpha = t.bestU, b.beta = t.bestV;
+			leafClosest(S, ref, t.r, eps, b, nTri);
+			t.bestId = b.id, t.bestU = b.alpha, t.bestV = b.beta;
+			travSetBest<false>(t, b.t, cullRel);
+		}
+		lanePop<false>(t, stk);
 	}
 	h.id = t.bestId, h.t = t.bestT, h.alpha = t.bestU, h.beta = t.bestV;
 }
@@ -447,20 +593,21 @@ template <int TRAV>
 RTB_DEV bool visibleAccel(const DevScene& S, const RayD& r, float eps, float maxT, float cullRel, uint32_t& nBox,
                           uint32_t& nTri)
 {
-	if (rayIsDegenerate(r) || travRoot<TRAV>(S) < 0) return visibleExact(S, r, eps, maxT, nBox, nTri);
-	int32_t stackNode[RTB_STACK];
-	float stackT[RTB_STACK];
+	if (travDegenerate<TRAV>(r) || travRoot<TRAV>(S) < 0) return visibleExact(S, r, eps, maxT, nBox, nTri);
+	LocalStack stk;
 	LaneTrav<true> t;
 	t.r = r;
 	travSetBest<true>(t, maxT, cullRel);
 	t.sp = 0;
 	t.cur = travRoot<TRAV>(S);
+	travStart<TRAV, true>(S, t);
 	for (;;)
 	{
-		while (t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, true>(S, t, stackNode, stackT, cullRel, nBox);
+		while (t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, true>(S, t, stk, nBox);
 		if (t.cur == RTB_TRAV_DONE_) return true;
-		if (leafOccludes(S, t.cur, t.r, eps, maxT, nTri)) return false;
-		lanePop<true>(t, stackNode, stackT, cullRel);
+		int32_t ref;
+		if (travLeafRef<TRAV, true>(S, t, ref, nBox) && leafOccludes(S, ref, t.r, eps, maxT, nTri)) return false;
+		lanePop<true>(t, stk);
 	}
 }
 

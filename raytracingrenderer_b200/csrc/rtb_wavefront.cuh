@@ -488,6 +488,9 @@ __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScen
 #ifndef WF_CHUNK
 #define WF_CHUNK 128u /* slots a warp claims per atomic */
 #endif
+#ifndef WF_SSTACK
+#define WF_SSTACK 12 /* stack entries per thread kept in shared memory by k_wf_extend (8 B x 128 threads each) */
+#endif
 
 template <int TRAV>
 __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
@@ -519,8 +522,13 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 	// work is claimed in chunks of WF_CHUNK consecutive slots (one atomic per chunk and warp)
 	uint32_t cursor = 0, end = 0;
 	bool exhausted = false;
-	int32_t stackNode[RTB_STACK];
-	float stackT[RTB_STACK];
+#if WF_SSTACK > 0
+	__shared__ float2 sStack[WF_SSTACK * 128];
+	SharedStack<WF_SSTACK, 128> stk;
+	stk.s = sStack + threadIdx.x;
+#else
+	LocalStack stk;
+#endif
 	LaneTrav<false> t;
 	t.cur = RTB_TRAV_DONE_;
 	t.sp = 0;
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 				slot = preSlot;
 				have = true;
 				tl.closest++;
-				if (rayIsDegenerate(t.r))
+				if (travDegenerate<TRAV>(t.r))
 				{
 					// 0*inf = NaN rays take the reference's own tree
 					HitD h;
@@ -551,7 +559,10 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 					have = false;
 				}
 				else
+				{
 					t.cur = travRoot<TRAV>(S);
+					travStart<TRAV, false>(S, t);
+				}
 			}
 		}
 		// ---- issue the next prefetches from the warp's chunk
@@ -601,16 +612,20 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 #endif
 			if (doInterior)
 			{
-				if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stackNode, stackT, P.cull_rel, tl.box);
+				if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stk, tl.box);
 			}
 			else if (have && t.cur < 0)
 			{
-				HitD h;
-				h.id = t.bestId, h.t = t.bestT, h.alpha = t.bestU, h.beta = t.bestV;
-				leafClosest(S, t.cur, t.r, P.epsilon, h, tl.tri);
-				t.bestId = h.id, t.bestU = h.alpha, t.bestV = h.beta;
-				travSetBest<false>(t, h.t, P.cull_rel);
-				lanePop<false>(t, stackNode, stackT, P.cull_rel);
+				int32_t ref;
+				if (travLeafRef<TRAV, false>(S, t, ref, tl.box))
+				{
+					HitD h;
+					h.id = t.bestId, h.t = t.bestT, h.alpha = t.bestU, h.beta = t.bestV;
+					leafClosest(S, ref, t.r, P.epsilon, h, tl.tri);
+					t.bestId = h.id, t.bestU = h.alpha, t.bestV = h.beta;
+					travSetBest<false>(t, h.t, P.cull_rel);
+				}
+				lanePop<false>(t, stk);
 			}
 			if (have && t.cur == RTB_TRAV_DONE_)
 			{

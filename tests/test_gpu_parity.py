@@ -16,7 +16,7 @@ from raytracingrenderer_b200 import abi
 pytestmark = pytest.mark.gpu
 
 FP = json.load(open(os.path.join(GOLDEN, "fingerprints.json")))
-TRAVS = [abi.TRAV_EXACT, abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW]
+TRAVS = [abi.TRAV_EXACT, abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW, abi.TRAV_Q16]
 
 
 def sha16(a):
@@ -303,7 +303,7 @@ def test_direct_integrator_equals_the_oracle_and_the_reference(rtb, oracle_mod, 
     assert g["closest_rays"] == st["closest_rays"] == g["samples"]           # one camera ray per sample, nothing else
     assert abs(g["shadow_rays"] / max(st["shadow_rays"], 1) - 1) < 2e-3
     # all three traversals and the primary-hit table give the same bits
-    for kw in (dict(traversal=abi.TRAV_EXACT), dict(traversal=abi.TRAV_WIDE), dict(traversal=abi.TRAV_CW), dict(primary_reuse=1)):
+    for kw in (dict(traversal=abi.TRAV_EXACT), dict(traversal=abi.TRAV_WIDE), dict(traversal=abi.TRAV_CW), dict(traversal=abi.TRAV_Q16), dict(primary_reuse=1)):
         rt.set_params(integrator=abi.INT_DIRECT, traversal=abi.TRAV_FAST, primary_reuse=0)
         rt.set_params(**kw)
         rt.clear()
@@ -481,7 +481,7 @@ def test_light_tracer_equals_the_oracle_and_the_reference(rtb, oracle_mod):
     rt.lightTracer(1, 0)
     rt.lightTracer(1, 1)
     two = rt.read_film().copy()
-    for trav in (abi.TRAV_EXACT, abi.TRAV_WIDE, abi.TRAV_CW):
+    for trav in (abi.TRAV_EXACT, abi.TRAV_WIDE, abi.TRAV_CW, abi.TRAV_Q16):
         rt.set_params(traversal=trav)
         rt.clear()
         rt.lightTracer(2, 0)
@@ -523,7 +523,7 @@ def test_instant_radiosity_equals_the_oracle_and_the_reference(rtb, oracle_mod):
     # ~3e-7: a VPL and a shading point on the SAME wall give a visibility ray lying in that wall's plane
     # (cos ~ 1e-8 passes the "<= 0" test), whose plane-intersection t is rounding noise — the one case where
     # the culled trees and the reference's exhaustive walk may accept different triangles.
-    for trav in (abi.TRAV_EXACT, abi.TRAV_WIDE, abi.TRAV_CW):
+    for trav in (abi.TRAV_EXACT, abi.TRAV_WIDE, abi.TRAV_CW, abi.TRAV_Q16):
         rt.set_params(traversal=trav)
         rt.clear()
         rt.instantRadiosity(2, 0)
@@ -633,7 +633,7 @@ def test_exact_and_fast_render_identical_films(rtb):
         rt.set_params(traversal=abi.TRAV_EXACT)
         rt.render(4, 0)
         a = rt.read_film().copy()
-        for trav in (abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW):
+        for trav in (abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW, abi.TRAV_Q16):
             rt.set_params(traversal=trav)
             rt.clear()
             rt.render(4, 0)
@@ -652,7 +652,7 @@ def test_exact_fast_wide_films_are_bit_identical_on_the_heavy_scenes(rtb, name):
     rt.render(spp, 0)
     a = rt.read_film().copy()
     sa = rt.stats()
-    for trav in (abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW):
+    for trav in (abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW, abi.TRAV_Q16):
         rt.set_params(traversal=trav)
         rt.clear()
         rt.render(spp, 0)

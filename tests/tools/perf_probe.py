@@ -15,7 +15,7 @@ specs = []
 while args:
     a = args.pop(0)
     if a == "--trav":
-        trav = {"exact": 0, "fast": 1, "wide": 2, "cw": 3}[args.pop(0)]
+        trav = {"exact": 0, "fast": 1, "wide": 2, "cw": 3, "q16": 4}[args.pop(0)]
     elif a == "--reuse":
         reuse = int(args.pop(0))
     elif a == "--set":

@@ -5,7 +5,7 @@ import raytracingrenderer_b200 as rtb
 from raytracingrenderer_b200 import abi
 name = sys.argv[1] if len(sys.argv) > 1 else "materialball"
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-trav = {"exact": abi.TRAV_EXACT, "fast": abi.TRAV_FAST, "wide": abi.TRAV_WIDE, "cw": abi.TRAV_CW}[sys.argv[3] if len(sys.argv) > 3 else "fast"]
+trav = {"exact": abi.TRAV_EXACT, "fast": abi.TRAV_FAST, "wide": abi.TRAV_WIDE, "cw": abi.TRAV_CW, "q16": abi.TRAV_Q16}[sys.argv[3] if len(sys.argv) > 3 else "fast"]
 from raytracingrenderer_b200 import host_api
 s = host_api.load_scene(os.path.join("scenes", "_staged", name))
 rt = rtb.RayTracer(0)

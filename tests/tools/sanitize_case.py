@@ -10,7 +10,7 @@ import refbvh, raysets
 s = refbvh.random_scene()
 rt = rtb.RayTracer(0)
 rt.init(s)
-for trav in (abi.TRAV_EXACT, abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW):
+for trav in (abi.TRAV_EXACT, abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW, abi.TRAV_Q16):
     ids, t, rays = rt.primary_hits(trav, want_rays=True)
     hits = rt.trace(rays, traversal=trav)
     sets = raysets.mixed_set(rays, hits, 1, 500)
