@@ -331,7 +331,7 @@ def serial_stage_pass(flats, keys, spp, depth, canon, rtb, abi, torch, stream, s
             rt.set_params(traversal=abi.TRAV_FAST, max_depth=depth, primary_reuse=0)
             rts.append(rt)
         for rt in rts:
-            rt.render(min(spp, 8), 0)
+            rt.render(spp, 0)              # warm-up at full size: the slot pool is sized (allocated) by the call's sample count
         ms = timed_render(rts, spp, torch)
         tot, st = stats_sum(rts)
         for rt in rts:
@@ -364,12 +364,16 @@ def serial_stage_pass(flats, keys, spp, depth, canon, rtb, abi, torch, stream, s
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     ach = flops[dom] / (stage[dom] / 1e3) / 1e12 if stage[dom] > 0 else 0.0
     share = stage[dom] * iters / ms if ms > 0 else 0.0
+    per_kernel = {"k_wf_%s" % k: {"ms_per_launch": stage[k], "share_of_step": stage[k] * iters / ms if ms > 0 else 0.0,
+                                  "alg_flops_per_launch": flops[k], "achieved_tflops": flops[k] / (stage[k] / 1e3) / 1e12 if stage[k] > 0 else 0.0,
+                                  "frac_of_fp32_peak": flops[k] / (stage[k] / 1e3) / 1e12 / fp32_peak if stage[k] > 0 else 0.0}
+                  for k in stage}
     return {
         "bound": "fp32-issue", "kernel": "k_wf_%s" % dom, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
         "traffic": None, "peak_source": "148 SMs x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json)" % sm_max,
         "kernel_ms_per_launch": stage[dom], "launches": iters, "kernel_share_of_step": share,
         "serialised_step_ms": ms, "stage_ms_per_launch": stage, "alg_flops_per_launch": flops[dom], "alg_bytes_per_launch": byts[dom],
-        "alg_source": src,
+        "alg_source": src, "per_kernel": per_kernel,
         "whole_step": {"achieved_tflops": (f_ext + f_sha) / (ms / 1e3) / 1e12, "frac": (f_ext + f_sha) / (ms / 1e3) / 1e12 / fp32_peak},
         "how": "serialised pass (one sub-pool, one stream): kernel_ms_per_launch x launches = %.1f ms <= the pass's %.1f ms; "
                "scene + slot state are L1/L2 traffic, so the bound is FP32 issue, not HBM (SURVEY 8d)" % (stage[dom] * iters, ms),
@@ -393,13 +397,21 @@ def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm):
             rts.append(rt)
         torch.cuda.synchronize()
         upload_s = time.perf_counter() - t0
-        for rt in rts:
-            rt.render(min(spp, 4), 0)
-        ms = timed_render(rts, spp, torch)
+        heavy = flats[0][1].n_tris > 200000 and spp >= 256      # bathroom: one timed render is 4 s
+        if not heavy:
+            for rt in rts:
+                rt.render(spp, 0)          # warm-up at full size (the slot pool is sized by the call's sample count)
+        else:
+            for rt in rts:
+                rt.render(64, 0)
+        ms = timed_render(rts, spp, torch, repeats=1 if heavy else 2)
         tot, _ = stats_sum(rts)
         films = [rt.read_film() / np.float32(spp) for rt in rts]
         for rt in rts:
             rt.set_params(primary_reuse=1)
+        if not heavy:
+            for rt in rts:
+                rt.render(min(spp, 8), 0)
         ms1 = timed_render(rts, spp, torch)
         for rt in rts:
             rt.close()
@@ -452,7 +464,7 @@ def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm):
                 rt.set_stream(stream.cuda_stream)
                 rt.init(s)
                 rt.set_params(traversal=abi.TRAV_FAST, max_depth=0, primary_reuse=0)
-                rt.render(2, 0)
+                rt.render(4, 0)
                 ms = timed_render([rt], 4, torch)
                 st = rt.stats()
                 rt.close()

@@ -115,6 +115,7 @@ struct rtb_ctx
 	int cwBlocksPerSM[2] = {0, 0}; // closest hit, any hit
 	int cwStageKB = 32;            // RTB_CW_STAGE_KB
 	int cwShadowPersistent = -1;   // RTB_CW_SHADOW: 1 = persistent any-hit kernel, 0 = one thread per queued ray, -1 = per scene
+	bool haveWide = false, haveCw = false, haveQ16 = false; // re-encodings of the FAST tree, built on first use
 	uint32_t poolSlots = 8u << 20; // profiles/r01_pool_sweep.txt: per-launch ramp/tail amortise up to ~8 M slots
 	bool simpleExtend = false;
 	int pools = 2; // sub-pools advancing concurrently on their own streams (profiles/r01_pool_sweep.txt)
@@ -965,9 +966,6 @@ struct PreparedScene
 	const rtb_scene_desc* sc = nullptr;
 	std::vector<rtb_accel::F4> xnodes;
 	rtb_accel::FastTree fast;
-	rtb_accel::WideTree wide;
-	rtb_accel::CwTree cw;
-	rtb_accel::Q16Tree q16;
 	std::vector<float> marginal, cond;
 	int envW = 0, envH = 0;
 };
@@ -1017,20 +1015,9 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
 	}
-	rtb_accel::WideTree& wide = ps.wide;
-	{
-		rtb_accel::WideBuilder wb(fast);
-		wb.build(wide);
-	}
-	{
-		rtb_accel::CwBuilder cb(fast);
-		cb.build(ps.cw);
-		if (ps.cw.maxDepth + 2 > RTB_CW_STACK) ps.cw.valid = false; // RTB_TRAV_CW then walks the FAST tree
-	}
-	rtb_accel::buildQ16(fast, ps.q16);
-	// stack need: one pending sibling per level (binary), up to three per level (4-wide)
-	if (fast.maxDepth + 2 > RTB_STACK || 3 * wide.maxDepth + 6 > RTB_STACK)
-		return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (binary %u, wide %u)", fast.maxDepth, wide.maxDepth);
+	// stack need: one pending sibling per level.  (The WIDE / CW / Q16 re-encodings of this tree are built on first use,
+	// ensureTraversal: the upload of a 16 M-triangle scene should not pay for trees nobody selected.)
+	if (fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u levels)", fast.maxDepth);
 
 	for (uint32_t i = 0; i < sc->n_lights; i++)
 	{
@@ -1051,7 +1038,6 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	const rtb_scene_desc* sc = ps.sc;
 	const std::vector<rtb_accel::F4>& xnodes = ps.xnodes;
 	const rtb_accel::FastTree& fast = ps.fast;
-	const rtb_accel::WideTree& wide = ps.wide;
 	if (int rc = bind(ctx)) return rc;
 	CK(cudaStreamSynchronize(ctx->stream));
 	freeScene(ctx);
@@ -1068,32 +1054,10 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	S.n_xnodes = sc->n_ref_nodes;
 	S.n_fnodes = (uint32_t)(fast.nodes.size() / 4);
 	S.fast_root = fast.root;
-	const rtb_accel::F4* dw = nullptr;
-	if ((rc = uploadArray(ctx, wide.nodes.data(), wide.nodes.size(), &dw))) return rc;
-	S.wnodes = (const float4*)dw;
-	S.n_wnodes = (uint32_t)(wide.nodes.size() / 8);
-	S.wide_root = wide.root;
 	ctx->fastDepth = fast.maxDepth;
-	if (ps.cw.valid)
-	{
-		const rtb_accel::F4 *dcn = nullptr, *dcl = nullptr;
-		if ((rc = uploadArray(ctx, ps.cw.nodes.data(), ps.cw.nodes.size(), &dcn))) return rc;
-		if ((rc = uploadArray(ctx, ps.cw.leaves.data(), ps.cw.leaves.size(), &dcl))) return rc;
-		S.cwnodes = (const float4*)dcn, S.cwleaves = (const float4*)dcl;
-		S.n_cwnodes = (uint32_t)(ps.cw.nodes.size() / 5), S.n_cwleaves = (uint32_t)(ps.cw.leaves.size() / 2);
-		S.cw_valid = 1u, S.cw_depth = ps.cw.maxDepth;
-	}
+	S.wide_root = S.q16_root = fast.root < 0 ? fast.root : 0; // a leaf root needs no tree; otherwise set by ensureTraversal
+	ctx->haveWide = ctx->haveCw = ctx->haveQ16 = false;
 	ctx->cwBlocksPerSM[0] = ctx->cwBlocksPerSM[1] = 0; // staging is sized per scene
-	{
-		const rtb_accel::F4 *dqn = nullptr, *dql = nullptr;
-		if ((rc = uploadArray(ctx, ps.q16.nodes.data(), ps.q16.nodes.size(), &dqn))) return rc;
-		if ((rc = uploadArray(ctx, ps.q16.leaves.data(), ps.q16.leaves.size(), &dql))) return rc;
-		S.qnodes = (const float4*)dqn, S.qleaves = (const float4*)dql;
-		S.n_qnodes = (uint32_t)(ps.q16.nodes.size() / 2);
-		S.q16_root = ps.q16.root;
-		memcpy(S.qmin, ps.q16.qmin, sizeof(S.qmin));
-		memcpy(S.qstep, ps.q16.qstep, sizeof(S.qstep));
-	}
 	const rtb_tri_isect* dti = nullptr;
 	const rtb_tri_shade* dts = nullptr;
 	if ((rc = uploadArray(ctx, sc->tri_isect, sc->n_tris, &dti))) return rc;
@@ -1149,6 +1113,75 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	return RTB_OK;
 }
 
+
+
+// The WIDE, CW and Q16 trees are re-encodings of the FAST tree; they are built the first time a call selects them (from
+// the FAST nodes already on the device) instead of at every upload.
+static int ensureTraversal(rtb_ctx* ctx, int trav)
+{
+	if (trav != RTB_TRAV_WIDE && trav != RTB_TRAV_CW && trav != RTB_TRAV_Q16) return RTB_OK;
+	bool& have = trav == RTB_TRAV_WIDE ? ctx->haveWide : trav == RTB_TRAV_CW ? ctx->haveCw : ctx->haveQ16;
+	if (have) return RTB_OK;
+	DevScene& S = ctx->S;
+	have = true;
+	if (S.fast_root < 0 || S.n_fnodes == 0) return RTB_OK; // single-leaf / empty scene: the traversals use the reference tree
+	if (int rc = bind(ctx)) return rc;
+	rtb_accel::FastTree fast;
+	fast.nodes.resize((size_t)S.n_fnodes * 4);
+	fast.root = S.fast_root;
+	fast.maxDepth = ctx->fastDepth;
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpy(fast.nodes.data(), S.fnodes, fast.nodes.size() * sizeof(rtb_accel::F4), cudaMemcpyDeviceToHost));
+	int rc;
+	if (trav == RTB_TRAV_WIDE)
+	{
+		rtb_accel::WideTree wide;
+		rtb_accel::WideBuilder wb(fast);
+		wb.build(wide);
+		if (3 * wide.maxDepth + 6 > RTB_STACK)
+		{
+			have = false;
+			return fail(ctx, RTB_ERR_STATE, "RTB_TRAV_WIDE: tree too deep (%u levels)", wide.maxDepth);
+		}
+		const rtb_accel::F4* dw = nullptr;
+		if ((rc = uploadArray(ctx, wide.nodes.data(), wide.nodes.size(), &dw))) return rc;
+		CK(cudaStreamSynchronize(ctx->stream)); // `wide` dies at return
+		S.wnodes = (const float4*)dw;
+		S.n_wnodes = (uint32_t)(wide.nodes.size() / 8);
+		S.wide_root = wide.root;
+	}
+	else if (trav == RTB_TRAV_CW)
+	{
+		rtb_accel::CwTree cw;
+		rtb_accel::CwBuilder cb(fast);
+		cb.build(cw);
+		if (cw.valid && cw.maxDepth + 2 <= RTB_CW_STACK) // deeper: RTB_TRAV_CW walks the FAST tree
+		{
+			const rtb_accel::F4 *dcn = nullptr, *dcl = nullptr;
+			if ((rc = uploadArray(ctx, cw.nodes.data(), cw.nodes.size(), &dcn))) return rc;
+			if ((rc = uploadArray(ctx, cw.leaves.data(), cw.leaves.size(), &dcl))) return rc;
+			CK(cudaStreamSynchronize(ctx->stream));
+			S.cwnodes = (const float4*)dcn, S.cwleaves = (const float4*)dcl;
+			S.n_cwnodes = (uint32_t)(cw.nodes.size() / 5), S.n_cwleaves = (uint32_t)(cw.leaves.size() / 2);
+			S.cw_valid = 1u, S.cw_depth = cw.maxDepth;
+		}
+	}
+	else
+	{
+		rtb_accel::Q16Tree q16;
+		rtb_accel::buildQ16(fast, q16);
+		const rtb_accel::F4 *dqn = nullptr, *dql = nullptr;
+		if ((rc = uploadArray(ctx, q16.nodes.data(), q16.nodes.size(), &dqn))) return rc;
+		if ((rc = uploadArray(ctx, q16.leaves.data(), q16.leaves.size(), &dql))) return rc;
+		CK(cudaStreamSynchronize(ctx->stream));
+		S.qnodes = (const float4*)dqn, S.qleaves = (const float4*)dql;
+		S.n_qnodes = (uint32_t)(q16.nodes.size() / 2);
+		S.q16_root = q16.root;
+		memcpy(S.qmin, q16.qmin, sizeof(S.qmin));
+		memcpy(S.qstep, q16.qstep, sizeof(S.qstep));
+	}
+	return RTB_OK;
+}
 
 extern "C" {
 
@@ -1418,6 +1451,7 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 	// threads per render() call too, Renderer.h:842-849); a plain context is a group of one
 	int rc = forEachMember(ctx, [ctx, spp_begin, spp_count](rtb_ctx* m, int d) {
 		if (int rc = bind(m)) return rc;
+		if (int rc = ensureTraversal(m, ctx->userParams.traversal)) return rc;
 		m->params = composedParams(ctx, d, spp_count);
 		bool mega = m->params.scheduler == RTB_SCHED_MEGAKERNEL;
 		int rc = mega ? renderMegakernel(m, spp_begin, spp_count) : renderWavefront(m, spp_begin, spp_count);
@@ -1434,6 +1468,7 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 static int lightOne(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 {
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = ensureTraversal(ctx, ctx->params.traversal)) return rc;
 	rtb_camera_ext ce;
 	if (!rtb_camera_derive(&ctx->S.cam, &ce)) return fail(ctx, RTB_ERR_ARG, "camera matrices are singular");
 	RenderArgs A;
@@ -1478,6 +1513,7 @@ int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 static int irOne(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths)
 {
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = ensureTraversal(ctx, ctx->params.traversal)) return rc;
 	if (ctx->vplPaths < n_paths)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -1538,6 +1574,7 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 	if (P.partition != RTB_PART_NONE && P.part_world > 1)
 		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: the tile sample counts come from the whole image; use one device per image");
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = ensureTraversal(ctx, P.traversal)) return rc;
 	// Every call draws from its own range of sample indices, like the reference's ever-advancing MTRandom makes
 	// successive adaptiveRender() calls independent: call number k (= Film::SPP before the call, one per call)
 	// uses [k * (init + max), (k + 1) * (init + max)).
@@ -1771,6 +1808,7 @@ int rtb_primary_hits(rtb_ctx* ctx, int traversal, uint32_t* ids, float* t, rtb_r
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = checkTrav(ctx, traversal)) return rc;
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = ensureTraversal(ctx, traversal)) return rc;
 	size_t n = (size_t)ctx->width * ctx->height;
 	Scratch sc;
 	uint32_t* dIds;
@@ -1798,6 +1836,7 @@ int rtb_trace(rtb_ctx* ctx, int traversal, int any_hit, const rtb_ray* rays, uin
 	if (n == 0) return RTB_OK;
 	if (!rays || !hits) return fail(ctx, RTB_ERR_ARG, "rtb_trace: NULL buffer");
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = ensureTraversal(ctx, traversal)) return rc;
 	Scratch sc;
 	rtb_ray* dR;
 	rtb_hit* dH;
@@ -1820,6 +1859,7 @@ int rtb_visible(rtb_ctx* ctx, int traversal, const float* p1p2, uint64_t n, uint
 	if (n == 0) return RTB_OK;
 	if (!p1p2 || !out) return fail(ctx, RTB_ERR_ARG, "rtb_visible: NULL buffer");
 	if (int rc = bind(ctx)) return rc;
+	if (int rc = ensureTraversal(ctx, traversal)) return rc;
 	Scratch sc;
 	float* dP;
 	uint8_t* dO;
