@@ -114,6 +114,8 @@ struct rtb_ctx
 	uint32_t cwStageNodes = 0, cwStageLeaves = 0, cwSmemBytes = 0;
 	int cwBlocksPerSM[2] = {0, 0}; // closest hit, any hit
 	int cwStageKB = 32;            // RTB_CW_STAGE_KB
+	int shadowPersistent = -1;     // RTB_SHADOW_PERSISTENT: the persistent any-hit kernel (1), one thread per queued ray (0), per scene (-1)
+	bool shadowPersistentAuto = false;
 	int cwShadowPersistent = -1;   // RTB_CW_SHADOW: 1 = persistent any-hit kernel, 0 = one thread per queued ray, -1 = per scene
 	bool haveWide = false, haveCw = false, haveQ16 = false; // re-encodings of the FAST tree, built on first use
 	uint32_t poolSlots = 8u << 20; // profiles/r01_pool_sweep.txt: per-launch ramp/tail amortise up to ~8 M slots
@@ -371,6 +373,12 @@ struct AdaptivePlan
 	uint32_t nTiles32;
 };
 
+template <int TRAV>
+static int32_t travRootHost(const DevScene& S)
+{
+	return TRAV == RTB_TRAV_WIDE ? S.wide_root : TRAV == RTB_TRAV_Q16 ? S.q16_root : S.fast_root;
+}
+
 static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count, const AdaptivePlan* plan = nullptr)
 {
 	const rtb_params& P = ctx->params;
@@ -470,7 +478,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		CK(cudaMemsetAsync(ctx->wfSortWork, 0, (size_t)RTB_MAX_POOLS * 4 * WF_SORT_BUCKETS * sizeof(uint32_t), ctx->stream));
 	}
 	if (!ctx->wfGlobal) CK(cudaMalloc((void**)&ctx->wfGlobal, sizeof(WfGlobal)));
-	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, (1 + RTB_MAX_POOLS) * sizeof(unsigned long long)));
+	if (!ctx->hostProbe) CK(cudaMallocHost((void**)&ctx->hostProbe, (1 + RTB_MAX_POOLS + RTB_COUNTER_STRIPES * 8) * sizeof(unsigned long long)));
 	uint32_t vertices = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_PATH_MIS) ? (uint32_t)P.max_depth + 2u : 1u;
 	// list-scheduling bound on the iterations of a sub-pool: total work / slots + longest job
 	unsigned long long bound64 = (totalJobs * vertices + perPool - 1) / perPool + vertices + 1;
@@ -502,6 +510,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 			if (v >= 0 && v <= 200) ctx->cwStageKB = v;
 		}
 		if (const char* e = getenv("RTB_CW_SHADOW")) ctx->cwShadowPersistent = atoi(e);
+		if (const char* e = getenv("RTB_SHADOW_PERSISTENT")) ctx->shadowPersistent = atoi(e);
 		if (const char* e = getenv("RTB_SIMPLE_EXTEND")) ctx->simpleExtend = atoi(e) != 0;
 		if (const char* e = getenv("RTB_PRIMARY_PASSES"))
 		{
@@ -669,7 +678,14 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 						k_sort_scatter<0><<<gridSort, 256, 0, sst>>>(ctx->S, A[k], it);
 						ctx->launches += 3;
 					}
-					if (cwShadow)
+					const bool persistShadow = !cwShadow && P.integrator != RTB_INT_PATH_MIS && ti != RTB_TRAV_EXACT && ti != RTB_TRAV_CW &&
+					                           (ctx->shadowPersistent < 0 ? ctx->shadowPersistentAuto : ctx->shadowPersistent != 0);
+					if (persistShadow)
+					{
+						RTB_TRAV_SWITCH(ti, if (travRootHost<TR>(ctx->S) >= 0) k_wf_shadow_persist<TR><<<gridExtend, 128, 0, sst>>>(ctx->S, A[k], it);
+						                else k_wf_shadow<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
+					}
+					else if (cwShadow)
 					{
 						unsigned g = (unsigned)(ctx->smCount * ctx->cwBlocksPerSM[1]);
 						k_wf_trace_cw<true><<<g, WF_CW_THREADS, ctx->cwSmemBytes, sst>>>(ctx->S, A[k], it, ctx->cwStageNodes, ctx->cwStageLeaves);
@@ -698,8 +714,20 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 			CK(cudaMemcpyAsync(&ctx->hostProbe[1 + k], &A[k].ctrl[it - 1], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->poolStreams[k]));
 		}
 		CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->poolStreams[0]));
+		CK(cudaMemcpyAsync(&ctx->hostProbe[1 + RTB_MAX_POOLS], ctx->counters, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+		                   ctx->poolStreams[0]));
 		for (int k = 0; k < K; k++) CK(cudaStreamSynchronize(ctx->poolStreams[k]));
 		ctx->wfHostSyncs++;
+		{
+			// Which any-hit kernel suits this scene: long shadow rays (bathroom: 65 box tests per ray, the soups: 130+) gain
+			// 6 ... 12 % from the persistent kernel, short ones (coffee: 38, the small scenes: 9 ... 14) lose 5 ... 10 %
+			// (profiles/r02_persistent_shadow.txt).  Decided from the work counters the probe brings along anyway; the film
+			// does not depend on the choice.
+			unsigned long long rays = 0, boxes = 0;
+			for (int r = 0; r < RTB_COUNTER_STRIPES; r++)
+				rays += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 2], boxes += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 5];
+			if (rays > 100000ull) ctx->shadowPersistentAuto = boxes > 50ull * rays;
+		}
 		unsigned long long claimed = ctx->hostProbe[0];
 		uint32_t alive = 0;
 		for (int k = 0; k < K; k++) alive += (uint32_t)(ctx->hostProbe[1 + k] >> 32); // WfCtrl{nShadow, alive}

@@ -295,6 +295,9 @@ struct LocalStack
 	float t[RTB_STACK];
 	RTB_DEV void put(int i, int32_t n, float te) { node[i] = n, t[i] = te; }
 	RTB_DEV void get(int i, int32_t& n, float& te) const { n = node[i], te = t[i]; }
+	// any-hit rays: maxT never changes, so an entry that was admitted when pushed is still admitted when popped
+	RTB_DEV void putNode(int i, int32_t n) { node[i] = n; }
+	RTB_DEV int32_t getNode(int i) const { return node[i]; }
 };
 template <int NS, int THREADS>
 struct SharedStack
@@ -316,6 +319,14 @@ struct SharedStack
 		}
 		else
 			n = node[i - NS], te = t[i - NS];
+	}
+	RTB_DEV void putNode(int i, int32_t n) { put(i, n, 0.0f); }
+	RTB_DEV int32_t getNode(int i) const
+	{
+		int32_t n;
+		float te;
+		get(i, n, te);
+		return n;
 	}
 };
 
@@ -340,6 +351,11 @@ template <bool ANYHIT, class STK>
 RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const STK& stk)
 {
 	t.cur = RTB_TRAV_DONE_;
+	if (ANYHIT)
+	{
+		if (t.sp > 0) t.cur = stk.getNode(--t.sp);
+		return;
+	}
 	while (t.sp > 0)
 	{
 		t.sp--;
@@ -368,7 +384,8 @@ RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t
 	if (h0 && h1)
 	{
 		bool swap = !ANYHIT && (t1 < t0);
-		stk.put(t.sp, swap ? c0 : c1, swap ? t0 : t1);
+		if (ANYHIT) stk.putNode(t.sp, c1);
+		else stk.put(t.sp, swap ? c0 : c1, swap ? t0 : t1);
 		t.sp++;
 		t.cur = swap ? c1 : c0;
 	}
@@ -410,7 +427,8 @@ RTB_DEV void stepQ16(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t&
 	if (h0 && h1)
 	{
 		bool swap = !ANYHIT && (t1 < t0);
-		stk.put(t.sp, swap ? c0 : c1, swap ? t0 : t1);
+		if (ANYHIT) stk.putNode(t.sp, c1);
+		else stk.put(t.sp, swap ? c0 : c1, swap ? t0 : t1);
 		t.sp++;
 		t.cur = swap ? c1 : c0;
 	}
@@ -464,10 +482,10 @@ RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t
 	if (ANYHIT)
 	{
 		// order is irrelevant for the result; push every admitted child, continue with the last
-		if (h0) stk.put(t.sp, c0, e0), t.sp++;
-		if (h1) stk.put(t.sp, c1, e1), t.sp++;
-		if (h2) stk.put(t.sp, c2, e2), t.sp++;
-		if (h3) stk.put(t.sp, c3, e3), t.sp++;
+		if (h0) stk.putNode(t.sp, c0), t.sp++;
+		if (h1) stk.putNode(t.sp, c1), t.sp++;
+		if (h2) stk.putNode(t.sp, c2), t.sp++;
+		if (h3) stk.putNode(t.sp, c3), t.sp++;
 		lanePop<ANYHIT>(t, stk);
 		return;
 	}

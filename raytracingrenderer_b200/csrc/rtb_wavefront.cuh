@@ -488,6 +488,15 @@ __global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ DevScen
 #ifndef WF_CHUNK
 #define WF_CHUNK 128u /* slots a warp claims per atomic */
 #endif
+#ifndef WF_SHADE_REGROUP
+// k_wf_shade: sort each block's 128 slots by vertex kind (surface hit / miss / dead) before shading, so that a warp runs
+// one path.  Measured (profiles/r02_shade_regroup.txt): -1 ... -4 % on every scene — the permuted slot accesses touch
+// four times the sectors per load and the two extra barriers cost more than the skipped path saves.  Off.
+#define WF_SHADE_REGROUP 0
+#endif
+#ifndef WF_ISTEPS
+#define WF_ISTEPS 3 /* interior steps per majority vote in k_wf_extend (profiles/r02_vote_granularity.txt: 1 -> 3 is +1.5 ... +5 %, 6+ loses again) */
+#endif
 #ifndef WF_SSTACK
 #define WF_SSTACK 12 /* stack entries per thread kept in shared memory by k_wf_extend (8 B x 128 threads each) */
 #endif
@@ -613,6 +622,12 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 			if (doInterior)
 			{
 				if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stk, tl.box);
+#if WF_ISTEPS > 1
+				// further interior steps without a new vote: the lanes that reached a leaf wait (measured: WF_ISTEPS)
+#pragma unroll
+				for (int rep = 1; rep < WF_ISTEPS; rep++)
+					if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, false>(S, t, stk, tl.box);
+#endif
 			}
 			else if (have && t.cur < 0)
 			{
@@ -797,6 +812,120 @@ __global__ void __launch_bounds__(WF_CW_THREADS, WF_CW_MIN_BLOCKS) k_wf_trace_cw
 	flushTally(tl, A.counters);
 }
 
+// The same schedule for the queued shadow rays (Scene::visible, Scene.h:161-169): persistent warps, per-lane prefetch,
+// majority vote, shared-memory short stack.  Round 1 measured a persistent any-hit kernel slower than one thread per
+// ray on every scene (profiles/r01_shadow_stage.txt: short rays, the refill bookkeeping outweighs the regained
+// lanes); on the heavy scenes the one-thread kernel sits at 4.6 of 32 lanes and 68 % of the issue slots
+// (profiles/r02_base_bathroom_summary.md), so with the cheaper stack and three interior steps per vote it is selectable
+// per scene (rtb_api.cu: shadowPersistent) — the numbers decide (profiles/r02_persistent_shadow.txt).
+template <int TRAV>
+__global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_shadow_persist(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
+{
+	const rtb_params& P = A.P;
+	const uint32_t nItems = A.ctrl[iter].nShadow;
+	if (nItems == 0) return;
+	Tally tl = {0, 0, 0, 0, 0, 0, 0};
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t ltMask = (1u << lane) - 1u;
+	uint32_t cursor = 0, end = 0;
+	bool exhausted = false;
+#if WF_SSTACK > 0
+	__shared__ float2 sStack[WF_SSTACK * 128];
+	SharedStack<WF_SSTACK, 128> stk;
+	stk.s = sStack + threadIdx.x;
+#else
+	LocalStack stk;
+#endif
+	LaneTrav<true> t;
+	t.cur = RTB_TRAV_DONE_;
+	t.sp = 0;
+	uint32_t item = 0, preItem = 0, pixel = 0;
+	float4 preO = make_float4(0, 0, 0, 0), preD = make_float4(0, 0, 0, 0);
+	bool have = false, pre = false;
+	for (;;)
+	{
+		if (!have && pre)
+		{
+			pre = false;
+			t.r = mkRay(mk(preO), mk(preD));
+			travSetBest<true>(t, preO.w, P.cull_rel);
+			t.sp = 0;
+			item = preItem, pixel = __float_as_uint(preD.w);
+			tl.shadow++;
+			if (travDegenerate<TRAV>(t.r))
+			{
+				if (visibleExact(S, t.r, P.epsilon, preO.w, tl.sbox, tl.stri)) filmAdd(A.accum, pixel, mk(A.shC[item]));
+			}
+			else
+			{
+				have = true;
+				t.cur = travRoot<TRAV>(S);
+				travStart<TRAV, true>(S, t);
+			}
+		}
+		unsigned want = __ballot_sync(0xFFFFFFFFu, !pre);
+		if (want && cursor >= end && !exhausted)
+		{
+			uint32_t c = 0;
+			if (lane == 0) c = atomicAdd(&A.ctrl[iter].shadowHead, (unsigned)WF_CHUNK);
+			c = __shfl_sync(0xFFFFFFFFu, c, 0);
+			if (c >= nItems) exhausted = true;
+			else
+			{
+				cursor = c;
+				end = (c + WF_CHUNK < nItems) ? c + WF_CHUNK : nItems;
+			}
+		}
+		if (want && cursor < end)
+		{
+			uint32_t idx = cursor + __popc(want & ltMask);
+			if (!pre && idx < end)
+			{
+				const uint32_t it = A.shPerm ? A.shPerm[idx] : idx;
+				preO = A.shO[it];
+				preD = A.shD[it];
+				preItem = it;
+				pre = true;
+			}
+			cursor += __popc(want);
+		}
+		unsigned busy = __ballot_sync(0xFFFFFFFFu, have);
+		if (!busy)
+		{
+			if (!__ballot_sync(0xFFFFFFFFu, pre) && cursor >= end && exhausted) break;
+			continue;
+		}
+		for (;;)
+		{
+			unsigned mI = __ballot_sync(0xFFFFFFFFu, have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_);
+			unsigned mL = __ballot_sync(0xFFFFFFFFu, have && t.cur < 0);
+			bool occluded = false;
+			if (__popc(mI) >= __popc(mL))
+			{
+#pragma unroll
+				for (int rep = 0; rep < WF_ISTEPS; rep++)
+					if (have && t.cur >= 0 && t.cur != RTB_TRAV_DONE_) stepInterior<TRAV, true>(S, t, stk, tl.sbox);
+			}
+			else if (have && t.cur < 0)
+			{
+				int32_t ref;
+				if (travLeafRef<TRAV, true>(S, t, ref, tl.sbox) && leafOccludes(S, ref, t.r, P.epsilon, t.bestT, tl.stri)) occluded = true;
+				else lanePop<true>(t, stk);
+			}
+			if (have && (occluded || t.cur == RTB_TRAV_DONE_))
+			{
+				if (!occluded) filmAdd(A.accum, pixel, mk(A.shC[item]));
+				have = false;
+				t.cur = RTB_TRAV_DONE_;
+			}
+			unsigned idle = __ballot_sync(0xFFFFFFFFu, !have);
+			if (idle == 0xFFFFFFFFu) break;
+			if (__popc(idle) >= WF_REFILL_IDLE && (__ballot_sync(0xFFFFFFFFu, pre) & idle)) break;
+		}
+	}
+	flushTally(tl, A.counters);
+}
+
 // One thread per slot (the v3 extend stage), kept selectable for A/B measurements against the
 // persistent kernel above (RTB_SIMPLE_EXTEND=1).
 template <int TRAV>
@@ -906,9 +1035,41 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 	__shared__ uint32_t sBaseN[2], sBaseQ[2]; // sBaseJ split into (sample ordinal, pixel ordinal): one 64-bit division per block
 	// whole blocks stride together: the cooperative queue/job operations below need every lane
 	uint32_t nRounds = (A.nSlots + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+#if WF_SHADE_REGROUP
+	__shared__ uint8_t sPerm[128];
+	__shared__ uint32_t sClsCnt[2][4];
+#endif
 	for (uint32_t round = 0; round < nRounds; round++)
 	{
 		uint32_t slot = round * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+#if WF_SHADE_REGROUP
+		// Regroup the block's 128 slots so that a warp shades one KIND of vertex: surface hits first, then misses
+		// (environment lookup + regeneration only), then dead slots.  Unsorted, nearly every warp holds both kinds and
+		// executes both paths (profiles/r01_v8_final_summary.md: 20 of 32 lanes per instruction); any thread of the
+		// block may shade any of its slots, the slot keeps its place in memory.
+		{
+			const uint32_t warp = threadIdx.x >> 5;
+			uint32_t cls = 2u; // dead / out of range
+			if (slot < A.nSlots && (__float_as_uint(A.rayD[slot].w) & WF_ALIVE)) cls = (__float_as_uint(A.hit[slot].x) == RTB_MISS_ID) ? 1u : 0u;
+			const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == 0u), m1 = __ballot_sync(0xFFFFFFFFu, cls == 1u);
+			if (lane == 0) sClsCnt[0][warp] = __popc(m0), sClsCnt[1][warp] = __popc(m1);
+			__syncthreads();
+			uint32_t n0 = 0, n1 = 0, b0 = 0, b1 = 0;
+			for (uint32_t w = 0; w < 4; w++)
+			{
+				if (w < warp) b0 += sClsCnt[0][w], b1 += sClsCnt[1][w];
+				n0 += sClsCnt[0][w], n1 += sClsCnt[1][w];
+			}
+			const uint32_t below = (1u << lane) - 1u;
+			uint32_t dst;
+			if (cls == 0u) dst = b0 + __popc(m0 & below);
+			else if (cls == 1u) dst = n0 + b1 + __popc(m1 & below);
+			else dst = n0 + n1 + (warp * 32u - b0 - b1) + __popc(~(m0 | m1) & below);
+			sPerm[dst] = (uint8_t)threadIdx.x;
+			__syncthreads();
+			slot = slot - threadIdx.x + sPerm[threadIdx.x];
+		}
+#endif
 		bool inRange = slot < A.nSlots;
 		bool haveVertex = false, slotLive = false;
 		uint32_t queued = 0;
