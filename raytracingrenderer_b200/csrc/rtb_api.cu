@@ -994,6 +994,7 @@ struct PreparedScene
 	const rtb_scene_desc* sc = nullptr;
 	std::vector<rtb_accel::F4> xnodes;
 	rtb_accel::FastTree fast;
+	std::vector<rtb_accel::F4> triPacked; // device triangle records (layout: triTest, rtb_dev_scene.cuh)
 	std::vector<float> marginal, cond;
 	int envW = 0, envH = 0;
 };
@@ -1043,6 +1044,17 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
 	}
+	// triangle records re-packed so that the plane test reads one 32-byte half and the edge tests the other
+	ps.triPacked.resize((size_t)sc->n_tris * 4);
+	for (uint32_t i = 0; i < sc->n_tris; i++)
+	{
+		const rtb_tri_isect& q = sc->tri_isect[i];
+		rtb_accel::F4* o = &ps.triPacked[(size_t)i * 4];
+		o[0] = {q.n[0], q.n[1], q.n[2], q.d};
+		o[1] = {q.v0[0], q.v0[1], q.v0[2], q.inv_area};
+		o[2] = {q.v1[0], q.v1[1], q.v1[2], rtb_accel::bitsToFloat(q.material)};
+		o[3] = {q.v2[0], q.v2[1], q.v2[2], q.area};
+	}
 	// stack need: one pending sibling per level.  (The WIDE / CW / Q16 re-encodings of this tree are built on first use,
 	// ensureTraversal: the upload of a 16 M-triangle scene should not pay for trees nobody selected.)
 	if (fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u levels)", fast.maxDepth);
@@ -1086,9 +1098,9 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	S.wide_root = S.q16_root = fast.root < 0 ? fast.root : 0; // a leaf root needs no tree; otherwise set by ensureTraversal
 	ctx->haveWide = ctx->haveCw = ctx->haveQ16 = false;
 	ctx->cwBlocksPerSM[0] = ctx->cwBlocksPerSM[1] = 0; // staging is sized per scene
-	const rtb_tri_isect* dti = nullptr;
+	const rtb_accel::F4* dti = nullptr;
 	const rtb_tri_shade* dts = nullptr;
-	if ((rc = uploadArray(ctx, sc->tri_isect, sc->n_tris, &dti))) return rc;
+	if ((rc = uploadArray(ctx, ps.triPacked.data(), ps.triPacked.size(), &dti))) return rc;
 	if ((rc = uploadArray(ctx, sc->tri_shade, sc->n_tris, &dts))) return rc;
 	S.tri = (const float4*)dti;
 	S.tsh = (const float4*)dts;

@@ -5,6 +5,12 @@
 #include "../../include/rtb.h"
 #include "rtb_dev_math.cuh"
 
+#ifndef RTB_LDG256
+#define RTB_LDG256 1
+#endif
+#ifndef RTB_TRI256
+#define RTB_TRI256 0 /* triangle records: [n, d] alone decides most tests, so one LDG.128 + three more measured 1.3 ... 2.5 % faster than 2 x 256 (profiles/r02_ldg256.txt) */
+#endif
 #define RTB_INTERIOR 0xFFFFFFFFu
 #define RTB_MISS_ID 0xFFFFFFFFu
 #define RTB_PI_F 3.14159274101257324f   /* (float)M_PI */
@@ -44,7 +50,7 @@ struct DevScene
 	int32_t q16_root;
 	uint32_t n_qnodes;
 	float qmin[3], qstep[3];
-	const float4* tri;  // 4 x float4 per triangle = rtb_tri_isect
+	const float4* tri;  // 4 x float4 per triangle: rtb_tri_isect re-packed for the intersection test (layout at triTest)
 	const float4* tsh;  // 4 x float4 per triangle = rtb_tri_shade
 	const rtb_material* mats;
 	const rtb_texture* texs;
@@ -74,6 +80,21 @@ struct HitD
 };
 
 RTB_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+// 32 bytes in ONE load instruction (sm_100: LDG.E.256), p 32-byte aligned.  profiles/r02_v2_bathroom_summary.md: the
+// traversal of the heavy scenes is bound by the L1 data pipe (87 % of the LSU wavefront peak) — every divergent lane costs
+// one wavefront per load INSTRUCTION, so a 64-byte node fetched as 2 x 256 bits costs half of 4 x 128.
+struct F8
+{
+	float4 a, b;
+};
+RTB_DEV F8 ldg8(const float4* p)
+{
+	F8 r;
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+	    : "l"(p));
+	return r;
+}
 
 // ---------------------------------------------------------------------------------------
 // AABB::rayAABB (RTBase/Geometry.h:173-184).  Returns the reference's accept decision;
@@ -97,21 +118,31 @@ RTB_DEV bool slabTest(float minx, float miny, float minz, float maxx, float maxy
 // ---------------------------------------------------------------------------------------
 RTB_DEV bool triTest(const float4* __restrict__ tri, uint32_t id, const RayD& r, float& t, float& u, float& v)
 {
+	// device record (rtb_api.cu prepareScene): [n.xyz, d] [v0.xyz, inv_area] [v1.xyz, bits(material)] [v2.xyz, area] — the plane
+	// test (which rejects most candidates) needs the first 16 bytes only
 	const float4* q = tri + (size_t)id * 4;
-	float4 q3 = ldg4(q + 3);
-	V3 n = mk(q3);
+#if RTB_TRI256
+	const F8 h0 = ldg8(q);
+	const float4 qn = h0.a, qv0 = h0.b;
+#else
+	const float4 qn = ldg4(q);
+#endif
+	V3 n = mk(qn);
 	float denom = dot(n, r.d);
 	if (denom == 0.0f) return false;
-	float4 q0 = ldg4(q);
-	t = (q0.w - dot(n, r.o)) / denom;
+	t = (qn.w - dot(n, r.o)) / denom;
 	if (t < 0.0f) return false;
-	float4 q1 = ldg4(q + 1);
-	float4 q2 = ldg4(q + 2);
-	V3 v0 = mk(q0), v1 = mk(q1), v2 = mk(q2);
+#if RTB_TRI256
+	const F8 h1 = ldg8(q + 2);
+	const float4 q1 = h1.a, q2 = h1.b;
+#else
+	const float4 qv0 = ldg4(q + 1), q1 = ldg4(q + 2), q2 = ldg4(q + 3);
+#endif
+	V3 v0 = mk(qv0), v1 = mk(q1), v2 = mk(q2);
 	V3 p = r.o + (r.d * t);
 	V3 e1 = v2 - v1;
 	V3 e2 = v0 - v2;
-	float invArea = q1.w;
+	float invArea = qv0.w;
 	u = dot(cross(e1, p - v1), n) * invArea;
 	if (u < 0.0f || u > 1.0f) return false;
 	v = dot(cross(e2, p - v2), n) * invArea;
@@ -373,7 +404,12 @@ template <bool ANYHIT, class STK>
 RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
 {
 	const float4* nd = S.fnodes + (size_t)t.cur * 4;
+#if RTB_LDG256
+	const F8 lo = ldg8(nd), hi = ldg8(nd + 2);
+	const float4 n0 = lo.a, n1 = lo.b, nz = hi.a, ch = hi.b;
+#else
 	float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), nz = ldg4(nd + 2), ch = ldg4(nd + 3);
+#endif
 	float t0, t1;
 	nBox += 2;
 	bool h0 = slabTestNoNaN(n0.x, n0.z, nz.x, n0.y, n0.w, nz.y, t.r, t0);
@@ -407,7 +443,12 @@ template <bool ANYHIT, class STK>
 RTB_DEV void stepQ16(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
 {
 	const float4* nd = S.qnodes + (size_t)t.cur * 2;
+#if RTB_LDG256
+	const F8 nn = ldg8(nd);
+	const float4 A = nn.a, B = nn.b;
+#else
 	const float4 A = ldg4(nd), B = ldg4(nd + 1);
+#endif
 	const uint32_t snx = t.qsel[0], sny = t.qsel[1], snz = t.qsel[2];
 	const uint32_t sfx = snx ^ 0x0022u, sfy = sny ^ 0x0022u, sfz = snz ^ 0x0022u;
 	const uint32_t a0 = __float_as_uint(A.x), a1 = __float_as_uint(A.y), a2 = __float_as_uint(A.z);
@@ -466,8 +507,13 @@ template <bool ANYHIT, class STK>
 RTB_DEV void stepWide(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
 {
 	const float4* nd = S.wnodes + (size_t)t.cur * 8;
+#if RTB_LDG256
+	const F8 w0 = ldg8(nd), w1 = ldg8(nd + 2), w2 = ldg8(nd + 4), w3 = ldg8(nd + 6);
+	const float4 mnx = w0.a, mxx = w0.b, mny = w1.a, mxy = w1.b, mnz = w2.a, mxz = w2.b, rf = w3.a;
+#else
 	float4 mnx = ldg4(nd), mxx = ldg4(nd + 1), mny = ldg4(nd + 2), mxy = ldg4(nd + 3), mnz = ldg4(nd + 4), mxz = ldg4(nd + 5);
 	float4 rf = ldg4(nd + 6);
+#endif
 	int32_t c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
 	float e0, e1, e2, e3;
 	bool h0 = slabTestNoNaN(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, t.r, e0);
@@ -561,7 +607,12 @@ RTB_DEV bool travLeafRef(const DevScene& S, const LaneTrav<ANYHIT>& t, int32_t& 
 		return true;
 	}
 	const float4* lf = S.qleaves + (size_t)(uint32_t)(~t.cur) * 2;
+#if RTB_LDG256
+	const F8 ll = ldg8(lf);
+	const float4 A = ll.a, B = ll.b;
+#else
 	const float4 A = ldg4(lf), B = ldg4(lf + 1);
+#endif
 	float te;
 	nBox++;
 	if (!slabTestNoNaN(A.x, A.y, A.z, B.x, B.y, B.z, t.r, te)) return false;
@@ -728,7 +779,7 @@ RTB_DEV void calcShading(const DevScene& S, uint32_t id, float t, float alpha, f
 {
 	const float4* qi = S.tri + (size_t)id * 4;
 	const float4* qs = S.tsh + (size_t)id * 4;
-	float4 i2 = ldg4(qi + 2), i3 = ldg4(qi + 3);
+	float4 i2 = ldg4(qi + 2), i3 = ldg4(qi); // device record: material in [2].w, n in [0] (triTest)
 	float4 s0 = ldg4(qs), s1 = ldg4(qs + 1), s2 = ldg4(qs + 2), s3 = ldg4(qs + 3);
 	sd.x = r.o + (r.d * t);
 	sd.gN = mk(i3) * s3.w;
@@ -931,7 +982,7 @@ RTB_DEV V3 backgroundEval(const DevScene& S, V3 wi)
 RTB_DEV V3 trianglePoint(const DevScene& S, uint32_t id, float r1, float r2)
 {
 	const float4* q = S.tri + (size_t)id * 4;
-	V3 v0 = mk(ldg4(q)), v1 = mk(ldg4(q + 1)), v2 = mk(ldg4(q + 2));
+	V3 v0 = mk(ldg4(q + 1)), v1 = mk(ldg4(q + 2)), v2 = mk(ldg4(q + 3));
 	float sr = sqrtf(r1);
 	float alpha = 1.0f - sr;
 	float beta = r2 * sr;
@@ -940,7 +991,7 @@ RTB_DEV V3 trianglePoint(const DevScene& S, uint32_t id, float r1, float r2)
 }
 RTB_DEV V3 triangleGNormal(const DevScene& S, uint32_t id)
 {
-	float4 n = ldg4(S.tri + (size_t)id * 4 + 3);
+	float4 n = ldg4(S.tri + (size_t)id * 4);
 	float gs = ldg4(S.tsh + (size_t)id * 4 + 3).w;
 	return mk(n) * gs;
 }

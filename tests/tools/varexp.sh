@@ -1,4 +1,4 @@
-SC="cornell-box:64 materialball:64 MaterialsScene:64 coffee:64 bathroom:32 soup20:4 soup22:4"
-for ps in 0 1; do
-echo "== RTB_SHADOW_PERSISTENT=$ps"; RTB_SHADOW_PERSISTENT=$ps python tests/tools/perf_probe.py $SC
-done
+SC="coffee:64 bathroom:32 soup20:4 soup22:4"
+for rep in 1 2; do for v in "" _t128; do
+echo "== variant librtb200$v.so (run $rep)"; RTB200_LIB=$PWD/raytracingrenderer_b200/librtb200$v.so python tests/tools/perf_probe.py $SC
+done; done
