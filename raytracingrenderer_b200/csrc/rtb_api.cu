@@ -116,6 +116,7 @@ struct rtb_ctx
 	int cwStageKB = 32;            // RTB_CW_STAGE_KB
 	int shadowPersistent = -1;     // RTB_SHADOW_PERSISTENT: the persistent any-hit kernel (1), one thread per queued ray (0), per scene (-1)
 	bool shadowPersistentAuto = false;
+	uint32_t chunkOverride = 0; // RTB_CHUNK
 	int cwShadowPersistent = -1;   // RTB_CW_SHADOW: 1 = persistent any-hit kernel, 0 = one thread per queued ray, -1 = per scene
 	bool haveWide = false, haveCw = false, haveQ16 = false; // re-encodings of the FAST tree, built on first use
 	uint32_t poolSlots = 8u << 20; // profiles/r01_pool_sweep.txt: per-launch ramp/tail amortise up to ~8 M slots
@@ -511,6 +512,11 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		}
 		if (const char* e = getenv("RTB_CW_SHADOW")) ctx->cwShadowPersistent = atoi(e);
 		if (const char* e = getenv("RTB_SHADOW_PERSISTENT")) ctx->shadowPersistent = atoi(e);
+		if (const char* e = getenv("RTB_CHUNK"))
+		{
+			int v = atoi(e);
+			if (v >= 32 && v <= 4096) ctx->chunkOverride = (uint32_t)v & ~31u;
+		}
 		if (const char* e = getenv("RTB_SIMPLE_EXTEND")) ctx->simpleExtend = atoi(e) != 0;
 		if (const char* e = getenv("RTB_PRIMARY_PASSES"))
 		{
@@ -560,6 +566,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		a.primaryPasses = (uint32_t)ctx->primaryPasses;
 		a.counters = ctx->counters;
 		a.accum = ctx->accum;
+		a.chunk = WF_CHUNK;
 		a.nSlots = perPool, a.nTiles = plan ? plan->nTiles32 * 32u : ctx->wfTileCount;
 		a.width = ctx->width, a.height = ctx->height;
 		a.sFirst = sFirst, a.sStep = sStep, a.sCount = sCount;
@@ -621,6 +628,9 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 					for (int e = 0; e < 4; e++) se.e[e] = getEvent(ctx);
 					cudaEventRecord(se.e[0], st);
 				}
+				// long rays (the scenes that also take the persistent any-hit kernel): smaller chunks shorten the tail of a
+				// persistent launch (+1.5 ... 2 %), short rays prefer fewer atomics (profiles/r02_refill_chunk_sweep.txt)
+				A[k].chunk = ctx->chunkOverride ? ctx->chunkOverride : (ctx->shadowPersistentAuto ? 64u : (uint32_t)WF_CHUNK);
 				if (sortEx && !ctx->simpleExtend && ti != RTB_TRAV_EXACT)
 				{
 					k_sort_count<1><<<gridSort, 256, 0, st>>>(ctx->S, A[k], it);

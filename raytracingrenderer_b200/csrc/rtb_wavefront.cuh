@@ -88,6 +88,7 @@ struct WfArgs
 	uint32_t primaryPasses;   // fresh primary vertices a shade thread may take on per launch
 	unsigned long long* counters;
 	long long* accum; // [width*height*3] fixed-point film sums
+	uint32_t chunk; // rays a warp of a persistent kernel claims per atomic (WF_CHUNK, or 64 on scenes with long rays)
 	uint32_t nSlots, nTiles;
 	uint32_t width, height;
 	uint32_t sFirst, sStep, sCount; // sample ordinal n -> global sample index sFirst + n * sStep
@@ -579,13 +580,13 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_extend(const _
 		if (want && cursor >= end && !exhausted)
 		{
 			uint32_t c = 0;
-			if (lane == 0) c = atomicAdd(&A.ctrl[iter].extendHead, (unsigned)WF_CHUNK);
+			if (lane == 0) c = atomicAdd(&A.ctrl[iter].extendHead, (unsigned)A.chunk);
 			c = __shfl_sync(0xFFFFFFFFu, c, 0);
 			if (c >= nItems) exhausted = true;
 			else
 			{
 				cursor = c;
-				end = (c + WF_CHUNK < nItems) ? c + WF_CHUNK : nItems;
+				end = (c + A.chunk < nItems) ? c + A.chunk : nItems;
 			}
 		}
 		if (want && cursor < end)
@@ -746,13 +747,13 @@ __global__ void __launch_bounds__(WF_CW_THREADS, WF_CW_MIN_BLOCKS) k_wf_trace_cw
 		if (want && cursor >= end && !exhausted)
 		{
 			uint32_t c = 0;
-			if (lane == 0) c = atomicAdd(head, (unsigned)WF_CHUNK);
+			if (lane == 0) c = atomicAdd(head, (unsigned)A.chunk);
 			c = __shfl_sync(0xFFFFFFFFu, c, 0);
 			if (c >= nItems) exhausted = true;
 			else
 			{
 				cursor = c;
-				end = (c + WF_CHUNK < nItems) ? c + WF_CHUNK : nItems;
+				end = (c + A.chunk < nItems) ? c + A.chunk : nItems;
 			}
 		}
 		if (want && cursor < end)
@@ -867,13 +868,13 @@ __global__ void __launch_bounds__(128, WF_EXTEND_MIN_BLOCKS) k_wf_shadow_persist
 		if (want && cursor >= end && !exhausted)
 		{
 			uint32_t c = 0;
-			if (lane == 0) c = atomicAdd(&A.ctrl[iter].shadowHead, (unsigned)WF_CHUNK);
+			if (lane == 0) c = atomicAdd(&A.ctrl[iter].shadowHead, (unsigned)A.chunk);
 			c = __shfl_sync(0xFFFFFFFFu, c, 0);
 			if (c >= nItems) exhausted = true;
 			else
 			{
 				cursor = c;
-				end = (c + WF_CHUNK < nItems) ? c + WF_CHUNK : nItems;
+				end = (c + A.chunk < nItems) ? c + A.chunk : nItems;
 			}
 		}
 		if (want && cursor < end)

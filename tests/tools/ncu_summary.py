@@ -7,12 +7,13 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(raw)))
 h, units = rows[0], rows[1]
 col = {c: i for i, c in enumerate(h)}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}   # -> bytes / microseconds
 def g(r, name, default=float("nan")):
     i = col.get(name)
     if i is None or r[i] == "":
         return default
     try:
-        return float(r[i].replace(",", ""))
+        return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
     except ValueError:
         return default
 M = [
