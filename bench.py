@@ -409,9 +409,8 @@ def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm):
         films = [rt.read_film() / np.float32(spp) for rt in rts]
         for rt in rts:
             rt.set_params(primary_reuse=1)
-        if not heavy:
-            for rt in rts:
-                rt.render(min(spp, 8), 0)
+        for rt in rts:
+            rt.render(64 if heavy else spp, 0)     # the table mode sizes its own shadow queue: warm up at full size again
         ms1 = timed_render(rts, spp, torch)
         for rt in rts:
             rt.close()
@@ -481,6 +480,11 @@ def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm):
             ach = alg / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else 0.0
             rec["roofline"] = {"bound": "hbm", "kernel": "k_wf_extend", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                                "traffic": traffic.get("soup2^%d_k_wf_extend_dram_bytes_per_launch" % lg),
+                               "l2_hit_pct": traffic.get("soup2^%d_k_wf_extend_l2_hit_pct" % lg),
+                               "note": "the scene (1 - 4 GB) does not fit the 126 MB L2, yet the measured DRAM traffic is a small part of the "
+                                       "algorithmic bytes: consecutive jobs are neighbouring pixels, so a launch's rays share the upper tree and L2 "
+                                       "serves 87 - 93 % of the sectors; the kernel is bound by the L1 data pipe (81 % of the LSU wavefront peak, "
+                                       "profiles/r02_final_soup22_summary.md), not by HBM",
                                "kernel_ms_per_launch": ext_ms, "launches": it, "alg_bytes_per_launch": alg,
                                "alg_source": "32 B per box test + 64 B per triangle test + 48 B per ray of the kernel's own traversal (the "
                                              "canonical counter replays the reference tree on the CPU: minutes at this size)",
@@ -727,6 +731,10 @@ def run_ours(args, rank, world, local_rank):
         canon = canonical_counts()
         keys = [("materialball_" + lab) if args.scene == "materialball7" else lab for lab, _ in flats]
         roof, _ = serial_stage_pass(flats, keys, spp, depth, canon, rtb, abi, torch, stream, sm_max)
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp) and args.scene == "materialball7":
+            roof["traffic"] = json.load(open(tp)).get("%s_dram_bytes_per_launch" % roof["kernel"])
+            roof["traffic_note"] = "dram__bytes_read + dram__bytes_write of one launch over a 4 M-slot sub-pool (ncu, profiles/r02_dram_materialball.csv); the serialised pass launches over 8 M slots"
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,

@@ -59,6 +59,29 @@ def test_errors_are_reported_not_swallowed(rtb):
     rt.close()
 
 
+def test_parameters_that_would_render_wrong_images_are_rejected(rtb):
+    """A zero-initialised rtb_params (instead of rtb_default_params) has rr_cap = 0 (every path ends at depth 0) and
+    cull_rel = 0 (no cull slack: FAST / WIDE hit IDs could differ); films above 2^32 / 3 pixels would be resolved only
+    partially.  All of these are errors, not silently wrong images."""
+    rt = rtb.RayTracer(0)
+    for kw in (dict(rr_cap=0.0), dict(rr_cap=1.5), dict(rr_cap=float("nan")), dict(cull_rel=0.0), dict(cull_rel=-1e-5),
+               dict(cull_rel=float("nan")), dict(filter_radius=float("nan")), dict(filter_alpha=float("inf")), dict(primary_reuse=7),
+               dict(traversal=9)):
+        with pytest.raises(rtb.RtbError) as e:
+            rt.set_params(**kw)
+        assert e.value.code == -1, kw
+    rt.set_params(rr_cap=1.0, cull_rel=1e-6)              # the edges of the accepted ranges
+    s = synthetic_scene()
+    big = abi.FlatScene()
+    big.__dict__.update(s.__dict__)
+    big.camera = s.camera.copy()
+    big.camera["width"], big.camera["height"] = 40000.0, 40000.0
+    with pytest.raises(rtb.RtbError) as e:
+        rt.init(big)
+    assert "too large" in str(e.value)
+    rt.close()
+
+
 def test_rng_stream_equals_the_oracle(rtb, oracle_mod):
     rt = gpu_scene(rtb, "synthetic")
     for seed, pixel, sample in ((1, 0, 0), (1, 12345, 77), (0xB200, 2 ** 31 + 5, 2 ** 20)):
