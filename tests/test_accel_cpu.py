@@ -1,0 +1,73 @@
+"""The host-side tree builders of the product (csrc/rtb_accel.hpp, csrc/rtb_cwbvh.hpp) checked on the CPU: the structural
+and CONSERVATIVENESS properties the device traversals rely on for returning the reference's hits — every
+reference leaf a primitive exactly once, FAST child boxes exactly the union of their leaves' boxes, CW / Q16 quantised boxes
+containing the exact boxes with the stated margin, exact leaf boxes carried bit for bit.  tests/tools/accel_check.cpp is
+compiled with g++ against the product headers."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, synthetic_scene
+from raytracingrenderer_b200 import abi
+
+SRC = os.path.join(ROOT, "tests", "tools", "accel_check.cpp")
+OUT = os.path.join("/tmp", "rtb_test_cache", "libaccel_check.so")
+
+
+@pytest.fixture(scope="module")
+def checker():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    deps = [SRC] + [os.path.join(ROOT, "raytracingrenderer_b200", "csrc", f) for f in ("rtb_accel.hpp", "rtb_cwbvh.hpp")]
+    if not os.path.isfile(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), SRC, "-o", OUT, "-lpthread"])
+    lib = C.CDLL(OUT)
+    lib.accel_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.accel_check_message.restype = C.c_char_p
+    return lib
+
+
+def run(lib, scene):
+    nodes = np.ascontiguousarray(scene.ref_nodes, abi.ref_node_dt)
+    stats = np.zeros(9, np.float64)
+    rc = lib.accel_check(nodes.ctypes.data, len(nodes), scene.n_tris, stats.ctypes.data)
+    assert rc == 0, lib.accel_check_message().decode()
+    return dict(zip(("fast_nodes", "fast_depth", "wide_nodes", "cw_nodes", "cw_depth", "cw_leaves", "q16_leaves", "cw_inflation", "q16_inflation"), stats))
+
+
+def test_trees_of_the_committed_and_synthetic_scenes(checker):
+    for s in (abi.FlatScene.load(os.path.join(GOLDEN, "cornell-box.rtbs")), synthetic_scene(), synthetic_scene(seed=11, n_tris=700)):
+        st = run(checker, s)
+        assert st["cw_leaves"] == st["q16_leaves"] == st["fast_nodes"] + 1        # a binary tree over L leaves has L - 1 nodes
+        assert st["cw_nodes"] <= st["fast_nodes"] and st["cw_depth"] <= st["fast_depth"]
+
+
+@pytest.mark.parametrize("name", ["MaterialsScene", "materialball", "coffee", "bathroom"])
+def test_trees_of_the_bundled_scenes(checker, name):
+    from raytracingrenderer_b200 import host_api
+    d = os.path.join(ROOT, "scenes", "_staged", name)
+    if not os.path.isfile(os.path.join(d, "scene.json")):
+        pytest.skip("staged scene assets missing")
+    st = run(checker, host_api.load_scene(d))
+    assert st["cw_depth"] + 2 <= 40                      # RTB_CW_STACK
+    assert st["fast_depth"] + 2 <= 96                    # RTB_STACK
+    assert st["cw_nodes"] < 0.45 * st["fast_nodes"]      # eight-wide: far fewer nodes than the binary tree
+
+
+def test_soup_trees(checker):
+    from raytracingrenderer_b200 import host_api
+    s, _ = host_api.build_soup(1 << 15, 64, 36)
+    st = run(checker, s)
+    assert st["cw_leaves"] == st["fast_nodes"] + 1
+
+
+def test_a_broken_tree_is_noticed(checker):
+    """The checker itself: a reference BVH whose leaf range is out of bounds is rejected by the builder."""
+    s = synthetic_scene()
+    nodes = np.ascontiguousarray(s.ref_nodes, abi.ref_node_dt).copy()
+    leaf = np.flatnonzero(nodes["a"] < 0)[0]
+    nodes["b"][leaf] = 7
+    stats = np.zeros(9, np.float64)
+    assert checker.accel_check(nodes.ctypes.data, len(nodes), s.n_tris, stats.ctypes.data) < 0
