@@ -365,7 +365,8 @@ int rtb_device_count(void);
  * members' fixed-point sums to devices[0]'s — one kernel over NVLink peer memory that also converts
  * to the float film, or ncclReduce (libnccl.so.2, loaded on demand) when a member is not
  * peer-accessible; RTB_GROUP_REDUCE=nccl|staged forces a path.  Integer sums: the group's film equals
- * the single-GPU film bit for bit.  rtb_render_adaptive and the parity entry points run on
+ * the single-GPU film bit for bit.  rtb_render_adaptive: every member steers and samples the 32x32
+ * tiles t with t % n == member (same plan, same film as one GPU).  The parity entry points run on
  * devices[0] alone.  n = 1 is a plain context.                                             */
 int rtb_create_multi(const int* devices, int n, rtb_ctx** out);
 /* Members of ctx (1 for rtb_create).  rtb_group_info: devices[n], p2p[n] (1 = devices[0] reads that
@@ -387,8 +388,9 @@ void rtb_default_params(rtb_params* p);
 int rtb_set_params(rtb_ctx* ctx, const rtb_params* p);
 int rtb_get_params(const rtb_ctx* ctx, rtb_params* p);
 /* Copies the scene to the device, builds the accelerated tree over the reference leaves
- * and (re)allocates a cleared film of camera.width x camera.height.  Replaces
- * RayTracer::init (Renderer.h:45-63).                                                    */
+ * (host threads: binned SAH; RTB_GPU_BUILD=1: a linear BVH built on the device in milliseconds,
+ * same hits, ~10-25 % lower render rate) and (re)allocates a cleared film of camera.width x
+ * camera.height.  Replaces RayTracer::init (Renderer.h:45-63).                             */
 int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* scene);
 /* Camera::updateView / RTCamera::updateCamera (Scene.h:33-41): new camera, same scene.   */
 int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam);
@@ -413,7 +415,8 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count);
  * their mean is splatted, i.e. the film sum grows by one mean image and SPP by one.  The initial samples
  * only steer (sample indices 0..init-1), the splatted ones use indices init.. .  tile_samples /
  * tile_variance (tilesX*tilesY entries, row-major 32x32 tiles; may be NULL) receive the plan.
- * Wavefront schedule, single device per image.  Synchronous (the plan goes through the host).      */
+ * Wavefront schedule; one context per image (a device group shares the tiles out).  Synchronous (the
+ * plan goes through the host).                                                                       */
 int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_samples, uint32_t max_samples,
                         uint32_t* tile_samples, float* tile_variance);
 /* pass_count x RayTracer::lightTracer() (Renderer.h:220-326; a commented-out alternative in render(), :883):

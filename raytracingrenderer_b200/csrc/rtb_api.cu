@@ -4,6 +4,7 @@
 #include "rtb_accel.hpp"
 #include "rtb_cwbvh.hpp"
 #include "rtb_wavefront.cuh"
+#include "rtb_gpu_build.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -1004,6 +1005,8 @@ struct PreparedScene
 	const rtb_scene_desc* sc = nullptr;
 	std::vector<rtb_accel::F4> xnodes;
 	rtb_accel::FastTree fast;
+	bool gpuBuild = false;                   // the FAST tree is built on each device from `leaves` (rtb_gpu_build.cuh)
+	std::vector<rtb_accel::RefLeaf> leaves;
 	std::vector<rtb_accel::F4> triPacked; // device triangle records (layout: triTest, rtb_dev_scene.cuh)
 	std::vector<float> marginal, cond;
 	int envW = 0, envH = 0;
@@ -1046,10 +1049,23 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 
 	// host-side acceleration data
 	std::vector<rtb_accel::F4>& xnodes = ps.xnodes;
-	std::vector<rtb_accel::RefLeaf> leaves;
+	std::vector<rtb_accel::RefLeaf>& leaves = ps.leaves;
 	const char* err = nullptr;
 	if (!rtb_accel::buildExact(sc->ref_nodes, sc->n_ref_nodes, sc->n_tris, xnodes, leaves, &err)) return fail(ctx, RTB_ERR_ARG, "%s", err);
 	rtb_accel::FastTree& fast = ps.fast;
+	// The tree can be built on the device instead (a linear BVH over the same leaves: four kernels and a sort, where the
+	// host's binned-SAH recursion takes seconds on the largest soups).
+	{
+		// Opt-in (profiles/r02_gpu_builder.txt): the linear BVH is built in milliseconds (16 M triangles: upload 4.2 -> 2.2 s, the
+		// rest is host preparation + copies) but costs 8 % (soups) ... 25 % (coffee) of the render rate against the SAH
+		// tree, and the metric is the render rate.  RTB_GPU_BUILD=1, or RTB_GPU_BUILD_MIN_LEAVES=n for "from n leaves on".
+		size_t minLeaves = (size_t)-1;
+		if (const char* e = getenv("RTB_GPU_BUILD_MIN_LEAVES")) minLeaves = (size_t)atoll(e);
+		ps.gpuBuild = leaves.size() >= minLeaves;
+		if (const char* e = getenv("RTB_GPU_BUILD")) ps.gpuBuild = atoi(e) != 0;
+		if (leaves.size() < 2) ps.gpuBuild = false;
+	}
+	if (!ps.gpuBuild)
 	{
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
@@ -1067,7 +1083,7 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 	}
 	// stack need: one pending sibling per level.  (The WIDE / CW / Q16 re-encodings of this tree are built on first use,
 	// ensureTraversal: the upload of a 16 M-triangle scene should not pay for trees nobody selected.)
-	if (fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u levels)", fast.maxDepth);
+	if (!ps.gpuBuild && fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u levels)", fast.maxDepth);
 
 	for (uint32_t i = 0; i < sc->n_lights; i++)
 	{
@@ -1098,14 +1114,46 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	const rtb_accel::F4* dx = nullptr;
 	const rtb_accel::F4* df = nullptr;
 	if ((rc = uploadArray(ctx, xnodes.data(), xnodes.size(), &dx))) return rc;
-	if ((rc = uploadArray(ctx, fast.nodes.data(), fast.nodes.size(), &df))) return rc;
+	uint32_t fastDepth = fast.maxDepth;
+	bool built = false;
+	if (ps.gpuBuild)
+	{
+		const uint32_t nl = (uint32_t)ps.leaves.size();
+		void* p = nullptr;
+		CK(cudaMalloc(&p, (size_t)(nl - 1) * 4 * sizeof(float4)));
+		ctx->sceneAllocs.push_back(p);
+		CK(rtb_gpu_build::build(ps.leaves.data(), nl, sc->ref_nodes[0].bmin, sc->ref_nodes[0].bmax, (float4*)p, &fastDepth, ctx->stream));
+		if (fastDepth + 2 <= RTB_STACK)
+		{
+			df = (const rtb_accel::F4*)p;
+			S.n_fnodes = nl - 1;
+			S.fast_root = 0;
+			built = true;
+		}
+	}
+	if (!built)
+	{
+		// host tree (the default for scenes it builds in a fraction of a second; also if the linear BVH came out too deep)
+		rtb_accel::FastTree local;
+		const rtb_accel::FastTree* ft = &fast;
+		if (ps.gpuBuild)
+		{
+			rtb_accel::FastBuilder fb(ps.leaves);
+			fb.build(local);
+			if (local.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u levels)", local.maxDepth);
+			ft = &local;
+		}
+		if ((rc = uploadArray(ctx, ft->nodes.data(), ft->nodes.size(), &df))) return rc;
+		CK(cudaStreamSynchronize(ctx->stream)); // `local` dies with this block
+		S.n_fnodes = (uint32_t)(ft->nodes.size() / 4);
+		S.fast_root = ft->root;
+		fastDepth = ft->maxDepth;
+	}
 	S.xnodes = (const float4*)dx;
 	S.fnodes = (const float4*)df;
 	S.n_xnodes = sc->n_ref_nodes;
-	S.n_fnodes = (uint32_t)(fast.nodes.size() / 4);
-	S.fast_root = fast.root;
-	ctx->fastDepth = fast.maxDepth;
-	S.wide_root = S.q16_root = fast.root < 0 ? fast.root : 0; // a leaf root needs no tree; otherwise set by ensureTraversal
+	ctx->fastDepth = fastDepth;
+	S.wide_root = S.q16_root = S.fast_root < 0 ? S.fast_root : 0; // a leaf root needs no tree; otherwise set by ensureTraversal
 	ctx->haveWide = ctx->haveCw = ctx->haveQ16 = false;
 	ctx->cwBlocksPerSM[0] = ctx->cwBlocksPerSM[1] = 0; // staging is sized per scene
 	const rtb_accel::F4* dti = nullptr;
@@ -1611,20 +1659,60 @@ int rtb_render_ir(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32
 	return splitPasses(ctx, pass_begin, pass_count, [n_paths](rtb_ctx* m, uint32_t b, uint32_t c) { return irOne(m, b, c, n_paths); });
 }
 
-// RayTracer::adaptiveRender (Renderer.h:679-749) on the wavefront schedule.
+// One member's share of RayTracer::adaptiveRender: member d of n owns the 32x32 tiles t with t % n == d (the tile
+// partition of rtb_params); tiles it does not own get no jobs in its plans and add nothing to its film.
+static int adaptiveAlloc(rtb_ctx* ctx)
+{
+	const uint32_t W = ctx->width, H = ctx->height, t32x = (W + 31) / 32, t32y = (H + 31) / 32, nT = t32x * t32y;
+	if (ctx->accumScratch) return RTB_OK;
+	CK(cudaMalloc((void**)&ctx->accumScratch, (size_t)W * H * 3 * sizeof(long long)));
+	CK(cudaMalloc((void**)&ctx->adaptJobBase, (size_t)(nT + 1) * sizeof(unsigned long long)));
+	CK(cudaMalloc((void**)&ctx->adaptSamples, (size_t)nT * sizeof(uint32_t)));
+	CK(cudaMalloc((void**)&ctx->adaptVariance, (size_t)nT * sizeof(float)));
+	std::vector<uint32_t> sub((size_t)nT * 32);
+	uint32_t tilesX = (W + 7) / 8, tilesY = (H + 3) / 4;
+	for (uint32_t t = 0; t < nT; t++)
+		for (uint32_t k = 0; k < 32; k++)
+		{
+			uint32_t tx = (t % t32x) * 4 + (k & 3u), ty = (t / t32x) * 8 + (k >> 2);
+			sub[(size_t)t * 32 + k] = (tx < tilesX && ty < tilesY) ? ((ty << 16) | tx) : 0xFFFFFFFFu;
+		}
+	CK(cudaMalloc((void**)&ctx->wfTilesAdaptive, sub.size() * sizeof(uint32_t)));
+	CK(cudaMemcpy(ctx->wfTilesAdaptive, sub.data(), sub.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	return RTB_OK;
+}
+
+// renders counts[t] samples (sample indices from sampleFirst on) per pixel of every OWNED tile into the scratch sums
+static int adaptiveRenderPlan(rtb_ctx* ctx, int d, int n, uint32_t sampleFirst, uint32_t maxCount, const std::vector<uint32_t>& counts)
+{
+	const uint32_t nT = (uint32_t)counts.size();
+	std::vector<unsigned long long> base(nT + 1);
+	base[0] = 0;
+	for (uint32_t t = 0; t < nT; t++) base[t + 1] = base[t] + (((int)(t % (uint32_t)n) == d) ? 1024ull * counts[t] : 0ull);
+	CK(cudaMemsetAsync(ctx->accumScratch, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(long long), ctx->stream));
+	CK(cudaMemcpyAsync(ctx->adaptJobBase, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream)); // `base` is pageable host memory
+	AdaptivePlan plan = {base[nT], nT};
+	long long* film = ctx->accum;
+	ctx->accum = ctx->accumScratch;
+	int rc = renderWavefront(ctx, sampleFirst, maxCount, &plan);
+	ctx->accum = film;
+	return rc;
+}
+
+// RayTracer::adaptiveRender (Renderer.h:679-749) on the wavefront schedule; on a device group every member steers and
+// samples its own tiles, and the tile variances meet on the host (they go through it anyway: the plan is host arithmetic).
 int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_samples, uint32_t max_samples, uint32_t* tile_samples,
                         float* tile_variance)
 {
 	if (!ctx) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "rtb_render_adaptive before rtb_upload_scene");
-	const rtb_params& P = ctx->params;
+	const rtb_params P = ctx->userParams;
 	if (init_samples < 1 || min_samples < 1 || max_samples < min_samples || max_samples > (1u << 20))
 		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: need 1 <= init, 1 <= min <= max <= 2^20");
 	if (P.scheduler != RTB_SCHED_WAVEFRONT) return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive runs on the wavefront schedule");
 	if (P.partition != RTB_PART_NONE && P.part_world > 1)
-		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: the tile sample counts come from the whole image; use one device per image");
-	if (int rc = bind(ctx)) return rc;
-	if (int rc = ensureTraversal(ctx, P.traversal)) return rc;
+		return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: the tile sample counts come from the whole image; use one context (a device group) per image");
 	// Every call draws from its own range of sample indices, like the reference's ever-advancing MTRandom makes
 	// successive adaptiveRender() calls independent: call number k (= Film::SPP before the call, one per call)
 	// uses [k * (init + max), (k + 1) * (init + max)).
@@ -1632,40 +1720,25 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 	if (base64 + init_samples + max_samples > 0xFFFFFFFFull) return fail(ctx, RTB_ERR_ARG, "rtb_render_adaptive: sample index overflow (clear the film)");
 	const uint32_t sampleBase = (uint32_t)base64;
 	const uint32_t W = ctx->width, H = ctx->height, t32x = (W + 31) / 32, t32y = (H + 31) / 32, nT = t32x * t32y;
-	const size_t accBytes = (size_t)W * H * 3 * sizeof(long long);
-	if (!ctx->accumScratch)
-	{
-		CK(cudaMalloc((void**)&ctx->accumScratch, accBytes));
-		CK(cudaMalloc((void**)&ctx->adaptJobBase, (size_t)(nT + 1) * sizeof(unsigned long long)));
-		CK(cudaMalloc((void**)&ctx->adaptSamples, (size_t)nT * sizeof(uint32_t)));
-		CK(cudaMalloc((void**)&ctx->adaptVariance, (size_t)nT * sizeof(float)));
-		std::vector<uint32_t> sub((size_t)nT * 32);
-		uint32_t tilesX = (W + 7) / 8, tilesY = (H + 3) / 4;
-		for (uint32_t t = 0; t < nT; t++)
-			for (uint32_t k = 0; k < 32; k++)
-			{
-				uint32_t tx = (t % t32x) * 4 + (k & 3u), ty = (t / t32x) * 8 + (k >> 2);
-				sub[(size_t)t * 32 + k] = (tx < tilesX && ty < tilesY) ? ((ty << 16) | tx) : 0xFFFFFFFFu;
-			}
-		CK(cudaMalloc((void**)&ctx->wfTilesAdaptive, sub.size() * sizeof(uint32_t)));
-		CK(cudaMemcpy(ctx->wfTilesAdaptive, sub.data(), sub.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-	}
+	const int n = (int)groupSize(ctx);
 	// ---- phase 1 (adaptiveSampling): init_samples per pixel into the scratch sums, tile variances
-	long long* film = ctx->accum;
-	std::vector<unsigned long long> base(nT + 1);
-	for (uint32_t t = 0; t <= nT; t++) base[t] = (unsigned long long)t * 1024ull * init_samples;
-	CK(cudaMemsetAsync(ctx->accumScratch, 0, accBytes, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->adaptJobBase, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-	AdaptivePlan plan = {base[nT], nT};
-	ctx->accum = ctx->accumScratch;
-	int rc = renderWavefront(ctx, sampleBase, init_samples, &plan);
-	ctx->accum = film;
+	std::vector<std::vector<float>> varOf((size_t)n, std::vector<float>(nT, 0.0f));
+	const std::vector<uint32_t> initCounts(nT, init_samples);
+	int rc = forEachMember(ctx, [&](rtb_ctx* m, int d) {
+		if (int rc = bind(m)) return rc;
+		if (int rc = ensureTraversal(m, P.traversal)) return rc;
+		if (int rc = adaptiveAlloc(m)) return rc;
+		if (int rc = adaptiveRenderPlan(m, d, n, sampleBase, init_samples, initCounts)) return rc;
+		rtb_ctx* ctx = m; // for CK
+		k_tile_variance<<<nT, 256, 0, m->stream>>>(m->accumScratch, W, H, init_samples, m->adaptVariance);
+		m->launches++;
+		CK(cudaMemcpyAsync(varOf[(size_t)d].data(), m->adaptVariance, nT * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+		CK(cudaStreamSynchronize(m->stream));
+		return (int)RTB_OK;
+	});
 	if (rc) return rc;
-	k_tile_variance<<<nT, 256, 0, ctx->stream>>>(ctx->accumScratch, W, H, init_samples, ctx->adaptVariance);
-	ctx->launches++;
 	std::vector<float> var(nT);
-	CK(cudaMemcpyAsync(var.data(), ctx->adaptVariance, nT * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
+	for (uint32_t t = 0; t < nT; t++) var[t] = varOf[(size_t)(t % (uint32_t)n)][t];
 	// ---- weights and sample counts exactly like adaptiveRender / sampleTileWithWeight (float arithmetic)
 	float total = 0.0f;
 	for (float v : var) total += v;
@@ -1677,22 +1750,22 @@ int rtb_render_adaptive(rtb_ctx* ctx, uint32_t init_samples, uint32_t min_sample
 		int sample = (int)(w * (float)max_samples);
 		samples[t] = (uint32_t)((sample > (int)min_samples) ? sample : (int)min_samples);
 	}
-	base[0] = 0;
-	for (uint32_t t = 0; t < nT; t++) base[t + 1] = base[t] + 1024ull * samples[t];
 	// ---- phase 2 (sampleTileWithWeight): fresh samples (indices init_samples...), film += their mean
-	CK(cudaMemsetAsync(ctx->accumScratch, 0, accBytes, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->adaptJobBase, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->adaptSamples, samples.data(), nT * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-	plan.totalJobs = base[nT];
-	ctx->accum = ctx->accumScratch;
-	rc = renderWavefront(ctx, sampleBase + init_samples, max_samples, &plan);
-	ctx->accum = film;
+	rc = forEachMember(ctx, [&](rtb_ctx* m, int d) {
+		if (int rc = bind(m)) return rc;
+		if (int rc = adaptiveRenderPlan(m, d, n, sampleBase + init_samples, max_samples, samples)) return rc;
+		rtb_ctx* ctx = m; // for CK
+		CK(cudaMemcpyAsync(m->adaptSamples, samples.data(), nT * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+		k_adaptive_merge<<<(W * H + 255) / 256, 256, 0, m->stream>>>(m->accumScratch, m->accum, W, H, m->adaptSamples);
+		m->launches++;
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(m->stream)); // `samples` is pageable host memory
+		m->filmDirty = true;
+		m->accumDirty = true;
+		return (int)RTB_OK;
+	});
 	if (rc) return rc;
-	k_adaptive_merge<<<(W * H + 255) / 256, 256, 0, ctx->stream>>>(ctx->accumScratch, ctx->accum, W, H, ctx->adaptSamples);
-	ctx->launches++;
-	CK(cudaGetLastError());
-	CK(cudaStreamSynchronize(ctx->stream)); // `base` / `samples` are pageable host memory
-	ctx->filmDirty = true;
+	if (n > 1) cudaSetDevice(ctx->device);
 	ctx->spp += 1; // Film::incrementSPP once per render() (Renderer.h:878)
 	if (tile_samples) memcpy(tile_samples, samples.data(), nT * sizeof(uint32_t));
 	if (tile_variance) memcpy(tile_variance, var.data(), nT * sizeof(float));

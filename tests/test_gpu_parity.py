@@ -686,6 +686,35 @@ def test_exact_fast_wide_films_are_bit_identical_on_the_heavy_scenes(rtb, name):
         assert (sa["closest_rays"], sa["shadow_rays"]) == (sb["closest_rays"], sb["shadow_rays"])
 
 
+@pytest.mark.parametrize("name", ["synthetic", "cornell-box", "coffee"])
+def test_device_built_tree_returns_the_same_hits_and_film(rtb, monkeypatch, name):
+    """RTB_GPU_BUILD=1: the FAST tree built on the device (linear BVH over the reference's leaves, rtb_gpu_build.cuh — the
+    default from 2^20 leaves on) instead of the host's SAH tree.  A different tree over the same leaves: primary hits, the
+    recorded ray kinds and the film must not change by a bit, for FAST and for the trees re-encoded from it."""
+    host = gpu_scene(rtb, name)
+    ids, t, rays = host.primary_hits(abi.TRAV_FAST, want_rays=True)
+    host.set_params(primary_reuse=0)
+    host.render(2, 0)
+    film = host.read_film().copy()
+    monkeypatch.setenv("RTB_GPU_BUILD", "1")
+    dev = rtb.RayTracer(0)
+    dev.init(host.scene)
+    ph = dev.trace(rays, traversal=abi.TRAV_EXACT)
+    sets = raysets.mixed_set(rays, ph, seed=5, n_each=3000)
+    want = host.trace(sets["closest"], traversal=abi.TRAV_EXACT)
+    want_any = host.trace(sets["anyhit"], any_hit=True, traversal=abi.TRAV_EXACT)["id"]
+    for trav in (abi.TRAV_FAST, abi.TRAV_WIDE, abi.TRAV_CW, abi.TRAV_Q16):
+        i2, t2 = dev.primary_hits(trav)
+        assert np.array_equal(i2, ids) and t2.tobytes() == t.tobytes(), trav
+        assert dev.trace(sets["closest"], traversal=trav).tobytes() == want.tobytes(), trav
+        assert np.array_equal(dev.trace(sets["anyhit"], any_hit=True, traversal=trav)["id"], want_any), trav
+        dev.set_params(traversal=trav, primary_reuse=0)
+        dev.clear()
+        dev.render(2, 0)
+        assert dev.read_film().tobytes() == film.tobytes(), trav
+    dev.close()
+
+
 def test_megakernel_and_wavefront_schedules_agree(rtb):
     """Same samples, same RNG streams; only the summation order differs."""
     for name in ("synthetic", "cornell-box"):
@@ -1018,6 +1047,16 @@ def test_device_group_film_equals_the_single_gpu_film(rtb, monkeypatch):
     one.instantRadiosity(3, 0)
     g.instantRadiosity(3, 0)
     assert g.read_film().tobytes() == one.read_film().tobytes() and g.getSPP() == 3
+    # adaptiveRender: every member steers and samples its own tiles; plan and film are the single-GPU ones
+    one.clear()
+    g.clear()
+    c1, v1 = one.adaptiveRender(2, 1, 512)
+    cg, vg = g.adaptiveRender(2, 1, 512)
+    assert np.array_equal(c1, cg) and np.array_equal(v1, vg)
+    assert g.read_film().tobytes() == one.read_film().tobytes() and g.getSPP() == 1
+    c1, _ = one.adaptiveRender(2, 1, 512)
+    cg, _ = g.adaptiveRender(2, 1, 512)          # the second call draws fresh sample indices on every member
+    assert np.array_equal(c1, cg) and g.read_film().tobytes() == one.read_film().tobytes()
     # write_film replaces the whole group's film
     g.write_film(np.ones((256, 256, 3), np.float32))
     assert np.allclose(g.read_film(), 1.0, atol=1e-9)
