@@ -30,5 +30,25 @@ n = int(m.sum())
 rng = np.random.default_rng(0)
 rt.eval_bsdf(sd[m], raysets.unit(rng.normal(size=(n, 3))), rng.random((n, 3), dtype=np.float32))
 rt.eval_light(rng.integers(0, len(s.lights), n).astype(np.int32), raysets.unit(rng.normal(size=(n, 3))), rng.random((n, 2), dtype=np.float32))
-print("sanitize case ok", rt.stats()["kernel_launches"], "launches")
+n_launch = rt.stats()["kernel_launches"]
 rt.close()
+# round 2: ray binning, the persistent any-hit kernel, small chunks, the device-built tree, MIS + importance sampling,
+# adaptive / light / IR on a device group of one, film write-back
+for env in (dict(RTB_SORT_SHADOW="1", RTB_SORT_EXTEND="1"), dict(RTB_SHADOW_PERSISTENT="1", RTB_CHUNK="32"), dict(RTB_GPU_BUILD="1"),
+            dict(RTB_CW_STAGE_KB="0", RTB_CW_SHADOW="0")):
+    os.environ.update(env)
+    r2 = rtb.RayTracer([0])
+    r2.init(s)
+    for trav in (abi.TRAV_FAST, abi.TRAV_CW, abi.TRAV_Q16):
+        for integ in (abi.INT_PATH, abi.INT_PATH_MIS):
+            r2.set_params(traversal=trav, integrator=integ, sampling=abi.SAMPLING_IMPORTANCE)
+            r2.clear(); r2.render(3, 0)
+            assert np.isfinite(r2.read_film()).all()
+    r2.set_params(traversal=abi.TRAV_FAST, integrator=abi.INT_PATH)
+    r2.clear(); r2.adaptiveRender(2, 1, 16); r2.lightTracer(2); r2.instantRadiosity(1); f = r2.read_film()
+    r2.write_film(f); r2.tonemap()
+    n_launch += r2.stats()["kernel_launches"]
+    r2.close()
+    for k in env:
+        del os.environ[k]
+print("sanitize case ok", n_launch, "launches")
