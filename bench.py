@@ -380,10 +380,11 @@ def serial_stage_pass(flats, keys, spp, depth, canon, rtb, abi, torch, stream, s
     }, tot
 
 
-def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm):
+def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm, sm_max=1965.0):
     """(N = 1) every BASELINE config: throughput + image error against the CPU reference."""
     import numpy as np
     out = []
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     dev = torch.cuda.current_device()
 
     def gpu_config(flats, spp, depth):
@@ -428,6 +429,14 @@ def per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm):
         flats = [(d, host_api.load_scene(os.path.join(STAGED, d))) for d in dirs]
         rec, films = gpu_config(flats, spp, depth)
         rec.update(scene=key, resolution=[flats[0][1].width, flats[0][1].height], triangles=int(flats[0][1].n_tris))
+        if all(d in canon for d in dirs):
+            # whole render against the FP32 issue peak: canonical flops per ray (the reference tree's canonical
+            # traversal) x the rays traced / the render's device time (stages overlapped as in production)
+            k = [canon[d] for d in dirs]
+            fl = sum(c["closest_flops_per_ray"] * c["closest_rays_per_sample"] + c["shadow_flops_per_ray"] * c["shadow_rays_per_sample"] for c in k) / len(k)
+            tf = fl * rec["msamples_s"] * 1e6 / 1e12
+            rec["roofline_fp32"] = {"bound": "fp32-issue", "canonical_flops_per_sample": fl, "achieved_tflops": tf, "peak_tflops": fp32_peak,
+                                    "frac": tf / fp32_peak}
         if not args.no_cpu:
             errs, cpu_rate, cpu = [], [], None
             for (d, s), film in zip(flats, films):
@@ -761,7 +770,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, log)
         if world == 1 and not args.no_per_scene:
-            line["per_scene"] = per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm)
+            line["per_scene"] = per_scene_records(args, rtb, abi, host_api, torch, stream, log, canon, hbm, sm_max)
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if dist is not None:

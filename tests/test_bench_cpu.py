@@ -52,3 +52,32 @@ def test_reference_arm_on_other_ranks_exits_quietly():
     out = run(["--impl", "reference", "--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, timeout=120)
     assert out.returncode == 0
     assert out.stdout.strip() == ""
+
+
+def test_image_error_gates_separate_an_unbiased_from_a_biased_image():
+    """bench.py's per-scene image error: for an estimator with the reference's own statistics the 8x8-block RMSE
+    sits at the value the reference's two half-buffers predict (ratio ~ 1) and both gates pass; a 3 % brightness bias or extra
+    block-scale structure fails them."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", BENCH)
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(1)
+    h, w = 256, 320
+    truth = 0.2 + 0.8 * rng.random((h // 8, w // 8, 3)).repeat(8, axis=0).repeat(8, axis=1)      # block-constant image
+    sigma1 = 0.7                                                                                      # noise of one sample per pixel
+
+    def mean_image(spp):
+        return (truth + rng.normal(0, sigma1 / np.sqrt(spp), truth.shape)).astype(np.float32)
+    n, m_half = 64, 8
+    ha, hb = mean_image(m_half), mean_image(m_half)
+    good = bench.image_error(mean_image(n), n, ha, hb, m_half)
+    assert 0.9 < good["block8_rmse_over_expected"] < 1.1
+    assert good["gate_mean_0p5pct_or_3x_cpu_noise"] and good["gate_block_rmse_3x_noise"]
+    assert good["gpu_spp"] == n and good["cpu_spp"] == 2 * m_half and good["relmse"] > 0
+    bright = bench.image_error(mean_image(n) * np.float32(1.03), n, ha, hb, m_half)
+    assert not bright["gate_mean_0p5pct_or_3x_cpu_noise"]
+    blotchy = mean_image(n) + 0.2 * rng.normal(0, 1, (h // 8, w // 8, 3)).repeat(8, axis=0).repeat(8, axis=1).astype(np.float32)
+    bad = bench.image_error(blotchy, n, ha, hb, m_half)
+    assert not bad["gate_block_rmse_3x_noise"] and bad["block8_rmse_over_expected"] > 3
