@@ -751,6 +751,34 @@ def test_cornell_image_against_reference_statistics(rtb):
     assert np.sqrt(np.mean((blocks - g["result_144"]) ** 2)) <= 0.003
 
 
+@pytest.mark.parametrize("name,spp,rspp", [("cornell-box", 64, 8), ("materialball", 256, 8), ("MaterialsScene", 512, 8), ("coffee", 1024, 8),
+                                           ("bathroom", 1024, 2)])
+def test_converged_images_at_the_baseline_spp_match_the_reference(rtb, name, spp, rspp):
+    """BASELINE.json's configs at their own spp against the UNMODIFIED reference (SURVEY A.7 gates i-iii, the same arithmetic
+    as bench.py's per_scene): mean luminance within max(0.5 %, 3 x the difference of two reference runs); 8x8-block RMSE
+    between 0.8 and 1.25 x the value the reference's own noise predicts (sigma_1 sqrt(1/N + 1/M), sigma_1 from two
+    independent reference half-buffers) — an estimator with any other expectation or variance lands outside; relMSE finite."""
+    rs = ref_scene(name)
+    rt = gpu_scene(rtb, name)
+    a, _, _ = rs.render(rspp, 0, fresh=True)
+    b2, _, _ = rs.render(rspp, 0, fresh=False)
+    ha, hb = a / rspp, (b2 - a) / rspp
+    rt.render(spp, 0)
+    img = rt.read_film() / spp
+    lum = np.array([0.2126, 0.7152, 0.0722])
+    ref = 0.5 * (ha + hb)
+    la, lr = float((img @ lum).mean()), float((ref @ lum).mean())
+    halves = abs(float(((ha - hb) @ lum).mean())) / lr
+    assert abs(la / lr - 1) < max(0.005, 3 * halves), (la, lr, halves)
+    ba, bb, bg, br = (raysets.block_mean(x) for x in (ha, hb, img, ref))
+    sigma1 = np.sqrt(np.mean((ba - bb) ** 2) / 2 * rspp)
+    expect = sigma1 * np.sqrt(1 / spp + 1 / (2 * rspp))
+    rmse = np.sqrt(np.mean((bg - br) ** 2))
+    assert 0.8 * expect < rmse < 1.25 * expect, (rmse, expect)
+    relmse = float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2)))
+    assert np.isfinite(relmse)
+
+
 @pytest.mark.parametrize("name,spp", [("MaterialsScene", 64), ("materialball", 64), ("coffee", 32), ("bathroom", 8),
                                       ("materialball_glass", 32), ("materialball_mirror", 32)])
 def test_image_statistics_equal_the_reference(rtb, name, spp):
