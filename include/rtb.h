@@ -402,10 +402,14 @@ int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam);
 int rtb_clear(rtb_ctx* ctx);
 /* spp_count calls of RayTracer::render() (Renderer.h:876-885) in one go: accumulates the
  * samples with global indices [spp_begin, spp_begin + spp_count) of every pixel this rank
- * owns (see rtb_params.partition) into the device sum-film.  Returns once the last batch of
- * kernels is enqueued on the context's stream (it may wait for earlier batches; the final
- * kernels still run asynchronously).  Resumable: the RNG is keyed by (seed, pixel, sample
- * index), not by call order.                                                              */
+ * owns (see rtb_params.partition) into the device sum-film.  ASYNCHRONOUS once the context has
+ * rendered this configuration (scene, sample count, parameters) before: the number of wavefront
+ * iterations it needed is remembered, the call enqueues that many (+ 6 % + 3; launches past the
+ * point where the pool drains exit at once) on the context's stream and returns; the next call
+ * on the context checks that the pool did drain and enqueues the rest if not.  The FIRST render
+ * of a configuration finds the iteration count with 2-5 small host probes and returns when its
+ * last batch is enqueued.  RTB_ASYNC_RENDER=0 keeps every call on the probing path.  Resumable:
+ * the RNG is keyed by (seed, pixel, sample index), not by call order.                        */
 int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count);
 /* RayTracer::adaptiveRender (Renderer.h:679-749; shipped commented out at :880), one call = one
  * render(): (1) adaptiveSampling (:583-641): init_samples (INIT_SAMPLES = 2, :23) paths per pixel,

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <dlfcn.h>
+#include <map>
 #include <new>
 #include <string>
 #include <thread>
@@ -66,6 +67,19 @@ struct StageEvents
 } // namespace
 
 #define RTB_MAX_POOLS 8
+
+// One wavefront render in flight (renderWavefront): everything needed to enqueue further iterations of it later.
+struct WfRun
+{
+	bool active = false; // iterations are enqueued but nobody has checked yet that the pool drained (rtb_render returned early)
+	WfArgs A[RTB_MAX_POOLS];
+	rtb_params P;
+	int K = 0, ti = 0;
+	uint32_t perPool = 0, nSlotsAlloc = 0, bound = 0, it = 0, vertices = 0, batch = 0;
+	unsigned gridExtend = 0, gridSlots = 0, gridSort = 0;
+	bool shadows = false, sortSh = false, sortEx = false, cwKernels = false, cwShadow = false, drained = false;
+	unsigned long long totalJobs = 0, key = 0;
+};
 
 struct rtb_ctx
 {
@@ -140,7 +154,14 @@ struct rtb_ctx
 	uint32_t* vplCounts = nullptr;
 	uint32_t vplPaths = 0;
 	cudaEvent_t evFork = nullptr;
-	uint64_t wfIterations = 0, wfHostSyncs = 0;
+	uint64_t wfIterations = 0, wfHostSyncs = 0, wfAsyncRenders = 0;
+	// rtb_render is asynchronous once a configuration has been rendered before: the iteration count it needed is remembered
+	// (iterHint) and the next identical call enqueues that many (+6 % + 3) at once and returns; whoever touches the context next
+	// (wfSettle) checks that the pool drained and enqueues the rest if it did not.
+	WfRun run;
+	std::map<unsigned long long, uint32_t> iterHint;
+	cudaEvent_t evProbe = nullptr;
+	int asyncRender = 1; // RTB_ASYNC_RENDER
 	// ---- device group (rtb_create_multi): this context is device 0 of the group and owns the film that is read
 	// out; `peers` are complete single-device contexts on the other GPUs (same scene, their own slot pools and
 	// accumulators).  See the "device groups" section below.
@@ -330,8 +351,11 @@ static void launchRender(rtb_ctx* ctx, const RenderArgs& A, dim3 grid, dim3 bloc
 }
 
 
+static int wfSettle(rtb_ctx* ctx);
+
 static int renderMegakernel(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 {
+	if (int rc = wfSettle(ctx)) return rc;
 	RenderArgs A;
 	A.accum = ctx->accum;
 	A.counters = ctx->counters;
@@ -381,8 +405,251 @@ static int32_t travRootHost(const DevScene& S)
 	return TRAV == RTB_TRAV_WIDE ? S.wide_root : TRAV == RTB_TRAV_Q16 ? S.q16_root : S.fast_root;
 }
 
+// enqueues iterations [R.it, end) of the run on its sub-pools' streams
+static void wfLaunch(rtb_ctx* ctx, WfRun& R, uint32_t end)
+{
+	ctx->wfIterations += (uint64_t)(end - R.it) * R.K;
+	for (; R.it < end; R.it++)
+	{
+			for (int k = 0; k < R.K; k++)
+			{
+				cudaStream_t st = ctx->poolStreams[k];
+				// stage timing: sub-pool 0, every 8th iteration (other sub-pools run concurrently)
+				bool timed = (k == 0) && (R.it % 8u) == 4u;
+				StageEvents se;
+				if (timed)
+				{
+					for (int e = 0; e < 4; e++) se.e[e] = getEvent(ctx);
+					cudaEventRecord(se.e[0], st);
+				}
+				// long rays (the scenes that also take the persistent any-hit kernel): smaller chunks shorten the tail of a
+				// persistent launch (+1.5 ... 2 %), short rays prefer fewer atomics (profiles/r02_refill_chunk_sweep.txt)
+				R.A[k].chunk = ctx->chunkOverride ? ctx->chunkOverride : (ctx->shadowPersistentAuto ? 64u : (uint32_t)WF_CHUNK);
+				if (R.sortEx && !ctx->simpleExtend && R.ti != RTB_TRAV_EXACT)
+				{
+					k_sort_count<1><<<R.gridSort, 256, 0, st>>>(ctx->S, R.A[k], R.it);
+					k_sort_scan<1><<<1, 1024, 0, st>>>(R.A[k], R.it);
+					k_sort_scatter<1><<<R.gridSort, 256, 0, st>>>(ctx->S, R.A[k], R.it);
+					ctx->launches += 3;
+				}
+				if (ctx->simpleExtend)
+				{
+					RTB_TRAV_SWITCH(R.ti, k_wf_extend_simple<TR><<<(R.perPool + 127) / 128, 128, 0, st>>>(ctx->S, R.A[k], R.it));
+				}
+				else if (R.cwKernels)
+				{
+					unsigned g = (unsigned)(ctx->smCount * ctx->cwBlocksPerSM[0]);
+					unsigned need = (R.perPool + WF_CW_THREADS - 1) / WF_CW_THREADS;
+					k_wf_trace_cw<false><<<g < need ? g : need, WF_CW_THREADS, ctx->cwSmemBytes, st>>>(ctx->S, R.A[k], R.it, ctx->cwStageNodes, ctx->cwStageLeaves);
+				}
+				else
+				{
+					RTB_TRAV_SWITCH(R.ti, k_wf_extend<TR><<<R.gridExtend, 128, 0, st>>>(ctx->S, R.A[k], R.it));
+				}
+				if (timed) cudaEventRecord(se.e[1], st);
+				// the shade stage refills the shadow queue: the previous iteration's shadow stage must be done with it
+				if (R.shadows && ctx->shadowAsync) cudaStreamWaitEvent(st, ctx->evShadowed[k], 0);
+#define RTB_SHADE_LAUNCH(INTEG)                                                                      \
+	do                                                                                               \
+	{                                                                                                \
+		if (R.A[k].primary) k_wf_shade<INTEG, true><<<R.gridSlots, 128, 0, st>>>(ctx->S, R.A[k], R.it);      \
+		else k_wf_shade<INTEG, false><<<R.gridSlots, 128, 0, st>>>(ctx->S, R.A[k], R.it);                  \
+	} while (0)
+				switch (R.P.integrator)
+				{
+				case RTB_INT_DIRECT: RTB_SHADE_LAUNCH(RTB_INT_DIRECT); break;
+				case RTB_INT_ALBEDO: RTB_SHADE_LAUNCH(RTB_INT_ALBEDO); break;
+				case RTB_INT_NORMALS: RTB_SHADE_LAUNCH(RTB_INT_NORMALS); break;
+				case RTB_INT_PATH_MIS: RTB_SHADE_LAUNCH(RTB_INT_PATH_MIS); break;
+				default: RTB_SHADE_LAUNCH(RTB_INT_PATH); break;
+				}
+#undef RTB_SHADE_LAUNCH
+				ctx->launches += 2;
+				if (timed) cudaEventRecord(se.e[2], st);
+				cudaStream_t sst = st;
+				if (R.shadows)
+				{
+					if (ctx->shadowAsync)
+					{
+						sst = ctx->shadowStreams[k];
+						cudaEventRecord(ctx->evShaded[k], st);
+						cudaStreamWaitEvent(sst, ctx->evShaded[k], 0);
+					}
+					if (R.sortSh)
+					{
+						k_sort_count<0><<<R.gridSort, 256, 0, sst>>>(ctx->S, R.A[k], R.it);
+						k_sort_scan<0><<<1, 1024, 0, sst>>>(R.A[k], R.it);
+						k_sort_scatter<0><<<R.gridSort, 256, 0, sst>>>(ctx->S, R.A[k], R.it);
+						ctx->launches += 3;
+					}
+					const bool persistShadow = !R.cwShadow && R.P.integrator != RTB_INT_PATH_MIS && R.ti != RTB_TRAV_EXACT && R.ti != RTB_TRAV_CW &&
+					                           (ctx->shadowPersistent < 0 ? ctx->shadowPersistentAuto : ctx->shadowPersistent != 0);
+					if (persistShadow)
+					{
+						RTB_TRAV_SWITCH(R.ti, if (travRootHost<TR>(ctx->S) >= 0) k_wf_shadow_persist<TR><<<R.gridExtend, 128, 0, sst>>>(ctx->S, R.A[k], R.it);
+						                else k_wf_shadow<TR><<<R.gridSlots, 128, 0, sst>>>(ctx->S, R.A[k], R.it));
+					}
+					else if (R.cwShadow)
+					{
+						unsigned g = (unsigned)(ctx->smCount * ctx->cwBlocksPerSM[1]);
+						k_wf_trace_cw<true><<<g, WF_CW_THREADS, ctx->cwSmemBytes, sst>>>(ctx->S, R.A[k], R.it, ctx->cwStageNodes, ctx->cwStageLeaves);
+					}
+					else if (R.P.integrator == RTB_INT_PATH_MIS)
+					{
+						RTB_TRAV_SWITCH(R.ti, k_wf_mis<TR><<<R.gridSlots, 128, 0, sst>>>(ctx->S, R.A[k], R.it));
+					}
+					else
+					{
+						RTB_TRAV_SWITCH(R.ti, k_wf_shadow<TR><<<R.gridSlots, 128, 0, sst>>>(ctx->S, R.A[k], R.it));
+					}
+					ctx->launches++;
+					if (ctx->shadowAsync) cudaEventRecord(ctx->evShadowed[k], sst);
+				}
+				if (timed)
+				{
+					cudaEventRecord(se.e[3], sst);
+					ctx->pendingStages.push_back(se);
+				}
+			}
+	}
+}
+
+// device -> host: {shadow rays, slots alive} of the last enqueued iteration of every sub-pool, jobs claimed, work counters
+static int wfProbeIssue(rtb_ctx* ctx, WfRun& R)
+{
+	for (int k = 0; k < R.K; k++)
+		CK(cudaMemcpyAsync(&ctx->hostProbe[1 + k], &R.A[k].ctrl[R.it - 1], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->poolStreams[k]));
+	CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->poolStreams[0]));
+	CK(cudaMemcpyAsync(&ctx->hostProbe[1 + RTB_MAX_POOLS], ctx->counters, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+	                   ctx->poolStreams[0]));
+	return RTB_OK;
+}
+
+// after the probe's copies have completed: drained?  otherwise the size of the next batch
+static void wfProbeRead(rtb_ctx* ctx, WfRun& R)
+{
+	ctx->wfHostSyncs++;
+	{
+		// Which any-hit kernel suits this scene: long shadow rays (bathroom: 65 box tests per ray, the soups: 130+) gain
+		// 6 ... 12 % from the persistent kernel, short ones (coffee: 38, the small scenes: 9 ... 14) lose 5 ... 10 %
+		// (profiles/r02_persistent_shadow.txt).  Decided from the work counters the probe brings along anyway; the film
+		// does not depend on the choice.
+		unsigned long long rays = 0, boxes = 0;
+		for (int r = 0; r < RTB_COUNTER_STRIPES; r++)
+			rays += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 2], boxes += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 5];
+		if (rays > 100000ull) ctx->shadowPersistentAuto = boxes > 50ull * rays;
+	}
+	unsigned long long claimed = ctx->hostProbe[0];
+	uint32_t alive = 0;
+	for (int k = 0; k < R.K; k++) alive += (uint32_t)(ctx->hostProbe[1 + k] >> 32); // WfCtrl{nShadow, alive}
+	if (alive == 0)
+	{
+		R.drained = true;
+		return;
+	}
+	// predict the remaining iterations from the job rate seen so far
+	unsigned long long started = claimed < R.totalJobs ? claimed : R.totalJobs;
+	double perIter = (started > R.nSlotsAlloc) ? (double)(started - R.nSlotsAlloc) / (double)R.it : 0.0;
+	double remaining = (double)(R.totalJobs - started);
+	double predict = (perIter > 0.0) ? remaining / perIter : (double)R.batch * 2.0;
+	uint32_t next = (uint32_t)(predict * 0.9);
+	if (remaining == 0.0) next = R.vertices; // tail: the last paths finish within `vertices` iterations
+	if (next < 4) next = 4;
+	if (next > 4096) next = 4096;
+	R.batch = next;
+}
+
+// the sub-pools' streams rejoin ctx->stream; the render's device time runs from `ev.a` to here
+static void wfJoin(rtb_ctx* ctx, WfRun& R, EventPair ev)
+{
+	for (int k = 0; k < R.K; k++)
+	{
+		if (R.shadows && ctx->shadowAsync) cudaStreamWaitEvent(ctx->poolStreams[k], ctx->evShadowed[k], 0);
+		cudaEventRecord(ctx->poolDone[k], ctx->poolStreams[k]);
+		cudaStreamWaitEvent(ctx->stream, ctx->poolDone[k], 0);
+	}
+	cudaEventRecord(ev.b, ctx->stream);
+	ctx->pending.push_back(ev);
+}
+
+// batches + probes until the pool has drained (the synchronous part of a render)
+static int wfRunToEnd(rtb_ctx* ctx, WfRun& R)
+{
+	while (!R.drained && R.it < R.bound)
+	{
+		uint32_t end = R.it + R.batch;
+		if (end > R.bound) end = R.bound;
+		wfLaunch(ctx, R, end);
+		if (int rc = wfProbeIssue(ctx, R)) return rc;
+		for (int k = 0; k < R.K; k++) CK(cudaStreamSynchronize(ctx->poolStreams[k]));
+		wfProbeRead(ctx, R);
+	}
+	if (R.drained)
+	{
+		// how many iterations the sub-pools really needed: the first whose shade stage left no slot alive
+		uint32_t lookBack = R.it < 4096u ? R.it : 4096u, needed = R.it;
+		std::vector<WfCtrl> tail((size_t)lookBack);
+		uint32_t worst = 0;
+		for (int k = 0; k < R.K; k++)
+		{
+			CK(cudaMemcpy(tail.data(), &R.A[k].ctrl[R.it - lookBack], (size_t)lookBack * sizeof(WfCtrl), cudaMemcpyDeviceToHost));
+			uint32_t first = R.it;
+			for (uint32_t j = 0; j < lookBack; j++)
+				if (tail[j].alive == 0)
+				{
+					first = R.it - lookBack + j + 1;
+					break;
+				}
+			if (first > worst) worst = first;
+		}
+		if (worst) needed = worst;
+		ctx->iterHint[R.key] = needed;
+	}
+	return RTB_OK;
+}
+
+// Completes a render that rtb_render left in flight (WfRun::active): waits for its probe, and if the remembered iteration
+// count fell short, enqueues the rest.  Called by every entry point before it touches the context.
+static int wfSettle(rtb_ctx* ctx)
+{
+	WfRun& R = ctx->run;
+	if (!R.active) return RTB_OK;
+	R.active = false;
+	if (int rc = bind(ctx)) return rc;
+	CK(cudaEventSynchronize(ctx->evProbe));
+	wfProbeRead(ctx, R);
+	if (!R.drained)
+	{
+		EventPair ev = {getEvent(ctx), getEvent(ctx)};
+		cudaEventRecord(ev.a, ctx->stream);
+		cudaEventRecord(ctx->evFork, ctx->stream);
+		for (int k = 0; k < R.K; k++) cudaStreamWaitEvent(ctx->poolStreams[k], ctx->evFork, 0);
+		int rc = wfRunToEnd(ctx, R);
+		wfJoin(ctx, R, ev);
+		if (rc) return rc;
+		CK(cudaGetLastError());
+		if (!R.drained) return fail(ctx, RTB_ERR_STATE, "wavefront did not drain within its iteration bound (%u)", R.bound);
+	}
+	return RTB_OK;
+}
+
+// the context and, for a device group, every member
+static int wfSettleAll(rtb_ctx* ctx)
+{
+	for (rtb_ctx* m : ctx->peers)
+		if (int rc = wfSettle(m))
+		{
+			ctx->error = m->error;
+			return rc;
+		}
+	int rc = wfSettle(ctx);
+	if (!ctx->peers.empty()) cudaSetDevice(ctx->device);
+	return rc;
+}
+
 static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count, const AdaptivePlan* plan = nullptr)
 {
+	if (int rc = wfSettle(ctx)) return rc; // the previous render of this context may still be in flight
 	const rtb_params& P = ctx->params;
 	uint32_t sFirst = spp_begin, sStep = 1, sCount = spp_count;
 	if (!plan && P.partition == RTB_PART_SPP && P.part_world > 1)
@@ -441,6 +708,7 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 			CK(cudaEventCreateWithFlags(&ctx->evShadowed[k], cudaEventDisableTiming));
 		}
 		if (const char* e = getenv("RTB_SHADOW_ASYNC")) ctx->shadowAsync = atoi(e) != 0;
+		if (const char* e = getenv("RTB_ASYNC_RENDER")) ctx->asyncRender = atoi(e);
 		CK(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
 	}
 	uint32_t nSlotsAll = ctx->poolSlots;
@@ -451,8 +719,8 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	uint32_t nSlotsAlloc = perPool * (uint32_t)K;
 	// shadow queue: one entry per slot and launch, WF_SHADOW_PER_SLOT with the multi-pass shade stage
 	const size_t F = P.primary_reuse ? WF_SHADOW_PER_SLOT : 1u;
-	const size_t R = (P.integrator == RTB_INT_PATH_MIS) ? 6u : 3u; // float4 per queue record
-	size_t need = (size_t)nSlotsAlloc * (4 + R * F) * sizeof(float4);
+	const size_t RQ = (P.integrator == RTB_INT_PATH_MIS) ? 6u : 3u; // float4 per queue record
+	size_t need = (size_t)nSlotsAlloc * (4 + RQ * F) * sizeof(float4);
 	if (need > ctx->wfStateBytes)
 	{
 		CK(cudaStreamSynchronize(ctx->stream));
@@ -545,7 +813,8 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	}
 	const bool cwShadow = cwKernels && (ctx->cwShadowPersistent < 0 ? true : ctx->cwShadowPersistent != 0) && P.integrator != RTB_INT_PATH_MIS;
 	if (P.primary_reuse && !ctx->wfPrimary) CK(cudaMalloc((void**)&ctx->wfPrimary, (size_t)ctx->width * ctx->height * sizeof(float4)));
-	WfArgs A[RTB_MAX_POOLS];
+	WfRun& R = ctx->run;
+	WfArgs* A = R.A;
 	float4* base = (float4*)ctx->wfState;
 	for (int k = 0; k < K; k++)
 	{
@@ -589,6 +858,9 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 	if (gridSlots > maxBlocks) gridSlots = maxBlocks;
 	if (gridExtend > (perPool + 127) / 128) gridExtend = (perPool + 127) / 128;
 	bool shadows = (P.integrator == RTB_INT_PATH || P.integrator == RTB_INT_DIRECT || P.integrator == RTB_INT_PATH_MIS);
+	R.P = P, R.K = K, R.ti = ti, R.perPool = perPool, R.nSlotsAlloc = nSlotsAlloc, R.bound = bound, R.vertices = vertices;
+	R.gridExtend = gridExtend, R.gridSlots = gridSlots, R.gridSort = gridSort;
+	R.shadows = shadows, R.sortSh = sortSh, R.sortEx = sortEx, R.cwKernels = cwKernels, R.cwShadow = cwShadow, R.totalJobs = totalJobs;
 	EventPair ev = {getEvent(ctx), getEvent(ctx)};
 	cudaEventRecord(ev.a, ctx->stream);
 	if (P.primary_reuse)
@@ -608,167 +880,41 @@ static int renderWavefront(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count,
 		k_wf_init<<<(perPool + 255) / 256, 256, 0, ctx->poolStreams[k]>>>(ctx->S, A[k]);
 		ctx->launches++;
 	}
-	uint32_t it = 0;
-	uint32_t batch = vertices * 4 < 16 ? 16 : vertices * 4;
-	bool drained = false;
-	while (!drained && it < bound)
+	R.it = 0;
+	R.batch = R.vertices * 4 < 16 ? 16 : R.vertices * 4;
+	R.drained = false;
+	// A configuration that has been rendered before is enqueued in one go and NOT waited for: the remembered iteration
+	// count + 6 % + 3 (launches past the drain exit at once); wfSettle checks later and enqueues the rest if need be.
 	{
-		uint32_t end = it + batch;
-		if (end > bound) end = bound;
-		ctx->wfIterations += (uint64_t)(end - it) * K;
-		for (; it < end; it++)
-		{
-			for (int k = 0; k < K; k++)
-			{
-				cudaStream_t st = ctx->poolStreams[k];
-				// stage timing: sub-pool 0, every 8th iteration (other sub-pools run concurrently)
-				bool timed = (k == 0) && (it % 8u) == 4u;
-				StageEvents se;
-				if (timed)
-				{
-					for (int e = 0; e < 4; e++) se.e[e] = getEvent(ctx);
-					cudaEventRecord(se.e[0], st);
-				}
-				// long rays (the scenes that also take the persistent any-hit kernel): smaller chunks shorten the tail of a
-				// persistent launch (+1.5 ... 2 %), short rays prefer fewer atomics (profiles/r02_refill_chunk_sweep.txt)
-				A[k].chunk = ctx->chunkOverride ? ctx->chunkOverride : (ctx->shadowPersistentAuto ? 64u : (uint32_t)WF_CHUNK);
-				if (sortEx && !ctx->simpleExtend && ti != RTB_TRAV_EXACT)
-				{
-					k_sort_count<1><<<gridSort, 256, 0, st>>>(ctx->S, A[k], it);
-					k_sort_scan<1><<<1, 1024, 0, st>>>(A[k], it);
-					k_sort_scatter<1><<<gridSort, 256, 0, st>>>(ctx->S, A[k], it);
-					ctx->launches += 3;
-				}
-				if (ctx->simpleExtend)
-				{
-					RTB_TRAV_SWITCH(ti, k_wf_extend_simple<TR><<<(perPool + 127) / 128, 128, 0, st>>>(ctx->S, A[k], it));
-				}
-				else if (cwKernels)
-				{
-					unsigned g = (unsigned)(ctx->smCount * ctx->cwBlocksPerSM[0]);
-					unsigned need = (perPool + WF_CW_THREADS - 1) / WF_CW_THREADS;
-					k_wf_trace_cw<false><<<g < need ? g : need, WF_CW_THREADS, ctx->cwSmemBytes, st>>>(ctx->S, A[k], it, ctx->cwStageNodes, ctx->cwStageLeaves);
-				}
-				else
-				{
-					RTB_TRAV_SWITCH(ti, k_wf_extend<TR><<<gridExtend, 128, 0, st>>>(ctx->S, A[k], it));
-				}
-				if (timed) cudaEventRecord(se.e[1], st);
-				// the shade stage refills the shadow queue: the previous iteration's shadow stage must be done with it
-				if (shadows && ctx->shadowAsync) cudaStreamWaitEvent(st, ctx->evShadowed[k], 0);
-#define RTB_SHADE_LAUNCH(INTEG)                                                                      \
-	do                                                                                               \
-	{                                                                                                \
-		if (A[k].primary) k_wf_shade<INTEG, true><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);      \
-		else k_wf_shade<INTEG, false><<<gridSlots, 128, 0, st>>>(ctx->S, A[k], it);                  \
-	} while (0)
-				switch (P.integrator)
-				{
-				case RTB_INT_DIRECT: RTB_SHADE_LAUNCH(RTB_INT_DIRECT); break;
-				case RTB_INT_ALBEDO: RTB_SHADE_LAUNCH(RTB_INT_ALBEDO); break;
-				case RTB_INT_NORMALS: RTB_SHADE_LAUNCH(RTB_INT_NORMALS); break;
-				case RTB_INT_PATH_MIS: RTB_SHADE_LAUNCH(RTB_INT_PATH_MIS); break;
-				default: RTB_SHADE_LAUNCH(RTB_INT_PATH); break;
-				}
-#undef RTB_SHADE_LAUNCH
-				ctx->launches += 2;
-				if (timed) cudaEventRecord(se.e[2], st);
-				cudaStream_t sst = st;
-				if (shadows)
-				{
-					if (ctx->shadowAsync)
-					{
-						sst = ctx->shadowStreams[k];
-						cudaEventRecord(ctx->evShaded[k], st);
-						cudaStreamWaitEvent(sst, ctx->evShaded[k], 0);
-					}
-					if (sortSh)
-					{
-						k_sort_count<0><<<gridSort, 256, 0, sst>>>(ctx->S, A[k], it);
-						k_sort_scan<0><<<1, 1024, 0, sst>>>(A[k], it);
-						k_sort_scatter<0><<<gridSort, 256, 0, sst>>>(ctx->S, A[k], it);
-						ctx->launches += 3;
-					}
-					const bool persistShadow = !cwShadow && P.integrator != RTB_INT_PATH_MIS && ti != RTB_TRAV_EXACT && ti != RTB_TRAV_CW &&
-					                           (ctx->shadowPersistent < 0 ? ctx->shadowPersistentAuto : ctx->shadowPersistent != 0);
-					if (persistShadow)
-					{
-						RTB_TRAV_SWITCH(ti, if (travRootHost<TR>(ctx->S) >= 0) k_wf_shadow_persist<TR><<<gridExtend, 128, 0, sst>>>(ctx->S, A[k], it);
-						                else k_wf_shadow<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
-					}
-					else if (cwShadow)
-					{
-						unsigned g = (unsigned)(ctx->smCount * ctx->cwBlocksPerSM[1]);
-						k_wf_trace_cw<true><<<g, WF_CW_THREADS, ctx->cwSmemBytes, sst>>>(ctx->S, A[k], it, ctx->cwStageNodes, ctx->cwStageLeaves);
-					}
-					else if (P.integrator == RTB_INT_PATH_MIS)
-					{
-						RTB_TRAV_SWITCH(ti, k_wf_mis<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
-					}
-					else
-					{
-						RTB_TRAV_SWITCH(ti, k_wf_shadow<TR><<<gridSlots, 128, 0, sst>>>(ctx->S, A[k], it));
-					}
-					ctx->launches++;
-					if (ctx->shadowAsync) cudaEventRecord(ctx->evShadowed[k], sst);
-				}
-				if (timed)
-				{
-					cudaEventRecord(se.e[3], sst);
-					ctx->pendingStages.push_back(se);
-				}
-			}
-		}
-		// probe: jobs claimed so far and slots alive after the last enqueued iteration of every sub-pool
-		for (int k = 0; k < K; k++)
-		{
-			CK(cudaMemcpyAsync(&ctx->hostProbe[1 + k], &A[k].ctrl[it - 1], 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->poolStreams[k]));
-		}
-		CK(cudaMemcpyAsync(&ctx->hostProbe[0], &ctx->wfGlobal->nextJob, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->poolStreams[0]));
-		CK(cudaMemcpyAsync(&ctx->hostProbe[1 + RTB_MAX_POOLS], ctx->counters, RTB_COUNTER_STRIPES * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-		                   ctx->poolStreams[0]));
-		for (int k = 0; k < K; k++) CK(cudaStreamSynchronize(ctx->poolStreams[k]));
-		ctx->wfHostSyncs++;
-		{
-			// Which any-hit kernel suits this scene: long shadow rays (bathroom: 65 box tests per ray, the soups: 130+) gain
-			// 6 ... 12 % from the persistent kernel, short ones (coffee: 38, the small scenes: 9 ... 14) lose 5 ... 10 %
-			// (profiles/r02_persistent_shadow.txt).  Decided from the work counters the probe brings along anyway; the film
-			// does not depend on the choice.
-			unsigned long long rays = 0, boxes = 0;
-			for (int r = 0; r < RTB_COUNTER_STRIPES; r++)
-				rays += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 2], boxes += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 5];
-			if (rays > 100000ull) ctx->shadowPersistentAuto = boxes > 50ull * rays;
-		}
-		unsigned long long claimed = ctx->hostProbe[0];
-		uint32_t alive = 0;
-		for (int k = 0; k < K; k++) alive += (uint32_t)(ctx->hostProbe[1 + k] >> 32); // WfCtrl{nShadow, alive}
-		if (alive == 0)
-		{
-			drained = true;
-			break;
-		}
-		// predict the remaining iterations from the job rate seen so far
-		unsigned long long started = claimed < totalJobs ? claimed : totalJobs;
-		double perIter = (started > nSlotsAlloc) ? (double)(started - nSlotsAlloc) / (double)it : 0.0;
-		double remaining = (double)(totalJobs - started);
-		double predict = (perIter > 0.0) ? remaining / perIter : (double)batch * 2.0;
-		uint32_t next = (uint32_t)(predict * 0.9);
-		if (remaining == 0.0) next = vertices; // tail: the last paths finish within `vertices` iterations
-		if (next < 4) next = 4;
-		if (next > 4096) next = 4096;
-		batch = next;
+		unsigned long long h = 1469598103934665603ull;
+		const unsigned long long parts[10] = {R.totalJobs, R.perPool, (unsigned long long)R.K, (unsigned long long)P.integrator, (unsigned long long)P.max_depth,
+		                                       (unsigned long long)P.traversal, (unsigned long long)P.primary_reuse, (unsigned long long)P.sampling,
+		                                       (unsigned long long)(plan ? 1 : 0), (unsigned long long)ctx->S.n_tris};
+		for (unsigned long long v : parts) h = (h ^ v) * 1099511628211ull;
+		R.key = h;
 	}
-	// join
-	for (int k = 0; k < K; k++)
+	auto hint = ctx->iterHint.find(R.key);
+	if (ctx->asyncRender && !plan && hint != ctx->iterHint.end())
 	{
-		if (shadows && ctx->shadowAsync) cudaStreamWaitEvent(ctx->poolStreams[k], ctx->evShadowed[k], 0);
-		cudaEventRecord(ctx->poolDone[k], ctx->poolStreams[k]);
-		cudaStreamWaitEvent(ctx->stream, ctx->poolDone[k], 0);
+		if (!ctx->evProbe) CK(cudaEventCreateWithFlags(&ctx->evProbe, cudaEventDisableTiming));
+		uint32_t n = hint->second + hint->second / 16u + 3u;
+		if (ctx->asyncRender == 2) n = hint->second / 2u + 1u; // RTB_ASYNC_RENDER=2 (tests): deliberately too few, wfSettle must enqueue the rest
+		if (n > R.bound) n = R.bound;
+		wfLaunch(ctx, R, n);
+		if (int rc = wfProbeIssue(ctx, R)) return rc;
+		wfJoin(ctx, R, ev);
+		CK(cudaEventRecord(ctx->evProbe, ctx->stream)); // ctx->stream now waits for every sub-pool stream, hence for the probe's copies
+		CK(cudaGetLastError());
+		R.active = true;
+		ctx->wfAsyncRenders++;
+		ctx->filmDirty = true;
+		return RTB_OK;
 	}
-	cudaEventRecord(ev.b, ctx->stream);
-	ctx->pending.push_back(ev);
+	int rc = wfRunToEnd(ctx, R);
+	wfJoin(ctx, R, ev);
+	if (rc) return rc;
 	CK(cudaGetLastError());
-	if (!drained) return fail(ctx, RTB_ERR_STATE, "wavefront did not drain within its iteration bound (%u)", bound);
+	if (!R.drained) return fail(ctx, RTB_ERR_STATE, "wavefront did not drain within its iteration bound (%u)", R.bound);
 	ctx->filmDirty = true;
 	return RTB_OK;
 }
@@ -919,6 +1065,7 @@ static int ncclInit(rtb_ctx* g)
 static int gatherAccum(rtb_ctx* g)
 {
 	rtb_ctx* ctx = g; // for CK
+	if (int rc = wfSettleAll(g)) return rc;
 	size_t n = groupSize(g);
 	if (n == 1) return RTB_OK;
 	bool any = false;
@@ -1208,6 +1355,7 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->haveScene = true;
 	ctx->accumDirty = false;
+	ctx->iterHint.clear(); // iteration counts remembered for the previous scene
 	return RTB_OK;
 }
 
@@ -1416,6 +1564,8 @@ int rtb_group_info(const rtb_ctx* ctx, int* devices, int* p2p, uint64_t* gathers
 void rtb_destroy(rtb_ctx* ctx)
 {
 	if (!ctx) return;
+	wfSettle(ctx);
+	if (ctx->evProbe) cudaEventDestroy(ctx->evProbe);
 	for (int d = 0; d < 8; d++)
 		if (ctx->ncclComms[d] && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->ncclComms[d]);
 	for (rtb_ctx* p : ctx->peers) rtb_destroy(p);
@@ -1453,6 +1603,7 @@ int rtb_set_stream(rtb_ctx* ctx, void* cuda_stream)
 int rtb_synchronize(rtb_ctx* ctx)
 {
 	if (!ctx) return RTB_ERR_ARG;
+	if (int rc = wfSettleAll(ctx)) return rc;
 	for (rtb_ctx* p : ctx->peers)
 	{
 		CK(cudaSetDevice(p->device));
@@ -1484,6 +1635,7 @@ int rtb_set_params(rtb_ctx* ctx, const rtb_params* p)
 	if (!(p->filter_radius >= 0.0f && p->filter_radius <= 16.0f) || !(fabsf(p->filter_alpha) <= 1e6f))
 		return fail(ctx, RTB_ERR_ARG, "bad Gaussian filter parameters (radius %g, alpha %g)", p->filter_radius, p->filter_alpha);
 	if (p->primary_reuse != 0 && p->primary_reuse != 1) return fail(ctx, RTB_ERR_ARG, "primary_reuse must be 0 or 1");
+	if (int rc = wfSettleAll(ctx)) return rc;
 	ctx->params = *p;
 	ctx->userParams = *p;
 	for (rtb_ctx* m : ctx->peers) m->params = *p, m->userParams = *p;
@@ -1500,6 +1652,7 @@ int rtb_get_params(const rtb_ctx* ctx, rtb_params* p)
 int rtb_upload_scene(rtb_ctx* ctx, const rtb_scene_desc* sc)
 {
 	if (!ctx || !sc) return fail(ctx, RTB_ERR_ARG, "rtb_upload_scene: NULL argument");
+	if (int rc = wfSettleAll(ctx)) return rc;
 	PreparedScene ps;
 	if (int rc = prepareScene(ctx, sc, ps)) return rc;
 	return forEachMember(ctx, [&ps](rtb_ctx* m, int) { return uploadPrepared(m, ps); });
@@ -1511,6 +1664,7 @@ int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam)
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if ((uint32_t)cam->width != ctx->width || (uint32_t)cam->height != ctx->height)
 		return fail(ctx, RTB_ERR_ARG, "camera film size differs from the uploaded scene's");
+	if (int rc = wfSettleAll(ctx)) return rc; // iterations enqueued later must not see another camera
 	ctx->S.cam = *cam;
 	for (rtb_ctx* m : ctx->peers) m->S.cam = *cam;
 	return RTB_OK;
@@ -1519,6 +1673,7 @@ int rtb_update_camera(rtb_ctx* ctx, const rtb_camera* cam)
 static int clearOne(rtb_ctx* ctx)
 {
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = wfSettle(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	ctx->accumDirty = false;
 	CK(cudaMemsetAsync(ctx->film, 0, (size_t)ctx->width * ctx->height * 3 * sizeof(float), ctx->stream));
@@ -1565,6 +1720,7 @@ int rtb_render(rtb_ctx* ctx, uint32_t spp_begin, uint32_t spp_count)
 // pass_count x RayTracer::lightTracer() (Renderer.h:220-231).
 static int lightOne(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 {
+	if (int rc = wfSettle(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	if (int rc = ensureTraversal(ctx, ctx->params.traversal)) return rc;
 	rtb_camera_ext ce;
@@ -1610,6 +1766,7 @@ int rtb_render_light(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count)
 // pass_count x RayTracer::instantRadiosity() (Renderer.h:102-123).
 static int irOne(rtb_ctx* ctx, uint32_t pass_begin, uint32_t pass_count, uint32_t n_paths)
 {
+	if (int rc = wfSettle(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	if (int rc = ensureTraversal(ctx, ctx->params.traversal)) return rc;
 	if (ctx->vplPaths < n_paths)
@@ -1795,6 +1952,7 @@ int rtb_write_film(rtb_ctx* ctx, const float* rgb_sum)
 {
 	if (!ctx || !rgb_sum) return fail(ctx, RTB_ERR_ARG, "rtb_write_film: NULL argument");
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = wfSettleAll(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	// a device group: the written film replaces the sum of ALL members' accumulators
 	for (rtb_ctx* m : ctx->peers)
@@ -1830,6 +1988,7 @@ int rtb_accum_device_ptr(rtb_ctx* ctx, void** dptr, uint64_t* n_int64)
 {
 	if (!ctx || !dptr) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
+	if (int rc = wfSettleAll(ctx)) return rc; // the caller is about to reduce these sums: the render must be complete
 	if (!ctx->peers.empty())
 	{
 		if (int rc = bind(ctx)) return rc;
@@ -1902,6 +2061,7 @@ int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out)
 
 static int statsOne(rtb_ctx* ctx, rtb_stats* out)
 {
+	if (int rc = wfSettle(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	unsigned long long rows[RTB_COUNTER_STRIPES * 8], c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	CK(cudaMemcpyAsync(rows, ctx->counters, sizeof(rows), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1930,6 +2090,7 @@ int rtb_primary_hits(rtb_ctx* ctx, int traversal, uint32_t* ids, float* t, rtb_r
 	if (!ctx) return RTB_ERR_ARG;
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (int rc = checkTrav(ctx, traversal)) return rc;
+	if (int rc = wfSettleAll(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	if (int rc = ensureTraversal(ctx, traversal)) return rc;
 	size_t n = (size_t)ctx->width * ctx->height;
@@ -1958,6 +2119,7 @@ int rtb_trace(rtb_ctx* ctx, int traversal, int any_hit, const rtb_ray* rays, uin
 	if (int rc = checkTrav(ctx, traversal)) return rc;
 	if (n == 0) return RTB_OK;
 	if (!rays || !hits) return fail(ctx, RTB_ERR_ARG, "rtb_trace: NULL buffer");
+	if (int rc = wfSettleAll(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	if (int rc = ensureTraversal(ctx, traversal)) return rc;
 	Scratch sc;
@@ -1981,6 +2143,7 @@ int rtb_visible(rtb_ctx* ctx, int traversal, const float* p1p2, uint64_t n, uint
 	if (int rc = checkTrav(ctx, traversal)) return rc;
 	if (n == 0) return RTB_OK;
 	if (!p1p2 || !out) return fail(ctx, RTB_ERR_ARG, "rtb_visible: NULL buffer");
+	if (int rc = wfSettleAll(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	if (int rc = ensureTraversal(ctx, traversal)) return rc;
 	Scratch sc;
@@ -2003,6 +2166,7 @@ int rtb_shading_data(rtb_ctx* ctx, const rtb_ray* rays, const rtb_hit* hits, uin
 	if (!ctx->haveScene) return fail(ctx, RTB_ERR_STATE, "no scene uploaded");
 	if (n == 0) return RTB_OK;
 	if (!rays || !hits || !out) return fail(ctx, RTB_ERR_ARG, "rtb_shading_data: NULL buffer");
+	if (int rc = wfSettleAll(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	Scratch sc;
 	rtb_ray* dR;
@@ -2028,6 +2192,7 @@ int rtb_eval_bsdf(rtb_ctx* ctx, const rtb_shading* sd, const float* wi, const fl
 	if (!sd || !wi || !u) return fail(ctx, RTB_ERR_ARG, "rtb_eval_bsdf: NULL input");
 	for (uint64_t i = 0; i < n; i++)
 		if (sd[i].material < 0 || (uint32_t)sd[i].material >= ctx->S.n_mats) return fail(ctx, RTB_ERR_ARG, "rtb_eval_bsdf: record %llu has no material", (unsigned long long)i);
+	if (int rc = wfSettleAll(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	Scratch sc;
 	rtb_shading* dS;
@@ -2061,6 +2226,7 @@ int rtb_eval_light(rtb_ctx* ctx, const int32_t* light, const float* wi, const fl
 	if (!light || !wi || !u) return fail(ctx, RTB_ERR_ARG, "rtb_eval_light: NULL input");
 	for (uint64_t i = 0; i < n; i++)
 		if (light[i] < 0 || (uint32_t)light[i] >= ctx->S.n_lights) return fail(ctx, RTB_ERR_ARG, "rtb_eval_light: light index %d out of range", light[i]);
+	if (int rc = wfSettleAll(ctx)) return rc;
 	if (int rc = bind(ctx)) return rc;
 	Scratch sc;
 	int32_t* dL;

@@ -910,6 +910,63 @@ def test_film_is_a_resumable_deterministic_sum(rtb):
     assert rt.read_film().tobytes() == a.tobytes()      # bit-reproducible run to run
 
 
+def test_render_is_asynchronous_once_the_iteration_count_is_known(rtb, monkeypatch):
+    """rtb_render's contract (SURVEY 8b: "asynchronous"): the first render of a configuration probes the device a few times;
+    repeating it enqueues the remembered number of iterations and returns while the GPU is still working.  The film is the
+    same bits either way, also when the remembered count falls short (a later call enqueues the rest) and when the camera,
+    the film or the parameters are touched right after the call."""
+    import time
+    try:
+        rt = gpu_scene(rtb, "coffee")
+        spp = 192
+    except pytest.skip.Exception:
+        rt = gpu_scene(rtb, "cornell-box")
+        spp = 96
+    rt.set_params(primary_reuse=0)
+    rt.render(spp, 0)                        # finds the iteration count (probing path)
+    rt.synchronize()
+    want = rt.read_film().copy()
+    syncs0 = rt.stats()["host_syncs"]
+    rt.clear()
+    t0 = time.perf_counter()
+    rt.render(spp, 0)
+    t_call = time.perf_counter() - t0
+    rt.synchronize()
+    t_all = time.perf_counter() - t0
+    assert t_call < 0.5 * t_all, (t_call, t_all)          # the call returned long before the device was done
+    assert rt.read_film().tobytes() == want.tobytes()
+    assert rt.stats()["host_syncs"] == 1                   # one look at the probe instead of one per batch (clear reset the counter)
+    assert syncs0 >= 2
+    # touched immediately after the call: clear / camera / parameters / another render all see a completed render
+    rt.clear()
+    rt.render(spp, 0)
+    rt.update_camera(rt.scene.camera)
+    rt.set_params(primary_reuse=0)
+    rt.render(spp, spp)
+    both = rt.read_film().copy()
+    rt.clear()
+    rt.render(2 * spp, 0)
+    assert rt.read_film().tobytes() == both.tobytes()
+    # the probing path (0) gives the same bits, and so does a remembered count that falls short (2: half of what is needed
+    # is enqueued; the next call on the context finds the pool still alive and enqueues the rest)
+    for mode in ("0", "2"):
+        monkeypatch.setenv("RTB_ASYNC_RENDER", mode)
+        r2 = rtb.RayTracer(0)
+        r2.init(rt.scene)
+        r2.set_params(primary_reuse=0)
+        r2.render(spp, 0)
+        r2.clear()
+        r2.render(spp, 0)
+        assert r2.read_film().tobytes() == want.tobytes(), mode
+        st = r2.stats()
+        assert st["samples"] == rt.width * rt.height * spp, mode
+        r2.clear()
+        r2.render(spp, 0)
+        r2.render(spp, spp)                  # settles the first one (short in mode 2) before starting
+        assert r2.read_film().tobytes() == both.tobytes(), mode
+        r2.close()
+
+
 def test_partitions_compose_to_the_single_gpu_film(rtb):
     """Multi-GPU partitioning, emulated on one device: tile slices are disjoint and compose
     bit-exactly; spp slices compose up to summation order."""
