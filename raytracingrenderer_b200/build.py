@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtb200.so")
 
 SOURCES = ["rtb_api.cu"]
-DEPS = ["rtb_api.cu", "rtb_kernels.cuh", "rtb_dev_scene.cuh", "rtb_dev_math.cuh", "rtb_accel.hpp"]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h")))  # every source and header of the library
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

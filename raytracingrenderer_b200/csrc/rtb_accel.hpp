@@ -5,6 +5,9 @@
 //     box test that admits a leaf is the reference's own leaf test,
 //   * the environment-map sampling tables.
 #pragma once
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include "../../include/rtb.h"
 
 #include <algorithm>
@@ -37,39 +40,25 @@ struct RefLeaf
 	uint32_t start, count;
 };
 
-inline bool buildExact(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris, std::vector<F4>& xnodes,
-                       std::vector<RefLeaf>& leaves, const char** err)
+// One forward pass over the pre-order node array: skip[i] = first index after i's subtree (a parent precedes its
+// children, so skip[i] is final when i is reached), the leaves in index order, and the range checks.
+inline bool buildSkipLinks(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris, std::vector<uint32_t>& skip,
+                           std::vector<RefLeaf>& leaves, const char** err)
 {
-	xnodes.resize((size_t)n * 2);
+	skip.assign(n, 0);
 	leaves.clear();
 	if (n == 0) return true;
-	std::vector<uint32_t> skip(n, 0);
-	// iterative post-order: skip[i] = first index after i's subtree
-	struct Item
-	{
-		uint32_t node, end;
-	};
-	std::vector<Item> stack;
-	stack.push_back({0u, n});
-	while (!stack.empty())
-	{
-		Item it = stack.back();
-		stack.pop_back();
-		const rtb_ref_node& nd = nodes[it.node];
-		skip[it.node] = it.end;
-		if (nd.a < 0) continue;
-		if ((uint32_t)nd.a != it.node + 1 || (uint32_t)nd.b <= it.node + 1 || (uint32_t)nd.b >= it.end)
-		{
-			*err = "ref_nodes is not a pre-order tree";
-			return false;
-		}
-		stack.push_back({(uint32_t)nd.a, (uint32_t)nd.b});
-		stack.push_back({(uint32_t)nd.b, it.end});
-	}
+	leaves.reserve((size_t)n / 2 + 1);
+	skip[0] = n;
 	for (uint32_t i = 0; i < n; i++)
 	{
 		const rtb_ref_node& nd = nodes[i];
-		uint32_t leaf = 0xFFFFFFFFu;
+		const uint32_t end = skip[i];
+		if (end == 0)
+		{
+			*err = "ref_nodes is not a pre-order tree"; // a node no parent points to
+			return false;
+		}
 		if (nd.a < 0)
 		{
 			uint32_t start = (uint32_t)(~nd.a), count = (uint32_t)nd.b;
@@ -78,16 +67,50 @@ inline bool buildExact(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris, st
 				*err = "ref leaf out of range (count > 3 or start + count > n_tris)";
 				return false;
 			}
-			leaf = (start << 2) | count;
-			RefLeaf L;
-			memcpy(L.bmin, nd.bmin, 12);
-			memcpy(L.bmax, nd.bmax, 12);
-			L.start = start, L.count = count;
-			if (count) leaves.push_back(L);
+			if (end != i + 1)
+			{
+				*err = "ref_nodes is not a pre-order tree";
+				return false;
+			}
+			if (count)
+			{
+				RefLeaf L;
+				memcpy(L.bmin, nd.bmin, 12);
+				memcpy(L.bmax, nd.bmax, 12);
+				L.start = start, L.count = count;
+				leaves.push_back(L);
+			}
+			continue;
 		}
-		xnodes[(size_t)i * 2] = {nd.bmin[0], nd.bmin[1], nd.bmin[2], bitsToFloat(skip[i])};
-		xnodes[(size_t)i * 2 + 1] = {nd.bmax[0], nd.bmax[1], nd.bmax[2], bitsToFloat(leaf)};
+		if ((uint32_t)nd.a != i + 1 || (uint32_t)nd.b <= i + 1 || (uint32_t)nd.b >= end)
+		{
+			*err = "ref_nodes is not a pre-order tree";
+			return false;
+		}
+		skip[(uint32_t)nd.a] = (uint32_t)nd.b;
+		skip[(uint32_t)nd.b] = end;
 	}
+	return true;
+}
+
+// The EXACT traversal's node pair [bmin, skip][bmax, leaf] (the device assembles the same pair from ref_nodes + skip:
+// k_exact_nodes, rtb_api.cu)
+inline void exactNodePair(const rtb_ref_node& nd, uint32_t skip, F4* out)
+{
+	uint32_t leaf = 0xFFFFFFFFu;
+	if (nd.a < 0) leaf = ((uint32_t)(~nd.a) << 2) | (uint32_t)nd.b;
+	out[0] = {nd.bmin[0], nd.bmin[1], nd.bmin[2], bitsToFloat(skip)};
+	out[1] = {nd.bmax[0], nd.bmax[1], nd.bmax[2], bitsToFloat(leaf)};
+}
+
+inline bool buildExact(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris, std::vector<F4>& xnodes,
+                       std::vector<RefLeaf>& leaves, const char** err)
+{
+	std::vector<uint32_t> skip;
+	xnodes.clear();
+	if (!buildSkipLinks(nodes, n, nTris, skip, leaves, err)) return false;
+	xnodes.resize((size_t)n * 2);
+	for (uint32_t i = 0; i < n; i++) exactNodePair(nodes[i], skip[i], &xnodes[(size_t)i * 2]);
 	return true;
 }
 
@@ -141,37 +164,59 @@ public:
 			out.root = ~0; // empty leaf (start 0, count 0)
 			return;
 		}
-		idx.resize(n);
-		cen.resize((size_t)n * 3);
-		for (uint32_t i = 0; i < n; i++)
-		{
-			idx[i] = i;
-			for (int k = 0; k < 3; k++) cen[(size_t)i * 3 + k] = 0.5f * (L[i].bmin[k] + L[i].bmax[k]);
-		}
-		if (n == 1)
-		{
-			out.root = leafRef(0);
-			return;
-		}
-		out.nodes.reserve((size_t)(n - 1) * 4);
 		unsigned hw = std::thread::hardware_concurrency();
 		int par = 0; // top levels of the recursion that build the two halves concurrently
 		while ((1u << par) < hw && par < 5) par++;
-		if (n < 100000) par = 0;
+		if (n < 16384) par = 0;
+		if (n == 1)
+		{
+			out.root = leafRef(L[0]);
+			return;
+		}
+		// The builder permutes the 32-byte leaf records themselves, not indices into them: a subtree's leaves are
+		// contiguous in memory, so the lower levels (most of the work) run out of the caches.
+		items.resize(n);
+		parallelFor(n >= PAR_MIN ? (1u << par) : 1u, 0, n, [&](unsigned, uint32_t a, uint32_t b) { memcpy(&items[a], &L[a], (size_t)(b - a) * sizeof(RefLeaf)); });
+		// a binary tree over n leaves has n - 1 nodes and the subtree of idx[lo, hi) is laid out in pre-order from a
+		// known base: every thread writes its nodes in place, nothing is spliced afterwards
+		out.nodes.resize((size_t)(n - 1) * 4);
+		if (n >= PAR_MIN) tmp.resize(n);
 		Box b;
 		uint32_t depthSeen = 0;
-		out.root = recurse(out.nodes, 0, n, 0, b, par, depthSeen);
+		out.root = recurse(out.nodes.data(), 0, 0, n, 0, b, par, depthSeen);
 		out.maxDepth = depthSeen;
+		std::vector<RefLeaf>().swap(tmp);
+		std::vector<RefLeaf>().swap(items);
 	}
 
 private:
 	static const int BINS = 32;
 	static const uint32_t MAX_SAH_DEPTH = 40; // deeper than this: median splits (bounded stack on device)
+	// From this many leaves on a node's split is itself computed by several threads (binning per chunk, merged; stable
+	// partition through `tmp`).  The threshold depends on the node only: the tree is the same for any thread count.
+	static const uint32_t PAR_MIN = 1u << 18;
+	static const uint32_t SMALL = 32; // nodes of up to this many leaves: candidates from the sorted leaves, no bin arrays
 	const std::vector<RefLeaf>& L;
-	std::vector<uint32_t> idx;
-	std::vector<float> cen;
+	std::vector<RefLeaf> items, tmp;
 
-	int32_t leafRef(uint32_t prim) const { return ~(int32_t)((L[prim].start << 2) | L[prim].count); }
+	static int32_t leafRef(const RefLeaf& l) { return ~(int32_t)((l.start << 2) | l.count); }
+	static float centroid(const RefLeaf& l, int k) { return 0.5f * (l.bmin[k] + l.bmax[k]); }
+
+	template <class F>
+	static void parallelFor(unsigned threads, uint32_t lo, uint32_t hi, F fn)
+	{
+		if (threads <= 1 || hi - lo < 2 * threads)
+		{
+			fn(0u, lo, hi);
+			return;
+		}
+		std::vector<std::thread> th;
+		uint64_t n = hi - lo;
+		for (unsigned t = 1; t < threads; t++)
+			th.emplace_back([=]() { fn(t, lo + (uint32_t)(n * t / threads), lo + (uint32_t)(n * (t + 1) / threads)); });
+		fn(0u, lo, lo + (uint32_t)(n / threads));
+		for (auto& x : th) x.join();
+	}
 
 	static void writeNode(F4* nd, const Box& b0, const Box& b1, int32_t c0, int32_t c1)
 	{
@@ -180,107 +225,226 @@ private:
 		nd[2] = {b0.mn[2], b0.mx[2], b1.mn[2], b1.mx[2]};
 		nd[3] = {bitsToFloat((uint32_t)c0), bitsToFloat((uint32_t)c1), 0.0f, 0.0f};
 	}
-	static uint32_t floatBits(float f)
-	{
-		uint32_t u;
-		memcpy(&u, &f, 4);
-		return u;
-	}
 
-	// Builds the subtree of idx[lo, hi) into `nodes` (indices relative to that vector); returns the
-	// child reference and the exact box of the subtree (= union of leaf boxes).  With par > 0 the
-	// two halves are built concurrently into private vectors (disjoint slices of idx) and spliced
-	// in afterwards: the tree does not depend on the thread count.
-	int32_t recurse(std::vector<F4>& nodes, uint32_t lo, uint32_t hi, uint32_t depth, Box& box, int par, uint32_t& depthSeen)
+	// Builds the subtree of items[lo, hi) into nodes[base ...] (pre-order: the node, its left subtree, its right
+	// subtree); returns the child reference and the exact box of the subtree (= union of leaf boxes).  With par > 0
+	// the two halves are built concurrently (disjoint slices of items and of the node array).
+	int32_t recurse(F4* nodes, uint32_t base, uint32_t lo, uint32_t hi, uint32_t depth, Box& box, int par, uint32_t& depthSeen)
 	{
 		if (depth > depthSeen) depthSeen = depth;
 		uint32_t n = hi - lo;
 		box.reset();
 		if (n == 1)
 		{
-			box.grow(L[idx[lo]].bmin, L[idx[lo]].bmax);
-			return leafRef(idx[lo]);
+			box.grow(items[lo].bmin, items[lo].bmax);
+			return leafRef(items[lo]);
 		}
-		uint32_t mid = split(lo, hi, depth);
-		size_t self = nodes.size() / 4;
-		nodes.resize(nodes.size() + 4);
+		uint32_t mid = split(lo, hi, depth, par > 0 ? (1u << par) : 1u);
+		const uint32_t self = base, baseL = base + 1, baseR = base + (mid - lo);
 		Box b0, b1;
 		int32_t c0, c1;
-		if (par > 0 && n > 50000)
+		if (par > 0 && n > 8192)
 		{
-			std::vector<F4> left, right;
 			uint32_t dl = 0, dr = 0;
-			std::thread th([&]() { c0 = recurse(left, lo, mid, depth + 1, b0, par - 1, dl); });
-			c1 = recurse(right, mid, hi, depth + 1, b1, par - 1, dr);
+			std::thread th([&]() { c0 = recurse(nodes, baseL, lo, mid, depth + 1, b0, par - 1, dl); });
+			c1 = recurse(nodes, baseR, mid, hi, depth + 1, b1, par - 1, dr);
 			th.join();
 			if (dl > depthSeen) depthSeen = dl;
 			if (dr > depthSeen) depthSeen = dr;
-			auto splice = [&](std::vector<F4>& sub, int32_t& ref) {
-				int32_t off = (int32_t)(nodes.size() / 4);
-				for (size_t i = 0; i < sub.size(); i += 4)
-				{
-					int32_t a = (int32_t)floatBits(sub[i + 3].x), b = (int32_t)floatBits(sub[i + 3].y);
-					if (a >= 0) sub[i + 3].x = bitsToFloat((uint32_t)(a + off));
-					if (b >= 0) sub[i + 3].y = bitsToFloat((uint32_t)(b + off));
-				}
-				if (ref >= 0) ref += off;
-				nodes.insert(nodes.end(), sub.begin(), sub.end());
-				std::vector<F4>().swap(sub);
-			};
-			splice(left, c0);
-			splice(right, c1);
 		}
 		else
 		{
-			c0 = recurse(nodes, lo, mid, depth + 1, b0, 0, depthSeen);
-			c1 = recurse(nodes, mid, hi, depth + 1, b1, 0, depthSeen);
+			c0 = recurse(nodes, baseL, lo, mid, depth + 1, b0, 0, depthSeen);
+			c1 = recurse(nodes, baseR, mid, hi, depth + 1, b1, 0, depthSeen);
 		}
-		writeNode(&nodes[self * 4], b0, b1, c0, c1);
+		writeNode(&nodes[(size_t)self * 4], b0, b1, c0, c1);
 		box.grow(b0);
 		box.grow(b1);
 		return (int32_t)self;
 	}
 
-	uint32_t split(uint32_t lo, uint32_t hi, uint32_t depth)
+	struct Bins
+	{
+		Box bb[3][BINS];
+		uint32_t cnt[3][BINS];
+		void reset()
+		{
+			for (int a = 0; a < 3; a++)
+				for (int b = 0; b < BINS; b++) bb[a][b].reset(), cnt[a][b] = 0;
+		}
+	};
+	static int binOf(float c, float base, float scale)
+	{
+		int b = (int)((c - base) * scale);
+		if (b >= BINS) b = BINS - 1;
+		if (b < 0) b = 0;
+		return b;
+	}
+
+	uint32_t split(uint32_t lo, uint32_t hi, uint32_t depth, unsigned threads)
 	{
 		uint32_t n = hi - lo;
 		if (n == 2) return lo + 1;
+		const bool wide = n >= PAR_MIN; // chunked passes (results do not depend on `threads`)
+		if (!wide) threads = 1;
 		// centroid bounds
 		float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-		for (uint32_t i = lo; i < hi; i++)
+		if (threads <= 1)
 		{
-			const float* c = &cen[(size_t)idx[i] * 3];
-			for (int k = 0; k < 3; k++)
-			{
-				if (c[k] < cmn[k]) cmn[k] = c[k];
-				if (c[k] > cmx[k]) cmx[k] = c[k];
-			}
+			for (uint32_t i = lo; i < hi; i++)
+				for (int k = 0; k < 3; k++)
+				{
+					float c = centroid(items[i], k);
+					if (c < cmn[k]) cmn[k] = c;
+					if (c > cmx[k]) cmx[k] = c;
+				}
+		}
+		else
+		{
+			std::vector<Box> part(threads);
+			parallelFor(threads, lo, hi, [&](unsigned t, uint32_t a, uint32_t b) {
+				Box bx;
+				bx.reset();
+				for (uint32_t i = a; i < b; i++)
+				{
+					const float c[3] = {centroid(items[i], 0), centroid(items[i], 1), centroid(items[i], 2)};
+					bx.grow(c, c);
+				}
+				part[t] = bx;
+			});
+			for (unsigned t = 0; t < threads; t++)
+				for (int k = 0; k < 3; k++)
+				{
+					if (part[t].mn[k] < cmn[k]) cmn[k] = part[t].mn[k];
+					if (part[t].mx[k] > cmx[k]) cmx[k] = part[t].mx[k];
+				}
 		}
 		int bestAxis = -1, bestBin = -1;
 		float bestCost = FLT_MAX;
-		if (depth < MAX_SAH_DEPTH)
+		if (depth < MAX_SAH_DEPTH && n <= SMALL)
 		{
+			// Half of all nodes hold a handful of leaves: resetting and sweeping 3 x 32 bins for them is most of the
+			// build.  Same candidates, same costs, same order of evaluation from the leaves sorted by bin: a split
+			// after an empty bin costs what the split after the previous occupied bin costs and never wins (strict <).
 			for (int ax = 0; ax < 3; ax++)
 			{
 				float ext = cmx[ax] - cmn[ax];
 				if (!(ext > 0.0f)) continue;
 				float scale = (float)BINS / ext;
-				Box bb[BINS];
-				uint32_t cnt[BINS];
-				for (int b = 0; b < BINS; b++)
+				uint8_t bin[SMALL], ord[SMALL];
+				for (uint32_t i = 0; i < n; i++)
 				{
-					bb[b].reset();
-					cnt[b] = 0;
+					bin[i] = (uint8_t)binOf(centroid(items[lo + i], ax), cmn[ax], scale);
+					uint32_t j = i;
+					while (j > 0 && bin[ord[j - 1]] > bin[i]) ord[j] = ord[j - 1], j--;
+					ord[j] = (uint8_t)i;
 				}
-				for (uint32_t i = lo; i < hi; i++)
+				float rightArea[SMALL];
+				uint32_t rightCnt[SMALL];
+				Box acc;
+				acc.reset();
+				uint32_t c = 0;
+				for (uint32_t k = n; k-- > 1;)
 				{
-					uint32_t p = idx[i];
-					int b = (int)((cen[(size_t)p * 3 + ax] - cmn[ax]) * scale);
-					if (b >= BINS) b = BINS - 1;
-					if (b < 0) b = 0;
-					bb[b].grow(L[p].bmin, L[p].bmax);
-					cnt[b] += L[p].count; // cost weight: triangles in the leaf
+					const RefLeaf& lf = items[lo + ord[k]];
+					acc.grow(lf.bmin, lf.bmax);
+					c += lf.count;
+					rightArea[k] = acc.area();
+					rightCnt[k] = c;
 				}
+				acc.reset();
+				c = 0;
+				for (uint32_t k = 0; k + 1 < n; k++)
+				{
+					const RefLeaf& lf = items[lo + ord[k]];
+					acc.grow(lf.bmin, lf.bmax);
+					c += lf.count;
+					int b = bin[ord[k]];
+					if (b == bin[ord[k + 1]] || b >= BINS - 1) continue; // not the last leaf of its bin / no split after the last bin
+					if (c == 0 || rightCnt[k + 1] == 0) continue;
+					float cost = acc.area() * (float)c + rightArea[k + 1] * (float)rightCnt[k + 1];
+					if (cost < bestCost)
+					{
+						bestCost = cost;
+						bestAxis = ax;
+						bestBin = b;
+					}
+				}
+			}
+		}
+		else if (depth < MAX_SAH_DEPTH)
+		{
+			// one pass bins all three axes (each leaf record is fetched once)
+			float scale[3];
+			bool use[3];
+			for (int ax = 0; ax < 3; ax++)
+			{
+				float ext = cmx[ax] - cmn[ax];
+				use[ax] = ext > 0.0f;
+				scale[ax] = use[ax] ? (float)BINS / ext : 0.0f;
+			}
+			Bins one; // the common case (one thread) stays off the heap
+			std::vector<Bins> more(threads > 1 ? threads : 0);
+			Bins* part = threads > 1 ? more.data() : &one;
+			parallelFor(threads, lo, hi, [&](unsigned t, uint32_t a, uint32_t b) {
+				Bins& B = part[t];
+				B.reset();
+#if defined(__SSE2__)
+				// same arithmetic four lanes at a time (min/max operand order = the scalar selects'; lane 3 is ignored)
+				__m128 lo4[3][BINS], hi4[3][BINS];
+				for (int ax = 0; ax < 3; ax++)
+					for (int k = 0; k < BINS; k++) lo4[ax][k] = _mm_set1_ps(FLT_MAX), hi4[ax][k] = _mm_set1_ps(-FLT_MAX);
+				const __m128 base = _mm_setr_ps(cmn[0], cmn[1], cmn[2], 0.0f), sc = _mm_setr_ps(scale[0], scale[1], scale[2], 0.0f);
+				const __m128 half = _mm_set1_ps(0.5f);
+				for (uint32_t i = a; i < b; i++)
+				{
+					const RefLeaf& lf = items[i];
+					const __m128 mn = _mm_loadu_ps(lf.bmin);                                  // bmin.xyz, bmax.x
+					const __m128 mx = _mm_loadu_ps(lf.bmax);                                  // bmax.xyz, start
+					const __m128 cen = _mm_mul_ps(half, _mm_add_ps(mn, mx));
+					alignas(16) int bin[4];
+					_mm_store_si128((__m128i*)bin, _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(cen, base), sc)));
+					for (int ax = 0; ax < 3; ax++)
+					{
+						if (!use[ax]) continue;
+						int k = bin[ax];
+						if (k >= BINS) k = BINS - 1;
+						if (k < 0) k = 0;
+						lo4[ax][k] = _mm_min_ps(mn, lo4[ax][k]);
+						hi4[ax][k] = _mm_max_ps(mx, hi4[ax][k]);
+						B.cnt[ax][k] += lf.count;
+					}
+				}
+				for (int ax = 0; ax < 3; ax++)
+					for (int k = 0; k < BINS; k++)
+					{
+						alignas(16) float l[4], h[4];
+						_mm_store_ps(l, lo4[ax][k]), _mm_store_ps(h, hi4[ax][k]);
+						for (int c = 0; c < 3; c++) B.bb[ax][k].mn[c] = l[c], B.bb[ax][k].mx[c] = h[c];
+					}
+#else
+				for (uint32_t i = a; i < b; i++)
+				{
+					const RefLeaf& lf = items[i];
+					for (int ax = 0; ax < 3; ax++)
+					{
+						if (!use[ax]) continue;
+						int bin = binOf(centroid(lf, ax), cmn[ax], scale[ax]);
+						B.bb[ax][bin].grow(lf.bmin, lf.bmax);
+						B.cnt[ax][bin] += lf.count; // cost weight: triangles in the leaf
+					}
+				}
+#endif
+			});
+			Bins& B = part[0];
+			for (unsigned t = 1; t < threads; t++)
+				for (int ax = 0; ax < 3; ax++)
+					for (int b = 0; b < BINS; b++) B.bb[ax][b].grow(part[t].bb[ax][b]), B.cnt[ax][b] += part[t].cnt[ax][b];
+			for (int ax = 0; ax < 3; ax++)
+			{
+				if (!use[ax]) continue;
+				const Box* bb = B.bb[ax];
+				const uint32_t* cnt = B.cnt[ax];
 				float rightArea[BINS];
 				uint32_t rightCnt[BINS];
 				Box acc;
@@ -316,15 +480,35 @@ private:
 			float scale = (float)BINS / ext;
 			float base = cmn[bestAxis];
 			int ax = bestAxis, bin = bestBin;
-			uint32_t* first = &idx[lo];
-			uint32_t* last = &idx[hi];
-			uint32_t* m = std::partition(first, last, [&](uint32_t p) {
-				int b = (int)((cen[(size_t)p * 3 + ax] - base) * scale);
-				if (b >= BINS) b = BINS - 1;
-				if (b < 0) b = 0;
-				return b <= bin;
-			});
-			uint32_t mid = (uint32_t)(m - &idx[0]);
+			auto goesLeft = [&](const RefLeaf& l) { return binOf(centroid(l, ax), base, scale) <= bin; };
+			uint32_t mid;
+			if (wide)
+			{
+				// stable partition through `tmp`: per-chunk counts, then every chunk scatters to its own offsets
+				std::vector<uint32_t> nl(threads + 1, 0);
+				parallelFor(threads, lo, hi, [&](unsigned t, uint32_t a, uint32_t b) {
+					uint32_t c = 0;
+					for (uint32_t i = a; i < b; i++) c += goesLeft(items[i]) ? 1u : 0u;
+					nl[t + 1] = c;
+				});
+				for (unsigned t = 0; t < threads; t++) nl[t + 1] += nl[t];
+				mid = lo + nl[threads];
+				parallelFor(threads, lo, hi, [&](unsigned t, uint32_t a, uint32_t b) {
+					uint32_t l = lo + nl[t], r = mid + (a - lo) - nl[t];
+					for (uint32_t i = a; i < b; i++)
+					{
+						const RefLeaf& p = items[i];
+						if (goesLeft(p)) tmp[l++] = p;
+						else tmp[r++] = p;
+					}
+				});
+				parallelFor(threads, lo, hi, [&](unsigned, uint32_t a, uint32_t b) { memcpy(&items[a], &tmp[a], (size_t)(b - a) * sizeof(RefLeaf)); });
+			}
+			else
+			{
+				RefLeaf* m = std::partition(&items[lo], &items[0] + hi, goesLeft);
+				mid = (uint32_t)(m - &items[0]);
+			}
 			if (mid > lo && mid < hi) return mid;
 		}
 		// fallback: median split along the widest centroid axis (or by index if all equal)
@@ -333,9 +517,9 @@ private:
 		if (e1 > e0 && e1 >= e2) ax = 1;
 		else if (e2 > e0 && e2 > e1) ax = 2;
 		uint32_t mid = lo + n / 2;
-		std::nth_element(&idx[lo], &idx[mid], &idx[0] + hi, [&](uint32_t a, uint32_t b) {
-			float ca = cen[(size_t)a * 3 + ax], cb = cen[(size_t)b * 3 + ax];
-			return ca < cb || (ca == cb && a < b);
+		std::nth_element(&items[lo], &items[mid], &items[0] + hi, [&](const RefLeaf& a, const RefLeaf& b) {
+			float ca = centroid(a, ax), cb = centroid(b, ax);
+			return ca < cb || (ca == cb && a.start < b.start); // leaves come in ascending triangle order
 		});
 		return mid;
 	}

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <dlfcn.h>
+#include <chrono>
 #include <map>
 #include <new>
 #include <string>
@@ -1145,16 +1146,56 @@ static int gatherAccum(rtb_ctx* g)
 	return RTB_OK;
 }
 
+// RTB_UPLOAD_TIMING=1: rtb_upload_scene prints where its time goes (stderr), one line per stage
+struct UploadClock
+{
+	bool on;
+	std::chrono::steady_clock::time_point t;
+	UploadClock() : on(getenv("RTB_UPLOAD_TIMING") && atoi(getenv("RTB_UPLOAD_TIMING")) != 0), t(std::chrono::steady_clock::now()) {}
+	void lap(const char* what)
+	{
+		if (!on) return;
+		auto n = std::chrono::steady_clock::now();
+		fprintf(stderr, "[rtb upload] %-48s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+		t = n;
+	}
+};
+
+// rtb_upload_scene's device-side re-encodings (the host hands over the caller's arrays untouched):
+// EXACT tree node pair [bmin, a][bmax, b] -> [bmin, skip link][bmax, leaf code] (rtb_accel::exactNodePair)
+__global__ void k_exact_nodes(float4* nodes, const uint32_t* __restrict__ skip, uint32_t n)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int32_t a = __float_as_int(nodes[2 * (size_t)i].w), b = __float_as_int(nodes[2 * (size_t)i + 1].w);
+	uint32_t leaf = 0xFFFFFFFFu;
+	if (a < 0) leaf = ((uint32_t)(~a) << 2) | (uint32_t)b;
+	nodes[2 * (size_t)i].w = __uint_as_float(skip[i]);
+	nodes[2 * (size_t)i + 1].w = __uint_as_float(leaf);
+}
+// rtb_tri_isect [v0,d][v1,1/A][v2,material][n,A] -> [n,d][v0,1/A][v1,material][v2,A]: the plane test reads one
+// 16-byte row, the edge tests the other three
+__global__ void k_pack_tris(float4* tris, uint32_t n)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4* t = tris + 4 * (size_t)i;
+	const float4 r0 = t[0], r1 = t[1], r2 = t[2], r3 = t[3];
+	t[0] = make_float4(r3.x, r3.y, r3.z, r0.w);
+	t[1] = make_float4(r0.x, r0.y, r0.z, r1.w);
+	t[2] = make_float4(r1.x, r1.y, r1.z, r2.w);
+	t[3] = make_float4(r2.x, r2.y, r2.z, r3.w);
+}
+
 // Host side of rtb_upload_scene: validate the description and build everything derived from it (skip links, the
 // accelerated trees, the env sampling tables) ONCE; a device group uploads the same prepared scene to every member.
 struct PreparedScene
 {
 	const rtb_scene_desc* sc = nullptr;
-	std::vector<rtb_accel::F4> xnodes;
+	std::vector<uint32_t> skip;              // EXACT tree: first node after each node's subtree (k_exact_nodes)
 	rtb_accel::FastTree fast;
 	bool gpuBuild = false;                   // the FAST tree is built on each device from `leaves` (rtb_gpu_build.cuh)
 	std::vector<rtb_accel::RefLeaf> leaves;
-	std::vector<rtb_accel::F4> triPacked; // device triangle records (layout: triTest, rtb_dev_scene.cuh)
 	std::vector<float> marginal, cond;
 	int envW = 0, envH = 0;
 };
@@ -1195,10 +1236,11 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		return fail(ctx, RTB_ERR_ARG, "background env texture out of range");
 
 	// host-side acceleration data
-	std::vector<rtb_accel::F4>& xnodes = ps.xnodes;
 	std::vector<rtb_accel::RefLeaf>& leaves = ps.leaves;
 	const char* err = nullptr;
-	if (!rtb_accel::buildExact(sc->ref_nodes, sc->n_ref_nodes, sc->n_tris, xnodes, leaves, &err)) return fail(ctx, RTB_ERR_ARG, "%s", err);
+	UploadClock clk;
+	if (!rtb_accel::buildSkipLinks(sc->ref_nodes, sc->n_ref_nodes, sc->n_tris, ps.skip, leaves, &err)) return fail(ctx, RTB_ERR_ARG, "%s", err);
+	clk.lap("skip links + leaves");
 	rtb_accel::FastTree& fast = ps.fast;
 	// The tree can be built on the device instead (a linear BVH over the same leaves: four kernels and a sort, where the
 	// host's binned-SAH recursion takes seconds on the largest soups).
@@ -1217,17 +1259,7 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
 	}
-	// triangle records re-packed so that the plane test reads one 32-byte half and the edge tests the other
-	ps.triPacked.resize((size_t)sc->n_tris * 4);
-	for (uint32_t i = 0; i < sc->n_tris; i++)
-	{
-		const rtb_tri_isect& q = sc->tri_isect[i];
-		rtb_accel::F4* o = &ps.triPacked[(size_t)i * 4];
-		o[0] = {q.n[0], q.n[1], q.n[2], q.d};
-		o[1] = {q.v0[0], q.v0[1], q.v0[2], q.inv_area};
-		o[2] = {q.v1[0], q.v1[1], q.v1[2], rtb_accel::bitsToFloat(q.material)};
-		o[3] = {q.v2[0], q.v2[1], q.v2[2], q.area};
-	}
+	clk.lap(ps.gpuBuild ? "(tree built on the device)" : "binned-SAH tree");
 	// stack need: one pending sibling per level.  (The WIDE / CW / Q16 re-encodings of this tree are built on first use,
 	// ensureTraversal: the upload of a 16 M-triangle scene should not pay for trees nobody selected.)
 	if (!ps.gpuBuild && fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u levels)", fast.maxDepth);
@@ -1249,8 +1281,8 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 {
 	const rtb_scene_desc* sc = ps.sc;
-	const std::vector<rtb_accel::F4>& xnodes = ps.xnodes;
 	const rtb_accel::FastTree& fast = ps.fast;
+	UploadClock clk;
 	if (int rc = bind(ctx)) return rc;
 	CK(cudaStreamSynchronize(ctx->stream));
 	freeScene(ctx);
@@ -1260,7 +1292,23 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	int rc;
 	const rtb_accel::F4* dx = nullptr;
 	const rtb_accel::F4* df = nullptr;
-	if ((rc = uploadArray(ctx, xnodes.data(), xnodes.size(), &dx))) return rc;
+	// EXACT tree: the reference nodes go up as they are; the device swaps the child words for (skip link, leaf code)
+	{
+		const rtb_ref_node* dn = nullptr;
+		const uint32_t* dskip = nullptr;
+		if ((rc = uploadArray(ctx, sc->ref_nodes, sc->n_ref_nodes, &dn))) return rc;
+		if (sc->n_ref_nodes)
+		{
+			CK(cudaMalloc((void**)&dskip, (size_t)sc->n_ref_nodes * sizeof(uint32_t)));
+			CK(cudaMemcpyAsync((void*)dskip, ps.skip.data(), (size_t)sc->n_ref_nodes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			k_exact_nodes<<<(sc->n_ref_nodes + 255) / 256, 256, 0, ctx->stream>>>((float4*)dn, dskip, sc->n_ref_nodes);
+			CK(cudaGetLastError());
+			CK(cudaStreamSynchronize(ctx->stream));
+			CK(cudaFree((void*)dskip));
+		}
+		dx = (const rtb_accel::F4*)dn;
+	}
+	clk.lap("reference nodes -> device");
 	uint32_t fastDepth = fast.maxDepth;
 	bool built = false;
 	if (ps.gpuBuild)
@@ -1305,7 +1353,18 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	ctx->cwBlocksPerSM[0] = ctx->cwBlocksPerSM[1] = 0; // staging is sized per scene
 	const rtb_accel::F4* dti = nullptr;
 	const rtb_tri_shade* dts = nullptr;
-	if ((rc = uploadArray(ctx, ps.triPacked.data(), ps.triPacked.size(), &dti))) return rc;
+	clk.lap("accelerated tree -> device");
+	// triangle records: copied as they are, re-packed in place on the device (layout: triTest, rtb_dev_scene.cuh)
+	{
+		const rtb_tri_isect* draw = nullptr;
+		if ((rc = uploadArray(ctx, sc->tri_isect, sc->n_tris, &draw))) return rc;
+		if (sc->n_tris)
+		{
+			k_pack_tris<<<(sc->n_tris + 255) / 256, 256, 0, ctx->stream>>>((float4*)draw, sc->n_tris);
+			CK(cudaGetLastError());
+		}
+		dti = (const rtb_accel::F4*)draw;
+	}
 	if ((rc = uploadArray(ctx, sc->tri_shade, sc->n_tris, &dts))) return rc;
 	S.tri = (const float4*)dti;
 	S.tsh = (const float4*)dts;
@@ -1353,6 +1412,7 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	ctx->renderMs = 0.0;
 	// the host vectors above die at return: finish the async copies first
 	CK(cudaStreamSynchronize(ctx->stream));
+	clk.lap("triangles, materials, textures, film -> device");
 	ctx->haveScene = true;
 	ctx->accumDirty = false;
 	ctx->iterHint.clear(); // iteration counts remembered for the previous scene

@@ -34,6 +34,12 @@
 #ifndef WF_VOTE
 #define WF_VOTE 1
 #endif
+// k_wf_shade can fetch the next round's slot state ahead: 0 off (default), 1 prefetch.global.L2, 2 cp.async into shared memory.
+// Measured (profiles/r02_shade_prefetch.txt): no gain in either form - with the stages of two sub-pools overlapping, a
+// stalled shade warp is covered by the other kernels; the whole step is bound by issued instructions, not by latency.
+#ifndef WF_SHADE_PREFETCH
+#define WF_SHADE_PREFETCH 0
+#endif
 #ifndef WF_SHADE_MIN_BLOCKS
 #define WF_SHADE_MIN_BLOCKS 6
 #endif
@@ -1021,6 +1027,22 @@ __global__ void __launch_bounds__(128) k_wf_mis(const __grid_constant__ DevScene
 	flushTally(tl, A.counters);
 }
 
+// k_wf_shade's software prefetch of one slot's state (rayD, rayO, hit, thr: 4 x 16 bytes) into the thread's staging row
+__device__ __forceinline__ void shadePrefetchSlot(const WfArgs& A, uint32_t slot, float4 (*row)[128])
+{
+	if (slot < A.nSlots)
+	{
+		const float4* src[4] = {A.rayD + slot, A.rayO + slot, A.hit + slot, A.thr + slot};
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			uint32_t dst = (uint32_t)__cvta_generic_to_shared(&row[k][threadIdx.x]);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[k]) : "memory");
+		}
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int INTEGRATOR, bool REUSE>
 __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
@@ -1039,6 +1061,15 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 #if WF_SHADE_REGROUP
 	__shared__ uint8_t sPerm[128];
 	__shared__ uint32_t sClsCnt[2][4];
+#endif
+#if WF_SHADE_PREFETCH
+	// Most slots hold a live vertex in the steady state: fetch the NEXT round's slot state while this round is shaded.
+	// Near the drain (few live slots) the plain path reads 16 bytes per dead slot instead of 64.
+	const bool pre = iter > 0 && A.ctrl[iter - 1].alive > (A.nSlots >> 1);
+#endif
+#if WF_SHADE_PREFETCH == 2
+	__shared__ float4 sPre[2][4][128];
+	if (pre) shadePrefetchSlot(A, blockIdx.x * blockDim.x + threadIdx.x, sPre[0]);
 #endif
 	for (uint32_t round = 0; round < nRounds; round++)
 	{
@@ -1075,8 +1106,40 @@ __global__ void __launch_bounds__(128, WF_SHADE_MIN_BLOCKS) k_wf_shade(const __g
 		bool haveVertex = false, slotLive = false;
 		uint32_t queued = 0;
 		float4 ro, rd, hh, tq;
+#if WF_SHADE_PREFETCH == 2
+		if (pre)
+		{
+			// the slot's 64 bytes of state were requested one round ago (cp.async into the block's staging rows): the
+			// round starts on shared-memory latency instead of HBM latency, at no register cost
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			if (inRange)
+			{
+				rd = sPre[round & 1u][0][threadIdx.x];
+				if (__float_as_uint(rd.w) & WF_ALIVE)
+				{
+					ro = sPre[round & 1u][1][threadIdx.x], hh = sPre[round & 1u][2][threadIdx.x], tq = sPre[round & 1u][3][threadIdx.x];
+					haveVertex = true;
+				}
+			}
+			shadePrefetchSlot(A, slot + gridDim.x * blockDim.x, sPre[(round + 1u) & 1u]);
+		}
+		else
+#endif
 		if (inRange)
 		{
+#if WF_SHADE_PREFETCH == 1
+			if (pre)
+			{
+				const uint32_t nx = slot + gridDim.x * blockDim.x;
+				if (nx < A.nSlots)
+				{
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(A.rayD + nx));
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(A.rayO + nx));
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(A.hit + nx));
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(A.thr + nx));
+				}
+			}
+#endif
 			rd = A.rayD[slot];
 			if (__float_as_uint(rd.w) & WF_ALIVE)
 			{

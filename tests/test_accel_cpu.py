@@ -56,9 +56,11 @@ def test_trees_of_the_bundled_scenes(checker, name):
     assert st["cw_nodes"] < 0.45 * st["fast_nodes"]      # eight-wide: far fewer nodes than the binary tree
 
 
-def test_soup_trees(checker):
+@pytest.mark.parametrize("log2n", [15, 19])
+def test_soup_trees(checker, log2n):
+    """2^19 triangles (> 2^18 leaves) takes the builder's multi-threaded split path (chunked binning, stable partition)."""
     from raytracingrenderer_b200 import host_api
-    s, _ = host_api.build_soup(1 << 15, 64, 36)
+    s, _ = host_api.build_soup(1 << log2n, 64, 36)
     st = run(checker, s)
     assert st["cw_leaves"] == st["fast_nodes"] + 1
 
@@ -71,3 +73,45 @@ def test_a_broken_tree_is_noticed(checker):
     nodes["b"][leaf] = 7
     stats = np.zeros(9, np.float64)
     assert checker.accel_check(nodes.ctypes.data, len(nodes), s.n_tris, stats.ctypes.data) < 0
+
+
+def test_skip_links_equal_the_subtree_ends_and_malformed_trees_are_rejected(checker):
+    """rtb_accel::buildSkipLinks (one forward pass) against the definition: skip[i] = i + size of i's subtree, computed here
+    by recursion over the (a, b) child links; node arrays that are not one pre-order tree are errors, not walks."""
+    import sys
+    s = synthetic_scene(seed=5, n_tris=900)
+    nodes = np.ascontiguousarray(s.ref_nodes, abi.ref_node_dt).copy()
+    n = len(nodes)
+    want = np.zeros(n, np.uint32)
+    sys.setrecursionlimit(10000)
+
+    def size(i):
+        if nodes["a"][i] < 0:
+            want[i] = i + 1
+            return 1
+        k = 1 + size(int(nodes["a"][i])) + size(int(nodes["b"][i]))
+        want[i] = i + k
+        return k
+
+    assert size(0) == n
+    checker.accel_skip_links.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    got = np.zeros(n, np.uint32)
+    n_leaves = checker.accel_skip_links(nodes.ctypes.data, n, s.n_tris, got.ctypes.data)
+    assert n_leaves == int(((nodes["a"] < 0) & (nodes["b"] > 0)).sum())
+    assert np.array_equal(got, want)
+    interior = np.flatnonzero(nodes["a"] >= 0)
+    for what in ("b_points_back", "b_beyond_subtree", "a_not_next", "orphan_tail", "leaf_where_a_subtree_was"):
+        bad = nodes.copy()
+        i = int(interior[len(interior) // 2])
+        if what == "b_points_back":
+            bad["b"][i] = i
+        elif what == "b_beyond_subtree":
+            bad["b"][i] = want[i]
+        elif what == "a_not_next":
+            bad["a"][i] = i + 2
+        elif what == "orphan_tail":
+            bad = np.concatenate([bad, bad[-1:]])
+        else:
+            bad["a"][i], bad["b"][i] = -1, 1          # an interior node turned into a leaf: its old subtree has no parent
+        assert checker.accel_skip_links(bad.ctypes.data, len(bad), s.n_tris, np.zeros(len(bad), np.uint32).ctypes.data) < 0, what
+        assert b"pre-order" in checker.accel_check_message()

@@ -245,3 +245,16 @@ extern "C" int accel_check(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris
 	}
 	return 0;
 }
+
+// skip links of the EXACT traversal: out[i] = first node index after i's subtree (buildSkipLinks' one forward pass);
+// returns the number of leaves, or -1 with the builder's message if the node array is rejected
+extern "C" int accel_skip_links(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris, uint32_t* out)
+{
+	g_msg.clear();
+	std::vector<uint32_t> skip;
+	std::vector<RefLeaf> leaves;
+	const char* err = nullptr;
+	if (!buildSkipLinks(nodes, n, nTris, skip, leaves, &err)) return failf(-1, err);
+	for (uint32_t i = 0; i < n; i++) out[i] = skip[i];
+	return (int)leaves.size();
+}
