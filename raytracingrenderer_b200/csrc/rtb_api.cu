@@ -1245,9 +1245,9 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 	// The tree can be built on the device instead (a linear BVH over the same leaves: four kernels and a sort, where the
 	// host's binned-SAH recursion takes seconds on the largest soups).
 	{
-		// Opt-in (profiles/r02_gpu_builder.txt): the linear BVH is built in milliseconds (16 M triangles: upload 4.2 -> 2.2 s, the
-		// rest is host preparation + copies) but costs 8 % (soups) ... 25 % (coffee) of the render rate against the SAH
-		// tree, and the metric is the render rate.  RTB_GPU_BUILD=1, or RTB_GPU_BUILD_MIN_LEAVES=n for "from n leaves on".
+		// Opt-in (profiles/r02_gpu_builder.txt): the linear BVH is built in milliseconds (the host SAH tree of 16 M triangles
+		// takes 0.9 s of a 1.6 s upload, profiles/r02_upload_timing.txt) but costs 8 % (soups) ... 25 % (coffee) of the
+		// render rate, and the metric is the render rate.  RTB_GPU_BUILD=1, or RTB_GPU_BUILD_MIN_LEAVES=n for "from n leaves on".
 		size_t minLeaves = (size_t)-1;
 		if (const char* e = getenv("RTB_GPU_BUILD_MIN_LEAVES")) minLeaves = (size_t)atoll(e);
 		ps.gpuBuild = leaves.size() >= minLeaves;
