@@ -1187,6 +1187,12 @@ __global__ void k_pack_tris(float4* tris, uint32_t n)
 	t[3] = make_float4(r2.x, r2.y, r2.z, r3.w);
 }
 
+__global__ void k_pad_texels(const float* __restrict__ rgb, float4* out, size_t n)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = make_float4(rgb[3 * (size_t)i], rgb[3 * (size_t)i + 1], rgb[3 * (size_t)i + 2], 0.0f);
+}
+
 // Host side of rtb_upload_scene: validate the description and build everything derived from it (skip links, the
 // accelerated trees, the env sampling tables) ONCE; a device group uploads the same prepared scene to every member.
 struct PreparedScene
@@ -1219,6 +1225,8 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		if (m.type > RTB_BSDF_PLASTIC) return fail(ctx, RTB_ERR_ARG, "material %u: unknown bsdf type %u", i, m.type);
 		if (m.tex < 0 || (uint32_t)m.tex >= sc->n_textures) return fail(ctx, RTB_ERR_ARG, "material %u: texture %d out of range", i, m.tex);
 	}
+	if (sc->n_texels && !sc->texels) return fail(ctx, RTB_ERR_ARG, "texels missing");
+	if (sc->n_texels > (1ull << 36)) return fail(ctx, RTB_ERR_ARG, "texel pool too large");
 	for (uint32_t i = 0; i < sc->n_textures; i++)
 	{
 		const rtb_texture& t = sc->textures[i];
@@ -1371,7 +1379,30 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	S.n_tris = sc->n_tris;
 	if ((rc = uploadArray(ctx, sc->materials, sc->n_materials, &S.mats))) return rc;
 	if ((rc = uploadArray(ctx, sc->textures, sc->n_textures, &S.texs))) return rc;
-	if ((rc = uploadArray(ctx, sc->texels, (size_t)sc->n_texels * 3, &S.texels))) return rc;
+	if (sc->n_texels)
+	{
+		// texels: 12-byte RGB from the caller, 16-byte records on the device
+		float* raw = nullptr;
+		void* padded = nullptr;
+		CK(cudaMalloc((void**)&raw, (size_t)sc->n_texels * 3 * sizeof(float)));
+		cudaError_t e = cudaMalloc(&padded, (size_t)sc->n_texels * sizeof(float4));
+		if (e != cudaSuccess)
+		{
+			cudaFree(raw);
+			CK(e);
+		}
+		ctx->sceneAllocs.push_back(padded);
+		e = cudaMemcpyAsync(raw, sc->texels, (size_t)sc->n_texels * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+		if (e == cudaSuccess)
+		{
+			k_pad_texels<<<(unsigned)(((size_t)sc->n_texels + 255) / 256), 256, 0, ctx->stream>>>(raw, (float4*)padded, (size_t)sc->n_texels);
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		cudaFree(raw);
+		CK(e);
+		S.texels = (const float4*)padded;
+	}
 	if ((rc = uploadArray(ctx, sc->lights, sc->n_lights, &S.lights))) return rc;
 	S.n_mats = sc->n_materials, S.n_texs = sc->n_textures, S.n_lights = sc->n_lights;
 	S.bg_type = sc->background_type;
