@@ -32,6 +32,29 @@ for name, spp in (("cornell-box", 96), ("materialball", 48), ("materialball_glas
     check("%s EXACT == FAST" % name, np.array_equal(a, base))
     a, _ = render(rt, spp, traversal=abi.TRAV_WIDE)
     check("%s WIDE == FAST" % name, np.array_equal(a, base))
+    for trav, tn in ((abi.TRAV_CW, "CW"), (abi.TRAV_Q16, "Q16")):
+        a, _ = render(rt, spp, traversal=trav)
+        check("%s %s == FAST" % (name, tn), np.array_equal(a, base))
+    # round 2: the same configuration again and again takes the asynchronous rtb_render path (remembered iteration
+    # count); a different spp in between must not disturb it
+    ok = True
+    for k in range(4):
+        a, st = render(rt, spp, primary_reuse=0)
+        ok = ok and np.array_equal(a, base) and st["samples"] == st0["samples"]
+        if k == 1:
+            render(rt, max(1, spp // 3), primary_reuse=0)
+    check("%s repeated renders (async path) bit-identical" % name, ok)
+    # round 2: environment-selected kernels and builders give the same film
+    for env in (dict(RTB_SHADOW_PERSISTENT="1"), dict(RTB_SHADOW_PERSISTENT="0", RTB_CHUNK="32"), dict(RTB_GPU_BUILD="1"),
+                dict(RTB_SORT_SHADOW="1"), dict(RTB_ASYNC_RENDER="0"), dict(RTB_POOLS="1", RTB_SHADOW_ASYNC="0")):
+        os.environ.update(env)
+        r2 = rtb.RayTracer([0])          # a device group of one
+        r2.init(flat)
+        a, st = render(r2, spp, primary_reuse=0)
+        r2.close()
+        for k in env:
+            del os.environ[k]
+        check("%s %s == default" % (name, " ".join("%s=%s" % kv for kv in env.items())), np.array_equal(a, base) and st["samples"] == st0["samples"])
     # spp slices and tile slices of 3 ranks compose to the single-rank film (integer film sums)
     acc = np.zeros_like(base, dtype=np.float64)
     parts = [render(rt, spp, partition=abi.PART_TILE, part_rank=r, part_world=3)[0] for r in range(3)]
