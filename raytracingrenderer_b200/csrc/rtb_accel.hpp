@@ -527,6 +527,230 @@ private:
 
 
 // ---------------------------------------------------------------------------------------
+// Insertion-based optimisation of the FAST tree (after Bittner, Hapala, Havran: "Fast Insertion-Based Optimization of
+// Bounding Volume Hierarchies", 2013).  One pass visits the interior nodes by decreasing surface area; a node is taken
+// out together with its parent, and its two subtrees are re-inserted where they increase the summed surface area of the
+// tree least (branch-and-bound search from the root).  Leaves, their exact boxes and the rule "a node's box is the exact
+// union of its children's" are untouched, so the tree stays legal for hit-ID parity; only the topology above
+// the leaves changes.  Opt-in (RTB_TREE_OPT=<passes>): profiles/r02_tree_opt.txt.
+// ---------------------------------------------------------------------------------------
+class FastOptimizer
+{
+public:
+	struct ONode
+	{
+		float mn[3], mx[3];
+		int32_t parent, c[2]; // c[0] < 0: a leaf (leafRef holds the reference)
+		int32_t leafRef;
+		float area;
+	};
+	std::vector<ONode> N;
+	int32_t root = -1;
+	uint32_t nInterior = 0;
+
+	static float areaOf(const float* mn, const float* mx)
+	{
+		float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+		return 2.0f * (dx * dy + dy * dz + dz * dx);
+	}
+	static uint32_t bits(float f)
+	{
+		uint32_t u;
+		memcpy(&u, &f, 4);
+		return u;
+	}
+	void load(const FastTree& T)
+	{
+		nInterior = (uint32_t)(T.nodes.size() / 4);
+		N.assign((size_t)nInterior * 2 + 1, ONode());
+		uint32_t nextLeaf = nInterior;
+		for (uint32_t i = 0; i < nInterior; i++)
+		{
+			const F4* nd = &T.nodes[(size_t)i * 4];
+			int32_t ch[2] = {(int32_t)bits(nd[3].x), (int32_t)bits(nd[3].y)};
+			float cmn[2][3] = {{nd[0].x, nd[0].z, nd[2].x}, {nd[1].x, nd[1].z, nd[2].z}};
+			float cmx[2][3] = {{nd[0].y, nd[0].w, nd[2].y}, {nd[1].y, nd[1].w, nd[2].w}};
+			for (int k = 0; k < 2; k++)
+			{
+				int32_t id = ch[k] >= 0 ? ch[k] : (int32_t)nextLeaf++;
+				ONode& c = N[id];
+				memcpy(c.mn, cmn[k], 12), memcpy(c.mx, cmx[k], 12);
+				c.area = areaOf(c.mn, c.mx);
+				c.parent = (int32_t)i;
+				if (ch[k] < 0) c.c[0] = c.c[1] = -1, c.leafRef = ch[k];
+				N[i].c[k] = id;
+			}
+		}
+		root = T.root;
+		N[root].parent = -1;
+		refitOne(root);
+	}
+	void refitOne(int32_t i)
+	{
+		ONode& n = N[i];
+		const ONode &a = N[n.c[0]], &b = N[n.c[1]];
+		for (int k = 0; k < 3; k++) n.mn[k] = a.mn[k] < b.mn[k] ? a.mn[k] : b.mn[k], n.mx[k] = a.mx[k] > b.mx[k] ? a.mx[k] : b.mx[k];
+		n.area = areaOf(n.mn, n.mx);
+	}
+	void refitUp(int32_t i)
+	{
+		while (i >= 0)
+		{
+			refitOne(i);
+			i = N[i].parent;
+		}
+	}
+	double cost() const
+	{
+		double s = 0;
+		for (uint32_t i = 0; i < nInterior; i++) s += N[i].area;
+		return s / N[root].area;
+	}
+	static float unionArea(const ONode& a, const ONode& b)
+	{
+		float mn[3], mx[3];
+		for (int k = 0; k < 3; k++) mn[k] = a.mn[k] < b.mn[k] ? a.mn[k] : b.mn[k], mx[k] = a.mx[k] > b.mx[k] ? a.mx[k] : b.mx[k];
+		return areaOf(mn, mx);
+	}
+	struct QE
+	{
+		float ci;
+		int32_t node;
+		bool operator<(const QE& o) const { return ci > o.ci; }
+	};
+	std::vector<QE> heap;
+	int32_t findBest(int32_t x)
+	{
+		const ONode& X = N[x];
+		float best = FLT_MAX;
+		int32_t bestNode = root;
+		heap.clear();
+		heap.push_back({0.0f, root});
+		while (!heap.empty())
+		{
+			std::pop_heap(heap.begin(), heap.end());
+			QE e = heap.back();
+			heap.pop_back();
+			if (e.ci + X.area >= best) break;
+			const ONode& Y = N[e.node];
+			float direct = unionArea(Y, X);
+			float total = e.ci + direct;
+			if (total < best) best = total, bestNode = e.node;
+			if (Y.c[0] >= 0)
+			{
+				float ci = e.ci + (direct - Y.area);
+				if (ci + X.area < best)
+				{
+					heap.push_back({ci, Y.c[0]});
+					std::push_heap(heap.begin(), heap.end());
+					heap.push_back({ci, Y.c[1]});
+					std::push_heap(heap.begin(), heap.end());
+				}
+			}
+		}
+		return bestNode;
+	}
+	void insertAt(int32_t x, int32_t y, int32_t fresh)
+	{
+		// `fresh` becomes the parent of (y, x) where y was
+		int32_t p = N[y].parent;
+		ONode& F = N[fresh];
+		F.parent = p;
+		F.c[0] = y, F.c[1] = x;
+		N[y].parent = fresh, N[x].parent = fresh;
+		if (p < 0) root = fresh;
+		else N[p].c[N[p].c[0] == y ? 0 : 1] = fresh;
+		refitUp(fresh);
+	}
+	bool process(int32_t n)
+	{
+		if (n == root) return false;
+		int32_t p = N[n].parent;
+		if (p < 0) return false;
+		int32_t s = N[p].c[N[p].c[0] == n ? 1 : 0];
+		int32_t g = N[p].parent;
+		int32_t l = N[n].c[0], r = N[n].c[1];
+		// unlink p and n: s takes p's place
+		N[s].parent = g;
+		if (g < 0) root = s;
+		else
+		{
+			N[g].c[N[g].c[0] == p ? 0 : 1] = s;
+			refitUp(g);
+		}
+		if (N[l].area < N[r].area) std::swap(l, r);
+		insertAt(l, findBest(l), n);
+		insertAt(r, findBest(r), p);
+		return true;
+	}
+	// One pass over the `fraction` of the interior nodes with the largest boxes.  The re-insertions are greedy, not
+	// monotone: a pass that ends with a larger summed area than it started with is undone (returns false).
+	bool pass(float fraction)
+	{
+		const std::vector<ONode> before = N;
+		const int32_t rootBefore = root;
+		const double costBefore = cost();
+		std::vector<std::pair<float, int32_t>> order;
+		order.reserve(nInterior);
+		for (uint32_t i = 0; i < nInterior; i++) order.push_back({-N[i].area, (int32_t)i});
+		std::sort(order.begin(), order.end());
+		size_t k = (size_t)(order.size() * fraction);
+		for (size_t i = 0; i < k; i++) process(order[i].second);
+		if (cost() <= costBefore) return true;
+		N = before, root = rootBefore;
+		return false;
+	}
+	// pre-order re-encoding
+	uint32_t store(FastTree& T)
+	{
+		T.nodes.assign((size_t)nInterior * 4, F4{0, 0, 0, 0});
+		uint32_t next = 0, maxDepth = 0;
+		if (N[root].c[0] < 0)
+		{
+			T.root = N[root].leafRef;
+			return 0;
+		}
+		T.root = 0;
+		// slots in pre-order (node, left subtree, right subtree), like FastBuilder's layout
+		std::vector<int32_t> slotOf(N.size(), -1);
+		{
+			std::vector<int32_t> s2;
+			s2.push_back(root);
+			next = 0;
+			while (!s2.empty())
+			{
+				int32_t n = s2.back();
+				s2.pop_back();
+				slotOf[n] = (int32_t)next++;
+				if (N[N[n].c[1]].c[0] >= 0) s2.push_back(N[n].c[1]);
+				if (N[N[n].c[0]].c[0] >= 0) s2.push_back(N[n].c[0]);
+			}
+		}
+		std::vector<std::pair<int32_t, uint32_t>> s3;
+		s3.push_back({root, 0u});
+		while (!s3.empty())
+		{
+			auto [n, d] = s3.back();
+			s3.pop_back();
+			if (d > maxDepth) maxDepth = d;
+			const ONode &a = N[N[n].c[0]], &b = N[N[n].c[1]];
+			int32_t r0 = a.c[0] < 0 ? a.leafRef : slotOf[N[n].c[0]], r1 = b.c[0] < 0 ? b.leafRef : slotOf[N[n].c[1]];
+			F4* nd = &T.nodes[(size_t)slotOf[n] * 4];
+			nd[0] = {a.mn[0], a.mx[0], a.mn[1], a.mx[1]};
+			nd[1] = {b.mn[0], b.mx[0], b.mn[1], b.mx[1]};
+			nd[2] = {a.mn[2], a.mx[2], b.mn[2], b.mx[2]};
+			nd[3] = {bitsToFloat((uint32_t)r0), bitsToFloat((uint32_t)r1), 0.0f, 0.0f};
+			if (a.c[0] >= 0) s3.push_back({N[n].c[0], d + 1});
+			else if (d + 1 > maxDepth) maxDepth = d + 1;
+			if (b.c[0] >= 0) s3.push_back({N[n].c[1], d + 1});
+			else if (d + 1 > maxDepth) maxDepth = d + 1;
+		}
+		T.maxDepth = maxDepth;
+		return maxDepth;
+	}
+};
+
+// ---------------------------------------------------------------------------------------
 // WIDE tree: the FAST binary tree collapsed to 4 children per node (the child with the largest
 // surface area is replaced by its own two children until there are four).  Same boxes, same
 // leaves; half the dependent node fetches per ray.  128-byte nodes, structure of arrays:

@@ -1266,8 +1266,41 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 	{
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
+		clk.lap("binned-SAH tree");
+		// RTB_TREE_OPT=<passes>: insertion-based re-optimisation of the tree (rtb_accel::FastOptimizer); kept only if the
+		// result still fits the traversal stacks
+		int passes = 0;
+		float fraction = 1.0f;
+		if (const char* e = getenv("RTB_TREE_OPT"))
+		{
+			passes = atoi(e);
+			if (const char* c = strchr(e, ':')) fraction = (float)atof(c + 1);
+		}
+		if (passes > 0 && fast.root >= 0 && fast.nodes.size() >= 8)
+		{
+			rtb_accel::FastOptimizer opt;
+			opt.load(fast);
+			for (int k = 0; k < passes; k++) opt.pass(fraction);
+			rtb_accel::FastTree better;
+			if (opt.store(better) + 2 <= RTB_STACK) fast.nodes.swap(better.nodes), fast.root = better.root, fast.maxDepth = better.maxDepth;
+			clk.lap("tree optimisation (RTB_TREE_OPT)");
+		}
+		// RTB_TREE_ORDER=1: child 0 = the child with the larger surface area (what any-hit rays enter first)
+		const int order = getenv("RTB_TREE_ORDER") ? atoi(getenv("RTB_TREE_ORDER")) : 0; // 1 larger child first, 2 smaller child first
+		if (order == 1 || order == 2)
+			for (size_t i = 0; i + 3 < fast.nodes.size(); i += 4)
+			{
+				rtb_accel::F4* nd = &fast.nodes[i];
+				auto area = [](float x0, float x1, float y0, float y1, float z0, float z1) { return (x1 - x0) * (y1 - y0) + (y1 - y0) * (z1 - z0) + (z1 - z0) * (x1 - x0); };
+				const float a0 = area(nd[0].x, nd[0].y, nd[0].z, nd[0].w, nd[2].x, nd[2].y), a1 = area(nd[1].x, nd[1].y, nd[1].z, nd[1].w, nd[2].z, nd[2].w);
+				if (order == 1 ? (a1 > a0) : (a1 < a0))
+				{
+					std::swap(nd[0], nd[1]);
+					std::swap(nd[2].x, nd[2].z), std::swap(nd[2].y, nd[2].w);
+					std::swap(nd[3].x, nd[3].y);
+				}
+			}
 	}
-	clk.lap(ps.gpuBuild ? "(tree built on the device)" : "binned-SAH tree");
 	// stack need: one pending sibling per level.  (The WIDE / CW / Q16 re-encodings of this tree are built on first use,
 	// ensureTraversal: the upload of a 16 M-triangle scene should not pay for trees nobody selected.)
 	if (!ps.gpuBuild && fast.maxDepth + 2 > RTB_STACK) return fail(ctx, RTB_ERR_STATE, "accelerated tree too deep (%u levels)", fast.maxDepth);

@@ -400,6 +400,10 @@ RTB_DEV void lanePop(LaneTrav<ANYHIT>& t, const STK& stk)
 }
 
 // One interior step of the binary FAST tree: both child boxes, near child next, far child pushed.
+// any-hit rays at a node whose two children are both hit: 0 = stored order (child 0 first), 1 = nearer child first
+#ifndef RTB_ANYHIT_NEAR_FIRST
+#define RTB_ANYHIT_NEAR_FIRST 0
+#endif
 template <bool ANYHIT, class STK>
 RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t& nBox)
 {
@@ -419,8 +423,8 @@ RTB_DEV void stepFast(const DevScene& S, LaneTrav<ANYHIT>& t, STK& stk, uint32_t
 	int32_t c0 = __float_as_int(ch.x), c1 = __float_as_int(ch.y);
 	if (h0 && h1)
 	{
-		bool swap = !ANYHIT && (t1 < t0);
-		if (ANYHIT) stk.putNode(t.sp, c1);
+		bool swap = (!ANYHIT || RTB_ANYHIT_NEAR_FIRST) && (t1 < t0);
+		if (ANYHIT) stk.putNode(t.sp, swap ? c0 : c1);
 		else stk.put(t.sp, swap ? c0 : c1, swap ? t0 : t1);
 		t.sp++;
 		t.cur = swap ? c1 : c0;

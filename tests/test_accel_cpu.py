@@ -115,3 +115,26 @@ def test_skip_links_equal_the_subtree_ends_and_malformed_trees_are_rejected(chec
             bad["a"][i], bad["b"][i] = -1, 1          # an interior node turned into a leaf: its old subtree has no parent
         assert checker.accel_skip_links(bad.ctypes.data, len(bad), s.n_tris, np.zeros(len(bad), np.uint32).ctypes.data) < 0, what
         assert b"pre-order" in checker.accel_check_message()
+
+
+def test_reoptimised_trees_keep_every_property(checker):
+    """RTB_TREE_OPT (rtb_accel::FastOptimizer, insertion-based re-optimisation): the optimised tree passes the same checks
+    as the builder's — every reference leaf once, child boxes the exact unions, WIDE / CW / Q16 re-encodings conservative —
+    and its summed surface area is not larger."""
+    from raytracingrenderer_b200 import host_api
+    scenes = [synthetic_scene(seed=11, n_tris=700), host_api.build_soup(1 << 13, 64, 36)[0]]
+    d = os.path.join(ROOT, "scenes", "_staged", "coffee")
+    if os.path.isfile(os.path.join(d, "scene.json")):
+        scenes.append(host_api.load_scene(d))
+    try:
+        for passes, fraction in ((1, 1.0), (3, 0.05)):
+            checker.accel_set_optimise.argtypes = [C.c_int, C.c_double]
+            checker.accel_set_optimise(passes, fraction)
+            for s in scenes:
+                st = run(checker, s)
+                sah = np.zeros(2)
+                checker.accel_get_sah(C.c_void_p(sah.ctypes.data))
+                assert sah[0] > 0 and sah[1] <= sah[0] * 1.0001, sah
+                assert st["fast_depth"] + 2 <= 96
+    finally:
+        checker.accel_set_optimise(0, 1.0)

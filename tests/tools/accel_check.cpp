@@ -36,6 +36,12 @@ static int failf(int code, const char* fmt, double a = 0, double b = 0, double c
 	return code;
 }
 
+static int g_optPasses = 0;
+static double g_optFraction = 1.0, g_sah[2];
+// passes > 0: accel_check optimises the FAST tree first (rtb_accel::FastOptimizer); sah = summed interior surface area
+// over the root's, before and after
+extern "C" void accel_set_optimise(int passes, double fraction) { g_optPasses = passes, g_optFraction = fraction; }
+extern "C" void accel_get_sah(double* out) { out[0] = g_sah[0], out[1] = g_sah[1]; }
 extern "C" const char* accel_check_message() { return g_msg.c_str(); }
 
 // stats: [0] fast nodes [1] fast depth [2] wide nodes [3] cw nodes [4] cw depth [5] cw leaves [6] q16 leaves
@@ -51,6 +57,19 @@ extern "C" int accel_check(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris
 	{
 		FastBuilder fb(leaves);
 		fb.build(fast);
+	}
+	g_sah[0] = g_sah[1] = 0;
+	if (g_optPasses > 0 && fast.root >= 0 && fast.nodes.size() >= 8)
+	{
+		// the checks below then run on the re-optimised tree (RTB_TREE_OPT): same leaves, exact unions, legal depth
+		FastOptimizer opt;
+		opt.load(fast);
+		g_sah[0] = opt.cost();
+		for (int k = 0; k < g_optPasses; k++) opt.pass((float)g_optFraction);
+		g_sah[1] = opt.cost();
+		FastTree better;
+		opt.store(better);
+		fast = better;
 	}
 	std::map<uint32_t, const RefLeaf*> byKey; // (start << 2 | count) -> leaf
 	for (const RefLeaf& L : leaves) byKey[(L.start << 2) | L.count] = &L;
