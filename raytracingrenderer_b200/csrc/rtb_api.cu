@@ -1267,15 +1267,23 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 		rtb_accel::FastBuilder fb(leaves);
 		fb.build(fast);
 		clk.lap("binned-SAH tree");
-		// RTB_TREE_OPT=<passes>: insertion-based re-optimisation of the tree (rtb_accel::FastOptimizer); kept only if the
-		// result still fits the traversal stacks
-		int passes = 0;
-		float fraction = 1.0f;
+		// Insertion-based re-optimisation of the tree (rtb_accel::FastOptimizer) + a child order for any-hit rays
+		// (rtb_accel::orderForAnyHit).  Default: scenes of 32 K ... 400 K leaves get two passes over their 5 % largest
+		// nodes and the p / C order (coffee +5 %, bathroom +15 % Msamples/s for 0.05 / 0.2 s of upload); smaller scenes
+		// measured -1 % and uniform soups +1 % for seconds of build, so they keep the builder's tree
+		// (profiles/r02_tree_opt.txt).  RTB_TREE_OPT=<passes>[:fraction] and RTB_TREE_ORDER=0..4 override; the optimised
+		// tree is kept only if it still fits the traversal stacks.
+		const size_t nLeaves = leaves.size();
+		int passes = (nLeaves >= 32768 && nLeaves <= 400000) ? 2 : 0;
+		float fraction = 0.05f;
 		if (const char* e = getenv("RTB_TREE_OPT"))
 		{
 			passes = atoi(e);
+			fraction = 1.0f;
 			if (const char* c = strchr(e, ':')) fraction = (float)atof(c + 1);
 		}
+		int order = passes > 0 ? 3 : 0;
+		if (const char* e = getenv("RTB_TREE_ORDER")) order = atoi(e);
 		if (passes > 0 && fast.root >= 0 && fast.nodes.size() >= 8)
 		{
 			rtb_accel::FastOptimizer opt;
@@ -1283,23 +1291,13 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 			for (int k = 0; k < passes; k++) opt.pass(fraction);
 			rtb_accel::FastTree better;
 			if (opt.store(better) + 2 <= RTB_STACK) fast.nodes.swap(better.nodes), fast.root = better.root, fast.maxDepth = better.maxDepth;
-			clk.lap("tree optimisation (RTB_TREE_OPT)");
+			clk.lap("tree optimisation");
 		}
-		// RTB_TREE_ORDER=1: child 0 = the child with the larger surface area (what any-hit rays enter first)
-		const int order = getenv("RTB_TREE_ORDER") ? atoi(getenv("RTB_TREE_ORDER")) : 0; // 1 larger child first, 2 smaller child first
-		if (order == 1 || order == 2)
-			for (size_t i = 0; i + 3 < fast.nodes.size(); i += 4)
-			{
-				rtb_accel::F4* nd = &fast.nodes[i];
-				auto area = [](float x0, float x1, float y0, float y1, float z0, float z1) { return (x1 - x0) * (y1 - y0) + (y1 - y0) * (z1 - z0) + (z1 - z0) * (x1 - x0); };
-				const float a0 = area(nd[0].x, nd[0].y, nd[0].z, nd[0].w, nd[2].x, nd[2].y), a1 = area(nd[1].x, nd[1].y, nd[1].z, nd[1].w, nd[2].z, nd[2].w);
-				if (order == 1 ? (a1 > a0) : (a1 < a0))
-				{
-					std::swap(nd[0], nd[1]);
-					std::swap(nd[2].x, nd[2].z), std::swap(nd[2].y, nd[2].w);
-					std::swap(nd[3].x, nd[3].y);
-				}
-			}
+		if (order >= 1 && order <= 4 && fast.root >= 0)
+		{
+			rtb_accel::orderForAnyHit(fast, sc->tri_isect, order);
+			clk.lap("child order for any-hit rays");
+		}
 	}
 	// stack need: one pending sibling per level.  (The WIDE / CW / Q16 re-encodings of this tree are built on first use,
 	// ensureTraversal: the upload of a 16 M-triangle scene should not pay for trees nobody selected.)
