@@ -531,14 +531,15 @@ static void wfProbeRead(rtb_ctx* ctx, WfRun& R)
 {
 	ctx->wfHostSyncs++;
 	{
-		// Which any-hit kernel suits this scene: long shadow rays (bathroom: 65 box tests per ray, the soups: 130+) gain
-		// 6 ... 12 % from the persistent kernel, short ones (coffee: 38, the small scenes: 9 ... 14) lose 5 ... 10 %
-		// (profiles/r02_persistent_shadow.txt).  Decided from the work counters the probe brings along anyway; the film
-		// does not depend on the choice.
+		// Which any-hit kernel suits this scene: long shadow rays (bathroom: 51 box tests per ray with the optimised
+		// tree, 65 without; the soups: 130+) gain 6 ... 12 % from the persistent kernel, short ones (coffee: 33 ... 38, the
+		// small scenes: 9 ... 14) lose 5 ... 12 % (profiles/r02_persistent_shadow.txt, r02_tree_opt.txt).  The threshold
+		// sits midway between the two measured groups.  Decided from the work counters the probe brings along anyway; the
+		// film does not depend on the choice.
 		unsigned long long rays = 0, boxes = 0;
 		for (int r = 0; r < RTB_COUNTER_STRIPES; r++)
 			rays += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 2], boxes += ctx->hostProbe[1 + RTB_MAX_POOLS + r * 8 + 5];
-		if (rays > 100000ull) ctx->shadowPersistentAuto = boxes > 50ull * rays;
+		if (rays > 100000ull) ctx->shadowPersistentAuto = boxes > 42ull * rays;
 	}
 	unsigned long long claimed = ctx->hostProbe[0];
 	uint32_t alive = 0;
