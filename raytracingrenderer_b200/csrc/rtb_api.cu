@@ -1335,16 +1335,15 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	// EXACT tree: the reference nodes go up as they are; the device swaps the child words for (skip link, leaf code)
 	{
 		const rtb_ref_node* dn = nullptr;
-		const uint32_t* dskip = nullptr;
 		if ((rc = uploadArray(ctx, sc->ref_nodes, sc->n_ref_nodes, &dn))) return rc;
 		if (sc->n_ref_nodes)
 		{
-			CK(cudaMalloc((void**)&dskip, (size_t)sc->n_ref_nodes * sizeof(uint32_t)));
-			CK(cudaMemcpyAsync((void*)dskip, ps.skip.data(), (size_t)sc->n_ref_nodes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			Scratch tmp; // the skip links are only needed by the re-encoding kernel; freed on every path out
+			uint32_t* dskip = nullptr;
+			CK(tmp.in(ps.skip.data(), (size_t)sc->n_ref_nodes, &dskip, ctx->stream));
 			k_exact_nodes<<<(sc->n_ref_nodes + 255) / 256, 256, 0, ctx->stream>>>((float4*)dn, dskip, sc->n_ref_nodes);
 			CK(cudaGetLastError());
 			CK(cudaStreamSynchronize(ctx->stream));
-			CK(cudaFree((void*)dskip));
 		}
 		dx = (const rtb_accel::F4*)dn;
 	}
@@ -1414,25 +1413,15 @@ static int uploadPrepared(rtb_ctx* ctx, const PreparedScene& ps)
 	if (sc->n_texels)
 	{
 		// texels: 12-byte RGB from the caller, 16-byte records on the device
+		Scratch tmp;
 		float* raw = nullptr;
 		void* padded = nullptr;
-		CK(cudaMalloc((void**)&raw, (size_t)sc->n_texels * 3 * sizeof(float)));
-		cudaError_t e = cudaMalloc(&padded, (size_t)sc->n_texels * sizeof(float4));
-		if (e != cudaSuccess)
-		{
-			cudaFree(raw);
-			CK(e);
-		}
+		CK(tmp.in(sc->texels, (size_t)sc->n_texels * 3, &raw, ctx->stream));
+		CK(cudaMalloc(&padded, (size_t)sc->n_texels * sizeof(float4)));
 		ctx->sceneAllocs.push_back(padded);
-		e = cudaMemcpyAsync(raw, sc->texels, (size_t)sc->n_texels * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-		if (e == cudaSuccess)
-		{
-			k_pad_texels<<<(unsigned)(((size_t)sc->n_texels + 255) / 256), 256, 0, ctx->stream>>>(raw, (float4*)padded, (size_t)sc->n_texels);
-			e = cudaGetLastError();
-		}
-		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-		cudaFree(raw);
-		CK(e);
+		k_pad_texels<<<(unsigned)(((size_t)sc->n_texels + 255) / 256), 256, 0, ctx->stream>>>(raw, (float4*)padded, (size_t)sc->n_texels);
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(ctx->stream));
 		S.texels = (const float4*)padded;
 	}
 	if ((rc = uploadArray(ctx, sc->lights, sc->n_lights, &S.lights))) return rc;
