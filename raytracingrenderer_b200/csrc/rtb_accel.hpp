@@ -694,7 +694,9 @@ public:
 		order.reserve(nInterior);
 		for (uint32_t i = 0; i < nInterior; i++) order.push_back({-N[i].area, (int32_t)i});
 		std::sort(order.begin(), order.end());
-		size_t k = (size_t)(order.size() * fraction);
+		if (!(fraction > 0.0f)) return true;
+		size_t k = fraction >= 1.0f ? order.size() : (size_t)((double)order.size() * fraction);
+		if (k > order.size()) k = order.size();
 		for (size_t i = 0; i < k; i++) process(order[i].second);
 		if (cost() <= costBefore) return true;
 		N = before, root = rootBefore;

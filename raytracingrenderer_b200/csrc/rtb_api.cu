@@ -1282,6 +1282,7 @@ static int prepareScene(rtb_ctx* ctx, const rtb_scene_desc* sc, PreparedScene& p
 			passes = atoi(e);
 			fraction = 1.0f;
 			if (const char* c = strchr(e, ':')) fraction = (float)atof(c + 1);
+			if (passes > 64) passes = 64;
 		}
 		int order = passes > 0 ? 3 : 0;
 		if (const char* e = getenv("RTB_TREE_ORDER")) order = atoi(e);

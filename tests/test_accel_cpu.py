@@ -126,15 +126,21 @@ def test_reoptimised_trees_keep_every_property(checker):
     d = os.path.join(ROOT, "scenes", "_staged", "coffee")
     if os.path.isfile(os.path.join(d, "scene.json")):
         scenes.append(host_api.load_scene(d))
+    checker.accel_set_order.argtypes = [C.c_int, C.c_void_p]
     try:
-        for passes, fraction in ((1, 1.0), (3, 0.05)):
+        for passes, fraction, order in ((1, 1.0, 0), (3, 0.05, 3), (0, 1.0, 3), (2, 7.5, 2), (1, -1.0, 4)):
             checker.accel_set_optimise.argtypes = [C.c_int, C.c_double]
             checker.accel_set_optimise(passes, fraction)
             for s in scenes:
+                tris = np.ascontiguousarray(s.tri_isect)
+                checker.accel_set_order(order, tris.ctypes.data)     # the any-hit child order (RTB_TREE_ORDER) on top
                 st = run(checker, s)
+                if passes == 0:
+                    continue
                 sah = np.zeros(2)
                 checker.accel_get_sah(C.c_void_p(sah.ctypes.data))
                 assert sah[0] > 0 and sah[1] <= sah[0] * 1.0001, sah
                 assert st["fast_depth"] + 2 <= 96
     finally:
         checker.accel_set_optimise(0, 1.0)
+        checker.accel_set_order(0, None)

@@ -41,6 +41,9 @@ static double g_optFraction = 1.0, g_sah[2];
 // passes > 0: accel_check optimises the FAST tree first (rtb_accel::FastOptimizer); sah = summed interior surface area
 // over the root's, before and after
 extern "C" void accel_set_optimise(int passes, double fraction) { g_optPasses = passes, g_optFraction = fraction; }
+static int g_orderMode = 0;
+static const rtb_tri_isect* g_orderTris = nullptr;
+extern "C" void accel_set_order(int mode, const rtb_tri_isect* tris) { g_orderMode = mode, g_orderTris = tris; }
 extern "C" void accel_get_sah(double* out) { out[0] = g_sah[0], out[1] = g_sah[1]; }
 extern "C" const char* accel_check_message() { return g_msg.c_str(); }
 
@@ -71,6 +74,7 @@ extern "C" int accel_check(const rtb_ref_node* nodes, uint32_t n, uint32_t nTris
 		opt.store(better);
 		fast = better;
 	}
+	if (g_orderMode > 0) orderForAnyHit(fast, g_orderTris, g_orderMode); // swaps children only: every check below must still hold
 	std::map<uint32_t, const RefLeaf*> byKey; // (start << 2 | count) -> leaf
 	for (const RefLeaf& L : leaves) byKey[(L.start << 2) | L.count] = &L;
 	if (byKey.size() != leaves.size()) return failf(-2, "duplicate reference leaves");
