@@ -501,6 +501,10 @@ RTB_DEV void connectToCamera(const DevScene& S, const rtb_params& P, const rtb_c
 	if (px >= 0 && px < (int)S.cam.width && py >= 0 && py < (int)S.cam.height) filmAdd(accum, (uint32_t)py * (uint32_t)S.cam.width + (uint32_t)px, col);
 }
 
+// One flat loop per thread: an iteration starts a new light path in the lanes that have none and advances every live
+// path by one vertex, so a lane whose path ended does not wait for the longest path of its warp before it takes the next
+// one (round 1's path-per-iteration loop ran at 5 of 32 lanes per instruction).  Paths are keyed (path, pass) in the RNG
+// and the film is an integer sum: the result does not depend on which lane traces which path, or when.
 template <int TRAV>
 __global__ void __launch_bounds__(128) k_light_trace(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                      const __grid_constant__ rtb_camera_ext ce)
@@ -508,53 +512,67 @@ __global__ void __launch_bounds__(128) k_light_trace(const __grid_constant__ Dev
 	const rtb_params& P = A.P;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0};
 	const unsigned long long perPass = (unsigned long long)A.width * A.height, total = perPass * A.spp_count;
-	for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (unsigned long long)gridDim.x * blockDim.x)
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	bool live = false;
+	uint32_t pass = 0, path = 0, k = 0;
+	RayD r;
+	V3 T = mk(1.0f, 1.0f, 1.0f), Le = mk(0.0f, 0.0f, 0.0f);
+	while (live || j < total)
 	{
-		uint32_t pass = A.spp_begin + (uint32_t)(j / perPass), path = (uint32_t)(j % perPass);
-		tl.samples++;
-		if (S.n_lights == 0) continue;
-		float4 u0 = rngBlock(P.seed, path, pass, 0u, 1u), u1 = rngBlock(P.seed, path, pass, 1u, 1u);
-		float nl = (float)S.n_lights;
-		float pmf = 1.0f / nl;
-		int li = (int)(nl * u0.x);
-		if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
-		rtb_light L = S.lights[li];
-		if (L.type != RTB_LIGHT_AREA) continue;
-		V3 p = trianglePoint(S, L.triangle, u0.y, u0.z);
-		float pdfPos = 1.0f / L.area;
-		V3 wl = cosineSampleHemisphere(u0.w, u1.x);
-		float pdfDir = (wl.z >= 0.0f) ? (wl.z * RTB_INV_PI_F) : 0.0f;
-		V3 nL = triangleGNormal(S, L.triangle);
-		V3 fu, fv, fw;
-		frameFromVector(nL, fu, fv, fw);
-		V3 wi = ((fu * wl.x) + (fv * wl.y)) + (fw * wl.z);
-		float cosTheta = dot(nL, wi);
-		V3 Le = (dot(-wi, nL) < 0.0f) ? mk(L.emission) : mk(0.0f, 0.0f, 0.0f); // AreaLight::evaluate(-wi), Lights.h:41-48
-		Le = (Le * cosTheta) / (pmf * pdfDir * pdfPos);
-		connectToCamera<TRAV>(S, P, ce, A.accum, p, nL, Le, tl);
-		RayD r = mkRay(p, wi);
-		V3 T = mk(1.0f, 1.0f, 1.0f);
-		for (uint32_t k = 0; k < 100000u; k++)
+		if (!live)
 		{
-			HitD h;
-			closestHit<TRAV>(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
-			tl.closest++;
-			if (h.id == RTB_MISS_ID) break;
-			ShadeD sd;
-			calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), r, sd);
-			rtb_material m = S.mats[sd.mat];
-			if (m.flags & (RTB_MAT_LIGHT | RTB_MAT_SPECULAR)) break;
-			connectToCamera<TRAV>(S, P, ce, A.accum, sd.x, sd.sN, (T * bsdfEvaluate(S, m, sd, mk(0.0f, 1.0f, 0.0f))) * Le, tl);
-			float4 uk = rngBlock(P.seed, path, pass, 2u + k, 1u);
-			float rr = selMin(lum(T), P.rr_cap);
-			if (!(uk.x < rr)) break;
-			T = T / rr;
-			V3 f;
-			float pdf;
-			V3 wi2 = bsdfSample(S, m, sd, uk.y, uk.z, uk.w, f, pdf);
-			T = ((T * f) * fabsf(dot(wi2, sd.sN))) / pdf;
-			r = mkRay(sd.x + (wi2 * P.epsilon), wi2);
+			// lightTrace_init (Renderer.h:262-288)
+			pass = A.spp_begin + (uint32_t)(j / perPass), path = (uint32_t)(j % perPass);
+			j += stride;
+			tl.samples++;
+			if (S.n_lights == 0) continue;
+			float4 u0 = rngBlock(P.seed, path, pass, 0u, 1u), u1 = rngBlock(P.seed, path, pass, 1u, 1u);
+			float nl = (float)S.n_lights;
+			float pmf = 1.0f / nl;
+			int li = (int)(nl * u0.x);
+			if (li > (int)S.n_lights - 1) li = (int)S.n_lights - 1;
+			rtb_light L = S.lights[li];
+			if (L.type != RTB_LIGHT_AREA) continue;
+			V3 p = trianglePoint(S, L.triangle, u0.y, u0.z);
+			float pdfPos = 1.0f / L.area;
+			V3 wl = cosineSampleHemisphere(u0.w, u1.x);
+			float pdfDir = (wl.z >= 0.0f) ? (wl.z * RTB_INV_PI_F) : 0.0f;
+			V3 nL = triangleGNormal(S, L.triangle);
+			V3 fu, fv, fw;
+			frameFromVector(nL, fu, fv, fw);
+			V3 wi = ((fu * wl.x) + (fv * wl.y)) + (fw * wl.z);
+			float cosTheta = dot(nL, wi);
+			Le = (dot(-wi, nL) < 0.0f) ? mk(L.emission) : mk(0.0f, 0.0f, 0.0f); // AreaLight::evaluate(-wi), Lights.h:41-48
+			Le = (Le * cosTheta) / (pmf * pdfDir * pdfPos);
+			connectToCamera<TRAV>(S, P, ce, A.accum, p, nL, Le, tl);
+			r = mkRay(p, wi);
+			T = mk(1.0f, 1.0f, 1.0f);
+			k = 0;
+			live = true;
 		}
+		// one vertex of lightTracePath (Renderer.h:290-326)
+		live = false;
+		HitD h;
+		closestHit<TRAV>(S, r, P.epsilon, P.cull_rel, h, tl.box, tl.tri);
+		tl.closest++;
+		if (h.id == RTB_MISS_ID) continue;
+		ShadeD sd;
+		calcShading(S, h.id, h.t, h.alpha, h.beta, 1.0f - (h.alpha + h.beta), r, sd);
+		rtb_material m = S.mats[sd.mat];
+		if (m.flags & (RTB_MAT_LIGHT | RTB_MAT_SPECULAR)) continue;
+		connectToCamera<TRAV>(S, P, ce, A.accum, sd.x, sd.sN, (T * bsdfEvaluate(S, m, sd, mk(0.0f, 1.0f, 0.0f))) * Le, tl);
+		float4 uk = rngBlock(P.seed, path, pass, 2u + k, 1u);
+		float rr = selMin(lum(T), P.rr_cap);
+		if (!(uk.x < rr)) continue;
+		T = T / rr;
+		V3 f;
+		float pdf;
+		V3 wi2 = bsdfSample(S, m, sd, uk.y, uk.z, uk.w, f, pdf);
+		T = ((T * f) * fabsf(dot(wi2, sd.sN))) / pdf;
+		r = mkRay(sd.x + (wi2 * P.epsilon), wi2);
+		k++;
+		live = k < 100000u;
 	}
 	flushTally(tl, A.counters);
 }
