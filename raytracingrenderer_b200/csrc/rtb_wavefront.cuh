@@ -959,7 +959,10 @@ __global__ void __launch_bounds__(128) k_wf_extend_simple(const __grid_constant_
 // measured slower on EVERY scene, twice — profiles/r01_v4_persistent_traversal.txt and
 // profiles/r01_shadow_stage.txt: materialball -12 %, coffee -22 %, cornell-box -17 %, bathroom -2 %,
 // soups -6 %: any-hit rays end early, so the refill bookkeeping outweighs the regained lanes, and a
-// kernel that owns every resident block cannot share the SMs with the other streams.)
+// kernel that owns every resident block cannot share the SMs with the other streams.  Round 2 tried the lightest form -
+// this kernel with a per-lane grid-stride refill at leaf boundaries, no votes, chunks or shared memory: cornell-box -10 %,
+// materialball -5 %, coffee -18 %, bathroom / soup 0.  The refill's scattered 48-byte reads and set-up run at a few lanes
+// each time and cost more than the lanes they free.)
 template <int TRAV>
 __global__ void __launch_bounds__(128) k_wf_shadow(const __grid_constant__ DevScene S, const __grid_constant__ WfArgs A, uint32_t iter)
 {
