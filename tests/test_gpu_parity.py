@@ -56,6 +56,25 @@ def test_errors_are_reported_not_swallowed(rtb):
     with pytest.raises(rtb.RtbError) as e:
         rt.init(s)
     assert "material" in str(e.value)
+    # a texture that runs past the texel pool, and a node array that is not one pre-order tree (the skip links of the
+    # EXACT traversal would walk out of it): errors at upload, not reads out of bounds on the device
+    s = synthetic_scene()
+    s.textures = s.textures.copy()
+    s.textures["width"][0] = 1 << 14
+    s.textures["height"][0] = 1 << 14
+    with pytest.raises(rtb.RtbError) as e:
+        rt.init(s)
+    assert "texel pool" in str(e.value)
+    s = synthetic_scene()
+    s.ref_nodes = s.ref_nodes.copy()
+    interior = np.flatnonzero(s.ref_nodes["a"] >= 0)
+    s.ref_nodes["b"][interior[len(interior) // 2]] = len(s.ref_nodes) + 5
+    with pytest.raises(rtb.RtbError) as e:
+        rt.init(s)
+    assert "pre-order" in str(e.value)
+    rt.init(synthetic_scene())                     # the context is still usable after the rejected uploads
+    rt.render(1, 0)
+    assert np.isfinite(rt.read_film()).all()
     rt.close()
 
 
