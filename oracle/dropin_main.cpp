@@ -23,8 +23,11 @@ int main(int argc, char** argv)
 	rt.init(scene, &canvas);
 	int spp = atoi(argv[2]);
 	rt.setPresentEveryFrame(false);
-	rt.render();            // one sample, like the reference's loop body
-	rt.render(spp - 1);     // the rest in one call
+	// the reference's loop body: one render() per sample (Main.cpp:114).  The drop-in collects them (here at most 3 at a
+	// time, so that 8 samples take two full batches and a partial one); the last two samples come in one call.
+	rt.setRenderBatch(3);
+	for (int i = 0; i + 2 < spp; i++) rt.render();
+	rt.render(spp > 2 ? 2 : spp);
 	printf("SPP: %d\n", rt.getSPP());
 	rt.saveHDR(argv[3]);
 	if (argc > 4)

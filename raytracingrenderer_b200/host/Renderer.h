@@ -94,6 +94,7 @@ public:
 	// Scene geometry / materials changed: flatten and upload again.
 	void upload()
 	{
+		flush();
 		rtb::FlatScene flat = rtb::flatten(*scene);
 		rtb_scene_desc d = flat.desc();
 		check(rtb_upload_scene(ctx, &d), "rtb_upload_scene");
@@ -101,6 +102,7 @@ public:
 	}
 	void clear()
 	{
+		pendingCount = 0; // samples nobody looked at are not traced
 		film->clear();
 		// the camera may have moved (RTCamera::updateCamera -> Camera::updateView)
 		rtb_camera now = currentCamera();
@@ -112,20 +114,37 @@ public:
 		check(rtb_clear(ctx), "rtb_clear");
 		filmOnHost = true;
 	}
+	// RTBase calls render() once per sample (Main.cpp:114).  A GPU render has a fixed cost — the pool fills and drains
+	// once per rtb_render call, ~1 ms (profiles/r02_fixed_cost.txt) — so consecutive samples are collected and traced
+	// in ONE rtb_render call: when somebody needs the film (present / save / getFilm / the other estimators), when the
+	// parameters or the scene change, or after renderBatch samples.  Sample s of a pixel is the same sample whichever call
+	// traces it (counter RNG keyed (pixel, sample); integer film sums), so the film is bit-identical to per-sample calls.
+	// With a canvas and presentEveryFrame (the interactive shape of Main.cpp) every render() still shows its frame.
 	void render() { render(1); }
 	void render(int n)
 	{
 		if (n <= 0) return;
-		uint32_t begin = (uint32_t)film->SPP;
+		if (pendingCount == 0) pendingBegin = (uint32_t)film->SPP;
 		for (int i = 0; i < n; i++) film->incrementSPP();
-		check(rtb_render(ctx, begin, (uint32_t)n), "rtb_render");
+		pendingCount += (uint32_t)n;
 		filmOnHost = false;
 		if (presentEveryFrame && canvas) presentFilmToCanvas();
+		else if (pendingCount >= renderBatch) flush();
 	}
+	// Trace the samples render() has collected so far (rtb_render returns without waiting for the GPU).
+	void flush()
+	{
+		if (pendingCount == 0) return;
+		uint32_t begin = pendingBegin, count = pendingCount;
+		pendingCount = 0;
+		check(rtb_render(ctx, begin, count), "rtb_render");
+	}
+	void setRenderBatch(unsigned int samples) { renderBatch = samples ? samples : 1u; }
 	// RTBase/Renderer.h:679-749.  Like the original it is meant to be called from render() in place of
 	// pathTracerTileBased() (:880), after film->incrementSPP(); renderAdaptive() does both.
 	void adaptiveRender()
 	{
+		flush();
 		check(rtb_render_adaptive(ctx, INIT_SAMPLES, MIN_SAMPLES, MAX_SAMPLES, tileSamples.data(), tileVariances.data()),
 		      "rtb_render_adaptive");
 		check(rtb_set_spp(ctx, (uint32_t)film->SPP), "rtb_set_spp");
@@ -138,6 +157,7 @@ public:
 	// RTBase/Renderer.h:220-231 (render()'s commented-out alternative at :883): one light-tracing pass.
 	void lightTracer()
 	{
+		flush();
 		uint32_t pass = film->SPP > 0 ? (uint32_t)film->SPP - 1u : 0u; // render() has incremented SPP already
 		check(rtb_render_light(ctx, pass, 1), "rtb_render_light");
 		check(rtb_set_spp(ctx, (uint32_t)film->SPP), "rtb_set_spp");
@@ -147,6 +167,7 @@ public:
 	// RTBase/Renderer.h:102-123 (render()'s commented-out alternative at :884): one instant-radiosity pass.
 	void instantRadiosity()
 	{
+		flush();
 		uint32_t pass = film->SPP > 0 ? (uint32_t)film->SPP - 1u : 0u;
 		check(rtb_render_ir(ctx, pass, 1, MAX_VPL), "rtb_render_ir");
 		check(rtb_set_spp(ctx, (uint32_t)film->SPP), "rtb_set_spp");
@@ -189,6 +210,7 @@ public:
 	void presentFilmToCanvas()
 	{
 		if (!canvas) return;
+		flush();
 		std::vector<uint8_t> rgb((size_t)film->width * film->height * 3);
 		check(rtb_tonemap(ctx, rgb.data(), 1.0f), "rtb_tonemap");
 		for (unsigned int y = 0; y < film->height; y++)
@@ -202,6 +224,7 @@ public:
 	void syncFilm()
 	{
 		if (filmOnHost) return;
+		flush();
 		uint32_t spp = 0;
 		check(rtb_read_film(ctx, (float*)film->film, &spp), "rtb_read_film"); // Colour = 3 packed floats
 		filmOnHost = true;
@@ -221,8 +244,16 @@ public:
 	DenoiseFn denoiseFn = NULL;
 	void* denoiseUser = NULL;
 	rtb_params& params() { return prm; }
-	void applyParams() { check(rtb_set_params(ctx, &prm), "rtb_set_params"); }
-	rtb_ctx* context() { return ctx; }
+	void applyParams()
+	{
+		flush(); // the collected samples belong to the old parameters
+		check(rtb_set_params(ctx, &prm), "rtb_set_params");
+	}
+	rtb_ctx* context()
+	{
+		flush(); // whoever talks to the C ABI directly sees every sample render() was asked for
+		return ctx;
+	}
 	~RayTracer()
 	{
 		if (ctx) rtb_destroy(ctx);
@@ -234,6 +265,8 @@ private:
 	rtb_camera camera;
 	bool presentEveryFrame = true;
 	bool filmOnHost = true;
+	uint32_t pendingBegin = 0, pendingCount = 0; // samples asked for by render() and not traced yet
+	uint32_t renderBatch = 256;                  // at most this many are collected (setRenderBatch)
 
 	rtb_camera currentCamera()
 	{
